@@ -1,0 +1,197 @@
+/*
+ * oadg.h -- C ABI of libOADG.so: the B200 (sm_100a) implementation of the OA-DG
+ * per-step hot path (OA-Mix transform + OA-Loss contrastive loss).
+ *
+ * The reference (WoojuLee24/OA-DG) is pure Python and has NO FFI of its own
+ * (setup.py:220 ext_modules=[]); what it binds for this path are third-party
+ * wheels.  Each entry point below therefore names the reference *call site*
+ * whose native arithmetic it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain C: raw pointers + sizes, no torch / C++ types in any signature;
+ *   - every pointer named *_dev is DEVICE memory owned by the caller, every
+ *     pointer named *_host is host memory owned by the caller; the library never
+ *     frees caller memory and keeps no global state besides lazily-set kernel
+ *     attributes;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all work is stream-ordered and asynchronous unless stated otherwise;
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = argument error (OADG_E_*);
+ *     nothing throws;
+ *   - re-entrant: may be called concurrently from several host threads on
+ *     different streams with disjoint buffers.
+ *   - images are u8, HWC, 3 channels, row pitch = 3*W bytes (tightly packed, the
+ *     layout of the reference's numpy frames, loading.py:18-48).
+ */
+#ifndef OADG_H_
+#define OADG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OADG_ABI_VERSION 1
+
+#define OADG_E_ARG      (-1)   /* null pointer / bad size                         */
+#define OADG_E_PLAN     (-2)   /* malformed plan blob                             */
+#define OADG_E_LIMIT    (-3)   /* exceeds a compiled limit (OADG_MAX_*)           */
+#define OADG_E_ROWS     (-4)   /* OA-Loss: fewer than 2*ori_size rows (the reference
+                                  raises RuntimeError at contrastive_loss.py:205) */
+
+#define OADG_MAX_WIDTH    8    /* mixture_width  (reference default 3)            */
+#define OADG_MAX_DEPTH    8    /* mixture_depth  (reference draws 1..3)           */
+#define OADG_MAX_REGIONS  3    /* multi-level boxes (1..2) + the outside region   */
+
+/* ---- op kinds: reference aug list, oa_mix.py:15-29 ------------------------ */
+enum {
+  OADG_OP_AUTOCONTRAST = 0,  /* augmix.py:64  PIL.ImageOps.autocontrast          */
+  OADG_OP_EQUALIZE     = 1,  /* augmix.py:68  PIL.ImageOps.equalize              */
+  OADG_OP_POSTERIZE    = 2,  /* augmix.py:72  ImageOps.posterize(bits = p0)      */
+  OADG_OP_SOLARIZE     = 3,  /* augmix.py:103 ImageOps.solarize(thr = p0)        */
+  OADG_OP_INVERT       = 4,  /* oa_mix.py:270-276 -warpAffine(+-1 px)  (tx=p0, ty=p1) */
+  OADG_OP_COLOR        = 5,  /* augmix.py:192 ImageEnhance.Color(factor)         */
+  OADG_OP_CONTRAST     = 6,  /* augmix.py:198 ImageEnhance.Contrast(factor)      */
+  OADG_OP_BRIGHTNESS   = 7,  /* augmix.py:204 ImageEnhance.Brightness(factor)    */
+  OADG_OP_SHARPNESS    = 8,  /* augmix.py:210 ImageEnhance.Sharpness(factor)     */
+  OADG_OP_BG_AFFINE    = 9,  /* bbox_augmentation.py:240-302 bg_only_{rotate,shear,translate} */
+  OADG_OP_BBO_AFFINE   = 10  /* bbox_augmentation.py:31-118 bboxes_only_{rotate,shear,translate} */
+};
+
+/* ---- plan records (host blob, copied verbatim to the device) --------------
+ * All records are plain-old-data with natural alignment; Python packs them as
+ * numpy structured arrays (oadg_b200/plan.py) and oadg_struct_sizes() lets the
+ * binding verify the layout at load time.                                      */
+
+typedef struct oadg_gt {        /* one gt box of one view: blurred-mask source (oa_mix.py:78-91) */
+  int32_t lo[4];                /* x1,y1,x2,y2 on the (H/sr, W/sr) canvas, python-slice-resolved */
+  int32_t blur;                 /* 0 => GaussianBlur skipped (sigma <= 0, oa_mix.py:89)          */
+  int32_t kx, ky;               /* gaussian kernel sizes: cvRound(sigma*8+1)|1                   */
+  int32_t view;                 /* owning view index                                             */
+  double  sigma_x, sigma_y;
+  int32_t supp[4];              /* conservative support rect of the mask [x0,y0,x1,y1) full res  */
+} oadg_gt_t;
+
+typedef struct oadg_op {        /* one OAMix.aug() draw (oa_mix.py:264-279)                      */
+  int32_t kind;                 /* OADG_OP_*                                                     */
+  int32_t p0, p1;               /* posterize bits / solarize threshold / invert tx,ty            */
+  float   factor;               /* enhance factor                                                */
+  double  minv[6];              /* BG_AFFINE: inverse (dst->src) 2x3, doubles, cv::warpAffine    */
+  int32_t bbo_first, bbo_count; /* BBO_AFFINE: slice of the bbo record array                     */
+  int32_t lut;                  /* slot in the LUT workspace (filled by the library), -1 if none */
+  int32_t scratch;              /* BBO scratch image slot (filled by the library), -1 if none    */
+} oadg_op_t;
+
+typedef struct oadg_bbo {       /* one per (bboxes-only op, valid gt box), bbox_augmentation.py:45-71 */
+  int32_t gt;                   /* global gt index (into the oadg_gt array)                      */
+  int32_t pad;
+  double  minv[6];              /* inverse affine of this box's random warp                      */
+} oadg_bbo_t;
+
+typedef struct oadg_target {    /* one object-aware mixing target (oa_mix.py:245-262,287-301)    */
+  int32_t kind;                 /* 0 = blurred gt mask (gt = global gt index), 1 = hard box      */
+  int32_t gt;
+  int32_t box[4];               /* hard box x1,y1,x2,y2 (python-slice-resolved)                  */
+  float   m_oa;                 /* np.float32(uniform(0,.5|1))  (oa_mix.py:296,298)              */
+  int32_t pad;
+} oadg_target_t;
+
+typedef struct oadg_view {      /* one generated view (one oamix() call, oa_mix.py:207-243)      */
+  int32_t H, W;
+  int32_t img;                  /* index into the caller's source/output image pointer tables    */
+  int32_t n_gt, gt_first;       /* slice of the oadg_gt array                                    */
+  int32_t n_ml;                 /* multi-level boxes (regions = n_ml + 1, last = outside)        */
+  int32_t ml_box[2][4];
+  int32_t width;                /* mixture_width                                                 */
+  int32_t depth[OADG_MAX_WIDTH];
+  float   ws[OADG_MAX_WIDTH];   /* np.float32(dirichlet)  (oa_mix.py:212)                        */
+  int32_t op_first;             /* ops of branch b, depth d, region r live at
+                                   op_first + (b*OADG_MAX_DEPTH + d)*OADG_MAX_REGIONS + r         */
+  int32_t n_tgt, tgt_first;     /* slice of the oadg_target array                                */
+  int32_t pad;
+  double  m;                    /* np.random.beta(1,1)  (oa_mix.py:282)                          */
+} oadg_view_t;
+
+typedef struct oadg_plan_header {
+  int32_t magic;                /* 0x4F414447 "OADG"                                             */
+  int32_t abi;                  /* OADG_ABI_VERSION                                              */
+  int32_t n_views, n_gt, n_ops, n_bbo, n_tgt;
+  int32_t max_h, max_w;         /* frame size every workspace image is dimensioned for           */
+  int32_t off_views, off_gt, off_ops, off_bbo, off_tgt;   /* byte offsets from the blob start    */
+  int32_t total_bytes;
+  int32_t pad;
+} oadg_plan_header_t;
+
+/* ---- library ---------------------------------------------------------------- */
+int  oadg_abi_version(void);
+/* sizes of the six plan structs in the order header, view, gt, op, bbo, target */
+void oadg_struct_sizes(int32_t out[6]);
+const char* oadg_error_string(int code);
+
+/* ---- OA-Mix ----------------------------------------------------------------- */
+
+/* Spectral-residual saliency score of every gt box.
+ * Replaces oa_mix.py:107-110 (cv2.saliency.StaticSaliencySpectralResidual +
+ * np.mean(uint8(map*255))).  boxes_dev: n x 5 int32 {img, x1, y1, x2, y2} with the
+ * int32-truncated gt box (oa_mix.py:102); boxes with a side < 4 must not be passed
+ * (the caller assigns them -1, oa_mix.py:103-105).  imgs_dev: table (in device
+ * memory) of device pointers to u8 HWC frames; hw_dev: n_img x 2 int32 {H, W}. */
+int oadg_saliency_scores(const uint8_t* const* imgs_dev, const int32_t* hw_dev,
+                         const int32_t* boxes_dev, int n_boxes,
+                         double* scores_dev, void* stream);
+
+/* Bytes of device workspace oadg_oamix_execute needs for this plan. */
+int oadg_oamix_workspace_bytes(const void* plan_host, size_t plan_bytes, size_t* out_bytes);
+
+/* Execute a batch of OA-Mix views.
+ * Replaces OAMix.oamix (oa_mix.py:207-243) minus its RNG draws, which stay on the
+ * host and arrive as the plan: multi-level composite of random ops
+ * (oa_mix.py:222-236; augmix.py / bbox_augmentation.py ops), branch mixing and
+ * object-aware mixing (oa_mix.py:281-309).
+ *   plan_host   : packed plan blob (oadg_plan_header_t + arrays), host memory
+ *   src_dev     : table in HOST memory of n_img DEVICE pointers, u8 HWC sources
+ *   dst_dev     : table in HOST memory of n_views DEVICE pointers, u8 HWC outputs
+ *   workspace_dev / workspace_bytes : scratch from oadg_oamix_workspace_bytes
+ *   launches_out: optional, receives the number of kernels launched            */
+int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
+                       const uint8_t* const* src_dev, int n_img,
+                       uint8_t* const* dst_dev,
+                       void* workspace_dev, size_t workspace_bytes,
+                       int* launches_out, void* stream);
+
+/* ---- OA-Loss ---------------------------------------------------------------- */
+
+/* Workspace bytes for forward+backward at N rows, C channels. */
+int oadg_supcon_workspace_bytes(int n, int c, size_t* out_bytes);
+
+/* Forward of ContrastiveLossPlus (contrastive_loss_plus.py:31-50 ->
+ * contrastive_loss.py:170-232 supcontrast -> :147-167 supcontrast_mask):
+ * double L2 normalisation, similarity / temperature, masked InfoNCE.
+ *   feats_dev   : [n, c] f32 row-major (pre-normalisation RoI embeddings)
+ *   labels_dev  : [n] int64, already padded for random-proposal rows
+ *   pair_dev    : [n] int32 other-view row of each row or -1
+ *                 (the reference's hard-wired layout, or a generalised map)
+ *   loss_dev    : [1] f32 out (loss_weight applied); 0 when #fg <= min_samples
+ *   workspace   : keeps the normalised embeddings and per-row statistics for bwd */
+int oadg_supcon_forward(const float* feats_dev, const int64_t* labels_dev,
+                        const int32_t* pair_dev, int n, int c,
+                        float temperature, float loss_weight, int min_samples,
+                        int normalized_input,
+                        float* loss_dev, void* workspace_dev, size_t workspace_bytes,
+                        int* launches_out, void* stream);
+
+/* Backward: grad_feats_dev[n,c] = dloss/dfeats * (*grad_loss_dev).  Must follow a
+ * forward on the same workspace. */
+int oadg_supcon_backward(const float* feats_dev, const int64_t* labels_dev,
+                         const int32_t* pair_dev, int n, int c,
+                         float temperature, float loss_weight, int normalized_input,
+                         const float* grad_loss_dev, float* grad_feats_dev,
+                         void* workspace_dev, size_t workspace_bytes,
+                         int* launches_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OADG_H_ */

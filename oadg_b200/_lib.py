@@ -1,0 +1,67 @@
+"""ctypes binding of libOADG.so (C ABI declared in include/oadg.h).
+
+The product path has no CPU fallback: if the CUDA library cannot be loaded, or no
+CUDA device is present when a compute entry point is called, this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libOADG.so')
+
+_c = ctypes
+_vp, _i32, _sz, _f32 = _c.c_void_p, _c.c_int32, _c.c_size_t, _c.c_float
+
+# name -> (restype, argtypes); must list every symbol include/oadg.h declares
+SIGNATURES = {
+    'oadg_abi_version': (_c.c_int, []),
+    'oadg_struct_sizes': (None, [_c.POINTER(_i32)]),
+    'oadg_error_string': (_c.c_char_p, [_c.c_int]),
+    'oadg_saliency_scores': (_c.c_int, [_vp, _vp, _vp, _c.c_int, _vp, _vp]),
+    'oadg_oamix_workspace_bytes': (_c.c_int, [_vp, _sz, _c.POINTER(_sz)]),
+    'oadg_oamix_execute': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_supcon_workspace_bytes': (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_sz)]),
+    'oadg_supcon_forward': (_c.c_int, [_vp, _vp, _vp, _c.c_int, _c.c_int, _f32, _f32, _c.c_int, _c.c_int,
+                                       _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_supcon_backward': (_c.c_int, [_vp, _vp, _vp, _c.c_int, _c.c_int, _f32, _f32, _c.c_int,
+                                        _vp, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+}
+
+_lib = None
+
+
+class OADGError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libOADG.so (built in-tree by ``python -m oadg_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OADGError(
+            'libOADG.so not found at %s: build it with `python -m oadg_b200.build` '
+            '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.oadg_abi_version() != 1:
+        raise OADGError('libOADG.so ABI mismatch')
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().oadg_error_string(code)
+        raise OADGError('libOADG error %d: %s' % (code, msg.decode() if msg else '?'))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise OADGError('oadg_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback')
+    return torch

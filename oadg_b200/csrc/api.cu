@@ -1,0 +1,25 @@
+// Library-level entry points of libOADG.so (see include/oadg.h).
+#include "oadg_common.cuh"
+
+extern "C" int oadg_abi_version(void) { return OADG_ABI_VERSION; }
+
+extern "C" void oadg_struct_sizes(int32_t out[6]) {
+  out[0] = (int32_t)sizeof(oadg_plan_header_t);
+  out[1] = (int32_t)sizeof(oadg_view_t);
+  out[2] = (int32_t)sizeof(oadg_gt_t);
+  out[3] = (int32_t)sizeof(oadg_op_t);
+  out[4] = (int32_t)sizeof(oadg_bbo_t);
+  out[5] = (int32_t)sizeof(oadg_target_t);
+}
+
+extern "C" const char* oadg_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case OADG_E_ARG: return "OADG_E_ARG: null pointer, bad size or misaligned buffer";
+    case OADG_E_PLAN: return "OADG_E_PLAN: malformed plan blob";
+    case OADG_E_LIMIT: return "OADG_E_LIMIT: exceeds a compiled limit";
+    case OADG_E_ROWS: return "OADG_E_ROWS: fewer rows than the two-view layout needs";
+    default: return "unknown libOADG error";
+  }
+}

@@ -1,0 +1,53 @@
+// Shared device/host helpers for libOADG (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "oadg.h"
+
+#define OADG_CUDA_TRY(expr)                  \
+  do {                                       \
+    cudaError_t _e = (expr);                 \
+    if (_e != cudaSuccess) return (int)_e;   \
+  } while (0)
+
+#define OADG_LAUNCH_CHECK()                  \
+  do {                                       \
+    cudaError_t _e = cudaGetLastError();     \
+    if (_e != cudaSuccess) return (int)_e;   \
+  } while (0)
+
+namespace oadg {
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace oadg

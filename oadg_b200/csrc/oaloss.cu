@@ -1,0 +1,482 @@
+// OA-Loss: fused L2-normalise + all-pairs cosine similarity + masked InfoNCE.
+//
+// Replaces the reference torch op chain
+//   ContrastiveLossPlus.forward   contrastive_loss_plus.py:31-50
+//   supcontrast                   contrastive_loss.py:170-232   (mask construction)
+//   supcontrast_mask              contrastive_loss.py:147-167   (normalise, matmul/T, masked log-softmax)
+// in closed form: no N x N tensor ever reaches HBM.
+//   P_ij = [y_i = y_j != bg, i != j]  or  [y_i = y_j = bg, j = pair(i)],  bg = max(labels)
+//   z = f f^T / T,  lse_i = log sum_{k != i} exp(z_ik),  n_i = sum_j P_ij
+//   loss = -(w/N) sum_{i: n_i > 0} ( (1/n_i) sum_j P_ij z_ij - lse_i )      if #fg > min_samples else 0
+//   dL/dz_ij = c_i (P_ij - n_i softmax_ij), c_i = -(w/N)/n_i ;  dL/df = (G + G^T) f / T
+//
+// This file is the CUDA-core (FFMA, fp32) implementation; the similarity contraction
+// also has a tcgen05 path (oaloss_tc.cu) selected at run time.
+#include "oadg_common.cuh"
+
+namespace oadg {
+namespace {
+
+constexpr int kC = 256;  // embedding width (out_dim_cont, ..._oadg.py:34); other widths go through the generic loop
+
+struct RowStats {  // per row, kept for backward
+  float lse;       // log sum_{k != i} exp(z_ik)
+  float coef;      // -(w/N)/n_i or 0
+  float npos;      // n_i
+  float pad;
+};
+
+struct LossWs {
+  float* fhat;       // [n, c] doubly normalised embeddings
+  float* inv1;       // [n] 1/max(||x||, eps)
+  float* inv2;       // [n] 1/max(||x/||x||||, eps)
+  RowStats* stats;   // [n]
+  int* meta;         // [0] bg label (low 32 bits), [1] n_fg, [2] active flag
+  float* npos;       // [n]
+  float* partial;    // [col_tiles][n][3]  (max, sumexp, possum)
+  float* dfhat;      // [n, c] gradient wrt fhat
+  size_t bytes;
+};
+
+inline LossWs carve_loss_ws(void* base, int n, int c) {
+  LossWs w;
+  char* p = static_cast<char*>(base);
+  size_t o = 0;
+  auto take = [&](size_t b) {
+    size_t at = o;
+    o = align_up(o + b, 256);
+    return at;
+  };
+  const int col_tiles = (n + 63) / 64;
+  size_t o_f = take((size_t)n * c * 4), o_i1 = take((size_t)n * 4), o_i2 = take((size_t)n * 4);
+  size_t o_st = take((size_t)n * sizeof(RowStats)), o_meta = take(64), o_np = take((size_t)n * 4);
+  size_t o_pa = take((size_t)col_tiles * n * 3 * 4), o_df = take((size_t)n * c * 4);
+  w.fhat = reinterpret_cast<float*>(p + o_f);
+  w.inv1 = reinterpret_cast<float*>(p + o_i1);
+  w.inv2 = reinterpret_cast<float*>(p + o_i2);
+  w.stats = reinterpret_cast<RowStats*>(p + o_st);
+  w.meta = reinterpret_cast<int*>(p + o_meta);
+  w.npos = reinterpret_cast<float*>(p + o_np);
+  w.partial = reinterpret_cast<float*>(p + o_pa);
+  w.dfhat = reinterpret_cast<float*>(p + o_df);
+  w.bytes = o;
+  return w;
+}
+
+// ---- F.normalize twice (contrastive_loss_plus.py:41, contrastive_loss.py:155): warp per row
+__global__ void __launch_bounds__(256)
+normalize_kernel(const float* __restrict__ x, int n, int c, int normalized_input, float* __restrict__ fhat,
+                 float* __restrict__ inv1, float* __restrict__ inv2) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + (size_t)row * c;
+  float s = 0.f;
+  for (int k = lane; k < c; k += 32) {
+    float v = xr[k];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  float i1 = normalized_input ? 1.f / fmaxf(sqrtf(s), 1e-12f) : 1.f;
+  float s2 = 0.f;
+  for (int k = lane; k < c; k += 32) {
+    float v = xr[k] * i1;
+    s2 += v * v;
+  }
+  s2 = warp_sum(s2);
+  float i2 = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+  for (int k = lane; k < c; k += 32) fhat[(size_t)row * c + k] = (xr[k] * i1) * i2;
+  if (lane == 0) {
+    inv1[row] = i1;
+    inv2[row] = i2;
+  }
+}
+
+// ---- label prep: bg = max(labels), #fg, n_i per row.  Single block (N is a few thousand).
+__global__ void __launch_bounds__(1024)
+label_prep_kernel(const int64_t* __restrict__ labels, const int32_t* __restrict__ pair, int n, int min_samples,
+                  int* __restrict__ meta, float* __restrict__ npos) {
+  __shared__ long long smax[32];
+  __shared__ int scnt[32];
+  __shared__ long long bg_s;
+  const int tid = threadIdx.x;
+  long long m = LLONG_MIN;
+  for (int i = tid; i < n; i += blockDim.x) m = labels[i] > m ? labels[i] : m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t > m ? t : m;
+  }
+  if ((tid & 31) == 0) smax[tid >> 5] = m;
+  __syncthreads();
+  if (tid == 0) {
+    long long t = smax[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = smax[w] > t ? smax[w] : t;
+    bg_s = t;
+  }
+  __syncthreads();
+  const long long bg = bg_s;
+  int cnt = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const long long yi = labels[i];
+    float np = 0.f;
+    if (yi != bg) {
+      ++cnt;
+      int same = 0;
+      for (int j = 0; j < n; ++j) same += (labels[j] == yi);
+      np = (float)(same - 1);
+    } else {
+      int pj = pair[i];
+      np = (pj >= 0 && pj < n && pj != i && labels[pj] == bg) ? 1.f : 0.f;
+    }
+    npos[i] = np;
+  }
+  cnt = (int)warp_sum((float)cnt);
+  if ((tid & 31) == 0) scnt[tid >> 5] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += scnt[w];
+    meta[0] = (int)bg;
+    meta[1] = t;
+    meta[2] = t > min_samples ? 1 : 0;  // contrastive_loss.py:211
+  }
+}
+
+// ---- similarity tile: 64 x 64 outputs, K = c, 256 threads, 4x4 per thread -------------
+constexpr int kTM = 64, kTN = 64, kTK = 32;
+
+struct TileAcc {
+  float v[4][4];
+};
+
+// computes acc = F[i0:i0+64] . F[j0:j0+64]^T over K = c; As/Bs: [kTK][kTM+4]
+__device__ __forceinline__ void sim_tile(const float* __restrict__ f, int n, int c, int i0, int j0, float (*As)[kTM + 4],
+                                         float (*Bs)[kTN + 4], TileAcc& acc) {
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc.v[a][b] = 0.f;
+  for (int k0 = 0; k0 < c; k0 += kTK) {
+    // 64 rows x 32 k per operand = 2048 floats = 512 float4; 256 threads x 2
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int idx = tid + it * 256;
+      int r = idx >> 3, kq = (idx & 7) * 4;
+      float4 va = make_float4(0, 0, 0, 0), vb = make_float4(0, 0, 0, 0);
+      if (i0 + r < n) va = *reinterpret_cast<const float4*>(f + (size_t)(i0 + r) * c + k0 + kq);
+      if (j0 + r < n) vb = *reinterpret_cast<const float4*>(f + (size_t)(j0 + r) * c + k0 + kq);
+      As[kq + 0][r] = va.x; As[kq + 1][r] = va.y; As[kq + 2][r] = va.z; As[kq + 3][r] = va.w;
+      Bs[kq + 0][r] = vb.x; Bs[kq + 1][r] = vb.y; Bs[kq + 2][r] = vb.z; Bs[kq + 3][r] = vb.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc.v[p][q] = fmaf(av[p], bv[q], acc.v[p][q]);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ bool is_pos(long long yi, long long yj, long long bg, int i, int j, int pair_i) {
+  if (yi != yj || i == j) return false;
+  return yi != bg ? true : (j == pair_i);
+}
+
+// forward: per (row tile, col tile) partial row statistics
+__global__ void __launch_bounds__(256)
+sim_fwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels, const int32_t* __restrict__ pair,
+               const int* __restrict__ meta, int n, int c, float inv_t, float* __restrict__ partial) {
+  if (!meta[2]) return;
+  __shared__ __align__(16) float As[kTK][kTM + 4];
+  __shared__ __align__(16) float Bs[kTK][kTN + 4];
+  const int i0 = blockIdx.y * kTM, j0 = blockIdx.x * kTN;
+  TileAcc acc;
+  sim_tile(f, n, c, i0, j0, As, Bs, acc);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const long long bg = (long long)meta[0];
+  long long yj[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) yj[q] = (j0 + tx * 4 + q) < n ? labels[j0 + tx * 4 + q] : 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = i0 + ty * 4 + p;
+    const bool row_ok = i < n;
+    const long long yi = row_ok ? labels[i] : 0;
+    const int pi = row_ok ? pair[i] : -1;
+    float m = -INFINITY, ps = 0.f;
+    float z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + tx * 4 + q;
+      z[q] = acc.v[p][q] * inv_t;
+      if (row_ok && j < n) {
+        m = fmaxf(m, z[q]);
+        if (is_pos(yi, yj[q], bg, i, j, pi)) ps += z[q];
+      }
+    }
+    // reduce over the 16 threads (tx) that share this row
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + tx * 4 + q;
+      if (row_ok && j < n && j != i) s += expf(z[q] - m);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    }
+    if (tx == 0 && row_ok) {
+      float* out = partial + ((size_t)blockIdx.x * n + i) * 3;
+      out[0] = m;
+      out[1] = s;
+      out[2] = ps;
+    }
+  }
+}
+
+// combine the column-tile partials, emit per-row stats and the scalar loss (single block,
+// fixed summation order => deterministic)
+__global__ void __launch_bounds__(1024)
+row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ npos, const int* __restrict__ meta,
+                  int n, int col_tiles, float loss_weight, RowStats* __restrict__ stats, float* __restrict__ loss) {
+  __shared__ double red[32];
+  const int tid = threadIdx.x;
+  if (!meta[2]) {
+    for (int i = tid; i < n; i += blockDim.x) stats[i] = RowStats{0.f, 0.f, 0.f, 0.f};
+    if (tid == 0) *loss = 0.f;
+    return;
+  }
+  double local = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    float M = -INFINITY;
+    for (int t = 0; t < col_tiles; ++t) M = fmaxf(M, partial[((size_t)t * n + i) * 3]);
+    float S = 0.f, Ps = 0.f;
+    for (int t = 0; t < col_tiles; ++t) {
+      const float* p = partial + ((size_t)t * n + i) * 3;
+      S += p[1] * expf(p[0] - M);
+      Ps += p[2];
+    }
+    const float lse = M + logf(S);
+    const float np = npos[i];
+    RowStats st;
+    st.lse = lse;
+    st.npos = np;
+    st.coef = np > 0.f ? -(loss_weight / (float)n) / np : 0.f;
+    st.pad = 0.f;
+    stats[i] = st;
+    if (np > 0.f) local += (double)(Ps / np - lse);
+  }
+  local = warp_sum(local);
+  if ((tid & 31) == 0) red[tid >> 5] = local;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *loss = (float)(-(double)loss_weight * t / (double)n);
+  }
+}
+
+// backward: block (row tile I, column split s): for its column tiles J
+//   A_ij = G_ij + G_ji ;  dF_I += A . F_J / T       (atomicAdd into dfhat)
+constexpr int kBwdThreads = 256;
+__global__ void __launch_bounds__(kBwdThreads)
+sim_bwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels, const int32_t* __restrict__ pair,
+               const int* __restrict__ meta, const RowStats* __restrict__ stats, int n, int c, float inv_t,
+               int col_tiles, float* __restrict__ dfhat) {
+  if (!meta[2]) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float(*As)[kTM + 4] = reinterpret_cast<float(*)[kTM + 4]>(smem_raw);
+  float(*Bs)[kTN + 4] = As + kTK;
+  float(*At)[kTN + 1] = reinterpret_cast<float(*)[kTN + 1]>(Bs + kTK);  // [64 rows][64 cols] A tile
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int i0 = blockIdx.y * kTM;
+  const long long bg = (long long)meta[0];
+  // each thread owns dF rows (4 rows: r = tid>>6 .. ) x cols: 64 rows x c cols / 256 threads
+  // mapping: thread t -> row group rg = t >> 4 (16 groups of 4 rows), col lane cl = t & 15 (cols cl, cl+16, ...)
+  float dacc[4][kC / 16];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < kC / 16; ++q) dacc[p][q] = 0.f;
+  for (int jt = blockIdx.x; jt < col_tiles; jt += gridDim.x) {
+    const int j0 = jt * kTN;
+    TileAcc acc;
+    sim_tile(f, n, c, i0, j0, As, Bs, acc);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int i = i0 + ty * 4 + p;
+      const bool row_ok = i < n;
+      const long long yi = row_ok ? labels[i] : 0;
+      const int pi = row_ok ? pair[i] : -1;
+      const RowStats si = row_ok ? stats[i] : RowStats{0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + tx * 4 + q;
+        float a = 0.f;
+        if (row_ok && j < n && j != i) {
+          const float z = acc.v[p][q] * inv_t;
+          const long long yjq = labels[j];
+          const RowStats sj = stats[j];
+          const float pij = is_pos(yi, yjq, bg, i, j, pi) ? 1.f : 0.f;
+          const float pji = is_pos(yjq, yi, bg, j, i, pair[j]) ? 1.f : 0.f;
+          a = si.coef * (pij - si.npos * expf(z - si.lse)) + sj.coef * (pji - sj.npos * expf(z - sj.lse));
+        }
+        At[ty * 4 + p][tx * 4 + q] = a * inv_t;
+      }
+    }
+    __syncthreads();
+    // dF_I[r][col] += sum_j At[r][j] * F[j0+j][col]
+    for (int j = 0; j < kTN; ++j) {
+      if (j0 + j >= n) break;
+      const float* fr = f + (size_t)(j0 + j) * c;
+      float a[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) a[p] = At[ty * 4 + p][j];
+#pragma unroll
+      for (int q = 0; q < kC / 16; ++q) {
+        const float fv = __ldg(fr + tx + q * 16);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) dacc[p][q] = fmaf(a[p], fv, dacc[p][q]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = i0 + ty * 4 + p;
+    if (i >= n) continue;
+#pragma unroll
+    for (int q = 0; q < kC / 16; ++q) atomicAdd(dfhat + (size_t)i * c + tx + q * 16, dacc[p][q]);
+  }
+}
+
+// chain rule through the two normalisations (warp per row), scaled by the upstream gradient
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dfhat, const float* __restrict__ inv1,
+                     const float* __restrict__ inv2, const int* __restrict__ meta, const float* __restrict__ gscale,
+                     int n, int c, int normalized_input, float* __restrict__ gx) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float* out = gx + (size_t)row * c;
+  if (!meta[2]) {
+    for (int k = lane; k < c; k += 32) out[k] = 0.f;
+    return;
+  }
+  const float g0 = *gscale;
+  const float* xr = x + (size_t)row * c;
+  const float* gr = dfhat + (size_t)row * c;
+  const float i1 = inv1[row], i2 = inv2[row];
+  // second normalisation: v = x*i1, u = v*i2 ; g1 = (g - (u.g) u) * i2
+  float dot = 0.f;
+  for (int k = lane; k < c; k += 32) dot += (xr[k] * i1 * i2) * gr[k];
+  dot = warp_sum(dot);
+  if (!normalized_input) {
+    for (int k = lane; k < c; k += 32) out[k] = g0 * (gr[k] - dot * (xr[k] * i2)) * i2;
+    return;
+  }
+  // first normalisation: u1 = x*i1 ; gx = (g1 - (u1.g1) u1) * i1
+  float dot1 = 0.f;
+  for (int k = lane; k < c; k += 32) {
+    float u = xr[k] * i1 * i2;
+    float g1 = (gr[k] - dot * u) * i2;
+    dot1 += (xr[k] * i1) * g1;
+  }
+  dot1 = warp_sum(dot1);
+  for (int k = lane; k < c; k += 32) {
+    float u = xr[k] * i1 * i2;
+    float g1 = (gr[k] - dot * u) * i2;
+    out[k] = g0 * (g1 - dot1 * (xr[k] * i1)) * i1;
+  }
+}
+
+}  // namespace
+}  // namespace oadg
+
+using namespace oadg;
+
+extern "C" int oadg_supcon_workspace_bytes(int n, int c, size_t* out_bytes) {
+  if (!out_bytes || n < 0 || c <= 0) return OADG_E_ARG;
+  LossWs w = carve_loss_ws(nullptr, n > 0 ? n : 1, c);
+  *out_bytes = w.bytes;
+  return 0;
+}
+
+extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels_dev, const int32_t* pair_dev, int n,
+                                   int c, float temperature, float loss_weight, int min_samples,
+                                   int normalized_input, float* loss_dev, void* workspace_dev,
+                                   size_t workspace_bytes, int* launches_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!loss_dev || n < 0) return OADG_E_ARG;
+  if (n == 0) {
+    OADG_CUDA_TRY(cudaMemsetAsync(loss_dev, 0, sizeof(float), stream));
+    if (launches_out) *launches_out = 0;
+    return 0;
+  }
+  if (!feats_dev || !labels_dev || !pair_dev || !workspace_dev) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if (!(temperature > 0.f)) return OADG_E_ARG;
+  if (((uintptr_t)feats_dev & 15) || ((uintptr_t)workspace_dev & 255)) return OADG_E_ARG;
+  LossWs w = carve_loss_ws(workspace_dev, n, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  const int col_tiles = (n + kTN - 1) / kTN, row_tiles = (n + kTM - 1) / kTM;
+  int launches = 0;
+  normalize_kernel<<<(n + 7) / 8, 256, 0, stream>>>(feats_dev, n, c, normalized_input, w.fhat, w.inv1, w.inv2);
+  OADG_LAUNCH_CHECK();
+  label_prep_kernel<<<1, 1024, 0, stream>>>(labels_dev, pair_dev, n, min_samples, w.meta, w.npos);
+  OADG_LAUNCH_CHECK();
+  sim_fwd_kernel<<<dim3(col_tiles, row_tiles), 256, 0, stream>>>(w.fhat, labels_dev, pair_dev, w.meta, n, c,
+                                                                 1.f / temperature, w.partial);
+  OADG_LAUNCH_CHECK();
+  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n, col_tiles, loss_weight, w.stats, loss_dev);
+  OADG_LAUNCH_CHECK();
+  launches += 4;
+  if (launches_out) *launches_out = launches;
+  return 0;
+}
+
+extern "C" int oadg_supcon_backward(const float* feats_dev, const int64_t* labels_dev, const int32_t* pair_dev, int n,
+                                    int c, float temperature, float loss_weight, int normalized_input,
+                                    const float* grad_loss_dev, float* grad_feats_dev, void* workspace_dev,
+                                    size_t workspace_bytes, int* launches_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  (void)loss_weight;
+  if (n < 0) return OADG_E_ARG;
+  if (n == 0) {
+    if (launches_out) *launches_out = 0;
+    return 0;
+  }
+  if (!feats_dev || !labels_dev || !pair_dev || !workspace_dev || !grad_loss_dev || !grad_feats_dev) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  LossWs w = carve_loss_ws(workspace_dev, n, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  const int col_tiles = (n + kTN - 1) / kTN, row_tiles = (n + kTM - 1) / kTM;
+  OADG_CUDA_TRY(cudaMemsetAsync(w.dfhat, 0, (size_t)n * c * sizeof(float), stream));
+  int splits = (2 * kNumSMs + row_tiles - 1) / row_tiles;
+  if (splits > col_tiles) splits = col_tiles;
+  if (splits < 1) splits = 1;
+  const size_t smem = (size_t)2 * kTK * (kTM + 4) * 4 + (size_t)kTM * (kTN + 1) * 4;
+  static bool attr = false;
+  if (!attr) {
+    OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  sim_bwd_kernel<<<dim3(splits, row_tiles), kBwdThreads, smem, stream>>>(w.fhat, labels_dev, pair_dev, w.meta, w.stats,
+                                                                         n, c, 1.f / temperature, col_tiles, w.dfhat);
+  OADG_LAUNCH_CHECK();
+  normalize_bwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(feats_dev, w.dfhat, w.inv1, w.inv2, w.meta, grad_loss_dev, n, c,
+                                                       normalized_input, grad_feats_dev);
+  OADG_LAUNCH_CHECK();
+  if (launches_out) *launches_out = 2;
+  return 0;
+}

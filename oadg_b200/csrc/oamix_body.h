@@ -1,0 +1,222 @@
+// Per-pixel bodies of the OA-Mix kernels (device) -- also compiled for the host by the
+// arithmetic check in tests/hostsim (test infrastructure only, never a product path).
+#pragma once
+#include "oadg.h"
+#include "oamix_math.h"
+
+#ifdef __CUDA_ARCH__
+#define OADG_LDG(p) __ldg(p)
+#else
+#define OADG_LDG(p) (*(p))
+#endif
+
+namespace oadg {
+
+struct DevPlan {
+  const oadg_view_t* views;
+  const oadg_gt_t* gts;
+  const oadg_op_t* ops;
+  const oadg_bbo_t* bbo;
+  const oadg_target_t* tgts;
+  const float* prof_x;  // [n_gt][max_w]
+  const float* prof_y;  // [n_gt][max_h]
+  int max_w, max_h;
+  const uint8_t* luts;  // [slot][3][256]
+};
+
+struct Lane {            // one (view, branch) chain alive at the current depth
+  int32_t view, branch;
+  int32_t op_base;       // index of region 0's op for this (branch, depth)
+  int32_t hist_slot;     // -1 if no histogram needed
+  const uint8_t* in;
+  uint8_t* out;
+};
+
+struct Chain {           // one bboxes-only op being evaluated (sequential over its boxes)
+  int32_t view, n;       // n = boxes in the chain
+  int32_t bbo_first, lane;
+  uint8_t* S;            // running full frame (starts as a copy of the lane input)
+  uint8_t* T;            // ROI staging
+};
+
+struct MixJob {
+  int32_t view, pad;
+  const uint8_t* src;
+  const uint8_t* branch[OADG_MAX_WIDTH];
+  uint8_t* out;
+};
+
+struct LutJob {
+  int32_t op, hist_slot, view, pad;
+};
+
+struct LdRO {   // read-only for the whole launch
+  OADG_HD int operator()(const uint8_t* p) const { return (int)OADG_LDG(p); }
+};
+struct LdRW {   // frames rewritten by the same chain between launches
+  OADG_HD int operator()(const uint8_t* p) const { return (int)*p; }
+};
+OADG_HD int ldb(const uint8_t* p) { return (int)OADG_LDG(p); }
+
+OADG_HD bool is_lut_kind(int k) {
+  return k == OADG_OP_AUTOCONTRAST || k == OADG_OP_EQUALIZE || k == OADG_OP_POSTERIZE ||
+         k == OADG_OP_SOLARIZE || k == OADG_OP_CONTRAST || k == OADG_OP_BRIGHTNESS;
+}
+OADG_HD bool needs_hist(int k) {
+  return k == OADG_OP_AUTOCONTRAST || k == OADG_OP_EQUALIZE || k == OADG_OP_CONTRAST;
+}
+
+// blurred mask of gt g at (x, y): outer product of the two 1-D profiles (oa_mix.py:75-93)
+OADG_HD float fg_mask(const DevPlan& P, int g, int x, int y) {
+  const oadg_gt_t& G = P.gts[g];
+  if (x < G.supp[0] || x >= G.supp[2] || y < G.supp[1] || y >= G.supp[3]) return 0.f;
+  return fmul(OADG_LDG(P.prof_y + (size_t)g * P.max_h + y), OADG_LDG(P.prof_x + (size_t)g * P.max_w + x));
+}
+// np.max(mask_bboxes, axis=0) at (x, y)   (bbox_augmentation.py:260)
+OADG_HD float union_mask(const DevPlan& P, const oadg_view_t& V, int x, int y) {
+  float m = 0.f;
+  for (int k = 0; k < V.n_gt; ++k) {
+    float v = fg_mask(P, V.gt_first + k, x, y);
+    m = v > m ? v : m;
+  }
+  return m;
+}
+
+// LUT entry i of a non-histogram op / the CONTRAST op
+OADG_HD uint8_t lut_simple_at(const oadg_op_t& op, int i, double luma_sum, double npx) {
+  if (op.kind == OADG_OP_POSTERIZE) return lut_posterize_at(i, op.p0);
+  if (op.kind == OADG_OP_SOLARIZE) return lut_solarize_at(i, op.p0);
+  if (op.kind == OADG_OP_BRIGHTNESS) return (uint8_t)pil_blend(0, i, op.factor);
+  // CONTRAST: degenerate = int(mean(luma) + 0.5)  (PIL ImageEnhance.Contrast / ImageStat.mean)
+  double mean = luma_sum / npx;
+  int deg = (int)(mean + 0.5);
+  return (uint8_t)pil_blend(deg, i, op.factor);
+}
+
+// ---- one pixel of box j of a bboxes-only chain (bbox_augmentation.py:57-71) ----------
+OADG_HD void bbo_pixel(const DevPlan& P, const Chain& C, int j, int x, int y) {
+  const oadg_bbo_t& B = P.bbo[C.bbo_first + j];
+  const oadg_view_t& V = P.views[C.view];
+  const size_t o = ((size_t)y * V.W + x) * 3;
+  const float m = fmul(OADG_LDG(P.prof_y + (size_t)B.gt * P.max_h + y), OADG_LDG(P.prof_x + (size_t)B.gt * P.max_w + x));
+  int v[3] = {C.S[o], C.S[o + 1], C.S[o + 2]};
+  if (m != 0.f) {  // m == 0 => img*1 + aug*0 == img exactly
+    double minv[6];
+    for (int i = 0; i < 6; ++i) minv[i] = B.minv[i];
+    WarpTap t = warp_px(minv, warp_row(minv, y), x);
+    int a[3];
+    warp_fetch3(LdRW(), C.S, V.H, V.W, t, a);
+    for (int c = 0; c < 3; ++c) v[c] = bbo_blend(m, v[c], a[c]);
+  }
+  C.T[o] = (uint8_t)v[0];
+  C.T[o + 1] = (uint8_t)v[1];
+  C.T[o + 2] = (uint8_t)v[2];
+}
+
+// ---- one op at one pixel (oa_mix.py:264-279 dispatch) ------------------------------------
+OADG_HD void eval_op(const DevPlan& P, const oadg_view_t& V, const oadg_op_t& op, const uint8_t* in,
+                     const uint8_t* scratch, size_t frame_bytes, int x, int y, int out[3]) {
+  const int H = V.H, W = V.W;
+  const size_t o = ((size_t)y * W + x) * 3;
+  const int kind = op.kind;
+  if (kind == OADG_OP_BBO_AFFINE) {
+    const uint8_t* s = op.scratch >= 0 ? scratch + (size_t)op.scratch * frame_bytes : in;
+    out[0] = ldb(s + o);
+    out[1] = ldb(s + o + 1);
+    out[2] = ldb(s + o + 2);
+    return;
+  }
+  int v[3] = {ldb(in + o), ldb(in + o + 1), ldb(in + o + 2)};
+  if (is_lut_kind(kind)) {
+    const uint8_t* lut = P.luts + (size_t)op.lut * 768;
+    out[0] = ldb(lut + v[0]);
+    out[1] = ldb(lut + 256 + v[1]);
+    out[2] = ldb(lut + 512 + v[2]);
+  } else if (kind == OADG_OP_BG_AFFINE) {
+    double minv[6];
+    for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
+    WarpTap t = warp_px(minv, warp_row(minv, y), x);
+    int a[3];
+    warp_fetch3(LdRO(), in, H, W, t, a);
+    const float M = union_mask(P, V, x, y);
+    // cv2.warpAffine of uint8(mask*255) with the same matrix (bbox_augmentation.py:263-264)
+    int mk[4];
+    for (int q = 0; q < 4; ++q) {
+      int xx = t.sx + (q & 1), yy = t.sy + (q >> 1);
+      mk[q] = ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? mask_to_u8(union_mask(P, V, xx, yy)) : 0;
+    }
+    int wm = bilerp_fix(mk[0], mk[1], mk[2], mk[3], t.fx, t.fy);
+    for (int c = 0; c < 3; ++c) out[c] = bg_blend(M, wm, v[c], a[c]);
+  } else if (kind == OADG_OP_INVERT) {
+    // -cv2.warpAffine(img, [[1,0,tx],[0,1,ty]]) : integer shift, zero fill, uint8 negation
+    int xs = x - op.p0, ys = y - op.p1;
+    if ((unsigned)xs < (unsigned)W && (unsigned)ys < (unsigned)H) {
+      const uint8_t* p = in + ((size_t)ys * W + xs) * 3;
+      out[0] = (-ldb(p)) & 255;
+      out[1] = (-ldb(p + 1)) & 255;
+      out[2] = (-ldb(p + 2)) & 255;
+    } else {
+      out[0] = out[1] = out[2] = 0;
+    }
+  } else if (kind == OADG_OP_COLOR) {
+    int deg = pil_luma(v[0], v[1], v[2]);
+    for (int c = 0; c < 3; ++c) out[c] = pil_blend(deg, v[c], op.factor);
+  } else if (kind == OADG_OP_SHARPNESS) {
+    if (x == 0 || y == 0 || x == W - 1 || y == H - 1) {  // SMOOTH copies the border
+      for (int c = 0; c < 3; ++c) out[c] = pil_blend(v[c], v[c], op.factor);
+    } else {
+      for (int c = 0; c < 3; ++c) {
+        int nb[9];
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx)
+            nb[dy * 3 + dx] = ldb(in + ((size_t)(y + 1 - dy) * W + (x - 1 + dx)) * 3 + c);
+        out[c] = pil_blend(pil_smooth9(nb), v[c], op.factor);
+      }
+    }
+  } else {
+    out[0] = v[0];
+    out[1] = v[1];
+    out[2] = v[2];
+  }
+}
+
+// ---- one pixel of one depth step (oa_mix.py:226-234): the region picks the op ---------
+OADG_HD void step_pixel(const DevPlan& P, const Lane& L, const uint8_t* scratch, size_t frame_bytes, int x, int y) {
+  const oadg_view_t& V = P.views[L.view];
+  int r = V.n_ml;
+  for (int b = 0; b < V.n_ml; ++b)
+    if (x >= V.ml_box[b][0] && x < V.ml_box[b][2] && y >= V.ml_box[b][1] && y < V.ml_box[b][3]) r = b;
+  int out[3];
+  eval_op(P, V, P.ops[L.op_base + r], L.in, scratch, frame_bytes, x, y, out);
+  uint8_t* q = L.out + ((size_t)y * V.W + x) * 3;
+  q[0] = (uint8_t)out[0];
+  q[1] = (uint8_t)out[1];
+  q[2] = (uint8_t)out[2];
+}
+
+// ---- one pixel of branch mixing + object-aware mixing (oa_mix.py:236,281-309) ---------
+OADG_HD void mix_pixel(const DevPlan& P, const MixJob& J, int x, int y) {
+  const oadg_view_t& V = P.views[J.view];
+  const size_t o = ((size_t)y * V.W + x) * 3;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int i = 0; i < V.width; ++i) {
+    const uint8_t* b = J.branch[i] + o;
+    for (int c = 0; c < 3; ++c) acc[c] = fadd(acc[c], fmul(V.ws[i], (float)ldb(b + c)));
+  }
+  const int img[3] = {ldb(J.src + o), ldb(J.src + o + 1), ldb(J.src + o + 2)};
+  float orig[3] = {0.f, 0.f, 0.f}, aug[3] = {0.f, 0.f, 0.f};
+  MixMask ms = {0.f, 0.f};
+  for (int t = 0; t < V.n_tgt; ++t) {
+    const oadg_target_t& T = P.tgts[V.tgt_first + t];
+    float mask;
+    if (T.kind == 0) mask = fg_mask(P, T.gt, x, y);
+    else mask = (x >= T.box[0] && x < T.box[2] && y >= T.box[1] && y < T.box[3]) ? 1.f : 0.f;
+    if (mask == 0.f) continue;  // exact: weight 0 adds +0 and leaves sum == max
+    float w = mix_target_weight(ms, mask);
+    for (int c = 0; c < 3; ++c) mix_accumulate(orig[c], aug[c], T.m_oa, img[c], acc[c], w);
+  }
+  uint8_t* q = J.out + o;
+  for (int c = 0; c < 3; ++c) q[c] = (uint8_t)mix_finish(orig[c], aug[c], V.m, img[c], acc[c], ms.sum);
+}
+
+}  // namespace oadg

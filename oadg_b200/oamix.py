@@ -1,0 +1,470 @@
+"""OA-Mix pipeline transform on B200: host plan sampler + libOADG plan executor.
+
+Drop-in for the reference ``@PIPELINES.register_module() class OAMix``
+(mmdet/datasets/pipelines/oa_mix.py:32-313): same constructor keys, same
+``transform(results) -> results`` contract and result keys (oa_mix.py:187-204), and
+it consumes the global legacy ``np.random`` stream draw for draw in the reference
+order, so a seeded run picks the same boxes, ops and mixing
+coefficients as the reference.  All pixel work (saliency, colour/geometric ops,
+region composite, object-aware mixing) runs in CUDA kernels behind the C ABI in
+include/oadg.h; there is no CPU pixel path.
+
+Host/device split: the host draws a *plan* (a few KB), the device executes it.
+The one device->host dependency is the per-box saliency score, which gates the
+object-aware target list (oa_mix.py:249,295) and therefore later RNG draws.
+"""
+import math
+import warnings
+
+import numpy as np
+
+from . import _lib, plan as P
+from .registry import PIPELINES
+
+_AUG = {
+    'augmix': ['autocontrast', 'equalize', 'posterize', 'solarize',
+               'bbo_rotate', 'bbo_shear_xy', 'bbo_translate_xy',
+               'bg_rotate', 'bg_shear_xy', 'bg_translate_xy'],
+    'augmix.all': ['autocontrast', 'equalize', 'posterize', 'solarize', 'invert',
+                   'color', 'contrast', 'brightness', 'sharpness',
+                   'bbo_rotate', 'bbo_shear_xy', 'bbo_translate_xy',
+                   'bg_rotate', 'bg_shear_xy', 'bg_translate_xy'],
+}
+
+
+def get_aug_list(version):
+    """Names of the ops of reference oa_mix.py:15-29 (same order => same np.random.choice index)."""
+    if version not in _AUG:
+        raise NotImplementedError
+    return _AUG[version]
+
+
+def _f32(v):
+    return float(np.float32(v))
+
+
+def _invert_affine(m):
+    """Forward 2x3 (6 python floats) -> inverse map in doubles, as cv::warpAffine computes it."""
+    m = list(m)
+    D = m[0] * m[4] - m[1] * m[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = m[4] * D, m[0] * D
+    m[0] = A11
+    m[1] *= -D
+    m[3] *= -D
+    m[4] = A22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return m
+
+
+def _rotation(center, deg):
+    """cv2.getRotationMatrix2D(center, deg, 1.0): Point2f centre, double math (augmix.py:91)."""
+    cx, cy = _f32(center[0]), _f32(center[1])
+    a = deg * (math.pi / 180.0)
+    al, be = math.cos(a), math.sin(a)
+    return [al, be, (1 - al) * cx - be * cy, -be, al, be * cx + (1 - al) * cy]
+
+
+def _iou_1xk(box, boxes):
+    """float32 IoU of one box against k boxes (core/evaluation/bbox_overlaps.py:5-65)."""
+    b2 = np.asarray(boxes).astype(np.float32)
+    if b2.size == 0:
+        return np.zeros((1, 0), np.float32)
+    b1 = np.asarray(box, dtype=np.float32)
+    b2 = b2.reshape(-1, 4)
+    a1 = (b1[2] - b1[0]) * (b1[3] - b1[1])
+    a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    ov = np.maximum(np.minimum(b1[2], b2[:, 2]) - np.maximum(b1[0], b2[:, 0]), 0) * \
+        np.maximum(np.minimum(b1[3], b2[:, 3]) - np.maximum(b1[1], b2[:, 1]), 0)
+    union = np.maximum(a1 + a2 - ov, np.float32(1e-6))
+    return (ov / union).reshape(1, -1)
+
+
+def _slice(lo, hi, n):
+    s, e, _ = slice(int(lo), int(hi)).indices(n)
+    return s, max(e, s)
+
+
+class _ViewPlan:
+    __slots__ = ('h', 'w', 'ws', 'ml_boxes', 'depths', 'ops', 'scores', 'oa_low', 'oa_boxes', 'm', 'm_oa')
+
+
+@PIPELINES.register_module()
+class OAMix:
+    def __init__(self,
+                 version='augmix',
+                 num_views=2, keep_orig=True, severity=10,
+                 mixture_width=3, mixture_depth=-1,
+                 random_box_scale=(0.01, 0.1), random_box_ratio=(3, 1 / 3),
+                 oa_random_box_scale=(0.005, 0.1), oa_random_box_ratio=(3, 1 / 3), num_bboxes=(3, 5),
+                 spatial_ratio=4, sigma_ratio=0.3,
+                 **kwargs):
+        self.aug_list = get_aug_list(version)
+        self.num_views = num_views
+        self.keep_orig = keep_orig
+        if self.num_views == 1 and self.keep_orig:
+            warnings.warn('No augmentation will be applied since num_views=1 and keep_orig=True')
+        self.severity = severity
+        self.aug_prob_coeff = 1.0
+        self.mixture_width = mixture_width
+        self.mixture_depth = mixture_depth
+        self.random_box_scale = random_box_scale
+        self.random_box_ratio = random_box_ratio
+        self.oa_random_box_scale = oa_random_box_scale
+        self.oa_random_box_ratio = oa_random_box_ratio
+        self.score_thresh = 10
+        self.spatial_ratio = spatial_ratio
+        self.sigma_ratio = sigma_ratio
+        self._history = {}
+        self.kwargs = kwargs
+        if mixture_width > P.MAX_WIDTH or mixture_depth > P.MAX_DEPTH:
+            raise ValueError('mixture_width/depth above the compiled limit (%d/%d)' % (P.MAX_WIDTH, P.MAX_DEPTH))
+        if spatial_ratio != 4:
+            raise NotImplementedError('libOADG is built for spatial_ratio=4 (all reference configs)')
+        self._ws_cache = None
+        self.last_launches = 0
+
+    def __repr__(self):
+        return self.__class__.__name__
+
+    # ------------------------------------------------------------------ sampling
+    def _sample_regions(self, h, w, scale, ratio, num, gt=None, scores=None, max_iters=50, eps=1e-6):
+        """oa_mix.py:122-184."""
+        rs = np.random
+        target = rs.randint(*num) if isinstance(num, tuple) else num
+        boxes, bscores = [], []
+        for _ in range(max_iters):
+            if len(boxes) >= target:
+                break
+            x1, y1 = rs.randint(0, w), rs.randint(0, h)
+            area = rs.uniform(*scale) * h * w
+            r = rs.uniform(*ratio)
+            bw, bh = int(np.sqrt(area / r)), int(np.sqrt(area * r))
+            if x1 + bw > w or y1 + bh > h:
+                continue
+            box = np.array([x1, y1, min(x1 + bw, w), min(y1 + bh, h)])
+            if np.sum(_iou_1xk(box, boxes)) > eps:
+                continue
+            if gt is not None:
+                ious = _iou_1xk(box, gt)
+                s = float('inf')
+                if np.sum(ious) > eps:
+                    for iou, fb, fs in zip(ious[0], gt, scores):
+                        if iou == 0.0 or fb[2] - fb[0] < 1 or fb[3] - fb[1] < 1:
+                            continue
+                        if fs < s:
+                            s = fs
+                bscores.append(s)
+            boxes.append(box)
+        return boxes, bscores
+
+    def _level_sign(self, geo):
+        level = np.random.uniform(low=0.1, high=self.severity)
+        u = np.random.uniform() if geo in ('rotate', 'shear_x', 'shear_y') else np.random.random()
+        return level, u > 0.5
+
+    @staticmethod
+    def _forward_affine(geo, level, neg, size_for_level, center, img_size):
+        """2x3 forward matrix as augmix.py:83-188 builds it (float32 entries except rotate)."""
+        if geo == 'rotate':
+            deg = int(level * 30 / 10)
+            if neg:
+                deg = -deg
+            if center is None:
+                center = (img_size[0] / 2, img_size[1] / 2)
+            return _rotation(center, deg)
+        if geo == 'shear_x':
+            l = float(level) * 0.3 / 10.
+            if neg:
+                l = -l
+            tx = 0 if center is None else -l * center[1]
+            return [1.0, _f32(-l), _f32(-tx), 0.0, 1.0, 0.0]
+        if geo == 'shear_y':
+            l = float(level) * 0.3 / 10.
+            if neg:
+                l = -l
+            ty = 0 if center is None else -l * center[0]
+            return [1.0, 0.0, 0.0, _f32(-l), 1.0, _f32(-ty)]
+        if geo == 'translate_x':
+            l = int(level * (size_for_level[0] / 3) / 10)
+            if neg:
+                l = -l
+            return [1.0, 0.0, _f32(-l), 0.0, 1.0, 0.0]
+        l = int(level * (size_for_level[1] / 3) / 10)
+        if neg:
+            l = -l
+        return [1.0, 0.0, 0.0, 0.0, 1.0, _f32(-l)]
+
+    def _sample_op(self, gt, img_size):
+        """One OAMix.aug() (oa_mix.py:264-279): op index, then the op's own draws."""
+        name = self.aug_list[np.random.choice(len(self.aug_list))]
+        if name in ('autocontrast', 'equalize'):
+            return (name,)
+        if name == 'posterize':
+            return (name, 4 - int(np.random.uniform(low=0.1, high=self.severity) * 4 / 10))
+        if name == 'solarize':
+            return (name, 256 - int(np.random.uniform(low=0.1, high=self.severity) * 256 / 10))
+        if name in ('color', 'contrast', 'brightness', 'sharpness'):
+            return (name, float(np.random.uniform(low=0.1, high=self.severity)) * 1.8 / 10. + 0.1)
+        if name == 'invert':
+            tx = 1 if np.random.random() > 0.5 else -1
+            ty = 1 if np.random.random() > 0.5 else -1
+            return (name, tx, ty)
+        where, geo = name.split('_', 1)
+        if geo == 'shear_xy':
+            geo = 'shear_x' if np.random.rand() < 0.5 else 'shear_y'
+        elif geo == 'translate_xy':
+            geo = 'translate_x' if np.random.rand() < 0.5 else 'translate_y'
+        if where == 'bg':
+            level, neg = self._level_sign(geo)
+            return ('bg_affine', _invert_affine(self._forward_affine(geo, level, neg, img_size, None, img_size)))
+        chain = []
+        for k, b in enumerate(gt):
+            x1, y1, x2, y2 = int(b[0]), int(b[1]), int(b[2]), int(b[3])
+            if (x2 - x1) < 1 or (y2 - y1) < 1:
+                continue  # bbox_augmentation.py:45-47: skipped before any draw
+            level, neg = self._level_sign(geo)
+            center = ((x1 + x2) / 2., (y1 + y2) / 2.)
+            fwd = self._forward_affine(geo, level, neg, (x2 - x1 + 1, y2 - y1 + 1), center, img_size)
+            chain.append((k, _invert_affine(fwd)))
+        return ('bbo_affine', chain)
+
+    def _sample_head(self, h, w, gt):
+        """Draws of oamix() up to (not including) the object-aware part: oa_mix.py:212-234."""
+        vp = _ViewPlan()
+        vp.h, vp.w = h, w
+        vp.ws = np.float32(np.random.dirichlet([self.aug_prob_coeff] * self.mixture_width))
+        ml, _ = self._sample_regions(h, w, self.random_box_scale, self.random_box_ratio, (1, 3))
+        vp.ml_boxes = np.stack(ml, axis=0)  # ValueError when no box could be placed (oa_mix.py:217)
+        vp.depths, vp.ops = [], []
+        for _ in range(self.mixture_width):
+            depth = self.mixture_depth if self.mixture_depth > 0 else np.random.randint(1, 4)
+            vp.depths.append(depth)
+            vp.ops.append([[self._sample_op(gt, (w, h)) for _r in range(len(ml) + 1)] for _d in range(depth)])
+        return vp
+
+    def _sample_tail(self, vp, gt, scores):
+        """Object-aware targets and mixing coefficients: oa_mix.py:245-262,282,295-298."""
+        vp.scores = scores
+        vp.oa_low = [k for k, s in enumerate(scores) if s <= self.score_thresh]
+        vp.oa_boxes, oa_scores = self._sample_regions(
+            vp.h, vp.w, self.oa_random_box_scale, self.oa_random_box_ratio,
+            min(max(len(vp.oa_low), 1), 5), gt=gt, scores=scores)
+        vp.m = np.random.beta(self.aug_prob_coeff, self.aug_prob_coeff)
+        tgt_scores = [scores[k] for k in vp.oa_low] + list(oa_scores)
+        vp.m_oa = [np.float32(np.random.uniform(0.0, 0.5)) if s <= self.score_thresh
+                   else np.float32(np.random.uniform(0.0, 1.0)) for s in tgt_scores]
+        return vp
+
+    # ------------------------------------------------------------------ records
+    def _gt_records(self, gt, h, w, view):
+        sr = self.spatial_ratio
+        rec = np.zeros(len(gt), P.GT_DT)
+        h4, w4 = h // sr, w // sr
+        for k, b in enumerate(gt):
+            lo = np.array(b // sr, dtype=np.int32)  # oa_mix.py:79
+            x1, y1, x2, y2 = (int(v) for v in lo)
+            sx = (x2 - x1) * self.sigma_ratio / 3 * 2
+            sy = (y2 - y1) * self.sigma_ratio / 3 * 2
+            blur = not (sx <= 0 or sy <= 0)
+            xs, xe = _slice(x1, x2, w4)
+            ys, ye = _slice(y1, y2, h4)
+            r = rec[k]
+            r['lo'] = (xs, ys, xe, ye)
+            r['blur'] = int(blur)
+            r['view'] = view
+            r['kx'] = (int(round(sx * 8 + 1)) | 1) if blur else 1
+            r['ky'] = (int(round(sy * 8 + 1)) | 1) if blur else 1
+            r['sigma_x'], r['sigma_y'] = (sx, sy) if blur else (1.0, 1.0)
+            supp = [0, 0, 0, 0]
+            if xe > xs and ye > ys and w4 > 0 and h4 > 0:
+                for ax, (s, e, n_lo, n_hi, ks) in enumerate(((xs, xe, w4, w, r['kx']), (ys, ye, h4, h, r['ky']))):
+                    rad = int(ks) // 2 if blur else 0
+                    a, bnd = max(s - rad, 0), min(e - 1 + rad, n_lo - 1)
+                    up = n_hi / n_lo
+                    d0 = int(math.floor((a - 0.5) * up - 0.5)) - 1
+                    d1 = int(math.ceil((bnd + 1.5) * up - 0.5)) + 1
+                    supp[ax], supp[ax + 2] = max(d0, 0), min(d1, n_hi)
+            r['supp'] = supp
+        return rec
+
+    def _pack(self, jobs):
+        """jobs: list of (view_plan, gt, img_index).  Returns the plan blob."""
+        views = np.zeros(len(jobs), P.VIEW_DT)
+        ops = np.zeros(len(jobs) * P.OPS_PER_VIEW, P.OP_DT)
+        gts, bbos, tgts = [], [], []
+        n_gt = n_bbo = n_tgt = 0
+        max_h = max_w = 1
+        for v, (vp, gt, img_i) in enumerate(jobs):
+            V = views[v]
+            V['H'], V['W'], V['img'] = vp.h, vp.w, img_i
+            max_h, max_w = max(max_h, vp.h), max(max_w, vp.w)
+            g = self._gt_records(gt, vp.h, vp.w, v)
+            V['n_gt'], V['gt_first'] = len(gt), n_gt
+            gts.append(g)
+            V['n_ml'] = len(vp.ml_boxes)
+            V['ml_box'][:len(vp.ml_boxes)] = vp.ml_boxes
+            V['width'] = len(vp.depths)
+            V['depth'][:len(vp.depths)] = vp.depths
+            V['ws'][:len(vp.ws)] = vp.ws
+            V['op_first'] = v * P.OPS_PER_VIEW
+            for b, steps in enumerate(vp.ops):
+                for d, regs in enumerate(steps):
+                    for r, op in enumerate(regs):
+                        o = ops[v * P.OPS_PER_VIEW + (b * P.MAX_DEPTH + d) * P.MAX_REGIONS + r]
+                        o['kind'] = P.OP[op[0]]
+                        o['lut'] = o['scratch'] = -1
+                        if op[0] in ('posterize', 'solarize'):
+                            o['p0'] = op[1]
+                        elif op[0] in ('color', 'contrast', 'brightness', 'sharpness'):
+                            o['factor'] = op[1]
+                        elif op[0] == 'invert':
+                            o['p0'], o['p1'] = op[1], op[2]
+                        elif op[0] == 'bg_affine':
+                            o['minv'] = op[1]
+                        elif op[0] == 'bbo_affine':
+                            o['bbo_first'], o['bbo_count'] = n_bbo, len(op[1])
+                            for k, minv in op[1]:
+                                rec = np.zeros(1, P.BBO_DT)
+                                rec['gt'], rec['minv'] = n_gt + k, minv
+                                bbos.append(rec)
+                            n_bbo += len(op[1])
+            t = np.zeros(len(vp.oa_low) + len(vp.oa_boxes), P.TGT_DT)
+            for i, k in enumerate(vp.oa_low):
+                t[i]['kind'], t[i]['gt'] = 0, n_gt + k
+            for i, bx in enumerate(vp.oa_boxes):
+                j = len(vp.oa_low) + i
+                xs, xe = _slice(bx[0], bx[2], vp.w)
+                ys, ye = _slice(bx[1], bx[3], vp.h)
+                t[j]['kind'], t[j]['gt'], t[j]['box'] = 1, -1, (xs, ys, xe, ye)
+            t['m_oa'] = vp.m_oa
+            V['n_tgt'], V['tgt_first'], V['m'] = len(t), n_tgt, vp.m
+            tgts.append(t)
+            n_gt += len(gt)
+            n_tgt += len(t)
+        cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
+        return P.pack(views, cat(gts, P.GT_DT), ops, cat(bbos, P.BBO_DT), cat(tgts, P.TGT_DT), max_h, max_w)
+
+    # ------------------------------------------------------------------ device
+    def saliency_scores(self, imgs, gt_list, stream=None):
+        """Per image: list of saliency scores (oa_mix.py:100-111); one kernel + one D2H for the batch."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        sr = self.spatial_ratio
+        rows, slots = [], []
+        out = []
+        for i, (img, gt) in enumerate(zip(imgs, gt_list)):
+            h, w = int(img.shape[0]), int(img.shape[1])
+            sc = []
+            for k, b in enumerate(gt):
+                x1, y1, x2, y2 = (int(v) for v in np.array(b, dtype=np.int32))
+                if x2 - x1 < sr or y2 - y1 < sr:
+                    sc.append(-1)
+                    continue
+                xs, xe = _slice(x1, x2, w)
+                ys, ye = _slice(y1, y2, h)
+                if xe <= xs or ye <= ys:
+                    raise ValueError('empty crop for gt box %s (cv2 would raise on an empty image)' % (b,))
+                rows.append((i, xs, ys, xe, ye))
+                slots.append((i, k))
+                sc.append(None)
+            out.append(sc)
+        if rows:
+            dev = imgs[0].device
+            s = torch.cuda.current_stream(dev) if stream is None else stream
+            ptrs = torch.tensor([int(t.data_ptr()) for t in imgs], dtype=torch.int64, device=dev)
+            hw = torch.tensor([[int(t.shape[0]), int(t.shape[1])] for t in imgs], dtype=torch.int32, device=dev)
+            boxes = torch.tensor(rows, dtype=torch.int32, device=dev)
+            scores = torch.empty(len(rows), dtype=torch.float64, device=dev)
+            _lib.check(lib.oadg_saliency_scores(ptrs.data_ptr(), hw.data_ptr(), boxes.data_ptr(), len(rows),
+                                                scores.data_ptr(), s.cuda_stream))
+            self.last_launches += 1
+            host = scores.cpu().numpy()  # the one device->host sync of the path
+            for (i, k), v in zip(slots, host):
+                out[i][k] = np.float64(v)
+        return out
+
+    def _workspace(self, nbytes, device):
+        torch = _lib.require_cuda()
+        if self._ws_cache is None or self._ws_cache.numel() < nbytes or self._ws_cache.device != device:
+            self._ws_cache = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        return self._ws_cache
+
+    def execute(self, jobs, imgs, outs=None, stream=None):
+        """Run the packed plans.  imgs: list of CUDA u8 HWC tensors; returns one output tensor per job."""
+        import ctypes
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = imgs[0].device
+        blob = self._pack(jobs)
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.oadg_oamix_workspace_bytes(blob.ctypes.data, blob.nbytes, ctypes.byref(need)))
+        ws = self._workspace(need.value, dev)
+        if outs is None:
+            outs = [torch.empty_like(imgs[j[2]]) for j in jobs]
+        src = (ctypes.c_void_p * len(imgs))(*[int(t.data_ptr()) for t in imgs])
+        dst = (ctypes.c_void_p * len(outs))(*[int(t.data_ptr()) for t in outs])
+        s = torch.cuda.current_stream(dev) if stream is None else stream
+        n = ctypes.c_int(0)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base,
+                                          ws.numel() - (base - ws.data_ptr()), ctypes.byref(n), s.cuda_stream))
+        self.last_launches += n.value
+        return outs
+
+    def oamix_batch(self, imgs, gt_list, stream=None):
+        """Device fast path: one generated view per image (the ``num_views=2, keep_orig=True`` case).
+
+        imgs: list of CUDA uint8 HWC tensors; gt_list: list of float32 [n,4] arrays.
+        Returns (views, oamix_boxes, multilevel_boxes) with the reference's dtypes."""
+        torch = _lib.require_cuda()
+        self.last_launches = 0
+        for t in imgs:
+            if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3 and t.is_contiguous()):
+                raise TypeError('images must be contiguous CUDA uint8 HWC tensors')
+        gt_list = [np.asarray(g, dtype=np.float32).reshape(-1, 4) for g in gt_list]
+        scores = self.saliency_scores(imgs, gt_list, stream)
+        jobs = []
+        for i, (img, gt) in enumerate(zip(imgs, gt_list)):
+            vp = self._sample_head(int(img.shape[0]), int(img.shape[1]), gt)
+            self._sample_tail(vp, gt, scores[i])
+            jobs.append((vp, gt, i))
+        outs = self.execute(jobs, imgs, stream=stream)
+        oamix_boxes = [np.stack(vp.oa_boxes, axis=0) for vp, _, _ in jobs]
+        ml_boxes = [vp.ml_boxes for vp, _, _ in jobs]
+        return outs, oamix_boxes, ml_boxes
+
+    def oamix(self, img, gt_bboxes):
+        """One view of one host image (reference oa_mix.py:207-243): H2D, kernels, D2H."""
+        torch = _lib.require_cuda()
+        img = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
+        gt = np.asarray(gt_bboxes, dtype=np.float32).reshape(-1, 4)
+        dimg = torch.from_numpy(img).cuda(non_blocking=True)
+        vp = self._sample_head(img.shape[0], img.shape[1], gt)
+        self._history['random_box_list'] = vp.ml_boxes
+        scores = self.saliency_scores([dimg], [gt])[0]
+        self._sample_tail(vp, gt, scores)
+        self._history.update(fg_box_list=gt, fg_score_list=scores, oa_random_box_list=vp.oa_boxes)
+        out = self.execute([(vp, gt, 0)], [dimg])[0]
+        return out.cpu().numpy()
+
+    def __call__(self, results, *args, **kwargs):
+        """oa_mix.py:187-204."""
+        results['custom_field'] = []
+        for i in range(1, self.num_views + 1):
+            if i == 1:
+                self._history = {}
+                if not self.keep_orig:
+                    results['img'] = self.oamix(results['img'].copy(), results['gt_bboxes'].copy())
+                results['img_fields'] = ['img']
+            else:
+                results[f'img{i}'] = self.oamix(results['img'].copy(), results['gt_bboxes'].copy())
+                results['img_fields'] += [f'img{i}']
+                results[f'gt_bboxes{i}'] = results['gt_bboxes'].copy()
+                results['oamix_boxes'] = np.stack(self._history['oa_random_box_list'], axis=0)
+                results['custom_field'] += [f'img{i}', f'gt_bboxes{i}', 'oamix_boxes']
+                results['multilevel_boxes'] = self._history['random_box_list']
+                results['custom_field'] += ['multilevel_boxes']
+        return results

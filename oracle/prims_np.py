@@ -295,3 +295,103 @@ def resize_linear_exact_u8(gray, n_out_h=64, n_out_w=64):
     rows = g[:, x0] * (256 - ax)[None, :] + g[:, x1] * ax[None, :]            # 8.8
     out = rows[y0, :] * (256 - ay)[:, None] + rows[y1, :] * ay[:, None]        # 8.16
     return ((out + (1 << 15)) >> 16).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------
+# saliency: arithmetic spec of the CUDA kernel (own FFT; cv2's f32 cartToPolar emulated)
+# ----------------------------------------------------------------------------
+_F32 = np.float32
+_ATAN_P = [_F32(0.9997878412794807) * _F32(180 / np.pi), _F32(-0.3258083974640975) * _F32(180 / np.pi),
+           _F32(0.1555786518463281) * _F32(180 / np.pi), _F32(-0.04432655554792128) * _F32(180 / np.pi)]
+
+
+def _fma32(a, b, c):
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(_F32)
+
+
+def cv_magnitude_f32(re, im):
+    """cv2.cartToPolar magnitude for 64F input on an FMA host: sqrtf(fmaf(x,x,y*y)) in f32."""
+    x = np.asarray(re).astype(_F32)
+    y = np.asarray(im).astype(_F32)
+    return np.sqrt(_fma32(x, x, (y * y).astype(_F32))).astype(np.float64)
+
+
+def cv_fast_atan_f32(im, re):
+    """cv2.cartToPolar angle (radians) for 64F input: f32 polynomial fastAtan with FMAs."""
+    x = np.asarray(re).astype(_F32)
+    y = np.asarray(im).astype(_F32)
+    ax, ay = np.abs(x), np.abs(y)
+    eps = _F32(2.220446049250313e-16)
+    big = ax >= ay
+    with np.errstate(all='ignore'):
+        c = np.where(big, ay / (ax + eps), ax / (ay + eps)).astype(_F32)
+    c2 = (c * c).astype(_F32)
+    p1, p3, p5, p7 = _ATAN_P
+    a = _fma32(_fma32(_fma32(np.full_like(c, p7), c2, np.full_like(c, p5)), c2, np.full_like(c, p3)),
+               c2, np.full_like(c, p1))
+    a = (a * c).astype(_F32)
+    a = np.where(big, a, _F32(90) - a)
+    a = np.where(x < 0, _F32(180) - a, a)
+    a = np.where(y < 0, _F32(360) - a, a)
+    return (a * _F32(np.pi / 180)).astype(_F32).astype(np.float64)
+
+
+def _reflect101(i, n):
+    i = np.abs(i)
+    return np.where(i >= n, 2 * (n - 1) - i, i)
+
+
+def resize_linear_f32(m, w, h):
+    """cv2.resize(f32, INTER_LINEAR) generic path (IPP off): f32 weights, horizontal then vertical."""
+    def axis(n_in, n_out):
+        d = np.arange(n_out)
+        f = ((d + 0.5) * (n_in / n_out) - 0.5).astype(_F32)
+        s = np.floor(f).astype(np.int64)
+        t = (f - s).astype(_F32)
+        t = np.where(s < 0, _F32(0), t)
+        s = np.where(s < 0, 0, s)
+        t = np.where(s >= n_in - 1, _F32(0), t)
+        s = np.where(s >= n_in - 1, n_in - 1, s)
+        return s, np.minimum(s + 1, n_in - 1), t
+    sx, sx1, tx = axis(m.shape[1], w)
+    sy, sy1, ty = axis(m.shape[0], h)
+    rows = (m[:, sx] * (_F32(1) - tx) + m[:, sx1] * tx).astype(_F32)
+    return (rows[sy] * (_F32(1) - ty)[:, None] + rows[sy1] * ty[:, None]).astype(_F32)
+
+
+def saliency_map64(crop):
+    """64x64 f32 saliency map (before the final resize) with the kernel's arithmetic."""
+    g = resize_linear_exact_u8(gray_bgr(crop) if crop.ndim == 3 else crop).astype(np.float64)
+    F = np.fft.fft2(g)
+    re, im = F.real, F.imag
+    mag = cv_magnitude_f32(re, im)
+    ang = cv_fast_atan_f32(im, re)
+    with np.errstate(all='ignore'):
+        la = np.log(mag)
+        idx = _reflect101(np.arange(-1, 65), 64)
+        pad = la[idx][:, idx]
+        bl = sum(pad[dy:dy + 64, dx:dx + 64] for dy in range(3) for dx in range(3)) * (1.0 / 9)
+        nm = np.exp(la - bl)
+        G = np.fft.ifft2(nm * np.cos(ang) + 1j * nm * np.sin(ang)) * 4096
+    m = cv_magnitude_f32(G.real, G.imag)
+    x = np.arange(5) - 2.0
+    k = np.exp(-0.5 / 64.0 * x * x)
+    k = k / k.sum()
+    idx = _reflect101(np.arange(-2, 66), 64)
+    pad = m[:, idx]
+    m = sum(pad[:, d:d + 64] * k[d] for d in range(5))
+    pad = m[idx, :]
+    m = sum(pad[d:d + 64, :] * k[d] for d in range(5))
+    m = m * m
+    with np.errstate(all='ignore'):
+        m = m / m.max()
+    return m.astype(_F32)
+
+
+def saliency_score_emul(crop):
+    m = saliency_map64(crop)
+    h, w = crop.shape[:2]
+    out = resize_linear_f32(m, w, h)
+    with np.errstate(all='ignore'):
+        v = np.where(np.isnan(out), 0, out * _F32(255)).astype(np.uint8)
+    return float(v.astype(np.int64).sum() / (w * h))
