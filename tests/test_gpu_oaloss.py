@@ -1,0 +1,87 @@
+"""OA-Loss CUDA path (plugin -> C ABI) against the oracle (float64 restatement pinned to the reference).
+Tolerance from BASELINE.json north_star: 1e-5 relative on the loss and on the gradient."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import supcon_np, synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _run(cuda, x, labels, **kw):
+    import torch
+    from oadg_b200 import ContrastiveLossPlus
+    loss_fn = ContrastiveLossPlus(loss_weight=0.01, num_views=2, temperature=0.06, **kw)
+    xd = x.to(cuda).requires_grad_(True)
+    loss = loss_fn(xd, labels.to(cuda))
+    if loss.requires_grad:
+        loss.backward()
+    return loss, xd.grad, loss_fn
+
+
+@pytest.mark.parametrize('n', [2048, 2088, 2085])
+def test_loss_and_grad_match_oracle_and_reference_golden(cuda, n):
+    x, labels = synth.make_roi_set(n)
+    loss, grad, fn = _run(cuda, x, labels)
+    assert loss.dim() == 0 and loss.device.type == 'cuda' and fn.stats['launches'] >= 6
+    ref, gref = supcon_np.supcon_loss(x.numpy(), labels.numpy(), 0.06, 10, 0.01, want_grad=True)
+    assert abs(loss.item() - ref) <= RTOL * abs(ref)
+    g = grad.cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(g - gref) <= RTOL * np.linalg.norm(gref)
+    G = np.load(GOLDEN + '/supcon.npz')   # produced by the unmodified reference (f32 torch path)
+    assert abs(loss.item() - float(G['n%d/f32/loss' % n])) <= RTOL * abs(ref)
+    rows = np.concatenate([g[0:8], g[1024:1032], g[n - 8:n]])
+    assert np.linalg.norm(rows - G['n%d/f64/grad_rows' % n]) <= RTOL * np.linalg.norm(G['n%d/f64/grad_rows' % n])
+
+
+def test_upstream_gradient_and_dtype(cuda):
+    import torch
+    from oadg_b200 import ContrastiveLossPlus
+    x, labels = synth.make_roi_set(2088, seed=3)
+    fn = ContrastiveLossPlus(loss_weight=1.0, temperature=0.07)
+    xd = x.to(cuda).requires_grad_(True)
+    (fn(xd, labels.to(cuda)) * 3.0).backward()
+    ref, gref = supcon_np.supcon_loss(x.numpy(), labels.numpy(), 0.07, 10, 1.0, want_grad=True)
+    assert np.linalg.norm(xd.grad.cpu().numpy() - 3.0 * gref) <= RTOL * np.linalg.norm(3.0 * gref)
+
+
+def test_quirks(cuda):
+    import torch
+    from oadg_b200 import ContrastiveLossPlus
+    # #fg <= min_samples -> exactly 0 and zero gradient (contrastive_loss.py:211,229-230)
+    x, labels = synth.make_roi_set(2048, n_fg=5)
+    loss, grad, _ = _run(cuda, x, labels)
+    assert loss.item() == 0.0 and (grad is None or float(grad.abs().max()) == 0.0)
+    # no bg RoI in the batch: the highest fg class silently plays bg (contrastive_loss.py:197-200)
+    x, labels = synth.make_roi_set(2048, n_fg=1024, n_cls=4)
+    labels = labels.clamp(max=3)
+    loss, grad, _ = _run(cuda, x, labels)
+    ref, gref = supcon_np.supcon_loss(x.numpy(), labels.numpy(), 0.06, 10, 0.01, want_grad=True)
+    assert abs(loss.item() - ref) <= RTOL * abs(ref)
+    assert np.linalg.norm(grad.cpu().numpy() - gref) <= RTOL * np.linalg.norm(gref)
+    # fewer than 2048 rows: the reference raises RuntimeError (contrastive_loss.py:205)
+    with pytest.raises(RuntimeError):
+        ContrastiveLossPlus()(torch.randn(1024, 256, device=cuda), torch.zeros(1024, 1, dtype=torch.int64, device=cuda))
+    # normalized_input=False
+    x, labels = synth.make_roi_set(2088, seed=5)
+    loss, grad, _ = _run(cuda, x * 0.3, labels, normalized_input=False)
+    ref, gref = supcon_np.supcon_loss((x * 0.3).numpy(), labels.numpy(), 0.06, 10, 0.01, normalized_input=False, want_grad=True)
+    assert abs(loss.item() - ref) <= RTOL * abs(ref)
+    assert np.linalg.norm(grad.cpu().numpy() - gref) <= RTOL * np.linalg.norm(gref)
+
+
+def test_property_invariances(cuda):
+    """Size-independent properties at full size: row-scale invariance (double normalisation) and
+    invariance of the loss under a permutation that respects the two-view pairing."""
+    import torch
+    x, labels = synth.make_roi_set(2088, seed=11)
+    l0, _, _ = _run(cuda, x, labels)
+    scale = torch.rand(2088, 1) * 5 + 0.1
+    l1, _, _ = _run(cuda, x * scale, labels)
+    assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item())
+    perm = torch.randperm(1024)
+    idx = torch.cat([perm, perm + 1024, torch.arange(2048, 2088)])
+    l2, _, _ = _run(cuda, x[idx], labels[torch.cat([perm, perm + 1024])])
+    assert abs(l0.item() - l2.item()) <= 1e-5 * abs(l0.item())

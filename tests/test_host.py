@@ -1,0 +1,154 @@
+"""Host logic without a GPU: C ABI surface, plan records, registry / config surface, plan sampler vs oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import OAMIX_CFG, ROOT, sampler_cfg
+from oracle import oamix_np, synth
+
+REF = '/root/reference'
+
+
+def test_c_abi_exports_every_declared_symbol(libpath):
+    from oadg_b200 import _lib, plan
+    header = open(os.path.join(ROOT, 'include', 'oadg.h')).read()
+    declared = set(re.findall(r'\b(oadg_[a-z_0-9]+)\s*\(', header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(libpath)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib = _lib.load()
+    sizes = (ctypes.c_int32 * 6)()
+    lib.oadg_struct_sizes(sizes)
+    assert list(sizes) == plan.STRUCT_SIZES
+    assert lib.oadg_error_string(-2).startswith(b'OADG_E_PLAN')
+
+
+def test_plan_blob_validation(libpath):
+    from oadg_b200 import _lib
+    lib = _lib.load()
+    need = ctypes.c_size_t(0)
+    junk = np.zeros(64, np.uint8)
+    assert lib.oadg_oamix_workspace_bytes(junk.ctypes.data, junk.nbytes, ctypes.byref(need)) == -2
+    assert lib.oadg_oamix_workspace_bytes(None, 0, ctypes.byref(need)) == -1
+    from oadg_b200.oamix import OAMix
+    img, gt = synth.make_image(0, 96, 160, 3)
+    np.random.seed(1)
+    t = OAMix(version='augmix')
+    vp = t._sample_head(96, 160, gt)
+    t._sample_tail(vp, gt, [20.0, 5.0, -1])
+    blob = t._pack([(vp, gt, 0)])
+    assert lib.oadg_oamix_workspace_bytes(blob.ctypes.data, blob.nbytes, ctypes.byref(need)) == 0
+    assert need.value > 96 * 160 * 3 * 6
+    bad = blob.copy()
+    bad[8:12] = np.frombuffer(np.int32(-5).tobytes(), np.uint8)   # n_views < 0
+    assert lib.oadg_oamix_workspace_bytes(bad.ctypes.data, bad.nbytes, ctypes.byref(need)) == -2
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from oadg_b200 import OAMix, ContrastiveLossPlus, _lib
+    img, gt = synth.make_image(0, 64, 64, 1)
+    with pytest.raises(_lib.OADGError):
+        OAMix()(dict(img=img, gt_bboxes=gt))
+    with pytest.raises(_lib.OADGError):
+        ContrastiveLossPlus()(torch.randn(2048, 256), torch.zeros(2048, 1, dtype=torch.int64))
+
+
+def test_registry_surface_and_ctor_contract():
+    import oadg_b200
+    from oadg_b200 import PIPELINES, LOSSES, build_from_cfg, build_loss
+    import mmdet.datasets.pipelines.oa_mix as shim
+    from mmdet.datasets.builder import PIPELINES as P2
+    from mmdet.models.builder import LOSSES as L2
+    assert P2 is PIPELINES and L2 is LOSSES and shim.OAMix is oadg_b200.OAMix
+    t = build_from_cfg(dict(type='OAMix', version='augmix.all', use_mix=True, mixture_width=1, mixture_depth=-1,
+                            use_oa=True, oa_version='saliency_sparse', use_mrange=False, use_multilevel=True), PIPELINES)
+    assert t.mixture_width == 1 and t.kwargs['oa_version'] == 'saliency_sparse' and len(t.aug_list) == 15
+    assert t.score_thresh == 10 and t.aug_prob_coeff == 1.0 and repr(t) == 'OAMix'
+    with pytest.raises(NotImplementedError):
+        build_from_cfg(dict(type='OAMix', version='nope'), PIPELINES)
+    with pytest.warns(UserWarning):
+        oadg_b200.OAMix(num_views=1, keep_orig=True)
+    loss = build_loss(dict(type='ContrastiveLossPlus', loss_weight=0.01, num_views=2, temperature=0.06, version='r-cnn'))
+    assert (loss.loss_weight, loss.temperature, loss.num_views, loss.min_samples, loss.normalized_input) == (0.01, 0.06, 2, 10, True)
+    assert loss.kwargs == dict(version='r-cnn')
+    import torch
+    out = loss(torch.zeros(0, 256), torch.zeros(0, 1, dtype=torch.int64))   # contrastive_loss_plus.py:38-39
+    assert out.shape == (1,) and out.device.type == 'cpu' and float(out) == 0.0
+    with pytest.raises(KeyError):
+        build_from_cfg(dict(type='Missing'), PIPELINES)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF + '/configs/OA-DG'), reason='reference configs only exist in the dev container')
+def test_reference_configs_load_unchanged_and_build_our_plugins():
+    from oadg_b200 import Config, PIPELINES, build_from_cfg, build_loss, OAMix, ContrastiveLossPlus
+    remap = {'/ws/external/': REF + '/'}
+    n = 0
+    for sub, dirs, files in os.walk(REF + '/configs/OA-DG'):
+        for f in sorted(files):
+            if not f.endswith('.py'):
+                continue
+            cfg = Config.fromfile(os.path.join(sub, f), base_remap=remap)
+            n += 1
+            if 'oamix_config' in cfg:
+                t = build_from_cfg(cfg.oamix_config, PIPELINES)
+                assert isinstance(t, OAMix)
+                if 'train_pipeline' in cfg:
+                    assert any(isinstance(s, dict) and s.get('type') == 'OAMix' for s in cfg.train_pipeline)
+            lc = cfg.get('model', {}).get('roi_head', {}).get('bbox_head', {}).get('loss_cont')
+            if lc is not None:
+                loss = build_loss(lc)
+                assert isinstance(loss, ContrastiveLossPlus) and loss.temperature == 0.06 and loss.loss_weight == 0.01
+    assert n >= 8
+    cfg = Config.fromfile(REF + '/configs/OA-DG/cityscapes/faster_rcnn_r50_fpn_1x_cityscapes_oadg.py', base_remap=remap)
+    assert cfg.model.roi_head.type == 'ContrastiveRoIHead' and cfg.model.backbone.depth == 50   # merged through _base_
+    assert cfg.data.samples_per_gpu == 2 and cfg.custom_imports['imports'] == ['mmdet.datasets.pipelines.oa_mix']
+
+
+@pytest.mark.parametrize('case', [('augmix', 96, 160, 3, 0, 100, {}), ('augmix.all', 120, 200, 4, 1, 201, {}),
+                                  ('augmix', 64, 64, 0, 2, 302, dict(mixture_width=1)),
+                                  ('augmix.all', 80, 90, 2, 3, 7, dict(mixture_width=2, mixture_depth=2))])
+def test_plan_sampler_consumes_rng_like_the_oracle(case):
+    from oadg_b200.oamix import OAMix
+    version, h, w, n_gt, s, seed, extra = case
+    cfg = sampler_cfg(dict(OAMIX_CFG, version=version, **extra))
+    img, gt = synth.make_image(s, h, w, n_gt)
+    np.random.seed(seed)
+    plan = oamix_np.sample_plan(img, gt, **cfg)
+    st_o = np.random.get_state()
+    np.random.seed(seed)
+    t = OAMix(**cfg)
+    vp = t._sample_head(h, w, gt)
+    t._sample_tail(vp, gt, plan['scores'])
+    st_p = np.random.get_state()
+    assert st_o[2] == st_p[2] and np.array_equal(st_o[1], st_p[1])
+    assert np.array_equal(vp.ml_boxes, plan['ml_boxes']) and vp.ml_boxes.dtype == np.int64
+    assert len(vp.oa_boxes) == len(plan['oa_boxes']) and all(np.array_equal(a, b) for a, b in zip(vp.oa_boxes, plan['oa_boxes']))
+    assert np.array_equal(vp.ws, plan['ws']) and vp.m == plan['m'] and vp.m_oa == plan['m_oa']
+    assert vp.oa_low == plan['oa_low_fg']
+    for steps_p, steps_o in zip(vp.ops, plan['branches']):
+        assert len(steps_p) == len(steps_o)
+        for regs_p, regs_o in zip(steps_p, steps_o):
+            for a, b in zip(regs_p, regs_o):
+                if b['name'].startswith('bg_only'):
+                    from oracle import prims_np
+                    assert a[0] == 'bg_affine' and np.array_equal(np.array(a[1]), prims_np.invert_affine(b['M']))
+                elif b['name'].startswith('bboxes_only'):
+                    assert a[0] == 'bbo_affine' and [k for k, _ in a[1]] == [x['k'] for x in b['boxes']]
+                else:
+                    assert a[0] == b['name']
+
+
+def test_pair_map_and_row_check():
+    from oadg_b200 import reference_pair_map
+    from oracle import supcon_np
+    for n in (2048, 2088, 2085, 3100):
+        assert np.array_equal(reference_pair_map(n), supcon_np.pair_map(n))
+    with pytest.raises(RuntimeError):
+        reference_pair_map(1024)
