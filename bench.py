@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- OA-Mix + OA-Loss images/sec @1024x2048, bs=2/GPU (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = the per-GPU hot path of one training iteration of
+configs/OA-DG/cityscapes/faster_rcnn_r50_fpn_1x_cityscapes_oadg.py on synthetic data:
+  OA-Mix  : 2 source frames 1024x2048x3 u8 (8 gt boxes each) -> 2 generated views
+  OA-Loss : ContrastiveLossPlus forward + backward on [2088, 256] two-view RoI embeddings
+images/sec = source images consumed per second (2 per step per GPU), whole job.
+
+value  : inputs resident in HBM, CUDA-event timed (includes the saliency D2H sync, host plan
+         sampling and the plan upload -- they are part of the path).
+e2e    : the registered plugins called with HOST buffers (pinned): H2D of frames / embeddings and D2H of
+         the generated views / loss value inside the timed region.
+roofline: the OA-Mix step kernel, achieved = algorithmic bytes (2 * 3HW per lane step) / CUDA-event kernel
+         time from a second, event-instrumented pass over the same seeded plans.
+cpu_baseline / --impl reference: the oracle port of the reference's CPU path (oracle/oamix_np.py +
+         oracle/supcon_np.py: same cv2 / Pillow / NumPy calls as the reference; the reference itself is
+         Python under /root/reference and does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+H, W, N_GT, BS = 1024, 2048, 8, 2
+N_ROI, C_ROI = 2088, 256
+OAMIX_CFG = dict(version='augmix', num_views=2, keep_orig=True, severity=10,
+                 random_box_ratio=(3, 1 / 3), random_box_scale=(0.01, 0.1),
+                 oa_random_box_scale=(0.005, 0.1), oa_random_box_ratio=(3, 1 / 3),
+                 spatial_ratio=4, sigma_ratio=0.3)
+LOSS_CFG = dict(loss_weight=0.01, num_views=2, temperature=0.06)
+POOL = 24  # distinct source frames cycled through: 24 x 6.3 MB = 151 MB > 126 MB L2
+
+
+def make_image(seed, h=H, w=W, n_gt=N_GT):
+    """SURVEY.md 8d generator (same as oracle/synth.py; duplicated so the product arm never imports oracle)."""
+    import cv2
+    rng = np.random.RandomState(seed)
+    base = rng.randint(0, 256, (max(h // 32, 2), max(w // 32, 2), 3)).astype(np.uint8)
+    img = cv2.resize(base, (w, h), interpolation=cv2.INTER_CUBIC)
+    img = np.clip(img.astype(np.int16) + rng.randint(-12, 13, (h, w, 3)), 0, 255).astype(np.uint8)
+    bw = rng.randint(max(w * 32 // 2048, 2), max(w * 400 // 2048, 4), n_gt)
+    bh = rng.randint(max(h * 32 // 1024, 2), max(h * 300 // 1024, 4), n_gt)
+    x1 = rng.randint(0, w - bw)
+    y1 = rng.randint(0, h - bh)
+    return img, np.stack([x1, y1, x1 + bw, y1 + bh], axis=1).astype(np.float32)
+
+
+def make_roi_set(n=N_ROI, c=C_ROI, seed=0, n_fg=200, n_cls=8):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, c, generator=g, dtype=torch.float32)
+    base = torch.full((1024,), n_cls, dtype=torch.int64)
+    idx = torch.randperm(1024, generator=g)[:n_fg]
+    base[idx] = torch.randint(0, n_cls, (n_fg,), generator=g)
+    return x, torch.cat([base, base]).view(-1, 1)
+
+
+def workload_config(n_gpus):
+    return {'workload': 'oamix(2x1024x2048x3 u8, 8 gt/img, version=augmix) + '
+                        'contrastive_loss_plus fwd+bwd([2088,256] f32, T=0.06) per GPU step',
+            'imgs_per_gpu': BS, 'frame': [H, W, 3], 'gt_per_img': N_GT, 'rois': [N_ROI, C_ROI],
+            'sharding': 'by image, %d rank(s), no data-path collective' % n_gpus,
+            'l2': 'inputs larger than L2: %d distinct source frames (%.0f MB) cycled' % (POOL, POOL * H * W * 3 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_oamix_worker(job):
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import oamix_np
+    seed, plan_seed = job
+    img, gt = make_image(seed)
+    np.random.seed(plan_seed)
+    t0 = time.perf_counter()
+    oamix_np.oamix_view(img, gt, **{k: v for k, v in OAMIX_CFG.items() if k not in ('num_views', 'keep_orig', 'severity')})
+    return time.perf_counter() - t0
+
+
+def cpu_reference_round(pool, cores, round_idx, loss_inputs):
+    """One bounded sample: `cores` frames through the CPU OA-Mix (one per worker) + one CPU OA-Loss
+    forward/backward.  Returns (images, oamix_wall_s, loss_s)."""
+    from oracle import supcon_np
+    jobs = [((round_idx * cores + i) % 4, 1000 + round_idx * cores + i) for i in range(cores)]
+    t0 = time.perf_counter()
+    pool.map(_cpu_oamix_worker, jobs)
+    t_mix = time.perf_counter() - t0
+    x, labels = loss_inputs
+    t0 = time.perf_counter()
+    supcon_np.supcon_loss(x, labels, LOSS_CFG['temperature'], 10, LOSS_CFG['loss_weight'], dtype=np.float32, want_grad=True)
+    t_loss = time.perf_counter() - t0
+    return cores, t_mix, t_loss
+
+
+def cpu_images_per_sec(n_img, t_mix, t_loss_per_step):
+    """A step consumes BS frames and one loss evaluation: time per frame = 1/rate_mix + t_loss/BS."""
+    per_img = t_mix / n_img + t_loss_per_step / BS
+    return 1.0 / per_img
+
+
+def run_cpu_baseline(rounds, cores):
+    import multiprocessing as mp
+    x, labels = make_roi_set()
+    loss_inputs = (x.numpy(), labels.numpy())
+    ctx = mp.get_context('fork')
+    n_img, t_mix, t_loss = 0, 0.0, []
+    with ctx.Pool(cores) as pool:
+        for r in range(rounds):
+            n, tm, tl = cpu_reference_round(pool, cores, r, loss_inputs)
+            n_img += n
+            t_mix += tm
+            t_loss.append(tl)
+    return n_img, t_mix, statistics.median(t_loss)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = min(os.cpu_count() or 1, 64)
+    import multiprocessing as mp
+    x, labels = make_roi_set()
+    loss_inputs = (x.numpy(), labels.numpy())
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for r in range(args.warmup):
+            cpu_reference_round(pool, min(cores, 4), r, loss_inputs)
+        n_img, t_mix, t_loss = 0, 0.0, []
+        t_all = time.perf_counter()
+        for r in range(args.steps):
+            n, tm, tl = cpu_reference_round(pool, cores, r, loss_inputs)
+            n_img += n
+            t_mix += tm
+            t_loss.append(tl)
+        t_all = time.perf_counter() - t_all
+    value = cpu_images_per_sec(n_img, t_mix, statistics.median(t_loss))
+    sample = ('%d rounds x %d frames (1 per worker process, cv2 1 thread each) through the CPU OA-Mix port + '
+              '1 CPU OA-Loss fwd+bwd (numpy f32) per round; images/s = 1/(t_mix/frames + t_loss/%d)' %
+              (args.steps, cores, BS))
+    line = {'impl': 'reference', 'metric': 'oamix+oaloss images/sec @1024x2048 bs=2/GPU', 'value': value,
+            'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * BS / value, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u8/f32', 'data': 'synthetic', 'config': workload_config(args.gpus),
+            'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                             'oamix_s_per_img_per_core': t_mix * cores / n_img, 'loss_s': statistics.median(t_loss),
+                             'wall_s': t_all},
+            'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------
+def product_arm(args):
+    import torch
+    import torch.distributed as dist
+    from oadg_b200 import OAMix, ContrastiveLossPlus, build
+    build.build()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs (synthetic, resident in HBM) and their pinned host twins for the e2e leg
+    frames = [make_image(s) for s in range(rank * POOL, rank * POOL + POOL)]
+    gts = [g for _, g in frames]
+    host_frames = [torch.from_numpy(f).pin_memory() for f, _ in frames]
+    dev_frames = [t.to(dev) for t in host_frames]
+    x, labels = make_roi_set(seed=rank)
+    x_host = x.pin_memory()
+    x_dev = x.to(dev).requires_grad_(True)
+    labels_dev = labels.to(dev)
+    mix = OAMix(**OAMIX_CFG)
+    loss_fn = ContrastiveLossPlus(**LOSS_CFG)
+    out_bufs = [torch.empty_like(dev_frames[0]) for _ in range(BS)]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i, profile=None):
+        j = (i * BS) % POOL
+        imgs = [dev_frames[(j + b) % POOL] for b in range(BS)]
+        g = [gts[(j + b) % POOL] for b in range(BS)]
+        mix.oamix_batch(imgs, g, profile=profile, outs=out_bufs)
+        n_mix = mix.last_launches
+        x_dev.grad = None
+        loss = loss_fn(x_dev, labels_dev)
+        loss.backward()
+        return n_mix, loss
+
+    def e2e_step(i):
+        j = (i * BS) % POOL
+        views = []
+        for b in range(BS):
+            res = mix(dict(img=host_frames[(j + b) % POOL].numpy(), gt_bboxes=gts[(j + b) % POOL]))
+            views.append(res['img2'])
+        xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
+        loss = loss_fn(xd, labels_dev)
+        loss.backward()
+        return float(loss.item()), views
+
+    # ---- warm-up
+    np.random.seed(7 + rank)
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed region (device-resident inputs)
+    clocks = ClockSampler(local)
+    clocks.start()
+    np.random.seed(1000 + rank)
+    loss_fn.stats['launches'] = 0
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        n, _ = step(i)
+        launches += n
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches += loss_fn.stats['launches']
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = BS * args.steps * world / (ms_max / 1e3)
+
+    # ---- e2e through the registered plugins with host buffers
+    np.random.seed(7 + rank)
+    for i in range(2):
+        e2e_step(i)
+    np.random.seed(1000 + rank)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = BS * args.steps * world / (float(t.item()) / 1e3)
+    frame_bytes = H * W * 3
+    h2d = BS * frame_bytes + N_ROI * C_ROI * 4
+    d2h = BS * frame_bytes + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: event-instrumented replay of the same seeded plans (rank 0)
+    prof = {}
+    np.random.seed(1000 + rank)
+    for i in range(args.steps):
+        step(i, profile=prof)
+    torch.cuda.synchronize()
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    step_ms = prof.get('step_ms', 0.0)
+    achieved = prof.get('step_bytes', 0) / (step_ms / 1e3) / 1e9 if step_ms > 0 else 0.0
+    total_kernel_ms = sum(v for k, v in prof.items() if k.endswith('_ms'))
+    roofline = {'kernel': 'oadg::step_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'launches': prof.get('step_n', 0),
+                'algorithmic_bytes_per_launch': prof.get('step_bytes', 0) / max(prof.get('step_n', 1), 1),
+                'avg_launch_ms': step_ms / max(prof.get('step_n', 1), 1),
+                'share_of_oamix_kernel_time': step_ms / total_kernel_ms if total_kernel_ms else None,
+                'oamix_kernel_ms_by_kind': {k[:-3]: round(v, 4) for k, v in prof.items() if k.endswith('_ms')},
+                'oamix_launches_by_kind': {k[:-2]: v for k, v in prof.items() if k.endswith('_n')},
+                'oamix_whole_view_gbs': prof.get('view_bytes', 0) / (total_kernel_ms / 1e3) / 1e9 if total_kernel_ms else None}
+
+    # OA-Loss alone (CUDA events), for the record
+    for _ in range(3):
+        x_dev.grad = None
+        loss_fn(x_dev, labels_dev).backward()
+    e0.record(stream)
+    for _ in range(20):
+        x_dev.grad = None
+        loss_fn(x_dev, labels_dev).backward()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    loss_ms = e0.elapsed_time(e1) / 20
+    oaloss = {'fwd_bwd_ms': loss_ms, 'algorithmic_gflop': 6.0 * N_ROI * N_ROI * C_ROI / 1e9,
+              'tflops': 6.0 * N_ROI * N_ROI * C_ROI / (loss_ms / 1e3) / 1e12}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample on the host cores
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = min(os.cpu_count() or 1, 16)
+        n_img, t_mix, t_loss = run_cpu_baseline(1, cores)
+        cpu = {'value': cpu_images_per_sec(n_img, t_mix, t_loss), 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d frames (1 per worker process, cv2 1 thread each) through oracle/oamix_np.py + 1 OA-Loss '
+                         'fwd+bwd (oracle/supcon_np.py, numpy f32); images/s = 1/(t_mix/frames + t_loss/%d)' % (n_img, BS),
+               'oamix_s_per_img_per_core': t_mix * cores / n_img, 'loss_s': t_loss}
+
+    line = {'metric': 'oamix+oaloss images/sec @1024x2048 bs=2/GPU', 'value': value, 'unit': 'images/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_max / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32', 'data': 'synthetic',
+            'config': workload_config(world), 'clocks': clk,
+            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': launches, 'roofline': roofline, 'oaloss': oaloss, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        product_arm(args)
+
+
+if __name__ == '__main__':
+    main()

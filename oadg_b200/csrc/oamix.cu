@@ -223,10 +223,29 @@ mix_kernel(DevPlan P, const MixJob* __restrict__ jobs) {
     if (_e != cudaSuccess) return (int)_e; \
   } while (0)
 
+enum { kKProfile = 0, kKHist, kKLut, kKBboPass, kKBboCopy, kKStep, kKMix, kKCopy, kKinds };
+
 struct CudaBackend {
   cudaStream_t stream;
   int launches = 0;
-  int max_w = 0, max_h = 0;
+  // optional per-launch CUDA-event timing (oadg_oamix_execute_profiled)
+  bool profile = false;
+  struct Rec { int kind; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  cudaEvent_t pending = nullptr;
+  void begin() {
+    if (!profile) return;
+    cudaEventCreate(&pending);
+    cudaEventRecord(pending, stream);
+  }
+  void end(int kind) {
+    ++launches;
+    if (!profile) return;
+    cudaEvent_t b;
+    cudaEventCreate(&b);
+    cudaEventRecord(b, stream);
+    recs.push_back(Rec{kind, pending, b});
+  }
 
   int upload(void* dst, const void* src, size_t bytes) {
     BE_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
@@ -237,8 +256,9 @@ struct CudaBackend {
     return 0;
   }
   int copy(void* dst, const void* src, size_t bytes) {
+    begin();
     BE_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream));
-    ++launches;
+    end(kKCopy);
     return 0;
   }
   int profiles(const DevPlan& P, const PlanView& pv, float* px, float* py) {
@@ -254,48 +274,55 @@ struct CudaBackend {
     if (smem > 200 * 1024) return OADG_E_LIMIT;
     if (smem > 48 * 1024)
       BE_TRY(cudaFuncSetAttribute(profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    begin();
     profile_kernel<<<dim3(h.n_gt, 2), 256, smem, stream>>>(P, sr, px, py);
     BE_TRY(cudaGetLastError());
-    ++launches;
+    end(kKProfile);
     return 0;
   }
   int hist(const DevPlan& P, const Lane* lanes, const int32_t* ids, int n, unsigned* hist, unsigned long long* luma) {
+    begin();
     hist_kernel<<<dim3(kNumSMs * 2, n), kHistThreads, 0, stream>>>(P, lanes, ids, hist, luma);
     BE_TRY(cudaGetLastError());
-    ++launches;
+    end(kKHist);
     return 0;
   }
   int lut(const DevPlan& P, const LutJob* jobs, int n, const unsigned* hist, const unsigned long long* luma,
           uint8_t* luts) {
+    begin();
     lut_kernel<<<n, 256, 0, stream>>>(P, jobs, hist, luma, luts);
     BE_TRY(cudaGetLastError());
-    ++launches;
+    end(kKLut);
     return 0;
   }
   int bbo_pass(const DevPlan& P, const Chain* chains, int n, int j, int roi_w, int roi_h) {
+    begin();
     bbo_pass_kernel<<<dim3((roi_w + 31) / 32, (roi_h + 7) / 8, n), dim3(32, 8), 0, stream>>>(P, chains, j);
     BE_TRY(cudaGetLastError());
-    ++launches;
+    end(kKBboPass);
     return 0;
   }
   int bbo_copyback(const DevPlan& P, const Chain* chains, int n, int j, int roi_w, int roi_h) {
+    begin();
     bbo_copyback_kernel<<<dim3((roi_w + 31) / 32, (roi_h + 7) / 8, n), dim3(32, 8), 0, stream>>>(P, chains, j);
     BE_TRY(cudaGetLastError());
-    ++launches;
+    end(kKBboCopy);
     return 0;
   }
   int step(const DevPlan& P, const Lane* lanes, int n, const uint8_t* scratch, size_t frame_bytes) {
     dim3 grid((P.max_w + kStepTW - 1) / kStepTW, (P.max_h + kStepTH - 1) / kStepTH, n);
+    begin();
     step_kernel<<<grid, dim3(kStepTW, kStepTH), 0, stream>>>(P, lanes, scratch, frame_bytes);
     BE_TRY(cudaGetLastError());
-    ++launches;
+    end(kKStep);
     return 0;
   }
   int mix(const DevPlan& P, const MixJob* jobs, int n) {
     dim3 grid((P.max_w + kStepTW - 1) / kStepTW, (P.max_h + kStepTH - 1) / kStepTH, n);
+    begin();
     mix_kernel<<<grid, dim3(kStepTW, kStepTH), 0, stream>>>(P, jobs);
     BE_TRY(cudaGetLastError());
-    ++launches;
+    end(kKMix);
     return 0;
   }
 };
@@ -314,6 +341,33 @@ extern "C" int oadg_oamix_workspace_bytes(const void* plan_host, size_t plan_byt
   make_layout(pv, L);
   *out_bytes = L.total;
   return 0;
+}
+
+extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes, const uint8_t* const* src_dev,
+                                           int n_img, uint8_t* const* dst_dev, void* workspace_dev,
+                                           size_t workspace_bytes, float* ms_by_kind, int* count_by_kind,
+                                           void* stream) {
+  if (!ms_by_kind || !count_by_kind) return OADG_E_ARG;
+  CudaBackend be;
+  be.stream = (cudaStream_t)stream;
+  be.profile = true;
+  int rc = execute_plan(be, plan_host, plan_bytes, src_dev, n_img, dst_dev, workspace_dev, workspace_bytes);
+  cudaError_t e = cudaStreamSynchronize(be.stream);
+  for (int k = 0; k < kKinds; ++k) {
+    ms_by_kind[k] = 0.f;
+    count_by_kind[k] = 0;
+  }
+  for (auto& r : be.recs) {
+    float ms = 0.f;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_by_kind[r.kind] += ms;
+      ++count_by_kind[r.kind];
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (rc) return rc;
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 extern "C" int oadg_oamix_execute(const void* plan_host, size_t plan_bytes, const uint8_t* const* src_dev,

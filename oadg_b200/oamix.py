@@ -32,6 +32,9 @@ _AUG = {
 }
 
 
+PROFILE_KINDS = ('profile', 'hist', 'lut', 'bbo_pass', 'bbo_copyback', 'step', 'mix', 'copy')
+
+
 def get_aug_list(version):
     """Names of the ops of reference oa_mix.py:15-29 (same order => same np.random.choice index)."""
     if version not in _AUG:
@@ -392,8 +395,9 @@ class OAMix:
             self._ws_cache = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
         return self._ws_cache
 
-    def execute(self, jobs, imgs, outs=None, stream=None):
-        """Run the packed plans.  imgs: list of CUDA u8 HWC tensors; returns one output tensor per job."""
+    def execute(self, jobs, imgs, outs=None, stream=None, profile=None):
+        """Run the packed plans.  imgs: list of CUDA u8 HWC tensors; returns one output tensor per job.
+        ``profile`` (a dict) switches to the event-timed entry point and receives per-kernel ms / counts."""
         import ctypes
         torch = _lib.require_cuda()
         lib = _lib.load()
@@ -407,14 +411,25 @@ class OAMix:
         src = (ctypes.c_void_p * len(imgs))(*[int(t.data_ptr()) for t in imgs])
         dst = (ctypes.c_void_p * len(outs))(*[int(t.data_ptr()) for t in outs])
         s = torch.cuda.current_stream(dev) if stream is None else stream
-        n = ctypes.c_int(0)
         base = (ws.data_ptr() + 255) // 256 * 256
-        _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base,
-                                          ws.numel() - (base - ws.data_ptr()), ctypes.byref(n), s.cuda_stream))
+        room = ws.numel() - (base - ws.data_ptr())
+        if profile is not None:
+            ms = (ctypes.c_float * 8)()
+            cnt = (ctypes.c_int * 8)()
+            _lib.check(lib.oadg_oamix_execute_profiled(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
+                                                       ms, cnt, s.cuda_stream))
+            for i, k in enumerate(PROFILE_KINDS):
+                profile[k + '_ms'] = profile.get(k + '_ms', 0.0) + float(ms[i])
+                profile[k + '_n'] = profile.get(k + '_n', 0) + int(cnt[i])
+            self.last_launches += sum(cnt)
+            return outs
+        n = ctypes.c_int(0)
+        _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
+                                          ctypes.byref(n), s.cuda_stream))
         self.last_launches += n.value
         return outs
 
-    def oamix_batch(self, imgs, gt_list, stream=None):
+    def oamix_batch(self, imgs, gt_list, stream=None, profile=None, outs=None):
         """Device fast path: one generated view per image (the ``num_views=2, keep_orig=True`` case).
 
         imgs: list of CUDA uint8 HWC tensors; gt_list: list of float32 [n,4] arrays.
@@ -431,7 +446,12 @@ class OAMix:
             vp = self._sample_head(int(img.shape[0]), int(img.shape[1]), gt)
             self._sample_tail(vp, gt, scores[i])
             jobs.append((vp, gt, i))
-        outs = self.execute(jobs, imgs, stream=stream)
+        outs = self.execute(jobs, imgs, outs=outs, stream=stream, profile=profile)
+        if profile is not None:  # algorithmic bytes of the step kernel: 1 read + 1 write of a frame per lane step
+            for vp, _, _ in jobs:
+                profile['step_bytes'] = profile.get('step_bytes', 0) + 2 * 3 * vp.h * vp.w * sum(vp.depths)
+                profile['view_bytes'] = profile.get('view_bytes', 0) + \
+                    3 * vp.h * vp.w * (2 * sum(vp.depths) + len(vp.depths) + 2)
         oamix_boxes = [np.stack(vp.oa_boxes, axis=0) for vp, _, _ in jobs]
         ml_boxes = [vp.ml_boxes for vp, _, _ in jobs]
         return outs, oamix_boxes, ml_boxes
