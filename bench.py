@@ -156,29 +156,26 @@ def cpu_images_per_sec(n_img, t_mix, t_loss_per_step):
 
 
 def run_cpu_baseline(rounds, cores):
-    import multiprocessing as mp
-    x, labels = make_roi_set()
-    loss_inputs = (x.numpy(), labels.numpy())
-    ctx = mp.get_context('fork')
-    n_img, t_mix, t_loss = 0, 0.0, []
-    with ctx.Pool(cores) as pool:
-        for r in range(rounds):
-            n, tm, tl = cpu_reference_round(pool, cores, r, loss_inputs)
-            n_img += n
-            t_mix += tm
-            t_loss.append(tl)
-    return n_img, t_mix, statistics.median(t_loss)
+    """The CPU arm runs in a fresh interpreter (never forked from the CUDA process): (n_img, t_mix, t_loss)."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(rounds),
+                          '--warmup', '0', '--cores', str(cores)], capture_output=True, text=True, timeout=600)
+    for line in out.stdout.splitlines():
+        if line.startswith('{'):
+            d = json.loads(line)['cpu_baseline']
+            n_img = rounds * d['cores']
+            return n_img, d['oamix_s_per_img_per_core'] * n_img / d['cores'], d['loss_s']
+    raise RuntimeError('cpu baseline subprocess failed: ' + out.stderr[-2000:])
 
 
 def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = min(os.cpu_count() or 1, 64)
+    cores = args.cores if args.cores > 0 else min(os.cpu_count() or 1, 64)
     import multiprocessing as mp
     x, labels = make_roi_set()
     loss_inputs = (x.numpy(), labels.numpy())
-    ctx = mp.get_context('fork')
+    ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
         for r in range(args.warmup):
             cpu_reference_round(pool, min(cores, 4), r, loss_inputs)
@@ -265,12 +262,18 @@ def product_arm(args):
         loss.backward()
         return float(loss.item()), views
 
+    def log(msg):
+        if rank == 0:
+            print('[bench] ' + msg, file=sys.stderr, flush=True)
+
+    log('inputs ready')
     # ---- warm-up
     np.random.seed(7 + rank)
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
 
+    log('warm-up done')
     # ---- timed region (device-resident inputs)
     clocks = ClockSampler(local)
     clocks.start()
@@ -294,6 +297,7 @@ def product_arm(args):
     ms_max = float(t.item())
     value = BS * args.steps * world / (ms_max / 1e3)
 
+    log('timed region done: %.3f ms/step' % (ms_max / args.steps))
     # ---- e2e through the registered plugins with host buffers
     np.random.seed(7 + rank)
     for i in range(2):
@@ -313,6 +317,7 @@ def product_arm(args):
     h2d = BS * frame_bytes + N_ROI * C_ROI * 4
     d2h = BS * frame_bytes + 4
 
+    log('e2e done')
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -342,6 +347,7 @@ def product_arm(args):
                 'oamix_launches_by_kind': {k[:-2]: v for k, v in prof.items() if k.endswith('_n')},
                 'oamix_whole_view_gbs': prof.get('view_bytes', 0) / (total_kernel_ms / 1e3) / 1e9 if total_kernel_ms else None}
 
+    log('profiled replay done')
     # OA-Loss alone (CUDA events), for the record
     for _ in range(3):
         x_dev.grad = None
@@ -357,6 +363,7 @@ def product_arm(args):
               'tflops': 6.0 * N_ROI * N_ROI * C_ROI / (loss_ms / 1e3) / 1e12}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample on the host cores
+    log('loss timing done')
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = min(os.cpu_count() or 1, 16)
@@ -384,6 +391,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cores', type=int, default=0, help='worker processes of the CPU arm (0 = min(cpu_count, 64))')
+    ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

@@ -12,6 +12,8 @@
 //
 // This file is the CUDA-core (FFMA, fp32) implementation; the similarity contraction
 // also has a tcgen05 path (oaloss_tc.cu) selected at run time.
+#include <stdlib.h>
+
 #include "oadg_common.cuh"
 
 namespace oadg {
@@ -35,6 +37,8 @@ struct LossWs {
   float* npos;       // [n]
   float* partial;    // [col_tiles][n][3]  (max, sumexp, possum)
   float* dfhat;      // [n, c] gradient wrt fhat
+  float* f_hi;       // [n, c] TF32 split of fhat for the tcgen05 path
+  float* f_lo;
   size_t bytes;
 };
 
@@ -51,6 +55,7 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
   size_t o_f = take((size_t)n * c * 4), o_i1 = take((size_t)n * 4), o_i2 = take((size_t)n * 4);
   size_t o_st = take((size_t)n * sizeof(RowStats)), o_meta = take(64), o_np = take((size_t)n * 4);
   size_t o_pa = take((size_t)col_tiles * n * 3 * 4), o_df = take((size_t)n * c * 4);
+  size_t o_hi = take((size_t)n * c * 4), o_lo = take((size_t)n * c * 4);
   w.fhat = reinterpret_cast<float*>(p + o_f);
   w.inv1 = reinterpret_cast<float*>(p + o_i1);
   w.inv2 = reinterpret_cast<float*>(p + o_i2);
@@ -59,6 +64,8 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
   w.npos = reinterpret_cast<float*>(p + o_np);
   w.partial = reinterpret_cast<float*>(p + o_pa);
   w.dfhat = reinterpret_cast<float*>(p + o_df);
+  w.f_hi = reinterpret_cast<float*>(p + o_hi);
+  w.f_lo = reinterpret_cast<float*>(p + o_lo);
   w.bytes = o;
   return w;
 }
@@ -401,9 +408,24 @@ normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dfha
 }
 
 }  // namespace
+
+// oaloss_tc.cu
+int launch_sim_fwd_tc(const float* fhat, float* hi, float* lo, const int64_t* labels, const int32_t* pair,
+                      const int* meta, int n, float inv_t, float* partial, cudaStream_t stream, int* launches);
+
 }  // namespace oadg
 
 using namespace oadg;
+
+// 1 = tcgen05 similarity (default), 0 = CUDA-core FFMA path (OADG_LOSS_TC=0)
+static int loss_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OADG_LOSS_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
 
 extern "C" int oadg_supcon_workspace_bytes(int n, int c, size_t* out_bytes) {
   if (!out_bytes || n < 0 || c <= 0) return OADG_E_ARG;
@@ -435,12 +457,21 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
   OADG_LAUNCH_CHECK();
   label_prep_kernel<<<1, 1024, 0, stream>>>(labels_dev, pair_dev, n, min_samples, w.meta, w.npos);
   OADG_LAUNCH_CHECK();
-  sim_fwd_kernel<<<dim3(col_tiles, row_tiles), 256, 0, stream>>>(w.fhat, labels_dev, pair_dev, w.meta, n, c,
-                                                                 1.f / temperature, w.partial);
+  int red_tiles = col_tiles;
+  if (loss_tc_enabled()) {
+    int rc = launch_sim_fwd_tc(w.fhat, w.f_hi, w.f_lo, labels_dev, pair_dev, w.meta, n, 1.f / temperature, w.partial,
+                               stream, &launches);
+    if (rc) return rc;
+    red_tiles = (n + 127) / 128;
+  } else {
+    sim_fwd_kernel<<<dim3(col_tiles, row_tiles), 256, 0, stream>>>(w.fhat, labels_dev, pair_dev, w.meta, n, c,
+                                                                   1.f / temperature, w.partial);
+    OADG_LAUNCH_CHECK();
+    ++launches;
+  }
+  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n, red_tiles, loss_weight, w.stats, loss_dev);
   OADG_LAUNCH_CHECK();
-  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n, col_tiles, loss_weight, w.stats, loss_dev);
-  OADG_LAUNCH_CHECK();
-  launches += 4;
+  launches += 3;
   if (launches_out) *launches_out = launches;
   return 0;
 }

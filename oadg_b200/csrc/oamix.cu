@@ -16,6 +16,7 @@
 //   mix_kernel                          1 launch   (all views)
 #include "oadg_common.cuh"
 #include "oamix_exec.h"
+#include "oamix_tile.h"
 
 namespace oadg {
 namespace {
@@ -117,13 +118,40 @@ hist_kernel(DevPlan P, const Lane* __restrict__ lanes, const int32_t* __restrict
   __syncthreads();
   const size_t npx = (size_t)V.H * V.W;
   unsigned long long lsum = 0;
-  for (size_t i = (size_t)blockIdx.x * kHistThreads + tid; i < npx; i += (size_t)gridDim.x * kHistThreads) {
-    const uint8_t* p = L.in + i * 3;
-    int c0 = ldb(p), c1 = ldb(p + 1), c2 = ldb(p + 2);
-    atomicAdd(&sh[warp][c0], 1u);
-    atomicAdd(&sh[warp][256 + c1], 1u);
-    atomicAdd(&sh[warp][512 + c2], 1u);
-    lsum += (unsigned)pil_luma(c0, c1, c2);
+  unsigned* my = sh[warp];
+  if ((((uintptr_t)L.in) & 15) == 0) {
+    // 16 px = 48 B = 3 x uint4 per iteration: the channel of byte k is k % 3 at a compile-time phase
+    const size_t nchunk = npx / kChunkPx;
+    for (size_t i = (size_t)blockIdx.x * kHistThreads + tid; i < nchunk; i += (size_t)gridDim.x * kHistThreads) {
+      Chunk c;
+      chunk_load(L.in + i * 48, kChunkPx, true, c);
+#pragma unroll
+      for (int px = 0; px < kChunkPx; ++px) {
+        const int c0 = chunk_get(c, px * 3), c1 = chunk_get(c, px * 3 + 1), c2 = chunk_get(c, px * 3 + 2);
+        atomicAdd(&my[c0], 1u);
+        atomicAdd(&my[256 + c1], 1u);
+        atomicAdd(&my[512 + c2], 1u);
+        lsum += (unsigned)pil_luma(c0, c1, c2);
+      }
+    }
+    for (size_t i = nchunk * kChunkPx + (size_t)blockIdx.x * kHistThreads + tid; i < npx;
+         i += (size_t)gridDim.x * kHistThreads) {
+      const uint8_t* p = L.in + i * 3;
+      int c0 = ldb(p), c1 = ldb(p + 1), c2 = ldb(p + 2);
+      atomicAdd(&my[c0], 1u);
+      atomicAdd(&my[256 + c1], 1u);
+      atomicAdd(&my[512 + c2], 1u);
+      lsum += (unsigned)pil_luma(c0, c1, c2);
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * kHistThreads + tid; i < npx; i += (size_t)gridDim.x * kHistThreads) {
+      const uint8_t* p = L.in + i * 3;
+      int c0 = ldb(p), c1 = ldb(p + 1), c2 = ldb(p + 2);
+      atomicAdd(&my[c0], 1u);
+      atomicAdd(&my[256 + c1], 1u);
+      atomicAdd(&my[512 + c2], 1u);
+      lsum += (unsigned)pil_luma(c0, c1, c2);
+    }
   }
   __syncthreads();
   unsigned* dst = hist + (size_t)L.hist_slot * 768;
@@ -195,26 +223,64 @@ bbo_copyback_kernel(DevPlan P, const Chain* __restrict__ chains, int j) {
   C.S[o + 2] = C.T[o + 2];
 }
 
-constexpr int kStepTW = 32, kStepTH = 8;
+// ------------------------------------------------------------------------------------
+// one depth step of every live lane (oa_mix.py:226-234).  A CTA owns a 512 x 32 pixel tile: it classifies the
+// tile once (uniform op or region border; gt masks that can be non-zero), stages the op's LUT in shared memory,
+// then each warp streams rows: LUT / copy tiles as 16-pixel chunks (3 x 16-byte vectors per thread), bg-only
+// tiles lane-per-pixel so that the 4-tap gathers of a warp stay within a few cache lines.
+// grid = (ceil(W/512), ceil(H/32), lanes)
+// ------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
 
-__global__ void __launch_bounds__(kStepTW * kStepTH)
+__global__ void __launch_bounds__(kTileThreads)
 step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict__ scratch, size_t frame_bytes) {
+  __shared__ TileInfo T;
+  __shared__ __align__(16) uint8_t lut_s[768];
   const Lane L = lanes[blockIdx.z];
   const oadg_view_t& V = P.views[L.view];
-  const int x = blockIdx.x * kStepTW + threadIdx.x;
-  const int y = blockIdx.y * kStepTH + threadIdx.y;
-  if (x >= V.W || y >= V.H) return;
-  step_pixel(P, L, scratch, frame_bytes, x, y);
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  if (x0 >= V.W || y0 >= V.H) return;
+  const int x1 = min(x0 + kTileW, V.W), y1 = min(y0 + kTileH, V.H);
+  if (threadIdx.x == 0) classify_step_tile(P, L, x0, y0, x1, y1, T);
+  __syncthreads();
+  const bool lut_tile = T.mode == 0 && is_lut_kind(P.ops[T.op].kind);
+  if (lut_tile) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.luts + (size_t)P.ops[T.op].lut * 768);
+    if (threadIdx.x < 192) reinterpret_cast<uint32_t*>(lut_s)[threadIdx.x] = __ldg(src + threadIdx.x);
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = ((V.W * 3) & 15) == 0 && ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
+  if (tile_is_bg(P, T)) {
+    for (int y = y0 + warp; y < y1; y += kTileThreads / 32)
+      for (int x = x0 + lane; x < x1; x += 32) bg_pixel_cand(P, L, T, x, y);
+    return;
+  }
+  const int x = x0 + lane * kChunkPx;
+  if (x >= x1) return;
+  const int n = min(kChunkPx, x1 - x);
+  for (int y = y0 + warp; y < y1; y += kTileThreads / 32) step_chunk(P, L, T, lut_s, scratch, frame_bytes, x, y, n, vec);
 }
 
-__global__ void __launch_bounds__(kStepTW * kStepTH)
+// branch mixing + object-aware mixing (oa_mix.py:236,281-309), same tiling; grid = (.., .., views)
+__global__ void __launch_bounds__(kTileThreads)
 mix_kernel(DevPlan P, const MixJob* __restrict__ jobs) {
+  __shared__ MixTile T;
   const MixJob J = jobs[blockIdx.z];
   const oadg_view_t& V = P.views[J.view];
-  const int x = blockIdx.x * kStepTW + threadIdx.x;
-  const int y = blockIdx.y * kStepTH + threadIdx.y;
-  if (x >= V.W || y >= V.H) return;
-  mix_pixel(P, J, x, y);
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  if (x0 >= V.W || y0 >= V.H) return;
+  const int x1 = min(x0 + kTileW, V.W), y1 = min(y0 + kTileH, V.H);
+  if (threadIdx.x == 0) classify_mix_tile(P, J, x0, y0, x1, y1, T);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uintptr_t al = ((uintptr_t)J.src) | ((uintptr_t)J.out);
+  for (int b = 0; b < V.width; ++b) al |= (uintptr_t)J.branch[b];
+  const bool vec = ((V.W * 3) & 15) == 0 && (al & 15) == 0;
+  const int x = x0 + lane * kChunkPx;
+  if (x >= x1) return;
+  const int n = min(kChunkPx, x1 - x);
+  for (int y = y0 + warp; y < y1; y += kTileThreads / 32) mix_chunk(P, J, T, x, y, n, vec);
 }
 
 #define BE_TRY(expr)                       \
@@ -310,17 +376,17 @@ struct CudaBackend {
     return 0;
   }
   int step(const DevPlan& P, const Lane* lanes, int n, const uint8_t* scratch, size_t frame_bytes) {
-    dim3 grid((P.max_w + kStepTW - 1) / kStepTW, (P.max_h + kStepTH - 1) / kStepTH, n);
+    dim3 grid((P.max_w + kTileW - 1) / kTileW, (P.max_h + kTileH - 1) / kTileH, n);
     begin();
-    step_kernel<<<grid, dim3(kStepTW, kStepTH), 0, stream>>>(P, lanes, scratch, frame_bytes);
+    step_kernel<<<grid, kTileThreads, 0, stream>>>(P, lanes, scratch, frame_bytes);
     BE_TRY(cudaGetLastError());
     end(kKStep);
     return 0;
   }
   int mix(const DevPlan& P, const MixJob* jobs, int n) {
-    dim3 grid((P.max_w + kStepTW - 1) / kStepTW, (P.max_h + kStepTH - 1) / kStepTH, n);
+    dim3 grid((P.max_w + kTileW - 1) / kTileW, (P.max_h + kTileH - 1) / kTileH, n);
     begin();
-    mix_kernel<<<grid, dim3(kStepTW, kStepTH), 0, stream>>>(P, jobs);
+    mix_kernel<<<grid, kTileThreads, 0, stream>>>(P, jobs);
     BE_TRY(cudaGetLastError());
     end(kKMix);
     return 0;

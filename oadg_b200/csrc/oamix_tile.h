@@ -1,0 +1,277 @@
+// Tile-level bodies of the OA-Mix step / mix kernels: a CTA owns a kTileW x kTileH pixel tile, classifies it
+// once (which region/op covers it, which gt masks can be non-zero there) and then streams 16-pixel chunks
+// (48 bytes = three 16-byte vectors) per thread.  Shared with tests/hostsim (test infrastructure only).
+#pragma once
+#include <string.h>
+
+#include "oamix_body.h"
+
+namespace oadg {
+
+constexpr int kChunkPx = 16;  // 16 px * 3 B = 48 B = 3 x uint4: the smallest pixel run that is 16-byte periodic
+constexpr int kTileW = 512;   // 32 lanes x 16 px
+constexpr int kTileH = 32;    // 8 warps x 4 rows
+constexpr int kMaxCand = 12;
+
+struct Chunk {
+  uint32_t w[12];
+};
+
+OADG_HD void chunk_load(const uint8_t* p, int n, bool vec, Chunk& c) {
+#ifdef __CUDA_ARCH__
+  if (vec && n == kChunkPx) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2);
+    c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
+    c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
+    c.w[8] = d.x; c.w[9] = d.y; c.w[10] = d.z; c.w[11] = d.w;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (i * 4 + b < n * 3) v |= (uint32_t)__ldg(p + i * 4 + b) << (8 * b);
+    c.w[i] = v;
+  }
+#else
+  (void)vec;
+  memset(c.w, 0, sizeof(c.w));
+  memcpy(c.w, p, (size_t)n * 3);
+#endif
+}
+
+OADG_HD void chunk_store(uint8_t* p, int n, bool vec, const Chunk& c) {
+#ifdef __CUDA_ARCH__
+  if (vec && n == kChunkPx) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(c.w[0], c.w[1], c.w[2], c.w[3]);
+    q[1] = make_uint4(c.w[4], c.w[5], c.w[6], c.w[7]);
+    q[2] = make_uint4(c.w[8], c.w[9], c.w[10], c.w[11]);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (i * 4 + b < n * 3) p[i * 4 + b] = (uint8_t)(c.w[i] >> (8 * b));
+#else
+  (void)vec;
+  memcpy(p, c.w, (size_t)n * 3);
+#endif
+}
+
+// byte k (0..47) of a chunk; k must be a compile-time constant after unrolling for register residency
+OADG_HD int chunk_get(const Chunk& c, int k) { return (int)((c.w[k >> 2] >> ((k & 3) * 8)) & 255u); }
+
+struct TileInfo {
+  int32_t mode;  // 0: one op covers the tile (op = global op index), 1: several regions meet in the tile
+  int32_t op;
+  int32_t n_center, n_taps;  // gt boxes whose mask can be non-zero at the pixel / at the warped taps
+  int32_t overflow;          // more than kMaxCand candidates: evaluate every gt of the view
+  int32_t center[kMaxCand], taps[kMaxCand];
+};
+
+OADG_HD bool rect_hit(const int32_t* s, int x0, int y0, int x1, int y1) {
+  return s[0] < x1 && s[2] > x0 && s[1] < y1 && s[3] > y0;
+}
+
+// classify the tile [x0,x1) x [y0,y1) of lane L
+OADG_HD void classify_step_tile(const DevPlan& P, const Lane& L, int x0, int y0, int x1, int y1, TileInfo& T) {
+  const oadg_view_t& V = P.views[L.view];
+  int region = V.n_ml;
+  bool mixed = false;
+  for (int b = 0; b < V.n_ml; ++b) {
+    const int32_t* B = V.ml_box[b];
+    if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;     // disjoint
+    if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = b;  // tile inside box b
+    else mixed = true;
+  }
+  T.mode = mixed ? 1 : 0;
+  T.op = L.op_base + region;
+  T.n_center = T.n_taps = 0;
+  T.overflow = 0;
+  if (mixed) return;
+  const oadg_op_t& op = P.ops[T.op];
+  if (op.kind != OADG_OP_BG_AFFINE) return;
+  // source footprint of the tile under the inverse affine map: extremes sit at the corners; +-2 px of slack
+  // covers the fixed-point rounding and the second bilinear tap
+  double minv[6];
+  for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
+  int fx0 = 1 << 30, fy0 = 1 << 30, fx1 = -(1 << 30), fy1 = -(1 << 30);
+  for (int c = 0; c < 4; ++c) {
+    int xx = (c & 1) ? x1 - 1 : x0, yy = (c & 2) ? y1 - 1 : y0;
+    WarpTap t = warp_px(minv, warp_row(minv, yy), xx);
+    fx0 = imin(fx0, t.sx); fx1 = imax(fx1, t.sx);
+    fy0 = imin(fy0, t.sy); fy1 = imax(fy1, t.sy);
+  }
+  fx0 -= 2; fy0 -= 2; fx1 += 4; fy1 += 4;
+  for (int k = 0; k < V.n_gt; ++k) {
+    const int g = V.gt_first + k;
+    const int32_t* s = P.gts[g].supp;
+    if (rect_hit(s, x0, y0, x1, y1)) {
+      if (T.n_center < kMaxCand) T.center[T.n_center++] = g;
+      else T.overflow = 1;
+    }
+    if (rect_hit(s, fx0, fy0, fx1, fy1)) {
+      if (T.n_taps < kMaxCand) T.taps[T.n_taps++] = g;
+      else T.overflow = 1;
+    }
+  }
+}
+
+OADG_HD float union_mask_cand(const DevPlan& P, const int32_t* cand, int n, int x, int y) {
+  float m = 0.f;
+  for (int k = 0; k < n; ++k) {
+    float v = fg_mask(P, cand[k], x, y);
+    m = v > m ? v : m;
+  }
+  return m;
+}
+
+// One pixel of a tile that a bg-only op covers entirely, with the tile's candidate gt lists
+// (bbox_augmentation.py:240-272).  Lane-per-pixel mapping: the 4-tap gathers of a warp stay within a few lines.
+OADG_HD void bg_pixel_cand(const DevPlan& P, const Lane& L, const TileInfo& T, int x, int y) {
+  const oadg_view_t& V = P.views[L.view];
+  const oadg_op_t& op = P.ops[T.op];
+  double minv[6];
+  for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
+  const WarpTap t = warp_px(minv, warp_row(minv, y), x);
+  int px[3];
+  warp_fetch3(LdRO(), L.in, V.H, V.W, t, px);
+  const size_t o = ((size_t)y * V.W + x) * 3;
+  if ((T.n_center | T.n_taps) != 0) {
+    const float M = union_mask_cand(P, T.center, T.n_center, x, y);
+    int mk[4];
+    for (int c = 0; c < 4; ++c) {
+      int xx = t.sx + (c & 1), yy = t.sy + (c >> 1);
+      mk[c] = ((unsigned)xx < (unsigned)V.W && (unsigned)yy < (unsigned)V.H)
+                  ? mask_to_u8(union_mask_cand(P, T.taps, T.n_taps, xx, yy)) : 0;
+    }
+    const int wm = bilerp_fix(mk[0], mk[1], mk[2], mk[3], t.fx, t.fy);
+    if (M != 0.f || wm != 0)  // keep == 0 => 0*img + 1*aug == aug exactly
+      for (int c = 0; c < 3; ++c) px[c] = bg_blend(M, wm, ldb(L.in + o + c), px[c]);
+  }
+  uint8_t* q = L.out + o;
+  q[0] = (uint8_t)px[0];
+  q[1] = (uint8_t)px[1];
+  q[2] = (uint8_t)px[2];
+}
+OADG_HD bool tile_is_bg(const DevPlan& P, const TileInfo& T) {
+  return T.mode == 0 && !T.overflow && P.ops[T.op].kind == OADG_OP_BG_AFFINE;
+}
+
+// 16 pixels of one depth step.  `lut` points at the 3x256 table of the tile's op when it is a LUT op
+// (shared memory on the device).
+OADG_HD void step_chunk(const DevPlan& P, const Lane& L, const TileInfo& T, const uint8_t* lut,
+                        const uint8_t* scratch, size_t frame_bytes, int x, int y, int n, bool vec) {
+  const oadg_view_t& V = P.views[L.view];
+  const size_t o = ((size_t)y * V.W + x) * 3;
+  Chunk out;
+  if (T.mode == 0) {
+    const oadg_op_t& op = P.ops[T.op];
+    const int kind = op.kind;
+    if (is_lut_kind(kind)) {
+      Chunk in;
+      chunk_load(L.in + o, n, vec, in);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int i = 0; i < 12; ++i) {
+        uint32_t v = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int b = 0; b < 4; ++b) {
+          const int k = i * 4 + b;
+          v |= (uint32_t)lut[(k % 3) * 256 + chunk_get(in, k)] << (8 * b);
+        }
+        out.w[i] = v;
+      }
+      chunk_store(L.out + o, n, vec, out);
+      return;
+    }
+    if (kind == OADG_OP_BBO_AFFINE) {
+      const uint8_t* s = op.scratch >= 0 ? scratch + (size_t)op.scratch * frame_bytes : L.in;
+      chunk_load(s + o, n, vec, out);
+      chunk_store(L.out + o, n, vec, out);
+      return;
+    }
+  }
+  // generic (region borders, invert / color / sharpness, candidate overflow): per pixel, byte stores
+  for (int i = 0; i < n; ++i) step_pixel(P, L, scratch, frame_bytes, x + i, y);
+}
+
+// ---- mix ------------------------------------------------------------------------------------------
+struct MixTile {
+  int32_t n;          // object-aware targets that can be non-zero in the tile, in plan order
+  int32_t overflow;   // more than kMaxCand: walk every target
+  int32_t idx[kMaxCand];
+};
+
+OADG_HD void classify_mix_tile(const DevPlan& P, const MixJob& J, int x0, int y0, int x1, int y1, MixTile& T) {
+  const oadg_view_t& V = P.views[J.view];
+  T.n = 0;
+  T.overflow = 0;
+  for (int t = 0; t < V.n_tgt; ++t) {
+    const oadg_target_t& G = P.tgts[V.tgt_first + t];
+    const int32_t* s = G.kind == 0 ? P.gts[G.gt].supp : G.box;
+    if (!rect_hit(s, x0, y0, x1, y1)) continue;
+    if (T.n < kMaxCand) T.idx[T.n++] = V.tgt_first + t;
+    else T.overflow = 1;
+  }
+}
+
+OADG_HD void mix_chunk(const DevPlan& P, const MixJob& J, const MixTile& T, int x, int y, int n, bool vec) {
+  const oadg_view_t& V = P.views[J.view];
+  const size_t o = ((size_t)y * V.W + x) * 3;
+  if (T.overflow) {
+    for (int i = 0; i < n; ++i) mix_pixel(P, J, x + i, y);
+    return;
+  }
+  Chunk src, out;
+  chunk_load(J.src + o, n, vec, src);
+  float acc[kChunkPx * 3];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int k = 0; k < kChunkPx * 3; ++k) acc[k] = 0.f;
+  for (int b = 0; b < V.width; ++b) {
+    Chunk br;
+    chunk_load(J.branch[b] + o, n, vec, br);
+    const float wgt = V.ws[b];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < kChunkPx * 3; ++k) acc[k] = fadd(acc[k], fmul(wgt, (float)chunk_get(br, k)));
+  }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < kChunkPx; ++i) {
+    float orig[3] = {0.f, 0.f, 0.f}, aug[3] = {0.f, 0.f, 0.f};
+    MixMask ms = {0.f, 0.f};
+    const int img[3] = {chunk_get(src, i * 3), chunk_get(src, i * 3 + 1), chunk_get(src, i * 3 + 2)};
+    if (i < n) {
+      for (int t = 0; t < T.n; ++t) {
+        const oadg_target_t& G = P.tgts[T.idx[t]];
+        float mask;
+        if (G.kind == 0) mask = fg_mask(P, G.gt, x + i, y);
+        else mask = (x + i >= G.box[0] && x + i < G.box[2] && y >= G.box[1] && y < G.box[3]) ? 1.f : 0.f;
+        if (mask == 0.f) continue;
+        const float w = mix_target_weight(ms, mask);
+        for (int c = 0; c < 3; ++c) mix_accumulate(orig[c], aug[c], G.m_oa, img[c], acc[i * 3 + c], w);
+      }
+    }
+    for (int c = 0; c < 3; ++c) {
+      const int k = i * 3 + c;
+      const uint32_t v = (uint32_t)mix_finish(orig[c], aug[c], V.m, img[c], acc[k], ms.sum);
+      if ((k & 3) == 0) out.w[k >> 2] = v;
+      else out.w[k >> 2] |= v << ((k & 3) * 8);
+    }
+  }
+  chunk_store(J.out + o, n, vec, out);
+}
+
+}  // namespace oadg

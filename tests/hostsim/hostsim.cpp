@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "oamix_exec.h"
+#include "oamix_tile.h"
 
 using namespace oadg;
 
@@ -150,11 +151,26 @@ struct HostBackend {
     ++launches;
     return 0;
   }
+  // mirrors step_kernel: 512 x 32 tiles, classify once, LUT / copy tiles in 16-px chunks, bg tiles per pixel
   int step(const DevPlan& P, const Lane* lanes, int n, const uint8_t* scratch, size_t frame_bytes) {
     for (int k = 0; k < n; ++k) {
-      const oadg_view_t& V = P.views[lanes[k].view];
-      for (int y = 0; y < V.H; ++y)
-        for (int x = 0; x < V.W; ++x) step_pixel(P, lanes[k], scratch, frame_bytes, x, y);
+      const Lane& L = lanes[k];
+      const oadg_view_t& V = P.views[L.view];
+      for (int y0 = 0; y0 < V.H; y0 += kTileH)
+        for (int x0 = 0; x0 < V.W; x0 += kTileW) {
+          const int x1 = imin(x0 + kTileW, V.W), y1 = imin(y0 + kTileH, V.H);
+          TileInfo T;
+          classify_step_tile(P, L, x0, y0, x1, y1, T);
+          const uint8_t* lut = (T.mode == 0 && is_lut_kind(P.ops[T.op].kind)) ? P.luts + (size_t)P.ops[T.op].lut * 768 : nullptr;
+          for (int y = y0; y < y1; ++y) {
+            if (tile_is_bg(P, T)) {
+              for (int x = x0; x < x1; ++x) bg_pixel_cand(P, L, T, x, y);
+            } else {
+              for (int x = x0; x < x1; x += kChunkPx)
+                step_chunk(P, L, T, lut, scratch, frame_bytes, x, y, imin(kChunkPx, x1 - x), true);
+            }
+          }
+        }
     }
     ++launches;
     return 0;
@@ -162,8 +178,14 @@ struct HostBackend {
   int mix(const DevPlan& P, const MixJob* jobs, int n) {
     for (int k = 0; k < n; ++k) {
       const oadg_view_t& V = P.views[jobs[k].view];
-      for (int y = 0; y < V.H; ++y)
-        for (int x = 0; x < V.W; ++x) mix_pixel(P, jobs[k], x, y);
+      for (int y0 = 0; y0 < V.H; y0 += kTileH)
+        for (int x0 = 0; x0 < V.W; x0 += kTileW) {
+          const int x1 = imin(x0 + kTileW, V.W), y1 = imin(y0 + kTileH, V.H);
+          MixTile T;
+          classify_mix_tile(P, jobs[k], x0, y0, x1, y1, T);
+          for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; x += kChunkPx) mix_chunk(P, jobs[k], T, x, y, imin(kChunkPx, x1 - x), true);
+        }
     }
     ++launches;
     return 0;

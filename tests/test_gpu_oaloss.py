@@ -85,3 +85,26 @@ def test_property_invariances(cuda):
     idx = torch.cat([perm, perm + 1024, torch.arange(2048, 2088)])
     l2, _, _ = _run(cuda, x[idx], labels[torch.cat([perm, perm + 1024])])
     assert abs(l0.item() - l2.item()) <= 1e-5 * abs(l0.item())
+
+
+def test_cuda_core_path_agrees_with_tensor_core_path(cuda):
+    """OADG_LOSS_TC=0 selects the FFMA similarity kernels; both must meet the same tolerance."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch
+from oracle import supcon_np, synth
+from oadg_b200 import ContrastiveLossPlus
+x, labels = synth.make_roi_set(2088)
+xd = x.cuda().requires_grad_(True)
+loss = ContrastiveLossPlus(loss_weight=0.01, num_views=2, temperature=0.06)(xd, labels.cuda()); loss.backward()
+ref, gref = supcon_np.supcon_loss(x.numpy(), labels.numpy(), 0.06, 10, 0.01, want_grad=True)
+assert abs(loss.item() - ref) <= 1e-5 * abs(ref), (loss.item(), ref)
+assert np.linalg.norm(xd.grad.cpu().numpy() - gref) <= 1e-5 * np.linalg.norm(gref)
+print("FFMA-OK", loss.item())
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-c', code], cwd=root, capture_output=True, text=True,
+                         env=dict(os.environ, PYTHONPATH=root, OADG_LOSS_TC='0'))
+    assert 'FFMA-OK' in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
