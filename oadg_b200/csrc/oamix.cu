@@ -11,7 +11,7 @@
 //   profile_kernel                      1 launch   (all boxes of all views)
 //   for depth d:  hist_kernel           <=1 launch (lanes whose step needs a histogram)
 //                 lut_kernel            <=1 launch
-//                 bbo_pass/copyback     2 per chained gt box (bboxes-only ops, ROI-limited)
+//                 bbo_pass_kernel       1 per chained gt box (bboxes-only ops, ROI-limited, ping-pong frames)
 //                 step_kernel           1 launch   (all (view, branch) lanes alive at depth d)
 //   mix_kernel                          1 launch   (all views)
 #include "oadg_common.cuh"
@@ -195,32 +195,19 @@ lut_kernel(DevPlan P, const LutJob* __restrict__ jobs, const unsigned* __restric
 
 // ------------------------------------------------------------------------------------
 // bboxes-only chains (bbox_augmentation.py:74-88): box j of every active chain.
-// pass: T[roi] = blend(S, warp_j(S), m_j) ; copyback: S[roi] = T[roi].
+// pass j: Y[roi_j] = blend(X, warp_j(X), m_j), Y[roi_{j-1} \\ roi_j] = X  with (X, Y) = (S, T) swapping per box.
 // grid = (ceil(max_roi_w/32), ceil(max_roi_h/8), chains)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bbo_pass_kernel(DevPlan P, const Chain* __restrict__ chains, int j) {
   const Chain C = chains[blockIdx.z];
   if (j >= C.n) return;
-  const oadg_gt_t& G = P.gts[P.bbo[C.bbo_first + j].gt];
-  const int x = G.supp[0] + blockIdx.x * 32 + threadIdx.x;
-  const int y = G.supp[1] + blockIdx.y * 8 + threadIdx.y;
-  if (x >= G.supp[2] || y >= G.supp[3]) return;
+  int r[4];
+  bbo_pass_rect(P, C, j, r);
+  const int x = r[0] + blockIdx.x * 32 + threadIdx.x;
+  const int y = r[1] + blockIdx.y * 8 + threadIdx.y;
+  if (x >= r[2] || y >= r[3]) return;
   bbo_pixel(P, C, j, x, y);
-}
-__global__ void __launch_bounds__(256)
-bbo_copyback_kernel(DevPlan P, const Chain* __restrict__ chains, int j) {
-  const Chain C = chains[blockIdx.z];
-  if (j >= C.n) return;
-  const oadg_gt_t& G = P.gts[P.bbo[C.bbo_first + j].gt];
-  const oadg_view_t& V = P.views[C.view];
-  const int x = G.supp[0] + blockIdx.x * 32 + threadIdx.x;
-  const int y = G.supp[1] + blockIdx.y * 8 + threadIdx.y;
-  if (x >= G.supp[2] || y >= G.supp[3]) return;
-  const size_t o = ((size_t)y * V.W + x) * 3;
-  C.S[o] = C.T[o];
-  C.S[o + 1] = C.T[o + 1];
-  C.S[o + 2] = C.T[o + 2];
 }
 
 // ------------------------------------------------------------------------------------
@@ -235,7 +222,7 @@ constexpr int kTileThreads = 256;
 __global__ void __launch_bounds__(kTileThreads)
 step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict__ scratch, size_t frame_bytes) {
   __shared__ TileInfo T;
-  __shared__ __align__(16) uint8_t lut_s[768];
+  __shared__ __align__(16) uint8_t lut_s[OADG_MAX_REGIONS * 768];
   const Lane L = lanes[blockIdx.z];
   const oadg_view_t& V = P.views[L.view];
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -243,19 +230,21 @@ step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict
   const int x1 = min(x0 + kTileW, V.W), y1 = min(y0 + kTileH, V.H);
   if (threadIdx.x == 0) classify_step_tile(P, L, x0, y0, x1, y1, T);
   __syncthreads();
-  const bool lut_tile = T.mode == 0 && is_lut_kind(P.ops[T.op].kind);
-  if (lut_tile) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.luts + (size_t)P.ops[T.op].lut * 768);
-    if (threadIdx.x < 192) reinterpret_cast<uint32_t*>(lut_s)[threadIdx.x] = __ldg(src + threadIdx.x);
-    __syncthreads();
-  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool vec = ((V.W * 3) & 15) == 0 && ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
-  if (tile_is_bg(P, T)) {
+  if (T.any_bg) {
+    // lane-per-pixel mapping: the 4-tap gathers of a warp stay within a few cache lines
     for (int y = y0 + warp; y < y1; y += kTileThreads / 32)
-      for (int x = x0 + lane; x < x1; x += 32) bg_pixel_cand(P, L, T, x, y);
+      for (int x = x0 + lane; x < x1; x += 32) step_pixel_cand(P, L, T, scratch, frame_bytes, x, y);
     return;
   }
+  for (int r = 0; r <= V.n_ml; ++r) {
+    if (!T.R[r].present || !is_lut_kind(P.ops[T.R[r].op].kind)) continue;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.luts + (size_t)P.ops[T.R[r].op].lut * 768);
+    if (threadIdx.x < 192) reinterpret_cast<uint32_t*>(lut_s + r * 768)[threadIdx.x] = __ldg(src + threadIdx.x);
+  }
+  __syncthreads();
+  const bool vec = ((V.W * 3) & 15) == 0 &&
+                   ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
   const int x = x0 + lane * kChunkPx;
   if (x >= x1) return;
   const int n = min(kChunkPx, x1 - x);
@@ -366,13 +355,6 @@ struct CudaBackend {
     bbo_pass_kernel<<<dim3((roi_w + 31) / 32, (roi_h + 7) / 8, n), dim3(32, 8), 0, stream>>>(P, chains, j);
     BE_TRY(cudaGetLastError());
     end(kKBboPass);
-    return 0;
-  }
-  int bbo_copyback(const DevPlan& P, const Chain* chains, int n, int j, int roi_w, int roi_h) {
-    begin();
-    bbo_copyback_kernel<<<dim3((roi_w + 31) / 32, (roi_h + 7) / 8, n), dim3(32, 8), 0, stream>>>(P, chains, j);
-    BE_TRY(cudaGetLastError());
-    end(kKBboCopy);
     return 0;
   }
   int step(const DevPlan& P, const Lane* lanes, int n, const uint8_t* scratch, size_t frame_bytes) {

@@ -35,8 +35,8 @@ struct Lane {            // one (view, branch) chain alive at the current depth
 struct Chain {           // one bboxes-only op being evaluated (sequential over its boxes)
   int32_t view, n;       // n = boxes in the chain
   int32_t bbo_first, lane;
-  uint8_t* S;            // running full frame (starts as a copy of the lane input)
-  uint8_t* T;            // ROI staging
+  uint8_t* S;            // ping-pong frames, both start as copies of the lane input;
+  uint8_t* T;            // after n boxes the result is in T when n is odd, in S when n is even
 };
 
 struct MixJob {
@@ -94,23 +94,51 @@ OADG_HD uint8_t lut_simple_at(const oadg_op_t& op, int i, double luma_sum, doubl
 }
 
 // ---- one pixel of box j of a bboxes-only chain (bbox_augmentation.py:57-71) ----------
+// The chain ping-pongs between two full frames: pass j reads X (complete image after j-1 boxes) and writes
+// Y = X with box j blended in.  Y is one pass behind, so the pixels of box j-1's support that box j does not
+// touch are copied across as well; then Y is the complete image after j boxes and no copy-back launch is needed.
 OADG_HD void bbo_pixel(const DevPlan& P, const Chain& C, int j, int x, int y) {
+  const uint8_t* X = (j & 1) ? C.T : C.S;
+  uint8_t* Y = (j & 1) ? C.S : C.T;
   const oadg_bbo_t& B = P.bbo[C.bbo_first + j];
+  const oadg_gt_t& G = P.gts[B.gt];
   const oadg_view_t& V = P.views[C.view];
   const size_t o = ((size_t)y * V.W + x) * 3;
+  const bool in_cur = x >= G.supp[0] && x < G.supp[2] && y >= G.supp[1] && y < G.supp[3];
+  if (!in_cur) {
+    if (j == 0) return;
+    const int32_t* s = P.gts[P.bbo[C.bbo_first + j - 1].gt].supp;
+    if (!(x >= s[0] && x < s[2] && y >= s[1] && y < s[3])) return;
+    Y[o] = X[o];
+    Y[o + 1] = X[o + 1];
+    Y[o + 2] = X[o + 2];
+    return;
+  }
   const float m = fmul(OADG_LDG(P.prof_y + (size_t)B.gt * P.max_h + y), OADG_LDG(P.prof_x + (size_t)B.gt * P.max_w + x));
-  int v[3] = {C.S[o], C.S[o + 1], C.S[o + 2]};
+  int v[3] = {X[o], X[o + 1], X[o + 2]};
   if (m != 0.f) {  // m == 0 => img*1 + aug*0 == img exactly
     double minv[6];
     for (int i = 0; i < 6; ++i) minv[i] = B.minv[i];
     WarpTap t = warp_px(minv, warp_row(minv, y), x);
     int a[3];
-    warp_fetch3(LdRW(), C.S, V.H, V.W, t, a);
+    warp_fetch3(LdRW(), X, V.H, V.W, t, a);
     for (int c = 0; c < 3; ++c) v[c] = bbo_blend(m, v[c], a[c]);
   }
-  C.T[o] = (uint8_t)v[0];
-  C.T[o + 1] = (uint8_t)v[1];
-  C.T[o + 2] = (uint8_t)v[2];
+  Y[o] = (uint8_t)v[0];
+  Y[o + 1] = (uint8_t)v[1];
+  Y[o + 2] = (uint8_t)v[2];
+}
+// bounding rect of (support of box j) U (support of box j-1): the pixels pass j may write
+OADG_HD void bbo_pass_rect(const DevPlan& P, const Chain& C, int j, int r[4]) {
+  const int32_t* s = P.gts[P.bbo[C.bbo_first + j].gt].supp;
+  r[0] = s[0]; r[1] = s[1]; r[2] = s[2]; r[3] = s[3];
+  if (j > 0) {
+    const int32_t* q = P.gts[P.bbo[C.bbo_first + j - 1].gt].supp;
+    if (q[2] > q[0] && q[3] > q[1]) {
+      if (r[2] <= r[0] || r[3] <= r[1]) { r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; r[3] = q[3]; }
+      else { r[0] = imin(r[0], q[0]); r[1] = imin(r[1], q[1]); r[2] = imax(r[2], q[2]); r[3] = imax(r[3], q[3]); }
+    }
+  }
 }
 
 // ---- one op at one pixel (oa_mix.py:264-279 dispatch) ------------------------------------

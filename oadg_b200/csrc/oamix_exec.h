@@ -157,7 +157,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
 //   upload(dst, src_host, bytes)  zero(dst, bytes)  copy(dst, src, bytes)
 //   profiles(P, pv, prof_x, prof_y)
 //   hist(P, lanes, lane_ids, n, hist, luma)   lut(P, jobs, n, hist, luma, luts)
-//   bbo_pass(P, chains, n, j, roi_w, roi_h)   bbo_copyback(P, chains, n, j, roi_w, roi_h)
+//   bbo_pass(P, chains, n, j, roi_w, roi_h)
 //   step(P, lanes, n, scratch, frame_bytes)   mix(P, jobs, n)
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
@@ -258,17 +258,24 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
             c.n = op.bbo_count;
             c.bbo_first = op.bbo_first;
             c.lane = lane_n;  // lane whose input seeds S
-            op.scratch = scratch_used;
+            op.scratch = scratch_used + (op.bbo_count & 1);  // result frame: T after an odd number of boxes
             c.S = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)scratch_used * L.frame_bytes);
             c.T = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(scratch_used + 1) * L.frame_bytes);
             scratch_used += 2;
             ++D.n_chain;
             D.max_chain = c.n > D.max_chain ? c.n : D.max_chain;
-            for (int j = 0; j < c.n; ++j) {
-              const oadg_gt_t& G = pv.gts[pv.bbo[c.bbo_first + j].gt];
-              int rw = G.supp[2] - G.supp[0], rh = G.supp[3] - G.supp[1];
-              D.max_roi_w = rw > D.max_roi_w ? rw : D.max_roi_w;
-              D.max_roi_h = rh > D.max_roi_h ? rh : D.max_roi_h;
+            for (int j = 0; j < c.n; ++j) {  // pass j covers the bounding rect of supports j and j-1
+              const int32_t* a = pv.gts[pv.bbo[c.bbo_first + j].gt].supp;
+              int x0 = a[0], y0 = a[1], x1 = a[2], y1 = a[3];
+              if (j > 0) {
+                const int32_t* q = pv.gts[pv.bbo[c.bbo_first + j - 1].gt].supp;
+                if (q[2] > q[0] && q[3] > q[1]) {
+                  if (x1 <= x0 || y1 <= y0) { x0 = q[0]; y0 = q[1]; x1 = q[2]; y1 = q[3]; }
+                  else { x0 = x0 < q[0] ? x0 : q[0]; y0 = y0 < q[1] ? y0 : q[1]; x1 = x1 > q[2] ? x1 : q[2]; y1 = y1 > q[3] ? y1 : q[3]; }
+                }
+              }
+              D.max_roi_w = (x1 - x0) > D.max_roi_w ? (x1 - x0) : D.max_roi_w;
+              D.max_roi_h = (y1 - y0) > D.max_roi_h ? (y1 - y0) : D.max_roi_h;
             }
           }
         }
@@ -331,12 +338,11 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
         const Chain& C = chains[D.chain0 + c];
         const oadg_view_t& V = pv.views[C.view];
         if ((rc = be.copy(C.S, lanes[C.lane].in, (size_t)V.H * V.W * 3))) return rc;
+        if ((rc = be.copy(C.T, lanes[C.lane].in, (size_t)V.H * V.W * 3))) return rc;
       }
       if (D.max_roi_w > 0 && D.max_roi_h > 0) {
-        for (int j = 0; j < D.max_chain; ++j) {
+        for (int j = 0; j < D.max_chain; ++j)
           if ((rc = be.bbo_pass(P, d_chain + D.chain0, D.n_chain, j, D.max_roi_w, D.max_roi_h))) return rc;
-          if ((rc = be.bbo_copyback(P, d_chain + D.chain0, D.n_chain, j, D.max_roi_w, D.max_roi_h))) return rc;
-        }
       }
     }
     if ((rc = be.step(P, d_lanes + D.lane0, D.n_lanes, d_scratch, L.frame_bytes))) return rc;

@@ -65,12 +65,17 @@ OADG_HD void chunk_store(uint8_t* p, int n, bool vec, const Chunk& c) {
 // byte k (0..47) of a chunk; k must be a compile-time constant after unrolling for register residency
 OADG_HD int chunk_get(const Chunk& c, int k) { return (int)((c.w[k >> 2] >> ((k & 3) * 8)) & 255u); }
 
-struct TileInfo {
-  int32_t mode;  // 0: one op covers the tile (op = global op index), 1: several regions meet in the tile
-  int32_t op;
-  int32_t n_center, n_taps;  // gt boxes whose mask can be non-zero at the pixel / at the warped taps
-  int32_t overflow;          // more than kMaxCand candidates: evaluate every gt of the view
+struct RegionInfo {            // one region (multi-level box or the outside) as seen from a tile
+  int32_t present;             // the region intersects the tile
+  int32_t op;                  // global op index of the region for this lane step
+  int32_t n_center, n_taps;    // gt boxes whose mask can be non-zero at the pixel / at the warped taps
+  int32_t overflow;            // more than kMaxCand candidates: evaluate every gt of the view
   int32_t center[kMaxCand], taps[kMaxCand];
+};
+struct TileInfo {
+  int32_t uniform;             // region id covering the whole tile, or -1 when several regions meet in it
+  int32_t any_bg;              // some present region runs a bg-only op: the tile uses the lane-per-pixel mapping
+  RegionInfo R[OADG_MAX_REGIONS];
 };
 
 OADG_HD bool rect_hit(const int32_t* s, int x0, int y0, int x1, int y1) {
@@ -80,43 +85,52 @@ OADG_HD bool rect_hit(const int32_t* s, int x0, int y0, int x1, int y1) {
 // classify the tile [x0,x1) x [y0,y1) of lane L
 OADG_HD void classify_step_tile(const DevPlan& P, const Lane& L, int x0, int y0, int x1, int y1, TileInfo& T) {
   const oadg_view_t& V = P.views[L.view];
-  int region = V.n_ml;
-  bool mixed = false;
+  T.uniform = V.n_ml;
+  T.any_bg = 0;
+  for (int r = 0; r < OADG_MAX_REGIONS; ++r) T.R[r].present = 0;
+  T.R[V.n_ml].present = 1;
   for (int b = 0; b < V.n_ml; ++b) {
     const int32_t* B = V.ml_box[b];
-    if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;     // disjoint
-    if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = b;  // tile inside box b
-    else mixed = true;
-  }
-  T.mode = mixed ? 1 : 0;
-  T.op = L.op_base + region;
-  T.n_center = T.n_taps = 0;
-  T.overflow = 0;
-  if (mixed) return;
-  const oadg_op_t& op = P.ops[T.op];
-  if (op.kind != OADG_OP_BG_AFFINE) return;
-  // source footprint of the tile under the inverse affine map: extremes sit at the corners; +-2 px of slack
-  // covers the fixed-point rounding and the second bilinear tap
-  double minv[6];
-  for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
-  int fx0 = 1 << 30, fy0 = 1 << 30, fx1 = -(1 << 30), fy1 = -(1 << 30);
-  for (int c = 0; c < 4; ++c) {
-    int xx = (c & 1) ? x1 - 1 : x0, yy = (c & 2) ? y1 - 1 : y0;
-    WarpTap t = warp_px(minv, warp_row(minv, yy), xx);
-    fx0 = imin(fx0, t.sx); fx1 = imax(fx1, t.sx);
-    fy0 = imin(fy0, t.sy); fy1 = imax(fy1, t.sy);
-  }
-  fx0 -= 2; fy0 -= 2; fx1 += 4; fy1 += 4;
-  for (int k = 0; k < V.n_gt; ++k) {
-    const int g = V.gt_first + k;
-    const int32_t* s = P.gts[g].supp;
-    if (rect_hit(s, x0, y0, x1, y1)) {
-      if (T.n_center < kMaxCand) T.center[T.n_center++] = g;
-      else T.overflow = 1;
+    if (!rect_hit(B, x0, y0, x1, y1)) continue;
+    T.R[b].present = 1;
+    if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) {  // tile inside box b
+      T.uniform = b;
+      T.R[V.n_ml].present = 0;
+    } else {
+      T.uniform = -1;
     }
-    if (rect_hit(s, fx0, fy0, fx1, fy1)) {
-      if (T.n_taps < kMaxCand) T.taps[T.n_taps++] = g;
-      else T.overflow = 1;
+  }
+  for (int r = 0; r <= V.n_ml; ++r) {
+    RegionInfo& R = T.R[r];
+    if (!R.present) continue;
+    R.op = L.op_base + r;
+    R.n_center = R.n_taps = R.overflow = 0;
+    const oadg_op_t& op = P.ops[R.op];
+    if (op.kind != OADG_OP_BG_AFFINE) continue;
+    T.any_bg = 1;
+    // source footprint of the tile under the inverse affine map: extremes sit at the corners; +-2 px of slack
+    // covers the fixed-point rounding and the second bilinear tap
+    double minv[6];
+    for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
+    int fx0 = 1 << 30, fy0 = 1 << 30, fx1 = -(1 << 30), fy1 = -(1 << 30);
+    for (int c = 0; c < 4; ++c) {
+      int xx = (c & 1) ? x1 - 1 : x0, yy = (c & 2) ? y1 - 1 : y0;
+      WarpTap t = warp_px(minv, warp_row(minv, yy), xx);
+      fx0 = imin(fx0, t.sx); fx1 = imax(fx1, t.sx);
+      fy0 = imin(fy0, t.sy); fy1 = imax(fy1, t.sy);
+    }
+    fx0 -= 2; fy0 -= 2; fx1 += 4; fy1 += 4;
+    for (int k = 0; k < V.n_gt; ++k) {
+      const int g = V.gt_first + k;
+      const int32_t* s = P.gts[g].supp;
+      if (rect_hit(s, x0, y0, x1, y1)) {
+        if (R.n_center < kMaxCand) R.center[R.n_center++] = g;
+        else R.overflow = 1;
+      }
+      if (rect_hit(s, fx0, fy0, fx1, fy1)) {
+        if (R.n_taps < kMaxCand) R.taps[R.n_taps++] = g;
+        else R.overflow = 1;
+      }
     }
   }
 }
@@ -130,24 +144,23 @@ OADG_HD float union_mask_cand(const DevPlan& P, const int32_t* cand, int n, int 
   return m;
 }
 
-// One pixel of a tile that a bg-only op covers entirely, with the tile's candidate gt lists
-// (bbox_augmentation.py:240-272).  Lane-per-pixel mapping: the 4-tap gathers of a warp stay within a few lines.
-OADG_HD void bg_pixel_cand(const DevPlan& P, const Lane& L, const TileInfo& T, int x, int y) {
+// One pixel under a bg-only op with the tile's candidate gt lists (bbox_augmentation.py:240-272).
+OADG_HD void bg_pixel_cand(const DevPlan& P, const Lane& L, const RegionInfo& R, int x, int y) {
   const oadg_view_t& V = P.views[L.view];
-  const oadg_op_t& op = P.ops[T.op];
+  const oadg_op_t& op = P.ops[R.op];
   double minv[6];
   for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
   const WarpTap t = warp_px(minv, warp_row(minv, y), x);
   int px[3];
   warp_fetch3(LdRO(), L.in, V.H, V.W, t, px);
   const size_t o = ((size_t)y * V.W + x) * 3;
-  if ((T.n_center | T.n_taps) != 0) {
-    const float M = union_mask_cand(P, T.center, T.n_center, x, y);
+  if ((R.n_center | R.n_taps) != 0) {
+    const float M = union_mask_cand(P, R.center, R.n_center, x, y);
     int mk[4];
     for (int c = 0; c < 4; ++c) {
       int xx = t.sx + (c & 1), yy = t.sy + (c >> 1);
       mk[c] = ((unsigned)xx < (unsigned)V.W && (unsigned)yy < (unsigned)V.H)
-                  ? mask_to_u8(union_mask_cand(P, T.taps, T.n_taps, xx, yy)) : 0;
+                  ? mask_to_u8(union_mask_cand(P, R.taps, R.n_taps, xx, yy)) : 0;
     }
     const int wm = bilerp_fix(mk[0], mk[1], mk[2], mk[3], t.fx, t.fy);
     if (M != 0.f || wm != 0)  // keep == 0 => 0*img + 1*aug == aug exactly
@@ -158,21 +171,48 @@ OADG_HD void bg_pixel_cand(const DevPlan& P, const Lane& L, const TileInfo& T, i
   q[1] = (uint8_t)px[1];
   q[2] = (uint8_t)px[2];
 }
-OADG_HD bool tile_is_bg(const DevPlan& P, const TileInfo& T) {
-  return T.mode == 0 && !T.overflow && P.ops[T.op].kind == OADG_OP_BG_AFFINE;
+
+OADG_HD int region_of_pixel(const oadg_view_t& V, int x, int y) {
+  int r = V.n_ml;
+  for (int b = 0; b < V.n_ml; ++b)
+    if (x >= V.ml_box[b][0] && x < V.ml_box[b][2] && y >= V.ml_box[b][1] && y < V.ml_box[b][3]) r = b;
+  return r;
+}
+// region covering the whole pixel run [x, x+n) of row y, or -1 when a box edge falls inside it
+OADG_HD int region_of_run(const oadg_view_t& V, int x, int y, int n) {
+  int r = V.n_ml;
+  for (int b = 0; b < V.n_ml; ++b) {
+    const int32_t* B = V.ml_box[b];
+    if (y < B[1] || y >= B[3] || B[0] >= x + n || B[2] <= x) continue;
+    if (B[0] <= x && B[2] >= x + n) r = b;
+    else return -1;
+  }
+  return r;
 }
 
-// 16 pixels of one depth step.  `lut` points at the 3x256 table of the tile's op when it is a LUT op
-// (shared memory on the device).
-OADG_HD void step_chunk(const DevPlan& P, const Lane& L, const TileInfo& T, const uint8_t* lut,
+// one pixel, any op, using the tile's candidate lists where they help
+OADG_HD void step_pixel_cand(const DevPlan& P, const Lane& L, const TileInfo& T, const uint8_t* scratch,
+                             size_t frame_bytes, int x, int y) {
+  const oadg_view_t& V = P.views[L.view];
+  const int r = region_of_pixel(V, x, y);
+  const RegionInfo& R = T.R[r];
+  if (P.ops[R.op].kind == OADG_OP_BG_AFFINE && !R.overflow) bg_pixel_cand(P, L, R, x, y);
+  else step_pixel(P, L, scratch, frame_bytes, x, y);
+}
+
+// 16 pixels of one depth step.  `luts` holds the 3x256 table of region r at luts + r*768 when that region's op
+// is a LUT op (shared memory on the device).
+OADG_HD void step_chunk(const DevPlan& P, const Lane& L, const TileInfo& T, const uint8_t* luts,
                         const uint8_t* scratch, size_t frame_bytes, int x, int y, int n, bool vec) {
   const oadg_view_t& V = P.views[L.view];
   const size_t o = ((size_t)y * V.W + x) * 3;
-  Chunk out;
-  if (T.mode == 0) {
-    const oadg_op_t& op = P.ops[T.op];
+  const int r = T.uniform >= 0 ? T.uniform : region_of_run(V, x, y, n);
+  if (r >= 0) {
+    const oadg_op_t& op = P.ops[T.R[r].op];
     const int kind = op.kind;
+    Chunk out;
     if (is_lut_kind(kind)) {
+      const uint8_t* lut = luts + r * 768;
       Chunk in;
       chunk_load(L.in + o, n, vec, in);
 #ifdef __CUDA_ARCH__
@@ -199,8 +239,8 @@ OADG_HD void step_chunk(const DevPlan& P, const Lane& L, const TileInfo& T, cons
       return;
     }
   }
-  // generic (region borders, invert / color / sharpness, candidate overflow): per pixel, byte stores
-  for (int i = 0; i < n; ++i) step_pixel(P, L, scratch, frame_bytes, x + i, y);
+  // a box edge inside the run, or invert / color / sharpness: per pixel, byte stores
+  for (int i = 0; i < n; ++i) step_pixel_cand(P, L, T, scratch, frame_bytes, x + i, y);
 }
 
 // ---- mix ------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kRes = 64;
 constexpr int kN = kRes * kRes;
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;
 
 __device__ __forceinline__ int brev6(int v) { return (int)(__brev((unsigned)v) >> 26); }
 

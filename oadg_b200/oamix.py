@@ -134,21 +134,24 @@ class OAMix:
 
     # ------------------------------------------------------------------ sampling
     def _sample_regions(self, h, w, scale, ratio, num, gt=None, scores=None, max_iters=50, eps=1e-6):
-        """oa_mix.py:122-184."""
-        rs = np.random
-        target = rs.randint(*num) if isinstance(num, tuple) else num
+        """oa_mix.py:122-184.  Draws: randint(*num) once, then per attempt randint(0,w), randint(0,h),
+        uniform(*scale), uniform(*ratio); legacy uniform(a, b) is a + (b - a) * random_sample() bit for bit."""
+        randint, u01 = np.random.randint, np.random.random_sample
+        target = randint(*num) if isinstance(num, tuple) else num
+        s_lo, s_w = scale[0], scale[1] - scale[0]
+        r_lo, r_w = ratio[0], ratio[1] - ratio[0]
         boxes, bscores = [], []
         for _ in range(max_iters):
             if len(boxes) >= target:
                 break
-            x1, y1 = rs.randint(0, w), rs.randint(0, h)
-            area = rs.uniform(*scale) * h * w
-            r = rs.uniform(*ratio)
-            bw, bh = int(np.sqrt(area / r)), int(np.sqrt(area * r))
+            x1, y1 = int(randint(0, w)), int(randint(0, h))
+            area = (s_lo + s_w * u01()) * h * w
+            r = r_lo + r_w * u01()
+            bw, bh = int(math.sqrt(area / r)), int(math.sqrt(area * r))
             if x1 + bw > w or y1 + bh > h:
                 continue
             box = np.array([x1, y1, min(x1 + bw, w), min(y1 + bh, h)])
-            if np.sum(_iou_1xk(box, boxes)) > eps:
+            if boxes and np.sum(_iou_1xk(box, boxes)) > eps:
                 continue
             if gt is not None:
                 ious = _iou_1xk(box, gt)
@@ -164,9 +167,10 @@ class OAMix:
         return boxes, bscores
 
     def _level_sign(self, geo):
-        level = np.random.uniform(low=0.1, high=self.severity)
-        u = np.random.uniform() if geo in ('rotate', 'shear_x', 'shear_y') else np.random.random()
-        return level, u > 0.5
+        """augmix.py:61 sample_level = uniform(0.1, severity), then one sign draw (uniform()/random())."""
+        u01 = np.random.random_sample
+        level = 0.1 + (self.severity - 0.1) * u01()
+        return level, u01() > 0.5
 
     @staticmethod
     def _forward_affine(geo, level, neg, size_for_level, center, img_size):
@@ -200,32 +204,35 @@ class OAMix:
             l = -l
         return [1.0, 0.0, 0.0, 0.0, 1.0, _f32(-l)]
 
-    def _sample_op(self, gt, img_size):
-        """One OAMix.aug() (oa_mix.py:264-279): op index, then the op's own draws."""
-        name = self.aug_list[np.random.choice(len(self.aug_list))]
-        if name in ('autocontrast', 'equalize'):
+    def _sample_op(self, gt, img_size, gt_int=None):
+        """One OAMix.aug() (oa_mix.py:264-279): op index, then the op's own draws.
+        np.random.choice(list) draws randint(0, len) (same legacy stream); sample_level as in _level_sign."""
+        u01 = np.random.random_sample
+        name = self.aug_list[int(np.random.randint(0, len(self.aug_list)))]
+        if name == 'autocontrast' or name == 'equalize':
             return (name,)
         if name == 'posterize':
-            return (name, 4 - int(np.random.uniform(low=0.1, high=self.severity) * 4 / 10))
+            return (name, 4 - int((0.1 + (self.severity - 0.1) * u01()) * 4 / 10))
         if name == 'solarize':
-            return (name, 256 - int(np.random.uniform(low=0.1, high=self.severity) * 256 / 10))
+            return (name, 256 - int((0.1 + (self.severity - 0.1) * u01()) * 256 / 10))
         if name in ('color', 'contrast', 'brightness', 'sharpness'):
-            return (name, float(np.random.uniform(low=0.1, high=self.severity)) * 1.8 / 10. + 0.1)
+            return (name, float(0.1 + (self.severity - 0.1) * u01()) * 1.8 / 10. + 0.1)
         if name == 'invert':
-            tx = 1 if np.random.random() > 0.5 else -1
-            ty = 1 if np.random.random() > 0.5 else -1
+            tx = 1 if u01() > 0.5 else -1
+            ty = 1 if u01() > 0.5 else -1
             return (name, tx, ty)
         where, geo = name.split('_', 1)
         if geo == 'shear_xy':
-            geo = 'shear_x' if np.random.rand() < 0.5 else 'shear_y'
+            geo = 'shear_x' if u01() < 0.5 else 'shear_y'
         elif geo == 'translate_xy':
-            geo = 'translate_x' if np.random.rand() < 0.5 else 'translate_y'
+            geo = 'translate_x' if u01() < 0.5 else 'translate_y'
         if where == 'bg':
             level, neg = self._level_sign(geo)
             return ('bg_affine', _invert_affine(self._forward_affine(geo, level, neg, img_size, None, img_size)))
         chain = []
-        for k, b in enumerate(gt):
-            x1, y1, x2, y2 = int(b[0]), int(b[1]), int(b[2]), int(b[3])
+        if gt_int is None:
+            gt_int = [(int(b[0]), int(b[1]), int(b[2]), int(b[3])) for b in gt]
+        for k, (x1, y1, x2, y2) in enumerate(gt_int):
             if (x2 - x1) < 1 or (y2 - y1) < 1:
                 continue  # bbox_augmentation.py:45-47: skipped before any draw
             level, neg = self._level_sign(geo)
@@ -242,10 +249,11 @@ class OAMix:
         ml, _ = self._sample_regions(h, w, self.random_box_scale, self.random_box_ratio, (1, 3))
         vp.ml_boxes = np.stack(ml, axis=0)  # ValueError when no box could be placed (oa_mix.py:217)
         vp.depths, vp.ops = [], []
+        gt_int = [(int(b[0]), int(b[1]), int(b[2]), int(b[3])) for b in gt]   # bbox_augmentation.py:44
         for _ in range(self.mixture_width):
-            depth = self.mixture_depth if self.mixture_depth > 0 else np.random.randint(1, 4)
+            depth = self.mixture_depth if self.mixture_depth > 0 else int(np.random.randint(1, 4))
             vp.depths.append(depth)
-            vp.ops.append([[self._sample_op(gt, (w, h)) for _r in range(len(ml) + 1)] for _d in range(depth)])
+            vp.ops.append([[self._sample_op(gt, (w, h), gt_int) for _r in range(len(ml) + 1)] for _d in range(depth)])
         return vp
 
     def _sample_tail(self, vp, gt, scores):
@@ -257,98 +265,90 @@ class OAMix:
             min(max(len(vp.oa_low), 1), 5), gt=gt, scores=scores)
         vp.m = np.random.beta(self.aug_prob_coeff, self.aug_prob_coeff)
         tgt_scores = [scores[k] for k in vp.oa_low] + list(oa_scores)
-        vp.m_oa = [np.float32(np.random.uniform(0.0, 0.5)) if s <= self.score_thresh
-                   else np.float32(np.random.uniform(0.0, 1.0)) for s in tgt_scores]
+        u01 = np.random.random_sample
+        vp.m_oa = [np.float32(0.0 + 0.5 * u01()) if s <= self.score_thresh
+                   else np.float32(0.0 + 1.0 * u01()) for s in tgt_scores]
         return vp
 
     # ------------------------------------------------------------------ records
-    def _gt_records(self, gt, h, w, view):
+    def _gt_records(self, gt, h, w):
+        """Per gt box: (lo x1,y1,x2,y2, blur, kx, ky, sigma_x, sigma_y, supp x0,y0,x1,y1) -- oa_mix.py:78-91."""
         sr = self.spatial_ratio
-        rec = np.zeros(len(gt), P.GT_DT)
         h4, w4 = h // sr, w // sr
-        for k, b in enumerate(gt):
-            lo = np.array(b // sr, dtype=np.int32)  # oa_mix.py:79
-            x1, y1, x2, y2 = (int(v) for v in lo)
+        lo_all = np.array(gt // sr, dtype=np.int32).reshape(-1, 4).tolist() if len(gt) else []   # oa_mix.py:79
+        out = []
+        for x1, y1, x2, y2 in lo_all:
             sx = (x2 - x1) * self.sigma_ratio / 3 * 2
             sy = (y2 - y1) * self.sigma_ratio / 3 * 2
             blur = not (sx <= 0 or sy <= 0)
             xs, xe = _slice(x1, x2, w4)
             ys, ye = _slice(y1, y2, h4)
-            r = rec[k]
-            r['lo'] = (xs, ys, xe, ye)
-            r['blur'] = int(blur)
-            r['view'] = view
-            r['kx'] = (int(round(sx * 8 + 1)) | 1) if blur else 1
-            r['ky'] = (int(round(sy * 8 + 1)) | 1) if blur else 1
-            r['sigma_x'], r['sigma_y'] = (sx, sy) if blur else (1.0, 1.0)
+            kx = (int(round(sx * 8 + 1)) | 1) if blur else 1   # cvRound(sigma*8+1)|1 for non-8U depth
+            ky = (int(round(sy * 8 + 1)) | 1) if blur else 1
             supp = [0, 0, 0, 0]
             if xe > xs and ye > ys and w4 > 0 and h4 > 0:
-                for ax, (s, e, n_lo, n_hi, ks) in enumerate(((xs, xe, w4, w, r['kx']), (ys, ye, h4, h, r['ky']))):
-                    rad = int(ks) // 2 if blur else 0
+                for ax, (s, e, n_lo, n_hi, ks) in enumerate(((xs, xe, w4, w, kx), (ys, ye, h4, h, ky))):
+                    rad = ks // 2 if blur else 0
                     a, bnd = max(s - rad, 0), min(e - 1 + rad, n_lo - 1)
                     up = n_hi / n_lo
                     d0 = int(math.floor((a - 0.5) * up - 0.5)) - 1
                     d1 = int(math.ceil((bnd + 1.5) * up - 0.5)) + 1
                     supp[ax], supp[ax + 2] = max(d0, 0), min(d1, n_hi)
-            r['supp'] = supp
-        return rec
+            out.append((xs, ys, xe, ye, int(blur), kx, ky, sx if blur else 1.0, sy if blur else 1.0, supp))
+        return out
 
     def _pack(self, jobs):
-        """jobs: list of (view_plan, gt, img_index).  Returns the plan blob."""
-        views = np.zeros(len(jobs), P.VIEW_DT)
-        ops = np.zeros(len(jobs) * P.OPS_PER_VIEW, P.OP_DT)
-        gts, bbos, tgts = [], [], []
-        n_gt = n_bbo = n_tgt = 0
+        """jobs: list of (view_plan, gt, img_index).  Returns the plan blob (uint8 array)."""
+        n_gt = sum(len(gt) for _, gt, _ in jobs)
+        n_tgt = sum(len(vp.oa_low) + len(vp.oa_boxes) for vp, _, _ in jobs)
+        n_bbo = sum(len(op[1]) for vp, _, _ in jobs for steps in vp.ops for regs in steps for op in regs
+                    if op[0] == 'bbo_affine')
+        B = P.BlobBuilder(len(jobs), n_gt, n_bbo, n_tgt)
+        g0 = b0 = t0 = 0
         max_h = max_w = 1
         for v, (vp, gt, img_i) in enumerate(jobs):
-            V = views[v]
-            V['H'], V['W'], V['img'] = vp.h, vp.w, img_i
             max_h, max_w = max(max_h, vp.h), max(max_w, vp.w)
-            g = self._gt_records(gt, vp.h, vp.w, v)
-            V['n_gt'], V['gt_first'] = len(gt), n_gt
-            gts.append(g)
-            V['n_ml'] = len(vp.ml_boxes)
-            V['ml_box'][:len(vp.ml_boxes)] = vp.ml_boxes
-            V['width'] = len(vp.depths)
-            V['depth'][:len(vp.depths)] = vp.depths
-            V['ws'][:len(vp.ws)] = vp.ws
-            V['op_first'] = v * P.OPS_PER_VIEW
+            for k, (xs, ys, xe, ye, blur, kx, ky, sx, sy, supp) in enumerate(self._gt_records(gt, vp.h, vp.w)):
+                B.gt(g0 + k, xs, ys, xe, ye, blur, kx, ky, v, sx, sy, *supp)
+            base = v * P.OPS_PER_VIEW
             for b, steps in enumerate(vp.ops):
                 for d, regs in enumerate(steps):
                     for r, op in enumerate(regs):
-                        o = ops[v * P.OPS_PER_VIEW + (b * P.MAX_DEPTH + d) * P.MAX_REGIONS + r]
-                        o['kind'] = P.OP[op[0]]
-                        o['lut'] = o['scratch'] = -1
-                        if op[0] in ('posterize', 'solarize'):
-                            o['p0'] = op[1]
-                        elif op[0] in ('color', 'contrast', 'brightness', 'sharpness'):
-                            o['factor'] = op[1]
-                        elif op[0] == 'invert':
-                            o['p0'], o['p1'] = op[1], op[2]
-                        elif op[0] == 'bg_affine':
-                            o['minv'] = op[1]
-                        elif op[0] == 'bbo_affine':
-                            o['bbo_first'], o['bbo_count'] = n_bbo, len(op[1])
+                        i = base + (b * P.MAX_DEPTH + d) * P.MAX_REGIONS + r
+                        name = op[0]
+                        if name == 'bbo_affine':
+                            B.op(i, P.OP[name], bbo_first=b0, bbo_count=len(op[1]))
                             for k, minv in op[1]:
-                                rec = np.zeros(1, P.BBO_DT)
-                                rec['gt'], rec['minv'] = n_gt + k, minv
-                                bbos.append(rec)
-                            n_bbo += len(op[1])
-            t = np.zeros(len(vp.oa_low) + len(vp.oa_boxes), P.TGT_DT)
-            for i, k in enumerate(vp.oa_low):
-                t[i]['kind'], t[i]['gt'] = 0, n_gt + k
-            for i, bx in enumerate(vp.oa_boxes):
-                j = len(vp.oa_low) + i
+                                B.bbo(b0, g0 + k, minv)
+                                b0 += 1
+                        elif name == 'bg_affine':
+                            B.op(i, P.OP[name], minv=op[1])
+                        elif name == 'posterize' or name == 'solarize':
+                            B.op(i, P.OP[name], p0=op[1])
+                        elif name == 'invert':
+                            B.op(i, P.OP[name], p0=op[1], p1=op[2])
+                        elif len(op) > 1:
+                            B.op(i, P.OP[name], factor=op[1])
+                        else:
+                            B.op(i, P.OP[name])
+            nt = 0
+            for k, m_oa in zip(vp.oa_low, vp.m_oa):
+                B.tgt(t0 + nt, 0, g0 + k, (0, 0, 0, 0), float(m_oa))
+                nt += 1
+            for bx, m_oa in zip(vp.oa_boxes, vp.m_oa[len(vp.oa_low):]):
                 xs, xe = _slice(bx[0], bx[2], vp.w)
                 ys, ye = _slice(bx[1], bx[3], vp.h)
-                t[j]['kind'], t[j]['gt'], t[j]['box'] = 1, -1, (xs, ys, xe, ye)
-            t['m_oa'] = vp.m_oa
-            V['n_tgt'], V['tgt_first'], V['m'] = len(t), n_tgt, vp.m
-            tgts.append(t)
-            n_gt += len(gt)
-            n_tgt += len(t)
-        cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
-        return P.pack(views, cat(gts, P.GT_DT), ops, cat(bbos, P.BBO_DT), cat(tgts, P.TGT_DT), max_h, max_w)
+                B.tgt(t0 + nt, 1, -1, (xs, ys, xe, ye), float(m_oa))
+                nt += 1
+            ml = [int(c) for bx in vp.ml_boxes for c in bx] + [0] * (8 - 4 * len(vp.ml_boxes))
+            nb = len(vp.depths)
+            B.view(v, vp.h, vp.w, img_i, len(gt), g0, len(vp.ml_boxes), *ml, nb,
+                   *(list(vp.depths) + [0] * (P.MAX_WIDTH - nb)),
+                   *([float(x) for x in vp.ws] + [0.0] * (P.MAX_WIDTH - nb)),
+                   base, nt, t0, 0, float(vp.m))
+            g0 += len(gt)
+            t0 += nt
+        return B.finish(max_h, max_w)
 
     # ------------------------------------------------------------------ device
     def saliency_scores(self, imgs, gt_list, stream=None):

@@ -54,3 +54,58 @@ def pack(views, gts, ops, bbos, tgts, max_h, max_w):
         if arr.nbytes:
             blob[o:o + arr.nbytes] = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
     return blob
+
+
+# ---- fast packers (struct formats mirror the dtypes above; tests/test_host.py checks both against the C sizes)
+import struct as _struct
+
+HEADER_ST = _struct.Struct('<16i')
+VIEW_ST = _struct.Struct('<6i8ii8i8f4i4xd')
+GT_ST = _struct.Struct('<4i4i2d4i')
+OP_ST = _struct.Struct('<3if6d4i')
+BBO_ST = _struct.Struct('<2i6d')
+TGT_ST = _struct.Struct('<2i4ifi')
+assert [st.size for st in (HEADER_ST, VIEW_ST, GT_ST, OP_ST, BBO_ST, TGT_ST)] == STRUCT_SIZES
+_ZERO_MINV = (0.0,) * 6
+
+
+class BlobBuilder:
+    """Packs plan records straight into one bytearray (no per-field numpy assignments)."""
+
+    def __init__(self, n_views, n_gt, n_bbo, n_tgt):
+        self.n_views, self.n_gt, self.n_bbo, self.n_tgt = n_views, n_gt, n_bbo, n_tgt
+        self.n_ops = n_views * OPS_PER_VIEW
+        off = _a8(HEADER_ST.size)
+        self.off_views = off
+        off = _a8(off + n_views * VIEW_ST.size)
+        self.off_gt = off
+        off = _a8(off + n_gt * GT_ST.size)
+        self.off_ops = off
+        off = _a8(off + self.n_ops * OP_ST.size)
+        self.off_bbo = off
+        off = _a8(off + n_bbo * BBO_ST.size)
+        self.off_tgt = off
+        off = _a8(off + n_tgt * TGT_ST.size)
+        self.total = off
+        self.buf = bytearray(off)
+
+    def view(self, v, *fields):
+        VIEW_ST.pack_into(self.buf, self.off_views + v * VIEW_ST.size, *fields)
+
+    def gt(self, g, *fields):
+        GT_ST.pack_into(self.buf, self.off_gt + g * GT_ST.size, *fields)
+
+    def op(self, i, kind, p0=0, p1=0, factor=0.0, minv=_ZERO_MINV, bbo_first=0, bbo_count=0):
+        OP_ST.pack_into(self.buf, self.off_ops + i * OP_ST.size, kind, p0, p1, factor, *minv, bbo_first, bbo_count, -1, -1)
+
+    def bbo(self, i, gt, minv):
+        BBO_ST.pack_into(self.buf, self.off_bbo + i * BBO_ST.size, gt, 0, *minv)
+
+    def tgt(self, i, kind, gt, box, m_oa):
+        TGT_ST.pack_into(self.buf, self.off_tgt + i * TGT_ST.size, kind, gt, *box, m_oa, 0)
+
+    def finish(self, max_h, max_w):
+        HEADER_ST.pack_into(self.buf, 0, MAGIC, 1, self.n_views, self.n_gt, self.n_ops, self.n_bbo, self.n_tgt,
+                            max_h, max_w, self.off_views, self.off_gt, self.off_ops, self.off_bbo, self.off_tgt,
+                            self.total, 0)
+        return np.frombuffer(self.buf, dtype=np.uint8)

@@ -130,23 +130,10 @@ struct HostBackend {
     for (int k = 0; k < n; ++k) {
       const Chain& C = chains[k];
       if (j >= C.n) continue;
-      const oadg_gt_t& G = P.gts[P.bbo[C.bbo_first + j].gt];
-      for (int y = G.supp[1]; y < G.supp[3]; ++y)
-        for (int x = G.supp[0]; x < G.supp[2]; ++x) bbo_pixel(P, C, j, x, y);
-    }
-    ++launches;
-    return 0;
-  }
-  int bbo_copyback(const DevPlan& P, const Chain* chains, int n, int j, int, int) {
-    for (int k = 0; k < n; ++k) {
-      const Chain& C = chains[k];
-      if (j >= C.n) continue;
-      const oadg_gt_t& G = P.gts[P.bbo[C.bbo_first + j].gt];
-      const oadg_view_t& V = P.views[C.view];
-      if (G.supp[2] <= G.supp[0]) continue;
-      for (int y = G.supp[1]; y < G.supp[3]; ++y)
-        memcpy(C.S + ((size_t)y * V.W + G.supp[0]) * 3, C.T + ((size_t)y * V.W + G.supp[0]) * 3,
-               (size_t)(G.supp[2] - G.supp[0]) * 3);
+      int r[4];
+      bbo_pass_rect(P, C, j, r);
+      for (int y = r[1]; y < r[3]; ++y)
+        for (int x = r[0]; x < r[2]; ++x) bbo_pixel(P, C, j, x, y);
     }
     ++launches;
     return 0;
@@ -161,13 +148,17 @@ struct HostBackend {
           const int x1 = imin(x0 + kTileW, V.W), y1 = imin(y0 + kTileH, V.H);
           TileInfo T;
           classify_step_tile(P, L, x0, y0, x1, y1, T);
-          const uint8_t* lut = (T.mode == 0 && is_lut_kind(P.ops[T.op].kind)) ? P.luts + (size_t)P.ops[T.op].lut * 768 : nullptr;
+          // region r's LUT lives at luts + r*768 (shared memory on the device)
+          uint8_t luts[OADG_MAX_REGIONS * 768];
+          for (int r = 0; r <= V.n_ml; ++r)
+            if (T.R[r].present && is_lut_kind(P.ops[T.R[r].op].kind))
+              memcpy(luts + r * 768, P.luts + (size_t)P.ops[T.R[r].op].lut * 768, 768);
           for (int y = y0; y < y1; ++y) {
-            if (tile_is_bg(P, T)) {
-              for (int x = x0; x < x1; ++x) bg_pixel_cand(P, L, T, x, y);
+            if (T.any_bg) {
+              for (int x = x0; x < x1; ++x) step_pixel_cand(P, L, T, scratch, frame_bytes, x, y);
             } else {
               for (int x = x0; x < x1; x += kChunkPx)
-                step_chunk(P, L, T, lut, scratch, frame_bytes, x, y, imin(kChunkPx, x1 - x), true);
+                step_chunk(P, L, T, luts, scratch, frame_bytes, x, y, imin(kChunkPx, x1 - x), true);
             }
           }
         }
