@@ -99,29 +99,52 @@ normalize_kernel(const float* __restrict__ x, int n, int c, int normalized_input
 }
 
 // ---- label prep: bg = max(labels), #fg, n_i per row.  Single block (N is a few thousand).
+// n_i of a foreground row = (#rows with the same label) - 1: counted with a shared-memory histogram when the
+// label range is small (class ids), by direct comparison otherwise.
+constexpr int kLabelBins = 4096;
 __global__ void __launch_bounds__(1024)
 label_prep_kernel(const int64_t* __restrict__ labels, const int32_t* __restrict__ pair, int n, int min_samples,
                   int* __restrict__ meta, float* __restrict__ npos) {
-  __shared__ long long smax[32];
+  __shared__ long long smax[32], smin[32];
   __shared__ int scnt[32];
-  __shared__ long long bg_s;
+  __shared__ long long bg_s, lo_s;
+  __shared__ int bins[kLabelBins];
   const int tid = threadIdx.x;
-  long long m = LLONG_MIN;
-  for (int i = tid; i < n; i += blockDim.x) m = labels[i] > m ? labels[i] : m;
+  long long m = LLONG_MIN, mn = LLONG_MAX;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const long long v = labels[i];
+    m = v > m ? v : m;
+    mn = v < mn ? v : mn;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     long long t = __shfl_xor_sync(0xffffffffu, m, o);
     m = t > m ? t : m;
+    t = __shfl_xor_sync(0xffffffffu, mn, o);
+    mn = t < mn ? t : mn;
   }
-  if ((tid & 31) == 0) smax[tid >> 5] = m;
+  if ((tid & 31) == 0) {
+    smax[tid >> 5] = m;
+    smin[tid >> 5] = mn;
+  }
+  for (int i = tid; i < kLabelBins; i += blockDim.x) bins[i] = 0;
   __syncthreads();
   if (tid == 0) {
-    long long t = smax[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = smax[w] > t ? smax[w] : t;
+    long long t = smax[0], u = smin[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      t = smax[w] > t ? smax[w] : t;
+      u = smin[w] < u ? smin[w] : u;
+    }
     bg_s = t;
+    lo_s = u;
   }
   __syncthreads();
-  const long long bg = bg_s;
+  const long long bg = bg_s, lo = lo_s;
+  const bool small_range = (bg - lo) < (long long)kLabelBins;
+  if (small_range) {
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&bins[(int)(labels[i] - lo)], 1);
+    __syncthreads();
+  }
   int cnt = 0;
   for (int i = tid; i < n; i += blockDim.x) {
     const long long yi = labels[i];
@@ -129,7 +152,9 @@ label_prep_kernel(const int64_t* __restrict__ labels, const int32_t* __restrict_
     if (yi != bg) {
       ++cnt;
       int same = 0;
-      for (int j = 0; j < n; ++j) same += (labels[j] == yi);
+      if (small_range) same = bins[(int)(yi - lo)];
+      else
+        for (int j = 0; j < n; ++j) same += (labels[j] == yi);
       np = (float)(same - 1);
     } else {
       int pj = pair[i];

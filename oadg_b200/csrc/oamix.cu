@@ -103,6 +103,19 @@ profile_kernel(DevPlan P, int sr, float* __restrict__ prof_x, float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------
+// union of the blurred gt masks of every view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260), as float32
+// and as uint8(mask*255): computed once per batch, read by every bg-only op.  grid = (ceil(W/256), H, views)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_kernel(DevPlan P, float* __restrict__ maskf, uint8_t* __restrict__ masku) {
+  const int view = blockIdx.z;
+  const oadg_view_t& V = P.views[view];
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+  if (x >= V.W || y >= V.H) return;
+  mask_pixel(P, view, x, y, maskf, masku);
+}
+
+// ------------------------------------------------------------------------------------
 // per-channel histogram + luma sum of a lane's input frame (PIL Image.histogram())
 // grid = (blocks, lanes_with_hist)
 // ------------------------------------------------------------------------------------
@@ -234,7 +247,7 @@ step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict
   if (T.any_bg) {
     // lane-per-pixel mapping: the 4-tap gathers of a warp stay within a few cache lines
     for (int y = y0 + warp; y < y1; y += kTileThreads / 32)
-      for (int x = x0 + lane; x < x1; x += 32) step_pixel_cand(P, L, T, scratch, frame_bytes, x, y);
+      for (int x = x0 + lane; x < x1; x += 32) step_pixel(P, L, scratch, frame_bytes, x, y);
     return;
   }
   for (int r = 0; r <= V.n_ml; ++r) {
@@ -278,7 +291,7 @@ mix_kernel(DevPlan P, const MixJob* __restrict__ jobs) {
     if (_e != cudaSuccess) return (int)_e; \
   } while (0)
 
-enum { kKProfile = 0, kKHist, kKLut, kKBboPass, kKBboCopy, kKStep, kKMix, kKCopy, kKinds };
+enum { kKProfile = 0, kKHist, kKLut, kKBboPass, kKMask, kKStep, kKMix, kKCopy, kKinds };
 
 struct CudaBackend {
   cudaStream_t stream;
@@ -333,6 +346,13 @@ struct CudaBackend {
     profile_kernel<<<dim3(h.n_gt, 2), 256, smem, stream>>>(P, sr, px, py);
     BE_TRY(cudaGetLastError());
     end(kKProfile);
+    return 0;
+  }
+  int masks(const DevPlan& P, int n_views, float* maskf, uint8_t* masku) {
+    begin();
+    mask_kernel<<<dim3((P.max_w + 255) / 256, P.max_h, n_views), 256, 0, stream>>>(P, maskf, masku);
+    BE_TRY(cudaGetLastError());
+    end(kKMask);
     return 0;
   }
   int hist(const DevPlan& P, const Lane* lanes, const int32_t* ids, int n, unsigned* hist, unsigned long long* luma) {

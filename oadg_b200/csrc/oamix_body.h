@@ -22,6 +22,10 @@ struct DevPlan {
   const float* prof_y;  // [n_gt][max_h]
   int max_w, max_h;
   const uint8_t* luts;  // [slot][3][256]
+  // union of the blurred gt masks of each view, np.max(mask_bboxes, axis=0) (bbox_augmentation.py:260):
+  const float* maskf;    // [view][max_h*max_w] float32 value
+  const uint8_t* masku;  // [view][max_h*max_w] uint8(mask*255), the image bg-only ops warp (bbox_augmentation.py:264)
+  size_t mask_stride;    // max_h*max_w
 };
 
 struct Lane {            // one (view, branch) chain alive at the current depth
@@ -141,6 +145,36 @@ OADG_HD void bbo_pass_rect(const DevPlan& P, const Chain& C, int j, int r[4]) {
   }
 }
 
+// ---- union mask of one view at one pixel: written once per batch by mask_kernel -------------------
+OADG_HD void mask_pixel(const DevPlan& P, int view, int x, int y, float* maskf, uint8_t* masku) {
+  const oadg_view_t& V = P.views[view];
+  const float m = union_mask(P, V, x, y);
+  const size_t o = (size_t)view * P.mask_stride + (size_t)y * V.W + x;
+  maskf[o] = m;
+  masku[o] = (uint8_t)mask_to_u8(m);
+}
+
+// ---- bg-only op at one pixel (bbox_augmentation.py:240-272) ----------------------------------------
+OADG_HD void bg_pixel(const DevPlan& P, const oadg_view_t& V, const oadg_op_t& op, const uint8_t* in, int view,
+                      int x, int y, const int img[3], int out[3]) {
+  double minv[6];
+  for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
+  const WarpTap t = warp_px(minv, warp_row(minv, y), x);
+  warp_fetch3(LdRO(), in, V.H, V.W, t, out);
+  const size_t mo = (size_t)view * P.mask_stride;
+  const float M = OADG_LDG(P.maskf + mo + (size_t)y * V.W + x);
+  // cv2.warpAffine of uint8(mask*255) with the same matrix (bbox_augmentation.py:263-264)
+  const uint8_t* mu = P.masku + mo;
+  const bool x0 = (unsigned)t.sx < (unsigned)V.W, x1 = t.fx != 0 && (unsigned)(t.sx + 1) < (unsigned)V.W;
+  const bool y0 = (unsigned)t.sy < (unsigned)V.H, y1 = t.fy != 0 && (unsigned)(t.sy + 1) < (unsigned)V.H;
+  const uint8_t* r0 = mu + (size_t)t.sy * V.W + t.sx;
+  const uint8_t* r1 = r0 + V.W;
+  const int wm = bilerp_fix((y0 && x0) ? ldb(r0) : 0, (y0 && x1) ? ldb(r0 + 1) : 0, (y1 && x0) ? ldb(r1) : 0,
+                            (y1 && x1) ? ldb(r1 + 1) : 0, t.fx, t.fy);
+  if (M != 0.f || wm != 0)  // keep == 0 => 0*img + 1*aug == aug exactly
+    for (int c = 0; c < 3; ++c) out[c] = bg_blend(M, wm, img[c], out[c]);
+}
+
 // ---- one op at one pixel (oa_mix.py:264-279 dispatch) ------------------------------------
 OADG_HD void eval_op(const DevPlan& P, const oadg_view_t& V, const oadg_op_t& op, const uint8_t* in,
                      const uint8_t* scratch, size_t frame_bytes, int x, int y, int out[3]) {
@@ -161,20 +195,7 @@ OADG_HD void eval_op(const DevPlan& P, const oadg_view_t& V, const oadg_op_t& op
     out[1] = ldb(lut + 256 + v[1]);
     out[2] = ldb(lut + 512 + v[2]);
   } else if (kind == OADG_OP_BG_AFFINE) {
-    double minv[6];
-    for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
-    WarpTap t = warp_px(minv, warp_row(minv, y), x);
-    int a[3];
-    warp_fetch3(LdRO(), in, H, W, t, a);
-    const float M = union_mask(P, V, x, y);
-    // cv2.warpAffine of uint8(mask*255) with the same matrix (bbox_augmentation.py:263-264)
-    int mk[4];
-    for (int q = 0; q < 4; ++q) {
-      int xx = t.sx + (q & 1), yy = t.sy + (q >> 1);
-      mk[q] = ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? mask_to_u8(union_mask(P, V, xx, yy)) : 0;
-    }
-    int wm = bilerp_fix(mk[0], mk[1], mk[2], mk[3], t.fx, t.fy);
-    for (int c = 0; c < 3; ++c) out[c] = bg_blend(M, wm, v[c], a[c]);
+    bg_pixel(P, V, op, in, (int)(&V - P.views), x, y, v, out);
   } else if (kind == OADG_OP_INVERT) {
     // -cv2.warpAffine(img, [[1,0,tx],[0,1,ty]]) : integer shift, zero fill, uint8 negation
     int xs = x - op.p0, ys = y - op.p1;

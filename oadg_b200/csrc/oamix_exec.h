@@ -92,6 +92,8 @@ inline int parse_plan(const void* blob, size_t bytes, PlanView& pv) {
 struct Layout {
   size_t frame_bytes;
   size_t off_plan, off_prof_x, off_prof_y, off_branch, off_scratch, off_hist, off_luma, off_lut, off_tables;
+  size_t off_maskf, off_masku;
+  int any_bg;
   size_t tables_bytes;
   int n_lanes_total, n_scratch, n_lut, n_hist, max_depth;
   size_t total;
@@ -103,6 +105,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.frame_bytes = align_up_sz((size_t)h.max_h * h.max_w * 3, 256);
   int max_depth = 0, lanes_total = 0, n_lut = 0, n_hist = 0;
   int bbo_at_depth[OADG_MAX_DEPTH] = {0};
+  int any_bg = 0;
   for (int v = 0; v < h.n_views; ++v) {
     const oadg_view_t& V = pv.views[v];
     for (int b = 0; b < V.width; ++b) {
@@ -115,6 +118,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
           if (is_lut_kind(op.kind)) ++n_lut;
           if (needs_hist(op.kind)) hist = true;
           if (op.kind == OADG_OP_BBO_AFFINE && op.bbo_count > 0) ++bbo_at_depth[d];
+          if (op.kind == OADG_OP_BG_AFFINE) any_bg = 1;
         }
         if (hist) ++n_hist;
       }
@@ -150,12 +154,16 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
   L.off_lut = take((size_t)(n_lut > 0 ? n_lut : 1) * 768);
+  L.any_bg = any_bg;
+  const size_t mask_px = (size_t)h.max_h * h.max_w;
+  L.off_maskf = take(any_bg ? (size_t)h.n_views * mask_px * sizeof(float) : 0);
+  L.off_masku = take(any_bg ? (size_t)h.n_views * mask_px : 0);
   L.total = o;
 }
 
 // Backend concept (all return 0 or an error code):
 //   upload(dst, src_host, bytes)  zero(dst, bytes)  copy(dst, src, bytes)
-//   profiles(P, pv, prof_x, prof_y)
+//   profiles(P, pv, prof_x, prof_y)           masks(P, n_views, maskf, masku)
 //   hist(P, lanes, lane_ids, n, hist, luma)   lut(P, jobs, n, hist, luma, luts)
 //   bbo_pass(P, chains, n, j, roi_w, roi_h)
 //   step(P, lanes, n, scratch, frame_bytes)   mix(P, jobs, n)
@@ -308,6 +316,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   P.max_w = h.max_w;
   P.max_h = h.max_h;
   P.luts = reinterpret_cast<const uint8_t*>(ws + L.off_lut);
+  P.maskf = reinterpret_cast<const float*>(ws + L.off_maskf);
+  P.masku = reinterpret_cast<const uint8_t*>(ws + L.off_masku);
+  P.mask_stride = (size_t)h.max_h * h.max_w;
   const Lane* d_lanes = reinterpret_cast<const Lane*>(dplan + t_lanes);
   const int32_t* d_lane_ids = reinterpret_cast<const int32_t*>(dplan + t_lane_ids);
   const LutJob* d_lut = reinterpret_cast<const LutJob*>(dplan + t_lut);
@@ -320,6 +331,10 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
 
   if (h.n_gt > 0) {
     rc = be.profiles(P, pv, const_cast<float*>(P.prof_x), const_cast<float*>(P.prof_y));
+    if (rc) return rc;
+  }
+  if (L.any_bg) {  // union mask of every view, once per batch (views without gt boxes get zeros)
+    rc = be.masks(P, h.n_views, const_cast<float*>(P.maskf), const_cast<uint8_t*>(P.masku));
     if (rc) return rc;
   }
   if (hist_n > 0) {

@@ -108,8 +108,9 @@ OADG_HD int bilerp_fix(int v00, int v01, int v10, int v11, int fx, int fy) {
 // One warped u8x3 pixel from a tightly packed HWC image (out-of-frame taps = 0).
 template <typename Ld>
 OADG_HD void warp_fetch3(Ld ld, const uint8_t* img, int H, int W, WarpTap t, int out[3]) {
-  const bool x0 = (unsigned)t.sx < (unsigned)W, x1 = (unsigned)(t.sx + 1) < (unsigned)W;
-  const bool y0 = (unsigned)t.sy < (unsigned)H, y1 = (unsigned)(t.sy + 1) < (unsigned)H;
+  // a tap whose weight is zero (fx == 0 / fy == 0: translations, one axis of the shears) is never read
+  const bool x0 = (unsigned)t.sx < (unsigned)W, x1 = t.fx != 0 && (unsigned)(t.sx + 1) < (unsigned)W;
+  const bool y0 = (unsigned)t.sy < (unsigned)H, y1 = t.fy != 0 && (unsigned)(t.sy + 1) < (unsigned)H;
   const uint8_t* r0 = img + ((size_t)t.sy * W + t.sx) * 3;
   const uint8_t* r1 = r0 + (size_t)W * 3;
 #pragma unroll

@@ -68,9 +68,6 @@ OADG_HD int chunk_get(const Chunk& c, int k) { return (int)((c.w[k >> 2] >> ((k 
 struct RegionInfo {            // one region (multi-level box or the outside) as seen from a tile
   int32_t present;             // the region intersects the tile
   int32_t op;                  // global op index of the region for this lane step
-  int32_t n_center, n_taps;    // gt boxes whose mask can be non-zero at the pixel / at the warped taps
-  int32_t overflow;            // more than kMaxCand candidates: evaluate every gt of the view
-  int32_t center[kMaxCand], taps[kMaxCand];
 };
 struct TileInfo {
   int32_t uniform;             // region id covering the whole tile, or -1 when several regions meet in it
@@ -101,75 +98,10 @@ OADG_HD void classify_step_tile(const DevPlan& P, const Lane& L, int x0, int y0,
     }
   }
   for (int r = 0; r <= V.n_ml; ++r) {
-    RegionInfo& R = T.R[r];
-    if (!R.present) continue;
-    R.op = L.op_base + r;
-    R.n_center = R.n_taps = R.overflow = 0;
-    const oadg_op_t& op = P.ops[R.op];
-    if (op.kind != OADG_OP_BG_AFFINE) continue;
-    T.any_bg = 1;
-    // source footprint of the tile under the inverse affine map: extremes sit at the corners; +-2 px of slack
-    // covers the fixed-point rounding and the second bilinear tap
-    double minv[6];
-    for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
-    int fx0 = 1 << 30, fy0 = 1 << 30, fx1 = -(1 << 30), fy1 = -(1 << 30);
-    for (int c = 0; c < 4; ++c) {
-      int xx = (c & 1) ? x1 - 1 : x0, yy = (c & 2) ? y1 - 1 : y0;
-      WarpTap t = warp_px(minv, warp_row(minv, yy), xx);
-      fx0 = imin(fx0, t.sx); fx1 = imax(fx1, t.sx);
-      fy0 = imin(fy0, t.sy); fy1 = imax(fy1, t.sy);
-    }
-    fx0 -= 2; fy0 -= 2; fx1 += 4; fy1 += 4;
-    for (int k = 0; k < V.n_gt; ++k) {
-      const int g = V.gt_first + k;
-      const int32_t* s = P.gts[g].supp;
-      if (rect_hit(s, x0, y0, x1, y1)) {
-        if (R.n_center < kMaxCand) R.center[R.n_center++] = g;
-        else R.overflow = 1;
-      }
-      if (rect_hit(s, fx0, fy0, fx1, fy1)) {
-        if (R.n_taps < kMaxCand) R.taps[R.n_taps++] = g;
-        else R.overflow = 1;
-      }
-    }
+    if (!T.R[r].present) continue;
+    T.R[r].op = L.op_base + r;
+    if (P.ops[T.R[r].op].kind == OADG_OP_BG_AFFINE) T.any_bg = 1;
   }
-}
-
-OADG_HD float union_mask_cand(const DevPlan& P, const int32_t* cand, int n, int x, int y) {
-  float m = 0.f;
-  for (int k = 0; k < n; ++k) {
-    float v = fg_mask(P, cand[k], x, y);
-    m = v > m ? v : m;
-  }
-  return m;
-}
-
-// One pixel under a bg-only op with the tile's candidate gt lists (bbox_augmentation.py:240-272).
-OADG_HD void bg_pixel_cand(const DevPlan& P, const Lane& L, const RegionInfo& R, int x, int y) {
-  const oadg_view_t& V = P.views[L.view];
-  const oadg_op_t& op = P.ops[R.op];
-  double minv[6];
-  for (int i = 0; i < 6; ++i) minv[i] = op.minv[i];
-  const WarpTap t = warp_px(minv, warp_row(minv, y), x);
-  int px[3];
-  warp_fetch3(LdRO(), L.in, V.H, V.W, t, px);
-  const size_t o = ((size_t)y * V.W + x) * 3;
-  if ((R.n_center | R.n_taps) != 0) {
-    const float M = union_mask_cand(P, R.center, R.n_center, x, y);
-    int mk[4];
-    for (int c = 0; c < 4; ++c) {
-      int xx = t.sx + (c & 1), yy = t.sy + (c >> 1);
-      mk[c] = ((unsigned)xx < (unsigned)V.W && (unsigned)yy < (unsigned)V.H)
-                  ? mask_to_u8(union_mask_cand(P, R.taps, R.n_taps, xx, yy)) : 0;
-    }
-    const int wm = bilerp_fix(mk[0], mk[1], mk[2], mk[3], t.fx, t.fy);
-    if (M != 0.f || wm != 0)  // keep == 0 => 0*img + 1*aug == aug exactly
-      for (int c = 0; c < 3; ++c) px[c] = bg_blend(M, wm, ldb(L.in + o + c), px[c]);
-  }
-  uint8_t* q = L.out + o;
-  q[0] = (uint8_t)px[0];
-  q[1] = (uint8_t)px[1];
-  q[2] = (uint8_t)px[2];
 }
 
 OADG_HD int region_of_pixel(const oadg_view_t& V, int x, int y) {
@@ -188,16 +120,6 @@ OADG_HD int region_of_run(const oadg_view_t& V, int x, int y, int n) {
     else return -1;
   }
   return r;
-}
-
-// one pixel, any op, using the tile's candidate lists where they help
-OADG_HD void step_pixel_cand(const DevPlan& P, const Lane& L, const TileInfo& T, const uint8_t* scratch,
-                             size_t frame_bytes, int x, int y) {
-  const oadg_view_t& V = P.views[L.view];
-  const int r = region_of_pixel(V, x, y);
-  const RegionInfo& R = T.R[r];
-  if (P.ops[R.op].kind == OADG_OP_BG_AFFINE && !R.overflow) bg_pixel_cand(P, L, R, x, y);
-  else step_pixel(P, L, scratch, frame_bytes, x, y);
 }
 
 // 16 pixels of one depth step.  `luts` holds the 3x256 table of region r at luts + r*768 when that region's op
@@ -240,7 +162,7 @@ OADG_HD void step_chunk(const DevPlan& P, const Lane& L, const TileInfo& T, cons
     }
   }
   // a box edge inside the run, or invert / color / sharpness: per pixel, byte stores
-  for (int i = 0; i < n; ++i) step_pixel_cand(P, L, T, scratch, frame_bytes, x + i, y);
+  for (int i = 0; i < n; ++i) step_pixel(P, L, scratch, frame_bytes, x + i, y);
 }
 
 // ---- mix ------------------------------------------------------------------------------------------

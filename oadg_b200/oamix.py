@@ -32,7 +32,7 @@ _AUG = {
 }
 
 
-PROFILE_KINDS = ('profile', 'hist', 'lut', 'bbo_pass', 'bbo_copyback', 'step', 'mix', 'copy')
+PROFILE_KINDS = ('profile', 'hist', 'lut', 'bbo_pass', 'mask', 'step', 'mix', 'copy')
 
 
 def get_aug_list(version):

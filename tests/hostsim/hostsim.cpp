@@ -84,6 +84,13 @@ struct HostBackend {
     ++launches;
     return 0;
   }
+  int masks(const DevPlan& P, int n_views, float* maskf, uint8_t* masku) {
+    for (int v = 0; v < n_views; ++v)
+      for (int y = 0; y < P.views[v].H; ++y)
+        for (int x = 0; x < P.views[v].W; ++x) mask_pixel(P, v, x, y, maskf, masku);
+    ++launches;
+    return 0;
+  }
   int hist(const DevPlan& P, const Lane* lanes, const int32_t* ids, int n, unsigned* hist, unsigned long long* luma) {
     for (int k = 0; k < n; ++k) {
       const Lane& L = lanes[ids[k]];
@@ -155,7 +162,7 @@ struct HostBackend {
               memcpy(luts + r * 768, P.luts + (size_t)P.ops[T.R[r].op].lut * 768, 768);
           for (int y = y0; y < y1; ++y) {
             if (T.any_bg) {
-              for (int x = x0; x < x1; ++x) step_pixel_cand(P, L, T, scratch, frame_bytes, x, y);
+              for (int x = x0; x < x1; ++x) step_pixel(P, L, scratch, frame_bytes, x, y);
             } else {
               for (int x = x0; x < x1; x += kChunkPx)
                 step_chunk(P, L, T, luts, scratch, frame_bytes, x, y, imin(kChunkPx, x1 - x), true);
