@@ -15,60 +15,12 @@
 #include <stdlib.h>
 
 #include "oadg_common.cuh"
+#include "oaloss.h"
 
 namespace oadg {
 namespace {
 
 constexpr int kC = 256;  // embedding width (out_dim_cont, ..._oadg.py:34); other widths go through the generic loop
-
-struct RowStats {  // per row, kept for backward
-  float lse;       // log sum_{k != i} exp(z_ik)
-  float coef;      // -(w/N)/n_i or 0
-  float npos;      // n_i
-  float pad;
-};
-
-struct LossWs {
-  float* fhat;       // [n, c] doubly normalised embeddings
-  float* inv1;       // [n] 1/max(||x||, eps)
-  float* inv2;       // [n] 1/max(||x/||x||||, eps)
-  RowStats* stats;   // [n]
-  int* meta;         // [0] bg label (low 32 bits), [1] n_fg, [2] active flag
-  float* npos;       // [n]
-  float* partial;    // [col_tiles][n][3]  (max, sumexp, possum)
-  float* dfhat;      // [n, c] gradient wrt fhat
-  float* f_hi;       // [n, c] TF32 split of fhat for the tcgen05 path
-  float* f_lo;
-  size_t bytes;
-};
-
-inline LossWs carve_loss_ws(void* base, int n, int c) {
-  LossWs w;
-  char* p = static_cast<char*>(base);
-  size_t o = 0;
-  auto take = [&](size_t b) {
-    size_t at = o;
-    o = align_up(o + b, 256);
-    return at;
-  };
-  const int col_tiles = (n + 63) / 64;
-  size_t o_f = take((size_t)n * c * 4), o_i1 = take((size_t)n * 4), o_i2 = take((size_t)n * 4);
-  size_t o_st = take((size_t)n * sizeof(RowStats)), o_meta = take(64), o_np = take((size_t)n * 4);
-  size_t o_pa = take((size_t)col_tiles * n * 3 * 4), o_df = take((size_t)n * c * 4);
-  size_t o_hi = take((size_t)n * c * 4), o_lo = take((size_t)n * c * 4);
-  w.fhat = reinterpret_cast<float*>(p + o_f);
-  w.inv1 = reinterpret_cast<float*>(p + o_i1);
-  w.inv2 = reinterpret_cast<float*>(p + o_i2);
-  w.stats = reinterpret_cast<RowStats*>(p + o_st);
-  w.meta = reinterpret_cast<int*>(p + o_meta);
-  w.npos = reinterpret_cast<float*>(p + o_np);
-  w.partial = reinterpret_cast<float*>(p + o_pa);
-  w.dfhat = reinterpret_cast<float*>(p + o_df);
-  w.f_hi = reinterpret_cast<float*>(p + o_hi);
-  w.f_lo = reinterpret_cast<float*>(p + o_lo);
-  w.bytes = o;
-  return w;
-}
 
 // ---- F.normalize twice (contrastive_loss_plus.py:41, contrastive_loss.py:155): warp per row
 __global__ void __launch_bounds__(256)
@@ -305,7 +257,7 @@ row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ n
     st.lse = lse;
     st.npos = np;
     st.coef = np > 0.f ? -(loss_weight / (float)n) / np : 0.f;
-    st.pad = 0.f;
+    st.u = st.coef * np * expf(-lse);
     stats[i] = st;
     if (np > 0.f) local += (double)(Ps / np - lse);
   }
@@ -395,9 +347,9 @@ sim_bwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels, 
 
 // chain rule through the two normalisations (warp per row), scaled by the upstream gradient
 __global__ void __launch_bounds__(256)
-normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dfhat, const float* __restrict__ inv1,
-                     const float* __restrict__ inv2, const int* __restrict__ meta, const float* __restrict__ gscale,
-                     int n, int c, int normalized_input, float* __restrict__ gx) {
+normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dpart, int n_part,
+                     const float* __restrict__ inv1, const float* __restrict__ inv2, const int* __restrict__ meta,
+                     const float* __restrict__ gscale, int n, int c, int normalized_input, float* __restrict__ gx) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   float* out = gx + (size_t)row * c;
@@ -407,36 +359,39 @@ normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dfha
   }
   const float g0 = *gscale;
   const float* xr = x + (size_t)row * c;
-  const float* gr = dfhat + (size_t)row * c;
   const float i1 = inv1[row], i2 = inv2[row];
+  // dL/dfhat of this row = sum of the column-split partials, in a fixed order (c == 256: 8 values per lane)
+  float gr[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float a = 0.f;
+    for (int p = 0; p < n_part; ++p) a += dpart[((size_t)p * n + row) * c + lane + 32 * q];
+    gr[q] = a;
+  }
   // second normalisation: v = x*i1, u = v*i2 ; g1 = (g - (u.g) u) * i2
   float dot = 0.f;
-  for (int k = lane; k < c; k += 32) dot += (xr[k] * i1 * i2) * gr[k];
+  for (int k = lane, q = 0; k < c; k += 32, ++q) dot += (xr[k] * i1 * i2) * gr[q];
   dot = warp_sum(dot);
   if (!normalized_input) {
-    for (int k = lane; k < c; k += 32) out[k] = g0 * (gr[k] - dot * (xr[k] * i2)) * i2;
+    for (int k = lane, q = 0; k < c; k += 32, ++q) out[k] = g0 * (gr[q] - dot * (xr[k] * i2)) * i2;
     return;
   }
   // first normalisation: u1 = x*i1 ; gx = (g1 - (u1.g1) u1) * i1
   float dot1 = 0.f;
-  for (int k = lane; k < c; k += 32) {
+  for (int k = lane, q = 0; k < c; k += 32, ++q) {
     float u = xr[k] * i1 * i2;
-    float g1 = (gr[k] - dot * u) * i2;
+    float g1 = (gr[q] - dot * u) * i2;
     dot1 += (xr[k] * i1) * g1;
   }
   dot1 = warp_sum(dot1);
-  for (int k = lane; k < c; k += 32) {
+  for (int k = lane, q = 0; k < c; k += 32, ++q) {
     float u = xr[k] * i1 * i2;
-    float g1 = (gr[k] - dot * u) * i2;
+    float g1 = (gr[q] - dot * u) * i2;
     out[k] = g0 * (g1 - dot1 * (xr[k] * i1)) * i1;
   }
 }
 
 }  // namespace
-
-// oaloss_tc.cu
-int launch_sim_fwd_tc(const float* fhat, float* hi, float* lo, const int64_t* labels, const int32_t* pair,
-                      const int* meta, int n, float inv_t, float* partial, cudaStream_t stream, int* launches);
 
 }  // namespace oadg
 
@@ -484,8 +439,7 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
   OADG_LAUNCH_CHECK();
   int red_tiles = col_tiles;
   if (loss_tc_enabled()) {
-    int rc = launch_sim_fwd_tc(w.fhat, w.f_hi, w.f_lo, labels_dev, pair_dev, w.meta, n, 1.f / temperature, w.partial,
-                               stream, &launches);
+    int rc = launch_sim_fwd_tc(w, labels_dev, pair_dev, n, 1.f / temperature, stream, &launches);
     if (rc) return rc;
     red_tiles = (n + 127) / 128;
   } else {
@@ -517,22 +471,35 @@ extern "C" int oadg_supcon_backward(const float* feats_dev, const int64_t* label
   LossWs w = carve_loss_ws(workspace_dev, n, c);
   if (workspace_bytes < w.bytes) return OADG_E_ARG;
   const int col_tiles = (n + kTN - 1) / kTN, row_tiles = (n + kTM - 1) / kTM;
-  OADG_CUDA_TRY(cudaMemsetAsync(w.dfhat, 0, (size_t)n * c * sizeof(float), stream));
-  int splits = (2 * kNumSMs + row_tiles - 1) / row_tiles;
-  if (splits > col_tiles) splits = col_tiles;
-  if (splits < 1) splits = 1;
-  const size_t smem = (size_t)2 * kTK * (kTM + 4) * 4 + (size_t)kTM * (kTN + 1) * 4;
-  static bool attr = false;
-  if (!attr) {
-    OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+  int launches = 0;
+  const float* dpart = w.dfhat;
+  int n_part = 1;
+  if (loss_tc_enabled()) {
+    int rc = launch_sim_bwd_tc(w, labels_dev, pair_dev, n, 1.f / temperature, stream, &launches);
+    if (rc) return rc;
+    dpart = w.dpart;
+    n_part = kBwdSplits;
+  } else {
+    OADG_CUDA_TRY(cudaMemsetAsync(w.dfhat, 0, (size_t)n * c * sizeof(float), stream));
+    int splits = (2 * kNumSMs + row_tiles - 1) / row_tiles;
+    if (splits > col_tiles) splits = col_tiles;
+    if (splits < 1) splits = 1;
+    const size_t smem = (size_t)2 * kTK * (kTM + 4) * 4 + (size_t)kTM * (kTN + 1) * 4;
+    static bool attr = false;
+    if (!attr) {
+      OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    sim_bwd_kernel<<<dim3(splits, row_tiles), kBwdThreads, smem, stream>>>(w.fhat, labels_dev, pair_dev, w.meta,
+                                                                           w.stats, n, c, 1.f / temperature, col_tiles,
+                                                                           w.dfhat);
+    OADG_LAUNCH_CHECK();
+    ++launches;
   }
-  sim_bwd_kernel<<<dim3(splits, row_tiles), kBwdThreads, smem, stream>>>(w.fhat, labels_dev, pair_dev, w.meta, w.stats,
-                                                                         n, c, 1.f / temperature, col_tiles, w.dfhat);
+  normalize_bwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(feats_dev, dpart, n_part, w.inv1, w.inv2, w.meta, grad_loss_dev,
+                                                       n, c, normalized_input, grad_feats_dev);
   OADG_LAUNCH_CHECK();
-  normalize_bwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(feats_dev, w.dfhat, w.inv1, w.inv2, w.meta, grad_loss_dev, n, c,
-                                                       normalized_input, grad_feats_dev);
-  OADG_LAUNCH_CHECK();
-  if (launches_out) *launches_out = 2;
+  ++launches;
+  if (launches_out) *launches_out = launches;
   return 0;
 }

@@ -1,0 +1,78 @@
+// Shared declarations of the OA-Loss kernels (oaloss.cu: CUDA-core path + API, oaloss_tc.cu: tcgen05 path).
+#pragma once
+#include "oadg_common.cuh"
+
+namespace oadg {
+
+constexpr int kBwdSplits = 8;   // column splits of the tcgen05 backward (deterministic partial sums)
+
+struct RowStats {  // per row, kept for backward
+  float lse;       // log sum_{k != i} exp(z_ik)
+  float coef;      // -(w/N)/n_i or 0
+  float npos;      // n_i
+  float u;         // coef * n_i * exp(-lse): the softmax part of dL/dz_ij is -exp(z_ij) * (u_i + u_j)
+};
+
+struct LossWs {
+  float* fhat;       // [n, c] doubly normalised embeddings
+  float* inv1;       // [n] 1/max(||x||, eps)
+  float* inv2;       // [n] 1/max(||x/||x||||, eps)
+  RowStats* stats;   // [n]
+  int* meta;         // [0] bg label (low 32 bits), [1] n_fg, [2] active flag
+  float* npos;       // [n]
+  float* partial;    // [col_tiles][n][3]  (max, sumexp, possum)
+  float* dfhat;      // [n, c] gradient wrt fhat
+  float* f_hi;       // [n, c] TF32 split of fhat for the tcgen05 path
+  float* f_lo;
+  float* ft_hi;      // [c, ld] transposed split (B operand of the backward GEMM)
+  float* ft_lo;
+  float* z;          // [n, ld] logits kept by the tcgen05 forward for its backward (L2-resident, 17 MB at n=2088)
+  float* dpart;      // [kBwdSplits][n, c] partial gradients of the tcgen05 backward
+  int ld;            // n rounded up to 32
+  size_t bytes;
+};
+
+inline LossWs carve_loss_ws(void* base, int n, int c) {
+  LossWs w;
+  char* p = static_cast<char*>(base);
+  size_t o = 0;
+  auto take = [&](size_t b) {
+    size_t at = o;
+    o = align_up(o + b, 256);
+    return at;
+  };
+  const int col_tiles = (n + 63) / 64;
+  size_t o_f = take((size_t)n * c * 4), o_i1 = take((size_t)n * 4), o_i2 = take((size_t)n * 4);
+  size_t o_st = take((size_t)n * sizeof(RowStats)), o_meta = take(64), o_np = take((size_t)n * 4);
+  size_t o_pa = take((size_t)col_tiles * n * 3 * 4), o_df = take((size_t)n * c * 4);
+  size_t o_hi = take((size_t)n * c * 4), o_lo = take((size_t)n * c * 4);
+  const int ld = (n + 31) / 32 * 32;
+  size_t o_th = take((size_t)c * ld * 4), o_tl = take((size_t)c * ld * 4);
+  size_t o_z = take((size_t)n * ld * 4), o_dp = take((size_t)kBwdSplits * n * c * 4);
+  w.fhat = reinterpret_cast<float*>(p + o_f);
+  w.inv1 = reinterpret_cast<float*>(p + o_i1);
+  w.inv2 = reinterpret_cast<float*>(p + o_i2);
+  w.stats = reinterpret_cast<RowStats*>(p + o_st);
+  w.meta = reinterpret_cast<int*>(p + o_meta);
+  w.npos = reinterpret_cast<float*>(p + o_np);
+  w.partial = reinterpret_cast<float*>(p + o_pa);
+  w.dfhat = reinterpret_cast<float*>(p + o_df);
+  w.f_hi = reinterpret_cast<float*>(p + o_hi);
+  w.f_lo = reinterpret_cast<float*>(p + o_lo);
+  w.ft_hi = reinterpret_cast<float*>(p + o_th);
+  w.ft_lo = reinterpret_cast<float*>(p + o_tl);
+  w.z = reinterpret_cast<float*>(p + o_z);
+  w.dpart = reinterpret_cast<float*>(p + o_dp);
+  w.ld = ld;
+  w.bytes = o;
+  return w;
+}
+
+
+// oaloss_tc.cu
+int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
+                      cudaStream_t stream, int* launches);
+int launch_sim_bwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
+                      cudaStream_t stream, int* launches);
+
+}  // namespace oadg

@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include "oadg_common.cuh"
+#include "oaloss.h"
 
 namespace oadg {
 namespace tc {
@@ -92,18 +93,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// split the normalised embeddings into the two TF32 operands
+// split the normalised embeddings into the two TF32 operands, row-major [n, 256] for the forward and
+// transposed [256, ld] for the backward GEMM (32 x 32 tiles through shared memory)
 __global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ f, size_t count, float* __restrict__ hi, float* __restrict__ lo) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  float v = f[i];
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  float r = __fsub_rn(v, __uint_as_float(h));
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  hi[i] = __uint_as_float(h);
-  lo[i] = __uint_as_float(l);
+split_tf32_kernel(const float* __restrict__ f, int n, int ld, float* __restrict__ hi, float* __restrict__ lo,
+                  float* __restrict__ thi, float* __restrict__ tlo) {
+  __shared__ float sh[32][33], sl[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + k * 8;
+    float h = 0.f, l = 0.f;
+    if (r < n) {
+      const float v = f[(size_t)r * 256 + c0 + tx];
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      const float rem = __fsub_rn(v, __uint_as_float(hb));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+      h = __uint_as_float(hb);
+      l = __uint_as_float(lb);
+      hi[(size_t)r * 256 + c0 + tx] = h;
+      lo[(size_t)r * 256 + c0 + tx] = l;
+    }
+    sh[ty + k * 8][tx] = h;
+    sl[ty + k * 8][tx] = l;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + k * 8, r = r0 + tx;
+    if (r < ld) {
+      thi[(size_t)c * ld + r] = sh[tx][ty + k * 8];
+      tlo[(size_t)c * ld + r] = sl[tx][ty + k * 8];
+    }
+  }
 }
 
 __device__ __forceinline__ bool is_pos(long long yi, long long yj, long long bg, int i, int j, int pair_i) {
@@ -114,7 +138,8 @@ __device__ __forceinline__ bool is_pos(long long yi, long long yj, long long bg,
 __global__ void __launch_bounds__(128, 1)
 sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                   const int64_t* __restrict__ labels, const int32_t* __restrict__ pair,
-                  const int* __restrict__ meta, int n, float inv_t, float* __restrict__ partial) {
+                  const int* __restrict__ meta, int n, float inv_t, float* __restrict__ partial,
+                  float* __restrict__ zout, int ld) {
   if (!meta[2]) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -201,6 +226,13 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
       r[q] = __float_as_uint(z);
       if (j < n) cm = fmaxf(cm, z);
     }
+    if (row_ok && j0 + c0 < ld) {  // keep the logits for the backward (128 B per thread, L2-resident)
+      float4* zp = reinterpret_cast<float4*>(zout + (size_t)i * ld + j0 + c0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        zp[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                            __uint_as_float(r[4 * q + 3]));
+    }
     if (cm > m) {
       s *= expf(m - cm);
       m = cm;
@@ -243,13 +275,14 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [n, 256] fp32 row-major; box = 32 floats (128 B) x 128 rows; 128-byte swizzle; OOB rows read as zero
-inline int make_map(CUtensorMap* map, const float* base, int n) {
+// 2-D fp32 tensor [rows, cols] with row pitch ld_elems; box = 32 floats (128 B) x box_rows; 128-byte swizzle;
+// out-of-bounds elements read as zero
+inline int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld_elems, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
-  cuuint64_t dims[2] = {256, (cuuint64_t)n};
-  cuuint64_t strides[1] = {256 * sizeof(float)};
-  cuuint32_t box[2] = {kKC, kM};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * sizeof(float)};
+  cuuint32_t box[2] = {kKC, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -257,29 +290,236 @@ inline int make_map(CUtensorMap* map, const float* base, int n) {
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward: dF[I] += A[I, Jchunk] . F[Jchunk, :] / T  with  A = G + G^T built on the fly from the stored logits
+//   a_ij = ( c_i P_ij + c_j P_ji - exp(z_ij) (u_i + u_j) ) / T ,  a_ii = 0
+// CTA = (row block I of 128 rows, column split s); per 32-column chunk:
+//   TMA      z[I, chunk] (A operand buffer, K-major), Ft_hi / Ft_lo[:, chunk] (B operand, N = 256 channels)
+//   8 warps  transform z -> a in place (hi) and into the lo buffer (3xTF32), fence to the async proxy
+//   1 thread 12 x tcgen05.mma.kind::tf32 (M=128, N=256, K=8) into 256 TMEM columns
+// The CTA's 128 x 256 fp32 result goes to dpart[s] (summed deterministically by normalize_bwd_kernel).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBN = 256;
+constexpr int kBStages = 2;
+constexpr int kBStageBytes = 2 * kOperandBytes + 2 * (kBN * kKC * 4);   // z/a_hi + a_lo + Ft_hi + Ft_lo = 96 KB
+constexpr int kBSmemBytes = kBStages * kBStageBytes + 1024;
+constexpr int kBThreads = 320;                                           // 8 transform warps + TMA warp + MMA warp
+constexpr uint32_t kIdescB = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32_n256(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a), "l"(b), "r"(kIdescB), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kBThreads, 1)
+sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_thi,
+                  const __grid_constant__ CUtensorMap tm_tlo, const int64_t* __restrict__ labels,
+                  const int32_t* __restrict__ pair, const int* __restrict__ meta,
+                  const RowStats* __restrict__ stats, int n, float inv_t, int chunks_per_split,
+                  float* __restrict__ dpart) {
+  if (!meta[2]) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[kBStages], ready_bar[kBStages], empty_bar[kBStages], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_cj[kBStages][kKC], s_uj[kBStages][kKC];
+  __shared__ long long s_yj[kBStages][kKC];
+  __shared__ int s_pj[kBStages][kKC];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.y * kM;
+  const int total_chunks = (n + kKC - 1) / kKC;
+  const int kc0 = blockIdx.x * chunks_per_split;
+  const int kc1 = min(kc0 + chunks_per_split, total_chunks);
+  const int nk = max(kc1 - kc0, 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ready_bar[s], 256);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)kBN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 8) {
+    if (lane == 0) {  // ---- TMA producer
+      for (int k = 0; k < nk; ++k) {
+        const int s = k % kBStages, kc = kc0 + k;
+        if (k >= kBStages) mbar_wait(&empty_bar[s], ((k / kBStages) - 1) & 1);
+        uint8_t* st = smem + s * kBStageBytes;
+        mbar_expect_tx(&full_bar[s], kOperandBytes + 2 * kBN * kKC * 4);
+        tma_load_2d(st, &tm_z, &full_bar[s], kc * kKC, i0);
+        tma_load_2d(st + 2 * kOperandBytes, &tm_thi, &full_bar[s], kc * kKC, 0);
+        tma_load_2d(st + 2 * kOperandBytes + kBN * kKC * 4, &tm_tlo, &full_bar[s], kc * kKC, 0);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {  // ---- MMA issuer
+      for (int k = 0; k < nk; ++k) {
+        const int s = k % kBStages;
+        mbar_wait(&ready_bar[s], (k / kBStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = smem_u32(smem + s * kBStageBytes);
+        const uint64_t ah = umma_desc(base), al = umma_desc(base + kOperandBytes);
+        const uint64_t bh = umma_desc(base + 2 * kOperandBytes), bl = umma_desc(base + 2 * kOperandBytes + kBN * kKC * 4);
+#pragma unroll
+        for (int q = 0; q < kKC / 8; ++q) {
+          const uint64_t adv = (uint64_t)((q * 32) >> 4);
+          umma_tf32_n256(tmem_base, ah + adv, bh + adv, (k | q) ? 1u : 0u);
+          umma_tf32_n256(tmem_base, ah + adv, bl + adv, 1u);
+          umma_tf32_n256(tmem_base, al + adv, bh + adv, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    // ---- transform warps: thread -> (row = tid & 127, half = tid >> 7: 16 of the chunk's 32 columns)
+    const int row = tid & 127, half = tid >> 7;
+    const int i = i0 + row;
+    const bool row_ok = i < n;
+    const long long bg = (long long)meta[0];
+    const long long yi = row_ok ? labels[i] : 0;
+    const int pi = row_ok ? pair[i] : -1;
+    RowStats si = row_ok ? stats[i] : RowStats{0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < nk; ++k) {
+      const int s = k % kBStages, kc = kc0 + k;
+      // column metadata of this chunk (the stage's previous user finished: its MMAs were committed before the
+      // producer refilled the stage, and every transform thread passed ready_bar for it)
+      if (tid < kKC) {
+        const int j = kc * kKC + tid;
+        const bool ok = j < n;
+        RowStats sj = ok ? stats[j] : RowStats{0.f, 0.f, 0.f, 0.f};
+        s_cj[s][tid] = sj.coef;
+        s_uj[s][tid] = sj.u;
+        s_yj[s][tid] = ok ? labels[j] : (long long)-0x7fffffffffffffffLL;
+        s_pj[s][tid] = ok ? pair[j] : -1;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 transform warps only
+      mbar_wait(&full_bar[s], (k / kBStages) & 1);
+      uint8_t* st = smem + s * kBStageBytes;
+      float4* zrow = reinterpret_cast<float4*>(st + row * 128);
+      float4* lrow = reinterpret_cast<float4*>(st + kOperandBytes + row * 128);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int c = half * 4 + c4;              // logical 16-byte chunk: columns 4c .. 4c+3
+        const int pc = c ^ (row & 7);             // 128-byte swizzle
+        float4 zv = zrow[pc];
+        float z[4] = {zv.x, zv.y, zv.z, zv.w}, hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int jj = c * 4 + e, j = kc * kKC + jj;
+          float a = 0.f;
+          if (row_ok && j < n && j != i) {
+            const long long yj = s_yj[s][jj];
+            float pterm = 0.f;
+            if (yi == yj) {
+              if (yi != bg) pterm = si.coef + s_cj[s][jj];
+              else pterm = (j == pi ? si.coef : 0.f) + (s_pj[s][jj] == i ? s_cj[s][jj] : 0.f);
+            }
+            a = (pterm - expf(z[e]) * (si.u + s_uj[s][jj])) * inv_t;
+          }
+          uint32_t hb, lb;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+          const float rem = __fsub_rn(a, __uint_as_float(hb));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+          hi[e] = __uint_as_float(hb);
+          lo[e] = __uint_as_float(lb);
+        }
+        zrow[pc] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        lrow[pc] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+      mbar_arrive(&ready_bar[s]);
+    }
+    // ---- epilogue: warps 0-3 own columns 0..127, warps 4-7 columns 128..255 of TMEM lane quadrant warp % 4
+    mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3, chalf = warp >> 2;
+    const int orow = i0 + q * 32 + lane;
+    float* out = dpart + ((size_t)blockIdx.x * n + orow) * kBN + chalf * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chalf * 128 + c0), r);
+      if (orow < n) {
+        float4* o4 = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          o4[e] = nk > 0 ? make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
+                                       __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kBN));
+}
+
 }  // namespace tc
 
-// Launches the tcgen05 forward: fills `partial` [col_tiles_128][n][3].  Returns 0 or an error code.
-int launch_sim_fwd_tc(const float* fhat, float* hi, float* lo, const int64_t* labels, const int32_t* pair,
-                      const int* meta, int n, float inv_t, float* partial, cudaStream_t stream, int* launches) {
+int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
+                      cudaStream_t stream, int* launches) {
   using namespace tc;
-  const size_t count = (size_t)n * 256;
-  split_tf32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(fhat, count, hi, lo);
+  split_tf32_kernel<<<dim3((w.ld + 31) / 32, 8), 256, 0, stream>>>(w.fhat, n, w.ld, w.f_hi, w.f_lo, w.ft_hi, w.ft_lo);
   OADG_LAUNCH_CHECK();
   CUtensorMap mh, ml;
-  int rc = make_map(&mh, hi, n);
+  int rc = make_map(&mh, w.f_hi, n, 256, 256, kM);
   if (rc) return rc;
-  rc = make_map(&ml, lo, n);
+  rc = make_map(&ml, w.f_lo, n, 256, 256, kM);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
     OADG_CUDA_TRY(cudaFuncSetAttribute(sim_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     attr = true;
   }
   const int tiles = (n + kM - 1) / kM;
-  sim_fwd_tc_kernel<<<dim3(tiles, tiles), 128, kSmemBytes, stream>>>(mh, ml, labels, pair, meta, n, inv_t, partial);
+  sim_fwd_tc_kernel<<<dim3(tiles, tiles), 128, kSmemBytes, stream>>>(mh, ml, labels, pair, w.meta, n, inv_t, w.partial,
+                                                                    w.z, w.ld);
   OADG_LAUNCH_CHECK();
   if (launches) *launches += 2;
+  return 0;
+}
+
+int launch_sim_bwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
+                      cudaStream_t stream, int* launches) {
+  using namespace tc;
+  CUtensorMap mz, mth, mtl;
+  int rc = make_map(&mz, w.z, n, w.ld, w.ld, kM);
+  if (rc) return rc;
+  rc = make_map(&mth, w.ft_hi, 256, w.ld, w.ld, kBN);
+  if (rc) return rc;
+  rc = make_map(&mtl, w.ft_lo, 256, w.ld, w.ld, kBN);
+  if (rc) return rc;
+  const int tiles = (n + kM - 1) / kM;
+  const int total_chunks = (n + kKC - 1) / kKC;
+  const int cps = (total_chunks + kBwdSplits - 1) / kBwdSplits;
+  sim_bwd_tc_kernel<<<dim3(kBwdSplits, tiles), kBThreads, kBSmemBytes, stream>>>(mz, mth, mtl, labels, pair, w.meta,
+                                                                                 w.stats, n, inv_t, cps, w.dpart);
+  OADG_LAUNCH_CHECK();
+  if (launches) *launches += 1;
   return 0;
 }
 
