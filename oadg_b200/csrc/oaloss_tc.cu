@@ -17,6 +17,7 @@
 //   4 warps    epilogue: tcgen05.ld 32 lanes x 32 columns at a time; each thread owns one row
 //              of the tile and keeps an online (max, sum-exp, positive-sum) over its 128 columns
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "oadg_common.cuh"
 #include "oaloss.h"
@@ -278,6 +279,9 @@ inline EncodeTiledFn encode_fn() {
 // 2-D fp32 tensor [rows, cols] with row pitch ld_elems; box = 32 floats (128 B) x box_rows; 128-byte swizzle;
 // out-of-bounds elements read as zero
 inline int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld_elems, int box_rows) {
+  // the driver entry point needs a current context on the calling thread (torch's autograd thread has
+  // only used the runtime API so far): cudaFree(0) binds the primary context
+  cudaFree(0);
   EncodeTiledFn fn = encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -287,6 +291,9 @@ inline int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && getenv("OADG_DEBUG"))
+    fprintf(stderr, "[oadg] cuTensorMapEncodeTiled failed: %d (base %p rows %d cols %d ld %d box_rows %d)\n", (int)r,
+            (const void*)base, rows, cols, ld_elems, box_rows);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
@@ -518,7 +525,13 @@ int launch_sim_bwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pai
   const int cps = (total_chunks + kBwdSplits - 1) / kBwdSplits;
   sim_bwd_tc_kernel<<<dim3(kBwdSplits, tiles), kBThreads, kBSmemBytes, stream>>>(mz, mth, mtl, labels, pair, w.meta,
                                                                                  w.stats, n, inv_t, cps, w.dpart);
-  OADG_LAUNCH_CHECK();
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      if (getenv("OADG_DEBUG")) fprintf(stderr, "[oadg] sim_bwd_tc_kernel launch failed: %s\n", cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
   if (launches) *launches += 1;
   return 0;
 }

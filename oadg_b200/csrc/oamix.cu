@@ -224,48 +224,53 @@ bbo_pass_kernel(DevPlan P, const Chain* __restrict__ chains, int j) {
 }
 
 // ------------------------------------------------------------------------------------
-// one depth step of every live lane (oa_mix.py:226-234).  A CTA owns a 512 x 32 pixel tile: it classifies the
-// tile once (uniform op or region border; gt masks that can be non-zero), stages the op's LUT in shared memory,
-// then each warp streams rows: LUT / copy tiles as 16-pixel chunks (3 x 16-byte vectors per thread), bg-only
-// tiles lane-per-pixel so that the 4-tap gathers of a warp stay within a few cache lines.
-// grid = (ceil(W/512), ceil(H/32), lanes)
+// one depth step of every live lane (oa_mix.py:226-234).  A CTA owns a 256 x 16 pixel tile and one Lane record.
+//   streaming tile (one LUT / bbo-copy region covers it): one 16-pixel chunk (3 x 16-byte vectors) per thread,
+//       loads issued before the region's 3 x 256 LUT is staged in shared memory
+//   any other tile: 16 pixels per thread, consecutive lanes on consecutive pixels (gathers stay within a few lines)
+// grid = (ceil(W/256), ceil(H/16), lanes)
 // ------------------------------------------------------------------------------------
 constexpr int kTileThreads = 256;
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 4)
 step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict__ scratch, size_t frame_bytes) {
-  __shared__ TileInfo T;
-  __shared__ __align__(16) uint8_t lut_s[OADG_MAX_REGIONS * 768];
-  const Lane L = lanes[blockIdx.z];
-  const oadg_view_t& V = P.views[L.view];
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  if (x0 >= V.W || y0 >= V.H) return;
-  const int x1 = min(x0 + kTileW, V.W), y1 = min(y0 + kTileH, V.H);
-  if (threadIdx.x == 0) classify_step_tile(P, L, x0, y0, x1, y1, T);
+  __shared__ __align__(16) uint8_t lut_s[768];
+  __shared__ Lane Ls;
+  if (threadIdx.x < sizeof(Lane) / 4)
+    reinterpret_cast<uint32_t*>(&Ls)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(lanes + blockIdx.z) + threadIdx.x);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (T.any_bg) {
-    // lane-per-pixel mapping: the 4-tap gathers of a warp stay within a few cache lines
-    for (int y = y0 + warp; y < y1; y += kTileThreads / 32)
-      for (int x = x0 + lane; x < x1; x += 32) step_pixel(P, L, scratch, frame_bytes, x, y);
+  const Lane& L = Ls;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  if (x0 >= L.W || y0 >= L.H) return;
+  const int x1 = min(x0 + kTileW, L.W), y1 = min(y0 + kTileH, L.H);
+  const int region = tile_region(L, x0, y0, x1, y1);
+  const int t = threadIdx.x;
+  if (tile_streams(L, region)) {
+    const bool vec = ((L.W * 3) & 15) == 0 &&
+                     ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
+    const int y = y0 + (t >> 4), x = x0 + (t & 15) * kChunkPx;
+    const bool live = y < y1 && x < x1;
+    const int n = live ? min(kChunkPx, x1 - x) : 0;
+    Chunk in;
+    if (live) chunk_load(stream_src(L, region, scratch, frame_bytes) + ((size_t)y * L.W + x) * 3, n, vec, in);
+    if (L.lut[region] >= 0) {  // uniform over the CTA
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(P.luts + (size_t)L.lut[region] * 768);
+      if (t < 192) reinterpret_cast<uint32_t*>(lut_s)[t] = __ldg(src + t);
+      __syncthreads();
+    }
+    if (live) stream_chunk(L, region, lut_s, scratch, frame_bytes, in, x, y, n, vec);
     return;
   }
-  for (int r = 0; r <= V.n_ml; ++r) {
-    if (!T.R[r].present || !is_lut_kind(P.ops[T.R[r].op].kind)) continue;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.luts + (size_t)P.ops[T.R[r].op].lut * 768);
-    if (threadIdx.x < 192) reinterpret_cast<uint32_t*>(lut_s + r * 768)[threadIdx.x] = __ldg(src + threadIdx.x);
+#pragma unroll 1
+  for (int it = 0; it < kTileW * kTileH / kTileThreads; ++it) {
+    const int idx = it * kTileThreads + t;
+    const int x = x0 + (idx & (kTileW - 1)), y = y0 + idx / kTileW;
+    if (x < x1 && y < y1) step_pixel(P, L, scratch, frame_bytes, x, y);
   }
-  __syncthreads();
-  const bool vec = ((V.W * 3) & 15) == 0 &&
-                   ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
-  const int x = x0 + lane * kChunkPx;
-  if (x >= x1) return;
-  const int n = min(kChunkPx, x1 - x);
-  for (int y = y0 + warp; y < y1; y += kTileThreads / 32) step_chunk(P, L, T, lut_s, scratch, frame_bytes, x, y, n, vec);
 }
 
 // branch mixing + object-aware mixing (oa_mix.py:236,281-309), same tiling; grid = (.., .., views)
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 2)
 mix_kernel(DevPlan P, const MixJob* __restrict__ jobs) {
   __shared__ MixTile T;
   const MixJob J = jobs[blockIdx.z];
@@ -275,14 +280,13 @@ mix_kernel(DevPlan P, const MixJob* __restrict__ jobs) {
   const int x1 = min(x0 + kTileW, V.W), y1 = min(y0 + kTileH, V.H);
   if (threadIdx.x == 0) classify_mix_tile(P, J, x0, y0, x1, y1, T);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uintptr_t al = ((uintptr_t)J.src) | ((uintptr_t)J.out);
   for (int b = 0; b < V.width; ++b) al |= (uintptr_t)J.branch[b];
   const bool vec = ((V.W * 3) & 15) == 0 && (al & 15) == 0;
-  const int x = x0 + lane * kChunkPx;
-  if (x >= x1) return;
-  const int n = min(kChunkPx, x1 - x);
-  for (int y = y0 + warp; y < y1; y += kTileThreads / 32) mix_chunk(P, J, T, x, y, n, vec);
+  const int t = threadIdx.x;
+  const int y = y0 + (t >> 4), x = x0 + (t & 15) * kChunkPx;
+  if (x >= x1 || y >= y1) return;
+  mix_chunk(P, J, T, x, y, min(kChunkPx, x1 - x), vec);
 }
 
 #define BE_TRY(expr)                       \

@@ -34,6 +34,13 @@ struct Lane {            // one (view, branch) chain alive at the current depth
   int32_t hist_slot;     // -1 if no histogram needed
   const uint8_t* in;
   uint8_t* out;
+  // copied from the plan by the host so that a CTA needs one record, not a chain of dependent loads:
+  int32_t H, W, n_ml;
+  int32_t box[2][4];                 // multi-level boxes
+  int32_t kind[OADG_MAX_REGIONS];    // op kind of region r (r = n_ml: outside)
+  int32_t lut[OADG_MAX_REGIONS];     // LUT slot of region r or -1
+  int32_t scratch[OADG_MAX_REGIONS]; // bbo result frame slot of region r or -1
+  int32_t pad;
 };
 
 struct Chain {           // one bboxes-only op being evaluated (sequential over its boxes)

@@ -243,6 +243,13 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
         ln.in = d == 0 ? src[V.img] : branch_frame(v, b, (d - 1) & 1);
         ln.out = branch_frame(v, b, d & 1);
         ln.hist_slot = -1;
+        ln.H = V.H;
+        ln.W = V.W;
+        ln.n_ml = V.n_ml;
+        ln.pad = 0;
+        for (int q = 0; q < 2; ++q)
+          for (int e = 0; e < 4; ++e) ln.box[q][e] = q < V.n_ml ? V.ml_box[q][e] : 0;
+        for (int r = 0; r < OADG_MAX_REGIONS; ++r) ln.kind[r] = ln.lut[r] = ln.scratch[r] = -1;
         final_frame[(size_t)v * OADG_MAX_WIDTH + b] = ln.out;
         bool hist = false;
         for (int r = 0; r <= V.n_ml; ++r) hist |= needs_hist(ops[ln.op_base + r].kind);
@@ -286,6 +293,11 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
               D.max_roi_h = (y1 - y0) > D.max_roi_h ? (y1 - y0) : D.max_roi_h;
             }
           }
+        }
+        for (int r = 0; r <= V.n_ml; ++r) {
+          ln.kind[r] = ops[ln.op_base + r].kind;
+          ln.lut[r] = ops[ln.op_base + r].lut;
+          ln.scratch[r] = ops[ln.op_base + r].scratch;
         }
         ++lane_n;
         ++D.n_lanes;

@@ -1,6 +1,8 @@
-// Tile-level bodies of the OA-Mix step / mix kernels: a CTA owns a kTileW x kTileH pixel tile, classifies it
-// once (which region/op covers it, which gt masks can be non-zero there) and then streams 16-pixel chunks
-// (48 bytes = three 16-byte vectors) per thread.  Shared with tests/hostsim (test infrastructure only).
+// Tile-level bodies of the OA-Mix step / mix kernels.  A CTA of 256 threads owns a 256 x 16 pixel tile.
+// Streaming tiles (one LUT / bbo-copy region covers the tile) move one 16-pixel chunk (48 bytes = three
+// 16-byte vectors) per thread; every other tile (region borders, bg-only / invert / colour / sharpness ops)
+// is evaluated pixel by pixel with consecutive lanes on consecutive pixels.  Shared with tests/hostsim
+// (test infrastructure only).
 #pragma once
 #include <string.h>
 
@@ -9,8 +11,8 @@
 namespace oadg {
 
 constexpr int kChunkPx = 16;  // 16 px * 3 B = 48 B = 3 x uint4: the smallest pixel run that is 16-byte periodic
-constexpr int kTileW = 512;   // 32 lanes x 16 px
-constexpr int kTileH = 32;    // 8 warps x 4 rows
+constexpr int kTileW = 256;   // 16 chunks
+constexpr int kTileH = 16;    // 16 x 16 chunks = 256 threads
 constexpr int kMaxCand = 12;
 
 struct Chunk {
@@ -65,104 +67,56 @@ OADG_HD void chunk_store(uint8_t* p, int n, bool vec, const Chunk& c) {
 // byte k (0..47) of a chunk; k must be a compile-time constant after unrolling for register residency
 OADG_HD int chunk_get(const Chunk& c, int k) { return (int)((c.w[k >> 2] >> ((k & 3) * 8)) & 255u); }
 
-struct RegionInfo {            // one region (multi-level box or the outside) as seen from a tile
-  int32_t present;             // the region intersects the tile
-  int32_t op;                  // global op index of the region for this lane step
-};
-struct TileInfo {
-  int32_t uniform;             // region id covering the whole tile, or -1 when several regions meet in it
-  int32_t any_bg;              // some present region runs a bg-only op: the tile uses the lane-per-pixel mapping
-  RegionInfo R[OADG_MAX_REGIONS];
-};
-
 OADG_HD bool rect_hit(const int32_t* s, int x0, int y0, int x1, int y1) {
   return s[0] < x1 && s[2] > x0 && s[1] < y1 && s[3] > y0;
 }
 
-// classify the tile [x0,x1) x [y0,y1) of lane L
-OADG_HD void classify_step_tile(const DevPlan& P, const Lane& L, int x0, int y0, int x1, int y1, TileInfo& T) {
-  const oadg_view_t& V = P.views[L.view];
-  T.uniform = V.n_ml;
-  T.any_bg = 0;
-  for (int r = 0; r < OADG_MAX_REGIONS; ++r) T.R[r].present = 0;
-  T.R[V.n_ml].present = 1;
-  for (int b = 0; b < V.n_ml; ++b) {
-    const int32_t* B = V.ml_box[b];
+// Region that covers the whole tile [x0,x1) x [y0,y1), or -1 when a multi-level box edge crosses it.
+OADG_HD int tile_region(const Lane& L, int x0, int y0, int x1, int y1) {
+  int region = L.n_ml;
+  for (int b = 0; b < L.n_ml; ++b) {
+    const int32_t* B = L.box[b];
     if (!rect_hit(B, x0, y0, x1, y1)) continue;
-    T.R[b].present = 1;
-    if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) {  // tile inside box b
-      T.uniform = b;
-      T.R[V.n_ml].present = 0;
-    } else {
-      T.uniform = -1;
-    }
-  }
-  for (int r = 0; r <= V.n_ml; ++r) {
-    if (!T.R[r].present) continue;
-    T.R[r].op = L.op_base + r;
-    if (P.ops[T.R[r].op].kind == OADG_OP_BG_AFFINE) T.any_bg = 1;
-  }
-}
-
-OADG_HD int region_of_pixel(const oadg_view_t& V, int x, int y) {
-  int r = V.n_ml;
-  for (int b = 0; b < V.n_ml; ++b)
-    if (x >= V.ml_box[b][0] && x < V.ml_box[b][2] && y >= V.ml_box[b][1] && y < V.ml_box[b][3]) r = b;
-  return r;
-}
-// region covering the whole pixel run [x, x+n) of row y, or -1 when a box edge falls inside it
-OADG_HD int region_of_run(const oadg_view_t& V, int x, int y, int n) {
-  int r = V.n_ml;
-  for (int b = 0; b < V.n_ml; ++b) {
-    const int32_t* B = V.ml_box[b];
-    if (y < B[1] || y >= B[3] || B[0] >= x + n || B[2] <= x) continue;
-    if (B[0] <= x && B[2] >= x + n) r = b;
+    if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = b;
     else return -1;
   }
-  return r;
+  return region;
+}
+// a tile streams when one region covers it and that region's op is a table lookup or a bbo-result copy
+OADG_HD bool tile_streams(const Lane& L, int region) {
+  return region >= 0 && (is_lut_kind(L.kind[region]) || L.kind[region] == OADG_OP_BBO_AFFINE);
 }
 
-// 16 pixels of one depth step.  `luts` holds the 3x256 table of region r at luts + r*768 when that region's op
-// is a LUT op (shared memory on the device).
-OADG_HD void step_chunk(const DevPlan& P, const Lane& L, const TileInfo& T, const uint8_t* luts,
-                        const uint8_t* scratch, size_t frame_bytes, int x, int y, int n, bool vec) {
-  const oadg_view_t& V = P.views[L.view];
-  const size_t o = ((size_t)y * V.W + x) * 3;
-  const int r = T.uniform >= 0 ? T.uniform : region_of_run(V, x, y, n);
-  if (r >= 0) {
-    const oadg_op_t& op = P.ops[T.R[r].op];
-    const int kind = op.kind;
-    Chunk out;
-    if (is_lut_kind(kind)) {
-      const uint8_t* lut = luts + r * 768;
-      Chunk in;
-      chunk_load(L.in + o, n, vec, in);
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-      for (int i = 0; i < 12; ++i) {
-        uint32_t v = 0;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-        for (int b = 0; b < 4; ++b) {
-          const int k = i * 4 + b;
-          v |= (uint32_t)lut[(k % 3) * 256 + chunk_get(in, k)] << (8 * b);
-        }
-        out.w[i] = v;
-      }
-      chunk_store(L.out + o, n, vec, out);
-      return;
-    }
-    if (kind == OADG_OP_BBO_AFFINE) {
-      const uint8_t* s = op.scratch >= 0 ? scratch + (size_t)op.scratch * frame_bytes : L.in;
-      chunk_load(s + o, n, vec, out);
-      chunk_store(L.out + o, n, vec, out);
-      return;
-    }
+// 16 pixels of a streaming tile.  `lut`: the region's 3x256 table (shared memory on the device).
+OADG_HD void stream_chunk(const Lane& L, int region, const uint8_t* lut, const uint8_t* scratch, size_t frame_bytes,
+                          const Chunk& in, int x, int y, int n, bool vec) {
+  const size_t o = ((size_t)y * L.W + x) * 3;
+  if (L.kind[region] == OADG_OP_BBO_AFFINE) {  // `in` already holds the bbo result (or the input when no box was valid)
+    chunk_store(L.out + o, n, vec, in);
+    return;
   }
-  // a box edge inside the run, or invert / color / sharpness: per pixel, byte stores
-  for (int i = 0; i < n; ++i) step_pixel(P, L, scratch, frame_bytes, x + i, y);
+  Chunk out;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < 12; ++i) {
+    uint32_t v = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int b = 0; b < 4; ++b) {
+      const int k = i * 4 + b;
+      v |= (uint32_t)lut[(k % 3) * 256 + chunk_get(in, k)] << (8 * b);
+    }
+    out.w[i] = v;
+  }
+  chunk_store(L.out + o, n, vec, out);
+}
+// source frame of a streaming chunk: the lane input, or the bbo scratch frame
+OADG_HD const uint8_t* stream_src(const Lane& L, int region, const uint8_t* scratch, size_t frame_bytes) {
+  if (L.kind[region] == OADG_OP_BBO_AFFINE && L.scratch[region] >= 0)
+    return scratch + (size_t)L.scratch[region] * frame_bytes;
+  return L.in;
 }
 
 // ---- mix ------------------------------------------------------------------------------------------
@@ -185,53 +139,67 @@ OADG_HD void classify_mix_tile(const DevPlan& P, const MixJob& J, int x0, int y0
   }
 }
 
+// 16 pixels of branch mixing + object-aware mixing, 4 pixels (12 bytes = 3 words) at a time
 OADG_HD void mix_chunk(const DevPlan& P, const MixJob& J, const MixTile& T, int x, int y, int n, bool vec) {
   const oadg_view_t& V = P.views[J.view];
   const size_t o = ((size_t)y * V.W + x) * 3;
-  if (T.overflow) {
+  if (T.overflow || V.width > 4) {
     for (int i = 0; i < n; ++i) mix_pixel(P, J, x + i, y);
     return;
   }
-  Chunk src, out;
+  Chunk src, br[4], out;
   chunk_load(J.src + o, n, vec, src);
-  float acc[kChunkPx * 3];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-  for (int k = 0; k < kChunkPx * 3; ++k) acc[k] = 0.f;
-  for (int b = 0; b < V.width; ++b) {
-    Chunk br;
-    chunk_load(J.branch[b] + o, n, vec, br);
-    const float wgt = V.ws[b];
+  for (int b = 0; b < 4; ++b)
+    if (b < V.width) chunk_load(J.branch[b] + o, n, vec, br[b]);
+  const float w0 = V.ws[0], w1 = V.ws[1], w2 = V.ws[2], w3 = V.ws[3];
+  const int width = V.width;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int k = 0; k < kChunkPx * 3; ++k) acc[k] = fadd(acc[k], fmul(wgt, (float)chunk_get(br, k)));
-  }
+  for (int g = 0; g < 4; ++g) {     // pixels 4g .. 4g+3 = bytes 12g .. 12g+11 = words 3g .. 3g+2
+    float acc[12];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-  for (int i = 0; i < kChunkPx; ++i) {
-    float orig[3] = {0.f, 0.f, 0.f}, aug[3] = {0.f, 0.f, 0.f};
-    MixMask ms = {0.f, 0.f};
-    const int img[3] = {chunk_get(src, i * 3), chunk_get(src, i * 3 + 1), chunk_get(src, i * 3 + 2)};
-    if (i < n) {
-      for (int t = 0; t < T.n; ++t) {
-        const oadg_target_t& G = P.tgts[T.idx[t]];
-        float mask;
-        if (G.kind == 0) mask = fg_mask(P, G.gt, x + i, y);
-        else mask = (x + i >= G.box[0] && x + i < G.box[2] && y >= G.box[1] && y < G.box[3]) ? 1.f : 0.f;
-        if (mask == 0.f) continue;
-        const float w = mix_target_weight(ms, mask);
-        for (int c = 0; c < 3; ++c) mix_accumulate(orig[c], aug[c], G.m_oa, img[c], acc[i * 3 + c], w);
+    for (int k = 0; k < 12; ++k) {
+      const int kk = g * 12 + k;
+      float a = fadd(0.f, fmul(w0, (float)chunk_get(br[0], kk)));
+      if (width > 1) a = fadd(a, fmul(w1, (float)chunk_get(br[1], kk)));
+      if (width > 2) a = fadd(a, fmul(w2, (float)chunk_get(br[2], kk)));
+      if (width > 3) a = fadd(a, fmul(w3, (float)chunk_get(br[3], kk)));
+      acc[k] = a;
+    }
+    uint32_t ow[3] = {0u, 0u, 0u};
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+      const int px = g * 4 + i;
+      float orig[3] = {0.f, 0.f, 0.f}, aug[3] = {0.f, 0.f, 0.f};
+      MixMask ms = {0.f, 0.f};
+      const int img[3] = {chunk_get(src, px * 3), chunk_get(src, px * 3 + 1), chunk_get(src, px * 3 + 2)};
+      if (px < n) {
+        for (int t = 0; t < T.n; ++t) {
+          const oadg_target_t& G = P.tgts[T.idx[t]];
+          float mask;
+          if (G.kind == 0) mask = fg_mask(P, G.gt, x + px, y);
+          else mask = (x + px >= G.box[0] && x + px < G.box[2] && y >= G.box[1] && y < G.box[3]) ? 1.f : 0.f;
+          if (mask == 0.f) continue;
+          const float w = mix_target_weight(ms, mask);
+          for (int c = 0; c < 3; ++c) mix_accumulate(orig[c], aug[c], G.m_oa, img[c], acc[i * 3 + c], w);
+        }
+      }
+      for (int c = 0; c < 3; ++c) {
+        const int k = i * 3 + c;
+        ow[k >> 2] |= (uint32_t)mix_finish(orig[c], aug[c], V.m, img[c], acc[k], ms.sum) << ((k & 3) * 8);
       }
     }
-    for (int c = 0; c < 3; ++c) {
-      const int k = i * 3 + c;
-      const uint32_t v = (uint32_t)mix_finish(orig[c], aug[c], V.m, img[c], acc[k], ms.sum);
-      if ((k & 3) == 0) out.w[k >> 2] = v;
-      else out.w[k >> 2] |= v << ((k & 3) * 8);
-    }
+    out.w[g * 3] = ow[0];
+    out.w[g * 3 + 1] = ow[1];
+    out.w[g * 3 + 2] = ow[2];
   }
   chunk_store(J.out + o, n, vec, out);
 }

@@ -145,28 +145,27 @@ struct HostBackend {
     ++launches;
     return 0;
   }
-  // mirrors step_kernel: 512 x 32 tiles, classify once, LUT / copy tiles in 16-px chunks, bg tiles per pixel
+  // mirrors step_kernel: 256 x 16 tiles; streaming tiles in 16-px chunks, every other tile per pixel
   int step(const DevPlan& P, const Lane* lanes, int n, const uint8_t* scratch, size_t frame_bytes) {
     for (int k = 0; k < n; ++k) {
       const Lane& L = lanes[k];
-      const oadg_view_t& V = P.views[L.view];
-      for (int y0 = 0; y0 < V.H; y0 += kTileH)
-        for (int x0 = 0; x0 < V.W; x0 += kTileW) {
-          const int x1 = imin(x0 + kTileW, V.W), y1 = imin(y0 + kTileH, V.H);
-          TileInfo T;
-          classify_step_tile(P, L, x0, y0, x1, y1, T);
-          // region r's LUT lives at luts + r*768 (shared memory on the device)
-          uint8_t luts[OADG_MAX_REGIONS * 768];
-          for (int r = 0; r <= V.n_ml; ++r)
-            if (T.R[r].present && is_lut_kind(P.ops[T.R[r].op].kind))
-              memcpy(luts + r * 768, P.luts + (size_t)P.ops[T.R[r].op].lut * 768, 768);
-          for (int y = y0; y < y1; ++y) {
-            if (T.any_bg) {
+      for (int y0 = 0; y0 < L.H; y0 += kTileH)
+        for (int x0 = 0; x0 < L.W; x0 += kTileW) {
+          const int x1 = imin(x0 + kTileW, L.W), y1 = imin(y0 + kTileH, L.H);
+          const int region = tile_region(L, x0, y0, x1, y1);
+          if (tile_streams(L, region)) {
+            const uint8_t* lut = L.lut[region] >= 0 ? P.luts + (size_t)L.lut[region] * 768 : nullptr;
+            const uint8_t* src = stream_src(L, region, scratch, frame_bytes);
+            for (int y = y0; y < y1; ++y)
+              for (int x = x0; x < x1; x += kChunkPx) {
+                const int nn = imin(kChunkPx, x1 - x);
+                Chunk in;
+                chunk_load(src + ((size_t)y * L.W + x) * 3, nn, true, in);
+                stream_chunk(L, region, lut, scratch, frame_bytes, in, x, y, nn, true);
+              }
+          } else {
+            for (int y = y0; y < y1; ++y)
               for (int x = x0; x < x1; ++x) step_pixel(P, L, scratch, frame_bytes, x, y);
-            } else {
-              for (int x = x0; x < x1; x += kChunkPx)
-                step_chunk(P, L, T, luts, scratch, frame_bytes, x, y, imin(kChunkPx, x1 - x), true);
-            }
           }
         }
     }
