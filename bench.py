@@ -244,7 +244,7 @@ def product_arm(args):
         j = (i * BS) % POOL
         imgs = [dev_frames[(j + b) % POOL] for b in range(BS)]
         g = [gts[(j + b) % POOL] for b in range(BS)]
-        mix.oamix_batch(imgs, g, profile=profile, outs=out_bufs)
+        mix.oamix_batch(imgs, g, profile=profile, outs=out_bufs, inputs_ready=True)  # frames resident since setup
         n_mix = mix.last_launches
         x_dev.grad = None
         loss = loss_fn(x_dev, labels_dev)

@@ -21,6 +21,9 @@
 namespace oadg {
 namespace {
 
+// i / 255 in float64 (the reference divides a uint8 array by the python int 255, bbox_augmentation.py:267)
+__device__ const double g_div255[256] = {0.0 / 255.0, 1.0 / 255.0, 2.0 / 255.0, 3.0 / 255.0, 4.0 / 255.0, 5.0 / 255.0, 6.0 / 255.0, 7.0 / 255.0, 8.0 / 255.0, 9.0 / 255.0, 10.0 / 255.0, 11.0 / 255.0, 12.0 / 255.0, 13.0 / 255.0, 14.0 / 255.0, 15.0 / 255.0, 16.0 / 255.0, 17.0 / 255.0, 18.0 / 255.0, 19.0 / 255.0, 20.0 / 255.0, 21.0 / 255.0, 22.0 / 255.0, 23.0 / 255.0, 24.0 / 255.0, 25.0 / 255.0, 26.0 / 255.0, 27.0 / 255.0, 28.0 / 255.0, 29.0 / 255.0, 30.0 / 255.0, 31.0 / 255.0, 32.0 / 255.0, 33.0 / 255.0, 34.0 / 255.0, 35.0 / 255.0, 36.0 / 255.0, 37.0 / 255.0, 38.0 / 255.0, 39.0 / 255.0, 40.0 / 255.0, 41.0 / 255.0, 42.0 / 255.0, 43.0 / 255.0, 44.0 / 255.0, 45.0 / 255.0, 46.0 / 255.0, 47.0 / 255.0, 48.0 / 255.0, 49.0 / 255.0, 50.0 / 255.0, 51.0 / 255.0, 52.0 / 255.0, 53.0 / 255.0, 54.0 / 255.0, 55.0 / 255.0, 56.0 / 255.0, 57.0 / 255.0, 58.0 / 255.0, 59.0 / 255.0, 60.0 / 255.0, 61.0 / 255.0, 62.0 / 255.0, 63.0 / 255.0, 64.0 / 255.0, 65.0 / 255.0, 66.0 / 255.0, 67.0 / 255.0, 68.0 / 255.0, 69.0 / 255.0, 70.0 / 255.0, 71.0 / 255.0, 72.0 / 255.0, 73.0 / 255.0, 74.0 / 255.0, 75.0 / 255.0, 76.0 / 255.0, 77.0 / 255.0, 78.0 / 255.0, 79.0 / 255.0, 80.0 / 255.0, 81.0 / 255.0, 82.0 / 255.0, 83.0 / 255.0, 84.0 / 255.0, 85.0 / 255.0, 86.0 / 255.0, 87.0 / 255.0, 88.0 / 255.0, 89.0 / 255.0, 90.0 / 255.0, 91.0 / 255.0, 92.0 / 255.0, 93.0 / 255.0, 94.0 / 255.0, 95.0 / 255.0, 96.0 / 255.0, 97.0 / 255.0, 98.0 / 255.0, 99.0 / 255.0, 100.0 / 255.0, 101.0 / 255.0, 102.0 / 255.0, 103.0 / 255.0, 104.0 / 255.0, 105.0 / 255.0, 106.0 / 255.0, 107.0 / 255.0, 108.0 / 255.0, 109.0 / 255.0, 110.0 / 255.0, 111.0 / 255.0, 112.0 / 255.0, 113.0 / 255.0, 114.0 / 255.0, 115.0 / 255.0, 116.0 / 255.0, 117.0 / 255.0, 118.0 / 255.0, 119.0 / 255.0, 120.0 / 255.0, 121.0 / 255.0, 122.0 / 255.0, 123.0 / 255.0, 124.0 / 255.0, 125.0 / 255.0, 126.0 / 255.0, 127.0 / 255.0, 128.0 / 255.0, 129.0 / 255.0, 130.0 / 255.0, 131.0 / 255.0, 132.0 / 255.0, 133.0 / 255.0, 134.0 / 255.0, 135.0 / 255.0, 136.0 / 255.0, 137.0 / 255.0, 138.0 / 255.0, 139.0 / 255.0, 140.0 / 255.0, 141.0 / 255.0, 142.0 / 255.0, 143.0 / 255.0, 144.0 / 255.0, 145.0 / 255.0, 146.0 / 255.0, 147.0 / 255.0, 148.0 / 255.0, 149.0 / 255.0, 150.0 / 255.0, 151.0 / 255.0, 152.0 / 255.0, 153.0 / 255.0, 154.0 / 255.0, 155.0 / 255.0, 156.0 / 255.0, 157.0 / 255.0, 158.0 / 255.0, 159.0 / 255.0, 160.0 / 255.0, 161.0 / 255.0, 162.0 / 255.0, 163.0 / 255.0, 164.0 / 255.0, 165.0 / 255.0, 166.0 / 255.0, 167.0 / 255.0, 168.0 / 255.0, 169.0 / 255.0, 170.0 / 255.0, 171.0 / 255.0, 172.0 / 255.0, 173.0 / 255.0, 174.0 / 255.0, 175.0 / 255.0, 176.0 / 255.0, 177.0 / 255.0, 178.0 / 255.0, 179.0 / 255.0, 180.0 / 255.0, 181.0 / 255.0, 182.0 / 255.0, 183.0 / 255.0, 184.0 / 255.0, 185.0 / 255.0, 186.0 / 255.0, 187.0 / 255.0, 188.0 / 255.0, 189.0 / 255.0, 190.0 / 255.0, 191.0 / 255.0, 192.0 / 255.0, 193.0 / 255.0, 194.0 / 255.0, 195.0 / 255.0, 196.0 / 255.0, 197.0 / 255.0, 198.0 / 255.0, 199.0 / 255.0, 200.0 / 255.0, 201.0 / 255.0, 202.0 / 255.0, 203.0 / 255.0, 204.0 / 255.0, 205.0 / 255.0, 206.0 / 255.0, 207.0 / 255.0, 208.0 / 255.0, 209.0 / 255.0, 210.0 / 255.0, 211.0 / 255.0, 212.0 / 255.0, 213.0 / 255.0, 214.0 / 255.0, 215.0 / 255.0, 216.0 / 255.0, 217.0 / 255.0, 218.0 / 255.0, 219.0 / 255.0, 220.0 / 255.0, 221.0 / 255.0, 222.0 / 255.0, 223.0 / 255.0, 224.0 / 255.0, 225.0 / 255.0, 226.0 / 255.0, 227.0 / 255.0, 228.0 / 255.0, 229.0 / 255.0, 230.0 / 255.0, 231.0 / 255.0, 232.0 / 255.0, 233.0 / 255.0, 234.0 / 255.0, 235.0 / 255.0, 236.0 / 255.0, 237.0 / 255.0, 238.0 / 255.0, 239.0 / 255.0, 240.0 / 255.0, 241.0 / 255.0, 242.0 / 255.0, 243.0 / 255.0, 244.0 / 255.0, 245.0 / 255.0, 246.0 / 255.0, 247.0 / 255.0, 248.0 / 255.0, 249.0 / 255.0, 250.0 / 255.0, 251.0 / 255.0, 252.0 / 255.0, 253.0 / 255.0, 254.0 / 255.0, 255.0 / 255.0};
+
 // ------------------------------------------------------------------------------------
 // blurred-mask profiles (oa_mix.py:78-91): indicator on the 1/sr canvas -> GaussianBlur
 // (separable, BORDER_REFLECT_101, float32 kernel from getGaussianKernel) -> bilinear
@@ -211,6 +214,9 @@ lut_kernel(DevPlan P, const LutJob* __restrict__ jobs, const unsigned* __restric
 // pass j: Y[roi_j] = blend(X, warp_j(X), m_j), Y[roi_{j-1} \\ roi_j] = X  with (X, Y) = (S, T) swapping per box.
 // grid = (ceil(max_roi_w/32), ceil(max_roi_h/8), chains)
 // ------------------------------------------------------------------------------------
+// Each thread walks 8 rows of one column of the pass rectangle: the box record, the support rectangles and the
+// x-dependent half of the fixed-point affine coordinates are loaded / computed once per thread.
+constexpr int kBboRows = 8;
 __global__ void __launch_bounds__(256)
 bbo_pass_kernel(DevPlan P, const Chain* __restrict__ chains, int j) {
   const Chain C = chains[blockIdx.z];
@@ -218,54 +224,188 @@ bbo_pass_kernel(DevPlan P, const Chain* __restrict__ chains, int j) {
   int r[4];
   bbo_pass_rect(P, C, j, r);
   const int x = r[0] + blockIdx.x * 32 + threadIdx.x;
-  const int y = r[1] + blockIdx.y * 8 + threadIdx.y;
-  if (x >= r[2] || y >= r[3]) return;
-  bbo_pixel(P, C, j, x, y);
+  const int yb = r[1] + (blockIdx.y * 8 + threadIdx.y) * kBboRows;
+  if (x >= r[2] || yb >= r[3]) return;
+  const uint8_t* X = (j & 1) ? C.T : C.S;
+  uint8_t* Y = (j & 1) ? C.S : C.T;
+  const oadg_bbo_t& B = P.bbo[C.bbo_first + j];
+  const int g = B.gt;
+  const oadg_view_t& V = P.views[C.view];
+  const int W = V.W, H = V.H;
+  int cur[4], prev[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cur[i] = P.gts[g].supp[i];
+  if (j > 0) {
+    const int32_t* q = P.gts[P.bbo[C.bbo_first + j - 1].gt].supp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) prev[i] = q[i];
+  }
+  double minv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) minv[i] = B.minv[i];
+  const bool x_cur = x >= cur[0] && x < cur[2], x_prev = x >= prev[0] && x < prev[2];
+  if (!x_cur && !x_prev) return;
+  const int ax = cv_round(dmul(dmul(minv[0], (double)x), 1024.0));
+  const int bx = cv_round(dmul(dmul(minv[3], (double)x), 1024.0));
+  const float ux = x_cur ? __ldg(P.prof_x + (size_t)g * P.max_w + x) : 0.f;
+  const float* py = P.prof_y + (size_t)g * P.max_h;
+  const int y_end = min(yb + kBboRows, r[3]);
+#pragma unroll 1
+  for (int y = yb; y < y_end; ++y) {
+    const size_t o = ((size_t)y * W + x) * 3;
+    if (!(x_cur && y >= cur[1] && y < cur[3])) {
+      if (x_prev && y >= prev[1] && y < prev[3]) {  // catch up the pixels only box j-1 touched
+        Y[o] = X[o];
+        Y[o + 1] = X[o + 1];
+        Y[o + 2] = X[o + 2];
+      }
+      continue;
+    }
+    const float m = fmul(__ldg(py + y), ux);
+    int v[3] = {X[o], X[o + 1], X[o + 2]};
+    if (m != 0.f) {  // m == 0 => img*1 + aug*0 == img exactly
+      const int Xf = (cv_round(dmul(dadd(dmul(minv[1], (double)y), minv[2]), 1024.0)) + 16 + ax) >> 5;
+      const int Yf = (cv_round(dmul(dadd(dmul(minv[4], (double)y), minv[5]), 1024.0)) + 16 + bx) >> 5;
+      WarpTap t;
+      t.sx = imin(imax(Xf >> 5, -32768), 32767);
+      t.sy = imin(imax(Yf >> 5, -32768), 32767);
+      t.fx = Xf & 31;
+      t.fy = Yf & 31;
+      int a[3];
+      warp_fetch3(LdRW(), X, H, W, t, a);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = bbo_blend(m, v[c], a[c]);
+    }
+    Y[o] = (uint8_t)v[0];
+    Y[o + 1] = (uint8_t)v[1];
+    Y[o + 2] = (uint8_t)v[2];
+  }
 }
 
 // ------------------------------------------------------------------------------------
-// one depth step of every live lane (oa_mix.py:226-234).  A CTA owns a 256 x 16 pixel tile and one Lane record.
-//   streaming tile (one LUT / bbo-copy region covers it): one 16-pixel chunk (3 x 16-byte vectors) per thread,
-//       loads issued before the region's 3 x 256 LUT is staged in shared memory
-//   any other tile: 16 pixels per thread, consecutive lanes on consecutive pixels (gathers stay within a few lines)
-// grid = (ceil(W/256), ceil(H/16), lanes)
+// one depth step of every live lane (oa_mix.py:226-234).  A CTA owns a 256 x 32 pixel tile of one lane.
+//   streaming tile (one LUT / bbo-copy region covers it): two 16-pixel chunks (3 x 16-byte vectors each) per
+//       thread; the lane's LUTs live at a slot computable from blockIdx alone, so their loads, the Lane record
+//       and the pixel loads are all in flight together
+//   any other tile: 32 pixels per thread, consecutive lanes on consecutive pixels (gathers stay within a few
+//       cache lines); the op parameters of the lane's regions are staged in shared memory, the x-dependent
+//       half of the fixed-point affine coordinates is hoisted out of the row loop
+// grid = (ceil(W/256), ceil(H/32), lanes)
 // ------------------------------------------------------------------------------------
 constexpr int kTileThreads = 256;
 
+struct RegOp {      // op parameters of one region, staged in shared memory for per-pixel tiles
+  int32_t kind, p0, p1;
+  float factor;
+  double minv[6];
+};
+
+// one pixel of a bg-only op with hoisted coordinate terms (same arithmetic as bg_pixel / eval_op)
+__device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, const RegOp& R, int ax, int bx,
+                                              const double* __restrict__ div255, int x, int y) {
+  const int X = (cv_round(dmul(dadd(dmul(R.minv[1], (double)y), R.minv[2]), 1024.0)) + 16 + ax) >> 5;
+  const int Y = (cv_round(dmul(dadd(dmul(R.minv[4], (double)y), R.minv[5]), 1024.0)) + 16 + bx) >> 5;
+  WarpTap t;
+  t.sx = imin(imax(X >> 5, -32768), 32767);
+  t.sy = imin(imax(Y >> 5, -32768), 32767);
+  t.fx = X & 31;
+  t.fy = Y & 31;
+  int px[3];
+  warp_fetch3(LdRO(), L.in, L.H, L.W, t, px);
+  const size_t mo = (size_t)L.view * P.mask_stride;
+  const float M = __ldg(P.maskf + mo + (size_t)y * L.W + x);
+  const uint8_t* mu = P.masku + mo;
+  const bool x0 = (unsigned)t.sx < (unsigned)L.W, x1 = t.fx != 0 && (unsigned)(t.sx + 1) < (unsigned)L.W;
+  const bool y0 = (unsigned)t.sy < (unsigned)L.H, y1 = t.fy != 0 && (unsigned)(t.sy + 1) < (unsigned)L.H;
+  const uint8_t* r0 = mu + (size_t)t.sy * L.W + t.sx;
+  const uint8_t* r1 = r0 + L.W;
+  const int wm = bilerp_fix((y0 && x0) ? ldb(r0) : 0, (y0 && x1) ? ldb(r0 + 1) : 0, (y1 && x0) ? ldb(r1) : 0,
+                            (y1 && x1) ? ldb(r1 + 1) : 0, t.fx, t.fy);
+  const size_t o = ((size_t)y * L.W + x) * 3;
+  if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
+    const double am = __ldg(div255 + wm);  // wm / 255 in float64, tabulated (exactly the reference's quotient)
+    const double keep = (double)M > am ? (double)M : am;
+    const double rest = dsub(1.0, keep);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      px[c] = (int)dadd(dmul(keep, (double)ldb(L.in + o + c)), dmul(rest, (double)px[c]));
+  }
+  uint8_t* q = L.out + o;
+  q[0] = (uint8_t)px[0];
+  q[1] = (uint8_t)px[1];
+  q[2] = (uint8_t)px[2];
+}
+
 __global__ void __launch_bounds__(kTileThreads, 4)
-step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict__ scratch, size_t frame_bytes) {
-  __shared__ __align__(16) uint8_t lut_s[768];
-  __shared__ Lane Ls;
-  if (threadIdx.x < sizeof(Lane) / 4)
-    reinterpret_cast<uint32_t*>(&Ls)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(lanes + blockIdx.z) + threadIdx.x);
-  __syncthreads();
-  const Lane& L = Ls;
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  if (x0 >= L.W || y0 >= L.H) return;
-  const int x1 = min(x0 + kTileW, L.W), y1 = min(y0 + kTileH, L.H);
-  const int region = tile_region(L, x0, y0, x1, y1);
+step_kernel(DevPlan P, const Lane* __restrict__ lanes, int lane0, const uint8_t* __restrict__ scratch,
+            size_t frame_bytes, const double* __restrict__ div255) {
+  __shared__ __align__(16) uint8_t lut_s[OADG_MAX_REGIONS * 768];
+  __shared__ RegOp rop[OADG_MAX_REGIONS];
   const int t = threadIdx.x;
+  // the lane's LUT slots are (lane0 + blockIdx.z) * 3 + r: prefetch all three tables (garbage for non-LUT regions)
+  const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(P.luts + (size_t)(lane0 + blockIdx.z) * OADG_MAX_REGIONS * 768);
+  const uint32_t l0 = __ldg(lsrc + t), l1 = __ldg(lsrc + 256 + t), l2 = t < 64 ? __ldg(lsrc + 512 + t) : 0u;
+  const Lane& L = lanes[blockIdx.z];
+  const int W = L.W, H = L.H;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  if (x0 >= W || y0 >= H) return;
+  const int x1 = min(x0 + kTileW, W), y1 = min(y0 + kTileH, H);
+  const int region = tile_region(L, x0, y0, x1, y1);
   if (tile_streams(L, region)) {
-    const bool vec = ((L.W * 3) & 15) == 0 &&
+    const uint8_t* src = stream_src(L, region, scratch, frame_bytes);
+    const bool vec = ((W * 3) & 15) == 0 &&
                      ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
-    const int y = y0 + (t >> 4), x = x0 + (t & 15) * kChunkPx;
-    const bool live = y < y1 && x < x1;
-    const int n = live ? min(kChunkPx, x1 - x) : 0;
-    Chunk in;
-    if (live) chunk_load(stream_src(L, region, scratch, frame_bytes) + ((size_t)y * L.W + x) * 3, n, vec, in);
-    if (L.lut[region] >= 0) {  // uniform over the CTA
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(P.luts + (size_t)L.lut[region] * 768);
-      if (t < 192) reinterpret_cast<uint32_t*>(lut_s)[t] = __ldg(src + t);
-      __syncthreads();
-    }
-    if (live) stream_chunk(L, region, lut_s, scratch, frame_bytes, in, x, y, n, vec);
+    const int x = x0 + (t & 15) * kChunkPx;
+    const int ya = y0 + (t >> 4), yb = ya + 16;
+    const int n = x < x1 ? min(kChunkPx, x1 - x) : 0;
+    const bool la = n > 0 && ya < y1, lb = n > 0 && yb < y1;
+    Chunk ca, cb;
+    if (la) chunk_load(src + ((size_t)ya * W + x) * 3, n, vec, ca);
+    if (lb) chunk_load(src + ((size_t)yb * W + x) * 3, n, vec, cb);
+    uint32_t* ls = reinterpret_cast<uint32_t*>(lut_s);
+    ls[t] = l0;
+    ls[256 + t] = l1;
+    if (t < 64) ls[512 + t] = l2;
+    __syncthreads();
+    const uint8_t* lut = lut_s + region * 768;
+    if (la) stream_chunk(L, region, lut, scratch, frame_bytes, ca, x, ya, n, vec);
+    if (lb) stream_chunk(L, region, lut, scratch, frame_bytes, cb, x, yb, n, vec);
     return;
   }
+  // ---- per-pixel tile
+  if (t <= L.n_ml) {
+    const oadg_op_t& op = P.ops[L.op_base + t];
+    rop[t].kind = op.kind;
+    rop[t].p0 = op.p0;
+    rop[t].p1 = op.p1;
+    rop[t].factor = op.factor;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rop[t].minv[i] = op.minv[i];
+  }
+  __syncthreads();
+  const int x = x0 + t;  // this thread's column is fixed: idx = it*256 + t
+  if (x >= x1) return;
+  int ax[OADG_MAX_REGIONS], bx[OADG_MAX_REGIONS];
+#pragma unroll
+  for (int r = 0; r < OADG_MAX_REGIONS; ++r) {
+    ax[r] = bx[r] = 0;
+    if (r <= L.n_ml && rop[r].kind == OADG_OP_BG_AFFINE) {
+      ax[r] = cv_round(dmul(dmul(rop[r].minv[0], (double)x), 1024.0));
+      bx[r] = cv_round(dmul(dmul(rop[r].minv[3], (double)x), 1024.0));
+    }
+  }
 #pragma unroll 1
-  for (int it = 0; it < kTileW * kTileH / kTileThreads; ++it) {
-    const int idx = it * kTileThreads + t;
-    const int x = x0 + (idx & (kTileW - 1)), y = y0 + idx / kTileW;
-    if (x < x1 && y < y1) step_pixel(P, L, scratch, frame_bytes, x, y);
+  for (int y = y0; y < y1; ++y) {
+    int r = L.n_ml;
+    for (int b = 0; b < L.n_ml; ++b)
+      if (x >= L.box[b][0] && x < L.box[b][2] && y >= L.box[b][1] && y < L.box[b][3]) r = b;
+    if (rop[r].kind == OADG_OP_BG_AFFINE) {
+      const int axr = r == 0 ? ax[0] : (r == 1 ? ax[1] : ax[2]);
+      const int bxr = r == 0 ? bx[0] : (r == 1 ? bx[1] : bx[2]);
+      bg_pixel_fast(P, L, rop[r], axr, bxr, div255, x, y);
+    } else {
+      step_pixel(P, L, scratch, frame_bytes, x, y);
+    }
   }
 }
 
@@ -284,9 +424,11 @@ mix_kernel(DevPlan P, const MixJob* __restrict__ jobs) {
   for (int b = 0; b < V.width; ++b) al |= (uintptr_t)J.branch[b];
   const bool vec = ((V.W * 3) & 15) == 0 && (al & 15) == 0;
   const int t = threadIdx.x;
-  const int y = y0 + (t >> 4), x = x0 + (t & 15) * kChunkPx;
-  if (x >= x1 || y >= y1) return;
-  mix_chunk(P, J, T, x, y, min(kChunkPx, x1 - x), vec);
+  const int x = x0 + (t & 15) * kChunkPx;
+  if (x >= x1) return;
+  const int n = min(kChunkPx, x1 - x);
+#pragma unroll 1
+  for (int y = y0 + (t >> 4); y < y1; y += 16) mix_chunk(P, J, T, x, y, n, vec);
 }
 
 #define BE_TRY(expr)                       \
@@ -376,15 +518,18 @@ struct CudaBackend {
   }
   int bbo_pass(const DevPlan& P, const Chain* chains, int n, int j, int roi_w, int roi_h) {
     begin();
-    bbo_pass_kernel<<<dim3((roi_w + 31) / 32, (roi_h + 7) / 8, n), dim3(32, 8), 0, stream>>>(P, chains, j);
+    bbo_pass_kernel<<<dim3((roi_w + 31) / 32, (roi_h + 8 * kBboRows - 1) / (8 * kBboRows), n), dim3(32, 8), 0, stream>>>(
+        P, chains, j);
     BE_TRY(cudaGetLastError());
     end(kKBboPass);
     return 0;
   }
-  int step(const DevPlan& P, const Lane* lanes, int n, const uint8_t* scratch, size_t frame_bytes) {
+  int step(const DevPlan& P, const Lane* lanes, int n, int lane0, const uint8_t* scratch, size_t frame_bytes) {
     dim3 grid((P.max_w + kTileW - 1) / kTileW, (P.max_h + kTileH - 1) / kTileH, n);
+    const double* div255 = nullptr;
+    BE_TRY(cudaGetSymbolAddress((void**)&div255, g_div255));
     begin();
-    step_kernel<<<grid, kTileThreads, 0, stream>>>(P, lanes, scratch, frame_bytes);
+    step_kernel<<<grid, kTileThreads, 0, stream>>>(P, lanes, lane0, scratch, frame_bytes, div255);
     BE_TRY(cudaGetLastError());
     end(kKStep);
     return 0;

@@ -153,7 +153,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.off_scratch = take((size_t)L.n_scratch * L.frame_bytes);
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
-  L.off_lut = take((size_t)(n_lut > 0 ? n_lut : 1) * 768);
+  L.off_lut = take((size_t)(lanes_total > 0 ? lanes_total : 1) * OADG_MAX_REGIONS * 768);
   L.any_bg = any_bg;
   const size_t mask_px = (size_t)h.max_h * h.max_w;
   L.off_maskf = take(any_bg ? (size_t)h.n_views * mask_px * sizeof(float) : 0);
@@ -166,7 +166,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
 //   profiles(P, pv, prof_x, prof_y)           masks(P, n_views, maskf, masku)
 //   hist(P, lanes, lane_ids, n, hist, luma)   lut(P, jobs, n, hist, luma, luts)
 //   bbo_pass(P, chains, n, j, roi_w, roi_h)
-//   step(P, lanes, n, scratch, frame_bytes)   mix(P, jobs, n)
+//   step(P, lanes, n, lane0, scratch, frame_bytes)   mix(P, jobs, n)
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
                  uint8_t* const* dst, void* workspace, size_t workspace_bytes) {
@@ -263,7 +263,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           op.lut = -1;
           op.scratch = -1;
           if (is_lut_kind(op.kind)) {
-            op.lut = lut_n;
+            op.lut = lane_n * OADG_MAX_REGIONS + r;  // slot addressable from the lane index alone
             lutjobs[lut_n] = LutJob{ln.op_base + r, ln.hist_slot, v, 0};
             ++lut_n;
             ++D.n_lut;
@@ -372,7 +372,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           if ((rc = be.bbo_pass(P, d_chain + D.chain0, D.n_chain, j, D.max_roi_w, D.max_roi_h))) return rc;
       }
     }
-    if ((rc = be.step(P, d_lanes + D.lane0, D.n_lanes, d_scratch, L.frame_bytes))) return rc;
+    if ((rc = be.step(P, d_lanes + D.lane0, D.n_lanes, D.lane0, d_scratch, L.frame_bytes))) return rc;
   }
   return be.mix(P, d_mix, h.n_views);
 }

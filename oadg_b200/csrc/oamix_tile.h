@@ -1,4 +1,4 @@
-// Tile-level bodies of the OA-Mix step / mix kernels.  A CTA of 256 threads owns a 256 x 16 pixel tile.
+// Tile-level bodies of the OA-Mix step / mix kernels.  A CTA of 256 threads owns a 256 x 32 pixel tile.
 // Streaming tiles (one LUT / bbo-copy region covers the tile) move one 16-pixel chunk (48 bytes = three
 // 16-byte vectors) per thread; every other tile (region borders, bg-only / invert / colour / sharpness ops)
 // is evaluated pixel by pixel with consecutive lanes on consecutive pixels.  Shared with tests/hostsim
@@ -12,7 +12,7 @@ namespace oadg {
 
 constexpr int kChunkPx = 16;  // 16 px * 3 B = 48 B = 3 x uint4: the smallest pixel run that is 16-byte periodic
 constexpr int kTileW = 256;   // 16 chunks
-constexpr int kTileH = 16;    // 16 x 16 chunks = 256 threads
+constexpr int kTileH = 32;    // 16 x 32 chunks: two per thread
 constexpr int kMaxCand = 12;
 
 struct Chunk {

@@ -25,11 +25,15 @@ constexpr int kThreads = 1024;
 __device__ __forceinline__ int brev6(int v) { return (int)(__brev((unsigned)v) >> 26); }
 
 // 64 independent 64-point FFTs over smem; element e of line l lives at l*ls + e*es.
+// Thread mapping keeps consecutive threads on consecutive shared-memory words: along the element index for
+// the row pass (es == 1) and along the line index for the column pass (ls == 1); the other order would put a
+// whole warp on one bank (stride 64 doubles).
 __device__ void fft64_lines(double* re, double* im, int es, int ls, const double* twc, const double* tws,
                             bool inverse) {
   const int tid = threadIdx.x;
+  const bool lines_fast = ls == 1;
   for (int i = tid; i < kN; i += kThreads) {
-    int l = i >> 6, e = i & 63, r = brev6(e);
+    const int l = lines_fast ? (i & 63) : (i >> 6), e = lines_fast ? (i >> 6) : (i & 63), r = brev6(e);
     if (e < r) {
       int a = l * ls + e * es, b = l * ls + r * es;
       double t = re[a];
@@ -45,7 +49,7 @@ __device__ void fft64_lines(double* re, double* im, int es, int ls, const double
     const int half = 1 << (s - 1);
     const int tstep = 64 >> s;
     for (int i = tid; i < kN / 2; i += kThreads) {
-      int l = i >> 5, b = i & 31;
+      const int l = lines_fast ? (i & 63) : (i >> 5), b = lines_fast ? (i >> 6) : (i & 31);
       int grp = b / half, j = b - grp * half;
       int i0 = l * ls + (grp * 2 * half + j) * es;
       int i1 = i0 + half * es;

@@ -146,7 +146,7 @@ struct HostBackend {
     return 0;
   }
   // mirrors step_kernel: 256 x 16 tiles; streaming tiles in 16-px chunks, every other tile per pixel
-  int step(const DevPlan& P, const Lane* lanes, int n, const uint8_t* scratch, size_t frame_bytes) {
+  int step(const DevPlan& P, const Lane* lanes, int n, int /*lane0*/, const uint8_t* scratch, size_t frame_bytes) {
     for (int k = 0; k < n; ++k) {
       const Lane& L = lanes[k];
       for (int y0 = 0; y0 < L.H; y0 += kTileH)
