@@ -163,8 +163,8 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
 
 /* Same as oadg_oamix_execute, but every launch is bracketed by CUDA events on `stream` and the
  * call synchronises the stream before returning (measurement only).  ms_by_kind / count_by_kind
- * receive 8 entries: {profile, hist, lut, bbo_pass, mask, step, mix, frame copy}. */
-#define OADG_PROFILE_KINDS 8
+ * receive 9 entries: {profile, hist, lut, bbo_pass, mask, step (stream), mix, frame copy, step (pixel)}. */
+#define OADG_PROFILE_KINDS 9
 int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
                                 const uint8_t* const* src_dev, int n_img,
                                 uint8_t* const* dst_dev,

@@ -283,14 +283,15 @@ bbo_pass_kernel(DevPlan P, const Chain* __restrict__ chains, int j) {
 }
 
 // ------------------------------------------------------------------------------------
-// one depth step of every live lane (oa_mix.py:226-234).  A CTA owns a 256 x 32 pixel tile of one lane.
-//   streaming tile (one LUT / bbo-copy region covers it): two 16-pixel chunks (3 x 16-byte vectors each) per
-//       thread; the lane's LUTs live at a slot computable from blockIdx alone, so their loads, the Lane record
-//       and the pixel loads are all in flight together
-//   any other tile: 32 pixels per thread, consecutive lanes on consecutive pixels (gathers stay within a few
-//       cache lines); the op parameters of the lane's regions are staged in shared memory, the x-dependent
-//       half of the fixed-point affine coordinates is hoisted out of the row loop
-// grid = (ceil(W/256), ceil(H/32), lanes)
+// one depth step of every live lane (oa_mix.py:226-234), split by kind of work (run_is_stream, oamix_tile.h):
+//
+// step_kernel        the HBM-bound part: table-lookup ops and bbo-result copies.  Persistent CTAs, grid =
+//                    (CTAs per lane, lanes) sized to fill the 148 SMs once; a CTA stages its Lane record and the
+//                    lane's LUTs in shared memory once, then grid-strides over 16-pixel runs (48 B = 3 x 16-byte
+//                    vectors), two runs in flight per thread.
+// step_pixel_kernel  everything that needs per-pixel evaluation (bg-only gathers, invert / colour / sharpness,
+//                    runs cut by a multi-level box edge), one CTA per 256 x 32 tile, consecutive lanes on
+//                    consecutive pixels; launched only over lanes that have such an op.
 // ------------------------------------------------------------------------------------
 constexpr int kTileThreads = 256;
 
@@ -299,6 +300,64 @@ struct RegOp {      // op parameters of one region, staged in shared memory for 
   float factor;
   double minv[6];
 };
+
+__global__ void __launch_bounds__(kTileThreads, 4)
+step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict__ scratch, size_t frame_bytes) {
+  __shared__ __align__(16) uint8_t lut_s[OADG_MAX_REGIONS * 768];
+  __shared__ Lane Ls;
+  const int t = threadIdx.x;
+  if (t < (int)(sizeof(Lane) / 4))
+    reinterpret_cast<uint32_t*>(&Ls)[t] = __ldg(reinterpret_cast<const uint32_t*>(lanes + blockIdx.y) + t);
+  __syncthreads();
+  const Lane& L = Ls;
+  bool any_lut = false;
+#pragma unroll
+  for (int r = 0; r < OADG_MAX_REGIONS; ++r) {
+    if (r <= L.n_ml && L.lut[r] >= 0) {
+      any_lut = true;
+      if (t < 192)
+        reinterpret_cast<uint32_t*>(lut_s + r * 768)[t] =
+            __ldg(reinterpret_cast<const uint32_t*>(P.luts + (size_t)L.lut[r] * 768) + t);
+    }
+  }
+  if (any_lut) __syncthreads();
+  const int W = L.W, H = L.H;
+  const int cpr = (W + kChunkPx - 1) / kChunkPx;
+  const int total = cpr * H;
+  const int stride = gridDim.x * kTileThreads;
+  const bool vec = ((W * 3) & 15) == 0 &&
+                   ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
+  for (int u0 = blockIdx.x * kTileThreads + t; u0 < total; u0 += 2 * stride) {
+    // two independent runs per iteration so that six 16-byte loads are in flight per thread
+    int x[2], y[2], n[2], reg[2];
+    bool vecrun[2];
+    Chunk c[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int u = u0 + k * stride;
+      n[k] = 0;
+      vecrun[k] = false;
+      if (u < total) {
+        y[k] = u / cpr;
+        x[k] = (u - y[k] * cpr) * kChunkPx;
+        n[k] = min(kChunkPx, W - x[k]);
+        const bool mine = run_is_stream(L, x[k], y[k], n[k], reg[k]);
+        if (!mine) n[k] = 0;
+        else if (reg[k] >= 0 && kind_streams(L.kind[reg[k]])) {
+          vecrun[k] = true;
+          chunk_load(stream_src(L, reg[k], scratch, frame_bytes) + ((size_t)y[k] * W + x[k]) * 3, n[k], vec, c[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (n[k] == 0) continue;
+      if (vecrun[k]) stream_chunk(L, reg[k], lut_s + reg[k] * 768, scratch, frame_bytes, c[k], x[k], y[k], n[k], vec);
+      else
+        for (int i = 0; i < n[k]; ++i) stream_pixel(L, lut_s, scratch, frame_bytes, x[k] + i, y[k]);
+    }
+  }
+}
 
 // one pixel of a bg-only op with hoisted coordinate terms (same arithmetic as bg_pixel / eval_op)
 __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, const RegOp& R, int ax, int bx,
@@ -337,42 +396,23 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
 }
 
 __global__ void __launch_bounds__(kTileThreads, 4)
-step_kernel(DevPlan P, const Lane* __restrict__ lanes, int lane0, const uint8_t* __restrict__ scratch,
-            size_t frame_bytes, const double* __restrict__ div255) {
-  __shared__ __align__(16) uint8_t lut_s[OADG_MAX_REGIONS * 768];
+step_pixel_kernel(DevPlan P, const Lane* __restrict__ lanes, const int32_t* __restrict__ lane_ids,
+                  const uint8_t* __restrict__ scratch, size_t frame_bytes, const double* __restrict__ div255) {
   __shared__ RegOp rop[OADG_MAX_REGIONS];
+  __shared__ Lane Ls;
   const int t = threadIdx.x;
-  // the lane's LUT slots are (lane0 + blockIdx.z) * 3 + r: prefetch all three tables (garbage for non-LUT regions)
-  const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(P.luts + (size_t)(lane0 + blockIdx.z) * OADG_MAX_REGIONS * 768);
-  const uint32_t l0 = __ldg(lsrc + t), l1 = __ldg(lsrc + 256 + t), l2 = t < 64 ? __ldg(lsrc + 512 + t) : 0u;
-  const Lane& L = lanes[blockIdx.z];
+  if (t < (int)(sizeof(Lane) / 4))
+    reinterpret_cast<uint32_t*>(&Ls)[t] = __ldg(reinterpret_cast<const uint32_t*>(lanes + lane_ids[blockIdx.z]) + t);
+  __syncthreads();
+  const Lane& L = Ls;
   const int W = L.W, H = L.H;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   if (x0 >= W || y0 >= H) return;
   const int x1 = min(x0 + kTileW, W), y1 = min(y0 + kTileH, H);
-  const int region = tile_region(L, x0, y0, x1, y1);
-  if (tile_streams(L, region)) {
-    const uint8_t* src = stream_src(L, region, scratch, frame_bytes);
-    const bool vec = ((W * 3) & 15) == 0 &&
-                     ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)scratch) | frame_bytes) & 15) == 0;
-    const int x = x0 + (t & 15) * kChunkPx;
-    const int ya = y0 + (t >> 4), yb = ya + 16;
-    const int n = x < x1 ? min(kChunkPx, x1 - x) : 0;
-    const bool la = n > 0 && ya < y1, lb = n > 0 && yb < y1;
-    Chunk ca, cb;
-    if (la) chunk_load(src + ((size_t)ya * W + x) * 3, n, vec, ca);
-    if (lb) chunk_load(src + ((size_t)yb * W + x) * 3, n, vec, cb);
-    uint32_t* ls = reinterpret_cast<uint32_t*>(lut_s);
-    ls[t] = l0;
-    ls[256 + t] = l1;
-    if (t < 64) ls[512 + t] = l2;
-    __syncthreads();
-    const uint8_t* lut = lut_s + region * 768;
-    if (la) stream_chunk(L, region, lut, scratch, frame_bytes, ca, x, ya, n, vec);
-    if (lb) stream_chunk(L, region, lut, scratch, frame_bytes, cb, x, yb, n, vec);
-    return;
+  {  // a tile that one streaming region covers has nothing for this kernel
+    const int region = tile_region(L, x0, y0, x1, y1);
+    if (region >= 0 && kind_streams(L.kind[region])) return;
   }
-  // ---- per-pixel tile
   if (t <= L.n_ml) {
     const oadg_op_t& op = P.ops[L.op_base + t];
     rop[t].kind = op.kind;
@@ -383,8 +423,9 @@ step_kernel(DevPlan P, const Lane* __restrict__ lanes, int lane0, const uint8_t*
     for (int i = 0; i < 6; ++i) rop[t].minv[i] = op.minv[i];
   }
   __syncthreads();
-  const int x = x0 + t;  // this thread's column is fixed: idx = it*256 + t
+  const int x = x0 + t;  // this thread's column is fixed
   if (x >= x1) return;
+  const int xc = x & ~(kChunkPx - 1), nc = min(kChunkPx, W - xc);  // the 16-pixel run this column belongs to
   int ax[OADG_MAX_REGIONS], bx[OADG_MAX_REGIONS];
 #pragma unroll
   for (int r = 0; r < OADG_MAX_REGIONS; ++r) {
@@ -396,9 +437,9 @@ step_kernel(DevPlan P, const Lane* __restrict__ lanes, int lane0, const uint8_t*
   }
 #pragma unroll 1
   for (int y = y0; y < y1; ++y) {
-    int r = L.n_ml;
-    for (int b = 0; b < L.n_ml; ++b)
-      if (x >= L.box[b][0] && x < L.box[b][2] && y >= L.box[b][1] && y < L.box[b][3]) r = b;
+    int run_region;
+    if (run_is_stream(L, xc, y, nc, run_region)) continue;  // the stream kernel owns this run
+    const int r = region_of_pixel(L, x, y);
     if (rop[r].kind == OADG_OP_BG_AFFINE) {
       const int axr = r == 0 ? ax[0] : (r == 1 ? ax[1] : ax[2]);
       const int bxr = r == 0 ? bx[0] : (r == 1 ? bx[1] : bx[2]);
@@ -437,7 +478,7 @@ mix_kernel(DevPlan P, const MixJob* __restrict__ jobs) {
     if (_e != cudaSuccess) return (int)_e; \
   } while (0)
 
-enum { kKProfile = 0, kKHist, kKLut, kKBboPass, kKMask, kKStep, kKMix, kKCopy, kKinds };
+enum { kKProfile = 0, kKHist, kKLut, kKBboPass, kKMask, kKStep, kKMix, kKCopy, kKStepPx, kKinds };
 
 struct CudaBackend {
   cudaStream_t stream;
@@ -524,14 +565,24 @@ struct CudaBackend {
     end(kKBboPass);
     return 0;
   }
-  int step(const DevPlan& P, const Lane* lanes, int n, int lane0, const uint8_t* scratch, size_t frame_bytes) {
-    dim3 grid((P.max_w + kTileW - 1) / kTileW, (P.max_h + kTileH - 1) / kTileH, n);
-    const double* div255 = nullptr;
-    BE_TRY(cudaGetSymbolAddress((void**)&div255, g_div255));
+  // lanes of one depth; lane_px_ids / n_px: the lanes that have a per-pixel op
+  int step(const DevPlan& P, const Lane* lanes, int n, const int32_t* lane_px_ids, int n_px, const uint8_t* scratch,
+           size_t frame_bytes) {
+    int per_lane = (kNumSMs * 4 + n - 1) / n;  // persistent CTAs: fill the SMs once (4 CTAs of 256 threads per SM)
+    if (per_lane < 1) per_lane = 1;
     begin();
-    step_kernel<<<grid, kTileThreads, 0, stream>>>(P, lanes, lane0, scratch, frame_bytes, div255);
+    step_kernel<<<dim3(per_lane, n), kTileThreads, 0, stream>>>(P, lanes, scratch, frame_bytes);
     BE_TRY(cudaGetLastError());
     end(kKStep);
+    if (n_px > 0) {
+      const double* div255 = nullptr;
+      BE_TRY(cudaGetSymbolAddress((void**)&div255, g_div255));
+      dim3 grid((P.max_w + kTileW - 1) / kTileW, (P.max_h + kTileH - 1) / kTileH, n_px);
+      begin();
+      step_pixel_kernel<<<grid, kTileThreads, 0, stream>>>(P, lanes, lane_px_ids, scratch, frame_bytes, div255);
+      BE_TRY(cudaGetLastError());
+      end(kKStepPx);
+    }
     return 0;
   }
   int mix(const DevPlan& P, const MixJob* jobs, int n) {

@@ -40,7 +40,7 @@ struct Lane {            // one (view, branch) chain alive at the current depth
   int32_t kind[OADG_MAX_REGIONS];    // op kind of region r (r = n_ml: outside)
   int32_t lut[OADG_MAX_REGIONS];     // LUT slot of region r or -1
   int32_t scratch[OADG_MAX_REGIONS]; // bbo result frame slot of region r or -1
-  int32_t pad;
+  int32_t all_streaming;             // every region runs a table-lookup / bbo-copy op: no pixel kernel needed
 };
 
 struct Chain {           // one bboxes-only op being evaluated (sequential over its boxes)

@@ -138,7 +138,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
     return at;
   };
   L.tables_bytes = align_up_sz((size_t)lanes_total * sizeof(Lane), 16) +
-                   align_up_sz((size_t)lanes_total * sizeof(int32_t), 16) +
+                   2 * align_up_sz((size_t)lanes_total * sizeof(int32_t), 16) +
                    align_up_sz((size_t)(n_lut > 0 ? n_lut : 1) * sizeof(LutJob), 16) +
                    align_up_sz((size_t)lanes_total * OADG_MAX_REGIONS * sizeof(Chain), 16) +
                    align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
@@ -153,7 +153,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.off_scratch = take((size_t)L.n_scratch * L.frame_bytes);
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
-  L.off_lut = take((size_t)(lanes_total > 0 ? lanes_total : 1) * OADG_MAX_REGIONS * 768);
+  L.off_lut = take((size_t)(n_lut > 0 ? n_lut : 1) * 768);
   L.any_bg = any_bg;
   const size_t mask_px = (size_t)h.max_h * h.max_w;
   L.off_maskf = take(any_bg ? (size_t)h.n_views * mask_px * sizeof(float) : 0);
@@ -166,7 +166,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
 //   profiles(P, pv, prof_x, prof_y)           masks(P, n_views, maskf, masku)
 //   hist(P, lanes, lane_ids, n, hist, luma)   lut(P, jobs, n, hist, luma, luts)
 //   bbo_pass(P, chains, n, j, roi_w, roi_h)
-//   step(P, lanes, n, lane0, scratch, frame_bytes)   mix(P, jobs, n)
+//   step(P, lanes, n, pixel_lane_ids, n_pixel_lanes, scratch, frame_bytes)   mix(P, jobs, n)
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
                  uint8_t* const* dst, void* workspace, size_t workspace_bytes) {
@@ -209,18 +209,20 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   };
   const size_t t_lanes = carve((size_t)L.n_lanes_total * sizeof(Lane));
   const size_t t_lane_ids = carve((size_t)L.n_lanes_total * sizeof(int32_t));
+  const size_t t_px_ids = carve((size_t)L.n_lanes_total * sizeof(int32_t));
   const size_t t_lut = carve((size_t)(L.n_lut > 0 ? L.n_lut : 1) * sizeof(LutJob));
   const size_t t_chain = carve((size_t)L.n_lanes_total * OADG_MAX_REGIONS * sizeof(Chain));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
   auto* lane_ids = reinterpret_cast<int32_t*>(stage.data() + t_lane_ids);
+  auto* px_ids = reinterpret_cast<int32_t*>(stage.data() + t_px_ids);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
   auto* chains = reinterpret_cast<Chain*>(stage.data() + t_chain);
   auto* mixjobs = reinterpret_cast<MixJob*>(stage.data() + t_mix);
 
   struct DepthInfo {
     int lane0 = 0, n_lanes = 0, hist0 = 0, n_hist = 0, lut0 = 0, n_lut = 0, chain0 = 0, n_chain = 0;
-    int max_chain = 0, max_roi_w = 0, max_roi_h = 0;
+    int max_chain = 0, max_roi_w = 0, max_roi_h = 0, n_px = 0;
   };
   std::vector<DepthInfo> di(L.max_depth);
   int lane_n = 0, hist_n = 0, lut_n = 0, chain_n = 0, histid_n = 0;
@@ -246,7 +248,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
         ln.H = V.H;
         ln.W = V.W;
         ln.n_ml = V.n_ml;
-        ln.pad = 0;
+        ln.all_streaming = 1;
         for (int q = 0; q < 2; ++q)
           for (int e = 0; e < 4; ++e) ln.box[q][e] = q < V.n_ml ? V.ml_box[q][e] : 0;
         for (int r = 0; r < OADG_MAX_REGIONS; ++r) ln.kind[r] = ln.lut[r] = ln.scratch[r] = -1;
@@ -263,7 +265,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           op.lut = -1;
           op.scratch = -1;
           if (is_lut_kind(op.kind)) {
-            op.lut = lane_n * OADG_MAX_REGIONS + r;  // slot addressable from the lane index alone
+            op.lut = lut_n;
             lutjobs[lut_n] = LutJob{ln.op_base + r, ln.hist_slot, v, 0};
             ++lut_n;
             ++D.n_lut;
@@ -298,7 +300,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           ln.kind[r] = ops[ln.op_base + r].kind;
           ln.lut[r] = ops[ln.op_base + r].lut;
           ln.scratch[r] = ops[ln.op_base + r].scratch;
+          if (!(is_lut_kind(ln.kind[r]) || ln.kind[r] == OADG_OP_BBO_AFFINE)) ln.all_streaming = 0;
         }
+        if (!ln.all_streaming) px_ids[D.lane0 + D.n_px++] = lane_n - D.lane0;  // index within this depth's lane slice
         ++lane_n;
         ++D.n_lanes;
       }
@@ -333,6 +337,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   P.mask_stride = (size_t)h.max_h * h.max_w;
   const Lane* d_lanes = reinterpret_cast<const Lane*>(dplan + t_lanes);
   const int32_t* d_lane_ids = reinterpret_cast<const int32_t*>(dplan + t_lane_ids);
+  const int32_t* d_px_ids = reinterpret_cast<const int32_t*>(dplan + t_px_ids);
   const LutJob* d_lut = reinterpret_cast<const LutJob*>(dplan + t_lut);
   const Chain* d_chain = reinterpret_cast<const Chain*>(dplan + t_chain);
   const MixJob* d_mix = reinterpret_cast<const MixJob*>(dplan + t_mix);
@@ -372,7 +377,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           if ((rc = be.bbo_pass(P, d_chain + D.chain0, D.n_chain, j, D.max_roi_w, D.max_roi_h))) return rc;
       }
     }
-    if ((rc = be.step(P, d_lanes + D.lane0, D.n_lanes, D.lane0, d_scratch, L.frame_bytes))) return rc;
+    if ((rc = be.step(P, d_lanes + D.lane0, D.n_lanes, d_px_ids + D.lane0, D.n_px, d_scratch, L.frame_bytes))) return rc;
   }
   return be.mix(P, d_mix, h.n_views);
 }

@@ -19,6 +19,24 @@ struct Chunk {
   uint32_t w[12];
 };
 
+#ifdef __CUDA_ARCH__
+// cold paths (ragged right edge, unaligned frames): kept out of line so they do not inflate the registers of
+// the vector path
+__device__ __noinline__ void chunk_load_scalar(const uint8_t* p, int n, Chunk& c) {
+  for (int i = 0; i < 12; ++i) {
+    uint32_t v = 0;
+    for (int b = 0; b < 4; ++b)
+      if (i * 4 + b < n * 3) v |= (uint32_t)__ldg(p + i * 4 + b) << (8 * b);
+    c.w[i] = v;
+  }
+}
+__device__ __noinline__ void chunk_store_scalar(uint8_t* p, int n, const Chunk& c) {
+  for (int i = 0; i < 12; ++i)
+    for (int b = 0; b < 4; ++b)
+      if (i * 4 + b < n * 3) p[i * 4 + b] = (uint8_t)(c.w[i] >> (8 * b));
+}
+#endif
+
 OADG_HD void chunk_load(const uint8_t* p, int n, bool vec, Chunk& c) {
 #ifdef __CUDA_ARCH__
   if (vec && n == kChunkPx) {
@@ -29,14 +47,7 @@ OADG_HD void chunk_load(const uint8_t* p, int n, bool vec, Chunk& c) {
     c.w[8] = d.x; c.w[9] = d.y; c.w[10] = d.z; c.w[11] = d.w;
     return;
   }
-#pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    uint32_t v = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (i * 4 + b < n * 3) v |= (uint32_t)__ldg(p + i * 4 + b) << (8 * b);
-    c.w[i] = v;
-  }
+  chunk_load_scalar(p, n, c);
 #else
   (void)vec;
   memset(c.w, 0, sizeof(c.w));
@@ -53,11 +64,7 @@ OADG_HD void chunk_store(uint8_t* p, int n, bool vec, const Chunk& c) {
     q[2] = make_uint4(c.w[8], c.w[9], c.w[10], c.w[11]);
     return;
   }
-#pragma unroll
-  for (int i = 0; i < 12; ++i)
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (i * 4 + b < n * 3) p[i * 4 + b] = (uint8_t)(c.w[i] >> (8 * b));
+  chunk_store_scalar(p, n, c);
 #else
   (void)vec;
   memcpy(p, c.w, (size_t)n * 3);
@@ -71,7 +78,7 @@ OADG_HD bool rect_hit(const int32_t* s, int x0, int y0, int x1, int y1) {
   return s[0] < x1 && s[2] > x0 && s[1] < y1 && s[3] > y0;
 }
 
-// Region that covers the whole tile [x0,x1) x [y0,y1), or -1 when a multi-level box edge crosses it.
+// Region that covers the whole rectangle [x0,x1) x [y0,y1), or -1 when a multi-level box edge crosses it.
 OADG_HD int tile_region(const Lane& L, int x0, int y0, int x1, int y1) {
   int region = L.n_ml;
   for (int b = 0; b < L.n_ml; ++b) {
@@ -82,9 +89,37 @@ OADG_HD int tile_region(const Lane& L, int x0, int y0, int x1, int y1) {
   }
   return region;
 }
-// a tile streams when one region covers it and that region's op is a table lookup or a bbo-result copy
-OADG_HD bool tile_streams(const Lane& L, int region) {
-  return region >= 0 && (is_lut_kind(L.kind[region]) || L.kind[region] == OADG_OP_BBO_AFFINE);
+OADG_HD bool kind_streams(int kind) { return is_lut_kind(kind) || kind == OADG_OP_BBO_AFFINE; }
+// Work split of one depth step: the 16-pixel run [x, x+n) of row y belongs to the STREAM kernel when one
+// region covers it and that region's op is a table lookup / bbo-result copy (vector path), or when the lane has
+// no other kind of op at all (box-edge runs are then done per pixel by the stream kernel itself).  Every other
+// run belongs to the PIXEL kernel.  Returns the covering region (or -1) through `region`.
+OADG_HD bool run_is_stream(const Lane& L, int x, int y, int n, int& region) {
+  region = tile_region(L, x, y, x + n, y + 1);
+  return (region >= 0 && kind_streams(L.kind[region])) || L.all_streaming;
+}
+OADG_HD int region_of_pixel(const Lane& L, int x, int y) {
+  int r = L.n_ml;
+  for (int b = 0; b < L.n_ml; ++b)
+    if (x >= L.box[b][0] && x < L.box[b][2] && y >= L.box[b][1] && y < L.box[b][3]) r = b;
+  return r;
+}
+// one pixel of a table-lookup / bbo-copy op (box-edge runs of all-streaming lanes); luts: region r at luts + r*768
+OADG_HD void stream_pixel(const Lane& L, const uint8_t* luts, const uint8_t* scratch, size_t frame_bytes, int x, int y) {
+  const int r = region_of_pixel(L, x, y);
+  const size_t o = ((size_t)y * L.W + x) * 3;
+  uint8_t* q = L.out + o;
+  if (L.kind[r] == OADG_OP_BBO_AFFINE) {
+    const uint8_t* s = (L.scratch[r] >= 0 ? scratch + (size_t)L.scratch[r] * frame_bytes : L.in) + o;
+    q[0] = (uint8_t)ldb(s);
+    q[1] = (uint8_t)ldb(s + 1);
+    q[2] = (uint8_t)ldb(s + 2);
+  } else {
+    const uint8_t* lut = luts + r * 768;
+    q[0] = lut[ldb(L.in + o)];
+    q[1] = lut[256 + ldb(L.in + o + 1)];
+    q[2] = lut[512 + ldb(L.in + o + 2)];
+  }
 }
 
 // 16 pixels of a streaming tile.  `lut`: the region's 3x256 table (shared memory on the device).

@@ -32,7 +32,7 @@ _AUG = {
 }
 
 
-PROFILE_KINDS = ('profile', 'hist', 'lut', 'bbo_pass', 'mask', 'step', 'mix', 'copy')
+PROFILE_KINDS = ('profile', 'hist', 'lut', 'bbo_pass', 'mask', 'step', 'mix', 'copy', 'step_pixel')
 
 
 def get_aug_list(version):
@@ -440,8 +440,8 @@ class OAMix:
         base = (ws.data_ptr() + 255) // 256 * 256
         room = ws.numel() - (base - ws.data_ptr())
         if profile is not None:
-            ms = (ctypes.c_float * 8)()
-            cnt = (ctypes.c_int * 8)()
+            ms = (ctypes.c_float * len(PROFILE_KINDS))()
+            cnt = (ctypes.c_int * len(PROFILE_KINDS))()
             _lib.check(lib.oadg_oamix_execute_profiled(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
                                                        ms, cnt, s.cuda_stream))
             for i, k in enumerate(PROFILE_KINDS):

@@ -145,31 +145,39 @@ struct HostBackend {
     ++launches;
     return 0;
   }
-  // mirrors step_kernel: 256 x 16 tiles; streaming tiles in 16-px chunks, every other tile per pixel
-  int step(const DevPlan& P, const Lane* lanes, int n, int /*lane0*/, const uint8_t* scratch, size_t frame_bytes) {
+  // mirrors step_kernel (stream runs) + step_pixel_kernel (everything else), same work split predicate
+  int step(const DevPlan& P, const Lane* lanes, int n, const int32_t* px_ids, int n_px, const uint8_t* scratch,
+           size_t frame_bytes) {
     for (int k = 0; k < n; ++k) {
       const Lane& L = lanes[k];
-      for (int y0 = 0; y0 < L.H; y0 += kTileH)
-        for (int x0 = 0; x0 < L.W; x0 += kTileW) {
-          const int x1 = imin(x0 + kTileW, L.W), y1 = imin(y0 + kTileH, L.H);
-          const int region = tile_region(L, x0, y0, x1, y1);
-          if (tile_streams(L, region)) {
-            const uint8_t* lut = L.lut[region] >= 0 ? P.luts + (size_t)L.lut[region] * 768 : nullptr;
-            const uint8_t* src = stream_src(L, region, scratch, frame_bytes);
-            for (int y = y0; y < y1; ++y)
-              for (int x = x0; x < x1; x += kChunkPx) {
-                const int nn = imin(kChunkPx, x1 - x);
-                Chunk in;
-                chunk_load(src + ((size_t)y * L.W + x) * 3, nn, true, in);
-                stream_chunk(L, region, lut, scratch, frame_bytes, in, x, y, nn, true);
-              }
+      uint8_t luts[OADG_MAX_REGIONS * 768];
+      for (int r = 0; r <= L.n_ml; ++r)
+        if (L.lut[r] >= 0) memcpy(luts + r * 768, P.luts + (size_t)L.lut[r] * 768, 768);
+      for (int y = 0; y < L.H; ++y)
+        for (int x = 0; x < L.W; x += kChunkPx) {
+          const int nn = imin(kChunkPx, L.W - x);
+          int region;
+          if (!run_is_stream(L, x, y, nn, region)) continue;
+          if (region >= 0 && kind_streams(L.kind[region])) {
+            Chunk in;
+            chunk_load(stream_src(L, region, scratch, frame_bytes) + ((size_t)y * L.W + x) * 3, nn, true, in);
+            stream_chunk(L, region, luts + region * 768, scratch, frame_bytes, in, x, y, nn, true);
           } else {
-            for (int y = y0; y < y1; ++y)
-              for (int x = x0; x < x1; ++x) step_pixel(P, L, scratch, frame_bytes, x, y);
+            for (int i = 0; i < nn; ++i) stream_pixel(L, luts, scratch, frame_bytes, x + i, y);
           }
         }
     }
-    ++launches;
+    for (int k = 0; k < n_px; ++k) {
+      const Lane& L = lanes[px_ids[k]];
+      for (int y = 0; y < L.H; ++y)
+        for (int x = 0; x < L.W; ++x) {
+          const int xc = x & ~(kChunkPx - 1);
+          int region;
+          if (run_is_stream(L, xc, y, imin(kChunkPx, L.W - xc), region)) continue;
+          step_pixel(P, L, scratch, frame_bytes, x, y);
+        }
+    }
+    launches += n_px > 0 ? 2 : 1;
     return 0;
   }
   int mix(const DevPlan& P, const MixJob* jobs, int n) {
