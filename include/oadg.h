@@ -201,6 +201,25 @@ int oadg_supcon_backward(const float* feats_dev, const int64_t* labels_dev,
                          void* workspace_dev, size_t workspace_bytes,
                          int* launches_out, void* stream);
 
+/* ---- OA-Loss across ranks (new capability; the reference's loss is per-rank local) --------------------
+ * Anchors are this rank's rows [row0, row0 + n_rows) of the all-gathered, doubly-normalised embeddings
+ * fhat_all [n_total, c]; contrasts are all n_total rows.  The caller (oadg_b200/distributed.py) performs the
+ * collectives with torch.distributed / NCCL between the calls:
+ *   normalize (local) -> all_gather(fhat, labels) -> forward_gathered -> all_reduce(loss), all_gather(stats)
+ *   -> backward_gathered.  One workspace sized by oadg_supcon_workspace_bytes(n_total, c) spans the sequence. */
+int oadg_supcon_normalize(const float* feats_dev, int n_rows, int n_total, int c, int normalized_input,
+                          float* fhat_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int oadg_supcon_forward_gathered(const float* fhat_all_dev, const int64_t* labels_all_dev,
+                                 const int32_t* pair_all_dev, int n_total, int row0, int n_rows, int c,
+                                 float temperature, float loss_weight, int min_samples,
+                                 float* loss_part_dev, float* stats_local_dev /* [n_rows, 4] */,
+                                 void* workspace_dev, size_t workspace_bytes, int* launches_out, void* stream);
+int oadg_supcon_backward_gathered(const float* feats_local_dev, const int64_t* labels_all_dev,
+                                  const int32_t* pair_all_dev, const float* stats_all_dev /* [n_total, 4] */,
+                                  int n_total, int row0, int n_rows, int c, float temperature,
+                                  int normalized_input, const float* grad_loss_dev, float* grad_feats_dev,
+                                  void* workspace_dev, size_t workspace_bytes, int* launches_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

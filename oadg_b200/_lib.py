@@ -27,6 +27,11 @@ SIGNATURES = {
                                        _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
     'oadg_supcon_backward': (_c.c_int, [_vp, _vp, _vp, _c.c_int, _c.c_int, _f32, _f32, _c.c_int,
                                         _vp, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_supcon_normalize': (_c.c_int, [_vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _sz, _vp]),
+    'oadg_supcon_forward_gathered': (_c.c_int, [_vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _f32, _f32,
+                                                _c.c_int, _vp, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_supcon_backward_gathered': (_c.c_int, [_vp, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _f32,
+                                                 _c.c_int, _vp, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
 }
 
 _lib = None

@@ -233,7 +233,10 @@ sim_fwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels, 
 // fixed summation order => deterministic)
 __global__ void __launch_bounds__(1024)
 row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ npos, const int* __restrict__ meta,
-                  int n, int col_tiles, float loss_weight, RowStats* __restrict__ stats, float* __restrict__ loss) {
+                  int n, int row0, int n_total, int col_tiles, float loss_weight, RowStats* __restrict__ stats,
+                  float* __restrict__ loss) {
+  // rows [row0, row0 + n) of an n_total-row problem (single GPU: row0 = 0, n = n_total); partial / stats are
+  // indexed by the local row, npos by the global row; the loss is this range's share of the mean over n_total
   __shared__ double red[32];
   const int tid = threadIdx.x;
   if (!meta[2]) {
@@ -252,11 +255,11 @@ row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ n
       Ps += p[2];
     }
     const float lse = M + logf(S);
-    const float np = npos[i];
+    const float np = npos[row0 + i];
     RowStats st;
     st.lse = lse;
     st.npos = np;
-    st.coef = np > 0.f ? -(loss_weight / (float)n) / np : 0.f;
+    st.coef = np > 0.f ? -(loss_weight / (float)n_total) / np : 0.f;
     st.u = st.coef * np * expf(-lse);
     stats[i] = st;
     if (np > 0.f) local += (double)(Ps / np - lse);
@@ -267,7 +270,7 @@ row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ n
   if (tid == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    *loss = (float)(-(double)loss_weight * t / (double)n);
+    *loss = (float)(-(double)loss_weight * t / (double)n_total);
   }
 }
 
@@ -439,7 +442,7 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
   OADG_LAUNCH_CHECK();
   int red_tiles = col_tiles;
   if (loss_tc_enabled()) {
-    int rc = launch_sim_fwd_tc(w, labels_dev, pair_dev, n, 1.f / temperature, stream, &launches);
+    int rc = launch_sim_fwd_tc(w, labels_dev, pair_dev, n, 0, n, 1.f / temperature, stream, &launches);
     if (rc) return rc;
     red_tiles = (n + 127) / 128;
   } else {
@@ -448,7 +451,8 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
     OADG_LAUNCH_CHECK();
     ++launches;
   }
-  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n, red_tiles, loss_weight, w.stats, loss_dev);
+  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n, 0, n, red_tiles, loss_weight, w.stats,
+                                            loss_dev);
   OADG_LAUNCH_CHECK();
   launches += 3;
   if (launches_out) *launches_out = launches;
@@ -475,7 +479,7 @@ extern "C" int oadg_supcon_backward(const float* feats_dev, const int64_t* label
   const float* dpart = w.dfhat;
   int n_part = 1;
   if (loss_tc_enabled()) {
-    int rc = launch_sim_bwd_tc(w, labels_dev, pair_dev, n, 1.f / temperature, stream, &launches);
+    int rc = launch_sim_bwd_tc(w, w.stats, labels_dev, pair_dev, n, 0, n, 1.f / temperature, stream, &launches);
     if (rc) return rc;
     dpart = w.dpart;
     n_part = kBwdSplits;
@@ -498,6 +502,76 @@ extern "C" int oadg_supcon_backward(const float* feats_dev, const int64_t* label
   }
   normalize_bwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(feats_dev, dpart, n_part, w.inv1, w.inv2, w.meta, grad_loss_dev,
                                                        n, c, normalized_input, grad_feats_dev);
+  OADG_LAUNCH_CHECK();
+  ++launches;
+  if (launches_out) *launches_out = launches;
+  return 0;
+}
+
+
+// ---- cross-rank variant: anchors = this rank's rows, contrasts = the all-gathered rows -----------------------
+extern "C" int oadg_supcon_normalize(const float* feats_dev, int n_rows, int n_total, int c, int normalized_input,
+                                     float* fhat_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_rows <= 0 || n_total < n_rows || !feats_dev || !fhat_out_dev || !workspace_dev) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if ((uintptr_t)workspace_dev & 255) return OADG_E_ARG;
+  LossWs w = carve_loss_ws(workspace_dev, n_total, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  normalize_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(feats_dev, n_rows, c, normalized_input, fhat_out_dev, w.inv1,
+                                                         w.inv2);
+  OADG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int oadg_supcon_forward_gathered(const float* fhat_all_dev, const int64_t* labels_all_dev,
+                                            const int32_t* pair_all_dev, int n_total, int row0, int n_rows, int c,
+                                            float temperature, float loss_weight, int min_samples,
+                                            float* loss_part_dev, float* stats_local_dev, void* workspace_dev,
+                                            size_t workspace_bytes, int* launches_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!fhat_all_dev || !labels_all_dev || !pair_all_dev || !loss_part_dev || !stats_local_dev || !workspace_dev)
+    return OADG_E_ARG;
+  if (n_rows <= 0 || row0 < 0 || row0 + n_rows > n_total) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if (!(temperature > 0.f) || ((uintptr_t)fhat_all_dev & 15) || ((uintptr_t)workspace_dev & 255)) return OADG_E_ARG;
+  if (!loss_tc_enabled()) return OADG_E_LIMIT;  // the cross-rank path exists for the tcgen05 kernels only
+  LossWs w = carve_loss_ws(workspace_dev, n_total, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  int launches = 0;
+  w.fhat = const_cast<float*>(fhat_all_dev);
+  label_prep_kernel<<<1, 1024, 0, stream>>>(labels_all_dev, pair_all_dev, n_total, min_samples, w.meta, w.npos);
+  OADG_LAUNCH_CHECK();
+  int rc = launch_sim_fwd_tc(w, labels_all_dev, pair_all_dev, n_total, row0, n_rows, 1.f / temperature, stream, &launches);
+  if (rc) return rc;
+  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n_rows, row0, n_total, (n_total + 127) / 128,
+                                            loss_weight, reinterpret_cast<RowStats*>(stats_local_dev), loss_part_dev);
+  OADG_LAUNCH_CHECK();
+  launches += 2;
+  if (launches_out) *launches_out = launches;
+  return 0;
+}
+
+extern "C" int oadg_supcon_backward_gathered(const float* feats_local_dev, const int64_t* labels_all_dev,
+                                             const int32_t* pair_all_dev, const float* stats_all_dev, int n_total,
+                                             int row0, int n_rows, int c, float temperature, int normalized_input,
+                                             const float* grad_loss_dev, float* grad_feats_dev, void* workspace_dev,
+                                             size_t workspace_bytes, int* launches_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!feats_local_dev || !labels_all_dev || !pair_all_dev || !stats_all_dev || !grad_loss_dev || !grad_feats_dev ||
+      !workspace_dev)
+    return OADG_E_ARG;
+  if (n_rows <= 0 || row0 < 0 || row0 + n_rows > n_total) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if (!loss_tc_enabled()) return OADG_E_LIMIT;
+  LossWs w = carve_loss_ws(workspace_dev, n_total, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  int launches = 0;
+  int rc = launch_sim_bwd_tc(w, reinterpret_cast<const RowStats*>(stats_all_dev), labels_all_dev, pair_all_dev, n_total,
+                             row0, n_rows, 1.f / temperature, stream, &launches);
+  if (rc) return rc;
+  normalize_bwd_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(feats_local_dev, w.dpart, kBwdSplits, w.inv1, w.inv2, w.meta,
+                                                            grad_loss_dev, n_rows, c, normalized_input, grad_feats_dev);
   OADG_LAUNCH_CHECK();
   ++launches;
   if (launches_out) *launches_out = launches;

@@ -70,9 +70,10 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
 
 
 // oaloss_tc.cu
-int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
-                      cudaStream_t stream, int* launches);
-int launch_sim_bwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
-                      cudaStream_t stream, int* launches);
+// rows [row0, row0 + n_rows) of the n-row problem are the anchors (single GPU: row0 = 0, n_rows = n)
+int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, int row0, int n_rows,
+                      float inv_t, cudaStream_t stream, int* launches);
+int launch_sim_bwd_tc(const LossWs& w, const RowStats* stats_all, const int64_t* labels, const int32_t* pair, int n,
+                      int row0, int n_rows, float inv_t, cudaStream_t stream, int* launches);
 
 }  // namespace oadg

@@ -139,8 +139,8 @@ __device__ __forceinline__ bool is_pos(long long yi, long long yj, long long bg,
 __global__ void __launch_bounds__(128, 1)
 sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                   const int64_t* __restrict__ labels, const int32_t* __restrict__ pair,
-                  const int* __restrict__ meta, int n, float inv_t, float* __restrict__ partial,
-                  float* __restrict__ zout, int ld) {
+                  const int* __restrict__ meta, int n, int row0, int n_rows, float inv_t,
+                  float* __restrict__ partial, float* __restrict__ zout, int ld) {
   if (!meta[2]) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -149,7 +149,7 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   __shared__ long long ylab[kN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int i0 = blockIdx.y * kM, j0 = blockIdx.x * kN;
+  const int i0 = row0 + blockIdx.y * kM, j0 = blockIdx.x * kN;  // anchors: rows [row0, row0 + n_rows)
   constexpr int kChunks = 256 / kKC;
 
   if (tid == 0) {
@@ -210,7 +210,7 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   mbar_wait(&accum_bar, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int i = i0 + warp * 32 + lane;
-  const bool row_ok = i < n;
+  const bool row_ok = i < row0 + n_rows;
   const long long bg = (long long)meta[0];
   const long long yi = row_ok ? labels[i] : 0;
   const int pi = row_ok ? pair[i] : -1;
@@ -228,7 +228,7 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
       if (j < n) cm = fmaxf(cm, z);
     }
     if (row_ok && j0 + c0 < ld) {  // keep the logits for the backward (128 B per thread, L2-resident)
-      float4* zp = reinterpret_cast<float4*>(zout + (size_t)i * ld + j0 + c0);
+      float4* zp = reinterpret_cast<float4*>(zout + (size_t)(i - row0) * ld + j0 + c0);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         zp[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
@@ -249,7 +249,7 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
     }
   }
   if (row_ok) {
-    float* out = partial + ((size_t)blockIdx.x * n + i) * 3;
+    float* out = partial + ((size_t)blockIdx.x * n_rows + (i - row0)) * 3;
     out[0] = m;
     out[1] = s;
     out[2] = ps;
@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(kBThreads, 1)
 sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_thi,
                   const __grid_constant__ CUtensorMap tm_tlo, const int64_t* __restrict__ labels,
                   const int32_t* __restrict__ pair, const int* __restrict__ meta,
-                  const RowStats* __restrict__ stats, int n, float inv_t, int chunks_per_split,
-                  float* __restrict__ dpart) {
+                  const RowStats* __restrict__ stats, int n, int row0, int n_rows, float inv_t,
+                  int chunks_per_split, float* __restrict__ dpart) {
   if (!meta[2]) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -342,7 +342,8 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
   __shared__ int s_pj[kBStages][kKC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int i0 = blockIdx.y * kM;
+  const int il0 = blockIdx.y * kM;   // local row of the tile (z / dpart index); global row = row0 + local
+  const int i0 = row0 + il0;
   const int total_chunks = (n + kKC - 1) / kKC;
   const int kc0 = blockIdx.x * chunks_per_split;
   const int kc1 = min(kc0 + chunks_per_split, total_chunks);
@@ -374,7 +375,7 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
         if (k >= kBStages) mbar_wait(&empty_bar[s], ((k / kBStages) - 1) & 1);
         uint8_t* st = smem + s * kBStageBytes;
         mbar_expect_tx(&full_bar[s], kOperandBytes + 2 * kBN * kKC * 4);
-        tma_load_2d(st, &tm_z, &full_bar[s], kc * kKC, i0);
+        tma_load_2d(st, &tm_z, &full_bar[s], kc * kKC, il0);
         tma_load_2d(st + 2 * kOperandBytes, &tm_thi, &full_bar[s], kc * kKC, 0);
         tma_load_2d(st + 2 * kOperandBytes + kBN * kKC * 4, &tm_tlo, &full_bar[s], kc * kKC, 0);
       }
@@ -403,7 +404,7 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
     // ---- transform warps: thread -> (row = tid & 127, half = tid >> 7: 16 of the chunk's 32 columns)
     const int row = tid & 127, half = tid >> 7;
     const int i = i0 + row;
-    const bool row_ok = i < n;
+    const bool row_ok = il0 + row < n_rows;
     const long long bg = (long long)meta[0];
     const long long yi = row_ok ? labels[i] : 0;
     const int pi = row_ok ? pair[i] : -1;
@@ -462,13 +463,13 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
     mbar_wait(&accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3, chalf = warp >> 2;
-    const int orow = i0 + q * 32 + lane;
-    float* out = dpart + ((size_t)blockIdx.x * n + orow) * kBN + chalf * 128;
+    const int orow = il0 + q * 32 + lane;
+    float* out = dpart + ((size_t)blockIdx.x * n_rows + orow) * kBN + chalf * 128;
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chalf * 128 + c0), r);
-      if (orow < n) {
+      if (orow < n_rows) {
         float4* o4 = reinterpret_cast<float4*>(out + c0);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
@@ -486,8 +487,8 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
 
 }  // namespace tc
 
-int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
-                      cudaStream_t stream, int* launches) {
+int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, int row0, int n_rows,
+                      float inv_t, cudaStream_t stream, int* launches) {
   using namespace tc;
   split_tf32_kernel<<<dim3((w.ld + 31) / 32, 8), 256, 0, stream>>>(w.fhat, n, w.ld, w.f_hi, w.f_lo, w.ft_hi, w.ft_lo);
   OADG_LAUNCH_CHECK();
@@ -502,29 +503,29 @@ int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pai
     OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     attr = true;
   }
-  const int tiles = (n + kM - 1) / kM;
-  sim_fwd_tc_kernel<<<dim3(tiles, tiles), 128, kSmemBytes, stream>>>(mh, ml, labels, pair, w.meta, n, inv_t, w.partial,
-                                                                    w.z, w.ld);
+  sim_fwd_tc_kernel<<<dim3((n + kN - 1) / kN, (n_rows + kM - 1) / kM), 128, kSmemBytes, stream>>>(
+      mh, ml, labels, pair, w.meta, n, row0, n_rows, inv_t, w.partial, w.z, w.ld);
   OADG_LAUNCH_CHECK();
   if (launches) *launches += 2;
   return 0;
 }
 
-int launch_sim_bwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, float inv_t,
-                      cudaStream_t stream, int* launches) {
+int launch_sim_bwd_tc(const LossWs& w, const RowStats* stats_all, const int64_t* labels, const int32_t* pair, int n,
+                      int row0, int n_rows, float inv_t, cudaStream_t stream, int* launches) {
   using namespace tc;
   CUtensorMap mz, mth, mtl;
-  int rc = make_map(&mz, w.z, n, w.ld, w.ld, kM);
+  int rc = make_map(&mz, w.z, n_rows, w.ld, w.ld, kM);
   if (rc) return rc;
   rc = make_map(&mth, w.ft_hi, 256, w.ld, w.ld, kBN);
   if (rc) return rc;
   rc = make_map(&mtl, w.ft_lo, 256, w.ld, w.ld, kBN);
   if (rc) return rc;
-  const int tiles = (n + kM - 1) / kM;
+  const int tiles = (n_rows + kM - 1) / kM;
   const int total_chunks = (n + kKC - 1) / kKC;
   const int cps = (total_chunks + kBwdSplits - 1) / kBwdSplits;
   sim_bwd_tc_kernel<<<dim3(kBwdSplits, tiles), kBThreads, kBSmemBytes, stream>>>(mz, mth, mtl, labels, pair, w.meta,
-                                                                                 w.stats, n, inv_t, cps, w.dpart);
+                                                                                 stats_all, n, row0, n_rows, inv_t, cps,
+                                                                                 w.dpart);
   {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -132,19 +132,27 @@ OADG_HD void stream_chunk(const Lane& L, int region, const uint8_t* lut, const u
   }
   Chunk out;
 #ifdef __CUDA_ARCH__
+  // byte extraction / packing with PRMT, one LDS.U8 per byte; the channel of byte k is k % 3 (compile time)
+  const uint8_t* lc[3] = {lut, lut + 256, lut + 512};
 #pragma unroll
-#endif
+  for (int i = 0; i < 12; ++i) {
+    const uint32_t w = in.w[i];
+    const uint32_t r0 = lc[(4 * i) % 3][__byte_perm(w, 0, 0x4440)];
+    const uint32_t r1 = lc[(4 * i + 1) % 3][__byte_perm(w, 0, 0x4441)];
+    const uint32_t r2 = lc[(4 * i + 2) % 3][__byte_perm(w, 0, 0x4442)];
+    const uint32_t r3 = lc[(4 * i + 3) % 3][__byte_perm(w, 0, 0x4443)];
+    out.w[i] = __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);
+  }
+#else
   for (int i = 0; i < 12; ++i) {
     uint32_t v = 0;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
     for (int b = 0; b < 4; ++b) {
       const int k = i * 4 + b;
       v |= (uint32_t)lut[(k % 3) * 256 + chunk_get(in, k)] << (8 * b);
     }
     out.w[i] = v;
   }
+#endif
   chunk_store(L.out + o, n, vec, out);
 }
 // source frame of a streaming chunk: the lane input, or the bbo scratch frame

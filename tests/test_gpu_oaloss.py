@@ -108,3 +108,70 @@ print("FFMA-OK", loss.item())
     out = subprocess.run([sys.executable, '-c', code], cwd=root, capture_output=True, text=True,
                          env=dict(os.environ, PYTHONPATH=root, OADG_LOSS_TC='0'))
     assert 'FFMA-OK' in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
+
+
+def test_gathered_entry_points_match_oracle_single_rank(cuda, tmp_path):
+    """The cross-rank entry points (normalize / forward_gathered / backward_gathered) at world size 1 must equal
+    the local loss: same tolerance against the oracle."""
+    import torch
+    import torch.distributed as dist
+    from oadg_b200.distributed import gathered_contrastive_loss, CudaBackend
+    if not dist.is_initialized():
+        dist.init_process_group('gloo', init_method='file://%s' % (tmp_path / 'pg'), rank=0, world_size=1)
+    try:
+        x, labels = synth.make_roi_set(2088, seed=21)
+        xd = x.to(cuda).requires_grad_(True)
+        be = CudaBackend()
+        loss = gathered_contrastive_loss(xd, labels.to(cuda), temperature=0.06, loss_weight=0.01, backend=be)
+        loss.backward()
+        ref, gref = supcon_np.supcon_loss(x.numpy(), labels.numpy(), 0.06, 10, 0.01, want_grad=True)
+        assert abs(loss.item() - ref) <= RTOL * abs(ref)
+        assert np.linalg.norm(xd.grad.cpu().numpy() - gref) <= RTOL * np.linalg.norm(gref)
+        assert be.launches >= 6
+    finally:
+        dist.destroy_process_group()
+
+
+def _two_rank_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from oadg_b200.distributed import gathered_contrastive_loss
+    x, labels = synth.make_roi_set(2048, seed=40 + rank)
+    xd = x.cuda().requires_grad_(True)
+    loss = gathered_contrastive_loss(xd, labels.cuda(), temperature=0.06, loss_weight=0.01)
+    loss.backward()
+    q.put((rank, x.numpy(), labels.numpy().reshape(-1), loss.item(), xd.grad.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gathered_loss_two_gpus_nccl(cuda):
+    """2 ranks over NCCL: all-gathered contrast set vs the single-process oracle on the concatenated batch."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from oadg_b200.distributed import gathered_pair_map
+    from oadg_b200 import reference_pair_map
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
+    [p.join(60) for p in procs]
+    x_all = np.concatenate([r[1] for r in res])
+    y_all = np.concatenate([r[2] for r in res])
+    pair_all = gathered_pair_map(reference_pair_map(2048), 2)
+    ref, gref = supcon_np.supcon_loss(x_all, y_all, 0.06, 10, 0.01, want_grad=True, pair=pair_all)
+    for rank, _, _, loss, grad in res:
+        assert abs(loss - ref) <= RTOL * abs(ref)
+        want = 2 * gref[rank * 2048:(rank + 1) * 2048]
+        assert np.linalg.norm(grad - want) <= RTOL * np.linalg.norm(want)
