@@ -71,7 +71,8 @@ def workload_config(n_gpus):
     return {'workload': 'oamix(2x1024x2048x3 u8, 8 gt/img, version=augmix) + '
                         'contrastive_loss_plus fwd+bwd([2088,256] f32, T=0.06) per GPU step',
             'imgs_per_gpu': BS, 'frame': [H, W, 3], 'gt_per_img': N_GT, 'rois': [N_ROI, C_ROI],
-            'sharding': 'by image, %d rank(s), no data-path collective' % n_gpus,
+            'sharding': ('by image, %d rank(s); OA-Mix: no collective; OA-Loss: one all-gather of RoI embeddings'
+                         % n_gpus) if n_gpus > 1 else 'single rank',
             'l2': 'inputs larger than L2: %d distinct source frames (%.0f MB) cycled' % (POOL, POOL * H * W * 3 / 1e6)}
 
 
@@ -88,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -237,17 +238,29 @@ def product_arm(args):
     labels_dev = labels.to(dev)
     mix = OAMix(**OAMIX_CFG)
     loss_fn = ContrastiveLossPlus(**LOSS_CFG)
+    gather = world > 1 and not args.no_gather
+    if gather:
+        from oadg_b200.distributed import gathered_contrastive_loss, CudaBackend
+        gbe = CudaBackend()
+
+    def run_loss(xin):
+        if gather:   # one all-gather of the RoI embeddings over NVLink before the contrastive loss
+            return gathered_contrastive_loss(xin, labels_dev, temperature=LOSS_CFG['temperature'],
+                                             loss_weight=LOSS_CFG['loss_weight'], backend=gbe)
+        return loss_fn(xin, labels_dev)
     out_bufs = [torch.empty_like(dev_frames[0]) for _ in range(BS)]
     stream = torch.cuda.current_stream(dev)
 
-    def step(i, profile=None):
+    def step(i, profile=None, with_loss=True):
         j = (i * BS) % POOL
         imgs = [dev_frames[(j + b) % POOL] for b in range(BS)]
         g = [gts[(j + b) % POOL] for b in range(BS)]
         mix.oamix_batch(imgs, g, profile=profile, outs=out_bufs, inputs_ready=True)  # frames resident since setup
         n_mix = mix.last_launches
+        if not with_loss:
+            return n_mix, None
         x_dev.grad = None
-        loss = loss_fn(x_dev, labels_dev)
+        loss = run_loss(x_dev)
         loss.backward()
         return n_mix, loss
 
@@ -258,7 +271,7 @@ def product_arm(args):
             res = mix(dict(img=host_frames[(j + b) % POOL].numpy(), gt_bboxes=gts[(j + b) % POOL]))
             views.append(res['img2'])
         xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
-        loss = loss_fn(xd, labels_dev)
+        loss = run_loss(xd)
         loss.backward()
         return float(loss.item()), views
 
@@ -279,6 +292,8 @@ def product_arm(args):
     clocks.start()
     np.random.seed(1000 + rank)
     loss_fn.stats['launches'] = 0
+    if gather:
+        gbe.launches = 0
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -290,7 +305,7 @@ def product_arm(args):
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
-    launches += loss_fn.stats['launches']
+    launches += loss_fn.stats['launches'] + (gbe.launches if gather else 0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,7 +342,7 @@ def product_arm(args):
     prof = {}
     np.random.seed(1000 + rank)
     for i in range(args.steps):
-        step(i, profile=prof)
+        step(i, profile=prof, with_loss=False)   # rank 0 only: no collective may be issued here
     torch.cuda.synchronize()
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
@@ -352,6 +367,7 @@ def product_arm(args):
     for _ in range(3):
         x_dev.grad = None
         loss_fn(x_dev, labels_dev).backward()
+    torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(20):
         x_dev.grad = None
@@ -387,12 +403,13 @@ def product_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cores', type=int, default=0, help='worker processes of the CPU arm (0 = min(cpu_count, 64))')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-gather', action='store_true', help='N>1: keep the reference\'s per-rank local loss')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)
