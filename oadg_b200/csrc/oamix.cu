@@ -343,7 +343,7 @@ step_kernel(DevPlan P, const Lane* __restrict__ lanes, const uint8_t* __restrict
         n[k] = min(kChunkPx, W - x[k]);
         const bool mine = run_is_stream(L, x[k], y[k], n[k], reg[k]);
         if (!mine) n[k] = 0;
-        else if (reg[k] >= 0 && kind_streams(L.kind[reg[k]])) {
+        else if (reg[k] >= 0 && kind_streams(L.kind[reg[k]]) && vec && n[k] == kChunkPx) {
           vecrun[k] = true;
           chunk_load(stream_src(L, reg[k], scratch, frame_bytes) + ((size_t)y[k] * W + x[k]) * 3, n[k], vec, c[k]);
         }

@@ -19,35 +19,18 @@ struct Chunk {
   uint32_t w[12];
 };
 
-#ifdef __CUDA_ARCH__
-// cold paths (ragged right edge, unaligned frames): kept out of line so they do not inflate the registers of
-// the vector path
-__device__ __noinline__ void chunk_load_scalar(const uint8_t* p, int n, Chunk& c) {
-  for (int i = 0; i < 12; ++i) {
-    uint32_t v = 0;
-    for (int b = 0; b < 4; ++b)
-      if (i * 4 + b < n * 3) v |= (uint32_t)__ldg(p + i * 4 + b) << (8 * b);
-    c.w[i] = v;
-  }
-}
-__device__ __noinline__ void chunk_store_scalar(uint8_t* p, int n, const Chunk& c) {
-  for (int i = 0; i < 12; ++i)
-    for (int b = 0; b < 4; ++b)
-      if (i * 4 + b < n * 3) p[i * 4 + b] = (uint8_t)(c.w[i] >> (8 * b));
-}
-#endif
-
+// On the device a chunk is always a full, 16-byte aligned run (three vector loads / stores); ragged right edges
+// and unaligned frames take the per-pixel paths, so that a Chunk never has its address taken (it must stay in
+// registers).  The host build (tests/hostsim) copies n pixels.
 OADG_HD void chunk_load(const uint8_t* p, int n, bool vec, Chunk& c) {
 #ifdef __CUDA_ARCH__
-  if (vec && n == kChunkPx) {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2);
-    c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
-    c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
-    c.w[8] = d.x; c.w[9] = d.y; c.w[10] = d.z; c.w[11] = d.w;
-    return;
-  }
-  chunk_load_scalar(p, n, c);
+  (void)n;
+  (void)vec;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2);
+  c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
+  c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
+  c.w[8] = d.x; c.w[9] = d.y; c.w[10] = d.z; c.w[11] = d.w;
 #else
   (void)vec;
   memset(c.w, 0, sizeof(c.w));
@@ -57,14 +40,12 @@ OADG_HD void chunk_load(const uint8_t* p, int n, bool vec, Chunk& c) {
 
 OADG_HD void chunk_store(uint8_t* p, int n, bool vec, const Chunk& c) {
 #ifdef __CUDA_ARCH__
-  if (vec && n == kChunkPx) {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = make_uint4(c.w[0], c.w[1], c.w[2], c.w[3]);
-    q[1] = make_uint4(c.w[4], c.w[5], c.w[6], c.w[7]);
-    q[2] = make_uint4(c.w[8], c.w[9], c.w[10], c.w[11]);
-    return;
-  }
-  chunk_store_scalar(p, n, c);
+  (void)n;
+  (void)vec;
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(c.w[0], c.w[1], c.w[2], c.w[3]);
+  q[1] = make_uint4(c.w[4], c.w[5], c.w[6], c.w[7]);
+  q[2] = make_uint4(c.w[8], c.w[9], c.w[10], c.w[11]);
 #else
   (void)vec;
   memcpy(p, c.w, (size_t)n * 3);
@@ -186,7 +167,11 @@ OADG_HD void classify_mix_tile(const DevPlan& P, const MixJob& J, int x0, int y0
 OADG_HD void mix_chunk(const DevPlan& P, const MixJob& J, const MixTile& T, int x, int y, int n, bool vec) {
   const oadg_view_t& V = P.views[J.view];
   const size_t o = ((size_t)y * V.W + x) * 3;
-  if (T.overflow || V.width > 4) {
+  bool slow = T.overflow || V.width > 4;
+#ifdef __CUDA_ARCH__
+  slow = slow || !vec || n != kChunkPx;
+#endif
+  if (slow) {
     for (int i = 0; i < n; ++i) mix_pixel(P, J, x + i, y);
     return;
   }
