@@ -14,8 +14,8 @@ value  : inputs resident in HBM, CUDA-event timed (includes the saliency D2H syn
          sampling and the plan upload -- they are part of the path).
 e2e    : the registered plugins called with HOST buffers (pinned): H2D of frames / embeddings and D2H of
          the generated views / loss value inside the timed region.
-roofline: the OA-Mix step kernel, achieved = algorithmic bytes (2 * 3HW per lane step) / CUDA-event kernel
-         time from a second, event-instrumented pass over the same seeded plans.
+roofline: the OA-Mix chain kernel (one persistent launch per batch), achieved = algorithmic bytes (2 * 3HW per lane
+         step) / CUDA-event kernel time from a second, event-instrumented pass over the same seeded plans.
 cpu_baseline / --impl reference: the oracle port of the reference's CPU path (oracle/oamix_np.py +
          oracle/supcon_np.py: same cv2 / Pillow / NumPy calls as the reference; the reference itself is
          Python under /root/reference and does not exist on the GPU box) on the host cores.
@@ -349,18 +349,25 @@ def product_arm(args):
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    step_ms = prof.get('step_ms', 0.0)
-    achieved = prof.get('step_bytes', 0) / (step_ms / 1e3) / 1e9 if step_ms > 0 else 0.0
-    total_kernel_ms = sum(v for k, v in prof.items() if k.endswith('_ms'))
-    roofline = {'kernel': 'oadg::step_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+    chain_ms, mix_ms, n_l = prof.get('chain_ms', 0.0), prof.get('mix_ms', 0.0), max(prof.get('chain_n', 1), 1)
+    achieved = prof.get('step_bytes', 0) / (chain_ms / 1e3) / 1e9 if chain_ms > 0 else 0.0
+    total_kernel_ms = chain_ms + mix_ms
+    roofline = {'kernel': 'oadg::oamix_chain_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'launches': prof.get('step_n', 0),
-                'algorithmic_bytes_per_launch': prof.get('step_bytes', 0) / max(prof.get('step_n', 1), 1),
-                'avg_launch_ms': step_ms / max(prof.get('step_n', 1), 1),
-                'share_of_oamix_kernel_time': step_ms / total_kernel_ms if total_kernel_ms else None,
-                'oamix_kernel_ms_by_kind': {k[:-3]: round(v, 4) for k, v in prof.items() if k.endswith('_ms')},
-                'oamix_launches_by_kind': {k[:-2]: v for k, v in prof.items() if k.endswith('_n')},
-                'oamix_whole_view_gbs': prof.get('view_bytes', 0) / (total_kernel_ms / 1e3) / 1e9 if total_kernel_ms else None}
+                'launches': prof.get('chain_n', 0),
+                'algorithmic_bytes_per_launch': prof.get('step_bytes', 0) / n_l,
+                'algorithmic_bytes': 'sum over the launch\'s lane steps of 2 * 3HW (one read + one write of a frame per '
+                                     'depth step, SURVEY 8d); the launch also does the masks, histograms, LUTs and '
+                                     'bboxes-only chains, which count as zero useful bytes',
+                'avg_launch_ms': chain_ms / n_l,
+                'share_of_oamix_kernel_time': chain_ms / total_kernel_ms if total_kernel_ms else None,
+                'phases_per_launch': prof.get('phases', 0) / n_l,
+                'chain_phase_ms_by_item_kinds': {k: round(v, 4) for k, v in
+                                                 sorted(prof.get('phase_ms_by_kinds', {}).items(), key=lambda kv: -kv[1])},
+                'mix_kernel_ms': mix_ms, 'mix_launches': prof.get('mix_n', 0),
+                'oamix_whole_view_gbs': prof.get('view_bytes', 0) / (total_kernel_ms / 1e3) / 1e9 if total_kernel_ms else None,
+                'oamix_whole_view_frac': (prof.get('view_bytes', 0) / (total_kernel_ms / 1e3) / 1e9 / peak)
+                if total_kernel_ms else None}
 
     log('profiled replay done')
     # OA-Loss alone (CUDA events), for the record

@@ -161,15 +161,17 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
                        void* workspace_dev, size_t workspace_bytes,
                        int* launches_out, void* stream);
 
-/* Same as oadg_oamix_execute, but every launch is bracketed by CUDA events on `stream` and the
- * call synchronises the stream before returning (measurement only).  ms_by_kind / count_by_kind
- * receive 9 entries: {profile, hist, lut, bbo_pass, mask, step (stream), mix, frame copy, step (pixel)}. */
-#define OADG_PROFILE_KINDS 9
+/* Same as oadg_oamix_execute, with CUDA events on `stream` around the two launches (the chain kernel and the mix
+ * kernel); the call synchronises the stream before returning (measurement only).  The chain kernel stamps
+ * %globaltimer at every phase boundary: phase_ms[p] / phase_kinds[p] (bit k = the phase holds work items of kind k,
+ * k = 0 profile, 1 mask, 2 hist, 3 lut, 4 frame copy, 5 bbo read half, 6 bbo write half, 7 depth step) receive up
+ * to phase_cap entries. */
 int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
                                 const uint8_t* const* src_dev, int n_img,
                                 uint8_t* const* dst_dev,
                                 void* workspace_dev, size_t workspace_bytes,
-                                float* ms_by_kind, int* count_by_kind, void* stream);
+                                float* ms_chain, float* ms_mix, int* n_phases_out,
+                                float* phase_ms, int32_t* phase_kinds, int phase_cap, void* stream);
 
 /* ---- OA-Loss ---------------------------------------------------------------- */
 

@@ -4,11 +4,10 @@
 #include "oadg.h"
 #include "oamix_math.h"
 
-#ifdef __CUDA_ARCH__
-#define OADG_LDG(p) __ldg(p)
-#else
+// Every frame, profile, mask, histogram and LUT the chain kernel reads may have been written earlier in the SAME
+// launch by another SM (phases are separated by a grid barrier), so device loads are plain ld.global (coherent at
+// the barrier's fence), never the non-coherent __ldg path.
 #define OADG_LDG(p) (*(p))
-#endif
 
 namespace oadg {
 
@@ -43,12 +42,46 @@ struct Lane {            // one (view, branch) chain alive at the current depth
   int32_t all_streaming;             // every region runs a table-lookup / bbo-copy op: no pixel kernel needed
 };
 
-struct Chain {           // one bboxes-only op being evaluated (sequential over its boxes)
-  int32_t view, n;       // n = boxes in the chain
-  int32_t bbo_first, lane;
-  uint8_t* S;            // ping-pong frames, both start as copies of the lane input;
-  uint8_t* T;            // after n boxes the result is in T when n is odd, in S when n is even
+struct Chain {           // one bboxes-only op being evaluated (bbox_augmentation.py:74-88)
+  int32_t view, lane;
+  const uint8_t* in;     // the lane input the chain starts from
+  uint8_t* S;            // running image: full copy of `in`, updated box by box inside the box supports
+  uint8_t* T;            // staging frame: a level's blended supports land here, then are copied back into S
 };
+
+struct BboJob {          // one box of one chain
+  int32_t chain, bbo;    // chain index, index into the oadg_bbo array
+  int32_t rect[4];       // the box's mask support [x0,y0,x1,y1): the only pixels the box can change
+};
+
+// ---- work items of the chain kernel ------------------------------------------------------------------------
+// The host turns a plan into PHASES of independent work ITEMS; items are cut into TILES (one CTA iteration each).
+// Phase p+1 may read anything phase p wrote (grid barrier in between).
+enum {
+  OADG_IT_PROFILE = 0,   // obj = gt*2 + axis            1 tile
+  OADG_IT_MASK = 1,      // obj = view                   tiles of 256 x 32 px
+  OADG_IT_HIST = 2,      // obj = lane                   tiles of kHistTilePx px (linear)
+  OADG_IT_LUT = 3,       // obj = lut job                1 tile
+  OADG_IT_COPY = 4,      // obj = chain                  tiles of kCopyTileBytes (linear)
+  OADG_IT_BBO_R = 5,     // obj = bbo job                tiles of 64 x 16 px over the support
+  OADG_IT_BBO_W = 6,     // obj = bbo job                same tiling
+  OADG_IT_STEP = 7,      // obj = lane                   tiles of 256 x 64 px
+  OADG_IT_KINDS = 8
+};
+struct Item {
+  int32_t kind, obj;
+  int32_t tile0, ntiles;   // tile0: first tile index within the phase
+  int32_t tx;              // tiles per row (2-D kinds)
+  int32_t pad[3];
+};
+struct Phase {
+  int32_t item0, n_items, n_tiles, pad;
+};
+constexpr int kMaskTileW = 256, kMaskTileH = 32;
+constexpr int kHistTilePx = 32768;
+constexpr int kCopyTileBytes = 65536;
+constexpr int kBboTileW = 64, kBboTileH = 16;
+constexpr int kStepTileW = 256, kStepTileH = 64;
 
 struct MixJob {
   int32_t view, pad;
@@ -104,27 +137,15 @@ OADG_HD uint8_t lut_simple_at(const oadg_op_t& op, int i, double luma_sum, doubl
   return (uint8_t)pil_blend(deg, i, op.factor);
 }
 
-// ---- one pixel of box j of a bboxes-only chain (bbox_augmentation.py:57-71) ----------
-// The chain ping-pongs between two full frames: pass j reads X (complete image after j-1 boxes) and writes
-// Y = X with box j blended in.  Y is one pass behind, so the pixels of box j-1's support that box j does not
-// touch are copied across as well; then Y is the complete image after j boxes and no copy-back launch is needed.
-OADG_HD void bbo_pixel(const DevPlan& P, const Chain& C, int j, int x, int y) {
-  const uint8_t* X = (j & 1) ? C.T : C.S;
-  uint8_t* Y = (j & 1) ? C.S : C.T;
-  const oadg_bbo_t& B = P.bbo[C.bbo_first + j];
-  const oadg_gt_t& G = P.gts[B.gt];
+// ---- one pixel of one box of a bboxes-only chain (bbox_augmentation.py:57-71) ----------
+// Read half: T = blend(S, warp(S), m) inside the box's support; write half: S = T.  All boxes of a LEVEL
+// (mutually independent boxes, oamix_exec.h) run their read halves in one phase and their write halves in the next,
+// so a warp never sees a half-updated neighbour.
+OADG_HD void bbo_r_pixel(const DevPlan& P, const Chain& C, const oadg_bbo_t& B, int x, int y) {
   const oadg_view_t& V = P.views[C.view];
   const size_t o = ((size_t)y * V.W + x) * 3;
-  const bool in_cur = x >= G.supp[0] && x < G.supp[2] && y >= G.supp[1] && y < G.supp[3];
-  if (!in_cur) {
-    if (j == 0) return;
-    const int32_t* s = P.gts[P.bbo[C.bbo_first + j - 1].gt].supp;
-    if (!(x >= s[0] && x < s[2] && y >= s[1] && y < s[3])) return;
-    Y[o] = X[o];
-    Y[o + 1] = X[o + 1];
-    Y[o + 2] = X[o + 2];
-    return;
-  }
+  const uint8_t* X = C.S;
+  uint8_t* Y = C.T;
   const float m = fmul(OADG_LDG(P.prof_y + (size_t)B.gt * P.max_h + y), OADG_LDG(P.prof_x + (size_t)B.gt * P.max_w + x));
   int v[3] = {X[o], X[o + 1], X[o + 2]};
   if (m != 0.f) {  // m == 0 => img*1 + aug*0 == img exactly
@@ -139,17 +160,11 @@ OADG_HD void bbo_pixel(const DevPlan& P, const Chain& C, int j, int x, int y) {
   Y[o + 1] = (uint8_t)v[1];
   Y[o + 2] = (uint8_t)v[2];
 }
-// bounding rect of (support of box j) U (support of box j-1): the pixels pass j may write
-OADG_HD void bbo_pass_rect(const DevPlan& P, const Chain& C, int j, int r[4]) {
-  const int32_t* s = P.gts[P.bbo[C.bbo_first + j].gt].supp;
-  r[0] = s[0]; r[1] = s[1]; r[2] = s[2]; r[3] = s[3];
-  if (j > 0) {
-    const int32_t* q = P.gts[P.bbo[C.bbo_first + j - 1].gt].supp;
-    if (q[2] > q[0] && q[3] > q[1]) {
-      if (r[2] <= r[0] || r[3] <= r[1]) { r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; r[3] = q[3]; }
-      else { r[0] = imin(r[0], q[0]); r[1] = imin(r[1], q[1]); r[2] = imax(r[2], q[2]); r[3] = imax(r[3], q[3]); }
-    }
-  }
+OADG_HD void bbo_w_pixel(const DevPlan& P, const Chain& C, int x, int y) {
+  const size_t o = ((size_t)y * P.views[C.view].W + x) * 3;
+  C.S[o] = C.T[o];
+  C.S[o + 1] = C.T[o + 1];
+  C.S[o + 2] = C.T[o + 2];
 }
 
 // ---- union mask of one view at one pixel: written once per batch by mask_kernel -------------------

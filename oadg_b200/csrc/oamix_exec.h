@@ -89,22 +89,24 @@ inline int parse_plan(const void* blob, size_t bytes, PlanView& pv) {
   return 0;
 }
 
+constexpr int kMaxGrid = 256;   // the chain kernel never runs more CTAs than this (B200: 148)
+
 struct Layout {
   size_t frame_bytes;
-  size_t off_plan, off_prof_x, off_prof_y, off_branch, off_scratch, off_hist, off_luma, off_lut, off_tables;
-  size_t off_maskf, off_masku;
+  size_t off_plan, off_prof_x, off_prof_y, off_branch, off_scratch, off_zero, off_hist, off_luma, off_lut, off_tables;
+  size_t off_maskf, off_masku, off_ts;
+  size_t zero_bytes;
   int any_bg;
   size_t tables_bytes;
-  int n_lanes_total, n_scratch, n_lut, n_hist, max_depth;
+  int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_phases, n_bbo;
   size_t total;
 };
 
-// Everything is sized from the plan alone.
+// Everything is sized from the plan alone (upper bounds: dead boxes / chains are only pruned at execute time).
 inline void make_layout(const PlanView& pv, Layout& L) {
   const oadg_plan_header_t& h = *pv.h;
   L.frame_bytes = align_up_sz((size_t)h.max_h * h.max_w * 3, 256);
-  int max_depth = 0, lanes_total = 0, n_lut = 0, n_hist = 0;
-  int bbo_at_depth[OADG_MAX_DEPTH] = {0};
+  int max_depth = 0, lanes_total = 0, n_lut = 0, n_hist = 0, n_chains = 0, max_chain = 0;
   int any_bg = 0;
   for (int v = 0; v < h.n_views; ++v) {
     const oadg_view_t& V = pv.views[v];
@@ -117,20 +119,24 @@ inline void make_layout(const PlanView& pv, Layout& L) {
           const oadg_op_t& op = pv.ops[op_index(V, b, d, r)];
           if (is_lut_kind(op.kind)) ++n_lut;
           if (needs_hist(op.kind)) hist = true;
-          if (op.kind == OADG_OP_BBO_AFFINE && op.bbo_count > 0) ++bbo_at_depth[d];
+          if (op.kind == OADG_OP_BBO_AFFINE && op.bbo_count > 0) {
+            ++n_chains;
+            max_chain = op.bbo_count > max_chain ? op.bbo_count : max_chain;
+          }
           if (op.kind == OADG_OP_BG_AFFINE) any_bg = 1;
         }
         if (hist) ++n_hist;
       }
     }
   }
-  int n_scratch = 0;
-  for (int d = 0; d < OADG_MAX_DEPTH; ++d) n_scratch = bbo_at_depth[d] > n_scratch ? bbo_at_depth[d] : n_scratch;
   L.max_depth = max_depth;
   L.n_lanes_total = lanes_total;
-  L.n_scratch = n_scratch * 2;  // S + T per concurrent chain
+  L.n_chains = n_chains;
   L.n_lut = n_lut;
   L.n_hist = n_hist;
+  L.n_bbo = h.n_bbo;
+  L.max_items = 2 * h.n_gt + h.n_views + 2 * lanes_total + n_lut + n_chains + 2 * h.n_bbo + 8;
+  L.max_phases = 4 + max_depth * (3 + 2 * max_chain);
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -138,9 +144,12 @@ inline void make_layout(const PlanView& pv, Layout& L) {
     return at;
   };
   L.tables_bytes = align_up_sz((size_t)lanes_total * sizeof(Lane), 16) +
-                   2 * align_up_sz((size_t)lanes_total * sizeof(int32_t), 16) +
                    align_up_sz((size_t)(n_lut > 0 ? n_lut : 1) * sizeof(LutJob), 16) +
-                   align_up_sz((size_t)lanes_total * OADG_MAX_REGIONS * sizeof(Chain), 16) +
+                   align_up_sz((size_t)(n_chains > 0 ? n_chains : 1) * sizeof(Chain), 16) +
+                   align_up_sz((size_t)(h.n_bbo > 0 ? h.n_bbo : 1) * sizeof(BboJob), 16) +
+                   align_up_sz((size_t)L.max_items * sizeof(Item), 16) +
+                   align_up_sz((size_t)L.max_phases * sizeof(Phase), 16) +
+                   align_up_sz((size_t)L.max_phases * (kMaxGrid + 1) * sizeof(int32_t), 16) +
                    align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
   L.off_tables = align_up_sz((size_t)h.total_bytes, 16);
@@ -150,23 +159,149 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   size_t n_branch_frames = 0;
   for (int v = 0; v < h.n_views; ++v) n_branch_frames += (size_t)pv.views[v].width * 2;
   L.off_branch = take(n_branch_frames * L.frame_bytes);
-  L.off_scratch = take((size_t)L.n_scratch * L.frame_bytes);
+  L.off_scratch = take((size_t)n_chains * 2 * L.frame_bytes);  // S + T per chain
+  // one memset: [grid barrier counter | histograms | luma sums]
+  L.off_zero = take(256);
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
+  L.zero_bytes = o - L.off_zero;
   L.off_lut = take((size_t)(n_lut > 0 ? n_lut : 1) * 768);
   L.any_bg = any_bg;
   const size_t mask_px = (size_t)h.max_h * h.max_w;
   L.off_maskf = take(any_bg ? (size_t)h.n_views * mask_px * sizeof(float) : 0);
   L.off_masku = take(any_bg ? (size_t)h.n_views * mask_px : 0);
+  L.off_ts = take((size_t)(L.max_phases + 2) * sizeof(unsigned long long));
   L.total = o;
 }
 
+// ---- bboxes-only chains: dead-box elimination and level scheduling -----------------------------------------
+// Box j of a chain (bbox_augmentation.py:74-88) changes only the pixels of its mask support supp_j and reads the
+// running image at supp_j and at the inverse-affine footprint fp_j of supp_j.
+//   * box j is NEEDED when supp_j meets the region that keeps the chain's result, or a later needed box reads it;
+//     every other box cannot influence a kept pixel and is skipped (its RNG draws were already consumed).
+//   * level(j) = max over needed i < j of { level(i)+1 if (fp_j u supp_j) meets supp_i ;  level(i) if fp_i meets
+//     supp_j }.  Boxes of one level have disjoint supports and read nothing a same-level box writes, so a level
+//     runs as one read phase + one write phase.
+struct IRect {
+  int x0, y0, x1, y1;
+};
+inline bool irect_hit(const IRect& a, const IRect& b) {
+  return a.x0 < b.x1 && a.x1 > b.x0 && a.y0 < b.y1 && a.y1 > b.y0;
+}
+inline bool irect_empty(const IRect& a) { return a.x1 <= a.x0 || a.y1 <= a.y0; }
+inline IRect irect_union(const IRect& a, const IRect& b) {
+  if (irect_empty(a)) return b;
+  if (irect_empty(b)) return a;
+  return IRect{a.x0 < b.x0 ? a.x0 : b.x0, a.y0 < b.y0 ? a.y0 : b.y0, a.x1 > b.x1 ? a.x1 : b.x1, a.y1 > b.y1 ? a.y1 : b.y1};
+}
+// conservative source footprint of `s` under the dst->src map (fixed-point rounding < 1 px, +1 tap, +1 margin)
+inline IRect footprint(const double* m, const IRect& s, int W, int H) {
+  if (irect_empty(s)) return IRect{0, 0, 0, 0};
+  double xs[4], ys[4];
+  const double cx[2] = {(double)s.x0, (double)(s.x1 - 1)}, cy[2] = {(double)s.y0, (double)(s.y1 - 1)};
+  for (int i = 0; i < 4; ++i) {
+    xs[i] = m[0] * cx[i & 1] + m[1] * cy[i >> 1] + m[2];
+    ys[i] = m[3] * cx[i & 1] + m[4] * cy[i >> 1] + m[5];
+  }
+  double xa = xs[0], xb = xs[0], ya = ys[0], yb = ys[0];
+  for (int i = 1; i < 4; ++i) {
+    xa = xs[i] < xa ? xs[i] : xa; xb = xs[i] > xb ? xs[i] : xb;
+    ya = ys[i] < ya ? ys[i] : ya; yb = ys[i] > yb ? ys[i] : yb;
+  }
+  auto clampd = [](double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  IRect f;
+  f.x0 = (int)clampd(xa - 3.0, 0.0, (double)W);
+  f.y0 = (int)clampd(ya - 3.0, 0.0, (double)H);
+  f.x1 = (int)clampd(xb + 4.0, 0.0, (double)W);
+  f.y1 = (int)clampd(yb + 4.0, 0.0, (double)H);
+  return f;
+}
+
+struct ChainSched {
+  std::vector<int> box;     // needed boxes (offsets into the op's bbo slice), plan order
+  std::vector<int> level;   // 1-based level of each needed box
+  int n_levels = 0;
+};
+inline void schedule_chain(const PlanView& pv, const oadg_view_t& V, const oadg_op_t& op, const IRect* keep,
+                           ChainSched& out) {
+  const int n = op.bbo_count;
+  std::vector<IRect> supp(n), reads(n), fp(n);
+  for (int j = 0; j < n; ++j) {
+    const oadg_bbo_t& B = pv.bbo[op.bbo_first + j];
+    const int32_t* s = pv.gts[B.gt].supp;
+    supp[j] = IRect{s[0], s[1], s[2], s[3]};
+    fp[j] = footprint(B.minv, supp[j], V.W, V.H);
+    reads[j] = irect_union(fp[j], supp[j]);
+  }
+  std::vector<char> need(n, 0);
+  for (int j = n - 1; j >= 0; --j) {
+    if (irect_empty(supp[j])) continue;
+    bool nd = keep == nullptr || irect_hit(supp[j], *keep);
+    for (int k = j + 1; k < n && !nd; ++k) nd = need[k] && irect_hit(reads[k], supp[j]);
+    need[j] = nd;
+  }
+  std::vector<int> lvl(n, 0);
+  out.box.clear();
+  out.level.clear();
+  out.n_levels = 0;
+  for (int j = 0; j < n; ++j) {
+    if (!need[j]) continue;
+    int l = 1;
+    for (int i = 0; i < j; ++i) {
+      if (!need[i]) continue;
+      if (irect_hit(reads[j], supp[i])) l = lvl[i] + 1 > l ? lvl[i] + 1 : l;
+      else if (irect_hit(fp[i], supp[j])) l = lvl[i] > l ? lvl[i] : l;
+    }
+    lvl[j] = l;
+    out.box.push_back(j);
+    out.level.push_back(l);
+    out.n_levels = l > out.n_levels ? l : out.n_levels;
+  }
+}
+
+// relative time of one tile of each item kind (cost-balanced split of a phase over the CTAs)
+inline int tile_cost(int kind) {
+  switch (kind) {
+    case OADG_IT_PROFILE: return 16;
+    case OADG_IT_MASK: return 8;
+    case OADG_IT_HIST: return 12;
+    case OADG_IT_LUT: return 8;
+    case OADG_IT_COPY: return 5;
+    case OADG_IT_BBO_R: return 3;
+    case OADG_IT_BBO_W: return 1;
+    default: return 4;
+  }
+}
+constexpr int kStepCostStream = 4, kStepCostPixel = 40, kStepCostEdge = 10;
+
+struct ChainArgs {       // everything the chain kernel needs (device pointers)
+  DevPlan P;
+  const Lane* lanes;
+  const LutJob* lutjobs;
+  const Chain* chains;
+  const BboJob* bjobs;
+  const Item* items;
+  const Phase* phases;
+  const int32_t* ranges;     // [n_phases][grid + 1] tile boundaries of every CTA
+  int32_t n_phases, grid;
+  unsigned* hist;
+  unsigned long long* luma;
+  uint8_t* luts;
+  float* prof_x;
+  float* prof_y;
+  float* maskf;
+  uint8_t* masku;
+  const uint8_t* scratch;
+  size_t frame_bytes;
+  unsigned* bar;               // grid barrier counter (zeroed before the launch)
+  unsigned long long* phase_ts;  // globaltimer at the end of every phase (measurement aid)
+};
+
 // Backend concept (all return 0 or an error code):
-//   upload(dst, src_host, bytes)  zero(dst, bytes)  copy(dst, src, bytes)
-//   profiles(P, pv, prof_x, prof_y)           masks(P, n_views, maskf, masku)
-//   hist(P, lanes, lane_ids, n, hist, luma)   lut(P, jobs, n, hist, luma, luts)
-//   bbo_pass(P, chains, n, j, roi_w, roi_h)
-//   step(P, lanes, n, pixel_lane_ids, n_pixel_lanes, scratch, frame_bytes)   mix(P, jobs, n)
+//   grid()                         CTAs the chain kernel will run (<= kMaxGrid)
+//   upload(dst, src_host, bytes)   zero(dst, bytes)
+//   chain(args, host_tables...)    the phase/item interpreter (one persistent launch on the device)
+//   mix(P, jobs, n)
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
                  uint8_t* const* dst, void* workspace, size_t workspace_bytes) {
@@ -182,7 +317,17 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   make_layout(pv, L);
   if (workspace_bytes < L.total) return OADG_E_ARG;
   if (((uintptr_t)workspace & 255) != 0) return OADG_E_ARG;
+  {  // the profile tile keeps the low-res profile and the gaussian kernel in 24 KB of shared memory
+    int max_k = 1;
+    for (int g = 0; g < h.n_gt; ++g) {
+      max_k = pv.gts[g].kx > max_k ? pv.gts[g].kx : max_k;
+      max_k = pv.gts[g].ky > max_k ? pv.gts[g].ky : max_k;
+    }
+    if ((h.max_w > h.max_h ? h.max_w : h.max_h) / 4 + 1 + max_k > 6144) return OADG_E_LIMIT;
+  }
   char* ws = static_cast<char*>(workspace);
+  const int G = be.grid();
+  if (G < 1 || G > kMaxGrid) return OADG_E_LIMIT;
 
   // host staging buffer: plan (with lut / scratch slots filled in) followed by the launch tables
   std::vector<char> stage(L.off_tables + L.tables_bytes, 0);
@@ -208,37 +353,59 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     return at;
   };
   const size_t t_lanes = carve((size_t)L.n_lanes_total * sizeof(Lane));
-  const size_t t_lane_ids = carve((size_t)L.n_lanes_total * sizeof(int32_t));
-  const size_t t_px_ids = carve((size_t)L.n_lanes_total * sizeof(int32_t));
   const size_t t_lut = carve((size_t)(L.n_lut > 0 ? L.n_lut : 1) * sizeof(LutJob));
-  const size_t t_chain = carve((size_t)L.n_lanes_total * OADG_MAX_REGIONS * sizeof(Chain));
+  const size_t t_chain = carve((size_t)(L.n_chains > 0 ? L.n_chains : 1) * sizeof(Chain));
+  const size_t t_bjob = carve((size_t)(L.n_bbo > 0 ? L.n_bbo : 1) * sizeof(BboJob));
+  const size_t t_items = carve((size_t)L.max_items * sizeof(Item));
+  const size_t t_phases = carve((size_t)L.max_phases * sizeof(Phase));
+  const size_t t_ranges = carve((size_t)L.max_phases * (kMaxGrid + 1) * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
-  auto* lane_ids = reinterpret_cast<int32_t*>(stage.data() + t_lane_ids);
-  auto* px_ids = reinterpret_cast<int32_t*>(stage.data() + t_px_ids);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
   auto* chains = reinterpret_cast<Chain*>(stage.data() + t_chain);
+  auto* bjobs = reinterpret_cast<BboJob*>(stage.data() + t_bjob);
+  auto* items = reinterpret_cast<Item*>(stage.data() + t_items);
+  auto* phases = reinterpret_cast<Phase*>(stage.data() + t_phases);
+  auto* ranges = reinterpret_cast<int32_t*>(stage.data() + t_ranges);
   auto* mixjobs = reinterpret_cast<MixJob*>(stage.data() + t_mix);
 
-  struct DepthInfo {
-    int lane0 = 0, n_lanes = 0, hist0 = 0, n_hist = 0, lut0 = 0, n_lut = 0, chain0 = 0, n_chain = 0;
-    int max_chain = 0, max_roi_w = 0, max_roi_h = 0, n_px = 0;
+  // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
+  struct Todo {
+    int kind, obj, phase, w, hgt;   // w x hgt: pixel extent (2-D kinds) / w = linear size (1-D kinds)
   };
-  std::vector<DepthInfo> di(L.max_depth);
-  int lane_n = 0, hist_n = 0, lut_n = 0, chain_n = 0, histid_n = 0;
+  std::vector<Todo> todo;
+  todo.reserve(L.max_items);
+  int n_phases = 0;
+  auto add = [&](int kind, int obj, int phase, int w, int hgt) {
+    todo.push_back(Todo{kind, obj, phase, w, hgt});
+    n_phases = phase + 1 > n_phases ? phase + 1 : n_phases;
+  };
+  const int prof_done = h.n_gt > 0 ? 1 : 0;
+  for (int g = 0; g < h.n_gt; ++g)
+    for (int axis = 0; axis < 2; ++axis) add(OADG_IT_PROFILE, g * 2 + axis, 0, 1, 1);
+  int mask_done = prof_done;
+  if (L.any_bg) {  // union mask of every view (views without gt boxes get zeros)
+    for (int v = 0; v < h.n_views; ++v) add(OADG_IT_MASK, v, prof_done, pv.views[v].W, pv.views[v].H);
+    mask_done = prof_done + 1;
+  }
+
+  int lane_n = 0, hist_n = 0, lut_n = 0, chain_n = 0, bjob_n = 0;
   std::vector<const uint8_t*> final_frame((size_t)h.n_views * OADG_MAX_WIDTH, nullptr);
+  std::vector<int> step_phase((size_t)h.n_views * OADG_MAX_WIDTH, -1);  // phase of the lane's previous step
+  struct HistKey {
+    const uint8_t* in;
+    int slot, done;
+  };
+  std::vector<HistKey> hist_keys;
+  ChainSched cs;
   for (int d = 0; d < L.max_depth; ++d) {
-    DepthInfo& D = di[d];
-    D.lane0 = lane_n;
-    D.hist0 = histid_n;
-    D.lut0 = lut_n;
-    D.chain0 = chain_n;
-    int scratch_used = 0;
+    hist_keys.clear();  // branch frames are recycled every other depth: a key is only valid within one depth
     for (int v = 0; v < h.n_views; ++v) {
       const oadg_view_t& V = pv.views[v];
       for (int b = 0; b < V.width; ++b) {
         if (V.depth[b] <= d) continue;
-        Lane& ln = lanes[lane_n];
+        const int lane_id = lane_n++;
+        Lane& ln = lanes[lane_id];
         ln.view = v;
         ln.branch = b;
         ln.op_base = op_index(V, b, d, 0);
@@ -253,12 +420,23 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           for (int e = 0; e < 4; ++e) ln.box[q][e] = q < V.n_ml ? V.ml_box[q][e] : 0;
         for (int r = 0; r < OADG_MAX_REGIONS; ++r) ln.kind[r] = ln.lut[r] = ln.scratch[r] = -1;
         final_frame[(size_t)v * OADG_MAX_WIDTH + b] = ln.out;
+        const int ready = step_phase[(size_t)v * OADG_MAX_WIDTH + b] + 1;  // phase in which ln.in is complete
+        int step_at = ready;
         bool hist = false;
         for (int r = 0; r <= V.n_ml; ++r) hist |= needs_hist(ops[ln.op_base + r].kind);
-        if (hist) {
-          ln.hist_slot = hist_n++;
-          lane_ids[histid_n++] = lane_n;
-          ++D.n_hist;
+        int hist_done = 0;
+        if (hist) {  // lanes of one view share the histogram of the source frame at depth 0
+          int found = -1;
+          for (size_t k = 0; k < hist_keys.size(); ++k)
+            if (hist_keys[k].in == ln.in) found = (int)k;
+          if (found < 0) {
+            hist_keys.push_back(HistKey{ln.in, hist_n++, ready + 1});
+            found = (int)hist_keys.size() - 1;
+            ln.hist_slot = hist_keys[found].slot;
+            add(OADG_IT_HIST, lane_id, ready, V.W * V.H, 1);
+          }
+          ln.hist_slot = hist_keys[found].slot;
+          hist_done = hist_keys[found].done;
         }
         for (int r = 0; r <= V.n_ml; ++r) {
           oadg_op_t& op = ops[ln.op_base + r];
@@ -267,33 +445,41 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           if (is_lut_kind(op.kind)) {
             op.lut = lut_n;
             lutjobs[lut_n] = LutJob{ln.op_base + r, ln.hist_slot, v, 0};
+            const int at = needs_hist(op.kind) ? hist_done : 0;
+            add(OADG_IT_LUT, lut_n, at, 1, 1);
+            step_at = at + 1 > step_at ? at + 1 : step_at;
             ++lut_n;
-            ++D.n_lut;
           } else if (op.kind == OADG_OP_BBO_AFFINE && op.bbo_count > 0) {
-            Chain& c = chains[chain_n++];
-            c.view = v;
-            c.n = op.bbo_count;
-            c.bbo_first = op.bbo_first;
-            c.lane = lane_n;  // lane whose input seeds S
-            op.scratch = scratch_used + (op.bbo_count & 1);  // result frame: T after an odd number of boxes
-            c.S = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)scratch_used * L.frame_bytes);
-            c.T = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(scratch_used + 1) * L.frame_bytes);
-            scratch_used += 2;
-            ++D.n_chain;
-            D.max_chain = c.n > D.max_chain ? c.n : D.max_chain;
-            for (int j = 0; j < c.n; ++j) {  // pass j covers the bounding rect of supports j and j-1
-              const int32_t* a = pv.gts[pv.bbo[c.bbo_first + j].gt].supp;
-              int x0 = a[0], y0 = a[1], x1 = a[2], y1 = a[3];
-              if (j > 0) {
-                const int32_t* q = pv.gts[pv.bbo[c.bbo_first + j - 1].gt].supp;
-                if (q[2] > q[0] && q[3] > q[1]) {
-                  if (x1 <= x0 || y1 <= y0) { x0 = q[0]; y0 = q[1]; x1 = q[2]; y1 = q[3]; }
-                  else { x0 = x0 < q[0] ? x0 : q[0]; y0 = y0 < q[1] ? y0 : q[1]; x1 = x1 > q[2] ? x1 : q[2]; y1 = y1 > q[3] ? y1 : q[3]; }
-                }
+            IRect keep{0, 0, V.W, V.H};
+            if (r < V.n_ml) keep = IRect{V.ml_box[r][0], V.ml_box[r][1], V.ml_box[r][2], V.ml_box[r][3]};
+            schedule_chain(pv, V, op, &keep, cs);
+            if (!cs.box.empty()) {
+              const int c_id = chain_n++;
+              Chain& c = chains[c_id];
+              c.view = v;
+              c.lane = lane_id;
+              c.in = ln.in;
+              c.S = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(2 * c_id) * L.frame_bytes);
+              c.T = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(2 * c_id + 1) * L.frame_bytes);
+              op.scratch = 2 * c_id;  // the step reads the chain's S frame
+              add(OADG_IT_COPY, c_id, ready, V.W * V.H * 3, 1);
+              const int r0 = (ready + 1 > prof_done ? ready + 1 : prof_done);
+              for (size_t k = 0; k < cs.box.size(); ++k) {
+                BboJob& J = bjobs[bjob_n];
+                J.chain = c_id;
+                J.bbo = op.bbo_first + cs.box[k];
+                const int32_t* s = pv.gts[pv.bbo[J.bbo].gt].supp;
+                for (int e = 0; e < 4; ++e) J.rect[e] = s[e];
+                const int at = r0 + 2 * (cs.level[k] - 1);
+                add(OADG_IT_BBO_R, bjob_n, at, s[2] - s[0], s[3] - s[1]);
+                add(OADG_IT_BBO_W, bjob_n, at + 1, s[2] - s[0], s[3] - s[1]);
+                ++bjob_n;
               }
-              D.max_roi_w = (x1 - x0) > D.max_roi_w ? (x1 - x0) : D.max_roi_w;
-              D.max_roi_h = (y1 - y0) > D.max_roi_h ? (y1 - y0) : D.max_roi_h;
+              const int done = r0 + 2 * cs.n_levels;
+              step_at = done > step_at ? done : step_at;
             }
+          } else if (op.kind == OADG_OP_BG_AFFINE) {
+            step_at = mask_done > step_at ? mask_done : step_at;
           }
         }
         for (int r = 0; r <= V.n_ml; ++r) {
@@ -302,12 +488,113 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           ln.scratch[r] = ops[ln.op_base + r].scratch;
           if (!(is_lut_kind(ln.kind[r]) || ln.kind[r] == OADG_OP_BBO_AFFINE)) ln.all_streaming = 0;
         }
-        if (!ln.all_streaming) px_ids[D.lane0 + D.n_px++] = lane_n - D.lane0;  // index within this depth's lane slice
-        ++lane_n;
-        ++D.n_lanes;
+        add(OADG_IT_STEP, lane_id, step_at, V.W, V.H);
+        step_phase[(size_t)v * OADG_MAX_WIDTH + b] = step_at;
       }
     }
   }
+  if (n_phases > L.max_phases || (int)todo.size() > L.max_items) return OADG_E_LIMIT;
+
+  // ---- phase tables: items grouped by phase, tiles numbered within the phase, cost-balanced CTA ranges -----
+  std::vector<int> order(todo.size());
+  {
+    std::vector<int> count(n_phases + 1, 0);
+    for (const Todo& t : todo) ++count[t.phase + 1];
+    for (int p = 0; p < n_phases; ++p) count[p + 1] += count[p];
+    std::vector<int> fill(count.begin(), count.end() - 1);
+    for (size_t i = 0; i < todo.size(); ++i) order[fill[todo[i].phase]++] = (int)i;
+    for (int p = 0; p < n_phases; ++p) {
+      phases[p].item0 = count[p];
+      phases[p].n_items = count[p + 1] - count[p];
+      phases[p].n_tiles = 0;
+      phases[p].pad = 0;
+    }
+  }
+  std::vector<int> step_costs;
+  for (int p = 0; p < n_phases; ++p) {
+    Phase& ph = phases[p];
+    int tile0 = 0;
+    long long total = 0;
+    for (int k = 0; k < ph.n_items; ++k) {
+      const Todo& t = todo[order[ph.item0 + k]];
+      Item& it = items[ph.item0 + k];
+      it.kind = t.kind;
+      it.obj = t.obj;
+      it.tile0 = tile0;
+      it.pad[0] = it.pad[1] = it.pad[2] = 0;
+      int tw = 1, th = 1;
+      switch (t.kind) {
+        case OADG_IT_MASK: tw = kMaskTileW; th = kMaskTileH; break;
+        case OADG_IT_HIST: tw = kHistTilePx; break;
+        case OADG_IT_COPY: tw = kCopyTileBytes; break;
+        case OADG_IT_BBO_R:
+        case OADG_IT_BBO_W: tw = kBboTileW; th = kBboTileH; break;
+        case OADG_IT_STEP: tw = kStepTileW; th = kStepTileH; break;
+        default: break;
+      }
+      it.tx = (t.w + tw - 1) / tw;
+      it.ntiles = it.tx * ((t.hgt + th - 1) / th);
+      if (it.ntiles < 0) it.ntiles = 0;
+      tile0 += it.ntiles;
+    }
+    ph.n_tiles = tile0;
+    // cost of every tile in phase order -> boundary k = first tile whose cumulative cost reaches k/G of the total
+    int32_t* rg = ranges + (size_t)p * (G + 1);
+    auto step_tile_cost = [&](const Lane& ln, int ti, int tx) {
+      const int x0 = (ti % tx) * kStepTileW, y0 = (ti / tx) * kStepTileH;
+      const int x1 = x0 + kStepTileW < ln.W ? x0 + kStepTileW : ln.W, y1 = y0 + kStepTileH < ln.H ? y0 + kStepTileH : ln.H;
+      int region = ln.n_ml;
+      bool edge = false;
+      for (int bb = 0; bb < ln.n_ml; ++bb) {
+        const int32_t* B = ln.box[bb];
+        if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;
+        if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = bb;
+        else edge = true;
+      }
+      if (edge) return ln.all_streaming ? kStepCostEdge : kStepCostPixel;
+      const int kd = ln.kind[region];
+      return (is_lut_kind(kd) || kd == OADG_OP_BBO_AFFINE) ? kStepCostStream : kStepCostPixel;
+    };
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: total cost; pass 1: boundaries
+      long long cum = 0;
+      int kb = 1;
+      if (pass == 1) {
+        rg[0] = 0;
+        if (total == 0) {
+          for (int k2 = 1; k2 <= G; ++k2) rg[k2] = ph.n_tiles;
+          break;
+        }
+      }
+      for (int k = 0; k < ph.n_items; ++k) {
+        const Item& it = items[ph.item0 + k];
+        if (it.kind == OADG_IT_STEP) {
+          const Lane& ln = lanes[it.obj];
+          for (int ti = 0; ti < it.ntiles; ++ti) {
+            cum += step_tile_cost(ln, ti, it.tx);
+            if (pass == 1)
+              while (kb < G && cum * G >= total * kb) rg[kb++] = it.tile0 + ti + 1;
+          }
+        } else {
+          const long long w = tile_cost(it.kind);
+          if (pass == 1) {
+            while (kb < G && (cum + w * it.ntiles) * G >= total * kb) {
+              // smallest n with (cum + w n) G >= total kb
+              long long need = (total * kb + G - 1) / G - cum;
+              long long n = need <= 0 ? 0 : (need + w - 1) / w;
+              if (n > it.ntiles) n = it.ntiles;
+              rg[kb++] = it.tile0 + (int)n;
+            }
+          }
+          cum += w * it.ntiles;
+        }
+      }
+      if (pass == 0) total = cum;
+      else
+        while (kb <= G) rg[kb++] = ph.n_tiles;
+    }
+    rg[G] = ph.n_tiles;
+  }
+
   for (int v = 0; v < h.n_views; ++v) {
     const oadg_view_t& V = pv.views[v];
     MixJob& J = mixjobs[v];
@@ -317,11 +604,14 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     for (int b = 0; b < V.width; ++b) J.branch[b] = final_frame[(size_t)v * OADG_MAX_WIDTH + b];
   }
 
-  // upload plan + tables in one copy
+  // upload plan + tables in one copy; clear the barrier counter and the histograms in one memset
   rc = be.upload(ws + L.off_plan, stage.data(), stage.size());
   if (rc) return rc;
+  rc = be.zero(ws + L.off_zero, L.zero_bytes);
+  if (rc) return rc;
   const char* dplan = ws + L.off_plan;
-  DevPlan P;
+  ChainArgs A;
+  DevPlan& P = A.P;
   P.views = reinterpret_cast<const oadg_view_t*>(dplan + h.off_views);
   P.gts = reinterpret_cast<const oadg_gt_t*>(dplan + h.off_gt);
   P.ops = reinterpret_cast<const oadg_op_t*>(dplan + h.off_ops);
@@ -335,51 +625,37 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   P.maskf = reinterpret_cast<const float*>(ws + L.off_maskf);
   P.masku = reinterpret_cast<const uint8_t*>(ws + L.off_masku);
   P.mask_stride = (size_t)h.max_h * h.max_w;
-  const Lane* d_lanes = reinterpret_cast<const Lane*>(dplan + t_lanes);
-  const int32_t* d_lane_ids = reinterpret_cast<const int32_t*>(dplan + t_lane_ids);
-  const int32_t* d_px_ids = reinterpret_cast<const int32_t*>(dplan + t_px_ids);
-  const LutJob* d_lut = reinterpret_cast<const LutJob*>(dplan + t_lut);
-  const Chain* d_chain = reinterpret_cast<const Chain*>(dplan + t_chain);
-  const MixJob* d_mix = reinterpret_cast<const MixJob*>(dplan + t_mix);
-  unsigned* d_hist = reinterpret_cast<unsigned*>(ws + L.off_hist);
-  unsigned long long* d_luma = reinterpret_cast<unsigned long long*>(ws + L.off_luma);
-  uint8_t* d_luts = reinterpret_cast<uint8_t*>(ws + L.off_lut);
-  const uint8_t* d_scratch = reinterpret_cast<const uint8_t*>(ws + L.off_scratch);
-
-  if (h.n_gt > 0) {
-    rc = be.profiles(P, pv, const_cast<float*>(P.prof_x), const_cast<float*>(P.prof_y));
-    if (rc) return rc;
-  }
-  if (L.any_bg) {  // union mask of every view, once per batch (views without gt boxes get zeros)
-    rc = be.masks(P, h.n_views, const_cast<float*>(P.maskf), const_cast<uint8_t*>(P.masku));
-    if (rc) return rc;
-  }
-  if (hist_n > 0) {
-    rc = be.zero(d_hist, (size_t)hist_n * 768 * sizeof(unsigned));
-    if (rc) return rc;
-    rc = be.zero(d_luma, (size_t)hist_n * sizeof(unsigned long long));
-    if (rc) return rc;
-  }
-  for (int d = 0; d < L.max_depth; ++d) {
-    const DepthInfo& D = di[d];
-    if (D.n_lanes == 0) continue;
-    if (D.n_hist > 0 && (rc = be.hist(P, d_lanes, d_lane_ids + D.hist0, D.n_hist, d_hist, d_luma))) return rc;
-    if (D.n_lut > 0 && (rc = be.lut(P, d_lut + D.lut0, D.n_lut, d_hist, d_luma, d_luts))) return rc;
-    if (D.n_chain > 0) {
-      for (int c = 0; c < D.n_chain; ++c) {
-        const Chain& C = chains[D.chain0 + c];
-        const oadg_view_t& V = pv.views[C.view];
-        if ((rc = be.copy(C.S, lanes[C.lane].in, (size_t)V.H * V.W * 3))) return rc;
-        if ((rc = be.copy(C.T, lanes[C.lane].in, (size_t)V.H * V.W * 3))) return rc;
-      }
-      if (D.max_roi_w > 0 && D.max_roi_h > 0) {
-        for (int j = 0; j < D.max_chain; ++j)
-          if ((rc = be.bbo_pass(P, d_chain + D.chain0, D.n_chain, j, D.max_roi_w, D.max_roi_h))) return rc;
-      }
-    }
-    if ((rc = be.step(P, d_lanes + D.lane0, D.n_lanes, d_px_ids + D.lane0, D.n_px, d_scratch, L.frame_bytes))) return rc;
-  }
-  return be.mix(P, d_mix, h.n_views);
+  A.lanes = reinterpret_cast<const Lane*>(dplan + t_lanes);
+  A.lutjobs = reinterpret_cast<const LutJob*>(dplan + t_lut);
+  A.chains = reinterpret_cast<const Chain*>(dplan + t_chain);
+  A.bjobs = reinterpret_cast<const BboJob*>(dplan + t_bjob);
+  A.items = reinterpret_cast<const Item*>(dplan + t_items);
+  A.phases = reinterpret_cast<const Phase*>(dplan + t_phases);
+  A.ranges = reinterpret_cast<const int32_t*>(dplan + t_ranges);
+  A.n_phases = n_phases;
+  A.grid = G;
+  A.hist = reinterpret_cast<unsigned*>(ws + L.off_hist);
+  A.luma = reinterpret_cast<unsigned long long*>(ws + L.off_luma);
+  A.luts = reinterpret_cast<uint8_t*>(ws + L.off_lut);
+  A.prof_x = reinterpret_cast<float*>(ws + L.off_prof_x);
+  A.prof_y = reinterpret_cast<float*>(ws + L.off_prof_y);
+  A.maskf = reinterpret_cast<float*>(ws + L.off_maskf);
+  A.masku = reinterpret_cast<uint8_t*>(ws + L.off_masku);
+  A.scratch = reinterpret_cast<const uint8_t*>(ws + L.off_scratch);
+  A.frame_bytes = L.frame_bytes;
+  A.bar = reinterpret_cast<unsigned*>(ws + L.off_zero);
+  A.phase_ts = reinterpret_cast<unsigned long long*>(ws + L.off_ts);
+  // host views of the same tables (the host arithmetic check interprets them directly)
+  ChainArgs Hh = A;
+  Hh.lanes = lanes;
+  Hh.lutjobs = lutjobs;
+  Hh.chains = chains;
+  Hh.bjobs = bjobs;
+  Hh.items = items;
+  Hh.phases = phases;
+  Hh.ranges = ranges;
+  if ((rc = be.chain(A, Hh, pv))) return rc;
+  return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);
 }
 
 }  // namespace oadg

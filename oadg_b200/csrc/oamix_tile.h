@@ -11,7 +11,7 @@
 namespace oadg {
 
 constexpr int kChunkPx = 16;  // 16 px * 3 B = 48 B = 3 x uint4: the smallest pixel run that is 16-byte periodic
-constexpr int kTileW = 256;   // 16 chunks
+constexpr int kTileW = 256;   // mix tiles: 16 chunks
 constexpr int kTileH = 32;    // 16 x 32 chunks: two per thread
 constexpr int kMaxCand = 12;
 
@@ -27,7 +27,7 @@ OADG_HD void chunk_load(const uint8_t* p, int n, bool vec, Chunk& c) {
   (void)n;
   (void)vec;
   const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2);
+  uint4 a = q[0], b = q[1], d = q[2];  // plain loads: see OADG_LDG
   c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
   c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
   c.w[8] = d.x; c.w[9] = d.y; c.w[10] = d.z; c.w[11] = d.w;

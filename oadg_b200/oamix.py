@@ -32,7 +32,7 @@ _AUG = {
 }
 
 
-PROFILE_KINDS = ('profile', 'hist', 'lut', 'bbo_pass', 'mask', 'step', 'mix', 'copy', 'step_pixel')
+ITEM_KINDS = ('profile', 'mask', 'hist', 'lut', 'copy', 'bbo_read', 'bbo_write', 'step')   # chain-kernel work item kinds
 
 
 def get_aug_list(version):
@@ -440,14 +440,23 @@ class OAMix:
         base = (ws.data_ptr() + 255) // 256 * 256
         room = ws.numel() - (base - ws.data_ptr())
         if profile is not None:
-            ms = (ctypes.c_float * len(PROFILE_KINDS))()
-            cnt = (ctypes.c_int * len(PROFILE_KINDS))()
+            cap = 512
+            ms_chain, ms_mix, n_ph = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
+            ph_ms = (ctypes.c_float * cap)()
+            ph_kinds = (ctypes.c_int32 * cap)()
             _lib.check(lib.oadg_oamix_execute_profiled(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
-                                                       ms, cnt, s.cuda_stream))
-            for i, k in enumerate(PROFILE_KINDS):
-                profile[k + '_ms'] = profile.get(k + '_ms', 0.0) + float(ms[i])
-                profile[k + '_n'] = profile.get(k + '_n', 0) + int(cnt[i])
-            self.last_launches += sum(cnt)
+                                                       ctypes.byref(ms_chain), ctypes.byref(ms_mix), ctypes.byref(n_ph),
+                                                       ph_ms, ph_kinds, cap, s.cuda_stream))
+            profile['chain_ms'] = profile.get('chain_ms', 0.0) + float(ms_chain.value)
+            profile['mix_ms'] = profile.get('mix_ms', 0.0) + float(ms_mix.value)
+            profile['chain_n'] = profile.get('chain_n', 0) + 1
+            profile['mix_n'] = profile.get('mix_n', 0) + 1
+            profile['phases'] = profile.get('phases', 0) + int(n_ph.value)
+            by = profile.setdefault('phase_ms_by_kinds', {})
+            for p in range(min(int(n_ph.value), cap)):   # a phase is charged to the set of item kinds it holds
+                key = '+'.join(k for i, k in enumerate(ITEM_KINDS) if ph_kinds[p] >> i & 1)
+                by[key] = by.get(key, 0.0) + float(ph_ms[p])
+            self.last_launches += 2
             return outs
         n = ctypes.c_int(0)
         _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,

@@ -83,3 +83,40 @@ def test_two_views_one_batch(hostsim):
     for o, (ref, _) in zip(outs, refs):
         d = np.abs(o.astype(int) - ref.astype(int))
         assert d.max() <= 1 and (d != 0).mean() <= 1e-3
+
+
+def run_ex(hs, t, jobs, imgs, n_cta):
+    blob = t._pack(jobs)
+    outs = [np.zeros_like(imgs[j[2]]) for j in jobs]
+    src = (ctypes.c_void_p * len(imgs))(*[i.ctypes.data for i in imgs])
+    dst = (ctypes.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+    stats = (ctypes.c_int * 3)()
+    rc = hs.hostsim_oamix_execute_ex(ctypes.c_void_p(blob.ctypes.data), ctypes.c_size_t(blob.nbytes), src, len(imgs),
+                                     dst, n_cta, stats)
+    assert rc == 0, rc
+    return outs, list(stats)
+
+
+@pytest.mark.parametrize('seed', [11, 12, 13, 14])
+def test_chain_scheduler_medium_frames(hostsim, seed):
+    """8 gt boxes on a 320x576 frame: bboxes-only chains with several dependency levels, dead boxes pruned, phases
+    split over 1 / 7 / 148 pretend CTAs -- the output must not depend on the split and must match the oracle."""
+    from oadg_b200.oamix import OAMix
+    cfg = sampler_cfg(dict(OAMIX_CFG, version='augmix'))
+    img, gt = synth.make_image(seed, 320, 576, 8)
+    np.random.seed(seed)
+    ref, plan = oamix_np.oamix_view(img, gt, **cfg)
+    np.random.seed(seed)
+    t = OAMix(**cfg)
+    vp = t._sample_head(320, 576, gt)
+    t._sample_tail(vp, gt, plan['scores'])
+    outs = []
+    for n_cta in (1, 7, 148):
+        (o,), stats = run_ex(hostsim, t, [(vp, gt, 0)], [img], n_cta)
+        outs.append(o)
+        assert stats[0] >= 1 and stats[1] >= 1
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    d = np.abs(outs[0].astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d != 0).mean() <= 1e-3, (int(d.max()), float((d != 0).mean()))
+    n_boxes = sum(len(op[1]) for steps in vp.ops for regs in steps for op in regs if op[0] == 'bbo_affine')
+    assert stats[2] <= n_boxes      # dead-box elimination never adds work
