@@ -38,6 +38,8 @@ extern "C" {
 #define OADG_E_ARG      (-1)   /* null pointer / bad size                         */
 #define OADG_E_PLAN     (-2)   /* malformed plan blob                             */
 #define OADG_E_LIMIT    (-3)   /* exceeds a compiled limit (OADG_MAX_*)           */
+#define OADG_E_NOBOX    (-5)   /* OA-Mix sampler: no multi-level box could be placed
+                                  (the reference raises ValueError from np.stack([]), oa_mix.py:217) */
 #define OADG_E_ROWS     (-4)   /* OA-Loss: fewer than 2*ori_size rows (the reference
                                   raises RuntimeError at contrastive_loss.py:205) */
 
@@ -132,6 +134,37 @@ const char* oadg_error_string(int code);
 
 /* ---- OA-Mix ----------------------------------------------------------------- */
 
+/* ---- host-side plan sampler (no CUDA) ------------------------------------------------------------------
+ * Draws everything random about n_img OAMix.oamix calls (oa_mix.py:207-262,281-298: Dirichlet weights,
+ * multi-level boxes, depths, ops and their parameters, object-aware boxes, Beta / uniform mixing coefficients)
+ * from the caller's random stream in the reference's draw order and packs the plan blob.  `rng` carries the
+ * generator: for the reference it is the MT19937 bit generator behind numpy's global np.random (its
+ * next_uint32 / next_double entry points), so np.random.seed(s) reproduces the reference's plan draw for draw.
+ * scores[i]: the saliency score of every gt box of image i (oadg_saliency_scores; -1 for boxes narrower than 4).
+ * Outputs besides the blob: the multi-level boxes ([n_img][2][4] int64, n_ml_out[i] valid) and object-aware
+ * random boxes ([n_img][5][4] int64, n_oa_out[i] valid) the transform returns in its result dict, and
+ * S(P) = sum of branch depths per image.  Returns OADG_E_NOBOX when an image got no multi-level box.          */
+typedef struct oadg_rng {
+  void*    state;
+  uint32_t (*next_uint32)(void* state);
+  double   (*next_double)(void* state);
+} oadg_rng_t;
+
+typedef struct oadg_sampler_cfg {   /* OAMix.__init__ keys (oa_mix.py:34-72) */
+  int32_t version;                  /* 0 = 'augmix', 1 = 'augmix.all' (oa_mix.py:15-29) */
+  int32_t severity, mixture_width, mixture_depth, spatial_ratio, score_thresh;
+  double  random_box_scale[2], random_box_ratio[2], oa_random_box_scale[2], oa_random_box_ratio[2];
+  double  sigma_ratio;
+} oadg_sampler_cfg_t;
+
+int oadg_oamix_sample_plan(const oadg_rng_t* rng, const oadg_sampler_cfg_t* cfg, int n_img,
+                           const int32_t* hw /* [n_img][2] = H, W */,
+                           const float* const* gt /* n_img x [n_gt][4] f32 */, const int32_t* n_gt,
+                           const double* const* scores,
+                           void* plan_out, size_t plan_cap, size_t* plan_bytes,
+                           int64_t* ml_boxes_out, int32_t* n_ml_out,
+                           int64_t* oa_boxes_out, int32_t* n_oa_out, int32_t* depth_sum_out);
+
 /* Spectral-residual saliency score of every gt box.
  * Replaces oa_mix.py:107-110 (cv2.saliency.StaticSaliencySpectralResidual +
  * np.mean(uint8(map*255))).  boxes_dev: n x 5 int32 {img, x1, y1, x2, y2} with the
@@ -164,7 +197,7 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
 /* Same as oadg_oamix_execute, with CUDA events on `stream` around the two launches (the chain kernel and the mix
  * kernel); the call synchronises the stream before returning (measurement only).  The chain kernel stamps
  * %globaltimer at every phase boundary: phase_ms[p] / phase_kinds[p] (bit k = the phase holds work items of kind k,
- * k = 0 profile, 1 mask, 2 hist, 3 lut, 4 frame copy, 5 bbo read half, 6 bbo write half, 7 depth step) receive up
+ * k = 0 profile, 1 mask, 2 hist, 3 lut, 4 frame copy, 5 bbo blend, 6 bbo catch-up, 7 depth step) receive up
  * to phase_cap entries. */
 int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
                                 const uint8_t* const* src_dev, int n_img,

@@ -12,10 +12,10 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libOADG.so')
 STAMP = os.path.join(HERE, '.libOADG.stamp')
-SOURCES = ['api.cu', 'saliency.cu', 'oamix.cu', 'oaloss.cu', 'oaloss_tc.cu']
+SOURCES = ['api.cu', 'saliency.cu', 'oamix.cu', 'oamix_sampler.cpp', 'oaloss.cu', 'oaloss_tc.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-         '-Xcompiler', '-fPIC', '-shared', '-fmad=false', '-Xptxas', '-v',
+         '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-shared', '-fmad=false', '-Xptxas', '-v',
          '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 # -fmad=false: the OA-Mix float stages must not contract a*b+c (oamix_math.h); kernels that
 # want FMA (the loss GEMMs) call fmaf() explicitly.

@@ -33,7 +33,17 @@ struct RegOp {      // op parameters of one region, staged in shared memory for 
   double minv[6];
 };
 
+struct BboStage {    // one bbo job staged for the CTA (bbo_r_segment / bbo_c_segment)
+  double minv[6];
+  int32_t rect[4];
+  int32_t W, H, gt, n_excl;
+  const uint8_t* X;
+  uint8_t* Y;
+  int32_t excl[16][4];   // supports of the next level's boxes (catch-up exclusion)
+};
+
 struct ChainSmem {
+  BboStage bs;
   union {
     unsigned hist[8][768];   // histogram tiles: 8 privatised copies (4 warps share one)
     float prof[6144];        // profile tiles: low-res blurred profile, then the gaussian kernel
@@ -246,30 +256,163 @@ __device__ void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
   }
 }
 
-// S = copy of the lane input, 64 KB per tile
-__device__ void copy_tile(const Chain& C, size_t nbytes, int local) {
-  const size_t b0 = (size_t)local * kCopyTileBytes;
-  const size_t b1 = b0 + kCopyTileBytes < nbytes ? b0 + kCopyTileBytes : nbytes;
+// T (and S when the chain has a second level) = copy of the lane input; tiles [l0, l1) of 64 KB
+__device__ void copy_segment(const Chain& C, size_t nbytes, bool both, int l0, int l1) {
+  const size_t b0 = (size_t)l0 * kCopyTileBytes;
+  const size_t b1 = (size_t)l1 * kCopyTileBytes < nbytes ? (size_t)l1 * kCopyTileBytes : nbytes;
   const int tid = threadIdx.x;
-  if (((((uintptr_t)C.in) | ((uintptr_t)C.S)) & 15) == 0) {
+  if (((((uintptr_t)C.in) | ((uintptr_t)C.S) | ((uintptr_t)C.T)) & 15) == 0) {
     const uint4* s = reinterpret_cast<const uint4*>(C.in);
-    uint4* d = reinterpret_cast<uint4*>(C.S);
+    uint4* d = reinterpret_cast<uint4*>(C.T);
+    uint4* d2 = reinterpret_cast<uint4*>(C.S);
     const size_t v1 = b1 / 16;
-    for (size_t i = b0 / 16 + tid; i < v1; i += kCT) d[i] = s[i];
-    for (size_t i = v1 * 16 + tid; i < b1; i += kCT) C.S[i] = C.in[i];
+#pragma unroll 4
+    for (size_t i = b0 / 16 + tid; i < v1; i += kCT) {
+      const uint4 v = s[i];
+      d[i] = v;
+      if (both) d2[i] = v;
+    }
+    for (size_t i = v1 * 16 + tid; i < b1; i += kCT) {
+      C.T[i] = C.in[i];
+      if (both) C.S[i] = C.in[i];
+    }
   } else {
-    for (size_t i = b0 + tid; i < b1; i += kCT) C.S[i] = C.in[i];
+    for (size_t i = b0 + tid; i < b1; i += kCT) {
+      C.T[i] = C.in[i];
+      if (both) C.S[i] = C.in[i];
+    }
   }
 }
 
-// one bbo box, read half (T = blend) or write half (S = T), tile = 64 x 16 px of the box support
-__device__ void bbo_tile(const ChainArgs& A, const BboJob& J, int local, int tx, bool write_half) {
-  const int x = J.rect[0] + (local % tx) * kBboTileW + (threadIdx.x & 63);
-  const int y = J.rect[1] + (local / tx) * kBboTileH + (threadIdx.x >> 6);
-  if (x >= J.rect[2] || y >= J.rect[3]) return;
-  const Chain& C = A.chains[J.chain];
-  if (write_half) bbo_w_pixel(A.P, C, x, y);
-  else bbo_r_pixel(A.P, C, A.P.bbo[J.bbo], x, y);
+// ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
+// A CTA stages the job once (inverse affine, support, the support's slices of the two mask profiles) and then walks
+// its tiles of 64 x 16 px, one pixel per thread, two tiles in flight.
+struct BboPx {
+  int v[3];      // the running image at the pixel
+  int tap[12];   // 4 taps x 3 channels of the warped image
+  float m;
+  int fx, fy;
+  size_t o;
+  bool on;
+};
+__device__ __forceinline__ void bbo_px_load(const ChainArgs& A, const BboStage& bs, const float* prof, bool prof_smem,
+                                            int x, int y, BboPx& q) {
+  q.on = x < bs.rect[2] && y < bs.rect[3];
+  q.m = 0.f;
+  if (!q.on) return;
+  const int W = bs.W, H = bs.H;
+  const uint8_t* X = bs.X;
+  q.o = ((size_t)y * W + x) * 3;
+  const int w = bs.rect[2] - bs.rect[0];
+  const float ux = prof_smem ? prof[x - bs.rect[0]] : A.prof_x[(size_t)bs.gt * A.P.max_w + x];
+  const float uy = prof_smem ? prof[w + y - bs.rect[1]] : A.prof_y[(size_t)bs.gt * A.P.max_h + y];
+  q.m = fmul(uy, ux);
+  q.v[0] = X[q.o];
+  q.v[1] = X[q.o + 1];
+  q.v[2] = X[q.o + 2];
+  if (q.m == 0.f) return;  // m == 0 => img*1 + aug*0 == img exactly
+  // cv::warpAffine fixed point (oamix_math.h warp_row / warp_px)
+  const int Xf = (cv_round(dmul(dadd(dmul(bs.minv[1], (double)y), bs.minv[2]), 1024.0)) + 16 +
+                  cv_round(dmul(dmul(bs.minv[0], (double)x), 1024.0))) >> 5;
+  const int Yf = (cv_round(dmul(dadd(dmul(bs.minv[4], (double)y), bs.minv[5]), 1024.0)) + 16 +
+                  cv_round(dmul(dmul(bs.minv[3], (double)x), 1024.0))) >> 5;
+  const int sx = imin(imax(Xf >> 5, -32768), 32767), sy = imin(imax(Yf >> 5, -32768), 32767);
+  q.fx = Xf & 31;
+  q.fy = Yf & 31;
+  const bool x0 = (unsigned)sx < (unsigned)W, x1 = q.fx != 0 && (unsigned)(sx + 1) < (unsigned)W;
+  const bool y0 = (unsigned)sy < (unsigned)H, y1 = q.fy != 0 && (unsigned)(sy + 1) < (unsigned)H;
+  const uint8_t* r0 = X + ((size_t)sy * W + sx) * 3;
+  const uint8_t* r1 = r0 + (size_t)W * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    q.tap[c] = (y0 && x0) ? r0[c] : 0;
+    q.tap[3 + c] = (y0 && x1) ? r0[3 + c] : 0;
+    q.tap[6 + c] = (y1 && x0) ? r1[c] : 0;
+    q.tap[9 + c] = (y1 && x1) ? r1[3 + c] : 0;
+  }
+}
+__device__ __forceinline__ void bbo_px_store(const BboStage& bs, const BboPx& q) {
+  if (!q.on) return;
+  int v[3] = {q.v[0], q.v[1], q.v[2]};
+  if (q.m != 0.f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      v[c] = bbo_blend(q.m, v[c], bilerp_fix(q.tap[c], q.tap[3 + c], q.tap[6 + c], q.tap[9 + c], q.fx, q.fy));
+  }
+  uint8_t* Y = bs.Y + q.o;
+  Y[0] = (uint8_t)v[0];
+  Y[1] = (uint8_t)v[1];
+  Y[2] = (uint8_t)v[2];
+}
+__device__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const BboJob J = A.bjobs[I.obj];
+    const Chain C = A.chains[J.chain];
+    const oadg_view_t& V = A.P.views[C.view];
+    BboStage& bs = S.bs;
+    const oadg_bbo_t& B = A.P.bbo[J.bbo];
+    for (int i = 0; i < 6; ++i) bs.minv[i] = B.minv[i];
+    for (int i = 0; i < 4; ++i) bs.rect[i] = J.rect[i];
+    bs.W = V.W;
+    bs.H = V.H;
+    bs.gt = B.gt;
+    const int level = catch_up ? J.level + 1 : J.level;   // a catch-up runs in the NEXT level's phase
+    bs.X = chain_src(C, level);
+    bs.Y = chain_dst(C, level);
+    bs.n_excl = catch_up ? J.next_count : 0;
+    for (int k = 0; k < bs.n_excl && k < 16; ++k)
+      for (int e = 0; e < 4; ++e) bs.excl[k][e] = A.bjobs[J.next_first + k].rect[e];
+  }
+  __syncthreads();
+}
+__device__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
+  bbo_stage(A, S, I, false);
+  const BboStage& bs = S.bs;
+  const int t = threadIdx.x;
+  const int w = bs.rect[2] - bs.rect[0], h = bs.rect[3] - bs.rect[1];
+  const bool prof_smem = w + h <= 6144;
+  if (prof_smem) {
+    for (int i = t; i < w; i += kCT) S.u.prof[i] = A.prof_x[(size_t)bs.gt * A.P.max_w + bs.rect[0] + i];
+    for (int i = t; i < h; i += kCT) S.u.prof[w + i] = A.prof_y[(size_t)bs.gt * A.P.max_h + bs.rect[1] + i];
+    __syncthreads();
+  }
+  const int lx = t & 63, ly = t >> 6, tx = I.tx;
+  for (int k = l0; k < l1; k += 2) {
+    BboPx q0, q1;
+    bbo_px_load(A, bs, S.u.prof, prof_smem, bs.rect[0] + (k % tx) * kBboTileW + lx, bs.rect[1] + (k / tx) * kBboTileH + ly, q0);
+    q1.on = false;
+    if (k + 1 < l1)
+      bbo_px_load(A, bs, S.u.prof, prof_smem, bs.rect[0] + ((k + 1) % tx) * kBboTileW + lx,
+                  bs.rect[1] + ((k + 1) / tx) * kBboTileH + ly, q1);
+    bbo_px_store(bs, q0);
+    bbo_px_store(bs, q1);
+  }
+}
+__device__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
+  bbo_stage(A, S, I, true);
+  const BboStage& bs = S.bs;
+  const int t = threadIdx.x;
+  const int lx = t & 63, ly = t >> 6, tx = I.tx;
+  const BboJob* jobs = A.bjobs;
+  const BboJob& J = A.bjobs[I.obj];
+  for (int k = l0; k < l1; ++k) {
+    const int x = bs.rect[0] + (k % tx) * kBboTileW + lx, y = bs.rect[1] + (k / tx) * kBboTileH + ly;
+    if (x >= bs.rect[2] || y >= bs.rect[3]) continue;
+    if (bs.n_excl <= 16) {
+      bool hit = false;
+      for (int e = 0; e < bs.n_excl; ++e)
+        hit |= x >= bs.excl[e][0] && x < bs.excl[e][2] && y >= bs.excl[e][1] && y < bs.excl[e][3];
+      if (hit) continue;
+      const size_t o = ((size_t)y * bs.W + x) * 3;
+      const int v0 = bs.X[o], v1 = bs.X[o + 1], v2 = bs.X[o + 2];
+      bs.Y[o] = (uint8_t)v0;
+      bs.Y[o + 1] = (uint8_t)v1;
+      bs.Y[o + 2] = (uint8_t)v2;
+    } else {
+      bbo_c_pixel(jobs, J, bs.W, bs.X, bs.Y, x, y);
+    }
+  }
 }
 
 // one pixel of a bg-only op with hoisted coordinate terms (same arithmetic as bg_pixel / eval_op)
@@ -406,52 +549,47 @@ oamix_chain_kernel(const ChainArgs A, const double* div255) {
     const int t0 = A.ranges[(size_t)p * (G + 1) + b], t1 = A.ranges[(size_t)p * (G + 1) + b + 1];
     int it = ph.item0;
     const int it_end = ph.item0 + ph.n_items;
-    int hist_lane = -1, hist_slot = -1;
-    unsigned long long lsum = 0;
-    for (int tile = t0; tile < t1; ++tile) {
+    int tile = t0;
+    while (tile < t1) {  // one segment = this CTA's tiles [l0, l1) of one item
       while (it + 1 < it_end && tile >= A.items[it].tile0 + A.items[it].ntiles) ++it;
       const Item I = A.items[it];
-      const int local = tile - I.tile0;
-      if (hist_lane >= 0 && (I.kind != OADG_IT_HIST || I.obj != hist_lane)) {
-        hist_flush(A, S, hist_slot, lsum);
-        hist_lane = -1;
-      }
+      const int seg_end = min(t1, I.tile0 + I.ntiles);
+      const int l0 = tile - I.tile0, l1 = seg_end - I.tile0;
+      tile = seg_end;
       switch (I.kind) {
         case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;
-        case OADG_IT_MASK: mask_tile(A, I.obj, local, I.tx); break;
+        case OADG_IT_MASK:
+          for (int k = l0; k < l1; ++k) mask_tile(A, I.obj, k, I.tx);
+          break;
         case OADG_IT_HIST: {
           const Lane& L = A.lanes[I.obj];
-          if (hist_lane != I.obj) {
-            hist_begin(S);
-            hist_lane = I.obj;
-            hist_slot = L.hist_slot;
-          }
-          hist_tile(L, S, local, lsum);
+          unsigned long long lsum = 0;
+          hist_begin(S);
+          for (int k = l0; k < l1; ++k) hist_tile(L, S, k, lsum);
+          hist_flush(A, S, L.hist_slot, lsum);
           break;
         }
         case OADG_IT_LUT: lut_tile(A, S, I.obj); break;
         case OADG_IT_COPY: {
           const Chain& C = A.chains[I.obj];
           const oadg_view_t& V = A.P.views[C.view];
-          copy_tile(C, (size_t)V.H * V.W * 3, local);
+          copy_segment(C, (size_t)V.H * V.W * 3, I.aux != 0, l0, l1);
           break;
         }
-        case OADG_IT_BBO_R: bbo_tile(A, A.bjobs[I.obj], local, I.tx, false); break;
-        case OADG_IT_BBO_W: bbo_tile(A, A.bjobs[I.obj], local, I.tx, true); break;
+        case OADG_IT_BBO_R: bbo_r_segment(A, S, I, l0, l1); break;
+        case OADG_IT_BBO_C: bbo_c_segment(A, S, I, l0, l1); break;
         case OADG_IT_STEP:
           if (staged_lane != I.obj) {
             stage_lane(A, S, I.obj);
             staged_lane = I.obj;
           }
-          step_tile(A, S, local, I.tx, div255);
+          for (int k = l0; k < l1; ++k) step_tile(A, S, k, I.tx, div255);
           break;
         default: break;
       }
     }
-    if (hist_lane >= 0) hist_flush(A, S, hist_slot, lsum);
     if (p + 1 < A.n_phases) grid_barrier(A.bar, (unsigned)(p + 1) * (unsigned)G);
     if (b == 0 && threadIdx.x == 0) A.phase_ts[p + 1] = globaltimer_ns();
-    if (p == 0 && b == 0 && threadIdx.x == 0) A.phase_ts[0] = 0;
   }
 }
 

@@ -44,15 +44,20 @@ struct Lane {            // one (view, branch) chain alive at the current depth
 
 struct Chain {           // one bboxes-only op being evaluated (bbox_augmentation.py:74-88)
   int32_t view, lane;
-  const uint8_t* in;     // the lane input the chain starts from
-  uint8_t* S;            // running image: full copy of `in`, updated box by box inside the box supports
-  uint8_t* T;            // staging frame: a level's blended supports land here, then are copied back into S
+  const uint8_t* in;     // the lane input the chain starts from (read-only source of level 1)
+  uint8_t* S;            // ping-pong frames of the running image: level l reads X_l and writes Y_l with
+  uint8_t* T;            //   Y_l = (l odd ? T : S),  X_l = (l == 1 ? in : (l odd ? S : T))
 };
 
-struct BboJob {          // one box of one chain
+struct BboJob {          // one needed box of one chain
   int32_t chain, bbo;    // chain index, index into the oadg_bbo array
+  int32_t level;         // 1-based dependency level (oamix_exec.h schedule_chain)
+  int32_t next_first, next_count;   // the chain's jobs of level + 1 (contiguous in the job table)
+  int32_t pad;
   int32_t rect[4];       // the box's mask support [x0,y0,x1,y1): the only pixels the box can change
 };
+OADG_HD const uint8_t* chain_src(const Chain& C, int level) { return level == 1 ? C.in : ((level & 1) ? C.S : C.T); }
+OADG_HD uint8_t* chain_dst(const Chain& C, int level) { return (level & 1) ? C.T : C.S; }
 
 // ---- work items of the chain kernel ------------------------------------------------------------------------
 // The host turns a plan into PHASES of independent work ITEMS; items are cut into TILES (one CTA iteration each).
@@ -62,9 +67,9 @@ enum {
   OADG_IT_MASK = 1,      // obj = view                   tiles of 256 x 32 px
   OADG_IT_HIST = 2,      // obj = lane                   tiles of kHistTilePx px (linear)
   OADG_IT_LUT = 3,       // obj = lut job                1 tile
-  OADG_IT_COPY = 4,      // obj = chain                  tiles of kCopyTileBytes (linear)
-  OADG_IT_BBO_R = 5,     // obj = bbo job                tiles of 64 x 16 px over the support
-  OADG_IT_BBO_W = 6,     // obj = bbo job                same tiling
+  OADG_IT_COPY = 4,      // obj = chain                  tiles of kCopyTileBytes (linear); aux = 1: S as well as T
+  OADG_IT_BBO_R = 5,     // obj = bbo job                blend of one box, tiles of 64 x 16 px over its support
+  OADG_IT_BBO_C = 6,     // obj = bbo job (level l-1)    catch-up copy X_l -> Y_l of its support minus level l's
   OADG_IT_STEP = 7,      // obj = lane                   tiles of 256 x 64 px
   OADG_IT_KINDS = 8
 };
@@ -72,7 +77,8 @@ struct Item {
   int32_t kind, obj;
   int32_t tile0, ntiles;   // tile0: first tile index within the phase
   int32_t tx;              // tiles per row (2-D kinds)
-  int32_t pad[3];
+  int32_t aux;
+  int32_t pad[2];
 };
 struct Phase {
   int32_t item0, n_items, n_tiles, pad;
@@ -138,14 +144,12 @@ OADG_HD uint8_t lut_simple_at(const oadg_op_t& op, int i, double luma_sum, doubl
 }
 
 // ---- one pixel of one box of a bboxes-only chain (bbox_augmentation.py:57-71) ----------
-// Read half: T = blend(S, warp(S), m) inside the box's support; write half: S = T.  All boxes of a LEVEL
-// (mutually independent boxes, oamix_exec.h) run their read halves in one phase and their write halves in the next,
-// so a warp never sees a half-updated neighbour.
-OADG_HD void bbo_r_pixel(const DevPlan& P, const Chain& C, const oadg_bbo_t& B, int x, int y) {
+// Boxes are grouped into dependency LEVELS (oamix_exec.h): all boxes of level l read the image as it stands after
+// level l-1 (X_l) and write their blended supports into the other frame (Y_l); the supports level l-1 wrote are
+// copied across where level l does not overwrite them (catch-up), so Y_l is the complete image after level l.
+OADG_HD void bbo_r_pixel(const DevPlan& P, const Chain& C, const oadg_bbo_t& B, const uint8_t* X, uint8_t* Y, int x, int y) {
   const oadg_view_t& V = P.views[C.view];
   const size_t o = ((size_t)y * V.W + x) * 3;
-  const uint8_t* X = C.S;
-  uint8_t* Y = C.T;
   const float m = fmul(OADG_LDG(P.prof_y + (size_t)B.gt * P.max_h + y), OADG_LDG(P.prof_x + (size_t)B.gt * P.max_w + x));
   int v[3] = {X[o], X[o + 1], X[o + 2]};
   if (m != 0.f) {  // m == 0 => img*1 + aug*0 == img exactly
@@ -160,11 +164,16 @@ OADG_HD void bbo_r_pixel(const DevPlan& P, const Chain& C, const oadg_bbo_t& B, 
   Y[o + 1] = (uint8_t)v[1];
   Y[o + 2] = (uint8_t)v[2];
 }
-OADG_HD void bbo_w_pixel(const DevPlan& P, const Chain& C, int x, int y) {
-  const size_t o = ((size_t)y * P.views[C.view].W + x) * 3;
-  C.S[o] = C.T[o];
-  C.S[o + 1] = C.T[o + 1];
-  C.S[o + 2] = C.T[o + 2];
+// catch-up of pixel (x, y) of a level l-1 support: copied unless a level-l box (jobs next_first..) rewrites it
+OADG_HD void bbo_c_pixel(const BboJob* jobs, const BboJob& J, int W, const uint8_t* X, uint8_t* Y, int x, int y) {
+  for (int k = 0; k < J.next_count; ++k) {
+    const int32_t* r = jobs[J.next_first + k].rect;
+    if (x >= r[0] && x < r[2] && y >= r[1] && y < r[3]) return;
+  }
+  const size_t o = ((size_t)y * W + x) * 3;
+  Y[o] = X[o];
+  Y[o + 1] = X[o + 1];
+  Y[o + 2] = X[o + 2];
 }
 
 // ---- union mask of one view at one pixel: written once per batch by mask_kernel -------------------

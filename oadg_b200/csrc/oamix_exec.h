@@ -136,7 +136,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.n_hist = n_hist;
   L.n_bbo = h.n_bbo;
   L.max_items = 2 * h.n_gt + h.n_views + 2 * lanes_total + n_lut + n_chains + 2 * h.n_bbo + 8;
-  L.max_phases = 4 + max_depth * (3 + 2 * max_chain);
+  L.max_phases = 4 + max_depth * (3 + max_chain);
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -268,7 +268,7 @@ inline int tile_cost(int kind) {
     case OADG_IT_LUT: return 8;
     case OADG_IT_COPY: return 5;
     case OADG_IT_BBO_R: return 3;
-    case OADG_IT_BBO_W: return 1;
+    case OADG_IT_BBO_C: return 1;
     default: return 4;
   }
 }
@@ -371,21 +371,21 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
 
   // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
   struct Todo {
-    int kind, obj, phase, w, hgt;   // w x hgt: pixel extent (2-D kinds) / w = linear size (1-D kinds)
+    int kind, obj, phase, w, hgt, aux;   // w x hgt: pixel extent (2-D kinds) / w = linear size (1-D kinds)
   };
   std::vector<Todo> todo;
   todo.reserve(L.max_items);
   int n_phases = 0;
-  auto add = [&](int kind, int obj, int phase, int w, int hgt) {
-    todo.push_back(Todo{kind, obj, phase, w, hgt});
+  auto add = [&](int kind, int obj, int phase, int w, int hgt, int aux) {
+    todo.push_back(Todo{kind, obj, phase, w, hgt, aux});
     n_phases = phase + 1 > n_phases ? phase + 1 : n_phases;
   };
   const int prof_done = h.n_gt > 0 ? 1 : 0;
   for (int g = 0; g < h.n_gt; ++g)
-    for (int axis = 0; axis < 2; ++axis) add(OADG_IT_PROFILE, g * 2 + axis, 0, 1, 1);
+    for (int axis = 0; axis < 2; ++axis) add(OADG_IT_PROFILE, g * 2 + axis, 0, 1, 1, 0);
   int mask_done = prof_done;
   if (L.any_bg) {  // union mask of every view (views without gt boxes get zeros)
-    for (int v = 0; v < h.n_views; ++v) add(OADG_IT_MASK, v, prof_done, pv.views[v].W, pv.views[v].H);
+    for (int v = 0; v < h.n_views; ++v) add(OADG_IT_MASK, v, prof_done, pv.views[v].W, pv.views[v].H, 0);
     mask_done = prof_done + 1;
   }
 
@@ -433,7 +433,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
             hist_keys.push_back(HistKey{ln.in, hist_n++, ready + 1});
             found = (int)hist_keys.size() - 1;
             ln.hist_slot = hist_keys[found].slot;
-            add(OADG_IT_HIST, lane_id, ready, V.W * V.H, 1);
+            add(OADG_IT_HIST, lane_id, ready, V.W * V.H, 1, 0);
           }
           ln.hist_slot = hist_keys[found].slot;
           hist_done = hist_keys[found].done;
@@ -446,7 +446,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
             op.lut = lut_n;
             lutjobs[lut_n] = LutJob{ln.op_base + r, ln.hist_slot, v, 0};
             const int at = needs_hist(op.kind) ? hist_done : 0;
-            add(OADG_IT_LUT, lut_n, at, 1, 1);
+            add(OADG_IT_LUT, lut_n, at, 1, 1, 0);
             step_at = at + 1 > step_at ? at + 1 : step_at;
             ++lut_n;
           } else if (op.kind == OADG_OP_BBO_AFFINE && op.bbo_count > 0) {
@@ -461,21 +461,37 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
               c.in = ln.in;
               c.S = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(2 * c_id) * L.frame_bytes);
               c.T = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(2 * c_id + 1) * L.frame_bytes);
-              op.scratch = 2 * c_id;  // the step reads the chain's S frame
-              add(OADG_IT_COPY, c_id, ready, V.W * V.H * 3, 1);
+              const int NL = cs.n_levels;
+              op.scratch = 2 * c_id + (NL & 1);  // the step reads Y of the last level: T when NL is odd, else S
+              // T (and S when a second level exists) start as copies of the lane input
+              add(OADG_IT_COPY, c_id, ready, V.W * V.H * 3, 1, NL >= 2 ? 1 : 0);
               const int r0 = (ready + 1 > prof_done ? ready + 1 : prof_done);
+              // jobs of the chain sorted by level (stable): level l occupies [first[l], first[l+1])
+              std::vector<int> first(NL + 2, 0);
+              for (size_t k = 0; k < cs.box.size(); ++k) ++first[cs.level[k] + 1];
+              for (int l = 1; l <= NL + 1; ++l) first[l] += first[l - 1];
+              std::vector<int> fill(first.begin(), first.end());
+              const int job0 = bjob_n;
               for (size_t k = 0; k < cs.box.size(); ++k) {
-                BboJob& J = bjobs[bjob_n];
+                const int l = cs.level[k];
+                BboJob& J = bjobs[job0 + fill[l]++];
                 J.chain = c_id;
                 J.bbo = op.bbo_first + cs.box[k];
+                J.level = l;
+                J.next_first = job0 + first[l + 1];
+                J.next_count = l < NL ? first[l + 2] - first[l + 1] : 0;
+                J.pad = 0;
                 const int32_t* s = pv.gts[pv.bbo[J.bbo].gt].supp;
                 for (int e = 0; e < 4; ++e) J.rect[e] = s[e];
-                const int at = r0 + 2 * (cs.level[k] - 1);
-                add(OADG_IT_BBO_R, bjob_n, at, s[2] - s[0], s[3] - s[1]);
-                add(OADG_IT_BBO_W, bjob_n, at + 1, s[2] - s[0], s[3] - s[1]);
-                ++bjob_n;
               }
-              const int done = r0 + 2 * cs.n_levels;
+              bjob_n += (int)cs.box.size();
+              for (int k = job0; k < bjob_n; ++k) {
+                const BboJob& J = bjobs[k];
+                const int w = J.rect[2] - J.rect[0], hg = J.rect[3] - J.rect[1];
+                add(OADG_IT_BBO_R, k, r0 + J.level - 1, w, hg, 0);
+                if (J.level < NL) add(OADG_IT_BBO_C, k, r0 + J.level, w, hg, 0);   // caught up by the next level
+              }
+              const int done = r0 + NL;
               step_at = done > step_at ? done : step_at;
             }
           } else if (op.kind == OADG_OP_BG_AFFINE) {
@@ -488,7 +504,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           ln.scratch[r] = ops[ln.op_base + r].scratch;
           if (!(is_lut_kind(ln.kind[r]) || ln.kind[r] == OADG_OP_BBO_AFFINE)) ln.all_streaming = 0;
         }
-        add(OADG_IT_STEP, lane_id, step_at, V.W, V.H);
+        add(OADG_IT_STEP, lane_id, step_at, V.W, V.H, 0);
         step_phase[(size_t)v * OADG_MAX_WIDTH + b] = step_at;
       }
     }
@@ -521,14 +537,15 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       it.kind = t.kind;
       it.obj = t.obj;
       it.tile0 = tile0;
-      it.pad[0] = it.pad[1] = it.pad[2] = 0;
+      it.aux = t.aux;
+      it.pad[0] = it.pad[1] = 0;
       int tw = 1, th = 1;
       switch (t.kind) {
         case OADG_IT_MASK: tw = kMaskTileW; th = kMaskTileH; break;
         case OADG_IT_HIST: tw = kHistTilePx; break;
         case OADG_IT_COPY: tw = kCopyTileBytes; break;
         case OADG_IT_BBO_R:
-        case OADG_IT_BBO_W: tw = kBboTileW; th = kBboTileH; break;
+        case OADG_IT_BBO_C: tw = kBboTileW; th = kBboTileH; break;
         case OADG_IT_STEP: tw = kStepTileW; th = kStepTileH; break;
         default: break;
       }

@@ -32,7 +32,7 @@ _AUG = {
 }
 
 
-ITEM_KINDS = ('profile', 'mask', 'hist', 'lut', 'copy', 'bbo_read', 'bbo_write', 'step')   # chain-kernel work item kinds
+ITEM_KINDS = ('profile', 'mask', 'hist', 'lut', 'copy', 'bbo_blend', 'bbo_catchup', 'step')   # chain-kernel work item kinds
 
 
 def get_aug_list(version):
@@ -90,6 +90,39 @@ def _slice(lo, hi, n):
     return s, max(e, s)
 
 
+class _NativePlan:
+    """What oadg_oamix_sample_plan returns for one batch: the packed blob and the boxes of the result dict."""
+    __slots__ = ('blob', 'ml_boxes', 'oa_boxes', 'depth_sums', 'hw')
+
+
+_RNG = None
+
+
+def _global_rng():
+    """oadg_rng_t over numpy's global legacy RandomState (np.random.seed / np.random.* share its MT19937 state)."""
+    global _RNG
+    import ctypes
+    bg = np.random.mtrand._rand._bit_generator
+    if _RNG is None or _RNG[0] is not bg:
+        i = bg.ctypes
+
+        class _Rng(ctypes.Structure):
+            _fields_ = [('state', ctypes.c_void_p), ('next_uint32', ctypes.c_void_p), ('next_double', ctypes.c_void_p)]
+        r = _Rng(i.state.value if hasattr(i.state, 'value') else int(i.state),
+                 ctypes.cast(i.next_uint32, ctypes.c_void_p).value, ctypes.cast(i.next_double, ctypes.c_void_p).value)
+        _RNG = (bg, r, i)   # keep the interface alive: it owns the function pointers
+    return _RNG[1]
+
+
+class _SamplerCfg(__import__('ctypes').Structure):
+    _c = __import__('ctypes')
+    _fields_ = [('version', _c.c_int32), ('severity', _c.c_int32), ('mixture_width', _c.c_int32),
+                ('mixture_depth', _c.c_int32), ('spatial_ratio', _c.c_int32), ('score_thresh', _c.c_int32),
+                ('random_box_scale', _c.c_double * 2), ('random_box_ratio', _c.c_double * 2),
+                ('oa_random_box_scale', _c.c_double * 2), ('oa_random_box_ratio', _c.c_double * 2),
+                ('sigma_ratio', _c.c_double)]
+
+
 class _ViewPlan:
     __slots__ = ('h', 'w', 'ws', 'ml_boxes', 'depths', 'ops', 'scores', 'oa_low', 'oa_boxes', 'm', 'm_oa')
 
@@ -105,6 +138,7 @@ class OAMix:
                  spatial_ratio=4, sigma_ratio=0.3,
                  **kwargs):
         self.aug_list = get_aug_list(version)
+        self.version = version
         self.num_views = num_views
         self.keep_orig = keep_orig
         if self.num_views == 1 and self.keep_orig:
@@ -128,6 +162,7 @@ class OAMix:
             raise NotImplementedError('libOADG is built for spatial_ratio=4 (all reference configs)')
         self._ws_cache = None
         self._sal_state = None
+        self._native_cfg = None
         self.last_launches = 0
 
     def __repr__(self):
@@ -270,6 +305,54 @@ class OAMix:
         vp.m_oa = [np.float32(0.0 + 0.5 * u01()) if s <= self.score_thresh
                    else np.float32(0.0 + 1.0 * u01()) for s in tgt_scores]
         return vp
+
+    # ------------------------------------------------------------------ native sampler
+    def sample_plan(self, hw_list, gt_list, scores):
+        """Draw + pack the plan of one batch in libOADG (oadg_oamix_sample_plan): consumes np.random draw for draw like
+        _sample_head/_sample_tail below (which remain as the readable statement of the draw order and are checked
+        against it byte for byte in tests/test_host.py)."""
+        import ctypes
+        lib = _lib.load()
+        n = len(hw_list)
+        cfg = self._native_cfg
+        if cfg is None:
+            cfg = self._native_cfg = _SamplerCfg(
+                0 if self.version == 'augmix' else 1, int(self.severity), int(self.mixture_width),
+                int(self.mixture_depth), int(self.spatial_ratio), int(self.score_thresh),
+                (ctypes.c_double * 2)(*map(float, self.random_box_scale)),
+                (ctypes.c_double * 2)(*map(float, self.random_box_ratio)),
+                (ctypes.c_double * 2)(*map(float, self.oa_random_box_scale)),
+                (ctypes.c_double * 2)(*map(float, self.oa_random_box_ratio)), float(self.sigma_ratio))
+        hw = np.asarray(hw_list, dtype=np.int32).reshape(n, 2)
+        gts = [np.ascontiguousarray(g, dtype=np.float32).reshape(-1, 4) for g in gt_list]
+        scs = [np.ascontiguousarray([float(v) for v in s], dtype=np.float64) for s in scores]
+        n_gt = np.asarray([len(g) for g in gts], dtype=np.int32)
+        gt_ptrs = (ctypes.c_void_p * max(n, 1))(*[g.ctypes.data for g in gts])
+        sc_ptrs = (ctypes.c_void_p * max(n, 1))(*[s_.ctypes.data for s_ in scs])
+        n_bbo_max = int(sum(self.mixture_width * max(self.mixture_depth, 3) * 3 * len(g) for g in gts))
+        cap = 4096 + n * (256 + P.OPS_PER_VIEW * P.OP_ST.size) + int(n_gt.sum()) * (P.GT_ST.size + P.TGT_ST.size) \
+            + n * 8 * P.TGT_ST.size + n_bbo_max * P.BBO_ST.size
+        blob = np.empty(cap, np.uint8)
+        nbytes = ctypes.c_size_t(0)
+        ml = np.zeros((n, 2, 4), np.int64)
+        oa = np.zeros((n, 5, 4), np.int64)
+        n_ml = np.zeros(n, np.int32)
+        n_oa = np.zeros(n, np.int32)
+        dsum = np.zeros(n, np.int32)
+        rc = lib.oadg_oamix_sample_plan(ctypes.addressof(_global_rng()), ctypes.addressof(cfg), n, hw.ctypes.data,
+                                        ctypes.addressof(gt_ptrs), n_gt.ctypes.data, ctypes.addressof(sc_ptrs),
+                                        blob.ctypes.data, cap, ctypes.byref(nbytes), ml.ctypes.data, n_ml.ctypes.data,
+                                        oa.ctypes.data, n_oa.ctypes.data, dsum.ctypes.data)
+        if rc == -5:   # OADG_E_NOBOX: np.stack([]) in the reference (oa_mix.py:217)
+            raise ValueError('need at least one array to stack')
+        _lib.check(rc)
+        out = _NativePlan()
+        out.blob = blob[:nbytes.value]
+        out.ml_boxes = [ml[i, :n_ml[i]].copy() for i in range(n)]
+        out.oa_boxes = [oa[i, :n_oa[i]].copy() for i in range(n)]
+        out.depth_sums = dsum
+        out.hw = hw
+        return out
 
     # ------------------------------------------------------------------ records
     def _gt_records(self, gt, h, w):
@@ -422,13 +505,18 @@ class OAMix:
         return self._ws_cache
 
     def execute(self, jobs, imgs, outs=None, stream=None, profile=None):
-        """Run the packed plans.  imgs: list of CUDA u8 HWC tensors; returns one output tensor per job.
+        """Run the packed plans.  jobs: a packed plan blob (uint8 array, one view per image) or a list of
+        (view_plan, gt, img_index); imgs: list of CUDA u8 HWC tensors; returns one output tensor per view.
         ``profile`` (a dict) switches to the event-timed entry point and receives per-kernel ms / counts."""
         import ctypes
         torch = _lib.require_cuda()
         lib = _lib.load()
         dev = imgs[0].device
-        blob = self._pack(jobs)
+        if isinstance(jobs, np.ndarray):
+            blob = jobs
+            jobs = [(None, None, i) for i in range(len(imgs))]
+        else:
+            blob = self._pack(jobs)
         need = ctypes.c_size_t(0)
         _lib.check(lib.oadg_oamix_workspace_bytes(blob.ctypes.data, blob.nbytes, ctypes.byref(need)))
         ws = self._workspace(need.value, dev)
@@ -476,20 +564,15 @@ class OAMix:
                 raise TypeError('images must be contiguous CUDA uint8 HWC tensors')
         gt_list = [np.asarray(g, dtype=np.float32).reshape(-1, 4) for g in gt_list]
         scores = self.saliency_scores(imgs, gt_list, stream, inputs_ready=inputs_ready)
-        jobs = []
-        for i, (img, gt) in enumerate(zip(imgs, gt_list)):
-            vp = self._sample_head(int(img.shape[0]), int(img.shape[1]), gt)
-            self._sample_tail(vp, gt, scores[i])
-            jobs.append((vp, gt, i))
-        outs = self.execute(jobs, imgs, outs=outs, stream=stream, profile=profile)
-        if profile is not None:  # algorithmic bytes of the step kernel: 1 read + 1 write of a frame per lane step
-            for vp, _, _ in jobs:
-                profile['step_bytes'] = profile.get('step_bytes', 0) + 2 * 3 * vp.h * vp.w * sum(vp.depths)
+        plan = self.sample_plan([(int(t.shape[0]), int(t.shape[1])) for t in imgs], gt_list, scores)
+        outs = self.execute(plan.blob, imgs, outs=outs, stream=stream, profile=profile)
+        if profile is not None:  # algorithmic bytes: 1 read + 1 write of a frame per lane step (+ the mix, per view)
+            for (h, w), dsum in zip(plan.hw, plan.depth_sums):
+                profile['step_bytes'] = profile.get('step_bytes', 0) + 2 * 3 * int(h) * int(w) * int(dsum)
                 profile['view_bytes'] = profile.get('view_bytes', 0) + \
-                    3 * vp.h * vp.w * (2 * sum(vp.depths) + len(vp.depths) + 2)
-        oamix_boxes = [np.stack(vp.oa_boxes, axis=0) for vp, _, _ in jobs]
-        ml_boxes = [vp.ml_boxes for vp, _, _ in jobs]
-        return outs, oamix_boxes, ml_boxes
+                    3 * int(h) * int(w) * (2 * int(dsum) + self.mixture_width + 2)
+        oamix_boxes = [np.stack(list(b), axis=0) for b in plan.oa_boxes]   # ValueError when none could be placed
+        return outs, oamix_boxes, plan.ml_boxes
 
     def oamix(self, img, gt_bboxes):
         """One view of one host image (reference oa_mix.py:207-243): H2D, kernels, D2H."""
@@ -497,12 +580,11 @@ class OAMix:
         img = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
         gt = np.asarray(gt_bboxes, dtype=np.float32).reshape(-1, 4)
         dimg = torch.from_numpy(img).cuda(non_blocking=True)
-        vp = self._sample_head(img.shape[0], img.shape[1], gt)
-        self._history['random_box_list'] = vp.ml_boxes
-        scores = self.saliency_scores([dimg], [gt])[0]
-        self._sample_tail(vp, gt, scores)
-        self._history.update(fg_box_list=gt, fg_score_list=scores, oa_random_box_list=vp.oa_boxes)
-        out = self.execute([(vp, gt, 0)], [dimg])[0]
+        scores = self.saliency_scores([dimg], [gt])[0]      # no RNG draw: may precede the plan head
+        plan = self.sample_plan([img.shape[:2]], [gt], [scores])
+        self._history.update(random_box_list=plan.ml_boxes[0], fg_box_list=gt, fg_score_list=scores,
+                             oa_random_box_list=list(plan.oa_boxes[0]))
+        out = self.execute(plan.blob, [dimg])[0]
         return out.cpu().numpy()
 
     def __call__(self, results, *args, **kwargs):

@@ -183,18 +183,22 @@ struct HostBackend {
               const Chain& C = A.chains[I.obj];
               const size_t nbytes = (size_t)P.views[C.view].H * P.views[C.view].W * 3;
               const size_t b0 = (size_t)local * kCopyTileBytes, b1 = b0 + kCopyTileBytes < nbytes ? b0 + kCopyTileBytes : nbytes;
-              memcpy(C.S + b0, C.in + b0, b1 - b0);
+              memcpy(C.T + b0, C.in + b0, b1 - b0);
+              if (I.aux) memcpy(C.S + b0, C.in + b0, b1 - b0);
               break;
             }
             case OADG_IT_BBO_R:
-            case OADG_IT_BBO_W: {
+            case OADG_IT_BBO_C: {
               const BboJob& J = A.bjobs[I.obj];
               const Chain& C = A.chains[J.chain];
+              const int level = I.kind == OADG_IT_BBO_R ? J.level : J.level + 1;
+              const uint8_t* X = chain_src(C, level);
+              uint8_t* Y = chain_dst(C, level);
               const int x0 = J.rect[0] + (local % I.tx) * kBboTileW, y0 = J.rect[1] + (local / I.tx) * kBboTileH;
               for (int y = y0; y < imin(y0 + kBboTileH, J.rect[3]); ++y)
                 for (int x = x0; x < imin(x0 + kBboTileW, J.rect[2]); ++x) {
-                  if (I.kind == OADG_IT_BBO_R) bbo_r_pixel(P, C, P.bbo[J.bbo], x, y);
-                  else bbo_w_pixel(P, C, x, y);
+                  if (I.kind == OADG_IT_BBO_R) bbo_r_pixel(P, C, P.bbo[J.bbo], X, Y, x, y);
+                  else bbo_c_pixel(A.bjobs, J, P.views[C.view].W, X, Y, x, y);
                 }
               if (I.kind == OADG_IT_BBO_R && local == 0) ++n_bbo_jobs;
               break;

@@ -145,6 +145,65 @@ def test_plan_sampler_consumes_rng_like_the_oracle(case):
                     assert a[0] == b['name']
 
 
+@pytest.mark.parametrize('case', [('augmix', 1024, 2048, 8, {}), ('augmix.all', 120, 200, 4, {}),
+                                  ('augmix.all', 99, 131, 6, dict(mixture_width=4, mixture_depth=3)),
+                                  ('augmix', 64, 64, 0, {}), ('augmix', 40, 36, 1, {})])
+def test_native_sampler_matches_python_sampler_byte_for_byte(libpath, case):
+    """libOADG's oadg_oamix_sample_plan (the product path) against the Python statement of the draw order
+    (_sample_head/_sample_tail/_pack, itself pinned to the oracle above): identical plan blob, identical boxes and
+    identical np.random state afterwards, image after image in one batch; same ValueError when no box fits."""
+    from oadg_b200.oamix import OAMix
+    version, h, w, n_gt, extra = case
+    cfg = dict(OAMIX_CFG, version=version, **extra)
+    for seed in range(40):
+        t = OAMix(**cfg)
+        gts = [synth.make_image(s, h, w, n_gt)[1] for s in (seed, seed + 1)]
+        if n_gt >= 2:
+            gts[0][1] = [5.3, 5.9, 7.1, 40.2]       # narrower than spatial_ratio
+        table = [3.5, 20.0, -1, 9.99, 10.0, 11.0, 50.0, 0.0]
+        scores = [[np.float64(table[(k + i) % 8]) for k in range(len(g))] for i, g in enumerate(gts)]
+        np.random.seed(seed)
+        jobs, err_py = [], None
+        try:
+            for i, g in enumerate(gts):
+                vp = t._sample_head(h, w, g)
+                t._sample_tail(vp, g, scores[i])
+                jobs.append((vp, g, i))
+            blob_py = t._pack(jobs)
+        except ValueError as e:
+            err_py = e
+        st_py = np.random.get_state()
+        np.random.seed(seed)
+        plan, err_c = None, None
+        try:
+            plan = t.sample_plan([(h, w)] * 2, gts, scores)
+        except ValueError as e:
+            err_c = e
+        st_c = np.random.get_state()
+        assert (err_py is None) == (err_c is None)
+        assert st_py[2] == st_c[2] and np.array_equal(st_py[1], st_c[1])
+        if plan is None:
+            continue
+        assert np.array_equal(blob_py, plan.blob)
+        for (vp, _, _), ml, oa, ds in zip(jobs, plan.ml_boxes, plan.oa_boxes, plan.depth_sums):
+            assert np.array_equal(vp.ml_boxes, ml) and ml.dtype == np.int64 and oa.dtype == np.int64
+            assert len(vp.oa_boxes) == len(oa) and all(np.array_equal(a, b) for a, b in zip(vp.oa_boxes, oa))
+            assert ds == sum(vp.depths)
+
+
+def test_native_sampler_raises_like_the_reference_when_no_box_fits(libpath):
+    from oadg_b200.oamix import OAMix
+    t = OAMix(version='augmix', random_box_scale=(0.9, 0.99))      # boxes nearly never fit a 8x8 frame
+    hits = 0
+    for seed in range(20):
+        np.random.seed(seed)
+        try:
+            t.sample_plan([(8, 8)], [np.zeros((0, 4), np.float32)], [[]])
+        except ValueError:
+            hits += 1
+    assert hits > 0
+
+
 def test_pair_map_and_row_check():
     from oadg_b200 import reference_pair_map
     from oracle import supcon_np
