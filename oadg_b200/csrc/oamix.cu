@@ -46,7 +46,11 @@ struct ChainSmem {
   BboStage bs;
   union {
     unsigned hist[8][768];   // histogram tiles: 8 privatised copies (4 warps share one)
-    float prof[6144];        // profile tiles: low-res blurred profile, then the gaussian kernel
+    float prof[6144];        // bbo jobs: the support's slices of the two mask profiles
+    struct {
+      double K[3073];        // profile tiles: exclusive prefix sums of the gaussian kernel
+      float p[2048];         //                low-res blurred profile
+    } g;
   } u;
   __align__(16) uint8_t lut[OADG_MAX_REGIONS * 768];
   RegOp rop[OADG_MAX_REGIONS];
@@ -92,8 +96,8 @@ __device__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
   const int lo = G.lo[axis], hi = G.lo[axis + 2];
   const int ks = axis == 0 ? G.kx : G.ky;
   const double sigma = axis == 0 ? G.sigma_x : G.sigma_y;
-  float* p = S.u.prof;
-  float* kern = S.u.prof + n_lo;
+  float* p = S.u.g.p;
+  double* K = S.u.g.K;
   float* out = (axis == 0 ? A.prof_x + (size_t)g * P.max_w : A.prof_y + (size_t)g * P.max_h);
   const int tid = threadIdx.x;
   __syncthreads();  // the shared buffers may still be in use by the previous tile
@@ -102,7 +106,7 @@ __device__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
     return;
   }
   if (G.blur) {
-    // cv::getGaussianKernel(ks, sigma, CV_32F): exp(-x^2/(2 sigma^2)) in double, normalised, cast
+    // cv::getGaussianKernel(ks, sigma, CV_32F): exp(-x^2/(2 sigma^2)) in double, normalised, cast to float32
     const double s2 = -0.5 / (sigma * sigma);
     double part = 0.0;
     for (int i = tid; i < ks; i += kCT) {
@@ -119,26 +123,53 @@ __device__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
     }
     __syncthreads();
     const double ksum = S.ksum;
-    for (int i = tid; i < ks; i += kCT) {
-      double x = i - (ks - 1) * 0.5;
-      kern[i] = (float)(exp(s2 * x * x) * ksum);
+    // K[j] = sum of the float32 taps 0..j-1 in float64 (the blur of an indicator is a difference of prefix sums)
+    for (int i = tid; i <= ks; i += kCT) {
+      double x = (i - 1) - (ks - 1) * 0.5;
+      K[i] = i == 0 ? 0.0 : (double)(float)(exp(s2 * x * x) * ksum);
     }
     __syncthreads();
+    for (int off = 1; off <= ks; off <<= 1) {  // Hillis-Steele inclusive scan over K[0..ks]
+      double v[3];
+      int n = 0;
+      for (int i = tid; i <= ks; i += kCT, ++n) v[n] = i >= off ? K[i] + K[i - off] : K[i];
+      __syncthreads();
+      n = 0;
+      for (int i = tid; i <= ks; i += kCT, ++n) K[i] = v[n];
+      __syncthreads();
+    }
     const int r = ks / 2;
-    const int period = 2 * (n_lo - 1);
-    for (int x = tid; x < n_lo; x += kCT) {
-      double acc = 0.0;
-      for (int j = 0; j < ks; ++j) {
-        int q = x + j - r;
-        if (n_lo == 1) q = 0;
-        else {
-          if (q < 0) q = -q;
-          q %= period;
-          if (q >= n_lo) q = period - q;
-        }
-        if (q >= lo && q < hi) acc += (double)kern[j];
+    auto range = [&](int a, int b) {  // sum of taps j in [a, b) clipped to [0, ks)
+      a = max(a, 0);
+      b = min(b, ks);
+      return b > a ? K[b] - K[a] : 0.0;
+    };
+    if (r <= n_lo - 1) {
+      // BORDER_REFLECT_101 with at most one reflection per side: tap j reads q = x + j - r, -q or 2(n_lo-1) - q
+      for (int x = tid; x < n_lo; x += kCT) {
+        const int s = r - x;  // j = q + s
+        double acc = range(lo + s, hi + s);                                    // q in [lo, hi)
+        acc += range(-hi + 1 + s, min(-lo, -1) + 1 + s);                       // q in [-hi+1, min(-lo,-1)]
+        const int m2 = 2 * (n_lo - 1);
+        acc += range(max(m2 - hi + 1, n_lo) + s, m2 - lo + 1 + s);             // q in [max(m2-hi+1,n_lo), m2-lo]
+        p[x] = (float)acc;
       }
-      p[x] = (float)acc;
+    } else {
+      const int period = 2 * (n_lo - 1);
+      for (int x = tid; x < n_lo; x += kCT) {
+        double acc = 0.0;
+        for (int j = 0; j < ks; ++j) {
+          int q = x + j - r;
+          if (n_lo == 1) q = 0;
+          else {
+            if (q < 0) q = -q;
+            q %= period;
+            if (q >= n_lo) q = period - q;
+          }
+          if (q >= lo && q < hi) acc += K[j + 1] - K[j];
+        }
+        p[x] = (float)acc;
+      }
     }
   } else {
     for (int x = tid; x < n_lo; x += kCT) p[x] = (x >= lo && x < hi) ? 1.f : 0.f;
@@ -546,8 +577,9 @@ oamix_chain_kernel(const ChainArgs A, const double* div255) {
   int staged_lane = -1;
   for (int p = 0; p < A.n_phases; ++p) {
     const Phase ph = A.phases[p];
-    const int t0 = A.ranges[(size_t)p * (G + 1) + b], t1 = A.ranges[(size_t)p * (G + 1) + b + 1];
-    int it = ph.item0;
+    const int32_t* rg = A.ranges + ((size_t)p * (G + 1) + b) * 2;
+    const int t0 = rg[0], t1 = rg[2];
+    int it = rg[1];
     const int it_end = ph.item0 + ph.n_items;
     int tile = t0;
     while (tile < t1) {  // one segment = this CTA's tiles [l0, l1) of one item
@@ -631,7 +663,7 @@ struct CudaBackend {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   int n_phases = 0;
   const unsigned long long* phase_ts_dev = nullptr;
-  std::vector<int32_t> phase_kinds;  // bit k set: the phase holds items of kind k
+  std::vector<int32_t> phase_kinds;  // bit k set: the phase holds items of kind k; bits 8..: tiles in the phase
 
   int grid() {
     if (n_sm == 0) {
@@ -659,7 +691,10 @@ struct CudaBackend {
       phase_ts_dev = A.phase_ts;
       phase_kinds.assign(A.n_phases, 0);
       for (int p = 0; p < A.n_phases; ++p)
+        {
         for (int k = 0; k < Hh.phases[p].n_items; ++k) phase_kinds[p] |= 1 << Hh.items[Hh.phases[p].item0 + k].kind;
+        phase_kinds[p] |= Hh.phases[p].n_tiles << 8;
+      }
     }
     if (A.n_phases > 0) {
       ChainArgs args = A;

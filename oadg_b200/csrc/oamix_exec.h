@@ -149,7 +149,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
                    align_up_sz((size_t)(h.n_bbo > 0 ? h.n_bbo : 1) * sizeof(BboJob), 16) +
                    align_up_sz((size_t)L.max_items * sizeof(Item), 16) +
                    align_up_sz((size_t)L.max_phases * sizeof(Phase), 16) +
-                   align_up_sz((size_t)L.max_phases * (kMaxGrid + 1) * sizeof(int32_t), 16) +
+                   align_up_sz((size_t)L.max_phases * (kMaxGrid + 1) * 2 * sizeof(int32_t), 16) +
                    align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
   L.off_tables = align_up_sz((size_t)h.total_bytes, 16);
@@ -282,7 +282,7 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   const BboJob* bjobs;
   const Item* items;
   const Phase* phases;
-  const int32_t* ranges;     // [n_phases][grid + 1] tile boundaries of every CTA
+  const int32_t* ranges;     // [n_phases][grid + 1][2]: first tile of every CTA and the item that tile belongs to
   int32_t n_phases, grid;
   unsigned* hist;
   unsigned long long* luma;
@@ -317,13 +317,13 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   make_layout(pv, L);
   if (workspace_bytes < L.total) return OADG_E_ARG;
   if (((uintptr_t)workspace & 255) != 0) return OADG_E_ARG;
-  {  // the profile tile keeps the low-res profile and the gaussian kernel in 24 KB of shared memory
+  {  // the profile tile keeps the kernel's prefix sums (<= 3072 taps) and the low-res profile (<= 2048) in shared memory
     int max_k = 1;
     for (int g = 0; g < h.n_gt; ++g) {
       max_k = pv.gts[g].kx > max_k ? pv.gts[g].kx : max_k;
       max_k = pv.gts[g].ky > max_k ? pv.gts[g].ky : max_k;
     }
-    if ((h.max_w > h.max_h ? h.max_w : h.max_h) / 4 + 1 + max_k > 6144) return OADG_E_LIMIT;
+    if ((h.max_w > h.max_h ? h.max_w : h.max_h) / 4 > 2048 || max_k > 3072) return OADG_E_LIMIT;
   }
   char* ws = static_cast<char*>(workspace);
   const int G = be.grid();
@@ -358,7 +358,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const size_t t_bjob = carve((size_t)(L.n_bbo > 0 ? L.n_bbo : 1) * sizeof(BboJob));
   const size_t t_items = carve((size_t)L.max_items * sizeof(Item));
   const size_t t_phases = carve((size_t)L.max_phases * sizeof(Phase));
-  const size_t t_ranges = carve((size_t)L.max_phases * (kMaxGrid + 1) * sizeof(int32_t));
+  const size_t t_ranges = carve((size_t)L.max_phases * (kMaxGrid + 1) * 2 * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
@@ -556,7 +556,8 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     }
     ph.n_tiles = tile0;
     // cost of every tile in phase order -> boundary k = first tile whose cumulative cost reaches k/G of the total
-    int32_t* rg = ranges + (size_t)p * (G + 1);
+    std::vector<int32_t> rgv(G + 1);
+    int32_t* rg = rgv.data();
     auto step_tile_cost = [&](const Lane& ln, int ti, int tx) {
       const int x0 = (ti % tx) * kStepTileW, y0 = (ti / tx) * kStepTileH;
       const int x1 = x0 + kStepTileW < ln.W ? x0 + kStepTileW : ln.W, y1 = y0 + kStepTileH < ln.H ? y0 + kStepTileH : ln.H;
@@ -610,6 +611,13 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
         while (kb <= G) rg[kb++] = ph.n_tiles;
     }
     rg[G] = ph.n_tiles;
+    int32_t* rt = ranges + (size_t)p * (G + 1) * 2;
+    int it = ph.item0;
+    for (int k = 0; k <= G; ++k) {
+      while (it + 1 < ph.item0 + ph.n_items && rg[k] >= items[it].tile0 + items[it].ntiles) ++it;
+      rt[2 * k] = rg[k];
+      rt[2 * k + 1] = it;
+    }
   }
 
   for (int v = 0; v < h.n_views; ++v) {

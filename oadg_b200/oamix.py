@@ -544,6 +544,8 @@ class OAMix:
             for p in range(min(int(n_ph.value), cap)):   # a phase is charged to the set of item kinds it holds
                 key = '+'.join(k for i, k in enumerate(ITEM_KINDS) if ph_kinds[p] >> i & 1)
                 by[key] = by.get(key, 0.0) + float(ph_ms[p])
+                if 'phase_log' in profile:
+                    profile['phase_log'].append((key, ph_kinds[p] >> 8, float(ph_ms[p])))
             self.last_launches += 2
             return outs
         n = ctypes.c_int(0)

@@ -1,0 +1,26 @@
+"""Per-phase durations of the OA-Mix chain kernel for a few bench batches (GPU box): kinds, tiles, microseconds."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from oadg_b200 import OAMix  # noqa: E402
+
+dev = torch.device('cuda:0')
+frames = [bench.make_image(s) for s in range(8)]
+imgs = [torch.from_numpy(f).to(dev) for f, _ in frames]
+gts = [g for _, g in frames]
+mix = OAMix(**bench.OAMIX_CFG)
+np.random.seed(1000)
+for i in range(3):
+    mix.oamix_batch(imgs[0:2], gts[0:2])
+for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
+    prof = {'phase_log': []}
+    j = (2 * i) % 8
+    mix.oamix_batch(imgs[j:j + 2], gts[j:j + 2], profile=prof)
+    print('batch %d: chain %.1f us, mix %.1f us, %d phases' % (i, prof['chain_ms'] * 1e3, prof['mix_ms'] * 1e3, prof['phases']))
+    for key, tiles, ms in prof['phase_log']:
+        print('   %8.1f us  %6d tiles  %s' % (ms * 1e3, tiles, key))
