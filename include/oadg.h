@@ -198,13 +198,15 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
  * kernel); the call synchronises the stream before returning (measurement only).  The chain kernel stamps
  * %globaltimer at every phase boundary: phase_ms[p] / phase_kinds[p] (bit k = the phase holds work items of kind k,
  * k = 0 profile, 1 mask, 2 hist, 3 lut, 4 frame copy, 5 bbo blend, 6 bbo catch-up, 7 depth step) receive up
- * to phase_cap entries. */
+ * to phase_cap entries; kind_stats (optional, 16 x uint64) receives the CTA-busy nanoseconds and the tile counts
+ * summed per item kind. */
 int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
                                 const uint8_t* const* src_dev, int n_img,
                                 uint8_t* const* dst_dev,
                                 void* workspace_dev, size_t workspace_bytes,
                                 float* ms_chain, float* ms_mix, int* n_phases_out,
-                                float* phase_ms, int32_t* phase_kinds, int phase_cap, void* stream);
+                                float* phase_ms, int32_t* phase_kinds, int phase_cap,
+                                unsigned long long* kind_stats, void* stream);
 
 /* ---- OA-Loss ---------------------------------------------------------------- */
 

@@ -315,66 +315,111 @@ __device__ void copy_segment(const Chain& C, size_t nbytes, bool both, int l0, i
   }
 }
 
-// ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
-// A CTA stages the job once (inverse affine, support, the support's slices of the two mask profiles) and then walks
-// its tiles of 64 x 16 px, one pixel per thread, two tiles in flight.
-struct BboPx {
-  int v[3];      // the running image at the pixel
-  int tap[12];   // 4 taps x 3 channels of the warped image
-  float m;
-  int fx, fy;
-  size_t o;
-  bool on;
+// ---- staged affine gathers ---------------------------------------------------------------------------------
+// Both geometric op families (bboxes-only blends and bg-only ops) resample a frame through cv::warpAffine's
+// fixed-point bilinear map.  A CTA works on sub-tiles of 128 x 32 output pixels: the source rectangle the sub-tile
+// reads (exact: the map is monotone in x and in y, so its extremes sit at the sub-tile corners) is copied into
+// shared memory with 16-byte vector loads of whole row spans, then every thread resamples 4 consecutive pixels
+// from shared memory and writes 12 bytes.  Out-of-frame taps read 0 (BORDER_CONSTANT).
+constexpr int kSubW = 128, kSubH = 32;
+constexpr int kDynSmem = 160 * 1024;
+
+struct StageView {
+  const uint8_t* sm;   // staged rows: row r holds the 16-byte aligned global span that covers source row by0 + r
+  int pitch;           // bytes per staged row (multiple of 16)
+  int bx0, by0, bx1, by1;
+  uint32_t lo;         // low bits of the frame pointer: byte phase of a row = (lo + (y*W + bx0)*C) & 15
+  int W, H, C;
 };
-__device__ __forceinline__ void bbo_px_load(const ChainArgs& A, const BboStage& bs, const float* prof, bool prof_smem,
-                                            int x, int y, BboPx& q) {
-  q.on = x < bs.rect[2] && y < bs.rect[3];
-  q.m = 0.f;
-  if (!q.on) return;
-  const int W = bs.W, H = bs.H;
-  const uint8_t* X = bs.X;
-  q.o = ((size_t)y * W + x) * 3;
-  const int w = bs.rect[2] - bs.rect[0];
-  const float ux = prof_smem ? prof[x - bs.rect[0]] : A.prof_x[(size_t)bs.gt * A.P.max_w + x];
-  const float uy = prof_smem ? prof[w + y - bs.rect[1]] : A.prof_y[(size_t)bs.gt * A.P.max_h + y];
-  q.m = fmul(uy, ux);
-  q.v[0] = X[q.o];
-  q.v[1] = X[q.o + 1];
-  q.v[2] = X[q.o + 2];
-  if (q.m == 0.f) return;  // m == 0 => img*1 + aug*0 == img exactly
-  // cv::warpAffine fixed point (oamix_math.h warp_row / warp_px)
-  const int Xf = (cv_round(dmul(dadd(dmul(bs.minv[1], (double)y), bs.minv[2]), 1024.0)) + 16 +
-                  cv_round(dmul(dmul(bs.minv[0], (double)x), 1024.0))) >> 5;
-  const int Yf = (cv_round(dmul(dadd(dmul(bs.minv[4], (double)y), bs.minv[5]), 1024.0)) + 16 +
-                  cv_round(dmul(dmul(bs.minv[3], (double)x), 1024.0))) >> 5;
-  const int sx = imin(imax(Xf >> 5, -32768), 32767), sy = imin(imax(Yf >> 5, -32768), 32767);
-  q.fx = Xf & 31;
-  q.fy = Yf & 31;
-  const bool x0 = (unsigned)sx < (unsigned)W, x1 = q.fx != 0 && (unsigned)(sx + 1) < (unsigned)W;
-  const bool y0 = (unsigned)sy < (unsigned)H, y1 = q.fy != 0 && (unsigned)(sy + 1) < (unsigned)H;
-  const uint8_t* r0 = X + ((size_t)sy * W + sx) * 3;
-  const uint8_t* r1 = r0 + (size_t)W * 3;
+
+__device__ __forceinline__ void warp_coord(const double* m, int x, int y, int& sx, int& sy, int& fx, int& fy) {
+  const int X = (cv_round(dmul(dadd(dmul(m[1], (double)y), m[2]), 1024.0)) + 16 + cv_round(dmul(dmul(m[0], (double)x), 1024.0))) >> 5;
+  const int Y = (cv_round(dmul(dadd(dmul(m[4], (double)y), m[5]), 1024.0)) + 16 + cv_round(dmul(dmul(m[3], (double)x), 1024.0))) >> 5;
+  sx = imin(imax(X >> 5, -32768), 32767);
+  sy = imin(imax(Y >> 5, -32768), 32767);
+  fx = X & 31;
+  fy = Y & 31;
+}
+// source rectangle of the output rectangle [x0,x1) x [y0,y1), clamped to the frame; false when it is empty
+__device__ __forceinline__ bool warp_src_rect(const double* m, int x0, int y0, int x1, int y1, int W, int H, int r[4]) {
+  int sxa = 1 << 30, sxb = -(1 << 30), sya = 1 << 30, syb = -(1 << 30);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int sx, sy, fx, fy;
+    warp_coord(m, (k & 1) ? x1 - 1 : x0, (k & 2) ? y1 - 1 : y0, sx, sy, fx, fy);
+    sxa = imin(sxa, sx); sxb = imax(sxb, sx);
+    sya = imin(sya, sy); syb = imax(syb, sy);
+  }
+  r[0] = imax(sxa, 0);
+  r[1] = imax(sya, 0);
+  r[2] = imin(sxb + 2, W);
+  r[3] = imin(syb + 2, H);
+  return r[2] > r[0] && r[3] > r[1];
+}
+__device__ __forceinline__ int stage_pitch(int bx0, int bx1, int C) { return (15 + (bx1 - bx0) * C + 15) & ~15; }
+// copy source rows [by0,by1) x [bx0,bx1) of a C-byte-per-pixel frame into shared memory (all threads)
+__device__ void stage_rows(StageView& v, uint8_t* sm, const uint8_t* base, int W, int H, int C, const int r[4]) {
+  v.sm = sm;
+  v.bx0 = r[0]; v.by0 = r[1]; v.bx1 = r[2]; v.by1 = r[3];
+  v.W = W; v.H = H; v.C = C;
+  v.lo = (uint32_t)(uintptr_t)base;
+  v.pitch = stage_pitch(r[0], r[2], C);
+  const int vpr = v.pitch >> 4, rows = r[3] - r[1];
+  const uint8_t* end = base + (size_t)H * W * C;
+  for (int i = threadIdx.x; i < rows * vpr; i += kCT) {
+    const int rr = i / vpr, vv = i - rr * vpr;
+    const uint8_t* g = base + ((size_t)(r[1] + rr) * W + r[0]) * C;
+    const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)15) + vv * 16;
+    uint4 val;
+    if (ga >= base && ga + 16 <= end) {
+      val = *reinterpret_cast<const uint4*>(ga);
+    } else {  // the vector straddles the frame's first / last bytes
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      for (int k = 0; k < 16; ++k)
+        if (ga + k >= base && ga + k < end) w[k >> 2] |= (uint32_t)ga[k] << ((k & 3) * 8);
+      val = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(sm + (size_t)rr * v.pitch + vv * 16) = val;
+  }
+}
+// first byte of source pixel (sx, sy) in the staged rows (the pixel must lie inside the staged rectangle)
+__device__ __forceinline__ const uint8_t* staged_px(const StageView& v, int sx, int sy) {
+  const uint32_t phase = (v.lo + (uint32_t)((sy * v.W + v.bx0) * v.C)) & 15u;
+  return v.sm + (sy - v.by0) * v.pitch + phase + (sx - v.bx0) * v.C;
+}
+// one warped u8x3 pixel from staged rows (same taps and weights as warp_fetch3)
+__device__ __forceinline__ void staged_fetch3(const StageView& v, int sx, int sy, int fx, int fy, int out[3]) {
+  const bool x0 = (unsigned)sx < (unsigned)v.W, x1 = fx != 0 && (unsigned)(sx + 1) < (unsigned)v.W;
+  const bool y0 = (unsigned)sy < (unsigned)v.H, y1 = fy != 0 && (unsigned)(sy + 1) < (unsigned)v.H;
+  const uint8_t* r0 = staged_px(v, sx, sy);
+  const uint8_t* r1 = staged_px(v, sx, sy + 1);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    q.tap[c] = (y0 && x0) ? r0[c] : 0;
-    q.tap[3 + c] = (y0 && x1) ? r0[3 + c] : 0;
-    q.tap[6 + c] = (y1 && x0) ? r1[c] : 0;
-    q.tap[9 + c] = (y1 && x1) ? r1[3 + c] : 0;
+    const int v00 = (y0 && x0) ? r0[c] : 0, v01 = (y0 && x1) ? r0[3 + c] : 0;
+    const int v10 = (y1 && x0) ? r1[c] : 0, v11 = (y1 && x1) ? r1[3 + c] : 0;
+    out[c] = bilerp_fix(v00, v01, v10, v11, fx, fy);
   }
 }
-__device__ __forceinline__ void bbo_px_store(const BboStage& bs, const BboPx& q) {
-  if (!q.on) return;
-  int v[3] = {q.v[0], q.v[1], q.v[2]};
-  if (q.m != 0.f) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      v[c] = bbo_blend(q.m, v[c], bilerp_fix(q.tap[c], q.tap[3 + c], q.tap[6 + c], q.tap[9 + c], q.fx, q.fy));
-  }
-  uint8_t* Y = bs.Y + q.o;
-  Y[0] = (uint8_t)v[0];
-  Y[1] = (uint8_t)v[1];
-  Y[2] = (uint8_t)v[2];
+__device__ __forceinline__ int staged_fetch1(const StageView& v, int sx, int sy, int fx, int fy) {
+  const bool x0 = (unsigned)sx < (unsigned)v.W, x1 = fx != 0 && (unsigned)(sx + 1) < (unsigned)v.W;
+  const bool y0 = (unsigned)sy < (unsigned)v.H, y1 = fy != 0 && (unsigned)(sy + 1) < (unsigned)v.H;
+  const uint8_t* r0 = staged_px(v, sx, sy);
+  const uint8_t* r1 = staged_px(v, sx, sy + 1);
+  return bilerp_fix((y0 && x0) ? r0[0] : 0, (y0 && x1) ? r0[1] : 0, (y1 && x0) ? r1[0] : 0, (y1 && x1) ? r1[1] : 0, fx, fy);
 }
+// 4 consecutive pixels (12 bytes) of a u8x3 frame at byte offset o: three words when aligned, bytes otherwise
+__device__ __forceinline__ void load12(const uint8_t* p, bool vec, int n, uint32_t w[3]) {
+  if (vec) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
+  } else {
+    w[0] = w[1] = w[2] = 0u;
+    for (int k = 0; k < 3 * n; ++k) w[k >> 2] |= (uint32_t)p[k] << ((k & 3) * 8);
+  }
+}
+__device__ __forceinline__ int byte_of(const uint32_t w[3], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 255u); }
+
+// ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
 __device__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -397,52 +442,111 @@ __device__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool 
   }
   __syncthreads();
 }
-__device__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
+// blend of one box: tiles [l0, l1) of 128 x 32 px; Y = uint8(X*(1-m) + warp(X)*m) inside the support
+__device__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
   bbo_stage(A, S, I, false);
   const BboStage& bs = S.bs;
   const int t = threadIdx.x;
+  const int W = bs.W, H = bs.H;
   const int w = bs.rect[2] - bs.rect[0], h = bs.rect[3] - bs.rect[1];
   const bool prof_smem = w + h <= 6144;
   if (prof_smem) {
     for (int i = t; i < w; i += kCT) S.u.prof[i] = A.prof_x[(size_t)bs.gt * A.P.max_w + bs.rect[0] + i];
     for (int i = t; i < h; i += kCT) S.u.prof[w + i] = A.prof_y[(size_t)bs.gt * A.P.max_h + bs.rect[1] + i];
-    __syncthreads();
   }
-  const int lx = t & 63, ly = t >> 6, tx = I.tx;
-  for (int k = l0; k < l1; k += 2) {
-    BboPx q0, q1;
-    bbo_px_load(A, bs, S.u.prof, prof_smem, bs.rect[0] + (k % tx) * kBboTileW + lx, bs.rect[1] + (k / tx) * kBboTileH + ly, q0);
-    q1.on = false;
-    if (k + 1 < l1)
-      bbo_px_load(A, bs, S.u.prof, prof_smem, bs.rect[0] + ((k + 1) % tx) * kBboTileW + lx,
-                  bs.rect[1] + ((k + 1) / tx) * kBboTileH + ly, q1);
-    bbo_px_store(bs, q0);
-    bbo_px_store(bs, q1);
+  const bool vec = ((W * 3) & 3) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 3) == 0;
+  const int ax0 = bs.rect[0] & ~3, tx = I.tx;
+  for (int k = l0; k < l1; ++k) {
+    const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
+    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
+    int sr[4];
+    const bool any_src = warp_src_rect(bs.minv, x0, ty0, x1, y1, W, H, sr);
+    StageView sv;
+    sv.W = W; sv.H = H; sv.C = 3; sv.sm = dyn; sv.pitch = 16; sv.bx0 = sv.by0 = sv.bx1 = sv.by1 = 0; sv.lo = 0;
+    const bool staged = any_src && (size_t)(sr[3] - sr[1]) * stage_pitch(sr[0], sr[2], 3) <= (size_t)kDynSmem;
+    __syncthreads();  // the previous tile's gathers are done (and the profile slices are in place)
+    if (staged) stage_rows(sv, dyn, bs.X, W, H, 3, sr);
+    __syncthreads();
+    const int y = ty0 + (t >> 5), xg = tx0 + (t & 31) * 4;
+    if (y >= y1 || xg >= x1 || xg + 4 <= x0) continue;
+    const size_t o = ((size_t)y * W + xg) * 3;
+    const bool full = xg >= x0 && xg + 4 <= x1;
+    uint32_t in_w[3], out_w[3] = {0u, 0u, 0u};
+    if (full) load12(bs.X + o, vec, 4, in_w);
+    else {
+      in_w[0] = in_w[1] = in_w[2] = 0u;
+      for (int i = 0; i < 4; ++i)
+        if (xg + i >= x0 && xg + i < x1)
+          for (int c = 0; c < 3; ++c) in_w[(3 * i + c) >> 2] |= (uint32_t)bs.X[o + 3 * i + c] << (((3 * i + c) & 3) * 8);
+    }
+    const float uy = prof_smem ? S.u.prof[w + y - bs.rect[1]] : A.prof_y[(size_t)bs.gt * A.P.max_h + y];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = xg + i;
+      int v[3] = {byte_of(in_w, 3 * i), byte_of(in_w, 3 * i + 1), byte_of(in_w, 3 * i + 2)};
+      if (x >= x0 && x < x1) {
+        const float ux = prof_smem ? S.u.prof[x - bs.rect[0]] : A.prof_x[(size_t)bs.gt * A.P.max_w + x];
+        const float m = fmul(uy, ux);
+        if (m != 0.f) {  // m == 0 => img*1 + aug*0 == img exactly
+          int sx, sy, fx, fy, a[3];
+          warp_coord(bs.minv, x, y, sx, sy, fx, fy);
+          if (staged) staged_fetch3(sv, sx, sy, fx, fy, a);
+          else {
+            WarpTap tp;
+            tp.sx = sx; tp.sy = sy; tp.fx = fx; tp.fy = fy;
+            if (any_src) warp_fetch3(LdRW(), bs.X, H, W, tp, a);
+            else a[0] = a[1] = a[2] = 0;
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[c] = bbo_blend(m, v[c], a[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)v[c] << (((3 * i + c) & 3) * 8);
+    }
+    if (full && vec) {
+      uint32_t* q = reinterpret_cast<uint32_t*>(bs.Y + o);
+      q[0] = out_w[0]; q[1] = out_w[1]; q[2] = out_w[2];
+    } else {
+      for (int i = 0; i < 4; ++i)
+        if (xg + i >= x0 && xg + i < x1)
+          for (int c = 0; c < 3; ++c) bs.Y[o + 3 * i + c] = (uint8_t)byte_of(out_w, 3 * i + c);
+    }
   }
 }
+// catch-up copy of a level l-1 support into the frame level l writes, minus the supports level l rewrites
 __device__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
   bbo_stage(A, S, I, true);
   const BboStage& bs = S.bs;
-  const int t = threadIdx.x;
-  const int lx = t & 63, ly = t >> 6, tx = I.tx;
+  const int t = threadIdx.x, W = bs.W;
+  const bool vec = ((W * 3) & 3) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 3) == 0;
+  const int ax0 = bs.rect[0] & ~3, tx = I.tx;
   const BboJob* jobs = A.bjobs;
   const BboJob& J = A.bjobs[I.obj];
   for (int k = l0; k < l1; ++k) {
-    const int x = bs.rect[0] + (k % tx) * kBboTileW + lx, y = bs.rect[1] + (k / tx) * kBboTileH + ly;
-    if (x >= bs.rect[2] || y >= bs.rect[3]) continue;
-    if (bs.n_excl <= 16) {
-      bool hit = false;
-      for (int e = 0; e < bs.n_excl; ++e)
-        hit |= x >= bs.excl[e][0] && x < bs.excl[e][2] && y >= bs.excl[e][1] && y < bs.excl[e][3];
-      if (hit) continue;
-      const size_t o = ((size_t)y * bs.W + x) * 3;
-      const int v0 = bs.X[o], v1 = bs.X[o + 1], v2 = bs.X[o + 2];
-      bs.Y[o] = (uint8_t)v0;
-      bs.Y[o + 1] = (uint8_t)v1;
-      bs.Y[o + 2] = (uint8_t)v2;
-    } else {
-      bbo_c_pixel(jobs, J, bs.W, bs.X, bs.Y, x, y);
+    const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
+    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
+    const int y = ty0 + (t >> 5), xg = tx0 + (t & 31) * 4;
+    if (y >= y1 || xg >= x1 || xg + 4 <= x0) continue;
+    const size_t o = ((size_t)y * W + xg) * 3;
+    // does a next-level support touch this 4-px group?
+    bool touch = bs.n_excl > 16, all_in = false;
+    if (bs.n_excl <= 16)
+      for (int e = 0; e < bs.n_excl; ++e) {
+        const bool yy = y >= bs.excl[e][1] && y < bs.excl[e][3];
+        touch |= yy && xg < bs.excl[e][2] && xg + 4 > bs.excl[e][0];
+        all_in |= yy && xg >= bs.excl[e][0] && xg + 4 <= bs.excl[e][2];
+      }
+    if (all_in) continue;
+    if (!touch && vec && xg >= x0 && xg + 4 <= x1) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.X + o);
+      const uint32_t a0 = q[0], a1 = q[1], a2 = q[2];
+      uint32_t* d = reinterpret_cast<uint32_t*>(bs.Y + o);
+      d[0] = a0; d[1] = a1; d[2] = a2;
+      continue;
     }
+    for (int i = 0; i < 4; ++i)
+      if (xg + i >= x0 && xg + i < x1) bbo_c_pixel(jobs, J, W, bs.X, bs.Y, xg + i, y);
   }
 }
 
@@ -482,13 +586,92 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
   q[2] = (uint8_t)px[2];
 }
 
+// bg-only op (bbox_augmentation.py:240-272) on a sub-tile of 128 x 32 px that one region covers: the frame and the
+// uint8 union mask are both warped from staged shared-memory rows; 4 pixels per thread.
+__device__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int x0, int y0, int x1,
+                           int y1, const double* div255) {
+  const DevPlan& P = A.P;
+  const int W = L.W, H = L.H, t = threadIdx.x;
+  int sr[4];
+  const bool any_src = warp_src_rect(R.minv, x0, y0, x1, y1, W, H, sr);
+  const int pitch_i = any_src ? stage_pitch(sr[0], sr[2], 3) : 0, pitch_m = any_src ? stage_pitch(sr[0], sr[2], 1) : 0;
+  const int rows = any_src ? sr[3] - sr[1] : 0;
+  const bool staged = any_src && (size_t)rows * (pitch_i + pitch_m) <= (size_t)kDynSmem;
+  StageView si, sm;
+  si.W = sm.W = W; si.H = sm.H = H; si.C = 3; sm.C = 1;
+  si.sm = sm.sm = dyn; si.pitch = sm.pitch = 16; si.bx0 = si.by0 = si.bx1 = si.by1 = sm.bx0 = sm.by0 = sm.bx1 = sm.by1 = 0;
+  si.lo = sm.lo = 0;
+  const uint8_t* mu = P.masku + (size_t)L.view * P.mask_stride;
+  __syncthreads();  // the previous sub-tile's gathers are done
+  if (staged) {
+    stage_rows(si, dyn, L.in, W, H, 3, sr);
+    stage_rows(sm, dyn + (size_t)rows * pitch_i, mu, W, H, 1, sr);
+  }
+  __syncthreads();
+  const int y = y0 + (t >> 5), xg = x0 + (t & 31) * 4;
+  if (y >= y1 || xg >= x1) return;
+  const int n = imin(4, x1 - xg);
+  const size_t o = ((size_t)y * W + xg) * 3;
+  const bool vec = n == 4 && ((W * 3) & 3) == 0 && ((((uintptr_t)L.in) | ((uintptr_t)L.out)) & 3) == 0;
+  uint32_t in_w[3], out_w[3] = {0u, 0u, 0u};
+  load12(L.in + o, vec, n, in_w);
+  const float* mf = P.maskf + (size_t)L.view * P.mask_stride + (size_t)y * W + xg;
+  float Mv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n == 4 && (W & 3) == 0) {
+    const float4 q = *reinterpret_cast<const float4*>(mf);
+    Mv[0] = q.x; Mv[1] = q.y; Mv[2] = q.z; Mv[3] = q.w;
+  } else {
+    for (int i = 0; i < n; ++i) Mv[i] = mf[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int px[3] = {0, 0, 0};
+    if (i < n) {
+      const int x = xg + i;
+      int sx, sy, fx, fy, wm = 0;
+      warp_coord(R.minv, x, y, sx, sy, fx, fy);
+      if (staged) {
+        staged_fetch3(si, sx, sy, fx, fy, px);
+        wm = staged_fetch1(sm, sx, sy, fx, fy);
+      } else if (any_src) {
+        WarpTap tp;
+        tp.sx = sx; tp.sy = sy; tp.fx = fx; tp.fy = fy;
+        warp_fetch3(LdRO(), L.in, H, W, tp, px);
+        const bool bx0 = (unsigned)sx < (unsigned)W, bx1 = fx != 0 && (unsigned)(sx + 1) < (unsigned)W;
+        const bool by0 = (unsigned)sy < (unsigned)H, by1 = fy != 0 && (unsigned)(sy + 1) < (unsigned)H;
+        const uint8_t* r0 = mu + (size_t)sy * W + sx;
+        const uint8_t* r1 = r0 + W;
+        wm = bilerp_fix((by0 && bx0) ? ldb(r0) : 0, (by0 && bx1) ? ldb(r0 + 1) : 0, (by1 && bx0) ? ldb(r1) : 0,
+                        (by1 && bx1) ? ldb(r1 + 1) : 0, fx, fy);
+      }
+      const float M = Mv[i];
+      if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
+        const double am = __ldg(div255 + wm);  // wm / 255 in float64, tabulated (exactly the reference's quotient)
+        const double keep = (double)M > am ? (double)M : am;
+        const double rest = dsub(1.0, keep);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          px[c] = (int)dadd(dmul(keep, (double)byte_of(in_w, 3 * i + c)), dmul(rest, (double)px[c]));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)px[c] << (((3 * i + c) & 3) * 8);
+  }
+  if (vec) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(L.out + o);
+    q[0] = out_w[0]; q[1] = out_w[1]; q[2] = out_w[2];
+  } else {
+    for (int k = 0; k < 3 * n; ++k) L.out[o + k] = (uint8_t)byte_of(out_w, k);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // one 256 x 64 tile of one depth step of one lane (oa_mix.py:226-234).  Runs of 16 pixels that one table-lookup /
 // bbo-copy region covers move as three 16-byte vectors per thread (LUTs in shared memory); everything else (bg-only
 // gathers, invert / colour / sharpness, runs cut by a multi-level box edge) is evaluated per pixel with consecutive
 // lanes on consecutive pixels (run_is_stream, oamix_tile.h, decides which pass owns a run).
 // ------------------------------------------------------------------------------------
-__device__ void step_tile(const ChainArgs& A, ChainSmem& S, int local, int tx, const double* div255) {
+__device__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int local, int tx, const double* div255) {
   const Lane& L = S.lane;
   const int W = L.W, H = L.H, t = threadIdx.x;
   const int x0 = (local % tx) * kStepTileW, y0 = (local / tx) * kStepTileH;
@@ -496,6 +679,12 @@ __device__ void step_tile(const ChainArgs& A, ChainSmem& S, int local, int tx, c
   const int region = tile_region(L, x0, y0, x1, y1);
   const bool tile_stream = region >= 0 && kind_streams(L.kind[region]);
   const bool tile_pixel = region >= 0 && !tile_stream;
+  if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) {  // uniform bg-only tile: staged gathers
+    for (int sy0 = y0; sy0 < y1; sy0 += kSubH)
+      for (int sx0 = x0; sx0 < x1; sx0 += kSubW)
+        bg_subtile(A, dyn, L, S.rop[region], sx0, sy0, min(sx0 + kSubW, x1), min(sy0 + kSubH, y1), div255);
+    return;
+  }
   if (!tile_pixel) {
     const int x = x0 + (t & 15) * kChunkPx, y = y0 + (t >> 4);
     if (x < x1 && y < y1) {
@@ -573,6 +762,7 @@ __device__ void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
 __global__ void __launch_bounds__(kCT, 1)
 oamix_chain_kernel(const ChainArgs A, const double* div255) {
   __shared__ ChainSmem S;
+  extern __shared__ __align__(16) uint8_t dyn[];   // kDynSmem bytes: staged source rows of the affine gathers
   const int b = blockIdx.x, G = gridDim.x;
   int staged_lane = -1;
   for (int p = 0; p < A.n_phases; ++p) {
@@ -588,6 +778,7 @@ oamix_chain_kernel(const ChainArgs A, const double* div255) {
       const int seg_end = min(t1, I.tile0 + I.ntiles);
       const int l0 = tile - I.tile0, l1 = seg_end - I.tile0;
       tile = seg_end;
+      const unsigned long long seg_t0 = globaltimer_ns();
       switch (I.kind) {
         case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;
         case OADG_IT_MASK:
@@ -608,16 +799,20 @@ oamix_chain_kernel(const ChainArgs A, const double* div255) {
           copy_segment(C, (size_t)V.H * V.W * 3, I.aux != 0, l0, l1);
           break;
         }
-        case OADG_IT_BBO_R: bbo_r_segment(A, S, I, l0, l1); break;
+        case OADG_IT_BBO_R: bbo_r_segment(A, S, dyn, I, l0, l1); break;
         case OADG_IT_BBO_C: bbo_c_segment(A, S, I, l0, l1); break;
         case OADG_IT_STEP:
           if (staged_lane != I.obj) {
             stage_lane(A, S, I.obj);
             staged_lane = I.obj;
           }
-          for (int k = l0; k < l1; ++k) step_tile(A, S, k, I.tx, div255);
+          for (int k = l0; k < l1; ++k) step_tile(A, S, dyn, k, I.tx, div255);
           break;
         default: break;
+      }
+      if (threadIdx.x == 0) {
+        atomicAdd(A.kind_ns + I.kind, globaltimer_ns() - seg_t0);
+        atomicAdd(A.kind_ns + 8 + I.kind, (unsigned long long)(l1 - l0));
       }
     }
     if (p + 1 < A.n_phases) grid_barrier(A.bar, (unsigned)(p + 1) * (unsigned)G);
@@ -663,6 +858,7 @@ struct CudaBackend {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   int n_phases = 0;
   const unsigned long long* phase_ts_dev = nullptr;
+  const unsigned long long* kind_ns_dev = nullptr;
   std::vector<int32_t> phase_kinds;  // bit k set: the phase holds items of kind k; bits 8..: tiles in the phase
 
   int grid() {
@@ -689,6 +885,7 @@ struct CudaBackend {
       BE_TRY(cudaEventRecord(ev[0], stream));
       n_phases = A.n_phases;
       phase_ts_dev = A.phase_ts;
+      kind_ns_dev = A.kind_ns;
       phase_kinds.assign(A.n_phases, 0);
       for (int p = 0; p < A.n_phases; ++p)
         {
@@ -700,7 +897,13 @@ struct CudaBackend {
       ChainArgs args = A;
       void* params[2] = {(void*)&args, (void*)&div255};
       // cooperative launch: all CTAs are guaranteed co-resident, which the in-kernel grid barrier relies on
-      BE_TRY(cudaLaunchCooperativeKernel((const void*)oamix_chain_kernel, dim3(A.grid), dim3(kCT), params, 0, stream));
+      static bool attr_set = false;   // idempotent: a racing second thread sets the same value
+      if (!attr_set) {
+        BE_TRY(cudaFuncSetAttribute(oamix_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+        attr_set = true;
+      }
+      BE_TRY(cudaLaunchCooperativeKernel((const void*)oamix_chain_kernel, dim3(A.grid), dim3(kCT), params, kDynSmem,
+                                         stream));
       ++launches;
     }
     if (profile) BE_TRY(cudaEventRecord(ev[1], stream));
@@ -736,7 +939,7 @@ extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_by
                                            int n_img, uint8_t* const* dst_dev, void* workspace_dev,
                                            size_t workspace_bytes, float* ms_chain, float* ms_mix,
                                            int* n_phases_out, float* phase_ms, int32_t* phase_kinds, int phase_cap,
-                                           void* stream) {
+                                           unsigned long long* kind_stats, void* stream) {
   if (!ms_chain || !ms_mix || !n_phases_out) return OADG_E_ARG;
   CudaBackend be;
   be.stream = (cudaStream_t)stream;
@@ -762,6 +965,8 @@ extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_by
       if (phase_cap > 0) phase_ms[0] = *ms_chain - rest;
       for (int p = 0; p < be.n_phases && p < phase_cap; ++p) phase_kinds[p] = be.phase_kinds[p];
     }
+    if (kind_stats && be.kind_ns_dev)
+      e = cudaMemcpy(kind_stats, be.kind_ns_dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   }
   for (auto& ev : be.ev)
     if (ev) cudaEventDestroy(ev);

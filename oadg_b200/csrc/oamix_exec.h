@@ -161,7 +161,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.off_branch = take(n_branch_frames * L.frame_bytes);
   L.off_scratch = take((size_t)n_chains * 2 * L.frame_bytes);  // S + T per chain
   // one memset: [grid barrier counter | histograms | luma sums]
-  L.off_zero = take(256);
+  L.off_zero = take(256);   // [0] barrier counter; bytes 64..: per-kind busy ns [8] and tile counts [8] (uint64)
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
   L.zero_bytes = o - L.off_zero;
@@ -295,6 +295,7 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   size_t frame_bytes;
   unsigned* bar;               // grid barrier counter (zeroed before the launch)
   unsigned long long* phase_ts;  // globaltimer at the end of every phase (measurement aid)
+  unsigned long long* kind_ns;   // [8] CTA-busy nanoseconds per item kind, then [8] tiles per kind (measurement aid)
 };
 
 // Backend concept (all return 0 or an error code):
@@ -487,7 +488,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
               bjob_n += (int)cs.box.size();
               for (int k = job0; k < bjob_n; ++k) {
                 const BboJob& J = bjobs[k];
-                const int w = J.rect[2] - J.rect[0], hg = J.rect[3] - J.rect[1];
+                const int w = J.rect[2] - (J.rect[0] & ~3), hg = J.rect[3] - J.rect[1];  // tiles on a 4-px grid
                 add(OADG_IT_BBO_R, k, r0 + J.level - 1, w, hg, 0);
                 if (J.level < NL) add(OADG_IT_BBO_C, k, r0 + J.level, w, hg, 0);   // caught up by the next level
               }
@@ -670,6 +671,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.frame_bytes = L.frame_bytes;
   A.bar = reinterpret_cast<unsigned*>(ws + L.off_zero);
   A.phase_ts = reinterpret_cast<unsigned long long*>(ws + L.off_ts);
+  A.kind_ns = reinterpret_cast<unsigned long long*>(ws + L.off_zero + 64);
   // host views of the same tables (the host arithmetic check interprets them directly)
   ChainArgs Hh = A;
   Hh.lanes = lanes;

@@ -194,9 +194,9 @@ struct HostBackend {
               const int level = I.kind == OADG_IT_BBO_R ? J.level : J.level + 1;
               const uint8_t* X = chain_src(C, level);
               uint8_t* Y = chain_dst(C, level);
-              const int x0 = J.rect[0] + (local % I.tx) * kBboTileW, y0 = J.rect[1] + (local / I.tx) * kBboTileH;
+              const int x0 = (J.rect[0] & ~3) + (local % I.tx) * kBboTileW, y0 = J.rect[1] + (local / I.tx) * kBboTileH;
               for (int y = y0; y < imin(y0 + kBboTileH, J.rect[3]); ++y)
-                for (int x = x0; x < imin(x0 + kBboTileW, J.rect[2]); ++x) {
+                for (int x = imax(x0, J.rect[0]); x < imin(x0 + kBboTileW, J.rect[2]); ++x) {
                   if (I.kind == OADG_IT_BBO_R) bbo_r_pixel(P, C, P.bbo[J.bbo], X, Y, x, y);
                   else bbo_c_pixel(A.bjobs, J, P.views[C.view].W, X, Y, x, y);
                 }
