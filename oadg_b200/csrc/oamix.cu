@@ -15,6 +15,8 @@
 //                        range per phase; phases are separated by a grid barrier (release/acquire on one
 //                        counter), so nothing returns to the host between the ~10-40 dependent stages.
 //   mix_kernel           branch mixing + object-aware mixing of all views (oa_mix.py:236,281-309)
+#include <stdlib.h>
+
 #include "oadg_common.cuh"
 #include "oamix_exec.h"
 #include "oamix_tile.h"
@@ -43,6 +45,7 @@ struct BboStage {    // one bbo job staged for the CTA (bbo_r_segment / bbo_c_se
 };
 
 struct ChainSmem {
+  ChainArgs args;      // the kernel arguments, copied once: the (non-inlined) handlers read them from shared memory
   BboStage bs;
   union {
     unsigned hist[8][768];   // histogram tiles: 8 privatised copies (4 warps share one)
@@ -85,7 +88,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 // blurred-mask profile of one (gt box, axis) (oa_mix.py:78-91): indicator on the 1/sr canvas -> GaussianBlur
 // (separable, BORDER_REFLECT_101, float32 kernel from getGaussianKernel) -> bilinear cv2.resize to full resolution.
 // ------------------------------------------------------------------------------------
-__device__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
+__device__ __noinline__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
   const DevPlan& P = A.P;
   const int sr = 4;
   const int g = obj >> 1, axis = obj & 1;
@@ -130,7 +133,7 @@ __device__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
     }
     __syncthreads();
     for (int off = 1; off <= ks; off <<= 1) {  // Hillis-Steele inclusive scan over K[0..ks]
-      double v[3];
+      double v[4];
       int n = 0;
       for (int i = tid; i <= ks; i += kCT, ++n) v[n] = i >= off ? K[i] + K[i - off] : K[i];
       __syncthreads();
@@ -190,7 +193,7 @@ __device__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
 
 // union of the blurred gt masks of a view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260) as float32 and as
 // uint8(mask*255): written once per batch, read by every bg-only op.  Tile = 256 x 32 px, 8 rows per thread.
-__device__ void mask_tile(const ChainArgs& A, int view, int local, int tx) {
+__device__ __noinline__ void mask_tile(const ChainArgs& A, int view, int local, int tx) {
   const oadg_view_t& V = A.P.views[view];
   const int x = (local % tx) * kMaskTileW + (threadIdx.x & 255);
   const int yb = (local / tx) * kMaskTileH + (threadIdx.x >> 8) * 8;
@@ -199,7 +202,7 @@ __device__ void mask_tile(const ChainArgs& A, int view, int local, int tx) {
 }
 
 // per-channel histogram + luma sum of a lane's input frame (PIL Image.histogram()); tile = 32768 px (linear)
-__device__ void hist_tile(const Lane& L, ChainSmem& S, int local, unsigned long long& lsum) {
+__device__ __noinline__ void hist_tile(const Lane& L, ChainSmem& S, int local, unsigned long long& lsum) {
   const int tid = threadIdx.x;
   const size_t npx = (size_t)L.H * L.W;
   const size_t p0 = (size_t)local * kHistTilePx;
@@ -239,12 +242,12 @@ __device__ void hist_tile(const Lane& L, ChainSmem& S, int local, unsigned long 
     }
   }
 }
-__device__ void hist_begin(ChainSmem& S) {
+__device__ __noinline__ void hist_begin(ChainSmem& S) {
   __syncthreads();
   for (int i = threadIdx.x; i < 8 * 768; i += kCT) (&S.u.hist[0][0])[i] = 0;
   __syncthreads();
 }
-__device__ void hist_flush(const ChainArgs& A, ChainSmem& S, int slot, unsigned long long& lsum) {
+__device__ __noinline__ void hist_flush(const ChainArgs& A, ChainSmem& S, int slot, unsigned long long& lsum) {
   __syncthreads();
   unsigned* dst = A.hist + (size_t)slot * 768;
   for (int i = threadIdx.x; i < 768; i += kCT) {
@@ -260,7 +263,7 @@ __device__ void hist_flush(const ChainArgs& A, ChainSmem& S, int slot, unsigned 
 }
 
 // one LUT op: PIL.ImageOps autocontrast / equalize from the finished histogram, or a closed-form table
-__device__ void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
+__device__ __noinline__ void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
   const LutJob J = A.lutjobs[job];
   const oadg_op_t& op = A.P.ops[J.op];
   uint8_t* out = A.luts + (size_t)op.lut * 768;
@@ -288,7 +291,7 @@ __device__ void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
 }
 
 // T (and S when the chain has a second level) = copy of the lane input; tiles [l0, l1) of 64 KB
-__device__ void copy_segment(const Chain& C, size_t nbytes, bool both, int l0, int l1) {
+__device__ __noinline__ void copy_segment(const Chain& C, size_t nbytes, bool both, int l0, int l1) {
   const size_t b0 = (size_t)l0 * kCopyTileBytes;
   const size_t b1 = (size_t)l1 * kCopyTileBytes < nbytes ? (size_t)l1 * kCopyTileBytes : nbytes;
   const int tid = threadIdx.x;
@@ -358,7 +361,7 @@ __device__ __forceinline__ bool warp_src_rect(const double* m, int x0, int y0, i
 }
 __device__ __forceinline__ int stage_pitch(int bx0, int bx1, int C) { return (15 + (bx1 - bx0) * C + 15) & ~15; }
 // copy source rows [by0,by1) x [bx0,bx1) of a C-byte-per-pixel frame into shared memory (all threads)
-__device__ void stage_rows(StageView& v, uint8_t* sm, const uint8_t* base, int W, int H, int C, const int r[4]) {
+__device__ __noinline__ void stage_rows(StageView& v, uint8_t* sm, const uint8_t* base, int W, int H, int C, const int r[4]) {
   v.sm = sm;
   v.bx0 = r[0]; v.by0 = r[1]; v.bx1 = r[2]; v.by1 = r[3];
   v.W = W; v.H = H; v.C = C;
@@ -420,7 +423,7 @@ __device__ __forceinline__ void load12(const uint8_t* p, bool vec, int n, uint32
 __device__ __forceinline__ int byte_of(const uint32_t w[3], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 255u); }
 
 // ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
-__device__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
+__device__ __noinline__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const BboJob J = A.bjobs[I.obj];
@@ -443,10 +446,22 @@ __device__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool 
   __syncthreads();
 }
 // blend of one box: tiles [l0, l1) of 128 x 32 px; Y = uint8(X*(1-m) + warp(X)*m) inside the support
-__device__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
+__device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
   bbo_stage(A, S, I, false);
   const BboStage& bs = S.bs;
   const int t = threadIdx.x;
+  if (A.debug & 8) {   // reference path: the shared per-pixel body
+    const BboJob& J = A.bjobs[I.obj];
+    const Chain& C = A.chains[J.chain];
+    for (int k = l0; k < l1; ++k) {
+      const int tx0 = (bs.rect[0] & ~3) + (k % I.tx) * kBboTileW, ty0 = bs.rect[1] + (k / I.tx) * kBboTileH;
+      for (int q = t; q < kBboTileW * kBboTileH; q += kCT) {
+        const int x = tx0 + (q & (kBboTileW - 1)), y = ty0 + q / kBboTileW;
+        if (x >= bs.rect[0] && x < bs.rect[2] && y < bs.rect[3]) bbo_r_pixel(A.P, C, A.P.bbo[J.bbo], bs.X, bs.Y, x, y);
+      }
+    }
+    return;
+  }
   const int W = bs.W, H = bs.H;
   const int w = bs.rect[2] - bs.rect[0], h = bs.rect[3] - bs.rect[1];
   const bool prof_smem = w + h <= 6144;
@@ -463,7 +478,7 @@ __device__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, co
     const bool any_src = warp_src_rect(bs.minv, x0, ty0, x1, y1, W, H, sr);
     StageView sv;
     sv.W = W; sv.H = H; sv.C = 3; sv.sm = dyn; sv.pitch = 16; sv.bx0 = sv.by0 = sv.bx1 = sv.by1 = 0; sv.lo = 0;
-    const bool staged = any_src && (size_t)(sr[3] - sr[1]) * stage_pitch(sr[0], sr[2], 3) <= (size_t)kDynSmem;
+    const bool staged = any_src && (size_t)(sr[3] - sr[1]) * stage_pitch(sr[0], sr[2], 3) <= (size_t)kDynSmem && !(A.debug & 2);
     __syncthreads();  // the previous tile's gathers are done (and the profile slices are in place)
     if (staged) stage_rows(sv, dyn, bs.X, W, H, 3, sr);
     __syncthreads();
@@ -515,7 +530,7 @@ __device__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, co
   }
 }
 // catch-up copy of a level l-1 support into the frame level l writes, minus the supports level l rewrites
-__device__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
+__device__ __noinline__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
   bbo_stage(A, S, I, true);
   const BboStage& bs = S.bs;
   const int t = threadIdx.x, W = bs.W;
@@ -523,6 +538,16 @@ __device__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, i
   const int ax0 = bs.rect[0] & ~3, tx = I.tx;
   const BboJob* jobs = A.bjobs;
   const BboJob& J = A.bjobs[I.obj];
+  if (A.debug & 16) {   // reference path: the shared per-pixel body
+    for (int k = l0; k < l1; ++k) {
+      const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
+      for (int q = t; q < kBboTileW * kBboTileH; q += kCT) {
+        const int x = tx0 + (q & (kBboTileW - 1)), y = ty0 + q / kBboTileW;
+        if (x >= bs.rect[0] && x < bs.rect[2] && y < bs.rect[3]) bbo_c_pixel(jobs, J, W, bs.X, bs.Y, x, y);
+      }
+    }
+    return;
+  }
   for (int k = l0; k < l1; ++k) {
     const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
     const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
@@ -588,7 +613,7 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
 
 // bg-only op (bbox_augmentation.py:240-272) on a sub-tile of 128 x 32 px that one region covers: the frame and the
 // uint8 union mask are both warped from staged shared-memory rows; 4 pixels per thread.
-__device__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int x0, int y0, int x1,
+__device__ __noinline__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int x0, int y0, int x1,
                            int y1, const double* div255) {
   const DevPlan& P = A.P;
   const int W = L.W, H = L.H, t = threadIdx.x;
@@ -671,7 +696,7 @@ __device__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, cons
 // gathers, invert / colour / sharpness, runs cut by a multi-level box edge) is evaluated per pixel with consecutive
 // lanes on consecutive pixels (run_is_stream, oamix_tile.h, decides which pass owns a run).
 // ------------------------------------------------------------------------------------
-__device__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int local, int tx, const double* div255) {
+__device__ __noinline__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int local, int tx, const double* div255) {
   const Lane& L = S.lane;
   const int W = L.W, H = L.H, t = threadIdx.x;
   const int x0 = (local % tx) * kStepTileW, y0 = (local / tx) * kStepTileH;
@@ -679,7 +704,7 @@ __device__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int lo
   const int region = tile_region(L, x0, y0, x1, y1);
   const bool tile_stream = region >= 0 && kind_streams(L.kind[region]);
   const bool tile_pixel = region >= 0 && !tile_stream;
-  if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) {  // uniform bg-only tile: staged gathers
+  if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE && !(A.debug & 1)) {  // uniform bg-only tile: staged gathers
     for (int sy0 = y0; sy0 < y1; sy0 += kSubH)
       for (int sx0 = x0; sx0 < x1; sx0 += kSubW)
         bg_subtile(A, dyn, L, S.rop[region], sx0, sy0, min(sx0 + kSubW, x1), min(sy0 + kSubH, y1), div255);
@@ -734,7 +759,7 @@ __device__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int lo
 }
 
 // stage a lane record, its LUTs and its region ops in shared memory (once per lane a CTA works on)
-__device__ void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
+__device__ __noinline__ void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
   const int t = threadIdx.x;
   __syncthreads();
   if (t < (int)(sizeof(Lane) / 4))
@@ -760,9 +785,12 @@ __device__ void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
 }
 
 __global__ void __launch_bounds__(kCT, 1)
-oamix_chain_kernel(const ChainArgs A, const double* div255) {
+oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
   __shared__ ChainSmem S;
   extern __shared__ __align__(16) uint8_t dyn[];   // kDynSmem bytes: staged source rows of the affine gathers
+  if (threadIdx.x == 0) S.args = Aparam;
+  __syncthreads();
+  const ChainArgs& A = S.args;
   const int b = blockIdx.x, G = gridDim.x;
   int staged_lane = -1;
   for (int p = 0; p < A.n_phases; ++p) {
@@ -810,7 +838,7 @@ oamix_chain_kernel(const ChainArgs A, const double* div255) {
           break;
         default: break;
       }
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 0 && !(A.debug & 4)) {
         atomicAdd(A.kind_ns + I.kind, globaltimer_ns() - seg_t0);
         atomicAdd(A.kind_ns + 8 + I.kind, (unsigned long long)(l1 - l0));
       }
@@ -895,6 +923,7 @@ struct CudaBackend {
     }
     if (A.n_phases > 0) {
       ChainArgs args = A;
+      if (const char* dbg = getenv("OADG_DEBUG")) args.debug = atoi(dbg);
       void* params[2] = {(void*)&args, (void*)&div255};
       // cooperative launch: all CTAs are guaranteed co-resident, which the in-kernel grid barrier relies on
       static bool attr_set = false;   // idempotent: a racing second thread sets the same value

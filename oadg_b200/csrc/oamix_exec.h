@@ -295,6 +295,7 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   size_t frame_bytes;
   unsigned* bar;               // grid barrier counter (zeroed before the launch)
   unsigned long long* phase_ts;  // globaltimer at the end of every phase (measurement aid)
+  int32_t debug;                 // bit 0: no staged bg gathers, bit 1: no staged bbo gathers (OADG_DEBUG, tests only)
   unsigned long long* kind_ns;   // [8] CTA-busy nanoseconds per item kind, then [8] tiles per kind (measurement aid)
 };
 
@@ -671,6 +672,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.frame_bytes = L.frame_bytes;
   A.bar = reinterpret_cast<unsigned*>(ws + L.off_zero);
   A.phase_ts = reinterpret_cast<unsigned long long*>(ws + L.off_ts);
+  A.debug = 0;
   A.kind_ns = reinterpret_cast<unsigned long long*>(ws + L.off_zero + 64);
   // host views of the same tables (the host arithmetic check interprets them directly)
   ChainArgs Hh = A;

@@ -151,3 +151,55 @@ def test_edge_cases(cuda):
         # a frame-sized box saturates its blurred mask at 1.0 +- 1 ulp, where `img*(1-m) + aug*m` sits exactly on
         # an integer: the truncation then follows the last bit of cv2's float blur (still <= 1 LSB, <= 1e-4 rel)
         _close(out, ref, frac=2e-2 if gt.shape[0] == 1 and gt[0, 2] >= w else 2e-3)
+
+
+def test_single_op_plans_match_host_arithmetic_bit_for_bit(cuda):
+    """Hand-made one-step plans (every op family alone, mixed and uniform tiles, staged and direct gathers) through
+    the CUDA executor vs the same bodies compiled for the host (tests/hostsim): the two must agree exactly."""
+    import ctypes
+    import os
+    import subprocess
+    import torch
+    from conftest import ROOT
+    from oadg_b200.oamix import OAMix, _ViewPlan, _invert_affine
+    lib = os.path.join(ROOT, 'tests', 'hostsim', 'libhostsim.so')
+    if not os.path.exists(lib):
+        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC',
+                               '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'oadg_b200', 'csrc'),
+                               os.path.join(ROOT, 'tests', 'hostsim', 'hostsim.cpp'), '-o', lib])
+    hs = ctypes.CDLL(lib)
+    t = OAMix(version='augmix.all')
+    for (h, w, ml) in [(96, 160, [[14, 34, 29, 56]]), (131, 203, [[3, 5, 90, 60], [100, 70, 190, 120]]),
+                       (300, 533, [[100, 40, 400, 260]])]:
+        img, gt = synth.make_image(1, h, w, 3)
+        gi = [(int(b[0]), int(b[1]), int(b[2]), int(b[3])) for b in gt]
+        tr = ('bg_affine', _invert_affine([1.0, 0.0, -7.0, 0.0, 1.0, 0.0]))
+        sh = ('bg_affine', _invert_affine([1.0, 0.21, 0.0, 0.0, 1.0, 0.0]))
+        rot = ('bg_affine', _invert_affine(OAMix._forward_affine('rotate', 7.0, False, (w, h), None, (w, h))))
+        bbo = ('bbo_affine', [(k, _invert_affine(OAMix._forward_affine(
+            'rotate', 6.0, k % 2 == 0, (x2 - x1 + 1, y2 - y1 + 1), ((x1 + x2) / 2., (y1 + y2) / 2.), (w, h))))
+            for k, (x1, y1, x2, y2) in enumerate(gi)])
+        singles = [(('autocontrast',), ('solarize', 100)), (('autocontrast',), tr), (sh, ('posterize', 3)), (rot, rot),
+                   (bbo, ('autocontrast',)), (('equalize',), bbo), (('invert', 1, -1), ('color', 0.7)),
+                   (('sharpness', 1.5), ('contrast', 0.4)), (tr, sh)]
+        plans = [[[[a, b] + ([a] if len(ml) == 2 else [])]] for a, b in singles]
+        plans.append([[[('autocontrast',), tr] + ([sh] if len(ml) == 2 else [])],
+                      [[bbo, ('autocontrast',)] + ([rot] if len(ml) == 2 else []),
+                       [('posterize', 3), ('solarize', 99)] + ([bbo] if len(ml) == 2 else [])],
+                      [[sh, bbo] + ([tr] if len(ml) == 2 else []), [bbo, ('solarize', 77)] + ([rot] if len(ml) == 2 else [])]])
+        for ops in plans:
+            vp = _ViewPlan()
+            vp.h, vp.w = h, w
+            vp.ws = np.float32([1.0 / len(ops)] * len(ops))
+            vp.ml_boxes = np.array(ml, dtype=np.int64)
+            vp.depths = [len(s_) for s_ in ops]
+            vp.ops = ops
+            vp.scores, vp.oa_low, vp.oa_boxes, vp.m, vp.m_oa = [50.0] * len(gt), [], [], 1.0, []
+            blob = t._pack([(vp, gt, 0)])
+            ref = np.zeros_like(img)
+            src = (ctypes.c_void_p * 1)(img.ctypes.data)
+            dst = (ctypes.c_void_p * 1)(ref.ctypes.data)
+            assert hs.hostsim_oamix_execute(ctypes.c_void_p(blob.ctypes.data), ctypes.c_size_t(blob.nbytes), src, 1, dst,
+                                            None) == 0
+            out = t.execute(blob, [torch.from_numpy(img).to(cuda)])[0].cpu().numpy()
+            assert np.array_equal(out, ref), (h, w, [[op[0] for op in regs] for steps in ops for regs in steps])
