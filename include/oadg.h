@@ -198,8 +198,9 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
  * kernel); the call synchronises the stream before returning (measurement only).  The chain kernel stamps
  * %globaltimer at every phase boundary: phase_ms[p] / phase_kinds[p] (bit k = the phase holds work items of kind k,
  * k = 0 profile, 1 mask, 2 hist, 3 lut, 4 frame copy, 5 bbo blend, 6 bbo catch-up, 7 depth step) receive up
- * to phase_cap entries; kind_stats (optional, 16 x uint64) receives the CTA-busy nanoseconds and the tile counts
- * summed per item kind. */
+ * to phase_cap entries; kind_stats (optional, 48 x uint64) receives the CTA-busy nanoseconds and the tile counts
+ * summed per item kind
+ * (16 + 16 + 16 slots: busy ns, tiles, longest tile ns; slots 7, 8, 9 split the depth-step tiles into streaming / staged bg-only / mixed). */
 int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
                                 const uint8_t* const* src_dev, int n_img,
                                 uint8_t* const* dst_dev,

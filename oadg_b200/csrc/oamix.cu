@@ -8,7 +8,7 @@
 //   plan        the host-sampled plan blob (oadg.h records) + work tables, one H2D copy
 //
 // Two launches per batch:
-//   oamix_chain_kernel   ONE persistent launch (one 1024-thread CTA per SM) that walks the host-built PHASES
+//   oamix_chain_kernel   ONE persistent launch (four independent 256-thread CTAs per SM) that walks the host-built PHASES
 //                        (oamix_exec.h): mask profiles, union masks, histograms, LUTs, the bboxes-only chains
 //                        level by level and every depth step of every (view, branch) lane.  A phase is a list
 //                        of independent work items cut into tiles; each CTA owns a cost-balanced contiguous tile
@@ -27,7 +27,8 @@ namespace {
 // i / 255 in float64 (the reference divides a uint8 array by the python int 255, bbox_augmentation.py:267)
 __device__ const double g_div255[256] = {0.0 / 255.0, 1.0 / 255.0, 2.0 / 255.0, 3.0 / 255.0, 4.0 / 255.0, 5.0 / 255.0, 6.0 / 255.0, 7.0 / 255.0, 8.0 / 255.0, 9.0 / 255.0, 10.0 / 255.0, 11.0 / 255.0, 12.0 / 255.0, 13.0 / 255.0, 14.0 / 255.0, 15.0 / 255.0, 16.0 / 255.0, 17.0 / 255.0, 18.0 / 255.0, 19.0 / 255.0, 20.0 / 255.0, 21.0 / 255.0, 22.0 / 255.0, 23.0 / 255.0, 24.0 / 255.0, 25.0 / 255.0, 26.0 / 255.0, 27.0 / 255.0, 28.0 / 255.0, 29.0 / 255.0, 30.0 / 255.0, 31.0 / 255.0, 32.0 / 255.0, 33.0 / 255.0, 34.0 / 255.0, 35.0 / 255.0, 36.0 / 255.0, 37.0 / 255.0, 38.0 / 255.0, 39.0 / 255.0, 40.0 / 255.0, 41.0 / 255.0, 42.0 / 255.0, 43.0 / 255.0, 44.0 / 255.0, 45.0 / 255.0, 46.0 / 255.0, 47.0 / 255.0, 48.0 / 255.0, 49.0 / 255.0, 50.0 / 255.0, 51.0 / 255.0, 52.0 / 255.0, 53.0 / 255.0, 54.0 / 255.0, 55.0 / 255.0, 56.0 / 255.0, 57.0 / 255.0, 58.0 / 255.0, 59.0 / 255.0, 60.0 / 255.0, 61.0 / 255.0, 62.0 / 255.0, 63.0 / 255.0, 64.0 / 255.0, 65.0 / 255.0, 66.0 / 255.0, 67.0 / 255.0, 68.0 / 255.0, 69.0 / 255.0, 70.0 / 255.0, 71.0 / 255.0, 72.0 / 255.0, 73.0 / 255.0, 74.0 / 255.0, 75.0 / 255.0, 76.0 / 255.0, 77.0 / 255.0, 78.0 / 255.0, 79.0 / 255.0, 80.0 / 255.0, 81.0 / 255.0, 82.0 / 255.0, 83.0 / 255.0, 84.0 / 255.0, 85.0 / 255.0, 86.0 / 255.0, 87.0 / 255.0, 88.0 / 255.0, 89.0 / 255.0, 90.0 / 255.0, 91.0 / 255.0, 92.0 / 255.0, 93.0 / 255.0, 94.0 / 255.0, 95.0 / 255.0, 96.0 / 255.0, 97.0 / 255.0, 98.0 / 255.0, 99.0 / 255.0, 100.0 / 255.0, 101.0 / 255.0, 102.0 / 255.0, 103.0 / 255.0, 104.0 / 255.0, 105.0 / 255.0, 106.0 / 255.0, 107.0 / 255.0, 108.0 / 255.0, 109.0 / 255.0, 110.0 / 255.0, 111.0 / 255.0, 112.0 / 255.0, 113.0 / 255.0, 114.0 / 255.0, 115.0 / 255.0, 116.0 / 255.0, 117.0 / 255.0, 118.0 / 255.0, 119.0 / 255.0, 120.0 / 255.0, 121.0 / 255.0, 122.0 / 255.0, 123.0 / 255.0, 124.0 / 255.0, 125.0 / 255.0, 126.0 / 255.0, 127.0 / 255.0, 128.0 / 255.0, 129.0 / 255.0, 130.0 / 255.0, 131.0 / 255.0, 132.0 / 255.0, 133.0 / 255.0, 134.0 / 255.0, 135.0 / 255.0, 136.0 / 255.0, 137.0 / 255.0, 138.0 / 255.0, 139.0 / 255.0, 140.0 / 255.0, 141.0 / 255.0, 142.0 / 255.0, 143.0 / 255.0, 144.0 / 255.0, 145.0 / 255.0, 146.0 / 255.0, 147.0 / 255.0, 148.0 / 255.0, 149.0 / 255.0, 150.0 / 255.0, 151.0 / 255.0, 152.0 / 255.0, 153.0 / 255.0, 154.0 / 255.0, 155.0 / 255.0, 156.0 / 255.0, 157.0 / 255.0, 158.0 / 255.0, 159.0 / 255.0, 160.0 / 255.0, 161.0 / 255.0, 162.0 / 255.0, 163.0 / 255.0, 164.0 / 255.0, 165.0 / 255.0, 166.0 / 255.0, 167.0 / 255.0, 168.0 / 255.0, 169.0 / 255.0, 170.0 / 255.0, 171.0 / 255.0, 172.0 / 255.0, 173.0 / 255.0, 174.0 / 255.0, 175.0 / 255.0, 176.0 / 255.0, 177.0 / 255.0, 178.0 / 255.0, 179.0 / 255.0, 180.0 / 255.0, 181.0 / 255.0, 182.0 / 255.0, 183.0 / 255.0, 184.0 / 255.0, 185.0 / 255.0, 186.0 / 255.0, 187.0 / 255.0, 188.0 / 255.0, 189.0 / 255.0, 190.0 / 255.0, 191.0 / 255.0, 192.0 / 255.0, 193.0 / 255.0, 194.0 / 255.0, 195.0 / 255.0, 196.0 / 255.0, 197.0 / 255.0, 198.0 / 255.0, 199.0 / 255.0, 200.0 / 255.0, 201.0 / 255.0, 202.0 / 255.0, 203.0 / 255.0, 204.0 / 255.0, 205.0 / 255.0, 206.0 / 255.0, 207.0 / 255.0, 208.0 / 255.0, 209.0 / 255.0, 210.0 / 255.0, 211.0 / 255.0, 212.0 / 255.0, 213.0 / 255.0, 214.0 / 255.0, 215.0 / 255.0, 216.0 / 255.0, 217.0 / 255.0, 218.0 / 255.0, 219.0 / 255.0, 220.0 / 255.0, 221.0 / 255.0, 222.0 / 255.0, 223.0 / 255.0, 224.0 / 255.0, 225.0 / 255.0, 226.0 / 255.0, 227.0 / 255.0, 228.0 / 255.0, 229.0 / 255.0, 230.0 / 255.0, 231.0 / 255.0, 232.0 / 255.0, 233.0 / 255.0, 234.0 / 255.0, 235.0 / 255.0, 236.0 / 255.0, 237.0 / 255.0, 238.0 / 255.0, 239.0 / 255.0, 240.0 / 255.0, 241.0 / 255.0, 242.0 / 255.0, 243.0 / 255.0, 244.0 / 255.0, 245.0 / 255.0, 246.0 / 255.0, 247.0 / 255.0, 248.0 / 255.0, 249.0 / 255.0, 250.0 / 255.0, 251.0 / 255.0, 252.0 / 255.0, 253.0 / 255.0, 254.0 / 255.0, 255.0 / 255.0};
 
-constexpr int kCT = 1024;  // threads per CTA of the chain kernel (64 registers each: the whole register file)
+constexpr int kCT = 256;     // threads per CTA of the chain kernel
+constexpr int kCtaPerSm = 4; // independent CTAs per SM (64 registers per thread): tiles of different kinds overlap on an SM
 
 struct RegOp {      // op parameters of one region, staged in shared memory for per-pixel tiles
   int32_t kind, p0, p1;
@@ -45,14 +46,19 @@ struct BboStage {    // one bbo job staged for the CTA (bbo_r_segment / bbo_c_se
 };
 
 struct ChainSmem {
+  int next_tile;       // the CTA's next claimed tile of the current phase
+  int cand[16];        // mask tiles: the gt boxes whose support meets the tile
+  int step_class;      // measurement aid: class of the last step tile (7 stream, 8 staged bg, 9 mixed / per pixel)
+  int prof_ready;      // u.prof holds the profile slices of the staged blend job
+  int bs_key;          // which bbo job `bs` (and, for blends, the profile slices in u.prof) currently holds; -1 = none
   ChainArgs args;      // the kernel arguments, copied once: the (non-inlined) handlers read them from shared memory
   BboStage bs;
   union {
-    unsigned hist[8][768];   // histogram tiles: 8 privatised copies (4 warps share one)
-    float prof[6144];        // bbo jobs: the support's slices of the two mask profiles
+    unsigned hist[2][768];   // histogram tiles: 2 privatised copies (4 warps share one)
+    float prof[3072];        // bbo jobs: the support's slices of the two mask profiles
     struct {
-      double K[3073];        // profile tiles: exclusive prefix sums of the gaussian kernel
-      float p[2048];         //                low-res blurred profile
+      double K[1537];        // profile tiles: exclusive prefix sums of the gaussian kernel
+      float p[1024];         //                low-res blurred profile
     } g;
   } u;
   __align__(16) uint8_t lut[OADG_MAX_REGIONS * 768];
@@ -104,6 +110,7 @@ __device__ __noinline__ void profile_tile(const ChainArgs& A, ChainSmem& S, int 
   float* out = (axis == 0 ? A.prof_x + (size_t)g * P.max_w : A.prof_y + (size_t)g * P.max_h);
   const int tid = threadIdx.x;
   __syncthreads();  // the shared buffers may still be in use by the previous tile
+  if (tid == 0) S.bs_key = -1;   // u.g overwrites the staged profile slices
   if (n_lo <= 0) {
     for (int d = tid; d < n_hi; d += kCT) out[d] = 0.f;
     return;
@@ -133,7 +140,7 @@ __device__ __noinline__ void profile_tile(const ChainArgs& A, ChainSmem& S, int 
     }
     __syncthreads();
     for (int off = 1; off <= ks; off <<= 1) {  // Hillis-Steele inclusive scan over K[0..ks]
-      double v[4];
+      double v[8];
       int n = 0;
       for (int i = tid; i <= ks; i += kCT, ++n) v[n] = i >= off ? K[i] + K[i - off] : K[i];
       __syncthreads();
@@ -192,13 +199,64 @@ __device__ __noinline__ void profile_tile(const ChainArgs& A, ChainSmem& S, int 
 }
 
 // union of the blurred gt masks of a view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260) as float32 and as
-// uint8(mask*255): written once per batch, read by every bg-only op.  Tile = 256 x 32 px, 8 rows per thread.
-__device__ __noinline__ void mask_tile(const ChainArgs& A, int view, int local, int tx) {
-  const oadg_view_t& V = A.P.views[view];
-  const int x = (local % tx) * kMaskTileW + (threadIdx.x & 255);
-  const int yb = (local / tx) * kMaskTileH + (threadIdx.x >> 8) * 8;
-  if (x >= V.W) return;
-  for (int y = yb; y < min(yb + 8, V.H); ++y) mask_pixel(A.P, view, x, y, A.maskf, A.masku);
+// uint8(mask*255): written once per batch, read by every bg-only op.  Tile = 256 x 8 px, one column x 8 rows per
+// thread; the boxes whose support meets the tile are listed once per tile, and a thread keeps the x-profile value of
+// each listed box for its column in registers.
+__device__ __noinline__ void mask_tile(const ChainArgs& A, ChainSmem& S, int view, int local, int tx) {
+  const DevPlan& P = A.P;
+  const oadg_view_t& V = P.views[view];
+  const int x0 = (local % tx) * kMaskTileW, y0 = (local / tx) * kMaskTileH;
+  const int x1 = min(x0 + kMaskTileW, V.W), y1 = min(y0 + kMaskTileH, V.H);
+  __syncthreads();
+  if (threadIdx.x < 32) {  // lane k tests box k (+32, ...): one round trip instead of a serial walk
+    if (threadIdx.x == 0) S.bs_key = -1;   // bs.excl is reused below
+    int n = 0;
+    for (int k0 = 0; k0 < V.n_gt; k0 += 32) {
+      const int k = k0 + threadIdx.x;
+      int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      bool hit = false;
+      if (k < V.n_gt) {
+        const int32_t* s = P.gts[V.gt_first + k].supp;
+        s0 = s[0]; s1 = s[1]; s2 = s[2]; s3 = s[3];
+        hit = s0 < x1 && s2 > x0 && s1 < y1 && s3 > y0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      const int slot = n + __popc(bal & ((1u << threadIdx.x) - 1u));
+      if (hit && slot < 16) {
+        S.bs.excl[slot][0] = s0; S.bs.excl[slot][1] = s1; S.bs.excl[slot][2] = s2; S.bs.excl[slot][3] = s3;
+        S.cand[slot] = V.gt_first + k;
+      }
+      n += __popc(bal);
+    }
+    if (threadIdx.x == 0) S.bs.n_excl = n;
+  }
+  __syncthreads();
+  const int n = S.bs.n_excl;
+  const int x = x0 + (threadIdx.x & 255);
+  const int yb = y0;
+  if (x >= x1) return;
+  const size_t base = (size_t)view * P.mask_stride;
+  if (n > 8) {  // many overlapping boxes: the plain per-pixel walk
+    for (int y = yb; y < min(yb + 8, y1); ++y) mask_pixel(P, view, x, y, A.maskf, A.masku);
+    return;
+  }
+  float ux[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    ux[c] = (c < n && x >= S.bs.excl[c][0] && x < S.bs.excl[c][2]) ? A.prof_x[(size_t)S.cand[c] * P.max_w + x] : -1.f;
+  for (int y = yb; y < min(yb + 8, y1); ++y) {
+    float m = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < n && ux[c] >= 0.f && y >= S.bs.excl[c][1] && y < S.bs.excl[c][3]) {
+        const float v = fmul(A.prof_y[(size_t)S.cand[c] * P.max_h + y], ux[c]);
+        m = v > m ? v : m;
+      }
+    }
+    const size_t o = base + (size_t)y * V.W + x;
+    A.maskf[o] = m;
+    A.masku[o] = (uint8_t)mask_to_u8(m);
+  }
 }
 
 // per-channel histogram + luma sum of a lane's input frame (PIL Image.histogram()); tile = 32768 px (linear)
@@ -207,7 +265,7 @@ __device__ __noinline__ void hist_tile(const Lane& L, ChainSmem& S, int local, u
   const size_t npx = (size_t)L.H * L.W;
   const size_t p0 = (size_t)local * kHistTilePx;
   const size_t p1 = p0 + kHistTilePx < npx ? p0 + kHistTilePx : npx;
-  unsigned* my = S.u.hist[(tid >> 5) & 7];
+  unsigned* my = S.u.hist[(tid >> 5) & 1];
   if ((((uintptr_t)L.in) & 15) == 0) {
     // 16 px = 48 B = 3 x uint4 per iteration: the channel of byte k is k % 3 at a compile-time phase
     const size_t c1 = p1 / kChunkPx;
@@ -244,7 +302,8 @@ __device__ __noinline__ void hist_tile(const Lane& L, ChainSmem& S, int local, u
 }
 __device__ __noinline__ void hist_begin(ChainSmem& S) {
   __syncthreads();
-  for (int i = threadIdx.x; i < 8 * 768; i += kCT) (&S.u.hist[0][0])[i] = 0;
+  if (threadIdx.x == 0) S.bs_key = -1;   // u.hist overwrites the staged profile slices
+  for (int i = threadIdx.x; i < 2 * 768; i += kCT) (&S.u.hist[0][0])[i] = 0;
   __syncthreads();
 }
 __device__ __noinline__ void hist_flush(const ChainArgs& A, ChainSmem& S, int slot, unsigned long long& lsum) {
@@ -253,7 +312,7 @@ __device__ __noinline__ void hist_flush(const ChainArgs& A, ChainSmem& S, int sl
   for (int i = threadIdx.x; i < 768; i += kCT) {
     unsigned s = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += S.u.hist[w][i];
+    for (int w = 0; w < 2; ++w) s += S.u.hist[w][i];
     if (s) atomicAdd(dst + i, s);
   }
   lsum = warp_sum(lsum);
@@ -270,9 +329,12 @@ __device__ __noinline__ void lut_tile(const ChainArgs& A, ChainSmem& S, int job)
   const int tid = threadIdx.x;
   __syncthreads();
   if (op.kind == OADG_OP_AUTOCONTRAST || op.kind == OADG_OP_EQUALIZE) {
-    // 3 channels x 256 entries; the sequential scans are tiny: one thread per channel
+    // 3 channels x 256 entries: the histogram goes to shared memory first, then one thread per channel scans it
+    if (tid == 0) S.bs_key = -1;   // u.hist overwrites the staged profile slices
+    for (int i = tid; i < 768; i += kCT) S.u.hist[0][i] = A.hist[(size_t)J.hist_slot * 768 + i];
+    __syncthreads();
     if (tid < 3) {
-      const unsigned* h = A.hist + (size_t)J.hist_slot * 768 + tid * 256;
+      const unsigned* h = S.u.hist[0] + tid * 256;
       if (op.kind == OADG_OP_AUTOCONTRAST) lut_autocontrast_ch(h, S.tab[tid]);
       else lut_equalize_ch(h, S.tab[tid]);
     }
@@ -320,12 +382,12 @@ __device__ __noinline__ void copy_segment(const Chain& C, size_t nbytes, bool bo
 
 // ---- staged affine gathers ---------------------------------------------------------------------------------
 // Both geometric op families (bboxes-only blends and bg-only ops) resample a frame through cv::warpAffine's
-// fixed-point bilinear map.  A CTA works on sub-tiles of 128 x 32 output pixels: the source rectangle the sub-tile
+// fixed-point bilinear map.  A CTA works on sub-tiles of 64 x 16 output pixels: the source rectangle the sub-tile
 // reads (exact: the map is monotone in x and in y, so its extremes sit at the sub-tile corners) is copied into
 // shared memory with 16-byte vector loads of whole row spans, then every thread resamples 4 consecutive pixels
 // from shared memory and writes 12 bytes.  Out-of-frame taps read 0 (BORDER_CONSTANT).
-constexpr int kSubW = 128, kSubH = 32;
-constexpr int kDynSmem = 160 * 1024;
+constexpr int kSubW = 64, kSubH = 16;
+constexpr int kDynSmem = 30 * 1024;
 
 struct StageView {
   const uint8_t* sm;   // staged rows: row r holds the 16-byte aligned global span that covers source row by0 + r
@@ -361,17 +423,13 @@ __device__ __forceinline__ bool warp_src_rect(const double* m, int x0, int y0, i
 }
 __device__ __forceinline__ int stage_pitch(int bx0, int bx1, int C) { return (15 + (bx1 - bx0) * C + 15) & ~15; }
 // copy source rows [by0,by1) x [bx0,bx1) of a C-byte-per-pixel frame into shared memory (all threads)
-__device__ __noinline__ void stage_rows(StageView& v, uint8_t* sm, const uint8_t* base, int W, int H, int C, const int r[4]) {
-  v.sm = sm;
-  v.bx0 = r[0]; v.by0 = r[1]; v.bx1 = r[2]; v.by1 = r[3];
-  v.W = W; v.H = H; v.C = C;
-  v.lo = (uint32_t)(uintptr_t)base;
-  v.pitch = stage_pitch(r[0], r[2], C);
-  const int vpr = v.pitch >> 4, rows = r[3] - r[1];
+__device__ __noinline__ void stage_rows(uint8_t* sm, int pitch, const uint8_t* base, int W, int H, int C, int bx0, int by0,
+                                        int rows) {
+  const int vpr = pitch >> 4;
   const uint8_t* end = base + (size_t)H * W * C;
   for (int i = threadIdx.x; i < rows * vpr; i += kCT) {
     const int rr = i / vpr, vv = i - rr * vpr;
-    const uint8_t* g = base + ((size_t)(r[1] + rr) * W + r[0]) * C;
+    const uint8_t* g = base + ((size_t)(by0 + rr) * W + bx0) * C;
     const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)15) + vv * 16;
     uint4 val;
     if (ga >= base && ga + 16 <= end) {
@@ -382,8 +440,17 @@ __device__ __noinline__ void stage_rows(StageView& v, uint8_t* sm, const uint8_t
         if (ga + k >= base && ga + k < end) w[k >> 2] |= (uint32_t)ga[k] << ((k & 3) * 8);
       val = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    *reinterpret_cast<uint4*>(sm + (size_t)rr * v.pitch + vv * 16) = val;
+    *reinterpret_cast<uint4*>(sm + (size_t)rr * pitch + vv * 16) = val;
   }
+}
+__device__ __forceinline__ StageView make_view(uint8_t* sm, const uint8_t* base, int W, int H, int C, const int r[4]) {
+  StageView v;
+  v.sm = sm;
+  v.bx0 = r[0]; v.by0 = r[1]; v.bx1 = r[2]; v.by1 = r[3];
+  v.W = W; v.H = H; v.C = C;
+  v.lo = (uint32_t)(uintptr_t)base;
+  v.pitch = stage_pitch(r[0], r[2], C);
+  return v;
 }
 // first byte of source pixel (sx, sy) in the staged rows (the pixel must lie inside the staged rectangle)
 __device__ __forceinline__ const uint8_t* staged_px(const StageView& v, int sx, int sy) {
@@ -425,7 +492,12 @@ __device__ __forceinline__ int byte_of(const uint32_t w[3], int k) { return (int
 // ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
 __device__ __noinline__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
   __syncthreads();
+  const int key = I.obj * 2 + (catch_up ? 1 : 0);
+  if (S.bs_key == key) return;   // the job is still staged from this CTA's previous tile (uniform: S.bs_key is shared)
+  __syncthreads();
   if (threadIdx.x == 0) {
+    S.bs_key = key;
+    S.prof_ready = 0;
     const BboJob J = A.bjobs[I.obj];
     const Chain C = A.chains[J.chain];
     const oadg_view_t& V = A.P.views[C.view];
@@ -445,7 +517,7 @@ __device__ __noinline__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const I
   }
   __syncthreads();
 }
-// blend of one box: tiles [l0, l1) of 128 x 32 px; Y = uint8(X*(1-m) + warp(X)*m) inside the support
+// blend of one box: tiles [l0, l1) of 64 x 16 px; Y = uint8(X*(1-m) + warp(X)*m) inside the support
 __device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
   bbo_stage(A, S, I, false);
   const BboStage& bs = S.bs;
@@ -464,10 +536,12 @@ __device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
   }
   const int W = bs.W, H = bs.H;
   const int w = bs.rect[2] - bs.rect[0], h = bs.rect[3] - bs.rect[1];
-  const bool prof_smem = w + h <= 6144;
-  if (prof_smem) {
+  const bool prof_smem = w + h <= 3072;
+  if (prof_smem && !S.prof_ready) {
     for (int i = t; i < w; i += kCT) S.u.prof[i] = A.prof_x[(size_t)bs.gt * A.P.max_w + bs.rect[0] + i];
     for (int i = t; i < h; i += kCT) S.u.prof[w + i] = A.prof_y[(size_t)bs.gt * A.P.max_h + bs.rect[1] + i];
+    __syncthreads();
+    if (t == 0) S.prof_ready = 1;
   }
   const bool vec = ((W * 3) & 3) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 3) == 0;
   const int ax0 = bs.rect[0] & ~3, tx = I.tx;
@@ -476,13 +550,12 @@ __device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
     const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
     int sr[4];
     const bool any_src = warp_src_rect(bs.minv, x0, ty0, x1, y1, W, H, sr);
-    StageView sv;
-    sv.W = W; sv.H = H; sv.C = 3; sv.sm = dyn; sv.pitch = 16; sv.bx0 = sv.by0 = sv.bx1 = sv.by1 = 0; sv.lo = 0;
-    const bool staged = any_src && (size_t)(sr[3] - sr[1]) * stage_pitch(sr[0], sr[2], 3) <= (size_t)kDynSmem && !(A.debug & 2);
+    const StageView sv = make_view(dyn, bs.X, W, H, 3, sr);
+    const bool staged = any_src && (size_t)(sr[3] - sr[1]) * sv.pitch <= (size_t)kDynSmem && !(A.debug & 2);
     __syncthreads();  // the previous tile's gathers are done (and the profile slices are in place)
-    if (staged) stage_rows(sv, dyn, bs.X, W, H, 3, sr);
+    if (staged) stage_rows(dyn, sv.pitch, bs.X, W, H, 3, sr[0], sr[1], sr[3] - sr[1]);
     __syncthreads();
-    const int y = ty0 + (t >> 5), xg = tx0 + (t & 31) * 4;
+    const int y = ty0 + (t >> 4), xg = tx0 + (t & 15) * 4;
     if (y >= y1 || xg >= x1 || xg + 4 <= x0) continue;
     const size_t o = ((size_t)y * W + xg) * 3;
     const bool full = xg >= x0 && xg + 4 <= x1;
@@ -551,7 +624,7 @@ __device__ __noinline__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, con
   for (int k = l0; k < l1; ++k) {
     const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
     const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
-    const int y = ty0 + (t >> 5), xg = tx0 + (t & 31) * 4;
+    const int y = ty0 + (t >> 4), xg = tx0 + (t & 15) * 4;
     if (y >= y1 || xg >= x1 || xg + 4 <= x0) continue;
     const size_t o = ((size_t)y * W + xg) * 3;
     // does a next-level support touch this 4-px group?
@@ -611,10 +684,10 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
   q[2] = (uint8_t)px[2];
 }
 
-// bg-only op (bbox_augmentation.py:240-272) on a sub-tile of 128 x 32 px that one region covers: the frame and the
+// bg-only op (bbox_augmentation.py:240-272) on a sub-tile of 64 x 16 px that one region covers: the frame and the
 // uint8 union mask are both warped from staged shared-memory rows; 4 pixels per thread.
-__device__ __noinline__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int x0, int y0, int x1,
-                           int y1, const double* div255) {
+__device__ __noinline__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int r_only, int x0,
+                                        int y0, int x1, int y1, const double* div255) {
   const DevPlan& P = A.P;
   const int W = L.W, H = L.H, t = threadIdx.x;
   int sr[4];
@@ -622,36 +695,41 @@ __device__ __noinline__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const 
   const int pitch_i = any_src ? stage_pitch(sr[0], sr[2], 3) : 0, pitch_m = any_src ? stage_pitch(sr[0], sr[2], 1) : 0;
   const int rows = any_src ? sr[3] - sr[1] : 0;
   const bool staged = any_src && (size_t)rows * (pitch_i + pitch_m) <= (size_t)kDynSmem;
-  StageView si, sm;
-  si.W = sm.W = W; si.H = sm.H = H; si.C = 3; sm.C = 1;
-  si.sm = sm.sm = dyn; si.pitch = sm.pitch = 16; si.bx0 = si.by0 = si.bx1 = si.by1 = sm.bx0 = sm.by0 = sm.bx1 = sm.by1 = 0;
-  si.lo = sm.lo = 0;
   const uint8_t* mu = P.masku + (size_t)L.view * P.mask_stride;
-  __syncthreads();  // the previous sub-tile's gathers are done
-  if (staged) {
-    stage_rows(si, dyn, L.in, W, H, 3, sr);
-    stage_rows(sm, dyn + (size_t)rows * pitch_i, mu, W, H, 1, sr);
-  }
-  __syncthreads();
-  const int y = y0 + (t >> 5), xg = x0 + (t & 31) * 4;
-  if (y >= y1 || xg >= x1) return;
-  const int n = imin(4, x1 - xg);
+  const StageView si = make_view(dyn, L.in, W, H, 3, sr);
+  const StageView sm = make_view(dyn + (size_t)rows * pitch_i, mu, W, H, 1, sr);
+  // this thread's 4 pixels: the frame bytes and the float mask are requested before the staging barriers
+  const int y = y0 + (t >> 4), xg = x0 + (t & 15) * 4;
+  const bool active = y < y1 && xg < x1;
+  const int n = active ? imin(4, x1 - xg) : 0;
   const size_t o = ((size_t)y * W + xg) * 3;
   const bool vec = n == 4 && ((W * 3) & 3) == 0 && ((((uintptr_t)L.in) | ((uintptr_t)L.out)) & 3) == 0;
-  uint32_t in_w[3], out_w[3] = {0u, 0u, 0u};
-  load12(L.in + o, vec, n, in_w);
-  const float* mf = P.maskf + (size_t)L.view * P.mask_stride + (size_t)y * W + xg;
+  uint32_t in_w[3] = {0u, 0u, 0u}, out_w[3] = {0u, 0u, 0u};
   float Mv[4] = {0.f, 0.f, 0.f, 0.f};
-  if (n == 4 && (W & 3) == 0) {
-    const float4 q = *reinterpret_cast<const float4*>(mf);
-    Mv[0] = q.x; Mv[1] = q.y; Mv[2] = q.z; Mv[3] = q.w;
-  } else {
-    for (int i = 0; i < n; ++i) Mv[i] = mf[i];
+  if (active) {
+    load12(L.in + o, vec, n, in_w);
+    const float* mf = P.maskf + (size_t)L.view * P.mask_stride + (size_t)y * W + xg;
+    if (n == 4 && (((uintptr_t)mf) & 15) == 0) {
+      const float4 q = *reinterpret_cast<const float4*>(mf);
+      Mv[0] = q.x; Mv[1] = q.y; Mv[2] = q.z; Mv[3] = q.w;
+    } else {
+      for (int i = 0; i < n; ++i) Mv[i] = mf[i];
+    }
   }
+  __syncthreads();  // the previous sub-tile's gathers are done
+  if (staged) {
+    stage_rows(dyn, pitch_i, L.in, W, H, 3, sr[0], sr[1], rows);
+    stage_rows(dyn + (size_t)rows * pitch_i, pitch_m, mu, W, H, 1, sr[0], sr[1], rows);
+  }
+  __syncthreads();
+  if (!active) return;
+  unsigned keep_mask = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int px[3] = {0, 0, 0};
-    if (i < n) {
+    const bool mine = i < n && (r_only < 0 || region_of_pixel(L, xg + i, y) == r_only);
+    if (mine) {
+      keep_mask |= 1u << i;
       const int x = xg + i;
       int sx, sy, fx, fy, wm = 0;
       warp_coord(R.minv, x, y, sx, sy, fx, fy);
@@ -682,16 +760,61 @@ __device__ __noinline__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const 
 #pragma unroll
     for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)px[c] << (((3 * i + c) & 3) * 8);
   }
-  if (vec) {
+  if (vec && keep_mask == 15u) {
     uint32_t* q = reinterpret_cast<uint32_t*>(L.out + o);
     q[0] = out_w[0]; q[1] = out_w[1]; q[2] = out_w[2];
   } else {
-    for (int k = 0; k < 3 * n; ++k) L.out[o + k] = (uint8_t)byte_of(out_w, k);
+    for (int i = 0; i < 4; ++i)
+      if (keep_mask >> i & 1)
+        for (int c = 0; c < 3; ++c) L.out[o + 3 * i + c] = (uint8_t)byte_of(out_w, 3 * i + c);
   }
 }
 
+// one pixel of a non-bg op from the staged lane record, region op and LUTs (same arithmetic as eval_op, oamix_body.h)
+__device__ __forceinline__ void pixel_op_fast(const ChainArgs& A, const Lane& L, const RegOp& R, const uint8_t* luts,
+                                              int r, int x, int y) {
+  const int W = L.W, H = L.H;
+  const size_t o = ((size_t)y * W + x) * 3;
+  uint8_t* q = L.out + o;
+  const int kind = R.kind;
+  if (kind == OADG_OP_BBO_AFFINE) {
+    const uint8_t* s = (L.scratch[r] >= 0 ? A.scratch + (size_t)L.scratch[r] * A.frame_bytes : L.in) + o;
+    q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+    return;
+  }
+  const int v0 = L.in[o], v1 = L.in[o + 1], v2 = L.in[o + 2];
+  int out[3] = {v0, v1, v2};
+  if (is_lut_kind(kind)) {
+    const uint8_t* lut = luts + r * 768;
+    out[0] = lut[v0]; out[1] = lut[256 + v1]; out[2] = lut[512 + v2];
+  } else if (kind == OADG_OP_INVERT) {
+    const int xs = x - R.p0, ys = y - R.p1;
+    if ((unsigned)xs < (unsigned)W && (unsigned)ys < (unsigned)H) {
+      const uint8_t* p = L.in + ((size_t)ys * W + xs) * 3;
+      out[0] = (-(int)p[0]) & 255; out[1] = (-(int)p[1]) & 255; out[2] = (-(int)p[2]) & 255;
+    } else {
+      out[0] = out[1] = out[2] = 0;
+    }
+  } else if (kind == OADG_OP_COLOR) {
+    const int deg = pil_luma(v0, v1, v2);
+    out[0] = pil_blend(deg, v0, R.factor); out[1] = pil_blend(deg, v1, R.factor); out[2] = pil_blend(deg, v2, R.factor);
+  } else if (kind == OADG_OP_SHARPNESS) {
+    if (x == 0 || y == 0 || x == W - 1 || y == H - 1) {  // SMOOTH copies the border
+      for (int c = 0; c < 3; ++c) out[c] = pil_blend(out[c], out[c], R.factor);
+    } else {
+      for (int c = 0; c < 3; ++c) {
+        int nb[9];
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) nb[dy * 3 + dx] = L.in[((size_t)(y + 1 - dy) * W + (x - 1 + dx)) * 3 + c];
+        out[c] = pil_blend(pil_smooth9(nb), out[c], R.factor);
+      }
+    }
+  }
+  q[0] = (uint8_t)out[0]; q[1] = (uint8_t)out[1]; q[2] = (uint8_t)out[2];
+}
+
 // ------------------------------------------------------------------------------------
-// one 256 x 64 tile of one depth step of one lane (oa_mix.py:226-234).  Runs of 16 pixels that one table-lookup /
+// one 256 x 16 tile of one depth step of one lane (oa_mix.py:226-234).  Runs of 16 pixels that one table-lookup /
 // bbo-copy region covers move as three 16-byte vectors per thread (LUTs in shared memory); everything else (bg-only
 // gathers, invert / colour / sharpness, runs cut by a multi-level box edge) is evaluated per pixel with consecutive
 // lanes on consecutive pixels (run_is_stream, oamix_tile.h, decides which pass owns a run).
@@ -704,11 +827,25 @@ __device__ __noinline__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
   const int region = tile_region(L, x0, y0, x1, y1);
   const bool tile_stream = region >= 0 && kind_streams(L.kind[region]);
   const bool tile_pixel = region >= 0 && !tile_stream;
-  if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE && !(A.debug & 1)) {  // uniform bg-only tile: staged gathers
-    for (int sy0 = y0; sy0 < y1; sy0 += kSubH)
-      for (int sx0 = x0; sx0 < x1; sx0 += kSubW)
-        bg_subtile(A, dyn, L, S.rop[region], sx0, sy0, min(sx0 + kSubW, x1), min(sy0 + kSubH, y1), div255);
-    return;
+  if (t == 0) S.step_class = tile_stream ? 7 : ((tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) ? 8 : 9);
+  const bool staged_bg = !(A.debug & 1);
+  if (!tile_stream && staged_bg) {
+    // bg-only regions of the tile: staged gathers, sub-tile by sub-tile (a mixed tile filters by region per pixel)
+    for (int r = 0; r <= L.n_ml; ++r) {
+      if (S.rop[r].kind != OADG_OP_BG_AFFINE) continue;
+      if (tile_pixel && r != region) continue;
+      for (int sy0 = y0; sy0 < y1; sy0 += kSubH)
+        for (int sx0 = x0; sx0 < x1; sx0 += kSubW) {
+          const int sx1 = min(sx0 + kSubW, x1), sy1 = min(sy0 + kSubH, y1);
+          if (!tile_pixel) {  // skip sub-tiles that hold no pixel of region r
+            const int sub = tile_region(L, sx0, sy0, sx1, sy1);
+            if (sub >= 0 && sub != r) continue;
+            if (r < L.n_ml && !rect_hit(L.box[r], sx0, sy0, sx1, sy1)) continue;
+          }
+          bg_subtile(A, dyn, L, S.rop[r], tile_pixel ? -1 : r, sx0, sy0, sx1, sy1, div255);
+        }
+    }
+    if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) return;
   }
   if (!tile_pixel) {
     const int x = x0 + (t & 15) * kChunkPx, y = y0 + (t >> 4);
@@ -723,7 +860,10 @@ __device__ __noinline__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
           chunk_load(stream_src(L, reg, A.scratch, A.frame_bytes) + ((size_t)y * W + x) * 3, n, vec, c);
           stream_chunk(L, reg, S.lut + reg * 768, A.scratch, A.frame_bytes, c, x, y, n, vec);
         } else {
-          for (int i = 0; i < n; ++i) stream_pixel(L, S.lut, A.scratch, A.frame_bytes, x + i, y);
+          for (int i = 0; i < n; ++i) {
+            const int rr = region_of_pixel(L, x + i, y);
+            pixel_op_fast(A, L, S.rop[rr], S.lut, rr, x + i, y);
+          }
         }
       }
     }
@@ -741,18 +881,19 @@ __device__ __noinline__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
         bx[r] = cv_round(dmul(dmul(S.rop[r].minv[3], (double)x), 1024.0));
       }
     }
-    const int yb = y0 + (t >> 8) * 16, ye = min(yb + 16, y1);
+    const int yb = y0, ye = y1;
 #pragma unroll 1
     for (int y = yb; y < ye; ++y) {
       int run_region;
       if (run_is_stream(L, xc, y, nc, run_region)) continue;  // the vector pass owns this run
       const int r = region_of_pixel(L, x, y);
       if (S.rop[r].kind == OADG_OP_BG_AFFINE) {
+        if (staged_bg) continue;  // done above from staged rows
         const int axr = r == 0 ? ax[0] : (r == 1 ? ax[1] : ax[2]);
         const int bxr = r == 0 ? bx[0] : (r == 1 ? bx[1] : bx[2]);
         bg_pixel_fast(A.P, L, S.rop[r], axr, bxr, div255, x, y);
       } else {
-        step_pixel(A.P, L, A.scratch, A.frame_bytes, x, y);
+        pixel_op_fast(A, L, S.rop[r], S.lut, r, x, y);
       }
     }
   }
@@ -784,33 +925,40 @@ __device__ __noinline__ void stage_lane(const ChainArgs& A, ChainSmem& S, int la
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kCT, 1)
+__global__ void __launch_bounds__(kCT, kCtaPerSm)
 oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
   __shared__ ChainSmem S;
   extern __shared__ __align__(16) uint8_t dyn[];   // kDynSmem bytes: staged source rows of the affine gathers
-  if (threadIdx.x == 0) S.args = Aparam;
+  if (threadIdx.x == 0) {
+    S.args = Aparam;
+    S.bs_key = -1;
+    S.prof_ready = 0;
+    if (blockIdx.x == 0) Aparam.phase_ts[0] = globaltimer_ns();
+  }
   __syncthreads();
   const ChainArgs& A = S.args;
   const int b = blockIdx.x, G = gridDim.x;
   int staged_lane = -1;
   for (int p = 0; p < A.n_phases; ++p) {
     const Phase ph = A.phases[p];
-    const int32_t* rg = A.ranges + ((size_t)p * (G + 1) + b) * 2;
-    const int t0 = rg[0], t1 = rg[2];
-    int it = rg[1];
+    int it = ph.item0;
     const int it_end = ph.item0 + ph.n_items;
-    int tile = t0;
-    while (tile < t1) {  // one segment = this CTA's tiles [l0, l1) of one item
+    // dynamic tile claims: thread 0 fetches the next index while the CTA works on the current tile
+    if (threadIdx.x == 0) S.next_tile = (int)atomicAdd(A.tile_ctr + p, 1u);
+    __syncthreads();
+    int tile = S.next_tile;
+    while (tile < ph.n_tiles) {
+      __syncthreads();  // every thread has read S.next_tile
+      unsigned claim = 0;
+      if (threadIdx.x == 0) claim = atomicAdd(A.tile_ctr + p, 1u);
       while (it + 1 < it_end && tile >= A.items[it].tile0 + A.items[it].ntiles) ++it;
       const Item I = A.items[it];
-      const int seg_end = min(t1, I.tile0 + I.ntiles);
-      const int l0 = tile - I.tile0, l1 = seg_end - I.tile0;
-      tile = seg_end;
+      const int l0 = tile - I.tile0, l1 = l0 + 1;
       const unsigned long long seg_t0 = globaltimer_ns();
       switch (I.kind) {
         case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;
         case OADG_IT_MASK:
-          for (int k = l0; k < l1; ++k) mask_tile(A, I.obj, k, I.tx);
+          for (int k = l0; k < l1; ++k) mask_tile(A, S, I.obj, k, I.tx);
           break;
         case OADG_IT_HIST: {
           const Lane& L = A.lanes[I.obj];
@@ -838,10 +986,18 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
           break;
         default: break;
       }
-      if (threadIdx.x == 0 && !(A.debug & 4)) {
-        atomicAdd(A.kind_ns + I.kind, globaltimer_ns() - seg_t0);
-        atomicAdd(A.kind_ns + 8 + I.kind, (unsigned long long)(l1 - l0));
+      if (threadIdx.x == 0) {
+        if (!(A.debug & 4)) {
+          const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
+          const unsigned long long dt = globaltimer_ns() - seg_t0;
+          atomicAdd(A.kind_ns + kk, dt);
+          atomicAdd(A.kind_ns + 16 + kk, (unsigned long long)(l1 - l0));
+          atomicMax(A.kind_ns + 32 + kk, dt);
+        }
+        S.next_tile = (int)claim;
       }
+      __syncthreads();
+      tile = S.next_tile;
     }
     if (p + 1 < A.n_phases) grid_barrier(A.bar, (unsigned)(p + 1) * (unsigned)G);
     if (b == 0 && threadIdx.x == 0) A.phase_ts[p + 1] = globaltimer_ns();
@@ -880,7 +1036,7 @@ mix_kernel(DevPlan P, const MixJob* jobs) {
 struct CudaBackend {
   cudaStream_t stream;
   int launches = 0;
-  int n_sm = 0;
+  int n_sm = 0, ctas_per_sm = 0;
   // optional CUDA-event timing of the two launches (oadg_oamix_execute_profiled)
   bool profile = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -895,7 +1051,14 @@ struct CudaBackend {
       if (cudaGetDevice(&dev) != cudaSuccess) return -1;
       if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     }
-    return n_sm < kMaxGrid ? n_sm : kMaxGrid;
+    if (ctas_per_sm == 0) {
+      int nb = 0;
+      if (cudaFuncSetAttribute(oamix_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oamix_chain_kernel, kCT, kDynSmem) != cudaSuccess) return -1;
+      ctas_per_sm = nb < 1 ? 0 : (nb > kCtaPerSm ? kCtaPerSm : nb);
+      if (ctas_per_sm == 0) return -1;
+    }
+    return n_sm * ctas_per_sm;
   }
   int upload(void* dst, const void* src, size_t bytes) {
     BE_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
@@ -926,11 +1089,6 @@ struct CudaBackend {
       if (const char* dbg = getenv("OADG_DEBUG")) args.debug = atoi(dbg);
       void* params[2] = {(void*)&args, (void*)&div255};
       // cooperative launch: all CTAs are guaranteed co-resident, which the in-kernel grid barrier relies on
-      static bool attr_set = false;   // idempotent: a racing second thread sets the same value
-      if (!attr_set) {
-        BE_TRY(cudaFuncSetAttribute(oamix_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
-        attr_set = true;
-      }
       BE_TRY(cudaLaunchCooperativeKernel((const void*)oamix_chain_kernel, dim3(A.grid), dim3(kCT), params, kDynSmem,
                                          stream));
       ++launches;
@@ -984,18 +1142,12 @@ extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_by
     if (phase_ms && phase_kinds && be.n_phases > 0) {
       std::vector<unsigned long long> ts(be.n_phases + 1);
       e = cudaMemcpy(ts.data(), be.phase_ts_dev, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-      // ts[0] is unused (no in-kernel start stamp): phase 0 is charged from the first stamp backwards by the
-      // event time, so only phases 1.. carry in-kernel durations; phase 0 = chain time - sum of the others.
-      float rest = 0.f;
-      for (int p = 1; p < be.n_phases && p < phase_cap; ++p) {
-        phase_ms[p] = (float)((double)(ts[p + 1] - ts[p]) * 1e-6);
-        rest += phase_ms[p];
-      }
-      if (phase_cap > 0) phase_ms[0] = *ms_chain - rest;
+      // ts[0] = CTA 0 entering the kernel, ts[p + 1] = CTA 0 leaving the barrier that ends phase p
+      for (int p = 0; p < be.n_phases && p < phase_cap; ++p) phase_ms[p] = (float)((double)(ts[p + 1] - ts[p]) * 1e-6);
       for (int p = 0; p < be.n_phases && p < phase_cap; ++p) phase_kinds[p] = be.phase_kinds[p];
     }
     if (kind_stats && be.kind_ns_dev)
-      e = cudaMemcpy(kind_stats, be.kind_ns_dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      e = cudaMemcpy(kind_stats, be.kind_ns_dev, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   }
   for (auto& ev : be.ev)
     if (ev) cudaEventDestroy(ev);

@@ -64,13 +64,13 @@ OADG_HD uint8_t* chain_dst(const Chain& C, int level) { return (level & 1) ? C.T
 // Phase p+1 may read anything phase p wrote (grid barrier in between).
 enum {
   OADG_IT_PROFILE = 0,   // obj = gt*2 + axis            1 tile
-  OADG_IT_MASK = 1,      // obj = view                   tiles of 256 x 32 px
+  OADG_IT_MASK = 1,      // obj = view                   tiles of 256 x 8 px
   OADG_IT_HIST = 2,      // obj = lane                   tiles of kHistTilePx px (linear)
   OADG_IT_LUT = 3,       // obj = lut job                1 tile
   OADG_IT_COPY = 4,      // obj = chain                  tiles of kCopyTileBytes (linear); aux = 1: S as well as T
-  OADG_IT_BBO_R = 5,     // obj = bbo job                blend of one box, tiles of 128 x 32 px over its support
+  OADG_IT_BBO_R = 5,     // obj = bbo job                blend of one box, tiles of 64 x 16 px over its support
   OADG_IT_BBO_C = 6,     // obj = bbo job (level l-1)    catch-up copy X_l -> Y_l of its support minus level l's
-  OADG_IT_STEP = 7,      // obj = lane                   tiles of 256 x 64 px
+  OADG_IT_STEP = 7,      // obj = lane                   tiles of 256 x 16 px
   OADG_IT_KINDS = 8
 };
 struct Item {
@@ -83,11 +83,11 @@ struct Item {
 struct Phase {
   int32_t item0, n_items, n_tiles, pad;
 };
-constexpr int kMaskTileW = 256, kMaskTileH = 32;
+constexpr int kMaskTileW = 256, kMaskTileH = 8;
 constexpr int kHistTilePx = 32768;
 constexpr int kCopyTileBytes = 65536;
-constexpr int kBboTileW = 128, kBboTileH = 32;   // bbo tiles start at the support's x0 rounded down to a multiple of 4
-constexpr int kStepTileW = 256, kStepTileH = 64;
+constexpr int kBboTileW = 64, kBboTileH = 16;   // bbo tiles start at the support's x0 rounded down to a multiple of 4
+constexpr int kStepTileW = 256, kStepTileH = 16;
 
 struct MixJob {
   int32_t view, pad;

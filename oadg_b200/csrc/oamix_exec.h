@@ -89,7 +89,6 @@ inline int parse_plan(const void* blob, size_t bytes, PlanView& pv) {
   return 0;
 }
 
-constexpr int kMaxGrid = 256;   // the chain kernel never runs more CTAs than this (B200: 148)
 
 struct Layout {
   size_t frame_bytes;
@@ -149,7 +148,6 @@ inline void make_layout(const PlanView& pv, Layout& L) {
                    align_up_sz((size_t)(h.n_bbo > 0 ? h.n_bbo : 1) * sizeof(BboJob), 16) +
                    align_up_sz((size_t)L.max_items * sizeof(Item), 16) +
                    align_up_sz((size_t)L.max_phases * sizeof(Phase), 16) +
-                   align_up_sz((size_t)L.max_phases * (kMaxGrid + 1) * 2 * sizeof(int32_t), 16) +
                    align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
   L.off_tables = align_up_sz((size_t)h.total_bytes, 16);
@@ -161,7 +159,9 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.off_branch = take(n_branch_frames * L.frame_bytes);
   L.off_scratch = take((size_t)n_chains * 2 * L.frame_bytes);  // S + T per chain
   // one memset: [grid barrier counter | histograms | luma sums]
-  L.off_zero = take(256);   // [0] barrier counter; bytes 64..: per-kind busy ns [8] and tile counts [8] (uint64)
+  // [0] barrier counter; bytes 64..447: busy ns [16], tile counts [16], longest tile ns [16] per item kind (uint64); bytes 512..: one tile
+  // counter per phase
+  L.off_zero = take(512 + (size_t)L.max_phases * sizeof(unsigned));
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
   L.zero_bytes = o - L.off_zero;
@@ -259,20 +259,20 @@ inline void schedule_chain(const PlanView& pv, const oadg_view_t& V, const oadg_
   }
 }
 
-// relative time of one tile of each item kind (cost-balanced split of a phase over the CTAs)
-inline int tile_cost(int kind) {
+// Tiles of a phase are claimed dynamically (one atomic counter per phase), in item order: items that hold long
+// tiles come first so that the tail of a phase is made of short ones.
+inline int item_priority(int kind, bool lane_all_streaming) {
   switch (kind) {
-    case OADG_IT_PROFILE: return 16;
-    case OADG_IT_MASK: return 8;
-    case OADG_IT_HIST: return 12;
-    case OADG_IT_LUT: return 8;
-    case OADG_IT_COPY: return 5;
+    case OADG_IT_PROFILE: return 0;
+    case OADG_IT_LUT: return 1;
+    case OADG_IT_STEP: return lane_all_streaming ? 6 : 2;
     case OADG_IT_BBO_R: return 3;
-    case OADG_IT_BBO_C: return 1;
-    default: return 4;
+    case OADG_IT_HIST: return 4;
+    case OADG_IT_MASK: return 5;
+    case OADG_IT_COPY: return 7;
+    default: return 8;
   }
 }
-constexpr int kStepCostStream = 4, kStepCostPixel = 40, kStepCostEdge = 10;
 
 struct ChainArgs {       // everything the chain kernel needs (device pointers)
   DevPlan P;
@@ -282,7 +282,7 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   const BboJob* bjobs;
   const Item* items;
   const Phase* phases;
-  const int32_t* ranges;     // [n_phases][grid + 1][2]: first tile of every CTA and the item that tile belongs to
+  unsigned* tile_ctr;        // [n_phases] next unclaimed tile of every phase (zeroed before the launch)
   int32_t n_phases, grid;
   unsigned* hist;
   unsigned long long* luma;
@@ -296,11 +296,11 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   unsigned* bar;               // grid barrier counter (zeroed before the launch)
   unsigned long long* phase_ts;  // globaltimer at the end of every phase (measurement aid)
   int32_t debug;                 // bit 0: no staged bg gathers, bit 1: no staged bbo gathers (OADG_DEBUG, tests only)
-  unsigned long long* kind_ns;   // [8] CTA-busy nanoseconds per item kind, then [8] tiles per kind (measurement aid)
+  unsigned long long* kind_ns;   // [16] CTA-busy nanoseconds per item kind, then [16] tiles per kind (measurement aid)
 };
 
 // Backend concept (all return 0 or an error code):
-//   grid()                         CTAs the chain kernel will run (<= kMaxGrid)
+//   grid()                         CTAs the chain kernel will run (one per SM)
 //   upload(dst, src_host, bytes)   zero(dst, bytes)
 //   chain(args, host_tables...)    the phase/item interpreter (one persistent launch on the device)
 //   mix(P, jobs, n)
@@ -319,17 +319,17 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   make_layout(pv, L);
   if (workspace_bytes < L.total) return OADG_E_ARG;
   if (((uintptr_t)workspace & 255) != 0) return OADG_E_ARG;
-  {  // the profile tile keeps the kernel's prefix sums (<= 3072 taps) and the low-res profile (<= 2048) in shared memory
+  {  // the profile tile keeps the kernel's prefix sums (<= 1536 taps) and the low-res profile (<= 1024) in shared memory
     int max_k = 1;
     for (int g = 0; g < h.n_gt; ++g) {
       max_k = pv.gts[g].kx > max_k ? pv.gts[g].kx : max_k;
       max_k = pv.gts[g].ky > max_k ? pv.gts[g].ky : max_k;
     }
-    if ((h.max_w > h.max_h ? h.max_w : h.max_h) / 4 > 2048 || max_k > 3072) return OADG_E_LIMIT;
+    if ((h.max_w > h.max_h ? h.max_w : h.max_h) / 4 > 1024 || max_k > 1536) return OADG_E_LIMIT;
   }
   char* ws = static_cast<char*>(workspace);
   const int G = be.grid();
-  if (G < 1 || G > kMaxGrid) return OADG_E_LIMIT;
+  if (G < 1) return OADG_E_LIMIT;
 
   // host staging buffer: plan (with lut / scratch slots filled in) followed by the launch tables
   std::vector<char> stage(L.off_tables + L.tables_bytes, 0);
@@ -360,7 +360,6 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const size_t t_bjob = carve((size_t)(L.n_bbo > 0 ? L.n_bbo : 1) * sizeof(BboJob));
   const size_t t_items = carve((size_t)L.max_items * sizeof(Item));
   const size_t t_phases = carve((size_t)L.max_phases * sizeof(Phase));
-  const size_t t_ranges = carve((size_t)L.max_phases * (kMaxGrid + 1) * 2 * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
@@ -368,7 +367,6 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   auto* bjobs = reinterpret_cast<BboJob*>(stage.data() + t_bjob);
   auto* items = reinterpret_cast<Item*>(stage.data() + t_items);
   auto* phases = reinterpret_cast<Phase*>(stage.data() + t_phases);
-  auto* ranges = reinterpret_cast<int32_t*>(stage.data() + t_ranges);
   auto* mixjobs = reinterpret_cast<MixJob*>(stage.data() + t_mix);
 
   // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
@@ -513,14 +511,19 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   }
   if (n_phases > L.max_phases || (int)todo.size() > L.max_items) return OADG_E_LIMIT;
 
-  // ---- phase tables: items grouped by phase, tiles numbered within the phase, cost-balanced CTA ranges -----
+  // ---- phase tables: items grouped by phase (long-tile kinds first), tiles numbered within the phase ----------
   std::vector<int> order(todo.size());
   {
     std::vector<int> count(n_phases + 1, 0);
     for (const Todo& t : todo) ++count[t.phase + 1];
     for (int p = 0; p < n_phases; ++p) count[p + 1] += count[p];
+    // stable counting sort by (phase, priority)
     std::vector<int> fill(count.begin(), count.end() - 1);
-    for (size_t i = 0; i < todo.size(); ++i) order[fill[todo[i].phase]++] = (int)i;
+    for (int pr = 0; pr <= 8; ++pr)
+      for (size_t i = 0; i < todo.size(); ++i) {
+        const Todo& t = todo[i];
+        if (item_priority(t.kind, t.kind == OADG_IT_STEP && lanes[t.obj].all_streaming) == pr) order[fill[t.phase]++] = (int)i;
+      }
     for (int p = 0; p < n_phases; ++p) {
       phases[p].item0 = count[p];
       phases[p].n_items = count[p + 1] - count[p];
@@ -528,11 +531,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       phases[p].pad = 0;
     }
   }
-  std::vector<int> step_costs;
   for (int p = 0; p < n_phases; ++p) {
     Phase& ph = phases[p];
     int tile0 = 0;
-    long long total = 0;
     for (int k = 0; k < ph.n_items; ++k) {
       const Todo& t = todo[order[ph.item0 + k]];
       Item& it = items[ph.item0 + k];
@@ -557,69 +558,6 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       tile0 += it.ntiles;
     }
     ph.n_tiles = tile0;
-    // cost of every tile in phase order -> boundary k = first tile whose cumulative cost reaches k/G of the total
-    std::vector<int32_t> rgv(G + 1);
-    int32_t* rg = rgv.data();
-    auto step_tile_cost = [&](const Lane& ln, int ti, int tx) {
-      const int x0 = (ti % tx) * kStepTileW, y0 = (ti / tx) * kStepTileH;
-      const int x1 = x0 + kStepTileW < ln.W ? x0 + kStepTileW : ln.W, y1 = y0 + kStepTileH < ln.H ? y0 + kStepTileH : ln.H;
-      int region = ln.n_ml;
-      bool edge = false;
-      for (int bb = 0; bb < ln.n_ml; ++bb) {
-        const int32_t* B = ln.box[bb];
-        if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;
-        if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = bb;
-        else edge = true;
-      }
-      if (edge) return ln.all_streaming ? kStepCostEdge : kStepCostPixel;
-      const int kd = ln.kind[region];
-      return (is_lut_kind(kd) || kd == OADG_OP_BBO_AFFINE) ? kStepCostStream : kStepCostPixel;
-    };
-    for (int pass = 0; pass < 2; ++pass) {  // pass 0: total cost; pass 1: boundaries
-      long long cum = 0;
-      int kb = 1;
-      if (pass == 1) {
-        rg[0] = 0;
-        if (total == 0) {
-          for (int k2 = 1; k2 <= G; ++k2) rg[k2] = ph.n_tiles;
-          break;
-        }
-      }
-      for (int k = 0; k < ph.n_items; ++k) {
-        const Item& it = items[ph.item0 + k];
-        if (it.kind == OADG_IT_STEP) {
-          const Lane& ln = lanes[it.obj];
-          for (int ti = 0; ti < it.ntiles; ++ti) {
-            cum += step_tile_cost(ln, ti, it.tx);
-            if (pass == 1)
-              while (kb < G && cum * G >= total * kb) rg[kb++] = it.tile0 + ti + 1;
-          }
-        } else {
-          const long long w = tile_cost(it.kind);
-          if (pass == 1) {
-            while (kb < G && (cum + w * it.ntiles) * G >= total * kb) {
-              // smallest n with (cum + w n) G >= total kb
-              long long need = (total * kb + G - 1) / G - cum;
-              long long n = need <= 0 ? 0 : (need + w - 1) / w;
-              if (n > it.ntiles) n = it.ntiles;
-              rg[kb++] = it.tile0 + (int)n;
-            }
-          }
-          cum += w * it.ntiles;
-        }
-      }
-      if (pass == 0) total = cum;
-      else
-        while (kb <= G) rg[kb++] = ph.n_tiles;
-    }
-    rg[G] = ph.n_tiles;
-    int32_t* rt = ranges + (size_t)p * (G + 1) * 2;
-    int it = ph.item0;
-    for (int k = 0; k <= G; ++k) {
-      while (it + 1 < ph.item0 + ph.n_items && rg[k] >= items[it].tile0 + items[it].ntiles) ++it;
-      rt[2 * k] = rg[k];
-      rt[2 * k + 1] = it;
-    }
   }
 
   for (int v = 0; v < h.n_views; ++v) {
@@ -658,7 +596,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.bjobs = reinterpret_cast<const BboJob*>(dplan + t_bjob);
   A.items = reinterpret_cast<const Item*>(dplan + t_items);
   A.phases = reinterpret_cast<const Phase*>(dplan + t_phases);
-  A.ranges = reinterpret_cast<const int32_t*>(dplan + t_ranges);
+  A.tile_ctr = reinterpret_cast<unsigned*>(ws + L.off_zero + 512);
   A.n_phases = n_phases;
   A.grid = G;
   A.hist = reinterpret_cast<unsigned*>(ws + L.off_hist);
@@ -682,7 +620,6 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   Hh.bjobs = bjobs;
   Hh.items = items;
   Hh.phases = phases;
-  Hh.ranges = ranges;
   if ((rc = be.chain(A, Hh, pv))) return rc;
   return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);
 }

@@ -532,14 +532,16 @@ class OAMix:
             ms_chain, ms_mix, n_ph = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
             ph_ms = (ctypes.c_float * cap)()
             ph_kinds = (ctypes.c_int32 * cap)()
-            kstats = np.zeros(16, np.uint64)
+            kstats = np.zeros(48, np.uint64)
             _lib.check(lib.oadg_oamix_execute_profiled(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
                                                        ctypes.byref(ms_chain), ctypes.byref(ms_mix), ctypes.byref(n_ph),
                                                        ph_ms, ph_kinds, cap, kstats.ctypes.data, s.cuda_stream))
-            ks = profile.setdefault('kind_busy_us_and_tiles', {k: [0.0, 0] for k in ITEM_KINDS})
-            for i, k in enumerate(ITEM_KINDS):
+            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed')
+            ks = profile.setdefault('kind_busy_us_and_tiles', {k: [0.0, 0, 0.0] for k in names})
+            for i, k in enumerate(names):
                 ks[k][0] += float(kstats[i]) / 1e3
-                ks[k][1] += int(kstats[8 + i])
+                ks[k][1] += int(kstats[16 + i])
+                ks[k][2] = max(ks[k][2], float(kstats[32 + i]) / 1e3)
             profile['chain_ms'] = profile.get('chain_ms', 0.0) + float(ms_chain.value)
             profile['mix_ms'] = profile.get('mix_ms', 0.0) + float(ms_mix.value)
             profile['chain_n'] = profile.get('chain_n', 0) + 1

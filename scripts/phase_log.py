@@ -21,8 +21,9 @@ for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     prof = {'phase_log': []}
     j = (2 * i) % 8
     mix.oamix_batch(imgs[j:j + 2], gts[j:j + 2], profile=prof)
-    print('batch %d: chain %.1f us, mix %.1f us, %d phases' % (i, prof['chain_ms'] * 1e3, prof['mix_ms'] * 1e3, prof['phases']))
-    for k, (us, n) in prof['kind_busy_us_and_tiles'].items():
-        print('   kind %-12s busy %9.1f CTA-us over %6d tiles = %7.2f us/tile' % (k, us, n, us / max(n, 1)))
+    print('batch %d: chain %.1f us (in-kernel phases %.1f us), mix %.1f us, %d phases' % (
+        i, prof['chain_ms'] * 1e3, sum(ms for _, _, ms in prof['phase_log']) * 1e3, prof['mix_ms'] * 1e3, prof['phases']))
+    for k, (us, n, mx) in prof['kind_busy_us_and_tiles'].items():
+        print('   kind %-14s busy %9.1f CTA-us over %6d tiles = %7.2f us/tile, longest %7.1f us' % (k, us, n, us / max(n, 1), mx))
     for key, tiles, ms in prof['phase_log']:
         print('   %8.1f us  %6d tiles  %s' % (ms * 1e3, tiles, key))

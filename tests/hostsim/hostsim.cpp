@@ -142,13 +142,12 @@ struct HostBackend {
     for (int p = 0; p < A.n_phases; ++p) {
       const Phase& ph = A.phases[p];
       n_items += ph.n_items;
-      const int32_t* rg = A.ranges + (size_t)p * (G + 1) * 2;
-      if (rg[0] != 0 || rg[2 * G] != ph.n_tiles) return -200;
-      for (int b = 0; b < G; ++b) {
-        if (rg[2 * b + 2] < rg[2 * b]) return -201;
-        int it = rg[2 * b + 1];
+      // tiles are claimed dynamically on the device; any order within a phase must give the same result:
+      // the pretend CTAs take them round-robin, the last CTA first
+      for (int b = G - 1; b >= 0; --b) {
+        int it = ph.item0;
         const int it_end = ph.item0 + ph.n_items;
-        for (int tile = rg[2 * b]; tile < rg[2 * b + 2]; ++tile) {
+        for (int tile = b; tile < ph.n_tiles; tile += G) {
           while (it + 1 < it_end && tile >= A.items[it].tile0 + A.items[it].ntiles) ++it;
           const Item& I = A.items[it];
           const int local = tile - I.tile0;
