@@ -12,7 +12,8 @@ images/sec = source images consumed per second (2 per step per GPU), whole job.
 
 value  : inputs resident in HBM, CUDA-event timed (includes the saliency D2H sync, host plan
          sampling and the plan upload -- they are part of the path).
-e2e    : the registered plugins called with HOST buffers (pinned): H2D of frames / embeddings and D2H of
+e2e    : the registered plugins called with HOST buffers (pinned): OAMix.call_batch on the step's sample dicts (numpy
+         frames in, numpy views out) and ContrastiveLossPlus on a host tensor: H2D of frames / embeddings and D2H of
          the generated views / loss value inside the timed region.
 roofline: the OA-Mix chain kernel (one persistent launch per batch), achieved = algorithmic bytes (2 * 3HW per lane
          step) / CUDA-event kernel time from a second, event-instrumented pass over the same seeded plans.
@@ -266,10 +267,8 @@ def product_arm(args):
 
     def e2e_step(i):
         j = (i * BS) % POOL
-        views = []
-        for b in range(BS):
-            res = mix(dict(img=host_frames[(j + b) % POOL].numpy(), gt_bboxes=gts[(j + b) % POOL]))
-            views.append(res['img2'])
+        batch = [dict(img=host_frames[(j + b) % POOL].numpy(), gt_bboxes=gts[(j + b) % POOL]) for b in range(BS)]
+        views = [res['img2'] for res in mix.call_batch(batch)]   # host numpy in, host numpy out
         xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
         loss = run_loss(xd)
         loss.backward()

@@ -16,7 +16,7 @@ SOURCES = ['api.cu', 'saliency.cu', 'oamix.cu', 'oamix_sampler.cpp', 'oaloss.cu'
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-shared', '-fmad=false', '-Xptxas', '-v',
-         '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
+         '-I', os.path.join(ROOT, 'include'), '-I', CSRC] + os.environ.get('OADG_NVCC_EXTRA', '').split()
 # -fmad=false: the OA-Mix float stages must not contract a*b+c (oamix_math.h); kernels that
 # want FMA (the loss GEMMs) call fmaf() explicitly.
 

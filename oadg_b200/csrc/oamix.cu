@@ -27,6 +27,14 @@ namespace {
 // i / 255 in float64 (the reference divides a uint8 array by the python int 255, bbox_augmentation.py:267)
 __device__ const double g_div255[256] = {0.0 / 255.0, 1.0 / 255.0, 2.0 / 255.0, 3.0 / 255.0, 4.0 / 255.0, 5.0 / 255.0, 6.0 / 255.0, 7.0 / 255.0, 8.0 / 255.0, 9.0 / 255.0, 10.0 / 255.0, 11.0 / 255.0, 12.0 / 255.0, 13.0 / 255.0, 14.0 / 255.0, 15.0 / 255.0, 16.0 / 255.0, 17.0 / 255.0, 18.0 / 255.0, 19.0 / 255.0, 20.0 / 255.0, 21.0 / 255.0, 22.0 / 255.0, 23.0 / 255.0, 24.0 / 255.0, 25.0 / 255.0, 26.0 / 255.0, 27.0 / 255.0, 28.0 / 255.0, 29.0 / 255.0, 30.0 / 255.0, 31.0 / 255.0, 32.0 / 255.0, 33.0 / 255.0, 34.0 / 255.0, 35.0 / 255.0, 36.0 / 255.0, 37.0 / 255.0, 38.0 / 255.0, 39.0 / 255.0, 40.0 / 255.0, 41.0 / 255.0, 42.0 / 255.0, 43.0 / 255.0, 44.0 / 255.0, 45.0 / 255.0, 46.0 / 255.0, 47.0 / 255.0, 48.0 / 255.0, 49.0 / 255.0, 50.0 / 255.0, 51.0 / 255.0, 52.0 / 255.0, 53.0 / 255.0, 54.0 / 255.0, 55.0 / 255.0, 56.0 / 255.0, 57.0 / 255.0, 58.0 / 255.0, 59.0 / 255.0, 60.0 / 255.0, 61.0 / 255.0, 62.0 / 255.0, 63.0 / 255.0, 64.0 / 255.0, 65.0 / 255.0, 66.0 / 255.0, 67.0 / 255.0, 68.0 / 255.0, 69.0 / 255.0, 70.0 / 255.0, 71.0 / 255.0, 72.0 / 255.0, 73.0 / 255.0, 74.0 / 255.0, 75.0 / 255.0, 76.0 / 255.0, 77.0 / 255.0, 78.0 / 255.0, 79.0 / 255.0, 80.0 / 255.0, 81.0 / 255.0, 82.0 / 255.0, 83.0 / 255.0, 84.0 / 255.0, 85.0 / 255.0, 86.0 / 255.0, 87.0 / 255.0, 88.0 / 255.0, 89.0 / 255.0, 90.0 / 255.0, 91.0 / 255.0, 92.0 / 255.0, 93.0 / 255.0, 94.0 / 255.0, 95.0 / 255.0, 96.0 / 255.0, 97.0 / 255.0, 98.0 / 255.0, 99.0 / 255.0, 100.0 / 255.0, 101.0 / 255.0, 102.0 / 255.0, 103.0 / 255.0, 104.0 / 255.0, 105.0 / 255.0, 106.0 / 255.0, 107.0 / 255.0, 108.0 / 255.0, 109.0 / 255.0, 110.0 / 255.0, 111.0 / 255.0, 112.0 / 255.0, 113.0 / 255.0, 114.0 / 255.0, 115.0 / 255.0, 116.0 / 255.0, 117.0 / 255.0, 118.0 / 255.0, 119.0 / 255.0, 120.0 / 255.0, 121.0 / 255.0, 122.0 / 255.0, 123.0 / 255.0, 124.0 / 255.0, 125.0 / 255.0, 126.0 / 255.0, 127.0 / 255.0, 128.0 / 255.0, 129.0 / 255.0, 130.0 / 255.0, 131.0 / 255.0, 132.0 / 255.0, 133.0 / 255.0, 134.0 / 255.0, 135.0 / 255.0, 136.0 / 255.0, 137.0 / 255.0, 138.0 / 255.0, 139.0 / 255.0, 140.0 / 255.0, 141.0 / 255.0, 142.0 / 255.0, 143.0 / 255.0, 144.0 / 255.0, 145.0 / 255.0, 146.0 / 255.0, 147.0 / 255.0, 148.0 / 255.0, 149.0 / 255.0, 150.0 / 255.0, 151.0 / 255.0, 152.0 / 255.0, 153.0 / 255.0, 154.0 / 255.0, 155.0 / 255.0, 156.0 / 255.0, 157.0 / 255.0, 158.0 / 255.0, 159.0 / 255.0, 160.0 / 255.0, 161.0 / 255.0, 162.0 / 255.0, 163.0 / 255.0, 164.0 / 255.0, 165.0 / 255.0, 166.0 / 255.0, 167.0 / 255.0, 168.0 / 255.0, 169.0 / 255.0, 170.0 / 255.0, 171.0 / 255.0, 172.0 / 255.0, 173.0 / 255.0, 174.0 / 255.0, 175.0 / 255.0, 176.0 / 255.0, 177.0 / 255.0, 178.0 / 255.0, 179.0 / 255.0, 180.0 / 255.0, 181.0 / 255.0, 182.0 / 255.0, 183.0 / 255.0, 184.0 / 255.0, 185.0 / 255.0, 186.0 / 255.0, 187.0 / 255.0, 188.0 / 255.0, 189.0 / 255.0, 190.0 / 255.0, 191.0 / 255.0, 192.0 / 255.0, 193.0 / 255.0, 194.0 / 255.0, 195.0 / 255.0, 196.0 / 255.0, 197.0 / 255.0, 198.0 / 255.0, 199.0 / 255.0, 200.0 / 255.0, 201.0 / 255.0, 202.0 / 255.0, 203.0 / 255.0, 204.0 / 255.0, 205.0 / 255.0, 206.0 / 255.0, 207.0 / 255.0, 208.0 / 255.0, 209.0 / 255.0, 210.0 / 255.0, 211.0 / 255.0, 212.0 / 255.0, 213.0 / 255.0, 214.0 / 255.0, 215.0 / 255.0, 216.0 / 255.0, 217.0 / 255.0, 218.0 / 255.0, 219.0 / 255.0, 220.0 / 255.0, 221.0 / 255.0, 222.0 / 255.0, 223.0 / 255.0, 224.0 / 255.0, 225.0 / 255.0, 226.0 / 255.0, 227.0 / 255.0, 228.0 / 255.0, 229.0 / 255.0, 230.0 / 255.0, 231.0 / 255.0, 232.0 / 255.0, 233.0 / 255.0, 234.0 / 255.0, 235.0 / 255.0, 236.0 / 255.0, 237.0 / 255.0, 238.0 / 255.0, 239.0 / 255.0, 240.0 / 255.0, 241.0 / 255.0, 242.0 / 255.0, 243.0 / 255.0, 244.0 / 255.0, 245.0 / 255.0, 246.0 / 255.0, 247.0 / 255.0, 248.0 / 255.0, 249.0 / 255.0, 250.0 / 255.0, 251.0 / 255.0, 252.0 / 255.0, 253.0 / 255.0, 254.0 / 255.0, 255.0 / 255.0};
 
+// The phase handlers are separate device functions: compiled into one monolithic kernel body, ptxas (12.9) produced
+// wrong code for the mixed-tile path (caught by tests/test_gpu_oamix.py::test_single_op_plans_match_host_arithmetic).
+#ifdef OADG_INLINE_HANDLERS
+#define OADG_HANDLER __forceinline__
+#else
+#define OADG_HANDLER __noinline__
+#endif
+
 constexpr int kCT = 256;     // threads per CTA of the chain kernel
 constexpr int kCtaPerSm = 4; // independent CTAs per SM (64 registers per thread): tiles of different kinds overlap on an SM
 
@@ -94,7 +102,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 // blurred-mask profile of one (gt box, axis) (oa_mix.py:78-91): indicator on the 1/sr canvas -> GaussianBlur
 // (separable, BORDER_REFLECT_101, float32 kernel from getGaussianKernel) -> bilinear cv2.resize to full resolution.
 // ------------------------------------------------------------------------------------
-__device__ __noinline__ void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
+__device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
   const DevPlan& P = A.P;
   const int sr = 4;
   const int g = obj >> 1, axis = obj & 1;
@@ -202,7 +210,7 @@ __device__ __noinline__ void profile_tile(const ChainArgs& A, ChainSmem& S, int 
 // uint8(mask*255): written once per batch, read by every bg-only op.  Tile = 256 x 8 px, one column x 8 rows per
 // thread; the boxes whose support meets the tile are listed once per tile, and a thread keeps the x-profile value of
 // each listed box for its column in registers.
-__device__ __noinline__ void mask_tile(const ChainArgs& A, ChainSmem& S, int view, int local, int tx) {
+__device__ OADG_HANDLER void mask_tile(const ChainArgs& A, ChainSmem& S, int view, int local, int tx) {
   const DevPlan& P = A.P;
   const oadg_view_t& V = P.views[view];
   const int x0 = (local % tx) * kMaskTileW, y0 = (local / tx) * kMaskTileH;
@@ -260,7 +268,7 @@ __device__ __noinline__ void mask_tile(const ChainArgs& A, ChainSmem& S, int vie
 }
 
 // per-channel histogram + luma sum of a lane's input frame (PIL Image.histogram()); tile = 32768 px (linear)
-__device__ __noinline__ void hist_tile(const Lane& L, ChainSmem& S, int local, unsigned long long& lsum) {
+__device__ OADG_HANDLER void hist_tile(const Lane& L, ChainSmem& S, int local, unsigned long long& lsum) {
   const int tid = threadIdx.x;
   const size_t npx = (size_t)L.H * L.W;
   const size_t p0 = (size_t)local * kHistTilePx;
@@ -300,13 +308,13 @@ __device__ __noinline__ void hist_tile(const Lane& L, ChainSmem& S, int local, u
     }
   }
 }
-__device__ __noinline__ void hist_begin(ChainSmem& S) {
+__device__ OADG_HANDLER void hist_begin(ChainSmem& S) {
   __syncthreads();
   if (threadIdx.x == 0) S.bs_key = -1;   // u.hist overwrites the staged profile slices
   for (int i = threadIdx.x; i < 2 * 768; i += kCT) (&S.u.hist[0][0])[i] = 0;
   __syncthreads();
 }
-__device__ __noinline__ void hist_flush(const ChainArgs& A, ChainSmem& S, int slot, unsigned long long& lsum) {
+__device__ OADG_HANDLER void hist_flush(const ChainArgs& A, ChainSmem& S, int slot, unsigned long long& lsum) {
   __syncthreads();
   unsigned* dst = A.hist + (size_t)slot * 768;
   for (int i = threadIdx.x; i < 768; i += kCT) {
@@ -322,7 +330,7 @@ __device__ __noinline__ void hist_flush(const ChainArgs& A, ChainSmem& S, int sl
 }
 
 // one LUT op: PIL.ImageOps autocontrast / equalize from the finished histogram, or a closed-form table
-__device__ __noinline__ void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
+__device__ OADG_HANDLER void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
   const LutJob J = A.lutjobs[job];
   const oadg_op_t& op = A.P.ops[J.op];
   uint8_t* out = A.luts + (size_t)op.lut * 768;
@@ -353,7 +361,7 @@ __device__ __noinline__ void lut_tile(const ChainArgs& A, ChainSmem& S, int job)
 }
 
 // T (and S when the chain has a second level) = copy of the lane input; tiles [l0, l1) of 64 KB
-__device__ __noinline__ void copy_segment(const Chain& C, size_t nbytes, bool both, int l0, int l1) {
+__device__ OADG_HANDLER void copy_segment(const Chain& C, size_t nbytes, bool both, int l0, int l1) {
   const size_t b0 = (size_t)l0 * kCopyTileBytes;
   const size_t b1 = (size_t)l1 * kCopyTileBytes < nbytes ? (size_t)l1 * kCopyTileBytes : nbytes;
   const int tid = threadIdx.x;
@@ -423,7 +431,7 @@ __device__ __forceinline__ bool warp_src_rect(const double* m, int x0, int y0, i
 }
 __device__ __forceinline__ int stage_pitch(int bx0, int bx1, int C) { return (15 + (bx1 - bx0) * C + 15) & ~15; }
 // copy source rows [by0,by1) x [bx0,bx1) of a C-byte-per-pixel frame into shared memory (all threads)
-__device__ __noinline__ void stage_rows(uint8_t* sm, int pitch, const uint8_t* base, int W, int H, int C, int bx0, int by0,
+__device__ OADG_HANDLER void stage_rows(uint8_t* sm, int pitch, const uint8_t* base, int W, int H, int C, int bx0, int by0,
                                         int rows) {
   const int vpr = pitch >> 4;
   const uint8_t* end = base + (size_t)H * W * C;
@@ -490,7 +498,7 @@ __device__ __forceinline__ void load12(const uint8_t* p, bool vec, int n, uint32
 __device__ __forceinline__ int byte_of(const uint32_t w[3], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 255u); }
 
 // ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
-__device__ __noinline__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
+__device__ OADG_HANDLER void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
   __syncthreads();
   const int key = I.obj * 2 + (catch_up ? 1 : 0);
   if (S.bs_key == key) return;   // the job is still staged from this CTA's previous tile (uniform: S.bs_key is shared)
@@ -517,8 +525,8 @@ __device__ __noinline__ void bbo_stage(const ChainArgs& A, ChainSmem& S, const I
   }
   __syncthreads();
 }
-// blend of one box: tiles [l0, l1) of 64 x 16 px; Y = uint8(X*(1-m) + warp(X)*m) inside the support
-__device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
+// blend of one box: tiles [l0, l1) of 128 x 16 px; Y = uint8(X*(1-m) + warp(X)*m) inside the support
+__device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
   bbo_stage(A, S, I, false);
   const BboStage& bs = S.bs;
   const int t = threadIdx.x;
@@ -545,9 +553,11 @@ __device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
   }
   const bool vec = ((W * 3) & 3) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 3) == 0;
   const int ax0 = bs.rect[0] & ~3, tx = I.tx;
-  for (int k = l0; k < l1; ++k) {
-    const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
-    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
+  for (int k2 = 2 * l0; k2 < 2 * l1; ++k2) {   // two 64 x 16 sub-tiles per tile, each with its own staged source
+    const int k = k2 >> 1;
+    const int tx0 = ax0 + (k % tx) * kBboTileW + (k2 & 1) * kSubW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
+    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kSubW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
+    if (x1 <= x0) continue;   // uniform: the support ends inside the first sub-tile
     int sr[4];
     const bool any_src = warp_src_rect(bs.minv, x0, ty0, x1, y1, W, H, sr);
     const StageView sv = make_view(dyn, bs.X, W, H, 3, sr);
@@ -575,7 +585,8 @@ __device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
       if (x >= x0 && x < x1) {
         const float ux = prof_smem ? S.u.prof[x - bs.rect[0]] : A.prof_x[(size_t)bs.gt * A.P.max_w + x];
         const float m = fmul(uy, ux);
-        if (m != 0.f) {  // m == 0 => img*1 + aug*0 == img exactly
+        // m <= 2^-25: fl(1 - m) == 1 and fl(1 - 1) == 0, so img*1 + aug*0 == img exactly
+        if (m > 2.98023223876953125e-8f) {
           int sx, sy, fx, fy, a[3];
           warp_coord(bs.minv, x, y, sx, sy, fx, fy);
           if (staged) staged_fetch3(sv, sx, sy, fx, fy, a);
@@ -603,7 +614,7 @@ __device__ __noinline__ void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
   }
 }
 // catch-up copy of a level l-1 support into the frame level l writes, minus the supports level l rewrites
-__device__ __noinline__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
+__device__ OADG_HANDLER void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
   bbo_stage(A, S, I, true);
   const BboStage& bs = S.bs;
   const int t = threadIdx.x, W = bs.W;
@@ -613,38 +624,43 @@ __device__ __noinline__ void bbo_c_segment(const ChainArgs& A, ChainSmem& S, con
   const BboJob& J = A.bjobs[I.obj];
   if (A.debug & 16) {   // reference path: the shared per-pixel body
     for (int k = l0; k < l1; ++k) {
-      const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
-      for (int q = t; q < kBboTileW * kBboTileH; q += kCT) {
-        const int x = tx0 + (q & (kBboTileW - 1)), y = ty0 + q / kBboTileW;
+      const int tx0 = ax0 + (k % tx) * kBboCatchW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
+      for (int q = t; q < kBboCatchW * kBboTileH; q += kCT) {
+        const int x = tx0 + (q & (kBboCatchW - 1)), y = ty0 + q / kBboCatchW;
         if (x >= bs.rect[0] && x < bs.rect[2] && y < bs.rect[3]) bbo_c_pixel(jobs, J, W, bs.X, bs.Y, x, y);
       }
     }
     return;
   }
   for (int k = l0; k < l1; ++k) {
-    const int tx0 = ax0 + (k % tx) * kBboTileW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
-    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
-    const int y = ty0 + (t >> 4), xg = tx0 + (t & 15) * 4;
-    if (y >= y1 || xg >= x1 || xg + 4 <= x0) continue;
-    const size_t o = ((size_t)y * W + xg) * 3;
-    // does a next-level support touch this 4-px group?
-    bool touch = bs.n_excl > 16, all_in = false;
-    if (bs.n_excl <= 16)
-      for (int e = 0; e < bs.n_excl; ++e) {
-        const bool yy = y >= bs.excl[e][1] && y < bs.excl[e][3];
-        touch |= yy && xg < bs.excl[e][2] && xg + 4 > bs.excl[e][0];
-        all_in |= yy && xg >= bs.excl[e][0] && xg + 4 <= bs.excl[e][2];
+    const int tx0 = ax0 + (k % tx) * kBboCatchW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
+    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboCatchW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
+    const int y = ty0 + (t >> 4);
+    if (y >= y1) continue;
+#pragma unroll
+    for (int gq = 0; gq < kBboCatchW / 64; ++gq) {
+      const int xg = tx0 + gq * 64 + (t & 15) * 4;
+      if (xg >= x1 || xg + 4 <= x0) continue;
+      const size_t o = ((size_t)y * W + xg) * 3;
+      // does a next-level support touch this 4-px group?
+      bool touch = bs.n_excl > 16, all_in = false;
+      if (bs.n_excl <= 16)
+        for (int e = 0; e < bs.n_excl; ++e) {
+          const bool yy = y >= bs.excl[e][1] && y < bs.excl[e][3];
+          touch |= yy && xg < bs.excl[e][2] && xg + 4 > bs.excl[e][0];
+          all_in |= yy && xg >= bs.excl[e][0] && xg + 4 <= bs.excl[e][2];
+        }
+      if (all_in) continue;
+      if (!touch && vec && xg >= x0 && xg + 4 <= x1) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.X + o);
+        const uint32_t a0 = q[0], a1 = q[1], a2 = q[2];
+        uint32_t* d = reinterpret_cast<uint32_t*>(bs.Y + o);
+        d[0] = a0; d[1] = a1; d[2] = a2;
+        continue;
       }
-    if (all_in) continue;
-    if (!touch && vec && xg >= x0 && xg + 4 <= x1) {
-      const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.X + o);
-      const uint32_t a0 = q[0], a1 = q[1], a2 = q[2];
-      uint32_t* d = reinterpret_cast<uint32_t*>(bs.Y + o);
-      d[0] = a0; d[1] = a1; d[2] = a2;
-      continue;
+      for (int i = 0; i < 4; ++i)
+        if (xg + i >= x0 && xg + i < x1) bbo_c_pixel(jobs, J, W, bs.X, bs.Y, xg + i, y);
     }
-    for (int i = 0; i < 4; ++i)
-      if (xg + i >= x0 && xg + i < x1) bbo_c_pixel(jobs, J, W, bs.X, bs.Y, xg + i, y);
   }
 }
 
@@ -686,7 +702,7 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
 
 // bg-only op (bbox_augmentation.py:240-272) on a sub-tile of 64 x 16 px that one region covers: the frame and the
 // uint8 union mask are both warped from staged shared-memory rows; 4 pixels per thread.
-__device__ __noinline__ void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int r_only, int x0,
+__device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int r_only, int x0,
                                         int y0, int x1, int y1, const double* div255) {
   const DevPlan& P = A.P;
   const int W = L.W, H = L.H, t = threadIdx.x;
@@ -819,11 +835,12 @@ __device__ __forceinline__ void pixel_op_fast(const ChainArgs& A, const Lane& L,
 // gathers, invert / colour / sharpness, runs cut by a multi-level box edge) is evaluated per pixel with consecutive
 // lanes on consecutive pixels (run_is_stream, oamix_tile.h, decides which pass owns a run).
 // ------------------------------------------------------------------------------------
-__device__ __noinline__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int local, int tx, const double* div255) {
+__device__ OADG_HANDLER void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int local, int tx, int tw,
+                                       const double* div255) {
   const Lane& L = S.lane;
   const int W = L.W, H = L.H, t = threadIdx.x;
-  const int x0 = (local % tx) * kStepTileW, y0 = (local / tx) * kStepTileH;
-  const int x1 = min(x0 + kStepTileW, W), y1 = min(y0 + kStepTileH, H);
+  const int x0 = (local % tx) * tw, y0 = (local / tx) * kStepTileH;
+  const int x1 = min(x0 + tw, W), y1 = min(y0 + kStepTileH, H);
   const int region = tile_region(L, x0, y0, x1, y1);
   const bool tile_stream = region >= 0 && kind_streams(L.kind[region]);
   const bool tile_pixel = region >= 0 && !tile_stream;
@@ -900,7 +917,7 @@ __device__ __noinline__ void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
 }
 
 // stage a lane record, its LUTs and its region ops in shared memory (once per lane a CTA works on)
-__device__ __noinline__ void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
+__device__ OADG_HANDLER void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
   const int t = threadIdx.x;
   __syncthreads();
   if (t < (int)(sizeof(Lane) / 4))
@@ -943,9 +960,12 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
     const Phase ph = A.phases[p];
     int it = ph.item0;
     const int it_end = ph.item0 + ph.n_items;
-    // dynamic tile claims: thread 0 fetches the next index while the CTA works on the current tile
-    if (threadIdx.x == 0) S.next_tile = (int)atomicAdd(A.tile_ctr + p, 1u);
-    __syncthreads();
+    // dynamic tile claims: thread 0 fetches the next index while the CTA works on the current tile (the first
+    // claim of a phase was taken before the barrier that opened it)
+    if (p == 0) {
+      if (threadIdx.x == 0) S.next_tile = (int)atomicAdd(A.tile_ctr, 1u);
+      __syncthreads();
+    }
     int tile = S.next_tile;
     while (tile < ph.n_tiles) {
       __syncthreads();  // every thread has read S.next_tile
@@ -982,7 +1002,7 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
             stage_lane(A, S, I.obj);
             staged_lane = I.obj;
           }
-          for (int k = l0; k < l1; ++k) step_tile(A, S, dyn, k, I.tx, div255);
+          for (int k = l0; k < l1; ++k) step_tile(A, S, dyn, k, I.tx, I.aux, div255);
           break;
         default: break;
       }
@@ -999,7 +1019,13 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
       __syncthreads();
       tile = S.next_tile;
     }
-    if (p + 1 < A.n_phases) grid_barrier(A.bar, (unsigned)(p + 1) * (unsigned)G);
+    if (p + 1 < A.n_phases) {
+      unsigned first = 0;
+      if (threadIdx.x == 0) first = atomicAdd(A.tile_ctr + p + 1, 1u);   // claiming touches no phase data
+      grid_barrier(A.bar, (unsigned)(p + 1) * (unsigned)G);
+      if (threadIdx.x == 0) S.next_tile = (int)first;
+      __syncthreads();
+    }
     if (b == 0 && threadIdx.x == 0) A.phase_ts[p + 1] = globaltimer_ns();
   }
 }

@@ -68,7 +68,7 @@ enum {
   OADG_IT_HIST = 2,      // obj = lane                   tiles of kHistTilePx px (linear)
   OADG_IT_LUT = 3,       // obj = lut job                1 tile
   OADG_IT_COPY = 4,      // obj = chain                  tiles of kCopyTileBytes (linear); aux = 1: S as well as T
-  OADG_IT_BBO_R = 5,     // obj = bbo job                blend of one box, tiles of 64 x 16 px over its support
+  OADG_IT_BBO_R = 5,     // obj = bbo job                blend of one box, tiles of 128 x 16 px over its support
   OADG_IT_BBO_C = 6,     // obj = bbo job (level l-1)    catch-up copy X_l -> Y_l of its support minus level l's
   OADG_IT_STEP = 7,      // obj = lane                   tiles of 256 x 16 px
   OADG_IT_KINDS = 8
@@ -86,8 +86,10 @@ struct Phase {
 constexpr int kMaskTileW = 256, kMaskTileH = 8;
 constexpr int kHistTilePx = 32768;
 constexpr int kCopyTileBytes = 65536;
-constexpr int kBboTileW = 64, kBboTileH = 16;   // bbo tiles start at the support's x0 rounded down to a multiple of 4
-constexpr int kStepTileW = 256, kStepTileH = 16;
+constexpr int kBboTileW = 128, kBboTileH = 16;   // bbo tiles start at the support's x0 rounded down to a multiple of 4
+constexpr int kStepTileW = 256, kStepTileH = 16;   // lanes with per-pixel ops use kStepTileWPx wide tiles (Item.aux)
+constexpr int kStepTileWPx = 128;
+constexpr int kBboCatchW = 256;                     // catch-up copies move 256 x 16 px per tile
 
 struct MixJob {
   int32_t view, pad;

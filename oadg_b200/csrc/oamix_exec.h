@@ -266,10 +266,10 @@ inline int item_priority(int kind, bool lane_all_streaming) {
     case OADG_IT_PROFILE: return 0;
     case OADG_IT_LUT: return 1;
     case OADG_IT_STEP: return lane_all_streaming ? 6 : 2;
-    case OADG_IT_BBO_R: return 3;
-    case OADG_IT_HIST: return 4;
-    case OADG_IT_MASK: return 5;
-    case OADG_IT_COPY: return 7;
+    case OADG_IT_HIST: return 3;
+    case OADG_IT_BBO_R: return 4;
+    case OADG_IT_COPY: return 5;
+    case OADG_IT_MASK: return 7;
     default: return 8;
   }
 }
@@ -547,9 +547,12 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
         case OADG_IT_MASK: tw = kMaskTileW; th = kMaskTileH; break;
         case OADG_IT_HIST: tw = kHistTilePx; break;
         case OADG_IT_COPY: tw = kCopyTileBytes; break;
-        case OADG_IT_BBO_R:
-        case OADG_IT_BBO_C: tw = kBboTileW; th = kBboTileH; break;
-        case OADG_IT_STEP: tw = kStepTileW; th = kStepTileH; break;
+        case OADG_IT_BBO_R: tw = kBboTileW; th = kBboTileH; break;
+        case OADG_IT_BBO_C: tw = kBboCatchW; th = kBboTileH; break;
+        case OADG_IT_STEP:   // narrower tiles for lanes with per-pixel ops: their tiles are long
+          tw = it.aux = lanes[t.obj].all_streaming ? kStepTileW : kStepTileWPx;
+          th = kStepTileH;
+          break;
         default: break;
       }
       it.tx = (t.w + tw - 1) / tw;

@@ -163,6 +163,7 @@ class OAMix:
         self._ws_cache = None
         self._sal_state = None
         self._native_cfg = None
+        self._host_state = dict(dev={}, pin={})
         self.last_launches = 0
 
     def __repr__(self):
@@ -583,18 +584,70 @@ class OAMix:
         oamix_boxes = [np.stack(list(b), axis=0) for b in plan.oa_boxes]   # ValueError when none could be placed
         return outs, oamix_boxes, plan.ml_boxes
 
-    def oamix(self, img, gt_bboxes):
-        """One view of one host image (reference oa_mix.py:207-243): H2D, kernels, D2H."""
+    # ------------------------------------------------------------------ host buffers
+    def _to_device(self, img, slot):
+        """Host uint8 HWC array -> CUDA tensor on the current stream.  Page-locked arrays (e.g. a loader's pinned
+        buffers) are copied asynchronously in place; pageable ones go through a persistent pinned staging buffer."""
         torch = _lib.require_cuda()
         img = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
+        src = torch.from_numpy(img)
+        st = self._host_state
+        key = (slot, tuple(img.shape))
+        dev = st['dev'].get(key)
+        if dev is None:
+            dev = st['dev'][key] = torch.empty(img.shape, dtype=torch.uint8, device='cuda')
+        if not src.is_pinned():
+            pin = st['pin'].get(key)
+            if pin is None:
+                pin = st['pin'][key] = torch.empty(img.shape, dtype=torch.uint8).pin_memory()
+            pin.copy_(src)
+            src = pin
+        dev.copy_(src, non_blocking=True)
+        return dev, img
+
+    def _to_host(self, outs):
+        """CUDA views -> numpy arrays backed by freshly allocated page-locked memory (one sync for all of them)."""
+        torch = _lib.require_cuda()
+        host = [torch.empty(o.shape, dtype=torch.uint8, pin_memory=True) for o in outs]
+        for h_, o in zip(host, outs):
+            h_.copy_(o, non_blocking=True)
+        torch.cuda.current_stream(outs[0].device).synchronize()
+        return [h_.numpy() for h_ in host]
+
+    def oamix(self, img, gt_bboxes):
+        """One view of one host image (reference oa_mix.py:207-243): H2D, kernels, D2H."""
         gt = np.asarray(gt_bboxes, dtype=np.float32).reshape(-1, 4)
-        dimg = torch.from_numpy(img).cuda(non_blocking=True)
+        dimg, img = self._to_device(img, 0)
         scores = self.saliency_scores([dimg], [gt])[0]      # no RNG draw: may precede the plan head
         plan = self.sample_plan([img.shape[:2]], [gt], [scores])
         self._history.update(random_box_list=plan.ml_boxes[0], fg_box_list=gt, fg_score_list=scores,
                              oa_random_box_list=list(plan.oa_boxes[0]))
         out = self.execute(plan.blob, [dimg])[0]
-        return out.cpu().numpy()
+        return self._to_host([out])[0]
+
+    def call_batch(self, results_list):
+        """The transform on a list of sample dicts at once (what a collate-level hook calls): the same result keys
+        and the same np.random consumption as calling the transform on each dict in order (oa_mix.py:187-204), with
+        one H2D / kernel chain / D2H for the whole list.  Falls back to per-sample calls for configurations other
+        than num_views=2, keep_orig=True."""
+        if not (self.num_views == 2 and self.keep_orig):
+            return [self(r) for r in results_list]
+        gts = [np.asarray(r['gt_bboxes'], dtype=np.float32).reshape(-1, 4) for r in results_list]
+        staged = [self._to_device(r['img'], i) for i, r in enumerate(results_list)]
+        dimgs = [d for d, _ in staged]
+        scores = self.saliency_scores(dimgs, gts)
+        plan = self.sample_plan([h.shape[:2] for _, h in staged], gts, scores)
+        outs = self._to_host(self.execute(plan.blob, dimgs))
+        for r, out, oa, ml in zip(results_list, outs, plan.oa_boxes, plan.ml_boxes):
+            r['custom_field'] = []
+            r['img_fields'] = ['img', 'img2']
+            r['img2'] = out
+            r['gt_bboxes2'] = r['gt_bboxes'].copy()
+            r['oamix_boxes'] = np.stack(list(oa), axis=0)
+            r['custom_field'] += ['img2', 'gt_bboxes2', 'oamix_boxes']
+            r['multilevel_boxes'] = ml
+            r['custom_field'] += ['multilevel_boxes']
+        return results_list
 
     def __call__(self, results, *args, **kwargs):
         """oa_mix.py:187-204."""
@@ -603,10 +656,10 @@ class OAMix:
             if i == 1:
                 self._history = {}
                 if not self.keep_orig:
-                    results['img'] = self.oamix(results['img'].copy(), results['gt_bboxes'].copy())
+                    results['img'] = self.oamix(results['img'], results['gt_bboxes'].copy())   # the source is never mutated
                 results['img_fields'] = ['img']
             else:
-                results[f'img{i}'] = self.oamix(results['img'].copy(), results['gt_bboxes'].copy())
+                results[f'img{i}'] = self.oamix(results['img'], results['gt_bboxes'].copy())
                 results['img_fields'] += [f'img{i}']
                 results[f'gt_bboxes{i}'] = results['gt_bboxes'].copy()
                 results['oamix_boxes'] = np.stack(self._history['oa_random_box_list'], axis=0)

@@ -104,10 +104,10 @@ struct HostBackend {
     }
   }
   // mirrors step_tile (oamix.cu): the vector pass over streaming runs, then the per-pixel pass over the rest
-  static void step_item_tile(const ChainArgs& A, const Lane& L, int local, int tx) {
+  static void step_item_tile(const ChainArgs& A, const Lane& L, int local, int tx, int tw) {
     const DevPlan& P = A.P;
-    const int x0 = (local % tx) * kStepTileW, y0 = (local / tx) * kStepTileH;
-    const int x1 = imin(x0 + kStepTileW, L.W), y1 = imin(y0 + kStepTileH, L.H);
+    const int x0 = (local % tx) * tw, y0 = (local / tx) * kStepTileH;
+    const int x1 = imin(x0 + tw, L.W), y1 = imin(y0 + kStepTileH, L.H);
     uint8_t luts[OADG_MAX_REGIONS * 768];
     for (int r = 0; r <= L.n_ml; ++r)
       if (L.lut[r] >= 0) memcpy(luts + r * 768, P.luts + (size_t)L.lut[r] * 768, 768);
@@ -193,16 +193,17 @@ struct HostBackend {
               const int level = I.kind == OADG_IT_BBO_R ? J.level : J.level + 1;
               const uint8_t* X = chain_src(C, level);
               uint8_t* Y = chain_dst(C, level);
-              const int x0 = (J.rect[0] & ~3) + (local % I.tx) * kBboTileW, y0 = J.rect[1] + (local / I.tx) * kBboTileH;
+              const int tw = I.kind == OADG_IT_BBO_R ? kBboTileW : kBboCatchW;
+              const int x0 = (J.rect[0] & ~3) + (local % I.tx) * tw, y0 = J.rect[1] + (local / I.tx) * kBboTileH;
               for (int y = y0; y < imin(y0 + kBboTileH, J.rect[3]); ++y)
-                for (int x = imax(x0, J.rect[0]); x < imin(x0 + kBboTileW, J.rect[2]); ++x) {
+                for (int x = imax(x0, J.rect[0]); x < imin(x0 + tw, J.rect[2]); ++x) {
                   if (I.kind == OADG_IT_BBO_R) bbo_r_pixel(P, C, P.bbo[J.bbo], X, Y, x, y);
                   else bbo_c_pixel(A.bjobs, J, P.views[C.view].W, X, Y, x, y);
                 }
               if (I.kind == OADG_IT_BBO_R && local == 0) ++n_bbo_jobs;
               break;
             }
-            case OADG_IT_STEP: step_item_tile(A, A.lanes[I.obj], local, I.tx); break;
+            case OADG_IT_STEP: step_item_tile(A, A.lanes[I.obj], local, I.tx, I.aux); break;
             default: return -203;
           }
         }

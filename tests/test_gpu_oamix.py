@@ -203,3 +203,23 @@ def test_single_op_plans_match_host_arithmetic_bit_for_bit(cuda):
                                             None) == 0
             out = t.execute(blob, [torch.from_numpy(img).to(cuda)])[0].cpu().numpy()
             assert np.array_equal(out, ref), (h, w, [[op[0] for op in regs] for steps in ops for regs in steps])
+
+
+def test_call_batch_equals_per_sample_calls(cuda):
+    """OAMix.call_batch (one H2D / kernel chain / D2H for a list of sample dicts) vs the transform called on each
+    dict in turn: same result keys, same boxes, same pixels, same np.random state afterwards."""
+    from oadg_b200 import OAMix
+    t = OAMix(**dict(OAMIX_CFG, version='augmix'))
+    samples = [synth.make_image(s, 200, 333, 5) for s in (3, 4, 5)]
+    np.random.seed(77)
+    seq = [t(dict(img=img.copy(), gt_bboxes=gt.copy())) for img, gt in samples]
+    st_seq = np.random.get_state()
+    np.random.seed(77)
+    bat = t.call_batch([dict(img=img.copy(), gt_bboxes=gt.copy()) for img, gt in samples])
+    st_bat = np.random.get_state()
+    assert st_seq[2] == st_bat[2] and np.array_equal(st_seq[1], st_bat[1])
+    for a, b, (img, gt) in zip(seq, bat, samples):
+        assert a['custom_field'] == b['custom_field'] and a['img_fields'] == b['img_fields']
+        for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(b['img'], img) and b['img2'].dtype == np.uint8 and b['oamix_boxes'].dtype == np.int64
