@@ -55,6 +55,7 @@ struct BboStage {    // one bbo job staged for the CTA (bbo_r_segment / bbo_c_se
 
 struct ChainSmem {
   int next_tile;       // the CTA's next claimed tile of the current phase
+  int rowoff[2][96];   // staged gathers: byte offset of every staged source row (frame rows, mask rows)
   int cand[16];        // mask tiles: the gt boxes whose support meets the tile
   int step_class;      // measurement aid: class of the last step tile (7 stream, 8 staged bg, 9 mixed / per pixel)
   int prof_ready;      // u.prof holds the profile slices of the staged blend job
@@ -413,6 +414,24 @@ __device__ __forceinline__ void warp_coord(const double* m, int x, int y, int& s
   fx = X & 31;
   fy = Y & 31;
 }
+// the same map with the row terms (functions of y alone) computed once per thread
+struct WarpRowTerm {
+  int X0, Y0;
+};
+__device__ __forceinline__ WarpRowTerm warp_row_term(const double* m, int y) {
+  WarpRowTerm r;
+  r.X0 = cv_round(dmul(dadd(dmul(m[1], (double)y), m[2]), 1024.0)) + 16;
+  r.Y0 = cv_round(dmul(dadd(dmul(m[4], (double)y), m[5]), 1024.0)) + 16;
+  return r;
+}
+__device__ __forceinline__ void warp_coord_row(const double* m, WarpRowTerm r, int x, int& sx, int& sy, int& fx, int& fy) {
+  const int X = (r.X0 + cv_round(dmul(dmul(m[0], (double)x), 1024.0))) >> 5;
+  const int Y = (r.Y0 + cv_round(dmul(dmul(m[3], (double)x), 1024.0))) >> 5;
+  sx = imin(imax(X >> 5, -32768), 32767);
+  sy = imin(imax(Y >> 5, -32768), 32767);
+  fx = X & 31;
+  fy = Y & 31;
+}
 // source rectangle of the output rectangle [x0,x1) x [y0,y1), clamped to the frame; false when it is empty
 __device__ __forceinline__ bool warp_src_rect(const double* m, int x0, int y0, int x1, int y1, int W, int H, int r[4]) {
   int sxa = 1 << 30, sxb = -(1 << 30), sya = 1 << 30, syb = -(1 << 30);
@@ -484,6 +503,28 @@ __device__ __forceinline__ int staged_fetch1(const StageView& v, int sx, int sy,
   const uint8_t* r0 = staged_px(v, sx, sy);
   const uint8_t* r1 = staged_px(v, sx, sy + 1);
   return bilerp_fix((y0 && x0) ? r0[0] : 0, (y0 && x1) ? r0[1] : 0, (y1 && x0) ? r1[0] : 0, (y1 && x1) ? r1[1] : 0, fx, fy);
+}
+// row offset table of a staged view: rowoff[r] = r * pitch + byte phase of source row by0 + r  (threads 0..rows-1)
+__device__ __forceinline__ void fill_rowoff(int* rowoff, const StageView& v, int rows) {
+  const int r = threadIdx.x;
+  if (r < rows && r < 96) rowoff[r] = r * v.pitch + (int)((v.lo + (uint32_t)(((v.by0 + r) * v.W + v.bx0) * v.C)) & 15u);
+}
+// all four taps of (sx, sy) lie inside the staged rectangle (hence inside the frame): no per-tap tests needed
+__device__ __forceinline__ bool taps_inside(const StageView& v, int sx, int sy) {
+  return sx >= v.bx0 && sx + 1 < v.bx1 && sy >= v.by0 && sy + 1 < v.by1;
+}
+__device__ __forceinline__ void fast_fetch3(const StageView& v, const int* rowoff, int sx, int sy, int fx, int fy, int out[3]) {
+  const uint8_t* r0 = v.sm + rowoff[sy - v.by0] + (sx - v.bx0) * 3;
+  const uint8_t* r1 = v.sm + rowoff[sy + 1 - v.by0] + (sx - v.bx0) * 3;
+  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    out[c] = ((int)r0[c] * w00 + (int)r0[3 + c] * w01 + (int)r1[c] * w10 + (int)r1[3 + c] * w11 + (1 << 14)) >> 15;
+}
+__device__ __forceinline__ int fast_fetch1(const StageView& v, const int* rowoff, int sx, int sy, int fx, int fy) {
+  const uint8_t* r0 = v.sm + rowoff[sy - v.by0] + (sx - v.bx0);
+  const uint8_t* r1 = v.sm + rowoff[sy + 1 - v.by0] + (sx - v.bx0);
+  return bilerp_fix(r0[0], r0[1], r1[0], r1[1], fx, fy);
 }
 // 4 consecutive pixels (12 bytes) of a u8x3 frame at byte offset o: three words when aligned, bytes otherwise
 __device__ __forceinline__ void load12(const uint8_t* p, bool vec, int n, uint32_t w[3]) {
@@ -562,22 +603,29 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
     const bool any_src = warp_src_rect(bs.minv, x0, ty0, x1, y1, W, H, sr);
     const StageView sv = make_view(dyn, bs.X, W, H, 3, sr);
     const bool staged = any_src && (size_t)(sr[3] - sr[1]) * sv.pitch <= (size_t)kDynSmem && !(A.debug & 2);
-    __syncthreads();  // the previous tile's gathers are done (and the profile slices are in place)
-    if (staged) stage_rows(dyn, sv.pitch, bs.X, W, H, 3, sr[0], sr[1], sr[3] - sr[1]);
-    __syncthreads();
+    // this thread's 4 pixels of the running image are requested before the staging barriers
     const int y = ty0 + (t >> 4), xg = tx0 + (t & 15) * 4;
-    if (y >= y1 || xg >= x1 || xg + 4 <= x0) continue;
+    const bool active = !(y >= y1 || xg >= x1 || xg + 4 <= x0);
     const size_t o = ((size_t)y * W + xg) * 3;
     const bool full = xg >= x0 && xg + 4 <= x1;
-    uint32_t in_w[3], out_w[3] = {0u, 0u, 0u};
-    if (full) load12(bs.X + o, vec, 4, in_w);
-    else {
-      in_w[0] = in_w[1] = in_w[2] = 0u;
-      for (int i = 0; i < 4; ++i)
-        if (xg + i >= x0 && xg + i < x1)
-          for (int c = 0; c < 3; ++c) in_w[(3 * i + c) >> 2] |= (uint32_t)bs.X[o + 3 * i + c] << (((3 * i + c) & 3) * 8);
+    uint32_t in_w[3] = {0u, 0u, 0u}, out_w[3] = {0u, 0u, 0u};
+    if (active) {
+      if (full) load12(bs.X + o, vec, 4, in_w);
+      else
+        for (int i = 0; i < 4; ++i)
+          if (xg + i >= x0 && xg + i < x1)
+            for (int c = 0; c < 3; ++c) in_w[(3 * i + c) >> 2] |= (uint32_t)bs.X[o + 3 * i + c] << (((3 * i + c) & 3) * 8);
     }
+    __syncthreads();  // the previous tile's gathers are done (and the profile slices are in place)
+    const bool fast = staged && sr[3] - sr[1] <= 96;
+    if (staged) {
+      stage_rows(dyn, sv.pitch, bs.X, W, H, 3, sr[0], sr[1], sr[3] - sr[1]);
+      fill_rowoff(S.rowoff[0], sv, sr[3] - sr[1]);
+    }
+    __syncthreads();
+    if (!active) continue;
     const float uy = prof_smem ? S.u.prof[w + y - bs.rect[1]] : A.prof_y[(size_t)bs.gt * A.P.max_h + y];
+    const WarpRowTerm rt = warp_row_term(bs.minv, y);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int x = xg + i;
@@ -588,8 +636,9 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
         // m <= 2^-25: fl(1 - m) == 1 and fl(1 - 1) == 0, so img*1 + aug*0 == img exactly
         if (m > 2.98023223876953125e-8f) {
           int sx, sy, fx, fy, a[3];
-          warp_coord(bs.minv, x, y, sx, sy, fx, fy);
-          if (staged) staged_fetch3(sv, sx, sy, fx, fy, a);
+          warp_coord_row(bs.minv, rt, x, sx, sy, fx, fy);
+          if (fast && taps_inside(sv, sx, sy)) fast_fetch3(sv, S.rowoff[0], sx, sy, fx, fy, a);
+          else if (staged) staged_fetch3(sv, sx, sy, fx, fy, a);
           else {
             WarpTap tp;
             tp.sx = sx; tp.sy = sy; tp.fx = fx; tp.fy = fy;
@@ -702,8 +751,8 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
 
 // bg-only op (bbox_augmentation.py:240-272) on a sub-tile of 64 x 16 px that one region covers: the frame and the
 // uint8 union mask are both warped from staged shared-memory rows; 4 pixels per thread.
-__device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, uint8_t* dyn, const Lane& L, const RegOp& R, int r_only, int x0,
-                                        int y0, int x1, int y1, const double* div255) {
+__device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Lane& L, const RegOp& R,
+                                        int r_only, int x0, int y0, int x1, int y1, const double* div255) {
   const DevPlan& P = A.P;
   const int W = L.W, H = L.H, t = threadIdx.x;
   int sr[4];
@@ -733,12 +782,16 @@ __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, uint8_t* dyn, const 
     }
   }
   __syncthreads();  // the previous sub-tile's gathers are done
+  const bool fast = staged && rows <= 96;
   if (staged) {
     stage_rows(dyn, pitch_i, L.in, W, H, 3, sr[0], sr[1], rows);
     stage_rows(dyn + (size_t)rows * pitch_i, pitch_m, mu, W, H, 1, sr[0], sr[1], rows);
+    fill_rowoff(S.rowoff[0], si, rows);
+    fill_rowoff(S.rowoff[1], sm, rows);
   }
   __syncthreads();
   if (!active) return;
+  const WarpRowTerm rt = warp_row_term(R.minv, y);
   unsigned keep_mask = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -748,8 +801,11 @@ __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, uint8_t* dyn, const 
       keep_mask |= 1u << i;
       const int x = xg + i;
       int sx, sy, fx, fy, wm = 0;
-      warp_coord(R.minv, x, y, sx, sy, fx, fy);
-      if (staged) {
+      warp_coord_row(R.minv, rt, x, sx, sy, fx, fy);
+      if (fast && taps_inside(si, sx, sy)) {
+        fast_fetch3(si, S.rowoff[0], sx, sy, fx, fy, px);
+        wm = fast_fetch1(sm, S.rowoff[1], sx, sy, fx, fy);
+      } else if (staged) {
         staged_fetch3(si, sx, sy, fx, fy, px);
         wm = staged_fetch1(sm, sx, sy, fx, fy);
       } else if (any_src) {
@@ -859,7 +915,7 @@ __device__ OADG_HANDLER void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
             if (sub >= 0 && sub != r) continue;
             if (r < L.n_ml && !rect_hit(L.box[r], sx0, sy0, sx1, sy1)) continue;
           }
-          bg_subtile(A, dyn, L, S.rop[r], tile_pixel ? -1 : r, sx0, sy0, sx1, sy1, div255);
+          bg_subtile(A, S, dyn, L, S.rop[r], tile_pixel ? -1 : r, sx0, sy0, sx1, sy1, div255);
         }
     }
     if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) return;
@@ -1020,10 +1076,14 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
       tile = S.next_tile;
     }
     if (p + 1 < A.n_phases) {
+      const unsigned long long wait_t0 = globaltimer_ns();
       unsigned first = 0;
       if (threadIdx.x == 0) first = atomicAdd(A.tile_ctr + p + 1, 1u);   // claiming touches no phase data
       grid_barrier(A.bar, (unsigned)(p + 1) * (unsigned)G);
-      if (threadIdx.x == 0) S.next_tile = (int)first;
+      if (threadIdx.x == 0) {
+        S.next_tile = (int)first;
+        if (!(A.debug & 4)) atomicAdd(A.kind_ns + 10, globaltimer_ns() - wait_t0);   // slot 10: waiting at barriers
+      }
       __syncthreads();
     }
     if (b == 0 && threadIdx.x == 0) A.phase_ts[p + 1] = globaltimer_ns();

@@ -537,7 +537,7 @@ class OAMix:
             _lib.check(lib.oadg_oamix_execute_profiled(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
                                                        ctypes.byref(ms_chain), ctypes.byref(ms_mix), ctypes.byref(n_ph),
                                                        ph_ms, ph_kinds, cap, kstats.ctypes.data, s.cuda_stream))
-            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed')
+            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed', 'barrier_wait')
             ks = profile.setdefault('kind_busy_us_and_tiles', {k: [0.0, 0, 0.0] for k in names})
             for i, k in enumerate(names):
                 ks[k][0] += float(kstats[i]) / 1e3
