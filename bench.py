@@ -360,9 +360,9 @@ def product_arm(args):
                                      'bboxes-only chains, which count as zero useful bytes',
                 'avg_launch_ms': chain_ms / n_l,
                 'share_of_oamix_kernel_time': chain_ms / total_kernel_ms if total_kernel_ms else None,
-                'phases_per_launch': prof.get('phases', 0) / n_l,
-                'chain_phase_ms_by_item_kinds': {k: round(v, 4) for k, v in
-                                                 sorted(prof.get('phase_ms_by_kinds', {}).items(), key=lambda kv: -kv[1])},
+                'work_items_per_launch': prof.get('items', 0) / n_l, 'tiles_per_launch': prof.get('tiles', 0) / n_l,
+                'chain_cta_busy_us_per_launch_by_kind': {k: round(v[0] / n_l, 1) for k, v in
+                                                         prof.get('kind_busy_us_and_tiles', {}).items()},
                 'mix_kernel_ms': mix_ms, 'mix_launches': prof.get('mix_n', 0),
                 'oamix_whole_view_gbs': prof.get('view_bytes', 0) / (total_kernel_ms / 1e3) / 1e9 if total_kernel_ms else None,
                 'oamix_whole_view_frac': (prof.get('view_bytes', 0) / (total_kernel_ms / 1e3) / 1e9 / peak)

@@ -195,18 +195,16 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
                        int* launches_out, void* stream);
 
 /* Same as oadg_oamix_execute, with CUDA events on `stream` around the two launches (the chain kernel and the mix
- * kernel); the call synchronises the stream before returning (measurement only).  The chain kernel stamps
- * %globaltimer at every phase boundary: phase_ms[p] / phase_kinds[p] (bit k = the phase holds work items of kind k,
- * k = 0 profile, 1 mask, 2 hist, 3 lut, 4 frame copy, 5 bbo blend, 6 bbo catch-up, 7 depth step) receive up
- * to phase_cap entries; kind_stats (optional, 48 x uint64) receives the CTA-busy nanoseconds and the tile counts
- * summed per item kind
- * (16 + 16 + 16 slots: busy ns, tiles, longest tile ns; slots 7, 8, 9 split the depth-step tiles into streaming / staged bg-only / mixed). */
+ * kernel); the call synchronises the stream before returning (measurement only).  n_items_out / n_tiles_out: size
+ * of the chain kernel's work queue.  kind_stats (optional, 48 x uint64): CTA-busy nanoseconds [16], tiles [16] and
+ * longest tile ns [16] per work-item kind (0 profile, 1 mask, 2 hist, 3 lut, 4 frame copy, 5 bbo blend, 6 bbo
+ * catch-up, 7 / 8 / 9 depth-step tiles: streaming / staged bg-only / mixed; busy slot 10 = ns spent waiting for
+ * dependencies). */
 int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
                                 const uint8_t* const* src_dev, int n_img,
                                 uint8_t* const* dst_dev,
                                 void* workspace_dev, size_t workspace_bytes,
-                                float* ms_chain, float* ms_mix, int* n_phases_out,
-                                float* phase_ms, int32_t* phase_kinds, int phase_cap,
+                                float* ms_chain, float* ms_mix, int* n_items_out, int* n_tiles_out,
                                 unsigned long long* kind_stats, void* stream);
 
 /* ---- OA-Loss ---------------------------------------------------------------- */

@@ -21,8 +21,7 @@ SIGNATURES = {
     'oadg_oamix_workspace_bytes': (_c.c_int, [_vp, _sz, _c.POINTER(_sz)]),
     'oadg_oamix_execute': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
     'oadg_oamix_execute_profiled': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_f32),
-                                               _c.POINTER(_f32), _c.POINTER(_c.c_int), _c.POINTER(_f32),
-                                               _c.POINTER(_i32), _c.c_int, _vp, _vp]),
+                                               _c.POINTER(_f32), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _vp, _vp]),
     'oadg_oamix_sample_plan': (_c.c_int, [_vp, _vp, _c.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _c.POINTER(_sz),
                                           _vp, _vp, _vp, _vp, _vp]),
     'oadg_supcon_workspace_bytes': (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_sz)]),

@@ -8,12 +8,13 @@
 //   plan        the host-sampled plan blob (oadg.h records) + work tables, one H2D copy
 //
 // Two launches per batch:
-//   oamix_chain_kernel   ONE persistent launch (four independent 256-thread CTAs per SM) that walks the host-built PHASES
-//                        (oamix_exec.h): mask profiles, union masks, histograms, LUTs, the bboxes-only chains
-//                        level by level and every depth step of every (view, branch) lane.  A phase is a list
-//                        of independent work items cut into tiles; each CTA owns a cost-balanced contiguous tile
-//                        range per phase; phases are separated by a grid barrier (release/acquire on one
-//                        counter), so nothing returns to the host between the ~10-40 dependent stages.
+//   oamix_chain_kernel   ONE persistent launch (four independent 256-thread CTAs per SM) that drains the host-built
+//                        work queue (oamix_exec.h): mask profiles, union masks, histograms, LUTs, the bboxes-only
+//                        chains level by level and every depth step of every (view, branch) lane.  The queue is a
+//                        list of work items cut into tiles, ordered so that dependencies come first; CTAs claim
+//                        tiles with one atomic counter and an item starts as soon as the items it depends on are
+//                        complete (per-item completion counters, no grid-wide barrier), so nothing returns to the
+//                        host between the ~10-40 dependent stages.
 //   mix_kernel           branch mixing + object-aware mixing of all views (oa_mix.py:236,281-309)
 #include <stdlib.h>
 
@@ -84,19 +85,34 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return v;
 }
 
-// All CTAs are co-resident (cooperative launch, one per SM).  Monotonic counter: barrier k completes at k * grid.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
-  __syncthreads();
+// ---- dependencies between work items -------------------------------------------------------------------------
+// All CTAs are co-resident (cooperative launch) and claim tiles in queue order, so every tile an item waits for was
+// claimed earlier by a CTA that is running: waiting cannot deadlock.  A finished tile is published with
+// bar.sync + fence + atomic add by one thread; a waiter polls the counters with acquire loads, fences and bar.syncs
+// before the CTA touches the data (the pattern of a cooperative-groups grid sync, per item instead of per grid).
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_for_deps(const ChainArgs& A, const Item& I) {
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-    } while (v < target);
+    for (int k = 0; k < I.dep_count; ++k) {
+      const int d = A.deps[I.dep_first + k];
+      const unsigned need = (unsigned)A.items[d].ntiles;
+      while (ld_acquire(A.done + d) < need) {
+      }
+    }
     __threadfence();
   }
   __syncthreads();
+}
+__device__ __forceinline__ void publish_tile(const ChainArgs& A, int item) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(A.done + item, 1u);
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -338,17 +354,56 @@ __device__ OADG_HANDLER void lut_tile(const ChainArgs& A, ChainSmem& S, int job)
   const int tid = threadIdx.x;
   __syncthreads();
   if (op.kind == OADG_OP_AUTOCONTRAST || op.kind == OADG_OP_EQUALIZE) {
-    // 3 channels x 256 entries: the histogram goes to shared memory first, then one thread per channel scans it
-    if (tid == 0) S.bs_key = -1;   // u.hist overwrites the staged profile slices
-    for (int i = tid; i < 768; i += kCT) S.u.hist[0][i] = A.hist[(size_t)J.hist_slot * 768 + i];
-    __syncthreads();
-    if (tid < 3) {
-      const unsigned* h = S.u.hist[0] + tid * 256;
-      if (op.kind == OADG_OP_AUTOCONTRAST) lut_autocontrast_ch(h, S.tab[tid]);
-      else lut_equalize_ch(h, S.tab[tid]);
+    // one thread per bin, channel after channel (same integer / float64 arithmetic as lut_autocontrast_ch /
+    // lut_equalize_ch in oamix_math.h, with the scans done by ballots and a block prefix sum)
+    unsigned* msk = reinterpret_cast<unsigned*>(S.red);        // [8] non-empty-bin masks of the 8 warps
+    unsigned* wsum = reinterpret_cast<unsigned*>(S.red) + 8;   // [8] per-warp histogram sums
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int c = 0; c < 3; ++c) {
+      const unsigned hv = A.hist[(size_t)J.hist_slot * 768 + c * 256 + tid];
+      const unsigned bal = __ballot_sync(0xffffffffu, hv != 0u);
+      unsigned incl = hv;   // inclusive prefix sum inside the warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      __syncthreads();
+      if (lane == 31) wsum[warp] = incl;
+      if (lane == 0) msk[warp] = bal;
+      __syncthreads();
+      int lo = 256, hi = -1, nnz = 0;
+      unsigned total = 0, before = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const unsigned m = msk[w];
+        if (m) {
+          if (lo == 256) lo = w * 32 + __ffs(m) - 1;
+          hi = w * 32 + 31 - __clz(m);
+        }
+        nnz += __popc(m);
+        total += wsum[w];
+        if (w < warp) before += wsum[w];
+      }
+      const unsigned excl = before + incl - hv;   // sum of the bins below this one
+      uint8_t r = (uint8_t)tid;
+      if (op.kind == OADG_OP_AUTOCONTRAST) {
+        if (hi > lo) {
+          const double scale = 255.0 / (double)(hi - lo);
+          const double offset = dmul((double)(-lo), scale);
+          const int v = (int)dadd(dmul((double)tid, scale), offset);
+          r = (uint8_t)imin(imax(v, 0), 255);
+        }
+      } else {
+        const unsigned last = hi >= 0 ? A.hist[(size_t)J.hist_slot * 768 + c * 256 + hi] : 0u;
+        const unsigned step = nnz <= 1 ? 0u : (total - last) / 255u;
+        if (step) {
+          const unsigned v = (step / 2 + excl) / step;
+          r = (uint8_t)(v > 255u ? 255u : v);   // Image.point clips list entries to 8 bits
+        }
+      }
+      out[c * 256 + tid] = r;
     }
-    __syncthreads();
-    for (int i = tid; i < 768; i += kCT) out[i] = (&S.tab[0][0])[i];
     return;
   }
   if (tid < 256) {
@@ -594,9 +649,10 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
   }
   const bool vec = ((W * 3) & 3) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 3) == 0;
   const int ax0 = bs.rect[0] & ~3, tx = I.tx;
-  for (int k2 = 2 * l0; k2 < 2 * l1; ++k2) {   // two 64 x 16 sub-tiles per tile, each with its own staged source
-    const int k = k2 >> 1;
-    const int tx0 = ax0 + (k % tx) * kBboTileW + (k2 & 1) * kSubW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
+  constexpr int kSubPerTile = kBboTileW / kSubW;   // 64 x 16 sub-tiles per tile, each with its own staged source
+  for (int k2 = kSubPerTile * l0; k2 < kSubPerTile * l1; ++k2) {
+    const int k = k2 / kSubPerTile;
+    const int tx0 = ax0 + (k % tx) * kBboTileW + (k2 % kSubPerTile) * kSubW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
     const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kSubW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
     if (x1 <= x0) continue;   // uniform: the support ends inside the first sub-tile
     int sr[4];
@@ -1006,87 +1062,72 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
     S.args = Aparam;
     S.bs_key = -1;
     S.prof_ready = 0;
-    if (blockIdx.x == 0) Aparam.phase_ts[0] = globaltimer_ns();
   }
   __syncthreads();
   const ChainArgs& A = S.args;
-  const int b = blockIdx.x, G = gridDim.x;
-  int staged_lane = -1;
-  for (int p = 0; p < A.n_phases; ++p) {
-    const Phase ph = A.phases[p];
-    int it = ph.item0;
-    const int it_end = ph.item0 + ph.n_items;
-    // dynamic tile claims: thread 0 fetches the next index while the CTA works on the current tile (the first
-    // claim of a phase was taken before the barrier that opened it)
-    if (p == 0) {
-      if (threadIdx.x == 0) S.next_tile = (int)atomicAdd(A.tile_ctr, 1u);
-      __syncthreads();
+  int staged_lane = -1, ready_item = -1, it = 0;
+  // dynamic tile claims: thread 0 fetches the next index while the CTA works on the current tile
+  if (threadIdx.x == 0) S.next_tile = (int)atomicAdd(A.queue, 1u);
+  __syncthreads();
+  int tile = S.next_tile;
+  while (tile < A.n_tiles) {
+    __syncthreads();  // every thread has read S.next_tile
+    unsigned claim = 0;
+    if (threadIdx.x == 0) claim = atomicAdd(A.queue, 1u);
+    while (it + 1 < A.n_items && tile >= A.items[it].tile0 + A.items[it].ntiles) ++it;
+    const Item I = A.items[it];
+    const int l0 = tile - I.tile0, l1 = l0 + 1;
+    const unsigned long long wait_t0 = globaltimer_ns();
+    if (it != ready_item) {   // first tile of this item on this CTA: its inputs must be complete
+      wait_for_deps(A, I);
+      ready_item = it;
     }
-    int tile = S.next_tile;
-    while (tile < ph.n_tiles) {
-      __syncthreads();  // every thread has read S.next_tile
-      unsigned claim = 0;
-      if (threadIdx.x == 0) claim = atomicAdd(A.tile_ctr + p, 1u);
-      while (it + 1 < it_end && tile >= A.items[it].tile0 + A.items[it].ntiles) ++it;
-      const Item I = A.items[it];
-      const int l0 = tile - I.tile0, l1 = l0 + 1;
-      const unsigned long long seg_t0 = globaltimer_ns();
-      switch (I.kind) {
-        case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;
-        case OADG_IT_MASK:
-          for (int k = l0; k < l1; ++k) mask_tile(A, S, I.obj, k, I.tx);
-          break;
-        case OADG_IT_HIST: {
-          const Lane& L = A.lanes[I.obj];
-          unsigned long long lsum = 0;
-          hist_begin(S);
-          for (int k = l0; k < l1; ++k) hist_tile(L, S, k, lsum);
-          hist_flush(A, S, L.hist_slot, lsum);
-          break;
-        }
-        case OADG_IT_LUT: lut_tile(A, S, I.obj); break;
-        case OADG_IT_COPY: {
-          const Chain& C = A.chains[I.obj];
-          const oadg_view_t& V = A.P.views[C.view];
-          copy_segment(C, (size_t)V.H * V.W * 3, I.aux != 0, l0, l1);
-          break;
-        }
-        case OADG_IT_BBO_R: bbo_r_segment(A, S, dyn, I, l0, l1); break;
-        case OADG_IT_BBO_C: bbo_c_segment(A, S, I, l0, l1); break;
-        case OADG_IT_STEP:
-          if (staged_lane != I.obj) {
-            stage_lane(A, S, I.obj);
-            staged_lane = I.obj;
-          }
-          for (int k = l0; k < l1; ++k) step_tile(A, S, dyn, k, I.tx, I.aux, div255);
-          break;
-        default: break;
+    const unsigned long long seg_t0 = globaltimer_ns();
+    switch (I.kind) {
+      case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;
+      case OADG_IT_MASK:
+        for (int k = l0; k < l1; ++k) mask_tile(A, S, I.obj, k, I.tx);
+        break;
+      case OADG_IT_HIST: {
+        const Lane& L = A.lanes[I.obj];
+        unsigned long long lsum = 0;
+        hist_begin(S);
+        for (int k = l0; k < l1; ++k) hist_tile(L, S, k, lsum);
+        hist_flush(A, S, L.hist_slot, lsum);
+        break;
       }
-      if (threadIdx.x == 0) {
-        if (!(A.debug & 4)) {
-          const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
-          const unsigned long long dt = globaltimer_ns() - seg_t0;
-          atomicAdd(A.kind_ns + kk, dt);
-          atomicAdd(A.kind_ns + 16 + kk, (unsigned long long)(l1 - l0));
-          atomicMax(A.kind_ns + 32 + kk, dt);
-        }
-        S.next_tile = (int)claim;
+      case OADG_IT_LUT: lut_tile(A, S, I.obj); break;
+      case OADG_IT_COPY: {
+        const Chain& C = A.chains[I.obj];
+        const oadg_view_t& V = A.P.views[C.view];
+        copy_segment(C, (size_t)V.H * V.W * 3, I.aux != 0, l0, l1);
+        break;
       }
-      __syncthreads();
-      tile = S.next_tile;
+      case OADG_IT_BBO_R: bbo_r_segment(A, S, dyn, I, l0, l1); break;
+      case OADG_IT_BBO_C: bbo_c_segment(A, S, I, l0, l1); break;
+      case OADG_IT_STEP:
+        if (staged_lane != I.obj) {
+          stage_lane(A, S, I.obj);
+          staged_lane = I.obj;
+        }
+        for (int k = l0; k < l1; ++k) step_tile(A, S, dyn, k, I.tx, I.aux, div255);
+        break;
+      default: break;
     }
-    if (p + 1 < A.n_phases) {
-      const unsigned long long wait_t0 = globaltimer_ns();
-      unsigned first = 0;
-      if (threadIdx.x == 0) first = atomicAdd(A.tile_ctr + p + 1, 1u);   // claiming touches no phase data
-      grid_barrier(A.bar, (unsigned)(p + 1) * (unsigned)G);
-      if (threadIdx.x == 0) {
-        S.next_tile = (int)first;
-        if (!(A.debug & 4)) atomicAdd(A.kind_ns + 10, globaltimer_ns() - wait_t0);   // slot 10: waiting at barriers
+    publish_tile(A, it);
+    if (threadIdx.x == 0) {
+      if (!(A.debug & 4)) {
+        const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
+        const unsigned long long dt = globaltimer_ns() - seg_t0;
+        atomicAdd(A.kind_ns + kk, dt);
+        atomicAdd(A.kind_ns + 16 + kk, 1ull);
+        atomicMax(A.kind_ns + 32 + kk, dt);
+        atomicAdd(A.kind_ns + 10, seg_t0 - wait_t0);   // slot 10: waiting for dependencies
       }
-      __syncthreads();
+      S.next_tile = (int)claim;
     }
-    if (b == 0 && threadIdx.x == 0) A.phase_ts[p + 1] = globaltimer_ns();
+    __syncthreads();
+    tile = S.next_tile;
   }
 }
 
@@ -1126,10 +1167,8 @@ struct CudaBackend {
   // optional CUDA-event timing of the two launches (oadg_oamix_execute_profiled)
   bool profile = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  int n_phases = 0;
-  const unsigned long long* phase_ts_dev = nullptr;
+  int n_items = 0, n_tiles = 0;
   const unsigned long long* kind_ns_dev = nullptr;
-  std::vector<int32_t> phase_kinds;  // bit k set: the phase holds items of kind k; bits 8..: tiles in the phase
 
   int grid() {
     if (n_sm == 0) {
@@ -1160,17 +1199,12 @@ struct CudaBackend {
     if (profile) {
       for (auto& e : ev) BE_TRY(cudaEventCreate(&e));
       BE_TRY(cudaEventRecord(ev[0], stream));
-      n_phases = A.n_phases;
-      phase_ts_dev = A.phase_ts;
+      n_items = A.n_items;
+      n_tiles = A.n_tiles;
       kind_ns_dev = A.kind_ns;
-      phase_kinds.assign(A.n_phases, 0);
-      for (int p = 0; p < A.n_phases; ++p)
-        {
-        for (int k = 0; k < Hh.phases[p].n_items; ++k) phase_kinds[p] |= 1 << Hh.items[Hh.phases[p].item0 + k].kind;
-        phase_kinds[p] |= Hh.phases[p].n_tiles << 8;
-      }
     }
-    if (A.n_phases > 0) {
+    (void)Hh;
+    if (A.n_tiles > 0) {
       ChainArgs args = A;
       if (const char* dbg = getenv("OADG_DEBUG")) args.debug = atoi(dbg);
       void* params[2] = {(void*)&args, (void*)&div255};
@@ -1210,28 +1244,20 @@ extern "C" int oadg_oamix_workspace_bytes(const void* plan_host, size_t plan_byt
 
 extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes, const uint8_t* const* src_dev,
                                            int n_img, uint8_t* const* dst_dev, void* workspace_dev,
-                                           size_t workspace_bytes, float* ms_chain, float* ms_mix,
-                                           int* n_phases_out, float* phase_ms, int32_t* phase_kinds, int phase_cap,
-                                           unsigned long long* kind_stats, void* stream) {
-  if (!ms_chain || !ms_mix || !n_phases_out) return OADG_E_ARG;
+                                           size_t workspace_bytes, float* ms_chain, float* ms_mix, int* n_items_out,
+                                           int* n_tiles_out, unsigned long long* kind_stats, void* stream) {
+  if (!ms_chain || !ms_mix) return OADG_E_ARG;
   CudaBackend be;
   be.stream = (cudaStream_t)stream;
   be.profile = true;
   int rc = execute_plan(be, plan_host, plan_bytes, src_dev, n_img, dst_dev, workspace_dev, workspace_bytes);
   cudaError_t e = cudaStreamSynchronize(be.stream);
   *ms_chain = *ms_mix = 0.f;
-  *n_phases_out = 0;
+  if (n_items_out) *n_items_out = be.n_items;
+  if (n_tiles_out) *n_tiles_out = be.n_tiles;
   if (rc == 0 && e == cudaSuccess && be.ev[2]) {
     cudaEventElapsedTime(ms_chain, be.ev[0], be.ev[1]);
     cudaEventElapsedTime(ms_mix, be.ev[1], be.ev[2]);
-    *n_phases_out = be.n_phases;
-    if (phase_ms && phase_kinds && be.n_phases > 0) {
-      std::vector<unsigned long long> ts(be.n_phases + 1);
-      e = cudaMemcpy(ts.data(), be.phase_ts_dev, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-      // ts[0] = CTA 0 entering the kernel, ts[p + 1] = CTA 0 leaving the barrier that ends phase p
-      for (int p = 0; p < be.n_phases && p < phase_cap; ++p) phase_ms[p] = (float)((double)(ts[p + 1] - ts[p]) * 1e-6);
-      for (int p = 0; p < be.n_phases && p < phase_cap; ++p) phase_kinds[p] = be.phase_kinds[p];
-    }
     if (kind_stats && be.kind_ns_dev)
       e = cudaMemcpy(kind_stats, be.kind_ns_dev, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   }

@@ -60,8 +60,8 @@ OADG_HD const uint8_t* chain_src(const Chain& C, int level) { return level == 1 
 OADG_HD uint8_t* chain_dst(const Chain& C, int level) { return (level & 1) ? C.T : C.S; }
 
 // ---- work items of the chain kernel ------------------------------------------------------------------------
-// The host turns a plan into PHASES of independent work ITEMS; items are cut into TILES (one CTA iteration each).
-// Phase p+1 may read anything phase p wrote (grid barrier in between).
+// The host turns a plan into a queue of work ITEMS cut into TILES (one CTA iteration each), ordered so that every item
+// comes after the items it depends on; an item starts when all tiles of its dependencies are done.
 enum {
   OADG_IT_PROFILE = 0,   // obj = gt*2 + axis            1 tile
   OADG_IT_MASK = 1,      // obj = view                   tiles of 256 x 8 px
@@ -75,13 +75,10 @@ enum {
 };
 struct Item {
   int32_t kind, obj;
-  int32_t tile0, ntiles;   // tile0: first tile index within the phase
+  int32_t tile0, ntiles;   // tile0: first tile index in the work queue
   int32_t tx;              // tiles per row (2-D kinds)
   int32_t aux;
-  int32_t pad[2];
-};
-struct Phase {
-  int32_t item0, n_items, n_tiles, pad;
+  int32_t dep_first, dep_count;   // the items (indices into the item table) that must be complete before this one starts
 };
 constexpr int kMaskTileW = 256, kMaskTileH = 8;
 constexpr int kHistTilePx = 32768;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "oamix_body.h"
@@ -93,11 +94,11 @@ inline int parse_plan(const void* blob, size_t bytes, PlanView& pv) {
 struct Layout {
   size_t frame_bytes;
   size_t off_plan, off_prof_x, off_prof_y, off_branch, off_scratch, off_zero, off_hist, off_luma, off_lut, off_tables;
-  size_t off_maskf, off_masku, off_ts;
+  size_t off_maskf, off_masku;
   size_t zero_bytes;
   int any_bg;
   size_t tables_bytes;
-  int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_phases, n_bbo;
+  int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_deps, n_bbo;
   size_t total;
 };
 
@@ -135,7 +136,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.n_hist = n_hist;
   L.n_bbo = h.n_bbo;
   L.max_items = 2 * h.n_gt + h.n_views + 2 * lanes_total + n_lut + n_chains + 2 * h.n_bbo + 8;
-  L.max_phases = 4 + max_depth * (3 + max_chain);
+  L.max_deps = 8 * L.max_items + n_chains * 4 * max_chain * max_chain + 64;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -147,7 +148,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
                    align_up_sz((size_t)(n_chains > 0 ? n_chains : 1) * sizeof(Chain), 16) +
                    align_up_sz((size_t)(h.n_bbo > 0 ? h.n_bbo : 1) * sizeof(BboJob), 16) +
                    align_up_sz((size_t)L.max_items * sizeof(Item), 16) +
-                   align_up_sz((size_t)L.max_phases * sizeof(Phase), 16) +
+                   align_up_sz((size_t)L.max_deps * sizeof(int32_t), 16) +
                    align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
   L.off_tables = align_up_sz((size_t)h.total_bytes, 16);
@@ -159,9 +160,9 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.off_branch = take(n_branch_frames * L.frame_bytes);
   L.off_scratch = take((size_t)n_chains * 2 * L.frame_bytes);  // S + T per chain
   // one memset: [grid barrier counter | histograms | luma sums]
-  // [0] barrier counter; bytes 64..447: busy ns [16], tile counts [16], longest tile ns [16] per item kind (uint64); bytes 512..: one tile
-  // counter per phase
-  L.off_zero = take(512 + (size_t)L.max_phases * sizeof(unsigned));
+  // one memset: [0] work-queue counter; bytes 64..447: busy ns [16], tile counts [16], longest tile ns [16] per item
+  // kind (uint64); bytes 512..: tiles done per item | histograms | luma sums
+  L.off_zero = take(512 + (size_t)L.max_items * sizeof(unsigned));
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
   L.zero_bytes = o - L.off_zero;
@@ -170,7 +171,6 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   const size_t mask_px = (size_t)h.max_h * h.max_w;
   L.off_maskf = take(any_bg ? (size_t)h.n_views * mask_px * sizeof(float) : 0);
   L.off_masku = take(any_bg ? (size_t)h.n_views * mask_px : 0);
-  L.off_ts = take((size_t)(L.max_phases + 2) * sizeof(unsigned long long));
   L.total = o;
 }
 
@@ -259,8 +259,8 @@ inline void schedule_chain(const PlanView& pv, const oadg_view_t& V, const oadg_
   }
 }
 
-// Tiles of a phase are claimed dynamically (one atomic counter per phase), in item order: items that hold long
-// tiles come first so that the tail of a phase is made of short ones.
+// Tiles are claimed dynamically from one queue, in item order: within one dependency depth the items that hold long
+// tiles come first so that the short ones fill the gaps.
 inline int item_priority(int kind, bool lane_all_streaming) {
   switch (kind) {
     case OADG_IT_PROFILE: return 0;
@@ -281,9 +281,10 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   const Chain* chains;
   const BboJob* bjobs;
   const Item* items;
-  const Phase* phases;
-  unsigned* tile_ctr;        // [n_phases] next unclaimed tile of every phase (zeroed before the launch)
-  int32_t n_phases, grid;
+  const int32_t* deps;       // dependency lists of the items
+  int32_t n_items, n_tiles, grid, debug;
+  unsigned* queue;           // next unclaimed tile (zeroed before the launch)
+  unsigned* done;            // [n_items] finished tiles of every item (zeroed before the launch)
   unsigned* hist;
   unsigned long long* luma;
   uint8_t* luts;
@@ -293,16 +294,13 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   uint8_t* masku;
   const uint8_t* scratch;
   size_t frame_bytes;
-  unsigned* bar;               // grid barrier counter (zeroed before the launch)
-  unsigned long long* phase_ts;  // globaltimer at the end of every phase (measurement aid)
-  int32_t debug;                 // bit 0: no staged bg gathers, bit 1: no staged bbo gathers (OADG_DEBUG, tests only)
-  unsigned long long* kind_ns;   // [16] CTA-busy nanoseconds per item kind, then [16] tiles per kind (measurement aid)
+  unsigned long long* kind_ns;   // [16] CTA-busy ns per item kind, [16] tiles per kind, [16] longest tile (measurement aid)
 };
 
 // Backend concept (all return 0 or an error code):
 //   grid()                         CTAs the chain kernel will run (one per SM)
 //   upload(dst, src_host, bytes)   zero(dst, bytes)
-//   chain(args, host_tables...)    the phase/item interpreter (one persistent launch on the device)
+//   chain(args, host_tables...)    the work-queue interpreter (one persistent launch on the device)
 //   mix(P, jobs, n)
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
@@ -359,42 +357,59 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const size_t t_chain = carve((size_t)(L.n_chains > 0 ? L.n_chains : 1) * sizeof(Chain));
   const size_t t_bjob = carve((size_t)(L.n_bbo > 0 ? L.n_bbo : 1) * sizeof(BboJob));
   const size_t t_items = carve((size_t)L.max_items * sizeof(Item));
-  const size_t t_phases = carve((size_t)L.max_phases * sizeof(Phase));
+  const size_t t_deps = carve((size_t)L.max_deps * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
   auto* chains = reinterpret_cast<Chain*>(stage.data() + t_chain);
   auto* bjobs = reinterpret_cast<BboJob*>(stage.data() + t_bjob);
   auto* items = reinterpret_cast<Item*>(stage.data() + t_items);
-  auto* phases = reinterpret_cast<Phase*>(stage.data() + t_phases);
+  auto* deps = reinterpret_cast<int32_t*>(stage.data() + t_deps);
   auto* mixjobs = reinterpret_cast<MixJob*>(stage.data() + t_mix);
 
   // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
+  // `phase` (the length of the longest dependency chain below an item) only orders the work queue; what an item
+  // actually waits for is its `deps` list (indices into `todo`).
   struct Todo {
     int kind, obj, phase, w, hgt, aux;   // w x hgt: pixel extent (2-D kinds) / w = linear size (1-D kinds)
+    std::vector<int> deps;
   };
   std::vector<Todo> todo;
   todo.reserve(L.max_items);
   int n_phases = 0;
   auto add = [&](int kind, int obj, int phase, int w, int hgt, int aux) {
-    todo.push_back(Todo{kind, obj, phase, w, hgt, aux});
+    todo.push_back(Todo{kind, obj, phase, w, hgt, aux, {}});
     n_phases = phase + 1 > n_phases ? phase + 1 : n_phases;
+    return (int)todo.size() - 1;
+  };
+  auto dep = [&](int item, int on) {
+    if (on >= 0) todo[item].deps.push_back(on);
   };
   const int prof_done = h.n_gt > 0 ? 1 : 0;
+  std::vector<int> prof_item((size_t)h.n_gt * 2, -1);
   for (int g = 0; g < h.n_gt; ++g)
-    for (int axis = 0; axis < 2; ++axis) add(OADG_IT_PROFILE, g * 2 + axis, 0, 1, 1, 0);
+    for (int axis = 0; axis < 2; ++axis) prof_item[g * 2 + axis] = add(OADG_IT_PROFILE, g * 2 + axis, 0, 1, 1, 0);
   int mask_done = prof_done;
+  std::vector<int> mask_item(h.n_views, -1);
   if (L.any_bg) {  // union mask of every view (views without gt boxes get zeros)
-    for (int v = 0; v < h.n_views; ++v) add(OADG_IT_MASK, v, prof_done, pv.views[v].W, pv.views[v].H, 0);
+    for (int v = 0; v < h.n_views; ++v) {
+      const oadg_view_t& V = pv.views[v];
+      mask_item[v] = add(OADG_IT_MASK, v, prof_done, V.W, V.H, 0);
+      for (int g = V.gt_first; g < V.gt_first + V.n_gt; ++g) {
+        dep(mask_item[v], prof_item[2 * g]);
+        dep(mask_item[v], prof_item[2 * g + 1]);
+      }
+    }
     mask_done = prof_done + 1;
   }
 
   int lane_n = 0, hist_n = 0, lut_n = 0, chain_n = 0, bjob_n = 0;
   std::vector<const uint8_t*> final_frame((size_t)h.n_views * OADG_MAX_WIDTH, nullptr);
   std::vector<int> step_phase((size_t)h.n_views * OADG_MAX_WIDTH, -1);  // phase of the lane's previous step
+  std::vector<int> step_item((size_t)h.n_views * OADG_MAX_WIDTH, -1);   // ... and its item
   struct HistKey {
     const uint8_t* in;
-    int slot, done;
+    int slot, done, item;
   };
   std::vector<HistKey> hist_keys;
   ChainSched cs;
@@ -421,22 +436,27 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
         for (int r = 0; r < OADG_MAX_REGIONS; ++r) ln.kind[r] = ln.lut[r] = ln.scratch[r] = -1;
         final_frame[(size_t)v * OADG_MAX_WIDTH + b] = ln.out;
         const int ready = step_phase[(size_t)v * OADG_MAX_WIDTH + b] + 1;  // phase in which ln.in is complete
+        const int prev_step = step_item[(size_t)v * OADG_MAX_WIDTH + b];   // the item that writes ln.in (-1: source)
+        std::vector<int> step_deps;
+        if (prev_step >= 0) step_deps.push_back(prev_step);
         int step_at = ready;
         bool hist = false;
         for (int r = 0; r <= V.n_ml; ++r) hist |= needs_hist(ops[ln.op_base + r].kind);
-        int hist_done = 0;
+        int hist_done = 0, hist_item = -1;
         if (hist) {  // lanes of one view share the histogram of the source frame at depth 0
           int found = -1;
           for (size_t k = 0; k < hist_keys.size(); ++k)
             if (hist_keys[k].in == ln.in) found = (int)k;
           if (found < 0) {
-            hist_keys.push_back(HistKey{ln.in, hist_n++, ready + 1});
+            hist_keys.push_back(HistKey{ln.in, hist_n++, ready + 1, -1});
             found = (int)hist_keys.size() - 1;
             ln.hist_slot = hist_keys[found].slot;
-            add(OADG_IT_HIST, lane_id, ready, V.W * V.H, 1, 0);
+            hist_keys[found].item = add(OADG_IT_HIST, lane_id, ready, V.W * V.H, 1, 0);
+            dep(hist_keys[found].item, prev_step);
           }
           ln.hist_slot = hist_keys[found].slot;
           hist_done = hist_keys[found].done;
+          hist_item = hist_keys[found].item;
         }
         for (int r = 0; r <= V.n_ml; ++r) {
           oadg_op_t& op = ops[ln.op_base + r];
@@ -446,7 +466,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
             op.lut = lut_n;
             lutjobs[lut_n] = LutJob{ln.op_base + r, ln.hist_slot, v, 0};
             const int at = needs_hist(op.kind) ? hist_done : 0;
-            add(OADG_IT_LUT, lut_n, at, 1, 1, 0);
+            const int li = add(OADG_IT_LUT, lut_n, at, 1, 1, 0);
+            if (needs_hist(op.kind)) dep(li, hist_item);
+            step_deps.push_back(li);
             step_at = at + 1 > step_at ? at + 1 : step_at;
             ++lut_n;
           } else if (op.kind == OADG_OP_BBO_AFFINE && op.bbo_count > 0) {
@@ -464,7 +486,8 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
               const int NL = cs.n_levels;
               op.scratch = 2 * c_id + (NL & 1);  // the step reads Y of the last level: T when NL is odd, else S
               // T (and S when a second level exists) start as copies of the lane input
-              add(OADG_IT_COPY, c_id, ready, V.W * V.H * 3, 1, NL >= 2 ? 1 : 0);
+              const int copy_item = add(OADG_IT_COPY, c_id, ready, V.W * V.H * 3, 1, NL >= 2 ? 1 : 0);
+              dep(copy_item, prev_step);
               const int r0 = (ready + 1 > prof_done ? ready + 1 : prof_done);
               // jobs of the chain sorted by level (stable): level l occupies [first[l], first[l+1])
               std::vector<int> first(NL + 2, 0);
@@ -485,17 +508,34 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
                 for (int e = 0; e < 4; ++e) J.rect[e] = s[e];
               }
               bjob_n += (int)cs.box.size();
+              // items that run "in level l": the blends of level l and the catch-ups of the level l-1 boxes.  They
+              // read the frame level l-1 wrote and write the frame level l-1 read, so each waits for ALL items of
+              // level l-1 (level 1: for the initial copy); a blend also needs its box's two mask profiles.
+              std::vector<std::vector<int>> lvl_items(NL + 1);
               for (int k = job0; k < bjob_n; ++k) {
                 const BboJob& J = bjobs[k];
                 const int w = J.rect[2] - (J.rect[0] & ~3), hg = J.rect[3] - J.rect[1];  // tiles on a 4-px grid
-                add(OADG_IT_BBO_R, k, r0 + J.level - 1, w, hg, 0);
-                if (J.level < NL) add(OADG_IT_BBO_C, k, r0 + J.level, w, hg, 0);   // caught up by the next level
+                const int ri = add(OADG_IT_BBO_R, k, r0 + J.level - 1, w, hg, 0);
+                lvl_items[J.level].push_back(ri);
+                const int g = pv.bbo[J.bbo].gt;
+                dep(ri, prof_item[2 * g]);
+                dep(ri, prof_item[2 * g + 1]);
+                if (J.level < NL)   // caught up by the next level
+                  lvl_items[J.level + 1].push_back(add(OADG_IT_BBO_C, k, r0 + J.level, w, hg, 0));
               }
+              for (int l = 1; l <= NL; ++l)
+                for (int it : lvl_items[l]) {
+                  if (l == 1) dep(it, copy_item);
+                  else
+                    for (int pr : lvl_items[l - 1]) dep(it, pr);
+                }
+              for (int it : lvl_items[NL]) step_deps.push_back(it);
               const int done = r0 + NL;
               step_at = done > step_at ? done : step_at;
             }
           } else if (op.kind == OADG_OP_BG_AFFINE) {
             step_at = mask_done > step_at ? mask_done : step_at;
+            step_deps.push_back(mask_item[v]);
           }
         }
         for (int r = 0; r <= V.n_ml; ++r) {
@@ -504,63 +544,92 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           ln.scratch[r] = ops[ln.op_base + r].scratch;
           if (!(is_lut_kind(ln.kind[r]) || ln.kind[r] == OADG_OP_BBO_AFFINE)) ln.all_streaming = 0;
         }
-        add(OADG_IT_STEP, lane_id, step_at, V.W, V.H, 0);
+        const int si = add(OADG_IT_STEP, lane_id, step_at, V.W, V.H, 0);
+        for (int d2 : step_deps) dep(si, d2);
         step_phase[(size_t)v * OADG_MAX_WIDTH + b] = step_at;
+        step_item[(size_t)v * OADG_MAX_WIDTH + b] = si;
       }
     }
   }
-  if (n_phases > L.max_phases || (int)todo.size() > L.max_items) return OADG_E_LIMIT;
+  if ((int)todo.size() > L.max_items) return OADG_E_LIMIT;
 
-  // ---- phase tables: items grouped by phase (long-tile kinds first), tiles numbered within the phase ----------
-  std::vector<int> order(todo.size());
+  // ---- the work queue: items ordered by their estimated start time (a list schedule with rough per-kind tile
+  // durations), so that a CTA seldom claims a tile whose inputs are not ready while ready work waits behind it;
+  // ties: long-tile kinds first.  Dependencies always start earlier, so the order is topological.
+  const int n_items = (int)todo.size();
+  std::vector<int> order(n_items), pos(n_items);
   {
-    std::vector<int> count(n_phases + 1, 0);
-    for (const Todo& t : todo) ++count[t.phase + 1];
-    for (int p = 0; p < n_phases; ++p) count[p + 1] += count[p];
-    // stable counting sort by (phase, priority)
-    std::vector<int> fill(count.begin(), count.end() - 1);
-    for (int pr = 0; pr <= 8; ++pr)
-      for (size_t i = 0; i < todo.size(); ++i) {
-        const Todo& t = todo[i];
-        if (item_priority(t.kind, t.kind == OADG_IT_STEP && lanes[t.obj].all_streaming) == pr) order[fill[t.phase]++] = (int)i;
-      }
-    for (int p = 0; p < n_phases; ++p) {
-      phases[p].item0 = count[p];
-      phases[p].n_items = count[p + 1] - count[p];
-      phases[p].n_tiles = 0;
-      phases[p].pad = 0;
-    }
-  }
-  for (int p = 0; p < n_phases; ++p) {
-    Phase& ph = phases[p];
-    int tile0 = 0;
-    for (int k = 0; k < ph.n_items; ++k) {
-      const Todo& t = todo[order[ph.item0 + k]];
-      Item& it = items[ph.item0 + k];
-      it.kind = t.kind;
-      it.obj = t.obj;
-      it.tile0 = tile0;
-      it.aux = t.aux;
-      it.pad[0] = it.pad[1] = 0;
+    std::vector<double> start(n_items, 0.0), finish(n_items, 0.0);
+    const double n_cta = (double)G;
+    for (int i = 0; i < n_items; ++i) {   // todo is already topological (dependencies are created first)
+      const Todo& t = todo[i];
+      double s0 = 0.0;
+      for (int d2 : t.deps) s0 = finish[d2] > s0 ? finish[d2] : s0;
       int tw = 1, th = 1;
+      double us = 8.0;
       switch (t.kind) {
-        case OADG_IT_MASK: tw = kMaskTileW; th = kMaskTileH; break;
-        case OADG_IT_HIST: tw = kHistTilePx; break;
-        case OADG_IT_COPY: tw = kCopyTileBytes; break;
-        case OADG_IT_BBO_R: tw = kBboTileW; th = kBboTileH; break;
-        case OADG_IT_BBO_C: tw = kBboCatchW; th = kBboTileH; break;
-        case OADG_IT_STEP:   // narrower tiles for lanes with per-pixel ops: their tiles are long
-          tw = it.aux = lanes[t.obj].all_streaming ? kStepTileW : kStepTileWPx;
+        case OADG_IT_MASK: tw = kMaskTileW; th = kMaskTileH; us = 5.6; break;
+        case OADG_IT_HIST: tw = kHistTilePx; us = 20.0; break;
+        case OADG_IT_LUT: us = 4.0; break;
+        case OADG_IT_COPY: tw = kCopyTileBytes; us = 10.0; break;
+        case OADG_IT_BBO_R: tw = kBboTileW; th = kBboTileH; us = 13.0; break;
+        case OADG_IT_BBO_C: tw = kBboCatchW; th = kBboTileH; us = 7.0; break;
+        case OADG_IT_STEP:
+          tw = lanes[t.obj].all_streaming ? kStepTileW : kStepTileWPx;
           th = kStepTileH;
+          us = lanes[t.obj].all_streaming ? 5.3 : 15.0;
           break;
         default: break;
       }
-      it.tx = (t.w + tw - 1) / tw;
-      it.ntiles = it.tx * ((t.hgt + th - 1) / th);
-      if (it.ntiles < 0) it.ntiles = 0;
-      tile0 += it.ntiles;
+      const double tiles = (double)((t.w + tw - 1) / tw) * (double)((t.hgt + th - 1) / th);
+      const double waves = tiles / n_cta < 1.0 ? 1.0 : tiles / n_cta;
+      start[i] = s0;
+      finish[i] = s0 + waves * us;
     }
-    ph.n_tiles = tile0;
+    for (int i = 0; i < n_items; ++i) order[i] = i;
+    auto prio = [&](int i) {
+      const Todo& t = todo[i];
+      return item_priority(t.kind, t.kind == OADG_IT_STEP && lanes[t.obj].all_streaming);
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      if (start[x] != start[y]) return start[x] < start[y];
+      return prio(x) < prio(y);
+    });
+    for (int k = 0; k < n_items; ++k) pos[order[k]] = k;
+  }
+  int n_tiles = 0, n_deps = 0;
+  for (int k = 0; k < n_items; ++k) {
+    const Todo& t = todo[order[k]];
+    Item& it = items[k];
+    it.kind = t.kind;
+    it.obj = t.obj;
+    it.tile0 = n_tiles;
+    it.aux = t.aux;
+    int tw = 1, th = 1;
+    switch (t.kind) {
+      case OADG_IT_MASK: tw = kMaskTileW; th = kMaskTileH; break;
+      case OADG_IT_HIST: tw = kHistTilePx; break;
+      case OADG_IT_COPY: tw = kCopyTileBytes; break;
+      case OADG_IT_BBO_R: tw = kBboTileW; th = kBboTileH; break;
+      case OADG_IT_BBO_C: tw = kBboCatchW; th = kBboTileH; break;
+      case OADG_IT_STEP:   // narrower tiles for lanes with per-pixel ops: their tiles are long
+        tw = it.aux = lanes[t.obj].all_streaming ? kStepTileW : kStepTileWPx;
+        th = kStepTileH;
+        break;
+      default: break;
+    }
+    it.tx = (t.w + tw - 1) / tw;
+    it.ntiles = it.tx * ((t.hgt + th - 1) / th);
+    if (it.ntiles < 0) it.ntiles = 0;
+    n_tiles += it.ntiles;
+    it.dep_first = n_deps;
+    it.dep_count = 0;
+    for (int d2 : t.deps) {
+      if (pos[d2] >= k) return OADG_E_PLAN;   // cannot happen: a dependency always has a smaller depth
+      if (n_deps >= L.max_deps) return OADG_E_LIMIT;
+      deps[n_deps++] = pos[d2];
+      ++it.dep_count;
+    }
   }
 
   for (int v = 0; v < h.n_views; ++v) {
@@ -598,10 +667,12 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.chains = reinterpret_cast<const Chain*>(dplan + t_chain);
   A.bjobs = reinterpret_cast<const BboJob*>(dplan + t_bjob);
   A.items = reinterpret_cast<const Item*>(dplan + t_items);
-  A.phases = reinterpret_cast<const Phase*>(dplan + t_phases);
-  A.tile_ctr = reinterpret_cast<unsigned*>(ws + L.off_zero + 512);
-  A.n_phases = n_phases;
+  A.deps = reinterpret_cast<const int32_t*>(dplan + t_deps);
+  A.n_items = n_items;
+  A.n_tiles = n_tiles;
   A.grid = G;
+  A.queue = reinterpret_cast<unsigned*>(ws + L.off_zero);
+  A.done = reinterpret_cast<unsigned*>(ws + L.off_zero + 512);
   A.hist = reinterpret_cast<unsigned*>(ws + L.off_hist);
   A.luma = reinterpret_cast<unsigned long long*>(ws + L.off_luma);
   A.luts = reinterpret_cast<uint8_t*>(ws + L.off_lut);
@@ -611,8 +682,6 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.masku = reinterpret_cast<uint8_t*>(ws + L.off_masku);
   A.scratch = reinterpret_cast<const uint8_t*>(ws + L.off_scratch);
   A.frame_bytes = L.frame_bytes;
-  A.bar = reinterpret_cast<unsigned*>(ws + L.off_zero);
-  A.phase_ts = reinterpret_cast<unsigned long long*>(ws + L.off_ts);
   A.debug = 0;
   A.kind_ns = reinterpret_cast<unsigned long long*>(ws + L.off_zero + 64);
   // host views of the same tables (the host arithmetic check interprets them directly)
@@ -622,7 +691,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   Hh.chains = chains;
   Hh.bjobs = bjobs;
   Hh.items = items;
-  Hh.phases = phases;
+  Hh.deps = deps;
   if ((rc = be.chain(A, Hh, pv))) return rc;
   return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);
 }

@@ -529,31 +529,24 @@ class OAMix:
         base = (ws.data_ptr() + 255) // 256 * 256
         room = ws.numel() - (base - ws.data_ptr())
         if profile is not None:
-            cap = 512
-            ms_chain, ms_mix, n_ph = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
-            ph_ms = (ctypes.c_float * cap)()
-            ph_kinds = (ctypes.c_int32 * cap)()
+            ms_chain, ms_mix = ctypes.c_float(0), ctypes.c_float(0)
+            n_items, n_tiles = ctypes.c_int(0), ctypes.c_int(0)
             kstats = np.zeros(48, np.uint64)
             _lib.check(lib.oadg_oamix_execute_profiled(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
-                                                       ctypes.byref(ms_chain), ctypes.byref(ms_mix), ctypes.byref(n_ph),
-                                                       ph_ms, ph_kinds, cap, kstats.ctypes.data, s.cuda_stream))
-            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed', 'barrier_wait')
+                                                       ctypes.byref(ms_chain), ctypes.byref(ms_mix), ctypes.byref(n_items),
+                                                       ctypes.byref(n_tiles), kstats.ctypes.data, s.cuda_stream))
+            profile['chain_ms'] = profile.get('chain_ms', 0.0) + float(ms_chain.value)
+            profile['mix_ms'] = profile.get('mix_ms', 0.0) + float(ms_mix.value)
+            profile['chain_n'] = profile.get('chain_n', 0) + 1
+            profile['mix_n'] = profile.get('mix_n', 0) + 1
+            profile['items'] = profile.get('items', 0) + int(n_items.value)
+            profile['tiles'] = profile.get('tiles', 0) + int(n_tiles.value)
+            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed', 'dependency_wait')
             ks = profile.setdefault('kind_busy_us_and_tiles', {k: [0.0, 0, 0.0] for k in names})
             for i, k in enumerate(names):
                 ks[k][0] += float(kstats[i]) / 1e3
                 ks[k][1] += int(kstats[16 + i])
                 ks[k][2] = max(ks[k][2], float(kstats[32 + i]) / 1e3)
-            profile['chain_ms'] = profile.get('chain_ms', 0.0) + float(ms_chain.value)
-            profile['mix_ms'] = profile.get('mix_ms', 0.0) + float(ms_mix.value)
-            profile['chain_n'] = profile.get('chain_n', 0) + 1
-            profile['mix_n'] = profile.get('mix_n', 0) + 1
-            profile['phases'] = profile.get('phases', 0) + int(n_ph.value)
-            by = profile.setdefault('phase_ms_by_kinds', {})
-            for p in range(min(int(n_ph.value), cap)):   # a phase is charged to the set of item kinds it holds
-                key = '+'.join(k for i, k in enumerate(ITEM_KINDS) if ph_kinds[p] >> i & 1)
-                by[key] = by.get(key, 0.0) + float(ph_ms[p])
-                if 'phase_log' in profile:
-                    profile['phase_log'].append((key, ph_kinds[p] >> 8, float(ph_ms[p])))
             self.last_launches += 2
             return outs
         n = ctypes.c_int(0)

@@ -18,12 +18,13 @@ np.random.seed(1000)
 for i in range(3):
     mix.oamix_batch(imgs[0:2], gts[0:2])
 for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
-    prof = {'phase_log': []}
+    prof = {}
     j = (2 * i) % 8
     mix.oamix_batch(imgs[j:j + 2], gts[j:j + 2], profile=prof)
-    print('batch %d: chain %.1f us (in-kernel phases %.1f us), mix %.1f us, %d phases' % (
-        i, prof['chain_ms'] * 1e3, sum(ms for _, _, ms in prof['phase_log']) * 1e3, prof['mix_ms'] * 1e3, prof['phases']))
+    print('batch %d: chain %.1f us, mix %.1f us, %d items, %d tiles' % (
+        i, prof['chain_ms'] * 1e3, prof['mix_ms'] * 1e3, prof['items'], prof['tiles']))
+    tot = 0.0
     for k, (us, n, mx) in prof['kind_busy_us_and_tiles'].items():
-        print('   kind %-14s busy %9.1f CTA-us over %6d tiles = %7.2f us/tile, longest %7.1f us' % (k, us, n, us / max(n, 1), mx))
-    for key, tiles, ms in prof['phase_log']:
-        print('   %8.1f us  %6d tiles  %s' % (ms * 1e3, tiles, key))
+        tot += us
+        print('   kind %-16s busy %9.1f CTA-us over %6d tiles = %7.2f us/tile, longest %7.1f us' % (k, us, n, us / max(n, 1), mx))
+    print('   total %.1f CTA-us = %.1f us on 592 CTAs' % (tot, tot / 592))

@@ -20,7 +20,7 @@ namespace {
 
 struct HostBackend {
   int launches = 0;
-  int n_cta = 5;          // pretend grid: exercises the per-CTA tile ranges of every phase
+  int n_cta = 5;          // > 1: adversarial item order (see chain()); 1: queue order
   int n_phases = 0, n_items = 0, n_bbo_jobs = 0;
   int grid() { return n_cta; }
   int upload(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
@@ -134,80 +134,104 @@ struct HostBackend {
       }
   }
 
+  // one tile of one item (the host twin of the handlers in oamix.cu)
+  int run_tile(const ChainArgs& A, const Item& I, int local) {
+    const DevPlan& P = A.P;
+    switch (I.kind) {
+      case OADG_IT_PROFILE: profile_item(A, I.obj); break;
+      case OADG_IT_MASK: {
+        const oadg_view_t& V = P.views[I.obj];
+        const int x0 = (local % I.tx) * kMaskTileW, y0 = (local / I.tx) * kMaskTileH;
+        for (int y = y0; y < imin(y0 + kMaskTileH, V.H); ++y)
+          for (int x = x0; x < imin(x0 + kMaskTileW, V.W); ++x) mask_pixel(P, I.obj, x, y, A.maskf, A.masku);
+        break;
+      }
+      case OADG_IT_HIST: {
+        const Lane& L = A.lanes[I.obj];
+        const size_t npx = (size_t)L.H * L.W;
+        const size_t p0 = (size_t)local * kHistTilePx, p1 = p0 + kHistTilePx < npx ? p0 + kHistTilePx : npx;
+        unsigned* hh = A.hist + (size_t)L.hist_slot * 768;
+        unsigned long long ls = 0;
+        for (size_t i = p0; i < p1; ++i) {
+          const uint8_t* q = L.in + i * 3;
+          ++hh[q[0]];
+          ++hh[256 + q[1]];
+          ++hh[512 + q[2]];
+          ls += (unsigned)pil_luma(q[0], q[1], q[2]);
+        }
+        A.luma[L.hist_slot] += ls;
+        break;
+      }
+      case OADG_IT_LUT: lut_item(A, I.obj); break;
+      case OADG_IT_COPY: {
+        const Chain& C = A.chains[I.obj];
+        const size_t nbytes = (size_t)P.views[C.view].H * P.views[C.view].W * 3;
+        const size_t b0 = (size_t)local * kCopyTileBytes, b1 = b0 + kCopyTileBytes < nbytes ? b0 + kCopyTileBytes : nbytes;
+        memcpy(C.T + b0, C.in + b0, b1 - b0);
+        if (I.aux) memcpy(C.S + b0, C.in + b0, b1 - b0);
+        break;
+      }
+      case OADG_IT_BBO_R:
+      case OADG_IT_BBO_C: {
+        const BboJob& J = A.bjobs[I.obj];
+        const Chain& C = A.chains[J.chain];
+        const int level = I.kind == OADG_IT_BBO_R ? J.level : J.level + 1;
+        const uint8_t* X = chain_src(C, level);
+        uint8_t* Y = chain_dst(C, level);
+        const int tw = I.kind == OADG_IT_BBO_R ? kBboTileW : kBboCatchW;
+        const int x0 = (J.rect[0] & ~3) + (local % I.tx) * tw, y0 = J.rect[1] + (local / I.tx) * kBboTileH;
+        for (int y = y0; y < imin(y0 + kBboTileH, J.rect[3]); ++y)
+          for (int x = imax(x0, J.rect[0]); x < imin(x0 + tw, J.rect[2]); ++x) {
+            if (I.kind == OADG_IT_BBO_R) bbo_r_pixel(P, C, P.bbo[J.bbo], X, Y, x, y);
+            else bbo_c_pixel(A.bjobs, J, P.views[C.view].W, X, Y, x, y);
+          }
+        if (I.kind == OADG_IT_BBO_R && local == 0) ++n_bbo_jobs;
+        break;
+      }
+      case OADG_IT_STEP: step_item_tile(A, A.lanes[I.obj], local, I.tx, I.aux); break;
+      default: return -203;
+    }
+    return 0;
+  }
+
+  // The device drains the queue with hundreds of CTAs; an item may start as soon as its dependency list is complete.
+  // The host twin therefore runs the items in an ADVERSARIAL order that honours nothing but the dependency table:
+  // it always picks the LAST item of the queue whose dependencies are done (n_cta > 1), or plain queue order
+  // (n_cta == 1).  A missing dependency shows up as a wrong image in the tests.
   int chain(const ChainArgs& Adev, const ChainArgs& A, const PlanView&) {
     (void)Adev;
-    const DevPlan& P = A.P;
-    const int G = A.grid;
-    n_phases = A.n_phases;
-    for (int p = 0; p < A.n_phases; ++p) {
-      const Phase& ph = A.phases[p];
-      n_items += ph.n_items;
-      // tiles are claimed dynamically on the device; any order within a phase must give the same result:
-      // the pretend CTAs take them round-robin, the last CTA first
-      for (int b = G - 1; b >= 0; --b) {
-        int it = ph.item0;
-        const int it_end = ph.item0 + ph.n_items;
-        for (int tile = b; tile < ph.n_tiles; tile += G) {
-          while (it + 1 < it_end && tile >= A.items[it].tile0 + A.items[it].ntiles) ++it;
-          const Item& I = A.items[it];
-          const int local = tile - I.tile0;
-          if (local < 0 || local >= I.ntiles) return -202;
-          switch (I.kind) {
-            case OADG_IT_PROFILE: profile_item(A, I.obj); break;
-            case OADG_IT_MASK: {
-              const oadg_view_t& V = P.views[I.obj];
-              const int x0 = (local % I.tx) * kMaskTileW, y0 = (local / I.tx) * kMaskTileH;
-              for (int y = y0; y < imin(y0 + kMaskTileH, V.H); ++y)
-                for (int x = x0; x < imin(x0 + kMaskTileW, V.W); ++x) mask_pixel(P, I.obj, x, y, A.maskf, A.masku);
-              break;
-            }
-            case OADG_IT_HIST: {
-              const Lane& L = A.lanes[I.obj];
-              const size_t npx = (size_t)L.H * L.W;
-              const size_t p0 = (size_t)local * kHistTilePx, p1 = p0 + kHistTilePx < npx ? p0 + kHistTilePx : npx;
-              unsigned* hh = A.hist + (size_t)L.hist_slot * 768;
-              unsigned long long ls = 0;
-              for (size_t i = p0; i < p1; ++i) {
-                const uint8_t* q = L.in + i * 3;
-                ++hh[q[0]];
-                ++hh[256 + q[1]];
-                ++hh[512 + q[2]];
-                ls += (unsigned)pil_luma(q[0], q[1], q[2]);
-              }
-              A.luma[L.hist_slot] += ls;
-              break;
-            }
-            case OADG_IT_LUT: lut_item(A, I.obj); break;
-            case OADG_IT_COPY: {
-              const Chain& C = A.chains[I.obj];
-              const size_t nbytes = (size_t)P.views[C.view].H * P.views[C.view].W * 3;
-              const size_t b0 = (size_t)local * kCopyTileBytes, b1 = b0 + kCopyTileBytes < nbytes ? b0 + kCopyTileBytes : nbytes;
-              memcpy(C.T + b0, C.in + b0, b1 - b0);
-              if (I.aux) memcpy(C.S + b0, C.in + b0, b1 - b0);
-              break;
-            }
-            case OADG_IT_BBO_R:
-            case OADG_IT_BBO_C: {
-              const BboJob& J = A.bjobs[I.obj];
-              const Chain& C = A.chains[J.chain];
-              const int level = I.kind == OADG_IT_BBO_R ? J.level : J.level + 1;
-              const uint8_t* X = chain_src(C, level);
-              uint8_t* Y = chain_dst(C, level);
-              const int tw = I.kind == OADG_IT_BBO_R ? kBboTileW : kBboCatchW;
-              const int x0 = (J.rect[0] & ~3) + (local % I.tx) * tw, y0 = J.rect[1] + (local / I.tx) * kBboTileH;
-              for (int y = y0; y < imin(y0 + kBboTileH, J.rect[3]); ++y)
-                for (int x = imax(x0, J.rect[0]); x < imin(x0 + tw, J.rect[2]); ++x) {
-                  if (I.kind == OADG_IT_BBO_R) bbo_r_pixel(P, C, P.bbo[J.bbo], X, Y, x, y);
-                  else bbo_c_pixel(A.bjobs, J, P.views[C.view].W, X, Y, x, y);
-                }
-              if (I.kind == OADG_IT_BBO_R && local == 0) ++n_bbo_jobs;
-              break;
-            }
-            case OADG_IT_STEP: step_item_tile(A, A.lanes[I.obj], local, I.tx, I.aux); break;
-            default: return -203;
-          }
+    n_phases = 0;
+    n_items += A.n_items;
+    std::vector<char> finished(A.n_items, 0);
+    int tiles_seen = 0;
+    for (int k = 0; k < A.n_items; ++k) {
+      const Item& I = A.items[k];
+      if (I.tile0 != tiles_seen || I.ntiles < 0) return -200;
+      tiles_seen += I.ntiles;
+      for (int d = 0; d < I.dep_count; ++d)
+        if (A.deps[I.dep_first + d] < 0 || A.deps[I.dep_first + d] >= k) return -201;   // queue order must be topological
+    }
+    if (tiles_seen != A.n_tiles) return -202;
+    for (int left = A.n_items; left > 0; --left) {
+      int pick = -1;
+      for (int k = 0; k < A.n_items; ++k) {
+        const int cand = n_cta > 1 ? A.n_items - 1 - k : k;
+        if (finished[cand]) continue;
+        bool ready = true;
+        const Item& I = A.items[cand];
+        for (int d = 0; d < I.dep_count && ready; ++d) ready = finished[A.deps[I.dep_first + d]] != 0;
+        if (ready) {
+          pick = cand;
+          break;
         }
       }
+      if (pick < 0) return -204;
+      const Item& I = A.items[pick];
+      for (int t = I.ntiles - 1; t >= 0; --t) {   // tiles of an item are independent: any order
+        const int rc = run_tile(A, I, n_cta > 1 ? t : I.ntiles - 1 - t);
+        if (rc) return rc;
+      }
+      finished[pick] = 1;
     }
     ++launches;
     return 0;

@@ -100,7 +100,7 @@ def run_ex(hs, t, jobs, imgs, n_cta):
 @pytest.mark.parametrize('seed', [11, 12, 13, 14])
 def test_chain_scheduler_medium_frames(hostsim, seed):
     """8 gt boxes on a 320x576 frame: bboxes-only chains with several dependency levels, dead boxes pruned, phases
-    split over 1 / 7 / 148 pretend CTAs -- the output must not depend on the split and must match the oracle."""
+    executed in queue order (1) and in adversarial dependency-only orders (7, 148) -- the output must not depend on the order and must match the oracle."""
     from oadg_b200.oamix import OAMix
     cfg = sampler_cfg(dict(OAMIX_CFG, version='augmix'))
     img, gt = synth.make_image(seed, 320, 576, 8)
@@ -114,7 +114,7 @@ def test_chain_scheduler_medium_frames(hostsim, seed):
     for n_cta in (1, 7, 148):
         (o,), stats = run_ex(hostsim, t, [(vp, gt, 0)], [img], n_cta)
         outs.append(o)
-        assert stats[0] >= 1 and stats[1] >= 1
+        assert stats[1] >= 1
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     d = np.abs(outs[0].astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d != 0).mean() <= 1e-3, (int(d.max()), float((d != 0).mean()))
