@@ -55,7 +55,11 @@ class CudaBackend:
         lib = _lib.load()
         need = ctypes.c_size_t(0)
         _lib.check(lib.oadg_supcon_workspace_bytes(n_total, c, ctypes.byref(need)))
-        ws = torch.empty(need.value + 256, dtype=torch.uint8, device=device)
+        key = (n_total, c, str(device))
+        if getattr(self, '_ws_key', None) != key:   # one workspace per shape, reused every step
+            self._ws_buf = torch.empty(need.value + 256, dtype=torch.uint8, device=device)
+            self._ws_key = key
+        ws = self._ws_buf
         return ws, (ws.data_ptr() + 255) // 256 * 256, need.value
 
     def normalize(self, x, n_total, normalized_input):
@@ -95,24 +99,66 @@ class CudaBackend:
         return gx
 
 
+_PAIR_CACHE = {}
+
+
+def _pair_all_on(device, pair_local, world):
+    """The global pair map as a device tensor, cached per (layout, world, device): no per-step H2D copy."""
+    pl = np.asarray(pair_local, dtype=np.int64)
+    key = (pl.tobytes(), world, str(device))
+    t = _PAIR_CACHE.get(key)
+    if t is None:
+        if len(_PAIR_CACHE) > 16:
+            _PAIR_CACHE.clear()
+        t = _PAIR_CACHE[key] = torch.from_numpy(gathered_pair_map(pl, world)).to(device)
+    return t
+
+
+def _all_gather_rows(t, group):
+    """[n, k] -> [W * n, k] with ONE collective (all_gather_into_tensor where the backend has it)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return t
+    t = t.contiguous()
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    try:
+        dist.all_gather_into_tensor(out, t, group=group)
+    except (RuntimeError, NotImplementedError, AttributeError):   # e.g. gloo builds without the tensor variant
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        out = torch.cat(parts, dim=0)
+    return out
+
+
 class _GatheredSupCon(torch.autograd.Function):
+    """Two collectives in the forward (embeddings + labels in one buffer; row statistics + the rank's loss part in
+    another), none in the backward."""
 
     @staticmethod
     def forward(ctx, x, labels, pair_local, cfg, backend, group):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        n = x.shape[0]
+        n, c = x.shape
         temperature, loss_weight, min_samples, normalized_input = cfg
         x = x.contiguous()
         fhat = backend.normalize(x, world * n, normalized_input)
-        f_all = _all_gather_cat(fhat, group)
-        labels_all = _all_gather_cat(labels.contiguous().view(-1).to(torch.int64), group)
-        pair_all = torch.from_numpy(gathered_pair_map(pair_local, world)).to(x.device)
+        # one gather for [fhat | labels]: the int64 labels travel as two float32-sized columns of raw bits
+        lab = labels.contiguous().view(-1).to(torch.int64).view(n, 1).view(fhat.dtype)   # 2 columns of f32, 1 of f64
+        packed = torch.empty(n, c + lab.shape[1], dtype=fhat.dtype, device=x.device)
+        packed[:, :c] = fhat
+        packed[:, c:] = lab
+        g_all = _all_gather_rows(packed, group)
+        f_all = g_all[:, :c].contiguous()
+        labels_all = g_all[:, c:].contiguous().view(torch.int64).view(-1)
+        pair_all = _pair_all_on(x.device, pair_local, world)
         loss_part, stats = backend.forward(f_all, labels_all, pair_all, rank * n, n, temperature, loss_weight,
                                            min_samples)
-        loss = loss_part.clone()
-        if world > 1:
-            dist.all_reduce(loss, group=group)
-        stats_all = _all_gather_cat(stats, group)
+        # one gather for [row statistics ; loss part]: the loss is the sum of the W parts
+        tail = torch.zeros(n + 1, stats.shape[1], dtype=stats.dtype, device=x.device)
+        tail[:n] = stats
+        tail[n, 0] = loss_part
+        t_all = _all_gather_rows(tail, group).view(world, n + 1, stats.shape[1])
+        stats_all = t_all[:, :n].reshape(world * n, stats.shape[1]).contiguous()
+        loss = t_all[:, n, 0].sum()
         ctx.save_for_backward(x, f_all, labels_all, pair_all, stats_all)
         ctx.meta = (rank * n, temperature, normalized_input, world, backend)
         return loss
