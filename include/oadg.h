@@ -207,6 +207,10 @@ int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
                                 float* ms_chain, float* ms_mix, int* n_items_out, int* n_tiles_out,
                                 unsigned long long* kind_stats, void* stream);
 
+/* Measurement aid (set OADG_TRACE=1): per work item of the last profiled execution {kind, obj, tiles, dependency
+ * count, first claim / last publish in us, first 8 dependencies}; returns the number of items. */
+int oadg_oamix_last_trace(void* out, int cap);
+
 /* ---- OA-Loss ---------------------------------------------------------------- */
 
 /* Workspace bytes for forward+backward at N rows, C channels. */

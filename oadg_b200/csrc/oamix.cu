@@ -17,6 +17,7 @@
 //                        host between the ~10-40 dependent stages.
 //   mix_kernel           branch mixing + object-aware mixing of all views (oa_mix.py:236,281-309)
 #include <stdlib.h>
+#include <string.h>
 
 #include "oadg_common.cuh"
 #include "oamix_exec.h"
@@ -36,6 +37,7 @@ __device__ const double g_div255[256] = {0.0 / 255.0, 1.0 / 255.0, 2.0 / 255.0, 
 #define OADG_HANDLER __noinline__
 #endif
 
+constexpr int kMaxQueueItems = 4096;   // work items per launch (a CTA keeps a bitmap of the exhausted ones)
 constexpr int kCT = 256;     // threads per CTA of the chain kernel
 constexpr int kCtaPerSm = 4; // independent CTAs per SM (64 registers per thread): tiles of different kinds overlap on an SM
 
@@ -55,7 +57,10 @@ struct BboStage {    // one bbo job staged for the CTA (bbo_r_segment / bbo_c_se
 };
 
 struct ChainSmem {
-  int next_tile;       // the CTA's next claimed tile of the current phase
+  int next_tile;       // the CTA's next claimed tile ...
+  int next_item;       // ... and the item it belongs to (-1: the queue is drained)
+  unsigned epoch_seen; // value of the ready-epoch when this CTA last scanned the queue
+  unsigned exhausted[kMaxQueueItems / 32];   // items this CTA knows to have no unclaimed tile left
   int rowoff[2][96];   // staged gathers: byte offset of every staged source row (frame rows, mask rows)
   int cand[16];        // mask tiles: the gt boxes whose support meets the tile
   int step_class;      // measurement aid: class of the last step tile (7 stream, 8 staged bg, 9 mixed / per pixel)
@@ -85,33 +90,60 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return v;
 }
 
-// ---- dependencies between work items -------------------------------------------------------------------------
-// All CTAs are co-resident (cooperative launch) and claim tiles in queue order, so every tile an item waits for was
-// claimed earlier by a CTA that is running: waiting cannot deadlock.  A finished tile is published with
-// bar.sync + fence + atomic add by one thread; a waiter polls the counters with acquire loads, fences and bar.syncs
-// before the CTA touches the data (the pattern of a cooperative-groups grid sync, per item instead of per grid).
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// ---- the work queue ---------------------------------------------------------------------------------------
+// Every item has a counter of claimed tiles and a counter of outstanding dependency tiles (`pending`, initialised by
+// the host).  A CTA drains the item it is working on (one atomic per tile, issued before the tile is processed); when
+// that item runs out it scans the queue from the front for the first item that is READY (pending == 0) and still has
+// unclaimed tiles, skipping items whose inputs are not complete -- so a CTA only idles when nothing at all is ready.
+// A finished tile is published with bar.sync + fence by one thread, which then decrements `pending` of the item's
+// successors; a claimer reads `pending` with an acquire load, fences, and the CTA bar.syncs before touching the data
+// (the pattern of a cooperative-groups grid sync, per item instead of per grid).  All CTAs are co-resident
+// (cooperative launch), and a waiting CTA holds no tile, so the scheme cannot deadlock.
+__device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void wait_for_deps(const ChainArgs& A, const Item& I) {
-  if (threadIdx.x == 0) {
-    for (int k = 0; k < I.dep_count; ++k) {
-      const int d = A.deps[I.dep_first + k];
-      const unsigned need = (unsigned)A.items[d].ntiles;
-      while (ld_acquire(A.done + d) < need) {
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __forceinline__ void publish_tile(const ChainArgs& A, int item) {
+
+// thread 0 only: find the next (item, tile); returns false when every item is exhausted
+__device__ bool scan_for_work(const ChainArgs& A, unsigned* exhausted, int& scan_from, int& item, int& tile) {
+  for (;;) {
+    bool any_left = false;
+    while (scan_from < A.n_items && (exhausted[scan_from >> 5] >> (scan_from & 31) & 1u)) ++scan_from;
+    for (int k = scan_from; k < A.n_items; ++k) {
+      if (exhausted[k >> 5] >> (k & 31) & 1u) continue;
+      const unsigned nt = (unsigned)A.items[k].ntiles;
+      if (ld_relaxed_u32(A.claimed + k) >= nt) {
+        exhausted[k >> 5] |= 1u << (k & 31);
+        continue;
+      }
+      any_left = true;
+      if (ld_acquire_s32(A.pending + k) > 0) continue;   // inputs not complete yet: look further down the queue
+      const unsigned t = atomicAdd(A.claimed + k, 1u);
+      if (t < nt) {
+        item = k;
+        tile = (int)t;
+        __threadfence();
+        return true;
+      }
+      exhausted[k >> 5] |= 1u << (k & 31);
+    }
+    if (!any_left) return false;
+    __nanosleep(256);   // nothing is ready: back off before polling the counters again
+  }
+}
+__device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(A.done + item, 1u);
+    bool released = false;
+    for (int k = 0; k < I.succ_count; ++k) released |= atomicSub(A.pending + A.succ[I.succ_first + k], 1) == 1;
+    if (released) atomicAdd(A.epoch, 1u);   // an item became ready: CTAs on lower-priority items re-scan the queue
   }
 }
 
@@ -1065,23 +1097,31 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
   }
   __syncthreads();
   const ChainArgs& A = S.args;
-  int staged_lane = -1, ready_item = -1, it = 0;
-  // dynamic tile claims: thread 0 fetches the next index while the CTA works on the current tile
-  if (threadIdx.x == 0) S.next_tile = (int)atomicAdd(A.queue, 1u);
+  int staged_lane = -1, scan_from = 0;
+  if (threadIdx.x < kMaxQueueItems / 32) S.exhausted[threadIdx.x] = 0u;
   __syncthreads();
-  int tile = S.next_tile;
-  while (tile < A.n_tiles) {
-    __syncthreads();  // every thread has read S.next_tile
-    unsigned claim = 0;
-    if (threadIdx.x == 0) claim = atomicAdd(A.queue, 1u);
-    while (it + 1 < A.n_items && tile >= A.items[it].tile0 + A.items[it].ntiles) ++it;
+  if (threadIdx.x == 0) {
+    int item = -1, tile = -1;
+    const unsigned long long w0 = globaltimer_ns();
+    S.epoch_seen = ld_relaxed_u32(A.epoch);
+    if (!scan_for_work(A, S.exhausted, scan_from, item, tile)) item = -1;
+    if (!(A.debug & 4)) atomicAdd(A.kind_ns + 10, globaltimer_ns() - w0);
+    S.next_item = item;
+    S.next_tile = tile;
+  }
+  __syncthreads();
+  int it = S.next_item, tile = S.next_tile;
+  while (it >= 0) {
+    __syncthreads();  // every thread has read S.next_item / S.next_tile
     const Item I = A.items[it];
-    const int l0 = tile - I.tile0, l1 = l0 + 1;
-    const unsigned long long wait_t0 = globaltimer_ns();
-    if (it != ready_item) {   // first tile of this item on this CTA: its inputs must be complete
-      wait_for_deps(A, I);
-      ready_item = it;
+    unsigned claim = 0;
+    bool prefetched = false;
+    if (threadIdx.x == 0) {
+      // next tile of the same item, in flight during the work
+      prefetched = (A.debug & 32) ? ld_relaxed_u32(A.epoch) == S.epoch_seen : true;   // bit 5: preemptive re-scans (slower)
+      if (prefetched) claim = atomicAdd(A.claimed + it, 1u);
     }
+    const int l0 = tile, l1 = tile + 1;
     const unsigned long long seg_t0 = globaltimer_ns();
     switch (I.kind) {
       case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;
@@ -1114,19 +1154,30 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
         break;
       default: break;
     }
-    publish_tile(A, it);
+    publish_tile(A, I);
     if (threadIdx.x == 0) {
+      const unsigned long long t1 = globaltimer_ns();
+      int item = it, nt = (int)claim;
+      if (!prefetched || claim >= (unsigned)I.ntiles) {   // look for the first ready item with tiles left
+        if (prefetched) S.exhausted[it >> 5] |= 1u << (it & 31);
+        S.epoch_seen = ld_relaxed_u32(A.epoch);
+        if (!scan_for_work(A, S.exhausted, scan_from, item, nt)) item = -1;
+      }
       if (!(A.debug & 4)) {
         const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
-        const unsigned long long dt = globaltimer_ns() - seg_t0;
+        const unsigned long long dt = t1 - seg_t0;
         atomicAdd(A.kind_ns + kk, dt);
         atomicAdd(A.kind_ns + 16 + kk, 1ull);
         atomicMax(A.kind_ns + 32 + kk, dt);
-        atomicAdd(A.kind_ns + 10, seg_t0 - wait_t0);   // slot 10: waiting for dependencies
+        atomicAdd(A.kind_ns + 10, globaltimer_ns() - t1);   // slot 10: looking / waiting for ready work
+        atomicMax(A.item_ts + 2 * it, (1ull << 63) - seg_t0);
+        atomicMax(A.item_ts + 2 * it + 1, t1);
       }
-      S.next_tile = (int)claim;
+      S.next_item = item;
+      S.next_tile = nt;
     }
     __syncthreads();
+    it = S.next_item;
     tile = S.next_tile;
   }
 }
@@ -1169,6 +1220,9 @@ struct CudaBackend {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   int n_items = 0, n_tiles = 0;
   const unsigned long long* kind_ns_dev = nullptr;
+  const unsigned long long* item_ts_dev = nullptr;
+  std::vector<Item> items_host;
+  std::vector<int32_t> deps_host;
 
   int grid() {
     if (n_sm == 0) {
@@ -1202,8 +1256,12 @@ struct CudaBackend {
       n_items = A.n_items;
       n_tiles = A.n_tiles;
       kind_ns_dev = A.kind_ns;
+      item_ts_dev = A.item_ts;
+      items_host.assign(Hh.items, Hh.items + A.n_items);
+      int nd = 0;
+      for (const Item& I : items_host) nd = I.dep_first + I.dep_count > nd ? I.dep_first + I.dep_count : nd;
+      deps_host.assign(Hh.deps, Hh.deps + nd);
     }
-    (void)Hh;
     if (A.n_tiles > 0) {
       ChainArgs args = A;
       if (const char* dbg = getenv("OADG_DEBUG")) args.debug = atoi(dbg);
@@ -1242,6 +1300,20 @@ extern "C" int oadg_oamix_workspace_bytes(const void* plan_host, size_t plan_byt
   return 0;
 }
 
+// measurement aid: the work queue of the last profiled execution on this workspace (kind, obj, tiles, first claim and
+// last publish in ns relative to the earliest claim, dependencies) -- filled by oadg_oamix_execute_profiled
+struct ItemTrace {
+  int32_t kind, obj, ntiles, dep_count;
+  double t0_us, t1_us;
+  int32_t deps[8];
+};
+static std::vector<ItemTrace> g_last_trace;   // debugging only (not thread safe)
+extern "C" int oadg_oamix_last_trace(void* out, int cap) {
+  const int n = (int)g_last_trace.size() < cap ? (int)g_last_trace.size() : cap;
+  if (out && n > 0) memcpy(out, g_last_trace.data(), (size_t)n * sizeof(ItemTrace));
+  return (int)g_last_trace.size();
+}
+
 extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes, const uint8_t* const* src_dev,
                                            int n_img, uint8_t* const* dst_dev, void* workspace_dev,
                                            size_t workspace_bytes, float* ms_chain, float* ms_mix, int* n_items_out,
@@ -1260,6 +1332,24 @@ extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_by
     cudaEventElapsedTime(ms_mix, be.ev[1], be.ev[2]);
     if (kind_stats && be.kind_ns_dev)
       e = cudaMemcpy(kind_stats, be.kind_ns_dev, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (getenv("OADG_TRACE") && be.item_ts_dev && be.n_items > 0) {
+      std::vector<unsigned long long> ts((size_t)be.n_items * 2);
+      cudaMemcpy(ts.data(), be.item_ts_dev, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      unsigned long long base = ~0ull;
+      for (int k = 0; k < be.n_items; ++k) {
+        const unsigned long long t0 = (1ull << 63) - ts[2 * k];
+        if (ts[2 * k] && t0 < base) base = t0;
+      }
+      g_last_trace.assign(be.n_items, ItemTrace{});
+      for (int k = 0; k < be.n_items; ++k) {
+        ItemTrace& T = g_last_trace[k];
+        const Item& I = be.items_host[k];
+        T.kind = I.kind; T.obj = I.obj; T.ntiles = I.ntiles; T.dep_count = I.dep_count;
+        T.t0_us = ts[2 * k] ? (double)((1ull << 63) - ts[2 * k] - base) * 1e-3 : -1.0;
+        T.t1_us = ts[2 * k + 1] ? (double)(ts[2 * k + 1] - base) * 1e-3 : -1.0;
+        for (int d = 0; d < 8; ++d) T.deps[d] = d < I.dep_count ? be.deps_host[I.dep_first + d] : -1;
+      }
+    }
   }
   for (auto& ev : be.ev)
     if (ev) cudaEventDestroy(ev);

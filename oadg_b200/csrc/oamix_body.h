@@ -79,6 +79,7 @@ struct Item {
   int32_t tx;              // tiles per row (2-D kinds)
   int32_t aux;
   int32_t dep_first, dep_count;   // the items (indices into the item table) that must be complete before this one starts
+  int32_t succ_first, succ_count; // the items that wait for this one (entries of the successor table)
 };
 constexpr int kMaskTileW = 256, kMaskTileH = 8;
 constexpr int kHistTilePx = 32768;

@@ -148,7 +148,8 @@ inline void make_layout(const PlanView& pv, Layout& L) {
                    align_up_sz((size_t)(n_chains > 0 ? n_chains : 1) * sizeof(Chain), 16) +
                    align_up_sz((size_t)(h.n_bbo > 0 ? h.n_bbo : 1) * sizeof(BboJob), 16) +
                    align_up_sz((size_t)L.max_items * sizeof(Item), 16) +
-                   align_up_sz((size_t)L.max_deps * sizeof(int32_t), 16) +
+                   2 * align_up_sz((size_t)L.max_deps * sizeof(int32_t), 16) +
+                   align_up_sz((size_t)L.max_items * sizeof(int32_t), 16) +
                    align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
   L.off_tables = align_up_sz((size_t)h.total_bytes, 16);
@@ -162,7 +163,8 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   // one memset: [grid barrier counter | histograms | luma sums]
   // one memset: [0] work-queue counter; bytes 64..447: busy ns [16], tile counts [16], longest tile ns [16] per item
   // kind (uint64); bytes 512..: tiles done per item | histograms | luma sums
-  L.off_zero = take(512 + (size_t)L.max_items * sizeof(unsigned));
+  L.off_zero = take(512 + (size_t)L.max_items * (sizeof(unsigned) + 2 * sizeof(unsigned long long)));   // bytes 512..: tiles
+  // claimed per item, then (measurement aid) per item 2^63 - first claim time and last publish time (globaltimer ns)
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
   L.zero_bytes = o - L.off_zero;
@@ -281,10 +283,13 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   const Chain* chains;
   const BboJob* bjobs;
   const Item* items;
-  const int32_t* deps;       // dependency lists of the items
+  const int32_t* deps;       // dependency lists of the items (host-side checks only)
+  const int32_t* succ;       // successor lists of the items
+  int32_t* pending;          // [n_items] dependency tiles still outstanding (uploaded with the tables)
   int32_t n_items, n_tiles, grid, debug;
-  unsigned* queue;           // next unclaimed tile (zeroed before the launch)
-  unsigned* done;            // [n_items] finished tiles of every item (zeroed before the launch)
+  unsigned* epoch;           // bumped whenever an item becomes ready (zeroed before the launch)
+  unsigned* claimed;         // [n_items] tiles claimed of every item (zeroed before the launch)
+  unsigned long long* item_ts;   // [n_items][2] measurement aid: 2^63 - first claim time, last publish time
   unsigned* hist;
   unsigned long long* luma;
   uint8_t* luts;
@@ -358,6 +363,8 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const size_t t_bjob = carve((size_t)(L.n_bbo > 0 ? L.n_bbo : 1) * sizeof(BboJob));
   const size_t t_items = carve((size_t)L.max_items * sizeof(Item));
   const size_t t_deps = carve((size_t)L.max_deps * sizeof(int32_t));
+  const size_t t_succ = carve((size_t)L.max_deps * sizeof(int32_t));
+  const size_t t_pending = carve((size_t)L.max_items * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
@@ -365,6 +372,8 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   auto* bjobs = reinterpret_cast<BboJob*>(stage.data() + t_bjob);
   auto* items = reinterpret_cast<Item*>(stage.data() + t_items);
   auto* deps = reinterpret_cast<int32_t*>(stage.data() + t_deps);
+  auto* succ = reinterpret_cast<int32_t*>(stage.data() + t_succ);
+  auto* pending = reinterpret_cast<int32_t*>(stage.data() + t_pending);
   auto* mixjobs = reinterpret_cast<MixJob*>(stage.data() + t_mix);
 
   // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
@@ -551,20 +560,19 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       }
     }
   }
-  if ((int)todo.size() > L.max_items) return OADG_E_LIMIT;
+  if ((int)todo.size() > L.max_items || (int)todo.size() > 4096) return OADG_E_LIMIT;   // 4096: the kernel's item bitmap
 
-  // ---- the work queue: items ordered by their estimated start time (a list schedule with rough per-kind tile
-  // durations), so that a CTA seldom claims a tile whose inputs are not ready while ready work waits behind it;
-  // ties: long-tile kinds first.  Dependencies always start earlier, so the order is topological.
+  // ---- the work queue: items ordered by PRIORITY = the length of the longest dependency chain that still hangs on
+  // an item (its "bottom level" in a list schedule with rough per-kind tile durations).  CTAs always take the first
+  // READY item of the queue, so critical items are served as soon as their inputs are complete and the rest fills
+  // the gaps.  The order need not be topological: an item whose inputs are missing is skipped, never waited for.
   const int n_items = (int)todo.size();
   std::vector<int> order(n_items), pos(n_items);
   {
-    std::vector<double> start(n_items, 0.0), finish(n_items, 0.0);
+    std::vector<double> dur(n_items, 0.0), bottom(n_items, 0.0), start(n_items, 0.0);
     const double n_cta = (double)G;
-    for (int i = 0; i < n_items; ++i) {   // todo is already topological (dependencies are created first)
+    for (int i = 0; i < n_items; ++i) {   // todo is topological (dependencies are created first)
       const Todo& t = todo[i];
-      double s0 = 0.0;
-      for (int d2 : t.deps) s0 = finish[d2] > s0 ? finish[d2] : s0;
       int tw = 1, th = 1;
       double us = 8.0;
       switch (t.kind) {
@@ -583,17 +591,19 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       }
       const double tiles = (double)((t.w + tw - 1) / tw) * (double)((t.hgt + th - 1) / th);
       const double waves = tiles / n_cta < 1.0 ? 1.0 : tiles / n_cta;
+      dur[i] = waves * us + 3.0;   // + hand-over latency between dependent items
+      double s0 = 0.0;
+      for (int d2 : t.deps) s0 = start[d2] + dur[d2] > s0 ? start[d2] + dur[d2] : s0;
       start[i] = s0;
-      finish[i] = s0 + waves * us;
+    }
+    for (int i = n_items - 1; i >= 0; --i) {   // longest path from the start of item i to the end of the queue
+      bottom[i] += dur[i];
+      for (int d2 : todo[i].deps) bottom[d2] = bottom[i] > bottom[d2] ? bottom[i] : bottom[d2];
     }
     for (int i = 0; i < n_items; ++i) order[i] = i;
-    auto prio = [&](int i) {
-      const Todo& t = todo[i];
-      return item_priority(t.kind, t.kind == OADG_IT_STEP && lanes[t.obj].all_streaming);
-    };
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-      if (start[x] != start[y]) return start[x] < start[y];
-      return prio(x) < prio(y);
+      if (bottom[x] != bottom[y]) return bottom[x] > bottom[y];
+      return start[x] < start[y];
     });
     for (int k = 0; k < n_items; ++k) pos[order[k]] = k;
   }
@@ -625,11 +635,31 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     it.dep_first = n_deps;
     it.dep_count = 0;
     for (int d2 : t.deps) {
-      if (pos[d2] >= k) return OADG_E_PLAN;   // cannot happen: a dependency always has a smaller depth
       if (n_deps >= L.max_deps) return OADG_E_LIMIT;
       deps[n_deps++] = pos[d2];
       ++it.dep_count;
     }
+  }
+  {  // successor lists (the reverse of deps) and the number of dependency tiles every item starts with
+    std::vector<int> cnt(n_items + 1, 0);
+    for (int k = 0; k < n_items; ++k) {
+      pending[k] = 0;
+      for (int d2 = 0; d2 < items[k].dep_count; ++d2) {
+        const int pr = deps[items[k].dep_first + d2];
+        ++cnt[pr + 1];
+        pending[k] += items[pr].ntiles;
+      }
+    }
+    for (int k = 0; k < n_items; ++k) cnt[k + 1] += cnt[k];
+    for (int k = 0; k < n_items; ++k) {
+      items[k].succ_first = cnt[k];
+      items[k].succ_count = 0;
+    }
+    for (int k = 0; k < n_items; ++k)
+      for (int d2 = 0; d2 < items[k].dep_count; ++d2) {
+        Item& pr = items[deps[items[k].dep_first + d2]];
+        succ[pr.succ_first + pr.succ_count++] = k;
+      }
   }
 
   for (int v = 0; v < h.n_views; ++v) {
@@ -668,11 +698,14 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.bjobs = reinterpret_cast<const BboJob*>(dplan + t_bjob);
   A.items = reinterpret_cast<const Item*>(dplan + t_items);
   A.deps = reinterpret_cast<const int32_t*>(dplan + t_deps);
+  A.succ = reinterpret_cast<const int32_t*>(dplan + t_succ);
+  A.pending = reinterpret_cast<int32_t*>(const_cast<char*>(dplan) + t_pending);
   A.n_items = n_items;
   A.n_tiles = n_tiles;
   A.grid = G;
-  A.queue = reinterpret_cast<unsigned*>(ws + L.off_zero);
-  A.done = reinterpret_cast<unsigned*>(ws + L.off_zero + 512);
+  A.epoch = reinterpret_cast<unsigned*>(ws + L.off_zero);
+  A.claimed = reinterpret_cast<unsigned*>(ws + L.off_zero + 512);
+  A.item_ts = reinterpret_cast<unsigned long long*>(ws + L.off_zero + 512 + align_up_sz((size_t)L.max_items * sizeof(unsigned), 8));
   A.hist = reinterpret_cast<unsigned*>(ws + L.off_hist);
   A.luma = reinterpret_cast<unsigned long long*>(ws + L.off_luma);
   A.luts = reinterpret_cast<uint8_t*>(ws + L.off_lut);
@@ -692,6 +725,8 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   Hh.bjobs = bjobs;
   Hh.items = items;
   Hh.deps = deps;
+  Hh.succ = succ;
+  Hh.pending = pending;
   if ((rc = be.chain(A, Hh, pv))) return rc;
   return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);
 }

@@ -196,8 +196,8 @@ struct HostBackend {
 
   // The device drains the queue with hundreds of CTAs; an item may start as soon as its dependency list is complete.
   // The host twin therefore runs the items in an ADVERSARIAL order that honours nothing but the dependency table:
-  // it always picks the LAST item of the queue whose dependencies are done (n_cta > 1), or plain queue order
-  // (n_cta == 1).  A missing dependency shows up as a wrong image in the tests.
+  // it always picks the LAST item of the queue whose dependencies are done (n_cta > 1), or the FIRST one like the
+  // device does (n_cta == 1).  A missing dependency shows up as a wrong image in the tests.
   int chain(const ChainArgs& Adev, const ChainArgs& A, const PlanView&) {
     (void)Adev;
     n_phases = 0;
@@ -209,7 +209,7 @@ struct HostBackend {
       if (I.tile0 != tiles_seen || I.ntiles < 0) return -200;
       tiles_seen += I.ntiles;
       for (int d = 0; d < I.dep_count; ++d)
-        if (A.deps[I.dep_first + d] < 0 || A.deps[I.dep_first + d] >= k) return -201;   // queue order must be topological
+        if (A.deps[I.dep_first + d] < 0 || A.deps[I.dep_first + d] >= A.n_items || A.deps[I.dep_first + d] == k) return -201;
     }
     if (tiles_seen != A.n_tiles) return -202;
     for (int left = A.n_items; left > 0; --left) {
