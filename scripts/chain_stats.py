@@ -1,4 +1,4 @@
-"""Per-phase durations of the OA-Mix chain kernel for a few bench batches (GPU box): kinds, tiles, microseconds."""
+"""CTA-busy time per work-item kind of the OA-Mix chain kernel for a few bench batches (GPU box)."""
 import os
 import sys
 
