@@ -179,7 +179,9 @@ def test_single_op_plans_match_host_arithmetic_bit_for_bit(cuda):
         bbo = ('bbo_affine', [(k, _invert_affine(OAMix._forward_affine(
             'rotate', 6.0, k % 2 == 0, (x2 - x1 + 1, y2 - y1 + 1), ((x1 + x2) / 2., (y1 + y2) / 2.), (w, h))))
             for k, (x1, y1, x2, y2) in enumerate(gi)])
-        singles = [(('autocontrast',), ('solarize', 100)), (('autocontrast',), tr), (sh, ('posterize', 3)), (rot, rot),
+        bbo_tr = ('bbo_affine', [(k, _invert_affine([1.0, 0.0, float(-(3 + 2 * k)), 0.0, 1.0, 0.0] if k % 2 else
+                                                    [1.0, 0.0, 0.0, 0.0, 1.0, float(5 - 3 * k)])) for k in range(len(gi))])
+        singles = [(bbo_tr, ('autocontrast',)), (('equalize',), bbo_tr), (('autocontrast',), ('solarize', 100)), (('autocontrast',), tr), (sh, ('posterize', 3)), (rot, rot),
                    (bbo, ('autocontrast',)), (('equalize',), bbo), (('invert', 1, -1), ('color', 0.7)),
                    (('sharpness', 1.5), ('contrast', 0.4)), (tr, sh)]
         plans = [[[[a, b] + ([a] if len(ml) == 2 else [])]] for a, b in singles]
