@@ -351,8 +351,13 @@ def product_arm(args):
     chain_ms, mix_ms, n_l = prof.get('chain_ms', 0.0), prof.get('mix_ms', 0.0), max(prof.get('chain_n', 1), 1)
     achieved = prof.get('step_bytes', 0) / (chain_ms / 1e3) / 1e9 if chain_ms > 0 else 0.0
     total_kernel_ms = chain_ms + mix_ms
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'chain_kernel_traffic.json')
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj['dram_read_bytes'] + tj['dram_write_bytes'], tj.get('source')
     roofline = {'kernel': 'oadg::oamix_chain_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'launches': prof.get('chain_n', 0),
                 'algorithmic_bytes_per_launch': prof.get('step_bytes', 0) / n_l,
                 'algorithmic_bytes': 'sum over the launch\'s lane steps of 2 * 3HW (one read + one write of a frame per '

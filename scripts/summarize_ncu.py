@@ -58,6 +58,17 @@ def full(src, dst):
                         pass
             out.write('- top stall reasons (warps per issue-active): ' +
                       ', '.join('%s %.2f' % (h, v) for v, h in sorted(st, reverse=True)[:5]) + '\n\n')
+    if len(sys.argv) > 4:   # optional: DRAM traffic of the first captured launch as JSON (bench.py's roofline.traffic)
+        import json
+        r = rows[2]
+
+        def val(k):
+            v, u = float(r[hdr.index(k)]), units[hdr.index(k)].lower()
+            return v * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(u, 1)
+        json.dump({'kernel': r[hdr.index('Kernel Name')][:80], 'dram_read_bytes': val('dram__bytes_read.sum'),
+                   'dram_write_bytes': val('dram__bytes_write.sum'), 'gpu_time_us': float(r[hdr.index('gpu__time_duration.sum')]),
+                   'source': src, 'note': 'one ncu --set full capture of one launch (its plan differs from the bench average)'},
+                  open(sys.argv[4], 'w'), indent=1)
 
 
 if __name__ == '__main__':
