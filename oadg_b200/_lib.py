@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libOADG.so')
+LIB_PATH = os.environ.get('OADG_LIB') or os.path.join(_HERE, 'libOADG.so')   # OADG_LIB: a timing variant (scripts/)
 
 _c = ctypes
 _vp, _i32, _sz, _f32 = _c.c_void_p, _c.c_int32, _c.c_size_t, _c.c_float

@@ -682,11 +682,13 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
   const bool vec = ((W * 3) & 3) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 3) == 0;
   const int ax0 = bs.rect[0] & ~3, tx = I.tx;
   constexpr int kSubPerTile = kBboTileW / kSubW;   // 64 x 16 sub-tiles per tile, each with its own staged source
-  for (int k2 = kSubPerTile * l0; k2 < kSubPerTile * l1; ++k2) {
-    const int k = k2 / kSubPerTile;
-    const int tx0 = ax0 + (k % tx) * kBboTileW + (k2 % kSubPerTile) * kSubW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
-    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kSubW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
-    if (x1 <= x0) continue;   // uniform: the support ends inside the first sub-tile
+  constexpr int kRowsPerTile = kBboTileH / kSubH;
+  for (int k2 = kSubPerTile * kRowsPerTile * l0; k2 < kSubPerTile * kRowsPerTile * l1; ++k2) {
+    const int k = k2 / (kSubPerTile * kRowsPerTile), sub = k2 % (kSubPerTile * kRowsPerTile);
+    const int tx0 = ax0 + (k % tx) * kBboTileW + (sub % kSubPerTile) * kSubW;
+    const int ty0 = bs.rect[1] + (k / tx) * kBboTileH + (sub / kSubPerTile) * kSubH;
+    const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kSubW, bs.rect[2]), y1 = imin(ty0 + kSubH, bs.rect[3]);
+    if (x1 <= x0 || y1 <= ty0) continue;   // uniform: the support ends before this sub-tile
     int sr[4];
     const bool any_src = warp_src_rect(bs.minv, x0, ty0, x1, y1, W, H, sr);
     const StageView sv = make_view(dyn, bs.X, W, H, 3, sr);
@@ -772,8 +774,7 @@ __device__ OADG_HANDLER void bbo_c_segment(const ChainArgs& A, ChainSmem& S, con
   for (int k = l0; k < l1; ++k) {
     const int tx0 = ax0 + (k % tx) * kBboCatchW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
     const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboCatchW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
-    const int y = ty0 + (t >> 4);
-    if (y >= y1) continue;
+    for (int y = ty0 + (t >> 4); y < y1; y += 16)
 #pragma unroll
     for (int gq = 0; gq < kBboCatchW / 64; ++gq) {
       const int xg = tx0 + gq * 64 + (t & 15) * 4;
@@ -1009,8 +1010,9 @@ __device__ OADG_HANDLER void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
     if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) return;
   }
   if (!tile_pixel) {
-    const int x = x0 + (t & 15) * kChunkPx, y = y0 + (t >> 4);
-    if (x < x1 && y < y1) {
+    const int x = x0 + (t & 15) * kChunkPx;
+    for (int y = y0 + (t >> 4); y < y1; y += 16)
+    if (x < x1) {
       const int n = min(kChunkPx, W - x);
       int reg;
       if (run_is_stream(L, x, y, n, reg)) {
@@ -1097,7 +1099,8 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
   }
   __syncthreads();
   const ChainArgs& A = S.args;
-  int staged_lane = -1, scan_from = 0;
+  int staged_lane = -1, scan_from = 0, streak = 0;
+  const int kStickyTiles = (A.debug >> 8) > 0 ? (A.debug >> 8) : 1;
   if (threadIdx.x < kMaxQueueItems / 32) S.exhausted[threadIdx.x] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1118,7 +1121,9 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
     bool prefetched = false;
     if (threadIdx.x == 0) {
       // next tile of the same item, in flight during the work
-      prefetched = (A.debug & 32) ? ld_relaxed_u32(A.epoch) == S.epoch_seen : true;   // bit 5: preemptive re-scans (slower)
+      // kStickyTiles consecutive tiles of one item, then back to the queue: a more urgent item may have become ready.
+      // Measured over 24 bench batches: 1 -> 16.78 ms, 2..16 -> 17.2 ms, never -> 17.05 ms; OADG_DEBUG bits 8.. override.
+      prefetched = (++streak % kStickyTiles) != 0;
       if (prefetched) claim = atomicAdd(A.claimed + it, 1u);
     }
     const int l0 = tile, l1 = tile + 1;

@@ -68,7 +68,7 @@ enum {
   OADG_IT_HIST = 2,      // obj = lane                   tiles of kHistTilePx px (linear)
   OADG_IT_LUT = 3,       // obj = lut job                1 tile
   OADG_IT_COPY = 4,      // obj = chain                  tiles of kCopyTileBytes (linear); aux = 1: S as well as T
-  OADG_IT_BBO_R = 5,     // obj = bbo job                blend of one box, tiles of 128 x 16 px over its support
+  OADG_IT_BBO_R = 5,     // obj = bbo job                blend of one box, tiles of 256 x 16 px over its support
   OADG_IT_BBO_C = 6,     // obj = bbo job (level l-1)    catch-up copy X_l -> Y_l of its support minus level l's
   OADG_IT_STEP = 7,      // obj = lane                   tiles of 256 x 16 px
   OADG_IT_KINDS = 8
@@ -81,13 +81,37 @@ struct Item {
   int32_t dep_first, dep_count;   // the items (indices into the item table) that must be complete before this one starts
   int32_t succ_first, succ_count; // the items that wait for this one (entries of the successor table)
 };
+// (the OADG_* macros let scripts/tile_sweep.sh build timing variants; the defaults are the shipped configuration:
+// measured over 24 bench batches, 64-wide bbo / step tiles cost +9 % / +14 %, 256-wide ones save 3 % / 5 %, taller
+// (32-row) tiles cost +9 %: the queue wants tiles of ~20-30 us)
+#ifndef OADG_HIST_TILE_PX
+#define OADG_HIST_TILE_PX 32768
+#endif
+#ifndef OADG_COPY_TILE_BYTES
+#define OADG_COPY_TILE_BYTES 65536
+#endif
+#ifndef OADG_BBO_TILE_W
+#define OADG_BBO_TILE_W 256
+#endif
+#ifndef OADG_STEP_TILE_W_PX
+#define OADG_STEP_TILE_W_PX 256
+#endif
+#ifndef OADG_CATCH_TILE_W
+#define OADG_CATCH_TILE_W 512
+#endif
+#ifndef OADG_BBO_TILE_H
+#define OADG_BBO_TILE_H 16
+#endif
+#ifndef OADG_STEP_TILE_H
+#define OADG_STEP_TILE_H 16
+#endif
 constexpr int kMaskTileW = 256, kMaskTileH = 8;
-constexpr int kHistTilePx = 32768;
-constexpr int kCopyTileBytes = 65536;
-constexpr int kBboTileW = 128, kBboTileH = 16;   // bbo tiles start at the support's x0 rounded down to a multiple of 4
-constexpr int kStepTileW = 256, kStepTileH = 16;   // lanes with per-pixel ops use kStepTileWPx wide tiles (Item.aux)
-constexpr int kStepTileWPx = 128;
-constexpr int kBboCatchW = 256;                     // catch-up copies move 256 x 16 px per tile
+constexpr int kHistTilePx = OADG_HIST_TILE_PX;
+constexpr int kCopyTileBytes = OADG_COPY_TILE_BYTES;
+constexpr int kBboTileW = OADG_BBO_TILE_W, kBboTileH = OADG_BBO_TILE_H;   // bbo tiles start at the support's x0 rounded down to a multiple of 4
+constexpr int kStepTileW = 256, kStepTileH = OADG_STEP_TILE_H;   // lanes with per-pixel ops use kStepTileWPx wide tiles (Item.aux)
+constexpr int kStepTileWPx = OADG_STEP_TILE_W_PX;
+constexpr int kBboCatchW = OADG_CATCH_TILE_W;                     // catch-up copies move 512 x 16 px per tile
 
 struct MixJob {
   int32_t view, pad;
