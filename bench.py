@@ -256,6 +256,9 @@ def product_arm(args):
         j = (i * BS) % POOL
         imgs = [dev_frames[(j + b) % POOL] for b in range(BS)]
         g = [gts[(j + b) % POOL] for b in range(BS)]
+        if profile is None:   # like a loader that knows the next batch: its saliency scores are requested now, ahead of
+            jn = ((i + 1) * BS) % POOL   # this step's kernels, and are finished when step i + 1 asks for them
+            mix.prefetch_saliency([dev_frames[(jn + b) % POOL] for b in range(BS)], [gts[(jn + b) % POOL] for b in range(BS)])
         mix.oamix_batch(imgs, g, profile=profile, outs=out_bufs, inputs_ready=True)  # frames resident since setup
         n_mix = mix.last_launches
         if not with_loss:

@@ -225,3 +225,26 @@ def test_call_batch_equals_per_sample_calls(cuda):
         for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
             assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(b['img'], img) and b['img2'].dtype == np.uint8 and b['oamix_boxes'].dtype == np.int64
+
+
+def test_prefetched_saliency_gives_the_same_views(cuda):
+    """prefetch_saliency() for upcoming batches (two in flight) must not change anything but the timing."""
+    from oadg_b200 import OAMix
+    import torch
+    t = OAMix(**dict(OAMIX_CFG, version='augmix'))
+    batches = []
+    for k in range(3):
+        imgs, gts = zip(*[synth.make_image(20 + 2 * k + j, 160, 288, 4) for j in range(2)])
+        batches.append((_views(cuda, imgs), list(gts)))
+    np.random.seed(5)
+    plain = [[o.clone() for o in t.oamix_batch(d, g)[0]] for d, g in batches]
+    np.random.seed(5)
+    t.prefetch_saliency(*batches[0])
+    got = []
+    for k, (d, g) in enumerate(batches):
+        if k + 1 < len(batches):
+            t.prefetch_saliency(*batches[k + 1])
+        got.append([o.clone() for o in t.oamix_batch(d, g)[0]])
+    for a, b in zip(plain, got):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
