@@ -290,18 +290,17 @@ __device__ OADG_HANDLER void mask_tile(const ChainArgs& A, ChainSmem& S, int vie
   __syncthreads();
   const int n = S.bs.n_excl;
   const int x = x0 + (threadIdx.x & 255);
-  const int yb = y0;
   if (x >= x1) return;
   const size_t base = (size_t)view * P.mask_stride;
   if (n > 8) {  // many overlapping boxes: the plain per-pixel walk
-    for (int y = yb; y < min(yb + 8, y1); ++y) mask_pixel(P, view, x, y, A.maskf, A.masku);
+    for (int y = y0; y < y1; ++y) mask_pixel(P, view, x, y, A.maskf, A.masku);
     return;
   }
   float ux[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     ux[c] = (c < n && x >= S.bs.excl[c][0] && x < S.bs.excl[c][2]) ? A.prof_x[(size_t)S.cand[c] * P.max_w + x] : -1.f;
-  for (int y = yb; y < min(yb + 8, y1); ++y) {
+  for (int y = y0; y < y1; ++y) {
     float m = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -1010,9 +1009,8 @@ __device__ OADG_HANDLER void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
     if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) return;
   }
   if (!tile_pixel) {
-    const int x = x0 + (t & 15) * kChunkPx;
-    for (int y = y0 + (t >> 4); y < y1; y += 16)
-    if (x < x1) {
+    for (int x = x0 + (t & 15) * kChunkPx; x < x1; x += 16 * kChunkPx)
+    for (int y = y0 + (t >> 4); y < y1; y += 16) {
       const int n = min(kChunkPx, W - x);
       int reg;
       if (run_is_stream(L, x, y, n, reg)) {
@@ -1032,8 +1030,7 @@ __device__ OADG_HANDLER void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
     }
   }
   if (!tile_stream && !L.all_streaming) {
-    const int x = x0 + (t & 255);  // this thread's column is fixed
-    if (x >= x1) return;
+    for (int x = x0 + (t & 255); x < x1; x += 256) {  // this thread's columns
     const int xc = x & ~(kChunkPx - 1), nc = min(kChunkPx, W - xc);  // the 16-pixel run this column belongs to
     int ax[OADG_MAX_REGIONS], bx[OADG_MAX_REGIONS];
 #pragma unroll
@@ -1058,6 +1055,7 @@ __device__ OADG_HANDLER void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t
       } else {
         pixel_op_fast(A, L, S.rop[r], S.lut, r, x, y);
       }
+    }
     }
   }
 }

@@ -64,7 +64,7 @@ OADG_HD uint8_t* chain_dst(const Chain& C, int level) { return (level & 1) ? C.T
 // comes after the items it depends on; an item starts when all tiles of its dependencies are done.
 enum {
   OADG_IT_PROFILE = 0,   // obj = gt*2 + axis            1 tile
-  OADG_IT_MASK = 1,      // obj = view                   tiles of 256 x 8 px
+  OADG_IT_MASK = 1,      // obj = view                   tiles of 256 x 32 px
   OADG_IT_HIST = 2,      // obj = lane                   tiles of kHistTilePx px (linear)
   OADG_IT_LUT = 3,       // obj = lut job                1 tile
   OADG_IT_COPY = 4,      // obj = chain                  tiles of kCopyTileBytes (linear); aux = 1: S as well as T
@@ -105,11 +105,17 @@ struct Item {
 #ifndef OADG_STEP_TILE_H
 #define OADG_STEP_TILE_H 16
 #endif
-constexpr int kMaskTileW = 256, kMaskTileH = 8;
+#ifndef OADG_STEP_TILE_W
+#define OADG_STEP_TILE_W 512
+#endif
+#ifndef OADG_MASK_TILE_H
+#define OADG_MASK_TILE_H 32
+#endif
+constexpr int kMaskTileW = 256, kMaskTileH = OADG_MASK_TILE_H;
 constexpr int kHistTilePx = OADG_HIST_TILE_PX;
 constexpr int kCopyTileBytes = OADG_COPY_TILE_BYTES;
 constexpr int kBboTileW = OADG_BBO_TILE_W, kBboTileH = OADG_BBO_TILE_H;   // bbo tiles start at the support's x0 rounded down to a multiple of 4
-constexpr int kStepTileW = 256, kStepTileH = OADG_STEP_TILE_H;   // lanes with per-pixel ops use kStepTileWPx wide tiles (Item.aux)
+constexpr int kStepTileW = OADG_STEP_TILE_W, kStepTileH = OADG_STEP_TILE_H;   // lanes with per-pixel ops use kStepTileWPx wide tiles (Item.aux)
 constexpr int kStepTileWPx = OADG_STEP_TILE_W_PX;
 constexpr int kBboCatchW = OADG_CATCH_TILE_W;                     // catch-up copies move 512 x 16 px per tile
 
