@@ -112,6 +112,7 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
 
 // thread 0 only: find the next (item, tile); returns false when every item is exhausted
 __device__ bool scan_for_work(const ChainArgs& A, unsigned* exhausted, int& scan_from, int& item, int& tile) {
+  unsigned long long spin_t0 = 0;
   for (;;) {
     bool any_left = false;
     while (scan_from < A.n_items && (exhausted[scan_from >> 5] >> (scan_from & 31) & 1u)) ++scan_from;
@@ -135,6 +136,13 @@ __device__ bool scan_for_work(const ChainArgs& A, unsigned* exhausted, int& scan
     }
     if (!any_left) return false;
     __nanosleep(256);   // nothing is ready: back off before polling the counters again
+    // safety valve: a CTA that finds nothing ready for 2 s gives up (flag in stats slot 15) instead of hanging the GPU
+    const unsigned long long now = globaltimer_ns();
+    if (spin_t0 == 0) spin_t0 = now;
+    else if (now - spin_t0 > 2000000000ull) {
+      atomicAdd(A.kind_ns + 15, 1ull);
+      return false;
+    }
   }
 }
 __device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) {
@@ -1333,8 +1341,10 @@ extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_by
   if (rc == 0 && e == cudaSuccess && be.ev[2]) {
     cudaEventElapsedTime(ms_chain, be.ev[0], be.ev[1]);
     cudaEventElapsedTime(ms_mix, be.ev[1], be.ev[2]);
-    if (kind_stats && be.kind_ns_dev)
-      e = cudaMemcpy(kind_stats, be.kind_ns_dev, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    unsigned long long ks[48] = {0};
+    if (be.kind_ns_dev) e = cudaMemcpy(ks, be.kind_ns_dev, sizeof(ks), cudaMemcpyDeviceToHost);
+    if (kind_stats) memcpy(kind_stats, ks, sizeof(ks));
+    if (ks[15] != 0) rc = OADG_E_PLAN;   // a CTA gave up waiting: the dependency tables were inconsistent
     if (getenv("OADG_TRACE") && be.item_ts_dev && be.n_items > 0) {
       std::vector<unsigned long long> ts((size_t)be.n_items * 2);
       cudaMemcpy(ts.data(), be.item_ts_dev, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);

@@ -120,3 +120,42 @@ def test_chain_scheduler_medium_frames(hostsim, seed):
     assert d.max() <= 1 and (d != 0).mean() <= 1e-3, (int(d.max()), float((d != 0).mean()))
     n_boxes = sum(len(op[1]) for steps in vp.ops for regs in steps for op in regs if op[0] == 'bbo_affine')
     assert stats[2] <= n_boxes      # dead-box elimination never adds work
+
+
+def test_many_boxes_deep_chains(hostsim):
+    """40 gt boxes on a small frame: long bboxes-only chains (many dependency levels, hundreds of work items) and a
+    crowded union mask -- scheduler limits and dependency tables under stress, against the oracle."""
+    from oadg_b200.oamix import OAMix
+    cfg = sampler_cfg(dict(OAMIX_CFG, version='augmix'))
+    img, gt = synth.make_image(5, 192, 256, 40)
+    for seed in (3, 4):
+        np.random.seed(seed)
+        ref, plan = oamix_np.oamix_view(img, gt, **cfg)
+        np.random.seed(seed)
+        t = OAMix(**cfg)
+        vp = t._sample_head(192, 256, gt)
+        t._sample_tail(vp, gt, plan['scores'])
+        (a,), _ = run_ex(hostsim, t, [(vp, gt, 0)], [img], 1)
+        (b,), st = run_ex(hostsim, t, [(vp, gt, 0)], [img], 64)
+        assert np.array_equal(a, b) and st[1] >= 10
+        d = np.abs(a.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d != 0).mean() <= 2e-3, (int(d.max()), float((d != 0).mean()))
+
+
+def test_frames_beyond_the_compiled_limit_are_rejected(hostsim):
+    """The profile tile keeps <= 1024 low-res samples / taps in shared memory: a 4100-px-wide frame must come back as
+    OADG_E_LIMIT (-3) from the executor, not as a crash."""
+    from oadg_b200.oamix import OAMix
+    t = OAMix(**sampler_cfg(dict(OAMIX_CFG, version='augmix')))
+    h, w = 16, 4104
+    img = np.zeros((h, w, 3), np.uint8)
+    gt = np.float32([[10, 2, 300, 12]])
+    np.random.seed(1)
+    vp = t._sample_head(h, w, gt)
+    t._sample_tail(vp, gt, [np.float64(20.0)])
+    blob = t._pack([(vp, gt, 0)])
+    out = np.zeros_like(img)
+    src = (ctypes.c_void_p * 1)(img.ctypes.data)
+    dst = (ctypes.c_void_p * 1)(out.ctypes.data)
+    rc = hostsim.hostsim_oamix_execute(ctypes.c_void_p(blob.ctypes.data), ctypes.c_size_t(blob.nbytes), src, 1, dst, None)
+    assert rc == -3, rc
