@@ -17,13 +17,14 @@ mix = OAMix(**bench.OAMIX_CFG)
 np.random.seed(1000)
 for i in range(3):
     mix.oamix_batch(imgs[0:2], gts[0:2])
-tot_chain = 0.0
+tot_chain = tot_mix = 0.0
 quiet = len(sys.argv) > 2
 for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     prof = {}
     j = (2 * i) % 8
     mix.oamix_batch(imgs[j:j + 2], gts[j:j + 2], profile=prof)
     tot_chain += prof['chain_ms'] * 1e3
+    tot_mix += prof['mix_ms'] * 1e3
     if quiet:
         continue
     print('batch %d: chain %.1f us, mix %.1f us, %d items, %d tiles' % (
@@ -33,4 +34,4 @@ for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
         tot += us
         print('   kind %-16s busy %9.1f CTA-us over %6d tiles = %7.2f us/tile, longest %7.1f us' % (k, us, n, us / max(n, 1), mx))
     print('   total %.1f CTA-us = %.1f us on 592 CTAs' % (tot, tot / 592))
-print('chain kernel total over the batches: %.1f us' % tot_chain)
+print('chain kernel total over the batches: %.1f us, mix kernel total: %.1f us' % (tot_chain, tot_mix))
