@@ -119,12 +119,14 @@ __device__ bool scan_for_work(const ChainArgs& A, unsigned* exhausted, int& scan
     for (int k = scan_from; k < A.n_items; ++k) {
       if (exhausted[k >> 5] >> (k & 31) & 1u) continue;
       const unsigned nt = (unsigned)A.items[k].ntiles;
-      if (ld_relaxed_u32(A.claimed + k) >= nt) {
+      const unsigned cl = ld_relaxed_u32(A.claimed + k);   // the two loads are independent: one L2 round trip
+      const int pend = ld_acquire_s32(A.pending + k);
+      if (cl >= nt) {
         exhausted[k >> 5] |= 1u << (k & 31);
         continue;
       }
       any_left = true;
-      if (ld_acquire_s32(A.pending + k) > 0) continue;   // inputs not complete yet: look further down the queue
+      if (pend > 0) continue;   // inputs not complete yet: look further down the queue
       const unsigned t = atomicAdd(A.claimed + k, 1u);
       if (t < nt) {
         item = k;
@@ -149,9 +151,7 @@ __device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) 
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    bool released = false;
-    for (int k = 0; k < I.succ_count; ++k) released |= atomicSub(A.pending + A.succ[I.succ_first + k], 1) == 1;
-    if (released) atomicAdd(A.epoch, 1u);   // an item became ready: CTAs on lower-priority items re-scan the queue
+    for (int k = 0; k < I.succ_count; ++k) atomicSub(A.pending + A.succ[I.succ_first + k], 1);
   }
 }
 
@@ -1106,7 +1106,7 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
   __syncthreads();
   const ChainArgs& A = S.args;
   int staged_lane = -1, scan_from = 0, streak = 0;
-  const int kStickyTiles = (A.debug >> 8) > 0 ? (A.debug >> 8) : 1;
+  const int kStickyTiles = A.debug >> 8;
   if (threadIdx.x < kMaxQueueItems / 32) S.exhausted[threadIdx.x] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1126,10 +1126,11 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
     unsigned claim = 0;
     bool prefetched = false;
     if (threadIdx.x == 0) {
-      // next tile of the same item, in flight during the work
-      // kStickyTiles consecutive tiles of one item, then back to the queue: a more urgent item may have become ready.
-      // Measured over 24 bench batches: 1 -> 16.78 ms, 2..16 -> 17.2 ms, never -> 17.05 ms; OADG_DEBUG bits 8.. override.
-      prefetched = (++streak % kStickyTiles) != 0;
+      // A CTA never claims ahead: a tile claimed while the previous one is still being processed sits idle at the
+      // end of an item, and the items of the critical path then finish one tile time later (measured over 24 bench
+      // batches: claim-ahead 17.2-18.2 ms, re-scan after every tile 15.0 ms).  OADG_DEBUG bits 8..: n > 1 = claim ahead
+      // for n - 1 consecutive tiles, then re-scan.
+      prefetched = kStickyTiles > 1 && (++streak % kStickyTiles) != 0;
       if (prefetched) claim = atomicAdd(A.claimed + it, 1u);
     }
     const int l0 = tile, l1 = tile + 1;
