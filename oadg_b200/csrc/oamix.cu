@@ -1133,7 +1133,7 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
       prefetched = kStickyTiles > 1 && (++streak % kStickyTiles) != 0;
       if (prefetched) claim = atomicAdd(A.claimed + it, 1u);
     }
-    const int l0 = tile, l1 = tile + 1;
+    const int l0 = I.perm_first >= 0 ? A.perm[I.perm_first + tile] : tile, l1 = l0 + 1;
     const unsigned long long seg_t0 = globaltimer_ns();
     switch (I.kind) {
       case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;

@@ -80,6 +80,8 @@ struct Item {
   int32_t aux;
   int32_t dep_first, dep_count;   // the items (indices into the item table) that must be complete before this one starts
   int32_t succ_first, succ_count; // the items that wait for this one (entries of the successor table)
+  int32_t perm_first;             // >= 0: claim t runs tile perm[perm_first + t] (long tiles first), -1: tile t
+  int32_t pad;
 };
 // (the OADG_* macros let scripts/tile_sweep.sh build timing variants; the defaults are the shipped configuration:
 // measured over 24 bench batches, 64-wide bbo / step tiles cost +9 % / +14 %, 256-wide ones save 3 % / 5 %, taller

@@ -98,7 +98,7 @@ struct Layout {
   size_t zero_bytes;
   int any_bg;
   size_t tables_bytes;
-  int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_deps, n_bbo;
+  int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_deps, max_perm, n_bbo;
   size_t total;
 };
 
@@ -137,6 +137,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.n_bbo = h.n_bbo;
   L.max_items = 2 * h.n_gt + h.n_views + 2 * lanes_total + n_lut + n_chains + 2 * h.n_bbo + 8;
   L.max_deps = 8 * L.max_items + n_chains * 4 * max_chain * max_chain + 64;
+  L.max_perm = lanes_total * (((h.max_w + kStepTileWPx - 1) / kStepTileWPx) * ((h.max_h + kStepTileH - 1) / kStepTileH)) + 16;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -150,6 +151,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
                    align_up_sz((size_t)L.max_items * sizeof(Item), 16) +
                    2 * align_up_sz((size_t)L.max_deps * sizeof(int32_t), 16) +
                    align_up_sz((size_t)L.max_items * sizeof(int32_t), 16) +
+                   align_up_sz((size_t)L.max_perm * sizeof(int32_t), 16) +
                    align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
   L.off_tables = align_up_sz((size_t)h.total_bytes, 16);
@@ -285,6 +287,7 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   const Item* items;
   const int32_t* deps;       // dependency lists of the items (host-side checks only)
   const int32_t* succ;       // successor lists of the items
+  const int32_t* perm;       // tile orders of the depth-step items with per-pixel work (long tiles first)
   int32_t* pending;          // [n_items] dependency tiles still outstanding (uploaded with the tables)
   int32_t n_items, n_tiles, grid, debug;
   unsigned* epoch;           // bumped whenever an item becomes ready (zeroed before the launch)
@@ -365,6 +368,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const size_t t_deps = carve((size_t)L.max_deps * sizeof(int32_t));
   const size_t t_succ = carve((size_t)L.max_deps * sizeof(int32_t));
   const size_t t_pending = carve((size_t)L.max_items * sizeof(int32_t));
+  const size_t t_perm = carve((size_t)L.max_perm * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
@@ -374,6 +378,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   auto* deps = reinterpret_cast<int32_t*>(stage.data() + t_deps);
   auto* succ = reinterpret_cast<int32_t*>(stage.data() + t_succ);
   auto* pending = reinterpret_cast<int32_t*>(stage.data() + t_pending);
+  auto* perm = reinterpret_cast<int32_t*>(stage.data() + t_perm);
   auto* mixjobs = reinterpret_cast<MixJob*>(stage.data() + t_mix);
 
   // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
@@ -607,7 +612,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     });
     for (int k = 0; k < n_items; ++k) pos[order[k]] = k;
   }
-  int n_tiles = 0, n_deps = 0;
+  int n_tiles = 0, n_deps = 0, n_perm = 0;
   for (int k = 0; k < n_items; ++k) {
     const Todo& t = todo[order[k]];
     Item& it = items[k];
@@ -632,6 +637,32 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     it.ntiles = it.tx * ((t.hgt + th - 1) / th);
     if (it.ntiles < 0) it.ntiles = 0;
     n_tiles += it.ntiles;
+    it.perm_first = -1;
+    it.pad = 0;
+    if (t.kind == OADG_IT_STEP && !lanes[t.obj].all_streaming && n_perm + it.ntiles <= L.max_perm) {
+      // long tiles first: the item is complete when its LAST tile is, so the tail should be made of short ones
+      const Lane& ln = lanes[t.obj];
+      it.perm_first = n_perm;
+      for (int cls = 3; cls >= 0; --cls)
+        for (int ti = 0; ti < it.ntiles; ++ti) {
+          const int x0 = (ti % it.tx) * tw, y0 = (ti / it.tx) * th;
+          const int x1 = x0 + tw < ln.W ? x0 + tw : ln.W, y1 = y0 + th < ln.H ? y0 + th : ln.H;
+          int region = ln.n_ml, c = 0;
+          bool edge = false;
+          for (int bb = 0; bb < ln.n_ml; ++bb) {
+            const int32_t* B = ln.box[bb];
+            if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;
+            if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = bb;
+            else edge = true;
+          }
+          bool any_bg = false;
+          for (int r = 0; r <= ln.n_ml; ++r) any_bg |= ln.kind[r] == OADG_OP_BG_AFFINE;
+          if (edge) c = any_bg ? 3 : 1;
+          else if (ln.kind[region] == OADG_OP_BG_AFFINE) c = 2;
+          else c = (is_lut_kind(ln.kind[region]) || ln.kind[region] == OADG_OP_BBO_AFFINE) ? 0 : 1;
+          if (c == cls) perm[n_perm++] = ti;
+        }
+    }
     it.dep_first = n_deps;
     it.dep_count = 0;
     for (int d2 : t.deps) {
@@ -699,6 +730,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.items = reinterpret_cast<const Item*>(dplan + t_items);
   A.deps = reinterpret_cast<const int32_t*>(dplan + t_deps);
   A.succ = reinterpret_cast<const int32_t*>(dplan + t_succ);
+  A.perm = reinterpret_cast<const int32_t*>(dplan + t_perm);
   A.pending = reinterpret_cast<int32_t*>(const_cast<char*>(dplan) + t_pending);
   A.n_items = n_items;
   A.n_tiles = n_tiles;
@@ -726,6 +758,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   Hh.items = items;
   Hh.deps = deps;
   Hh.succ = succ;
+  Hh.perm = perm;
   Hh.pending = pending;
   if ((rc = be.chain(A, Hh, pv))) return rc;
   return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);

@@ -228,7 +228,8 @@ struct HostBackend {
       if (pick < 0) return -204;
       const Item& I = A.items[pick];
       for (int t = I.ntiles - 1; t >= 0; --t) {   // tiles of an item are independent: any order
-        const int rc = run_tile(A, I, n_cta > 1 ? t : I.ntiles - 1 - t);
+        const int tt = n_cta > 1 ? t : I.ntiles - 1 - t;
+        const int rc = run_tile(A, I, I.perm_first >= 0 ? A.perm[I.perm_first + tt] : tt);
         if (rc) return rc;
       }
       finished[pick] = 1;
