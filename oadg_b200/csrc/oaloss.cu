@@ -123,6 +123,7 @@ label_prep_kernel(const int64_t* __restrict__ labels, const int32_t* __restrict_
     meta[0] = (int)bg;
     meta[1] = t;
     meta[2] = t > min_samples ? 1 : 0;  // contrastive_loss.py:211
+    meta[4] = 0;                        // ticket of the row-reduce blocks
   }
 }
 
@@ -231,21 +232,24 @@ sim_fwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels, 
 
 // combine the column-tile partials, emit per-row stats and the scalar loss (single block,
 // fixed summation order => deterministic)
-__global__ void __launch_bounds__(1024)
-row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ npos, const int* __restrict__ meta,
+constexpr int kRowReduceThreads = 256;
+__global__ void __launch_bounds__(kRowReduceThreads)
+row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ npos, int* __restrict__ meta,
                   int n, int row0, int n_total, int col_tiles, float loss_weight, RowStats* __restrict__ stats,
-                  float* __restrict__ loss) {
+                  double* __restrict__ red, float* __restrict__ loss) {
   // rows [row0, row0 + n) of an n_total-row problem (single GPU: row0 = 0, n = n_total); partial / stats are
-  // indexed by the local row, npos by the global row; the loss is this range's share of the mean over n_total
-  __shared__ double red[32];
-  const int tid = threadIdx.x;
+  // indexed by the local row, npos by the global row; the loss is this range's share of the mean over n_total.
+  // One row per thread; the block sums go to `red` and the block that takes the last ticket adds them in block
+  // order (deterministic).
+  __shared__ double sred[kRowReduceThreads / 32];
+  const int tid = threadIdx.x, i = blockIdx.x * kRowReduceThreads + tid;
   if (!meta[2]) {
-    for (int i = tid; i < n; i += blockDim.x) stats[i] = RowStats{0.f, 0.f, 0.f, 0.f};
-    if (tid == 0) *loss = 0.f;
+    if (i < n) stats[i] = RowStats{0.f, 0.f, 0.f, 0.f};
+    if (i == 0) *loss = 0.f;
     return;
   }
   double local = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) {
+  if (i < n) {
     float M = -INFINITY;
     for (int t = 0; t < col_tiles; ++t) M = fmaxf(M, partial[((size_t)t * n + i) * 3]);
     float S = 0.f, Ps = 0.f;
@@ -262,15 +266,23 @@ row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ n
     st.coef = np > 0.f ? -(loss_weight / (float)n_total) / np : 0.f;
     st.u = st.coef * np * expf(-lse);
     stats[i] = st;
-    if (np > 0.f) local += (double)(Ps / np - lse);
+    if (np > 0.f) local = (double)(Ps / np - lse);
   }
   local = warp_sum(local);
-  if ((tid & 31) == 0) red[tid >> 5] = local;
+  if ((tid & 31) == 0) sred[tid >> 5] = local;
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    *loss = (float)(-(double)loss_weight * t / (double)n_total);
+    for (int w = 0; w < kRowReduceThreads / 32; ++w) t += sred[w];
+    red[blockIdx.x] = t;
+    __threadfence();
+    if (atomicAdd(&meta[4], 1) == (int)gridDim.x - 1) {   // the last block: every partial sum is visible
+      __threadfence();
+      double tot = 0.0;
+      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) tot += *((volatile double*)red + b2);
+      *loss = (float)(-(double)loss_weight * tot / (double)n_total);
+      meta[4] = 0;
+    }
   }
 }
 
@@ -451,8 +463,9 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
     OADG_LAUNCH_CHECK();
     ++launches;
   }
-  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n, 0, n, red_tiles, loss_weight, w.stats,
-                                            loss_dev);
+  if ((n + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
+  row_reduce_kernel<<<(n + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
+      w.partial, w.npos, w.meta, n, 0, n, red_tiles, loss_weight, w.stats, w.red, loss_dev);
   OADG_LAUNCH_CHECK();
   launches += 3;
   if (launches_out) *launches_out = launches;
@@ -544,8 +557,10 @@ extern "C" int oadg_supcon_forward_gathered(const float* fhat_all_dev, const int
   OADG_LAUNCH_CHECK();
   int rc = launch_sim_fwd_tc(w, labels_all_dev, pair_all_dev, n_total, row0, n_rows, 1.f / temperature, stream, &launches);
   if (rc) return rc;
-  row_reduce_kernel<<<1, 1024, 0, stream>>>(w.partial, w.npos, w.meta, n_rows, row0, n_total, (n_total + 127) / 128,
-                                            loss_weight, reinterpret_cast<RowStats*>(stats_local_dev), loss_part_dev);
+  if ((n_rows + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
+  row_reduce_kernel<<<(n_rows + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
+      w.partial, w.npos, w.meta, n_rows, row0, n_total, (n_total + 127) / 128, loss_weight,
+      reinterpret_cast<RowStats*>(stats_local_dev), w.red, loss_part_dev);
   OADG_LAUNCH_CHECK();
   launches += 2;
   if (launches_out) *launches_out = launches;

@@ -18,7 +18,8 @@ struct LossWs {
   float* inv1;       // [n] 1/max(||x||, eps)
   float* inv2;       // [n] 1/max(||x/||x||||, eps)
   RowStats* stats;   // [n]
-  int* meta;         // [0] bg label (low 32 bits), [1] n_fg, [2] active flag
+  int* meta;         // [0] bg label (low 32 bits), [1] n_fg, [2] active flag, [4] ticket of the row-reduce blocks
+  double* red;       // [<= 1024] per-block partial sums of the row reduce
   float* npos;       // [n]
   float* partial;    // [col_tiles][n][3]  (max, sumexp, possum)
   float* dfhat;      // [n, c] gradient wrt fhat
@@ -49,6 +50,7 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
   const int ld = (n + 31) / 32 * 32;
   size_t o_th = take((size_t)c * ld * 4), o_tl = take((size_t)c * ld * 4);
   size_t o_z = take((size_t)n * ld * 4), o_dp = take((size_t)kBwdSplits * n * c * 4);
+  size_t o_red = take(1024 * sizeof(double));
   w.fhat = reinterpret_cast<float*>(p + o_f);
   w.inv1 = reinterpret_cast<float*>(p + o_i1);
   w.inv2 = reinterpret_cast<float*>(p + o_i2);
@@ -63,6 +65,7 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
   w.ft_lo = reinterpret_cast<float*>(p + o_tl);
   w.z = reinterpret_cast<float*>(p + o_z);
   w.dpart = reinterpret_cast<float*>(p + o_dp);
+  w.red = reinterpret_cast<double*>(p + o_red);
   w.ld = ld;
   w.bytes = o;
   return w;
