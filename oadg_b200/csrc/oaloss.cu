@@ -376,12 +376,13 @@ normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dpar
   const float* xr = x + (size_t)row * c;
   const float i1 = inv1[row], i2 = inv2[row];
   // dL/dfhat of this row = sum of the column-split partials, in a fixed order (c == 256: 8 values per lane)
-  float gr[8];
+  // (partials outer, columns inner: eight independent loads per step, same summation order per column)
+  float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int p = 0; p < n_part; ++p) {
+    const float* dp = dpart + ((size_t)p * n + row) * c + lane;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float a = 0.f;
-    for (int p = 0; p < n_part; ++p) a += dpart[((size_t)p * n + row) * c + lane + 32 * q];
-    gr[q] = a;
+    for (int q = 0; q < 8; ++q) gr[q] += dp[32 * q];
   }
   // second normalisation: v = x*i1, u = v*i2 ; g1 = (g - (u.g) u) * i2
   float dot = 0.f;
