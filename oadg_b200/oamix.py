@@ -488,12 +488,13 @@ class OAMix:
             if st is None or st['cap'] < nbytes or st['dev'] != dev:
                 cap = max(4096, 2 * nbytes)
                 shared = next(iter(self._sal_state.values()), None)
+                side = shared['stream'] if shared and shared['dev'] == dev else torch.cuda.Stream(dev)
+                with torch.cuda.stream(side):   # device buffers owned by the stream that uses them (allocator pools
+                    devbuf = torch.empty(cap, dtype=torch.uint8, device=dev)          # are per stream: no block that a
+                    scores = torch.empty(cap // 8, dtype=torch.float64, device=dev)   # main-stream kernel still reads)
                 st = self._sal_state[slot] = dict(
-                    cap=cap, dev=dev, host=torch.empty(cap, dtype=torch.uint8).pin_memory(),
-                    devbuf=torch.empty(cap, dtype=torch.uint8, device=dev),
-                    scores=torch.empty(cap // 8, dtype=torch.float64, device=dev),
-                    scores_host=torch.empty(cap // 8, dtype=torch.float64).pin_memory(),
-                    stream=shared['stream'] if shared and shared['dev'] == dev else torch.cuda.Stream(dev),
+                    cap=cap, dev=dev, host=torch.empty(cap, dtype=torch.uint8).pin_memory(), devbuf=devbuf, scores=scores,
+                    scores_host=torch.empty(cap // 8, dtype=torch.float64).pin_memory(), stream=side,
                     event=torch.cuda.Event())
             hb = st['host'].numpy()
             hb[:o_hw].view(np.int64)[:] = [int(t.data_ptr()) for t in imgs]
@@ -534,7 +535,13 @@ class OAMix:
     def _workspace(self, nbytes, device):
         torch = _lib.require_cuda()
         if self._ws_cache is None or self._ws_cache.numel() < nbytes or self._ws_cache.device != device:
-            self._ws_cache = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+            # The old workspace may still be in use by kernels in flight; once released, the caching allocator may hand
+            # its block to a buffer that is used on ANOTHER stream (the saliency stream) right away.  Growing is rare:
+            # drain the device first.
+            if self._ws_cache is not None:
+                torch.cuda.synchronize(self._ws_cache.device)
+            self._ws_cache = None
+            self._ws_cache = torch.empty(int(nbytes * 1.5) + 4096, dtype=torch.uint8, device=device)
         return self._ws_cache
 
     def execute(self, jobs, imgs, outs=None, stream=None, profile=None):
