@@ -81,13 +81,50 @@ def workload_config(n_gpus):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region: an in-process NVML poller (every 5 ms, so that even a
+    sub-second region gets tens of samples), or `nvidia-smi -lms 50` when NVML is not importable."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.thread = index, None, None
+        self.sm, self.reasons, self.max_mhz, self.stop_flag = [], set(), None, False
+
+    def _nvml_loop(self, nv, h):
+        bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:   # noqa: BLE001  (a failed poll is just a missing sample)
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.index
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:   # NVML numbers physical devices
+                try:
+                    idx = int(vis.split(',')[self.index])
+                except (ValueError, IndexError):
+                    idx = self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:   # noqa: BLE001
+            self.thread = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '50'],
@@ -96,6 +133,11 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                    'samples': len(self.sm), 'reasons': sorted(self.reasons), 'source': 'nvml, 5 ms poll'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -118,7 +160,7 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'reasons': sorted(reasons), 'source': 'nvidia-smi -lms 50'}
 
 
 # ------------------------------------------------------------------------------------------
