@@ -36,3 +36,18 @@ def cuda(libpath):
 def sampler_cfg(cfg):
     """Keys the oracle's sample_plan / the product ctor share."""
     return {k: v for k, v in cfg.items() if k not in ('num_views', 'keep_orig', 'severity')}
+
+
+def build_hostsim():
+    """(Re)build tests/hostsim/libhostsim.so when it is missing or older than its sources; returns its path.
+    Test infrastructure only: the device bodies + host scheduler compiled for the CPU."""
+    import subprocess
+    src = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim.cpp')
+    lib = os.path.join(ROOT, 'tests', 'hostsim', 'libhostsim.so')
+    deps = [src, os.path.join(ROOT, 'include', 'oadg.h')] + [
+        os.path.join(ROOT, 'oadg_b200', 'csrc', f) for f in ('oamix_math.h', 'oamix_body.h', 'oamix_exec.h', 'oamix_tile.h')]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC',
+                               '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'oadg_b200', 'csrc'),
+                               src, '-o', lib])
+    return lib

@@ -162,11 +162,8 @@ def test_single_op_plans_match_host_arithmetic_bit_for_bit(cuda):
     import torch
     from conftest import ROOT
     from oadg_b200.oamix import OAMix, _ViewPlan, _invert_affine
-    lib = os.path.join(ROOT, 'tests', 'hostsim', 'libhostsim.so')
-    if not os.path.exists(lib):
-        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC',
-                               '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'oadg_b200', 'csrc'),
-                               os.path.join(ROOT, 'tests', 'hostsim', 'hostsim.cpp'), '-o', lib])
+    from conftest import build_hostsim
+    lib = build_hostsim()
     hs = ctypes.CDLL(lib)
     t = OAMix(version='augmix.all')
     for (h, w, ml) in [(96, 160, [[14, 34, 29, 56]]), (131, 203, [[3, 5, 90, 60], [100, 70, 190, 120]]),

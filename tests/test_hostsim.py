@@ -13,15 +13,8 @@ from oracle import oamix_np, synth
 
 @pytest.fixture(scope='module')
 def hostsim():
-    src = os.path.join(ROOT, 'tests', 'hostsim', 'hostsim.cpp')
-    lib = os.path.join(ROOT, 'tests', 'hostsim', 'libhostsim.so')
-    if not os.path.exists(lib) or os.path.getmtime(lib) < max(
-            os.path.getmtime(src), *(os.path.getmtime(os.path.join(ROOT, 'oadg_b200', 'csrc', f))
-                                     for f in ('oamix_math.h', 'oamix_body.h', 'oamix_exec.h'))):
-        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC',
-                               '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'oadg_b200', 'csrc'),
-                               src, '-o', lib])
-    return ctypes.CDLL(lib)
+    from conftest import build_hostsim
+    return ctypes.CDLL(build_hostsim())
 
 
 def run(hs, t, jobs, imgs):
