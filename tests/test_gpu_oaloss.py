@@ -175,3 +175,40 @@ def test_gathered_loss_two_gpus_nccl(cuda):
         assert abs(loss - ref) <= RTOL * abs(ref)
         want = 2 * gref[rank * 2048:(rank + 1) * 2048]
         assert np.linalg.norm(grad - want) <= RTOL * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize('world', [4, 8])
+def test_gathered_entry_points_at_multi_rank_scale_on_one_gpu(cuda, world):
+    """The contrast-set sizes the 4- and 8-GPU runs produce (n_total = W * 2088), without NCCL: one GPU plays every
+    rank in turn through the same C-ABI calls `_GatheredSupCon` makes.  Sum of the W loss parts and each rank's
+    gradient block against the oracle on the concatenated batch."""
+    import torch
+    from oadg_b200 import reference_pair_map
+    from oadg_b200.distributed import CudaBackend, gathered_pair_map
+    n, t, lw = 2088, 0.06, 0.01
+    xs, ys = [], []
+    for r in range(world):
+        x, lab = synth.make_roi_set(n, seed=60 + r)
+        lab = lab.view(-1)
+        xs.append(x)
+        ys.append(torch.cat([lab, lab[-1:].repeat(n - lab.shape[0])]))
+    pair_np = gathered_pair_map(reference_pair_map(n), world)
+    x_all, y_all = torch.cat(xs).numpy(), torch.cat(ys).numpy()
+    ref, gref = supcon_np.supcon_loss(x_all, y_all, t, 10, lw, want_grad=True, pair=pair_np)
+    be = CudaBackend()
+    xd = [x.to(cuda) for x in xs]
+    f_all = torch.cat([be.normalize(x, world * n, True) for x in xd]).contiguous()
+    labels_all = torch.cat(ys).to(cuda)
+    pair_all = torch.from_numpy(pair_np).to(cuda)
+    parts, stats = zip(*[be.forward(f_all, labels_all, pair_all, r * n, n, t, lw, 10) for r in range(world)])
+    loss = float(torch.stack(parts).double().sum())
+    assert abs(loss - ref) <= RTOL * abs(ref)
+    stats_all = torch.cat(stats).contiguous()
+    one = torch.ones((), dtype=torch.float32, device=cuda)
+    for r in (0, world // 2, world - 1):
+        # the workspace carries one rank's normalize -> forward -> backward sequence (include/oadg.h): replay it
+        be.normalize(xd[r], world * n, True)
+        be.forward(f_all, labels_all, pair_all, r * n, n, t, lw, 10)
+        gx = be.backward(xd[r], f_all, labels_all, pair_all, stats_all, r * n, t, True, one).cpu().numpy()
+        want = gref[r * n:(r + 1) * n]
+        assert np.linalg.norm(gx - want) <= RTOL * np.linalg.norm(want), r
