@@ -12,8 +12,9 @@ images/sec = source images consumed per second (2 per step per GPU), whole job.
 
 value  : inputs resident in HBM, CUDA-event timed (includes the saliency D2H sync, host plan
          sampling and the plan upload -- they are part of the path).
-e2e    : the registered plugins called with HOST buffers (pinned): OAMix.call_batch on the step's sample dicts (numpy
-         frames in, numpy views out) and ContrastiveLossPlus on a host tensor: H2D of frames / embeddings and D2H of
+e2e    : the registered plugins called with HOST buffers (pinned) in a loader loop: OAMix.iter_batches over the
+         steps' sample dicts (numpy frames in, numpy views out; the pipelined form of OAMix.call_batch, same values)
+         and ContrastiveLossPlus on a host tensor with loss.item() every step: H2D of frames / embeddings and D2H of
          the generated views / loss value inside the timed region.
 roofline: the OA-Mix chain kernel (one persistent launch per batch), achieved = algorithmic bytes (2 * 3HW per lane
          step) / CUDA-event kernel time from a second, event-instrumented pass over the same seeded plans.
@@ -310,14 +311,20 @@ def product_arm(args):
         loss.backward()
         return n_mix, loss
 
-    def e2e_step(i):
-        j = (i * BS) % POOL
-        batch = [dict(img=host_frames[(j + b) % POOL].numpy(), gt_bboxes=gts[(j + b) % POOL]) for b in range(BS)]
-        views = [res['img2'] for res in mix.call_batch(batch)]   # host numpy in, host numpy out
-        xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
-        loss = run_loss(xd)
-        loss.backward()
-        return float(loss.item()), views
+    def host_batches(n):
+        for i in range(n):
+            j = (i * BS) % POOL
+            yield [dict(img=host_frames[(j + b) % POOL].numpy(), gt_bboxes=gts[(j + b) % POOL]) for b in range(BS)]
+
+    def e2e_steps(n):
+        # the loader loop a user writes: host numpy in, host numpy out, every step's loss read back
+        for results in mix.iter_batches(host_batches(n)):
+            views = [res['img2'] for res in results]
+            xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
+            loss = run_loss(xd)
+            loss.backward()
+            last = float(loss.item()), views
+        return last
 
     def log(msg):
         if rank == 0:
@@ -359,13 +366,11 @@ def product_arm(args):
     log('timed region done: %.3f ms/step' % (ms_max / args.steps))
     # ---- e2e through the registered plugins with host buffers
     np.random.seed(7 + rank)
-    for i in range(2):
-        e2e_step(i)
+    e2e_steps(3)
     np.random.seed(1000 + rank)
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_steps(args.steps)
     e1.record(stream)
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

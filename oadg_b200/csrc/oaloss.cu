@@ -236,7 +236,8 @@ constexpr int kRowReduceThreads = 256;
 __global__ void __launch_bounds__(kRowReduceThreads)
 row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ npos, int* __restrict__ meta,
                   int n, int row0, int n_total, int col_tiles, float loss_weight, RowStats* __restrict__ stats,
-                  double* __restrict__ red, float* __restrict__ loss) {
+                  double* __restrict__ red, float* __restrict__ loss, const float* __restrict__ z, int ld,
+                  const int64_t* __restrict__ labels, const int32_t* __restrict__ pair) {
   // rows [row0, row0 + n) of an n_total-row problem (single GPU: row0 = 0, n = n_total); partial / stats are
   // indexed by the local row, npos by the global row; the loss is this range's share of the mean over n_total.
   // One row per thread; the block sums go to `red` and the block that takes the last ticket adds them in block
@@ -260,6 +261,9 @@ row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ n
     }
     const float lse = M + logf(S);
     const float np = npos[row0 + i];
+    // tcgen05 forward: a background row's only positive is its other view (contrastive_loss.py:216-221); the
+    // similarity kernel leaves it out and the stored logit is read here (np > 0 <=> the pair is a valid bg row)
+    if (z && np > 0.f && labels[row0 + i] == (int64_t)meta[0]) Ps = z[(size_t)i * ld + pair[row0 + i]];
     RowStats st;
     st.lse = lse;
     st.npos = np;
@@ -466,7 +470,8 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
   }
   if ((n + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
   row_reduce_kernel<<<(n + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
-      w.partial, w.npos, w.meta, n, 0, n, red_tiles, loss_weight, w.stats, w.red, loss_dev);
+      w.partial, w.npos, w.meta, n, 0, n, red_tiles, loss_weight, w.stats, w.red, loss_dev,
+      loss_tc_enabled() ? w.z : nullptr, w.ld, labels_dev, pair_dev);
   OADG_LAUNCH_CHECK();
   launches += 3;
   if (launches_out) *launches_out = launches;
@@ -561,7 +566,7 @@ extern "C" int oadg_supcon_forward_gathered(const float* fhat_all_dev, const int
   if ((n_rows + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
   row_reduce_kernel<<<(n_rows + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
       w.partial, w.npos, w.meta, n_rows, row0, n_total, (n_total + 127) / 128, loss_weight,
-      reinterpret_cast<RowStats*>(stats_local_dev), w.red, loss_part_dev);
+      reinterpret_cast<RowStats*>(stats_local_dev), w.red, loss_part_dev, w.z, w.ld, labels_all_dev, pair_all_dev);
   OADG_LAUNCH_CHECK();
   launches += 2;
   if (launches_out) *launches_out = launches;

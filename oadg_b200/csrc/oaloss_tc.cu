@@ -39,6 +39,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -131,25 +134,81 @@ split_tf32_kernel(const float* __restrict__ f, int n, int ld, float* __restrict_
   }
 }
 
-__device__ __forceinline__ bool is_pos(long long yi, long long yj, long long bg, int i, int j, int pair_i) {
-  if (yi != yj || i == j) return false;
-  return yi != bg ? true : (j == pair_i);
+// ---- forward: persistent, warp-specialised, two TMEM accumulators ------------------------------------
+//   warp 0     TMA producer (lane 0), runs up to kStages chunks ahead across tile boundaries
+//   warp 1     TMEM owner + MMA issuer (lane 0): tile t accumulates into TMEM columns (t & 1) * 128, so the
+//              contraction of tile t + 1 overlaps the epilogue of tile t
+//   warps 2-5  epilogue: warp w reads TMEM lane quadrant w % 4 (a hardware rule), one tile row per thread
+// The row maximum of the reference (contrastive_loss.py:159 `logits_max`) is the diagonal z_ii = |f_i|^2 / T and
+// rows are unit vectors, so every tile shifts by the same constant 1/T: exp(z - 1/T) = 2^(c1 * (dot - 1)),
+// one FFMA + one ex2 per logit and no running maximum.  Tiles that touch the diagonal or the ragged last
+// column tile take the general (per-element predicated) epilogue; all others the fast one.
+// Positives of background rows (a single column, pair[i]) are picked up from the stored logits by the
+// row reduce; here background rows contribute no positive sum.
+constexpr int kFwdThreads = 192;
+constexpr int kFwdTmemCols = 256;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-__global__ void __launch_bounds__(128, 1)
+template <bool kGeneral>
+__device__ __forceinline__ void fwd_epilogue_tile(uint32_t tacc, int i, int j0, int n, float inv_t, float c1,
+                                                  long long yi, bool fg_row, const long long* ycol, float* zrow,
+                                                  int ld, float& s_out, float& pa_out) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, pa0 = 0.f, pa1 = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < kN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tacc + (uint32_t)c0, r);
+    if (zrow && j0 + c0 < ld) {  // keep the logits for the backward (128 B per thread)
+      float4* zp = reinterpret_cast<float4*>(zrow + c0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        zp[q] = make_float4(__uint_as_float(r[4 * q]) * inv_t, __uint_as_float(r[4 * q + 1]) * inv_t,
+                            __uint_as_float(r[4 * q + 2]) * inv_t, __uint_as_float(r[4 * q + 3]) * inv_t);
+    }
+#pragma unroll
+    for (int q = 0; q < 32; q += 2) {
+      const float a0 = __uint_as_float(r[q]), a1 = __uint_as_float(r[q + 1]);
+      const float e0 = ex2_approx(fmaf(a0, c1, -c1)), e1 = ex2_approx(fmaf(a1, c1, -c1));
+      const longlong2 y2 = *reinterpret_cast<const longlong2*>(ycol + c0 + q);
+      bool v0 = true, v1 = true;
+      if (kGeneral) {
+        const int j = j0 + c0 + q;
+        v0 = j < n && j != i;
+        v1 = j + 1 < n && j + 1 != i;
+      }
+      if (q & 2) {
+        s2 += v0 ? e0 : 0.f;
+        s3 += v1 ? e1 : 0.f;
+      } else {
+        s0 += v0 ? e0 : 0.f;
+        s1 += v1 ? e1 : 0.f;
+      }
+      if (fg_row && v0 && y2.x == yi) pa0 += a0;
+      if (fg_row && v1 && y2.y == yi) pa1 += a1;
+    }
+  }
+  s_out = (s0 + s1) + (s2 + s3);
+  pa_out = pa0 + pa1;
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
 sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                  const int64_t* __restrict__ labels, const int32_t* __restrict__ pair,
-                  const int* __restrict__ meta, int n, int row0, int n_rows, float inv_t,
-                  float* __restrict__ partial, float* __restrict__ zout, int ld) {
+                  const int64_t* __restrict__ labels, const int* __restrict__ meta, int n, int row0, int n_rows,
+                  float inv_t, int col_tiles, int n_tiles, float* __restrict__ partial, float* __restrict__ zout,
+                  int ld) {
   if (!meta[2]) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ long long ylab[kN];
+  __shared__ __align__(16) long long ycol[2][kN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int i0 = row0 + blockIdx.y * kM, j0 = blockIdx.x * kN;  // anchors: rows [row0, row0 + n_rows)
   constexpr int kChunks = 256 / kKC;
 
   if (tid == 0) {
@@ -157,107 +216,112 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"((uint32_t)kTmemCols));
+                 "r"((uint32_t)kFwdTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  ylab[tid] = (j0 + tid) < n ? labels[j0 + tid] : 0;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
-  if (tid == 0) {
-    // ---- TMA producer
-    for (int kc = 0; kc < kChunks; ++kc) {
-      const int s = kc % kStages;
-      if (kc >= kStages) mbar_wait(&empty_bar[s], ((kc / kStages) - 1) & 1);
-      uint8_t* st = smem + s * kStageBytes;
-      mbar_expect_tx(&full_bar[s], kStageBytes);
-      tma_load_2d(st, &tm_hi, &full_bar[s], kc * kKC, i0);
-      tma_load_2d(st + kOperandBytes, &tm_lo, &full_bar[s], kc * kKC, i0);
-      tma_load_2d(st + 2 * kOperandBytes, &tm_hi, &full_bar[s], kc * kKC, j0);
-      tma_load_2d(st + 3 * kOperandBytes, &tm_lo, &full_bar[s], kc * kKC, j0);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer
+      int g = 0;   // chunks issued so far: stage = g % kStages
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int i0 = row0 + (t / col_tiles) * kM, j0 = (t % col_tiles) * kN;
+        for (int kc = 0; kc < kChunks; ++kc, ++g) {
+          const int s = g % kStages;
+          if (g >= kStages) mbar_wait(&empty_bar[s], ((g / kStages) - 1) & 1);
+          uint8_t* st = smem + s * kStageBytes;
+          mbar_expect_tx(&full_bar[s], kStageBytes);
+          tma_load_2d(st, &tm_hi, &full_bar[s], kc * kKC, i0);
+          tma_load_2d(st + kOperandBytes, &tm_lo, &full_bar[s], kc * kKC, i0);
+          tma_load_2d(st + 2 * kOperandBytes, &tm_hi, &full_bar[s], kc * kKC, j0);
+          tma_load_2d(st + 3 * kOperandBytes, &tm_lo, &full_bar[s], kc * kKC, j0);
+        }
+      }
     }
-  } else if (tid == 32) {
-    // ---- MMA issuer
-    for (int kc = 0; kc < kChunks; ++kc) {
-      const int s = kc % kStages;
-      mbar_wait(&full_bar[s], (kc / kStages) & 1);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer
+      int g = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        if (it >= 2) {   // the epilogue must have drained this accumulator (tile it - 2)
+          mbar_wait(&tempty_bar[acc], ((it >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * kN);
+        for (int kc = 0; kc < kChunks; ++kc, ++g) {
+          const int s = g % kStages;
+          mbar_wait(&full_bar[s], (g / kStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = smem_u32(smem + s * kStageBytes);
+          const uint64_t ah = umma_desc(base), al = umma_desc(base + kOperandBytes);
+          const uint64_t bh = umma_desc(base + 2 * kOperandBytes), bl = umma_desc(base + 3 * kOperandBytes);
+#pragma unroll
+          for (int k = 0; k < kKC / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 floats = 32 B along the swizzled row
+            umma_tf32(tacc, ah + adv, bh + adv, (kc | k) ? 1u : 0u);
+            umma_tf32(tacc, ah + adv, bl + adv, 1u);
+            umma_tf32(tacc, al + adv, bh + adv, 1u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: thread (quadrant, lane) owns tile row quadrant * 32 + lane
+    const int quad = warp & 3, et = tid - 64;   // et: 0..127, loads one column label per tile
+    const long long bg = (long long)meta[0];
+    const float c1 = inv_t * 1.4426950408889634f;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1, bx = t % col_tiles;
+      const int i0 = row0 + (t / col_tiles) * kM, j0 = bx * kN;
+      const int i = i0 + quad * 32 + lane;
+      const bool row_ok = i < row0 + n_rows;
+      const long long yi = row_ok ? labels[i] : 0;
+      ycol[acc][et] = (j0 + et) < n ? labels[j0 + et] : 0;
+      // ycol[acc] was last read for tile it - 2; every epilogue warp has passed the barrier of tile it - 1 since
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t base = smem_u32(smem + s * kStageBytes);
-      const uint64_t ah = umma_desc(base), al = umma_desc(base + kOperandBytes);
-      const uint64_t bh = umma_desc(base + 2 * kOperandBytes), bl = umma_desc(base + 3 * kOperandBytes);
-#pragma unroll
-      for (int k = 0; k < kKC / 8; ++k) {
-        const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 floats = 32 B along the swizzled row
-        umma_tf32(tmem_base, ah + adv, bh + adv, (kc | k) ? 1u : 0u);
-        umma_tf32(tmem_base, ah + adv, bl + adv, 1u);
-        umma_tf32(tmem_base, al + adv, bh + adv, 1u);
-      }
-      umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
-    }
-    umma_commit(&accum_bar);
-  }
-  __syncwarp();
-  // ---- epilogue: thread (warp, lane) owns tile row warp*32 + lane
-  mbar_wait(&accum_bar, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int i = i0 + warp * 32 + lane;
-  const bool row_ok = i < row0 + n_rows;
-  const long long bg = (long long)meta[0];
-  const long long yi = row_ok ? labels[i] : 0;
-  const int pi = row_ok ? pair[i] : -1;
-  float m = -INFINITY, s = 0.f, ps = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < kN; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-    float cm = -INFINITY;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      const int j = j0 + c0 + q;
-      const float z = __uint_as_float(r[q]) * inv_t;
-      r[q] = __float_as_uint(z);
-      if (j < n) cm = fmaxf(cm, z);
-    }
-    if (row_ok && j0 + c0 < ld) {  // keep the logits for the backward (128 B per thread, L2-resident)
-      float4* zp = reinterpret_cast<float4*>(zout + (size_t)(i - row0) * ld + j0 + c0);
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        zp[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                            __uint_as_float(r[4 * q + 3]));
-    }
-    if (cm > m) {
-      s *= expf(m - cm);
-      m = cm;
-    }
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      const int j = j0 + c0 + q;
-      if (j < n) {
-        const float z = __uint_as_float(r[q]);
-        if (j != i) s += expf(z - m);
-        if (is_pos(yi, ylab[c0 + q], bg, i, j, pi)) ps += z;
+      const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kN);
+      float* zrow = row_ok ? zout + (size_t)(i - row0) * ld + j0 : nullptr;
+      const bool general = (j0 + kN > n) || (i0 < j0 + kN && j0 < i0 + kM);
+      float s, pa;
+      if (general) fwd_epilogue_tile<true>(tacc, i, j0, n, inv_t, c1, yi, row_ok && yi != bg, ycol[acc], zrow, ld, s, pa);
+      else fwd_epilogue_tile<false>(tacc, i, j0, n, inv_t, c1, yi, row_ok && yi != bg, ycol[acc], zrow, ld, s, pa);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (row_ok) {
+        float* out = partial + ((size_t)bx * n_rows + (i - row0)) * 3;
+        out[0] = inv_t;          // the common shift
+        out[1] = s;
+        out[2] = pa * inv_t;
       }
     }
-  }
-  if (row_ok) {
-    float* out = partial + ((size_t)blockIdx.x * n_rows + (i - row0)) * 3;
-    out[0] = m;
-    out[1] = s;
-    out[2] = ps;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kFwdTmemCols));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -322,9 +386,6 @@ __device__ __forceinline__ void umma_tf32_n256(uint32_t tmem_d, uint64_t a, uint
       "}" ::"r"(tmem_d), "l"(a), "l"(b), "r"(kIdescB), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(kBThreads, 1)
 sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_thi,
@@ -337,9 +398,10 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[kBStages], ready_bar[kBStages], empty_bar[kBStages], accum_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_cj[kBStages][kKC], s_uj[kBStages][kKC];
-  __shared__ long long s_yj[kBStages][kKC];
-  __shared__ int s_pj[kBStages][kKC];
+  // column metadata of the chunk in each stage, written by the producer warp ahead of the TMA loads
+  __shared__ __align__(16) float s_cj[kBStages][kKC], s_uj[kBStages][kKC];
+  __shared__ __align__(16) long long s_yj[kBStages][kKC];
+  __shared__ __align__(16) int s_pj[kBStages][kKC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int il0 = blockIdx.y * kM;   // local row of the tile (z / dpart index); global row = row0 + local
@@ -352,7 +414,7 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
   if (tid == 0) {
     for (int s = 0; s < kBStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 256);
+      mbar_init(&ready_bar[s], 8);    // one arrival per transform warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
@@ -369,10 +431,23 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 8) {
-    if (lane == 0) {  // ---- TMA producer
-      for (int k = 0; k < nk; ++k) {
-        const int s = k % kBStages, kc = kc0 + k;
-        if (k >= kBStages) mbar_wait(&empty_bar[s], ((k / kBStages) - 1) & 1);
+    // ---- producer warp: every lane fetches one column's metadata (off the transform warps' critical path: this
+    // warp runs kBStages chunks ahead), then lane 0 issues the TMA loads.  The stage's previous readers are done:
+    // empty_bar fires after the MMAs that followed their ready_bar arrivals.
+    for (int k = 0; k < nk; ++k) {
+      const int s = k % kBStages, kc = kc0 + k;
+      const int j = kc * kKC + lane;
+      const bool ok = j < n;
+      const RowStats sj = ok ? stats[j] : RowStats{0.f, 0.f, 0.f, 0.f};
+      const long long yj = ok ? labels[j] : (long long)-0x7fffffffffffffffLL;
+      const int pj = ok ? pair[j] : -1;
+      if (k >= kBStages) mbar_wait(&empty_bar[s], ((k / kBStages) - 1) & 1);
+      s_cj[s][lane] = sj.coef;
+      s_uj[s][lane] = sj.u;
+      s_yj[s][lane] = yj;
+      s_pj[s][lane] = pj;
+      __syncwarp();
+      if (lane == 0) {
         uint8_t* st = smem + s * kBStageBytes;
         mbar_expect_tx(&full_bar[s], kOperandBytes + 2 * kBN * kKC * 4);
         tma_load_2d(st, &tm_z, &full_bar[s], kc * kKC, il0);
@@ -408,22 +483,12 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
     const long long bg = (long long)meta[0];
     const long long yi = row_ok ? labels[i] : 0;
     const int pi = row_ok ? pair[i] : -1;
-    RowStats si = row_ok ? stats[i] : RowStats{0.f, 0.f, 0.f, 0.f};
+    const RowStats si = row_ok ? stats[i] : RowStats{0.f, 0.f, 0.f, 0.f};
+    const bool fg_i = yi != bg;
+    constexpr float kLog2e = 1.4426950408889634f;
     for (int k = 0; k < nk; ++k) {
       const int s = k % kBStages, kc = kc0 + k;
-      // column metadata of this chunk (the stage's previous user finished: its MMAs were committed before the
-      // producer refilled the stage, and every transform thread passed ready_bar for it)
-      if (tid < kKC) {
-        const int j = kc * kKC + tid;
-        const bool ok = j < n;
-        RowStats sj = ok ? stats[j] : RowStats{0.f, 0.f, 0.f, 0.f};
-        s_cj[s][tid] = sj.coef;
-        s_uj[s][tid] = sj.u;
-        s_yj[s][tid] = ok ? labels[j] : (long long)-0x7fffffffffffffffLL;
-        s_pj[s][tid] = ok ? pair[j] : -1;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 transform warps only
-      mbar_wait(&full_bar[s], (k / kBStages) & 1);
+      mbar_wait(&full_bar[s], (k / kBStages) & 1);   // TMA bytes landed; the metadata was stored before the arrive
       uint8_t* st = smem + s * kBStageBytes;
       float4* zrow = reinterpret_cast<float4*>(st + row * 128);
       float4* lrow = reinterpret_cast<float4*>(st + kOperandBytes + row * 128);
@@ -431,21 +496,27 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
       for (int c4 = 0; c4 < 4; ++c4) {
         const int c = half * 4 + c4;              // logical 16-byte chunk: columns 4c .. 4c+3
         const int pc = c ^ (row & 7);             // 128-byte swizzle
-        float4 zv = zrow[pc];
-        float z[4] = {zv.x, zv.y, zv.z, zv.w}, hi[4], lo[4];
+        const float4 zv = zrow[pc];
+        const float4 cj4 = *reinterpret_cast<const float4*>(&s_cj[s][c * 4]);
+        const float4 uj4 = *reinterpret_cast<const float4*>(&s_uj[s][c * 4]);
+        const int4 pj4 = *reinterpret_cast<const int4*>(&s_pj[s][c * 4]);
+        const longlong2 ya = *reinterpret_cast<const longlong2*>(&s_yj[s][c * 4]);
+        const longlong2 yb = *reinterpret_cast<const longlong2*>(&s_yj[s][c * 4 + 2]);
+        const float z[4] = {zv.x, zv.y, zv.z, zv.w}, cj[4] = {cj4.x, cj4.y, cj4.z, cj4.w};
+        const float uj[4] = {uj4.x, uj4.y, uj4.z, uj4.w};
+        const int pj[4] = {pj4.x, pj4.y, pj4.z, pj4.w};
+        const long long yj[4] = {ya.x, ya.y, yb.x, yb.y};
+        float hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int jj = c * 4 + e, j = kc * kKC + jj;
-          float a = 0.f;
-          if (row_ok && j < n && j != i) {
-            const long long yj = s_yj[s][jj];
-            float pterm = 0.f;
-            if (yi == yj) {
-              if (yi != bg) pterm = si.coef + s_cj[s][jj];
-              else pterm = (j == pi ? si.coef : 0.f) + (s_pj[s][jj] == i ? s_cj[s][jj] : 0.f);
-            }
-            a = (pterm - expf(z[e]) * (si.u + s_uj[s][jj])) * inv_t;
-          }
+          const int j = kc * kKC + c * 4 + e;
+          // positives: same label; background rows only with their other view (either direction of the pair).
+          // Columns past n carry zero statistics and multiply zero rows of the B operand.
+          const float pi_part = (fg_i || j == pi) ? si.coef : 0.f;
+          const float pj_part = (fg_i || pj[e] == i) ? cj[e] : 0.f;
+          const float pterm = (yi == yj[e]) ? pi_part + pj_part : 0.f;
+          float a = fmaf(-ex2_approx(z[e] * kLog2e), si.u + uj[e], pterm) * inv_t;
+          if (j == i) a = 0.f;
           uint32_t hb, lb;
           asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
           const float rem = __fsub_rn(a, __uint_as_float(hb));
@@ -457,7 +528,8 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
         lrow[pc] = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
-      mbar_arrive(&ready_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready_bar[s]);
     }
     // ---- epilogue: warps 0-3 own columns 0..127, warps 4-7 columns 128..255 of TMEM lane quadrant warp % 4
     mbar_wait(&accum_bar, 0);
@@ -503,8 +575,15 @@ int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pai
     OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     attr = true;
   }
-  sim_fwd_tc_kernel<<<dim3((n + kN - 1) / kN, (n_rows + kM - 1) / kM), 128, kSmemBytes, stream>>>(
-      mh, ml, labels, pair, w.meta, n, row0, n_rows, inv_t, w.partial, w.z, w.ld);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    OADG_CUDA_TRY(cudaGetDevice(&dev));
+    OADG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int col_tiles = (n + kN - 1) / kN, n_tiles = col_tiles * ((n_rows + kM - 1) / kM);
+  sim_fwd_tc_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, kFwdThreads, kSmemBytes, stream>>>(
+      mh, ml, labels, w.meta, n, row0, n_rows, inv_t, col_tiles, n_tiles, w.partial, w.z, w.ld);
   OADG_LAUNCH_CHECK();
   if (launches) *launches += 2;
   return 0;

@@ -166,6 +166,7 @@ class OAMix:
         self._sal_slot = 0
         self._native_cfg = None
         self._host_state = dict(dev={}, pin={})
+        self._streams = {}
         self.last_launches = 0
 
     def __repr__(self):
@@ -487,8 +488,7 @@ class OAMix:
             st = self._sal_state.get(slot)
             if st is None or st['cap'] < nbytes or st['dev'] != dev:
                 cap = max(4096, 2 * nbytes)
-                shared = next(iter(self._sal_state.values()), None)
-                side = shared['stream'] if shared and shared['dev'] == dev else torch.cuda.Stream(dev)
+                side = self._side_stream(dev)
                 with torch.cuda.stream(side):   # device buffers owned by the stream that uses them (allocator pools
                     devbuf = torch.empty(cap, dtype=torch.uint8, device=dev)          # are per stream: no block that a
                     scores = torch.empty(cap // 8, dtype=torch.float64, device=dev)   # main-stream kernel still reads)
@@ -510,6 +510,14 @@ class OAMix:
                 st['event'].record(s)
             self.last_launches += 1
         return dict(out=out, slots=slots, st=st, n=len(rows))
+
+    def _side_stream(self, dev):
+        """The private stream of the saliency kernels (and of iter_batches' uploads), one per device."""
+        torch = _lib.require_cuda()
+        side = self._streams.get(('side', str(dev)))
+        if side is None:
+            side = self._streams[('side', str(dev))] = torch.cuda.Stream(dev)
+        return side
 
     def _saliency_collect(self, handle):
         out, st = handle['out'], handle['st']
@@ -675,6 +683,9 @@ class OAMix:
         scores = self.saliency_scores(dimgs, gts)
         plan = self.sample_plan([h.shape[:2] for _, h in staged], gts, scores)
         outs = self._to_host(self.execute(plan.blob, dimgs))
+        return self._fill_results(results_list, outs, plan)
+
+    def _fill_results(self, results_list, outs, plan):
         for r, out, oa, ml in zip(results_list, outs, plan.oa_boxes, plan.ml_boxes):
             r['custom_field'] = []
             r['img_fields'] = ['img', 'img2']
@@ -685,6 +696,92 @@ class OAMix:
             r['multilevel_boxes'] = ml
             r['custom_field'] += ['multilevel_boxes']
         return results_list
+
+    def iter_batches(self, batches):
+        """``call_batch`` for a loader loop, pipelined: yields ``call_batch(b)`` for every ``b`` of ``batches`` (lists
+        of sample dicts), in order and with the same values, while the NEXT batch's kernel chain and the one after
+        that's upload + saliency scores are already in flight, so host<->device copies, the score read-back and the
+        host sampling overlap the kernels instead of adding to them.
+
+        Differences from calling ``call_batch`` in a loop: ``batches`` is read two items ahead, and the np.random
+        draws of batch k + 1 are taken before batch k is yielded (the global stream is consumed in the same order, so
+        results match as long as the consumer draws nothing from np.random in between).  A batch whose plan cannot be
+        sampled raises when it is its turn to be yielded.  Configurations other than num_views=2, keep_orig=True are
+        served by ``call_batch`` without pipelining."""
+        if not (self.num_views == 2 and self.keep_orig):
+            for b in batches:
+                yield self.call_batch(b)
+            return
+        import collections
+        torch = _lib.require_cuda()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        cout = self._streams.get(('out', str(dev)))
+        if cout is None:
+            cout = self._streams[('out', str(dev))] = torch.cuda.Stream(dev)
+        it = iter(batches)
+        staged, launched = collections.deque(), collections.deque()
+        count = [0]
+
+        def stage_in():
+            try:
+                results_list = next(it)
+            except StopIteration:
+                return
+            idx = count[0]
+            count[0] += 1
+            gts = [np.asarray(r['gt_bboxes'], dtype=np.float32).reshape(-1, 4) for r in results_list]
+            with torch.cuda.stream(side):   # upload, then the saliency kernel behind it on the same stream
+                ins = [self._to_device(r['img'], (idx % 3, i)) for i, r in enumerate(results_list)]
+                ready = torch.cuda.Event()
+                ready.record(side)
+            job = dict(results=results_list, gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins],
+                       ready=ready, idx=idx, error=None)
+            try:
+                job['sal'] = self._saliency_launch(job['dimgs'], gts, None, True, slot=4 + idx % 3)
+            except Exception as e:   # surfaces when the batch is yielded
+                job['error'] = e
+            staged.append(job)
+
+        def launch(job):
+            if job['error'] is None:
+                try:
+                    scores = self._saliency_collect(job['sal'])
+                    plan = job['plan'] = self.sample_plan(job['hw'], job['gts'], scores)
+                    key = ('outs', job['idx'] % 2, tuple(tuple(d.shape) for d in job['dimgs']))
+                    douts = self._host_state['dev'].get(key)
+                    if douts is None:
+                        douts = self._host_state['dev'][key] = [torch.empty_like(d) for d in job['dimgs']]
+                    main.wait_event(job['ready'])
+                    self.execute(plan.blob, job['dimgs'], outs=douts, stream=main)
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    host = [torch.empty(o.shape, dtype=torch.uint8, pin_memory=True) for o in douts]
+                    with torch.cuda.stream(cout):
+                        cout.wait_event(done)
+                        for h_, o in zip(host, douts):
+                            h_.copy_(o, non_blocking=True)
+                        job['out_ready'] = torch.cuda.Event()
+                        job['out_ready'].record(cout)
+                    job['host'] = host
+                except Exception as e:
+                    job['error'] = e
+            launched.append(job)
+
+        stage_in()
+        stage_in()
+        if staged:
+            launch(staged.popleft())
+        while launched:
+            stage_in()                         # batch k + 2: upload + saliency
+            if staged:
+                launch(staged.popleft())       # batch k + 1: sampling + kernel chain + download
+            job = launched.popleft()           # batch k
+            if job['error'] is not None:
+                raise job['error']
+            job['out_ready'].synchronize()
+            yield self._fill_results(job['results'], [h_.numpy() for h_ in job['host']], job['plan'])
 
     def __call__(self, results, *args, **kwargs):
         """oa_mix.py:187-204."""

@@ -245,3 +245,39 @@ def test_prefetched_saliency_gives_the_same_views(cuda):
     for a, b in zip(plain, got):
         for x, y in zip(a, b):
             assert torch.equal(x, y)
+
+
+def test_iter_batches_equals_call_batch(cuda):
+    """The pipelined loader loop (upload / saliency two batches ahead, kernel chain one ahead) yields exactly what
+    call_batch returns for each batch in turn and leaves np.random in the same state; 7 batches exercise every
+    staging slot twice, mixed frame sizes the per-shape buffers."""
+    from oadg_b200 import OAMix
+    t = OAMix(**dict(OAMIX_CFG, version='augmix'))
+    sizes = [(200, 333), (200, 333), (160, 288), (200, 333), (160, 288), (160, 288), (200, 333)]
+
+    def make():
+        return [[dict(img=img.copy(), gt_bboxes=gt.copy())
+                 for img, gt in (synth.make_image(100 + 2 * k + j, h, w, 4) for j in range(2))]
+                for k, (h, w) in enumerate(sizes)]
+    np.random.seed(91)
+    want = [t.call_batch(b) for b in make()]
+    st_want = np.random.get_state()
+    np.random.seed(91)
+    got = []
+    for res in t.iter_batches(iter(make())):
+        got.append([{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()} for r in res])
+    st_got = np.random.get_state()
+    assert len(got) == len(want)
+    assert st_want[2] == st_got[2] and np.array_equal(st_want[1], st_got[1])
+    for wb, gb in zip(want, got):
+        for a, b in zip(wb, gb):
+            assert a['custom_field'] == b['custom_field'] and a['img_fields'] == b['img_fields']
+            for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
+                assert np.array_equal(a[k], b[k]), k
+    # an empty loader and a single batch
+    assert list(t.iter_batches([])) == []
+    np.random.seed(3)
+    one = t.call_batch(make()[0])
+    np.random.seed(3)
+    (again,) = list(t.iter_batches([make()[0]]))
+    assert np.array_equal(one[0]['img2'], again[0]['img2']) and np.array_equal(one[1]['img2'], again[1]['img2'])
