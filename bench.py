@@ -318,12 +318,22 @@ def product_arm(args):
 
     def e2e_steps(n):
         # the loader loop a user writes: host numpy in, host numpy out, every step's loss read back
+        marks = [time.perf_counter()]
+        mix.pipe_profile = {}
         for results in mix.iter_batches(host_batches(n)):
             views = [res['img2'] for res in results]
             xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
             loss = run_loss(xd)
             loss.backward()
             last = float(loss.item()), views
+            marks.append(time.perf_counter())
+        dt = np.diff(np.array(marks)) * 1e3
+        log('e2e step wall ms: median %.3f  p90 %.3f  max %.3f  (first %.3f)' % (
+            np.median(dt), np.percentile(dt, 90), dt.max(), dt[0]))
+        log('e2e pipeline host phases, avg / max us: ' + ', '.join(
+            '%s %.0f/%.0f' % (k, v / n * 1e6, mix.pipe_profile[k + '.max'] * 1e6)
+            for k, v in mix.pipe_profile.items() if not k.endswith('.max')))
+        mix.pipe_profile = None
         return last
 
     def log(msg):

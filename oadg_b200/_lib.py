@@ -70,8 +70,26 @@ def check(code):
         raise OADGError('libOADG error %d: %s' % (code, msg.decode() if msg else '?'))
 
 
+_torch_cuda = None
+
+
 def require_cuda():
+    """torch, after checking once that a CUDA device is there (the answer does not change within a process)."""
+    global _torch_cuda
+    if _torch_cuda is None:
+        import torch
+        if not torch.cuda.is_available():
+            raise OADGError('oadg_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback')
+        _torch_cuda = torch
+    return _torch_cuda
+
+
+def raw_stream(device):
+    """cudaStream_t (int) of torch's current stream on ``device``: the C accessor when this torch has it (a few
+    hundred ns instead of building a torch.cuda.Stream object), torch.cuda.current_stream otherwise."""
     import torch
-    if not torch.cuda.is_available():
-        raise OADGError('oadg_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback')
-    return torch
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    try:
+        return torch._C._cuda_getCurrentRawStream(idx)
+    except AttributeError:
+        return torch.cuda.current_stream(device).cuda_stream

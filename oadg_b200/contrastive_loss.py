@@ -64,7 +64,7 @@ class _SupConFn(torch.autograd.Function):
         base = (ws.data_ptr() + 255) // 256 * 256
         loss = torch.empty((), dtype=torch.float32, device=feats.device)
         nl = ctypes.c_int(0)
-        s = torch.cuda.current_stream(feats.device).cuda_stream
+        s = _lib.raw_stream(feats.device)
         _lib.check(lib.oadg_supcon_forward(feats.data_ptr(), labels.data_ptr(), pair.data_ptr(), n, c,
                                            float(temperature), float(loss_weight), int(min_samples),
                                            int(bool(normalized_input)), loss.data_ptr(), base, need.value,
@@ -84,7 +84,7 @@ class _SupConFn(torch.autograd.Function):
         g = grad_out.to(torch.float32).contiguous()
         gx = torch.empty_like(feats)
         nl = ctypes.c_int(0)
-        s = torch.cuda.current_stream(feats.device).cuda_stream
+        s = _lib.raw_stream(feats.device)
         _lib.check(lib.oadg_supcon_backward(feats.data_ptr(), labels.data_ptr(), pair.data_ptr(), n, c,
                                             temperature, loss_weight, normalized_input, g.data_ptr(),
                                             gx.data_ptr(), base, need, ctypes.byref(nl), s))
@@ -102,7 +102,9 @@ def supcontrast(logits_clean, labels=None, num_views=2, lambda_weight=0.1, tempe
     if not logits_clean.is_cuda:
         raise _lib.OADGError('supcontrast: features must live on a CUDA device (no CPU fallback)')
     n = logits_clean.shape[0]
-    labels = labels.contiguous().view(-1).to(device=logits_clean.device, dtype=torch.int64)
+    labels = labels.reshape(-1)
+    if labels.dtype != torch.int64 or labels.device != logits_clean.device:
+        labels = labels.to(device=logits_clean.device, dtype=torch.int64)
     if pair is None:
         pair = _pair_tensor(n, logits_clean.device)
     feats = logits_clean if logits_clean.dtype == torch.float32 else logits_clean.float()
@@ -137,7 +139,7 @@ class ContrastiveLossPlus(nn.Module):
             return torch.zeros(1)  # contrastive_loss_plus.py:38-39 (CPU tensor, shape [1])
         if len(cont_feats) != len(labels):  # random proposal case, contrastive_loss_plus.py:44-47
             random_proposal_len = len(cont_feats) - len(labels)
-            random_proposal_targets = labels[-1, :].repeat(random_proposal_len, 1)
+            random_proposal_targets = labels[-1:, :].expand(random_proposal_len, -1)   # a view: one kernel (the cat)
             labels = torch.cat([labels, random_proposal_targets], dim=0)
         # the two F.normalize calls (contrastive_loss_plus.py:41, contrastive_loss.py:155) are fused
         # into the kernel; loss_weight is applied inside it as well

@@ -29,7 +29,6 @@ constexpr int kM = 128, kN = 128, kKC = 32, kStages = 3;
 constexpr int kOperandBytes = kM * kKC * 4;          // 16 KB: 128 rows x 128 B
 constexpr int kStageBytes = 4 * kOperandBytes;       // A-hi, A-lo, B-hi, B-lo
 constexpr int kSmemBytes = kStages * kStageBytes + 1024;
-constexpr int kTmemCols = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -345,7 +344,25 @@ inline EncodeTiledFn encode_fn() {
 inline int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld_elems, int box_rows) {
   // the driver entry point needs a current context on the calling thread (torch's autograd thread has
   // only used the runtime API so far): cudaFree(0) binds the primary context
-  cudaFree(0);
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(0);
+    bound = true;
+  }
+  // the same few (pointer, shape) combinations come back every step: the workspace is a cached block
+  struct Cached {
+    const float* base;
+    int rows, cols, ld, box_rows;
+    CUtensorMap map;
+  };
+  static thread_local Cached cache[8];
+  static thread_local int n_cached = 0, victim = 0;
+  for (int k = 0; k < n_cached; ++k)
+    if (cache[k].base == base && cache[k].rows == rows && cache[k].cols == cols && cache[k].ld == ld_elems &&
+        cache[k].box_rows == box_rows) {
+      *map = cache[k].map;
+      return 0;
+    }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -358,7 +375,15 @@ inline int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
   if (r != CUDA_SUCCESS && getenv("OADG_DEBUG"))
     fprintf(stderr, "[oadg] cuTensorMapEncodeTiled failed: %d (base %p rows %d cols %d ld %d box_rows %d)\n", (int)r,
             (const void*)base, rows, cols, ld_elems, box_rows);
-  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+  if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  Cached& c = cache[n_cached < 8 ? n_cached++ : (victim = (victim + 1) & 7)];
+  c.base = base;
+  c.rows = rows;
+  c.cols = cols;
+  c.ld = ld_elems;
+  c.box_rows = box_rows;
+  c.map = *map;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1238,11 +1238,12 @@ struct CudaBackend {
   std::vector<int32_t> deps_host;
 
   int grid() {
-    if (n_sm == 0) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-      if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    }
+    // per device, queried once per process (one process drives one GPU; the table covers the multi-device case)
+    static int grid_of_device[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64 && grid_of_device[dev] > 0) return grid_of_device[dev];
+    if (n_sm == 0 && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     if (ctas_per_sm == 0) {
       int nb = 0;
       if (cudaFuncSetAttribute(oamix_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
@@ -1250,10 +1251,42 @@ struct CudaBackend {
       ctas_per_sm = nb < 1 ? 0 : (nb > kCtaPerSm ? kCtaPerSm : nb);
       if (ctas_per_sm == 0) return -1;
     }
+    if (dev >= 0 && dev < 64) grid_of_device[dev] = n_sm * ctas_per_sm;
     return n_sm * ctas_per_sm;
   }
+  // Plan + launch tables go up through a small ring of page-locked buffers (per calling thread): a copy from
+  // pageable memory may make the host wait for the stream's earlier kernels, which would serialise the loader
+  // loop with the GPU.  A slot is reused once the copy that read it has finished (event).
+  struct PinSlot {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+    int dev = -1;
+  };
   int upload(void* dst, const void* src, size_t bytes) {
-    BE_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    static thread_local PinSlot ring[4];
+    static thread_local int next = 0;
+    PinSlot& sl = ring[next];
+    next = (next + 1) & 3;
+    int dev = 0;
+    BE_TRY(cudaGetDevice(&dev));
+    if (sl.ev && sl.dev != dev) {
+      cudaEventDestroy(sl.ev);
+      sl.ev = nullptr;
+    }
+    if (sl.ev) BE_TRY(cudaEventSynchronize(sl.ev));
+    else BE_TRY(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    sl.dev = dev;
+    if (sl.cap < bytes) {
+      if (sl.p) cudaFreeHost(sl.p);
+      sl.p = nullptr;
+      sl.cap = 0;
+      BE_TRY(cudaHostAlloc(&sl.p, 2 * bytes, cudaHostAllocPortable));
+      sl.cap = 2 * bytes;
+    }
+    memcpy(sl.p, src, bytes);
+    BE_TRY(cudaMemcpyAsync(dst, sl.p, bytes, cudaMemcpyHostToDevice, stream));
+    BE_TRY(cudaEventRecord(sl.ev, stream));
     return 0;
   }
   int zero(void* dst, size_t bytes) {

@@ -67,7 +67,7 @@ class CudaBackend:
         lib = _lib.load()
         self.ws = self._ws(n_total, x.shape[1], x.device)
         fhat = torch.empty_like(x)
-        s = torch.cuda.current_stream(x.device).cuda_stream
+        s = _lib.raw_stream(x.device)
         _lib.check(lib.oadg_supcon_normalize(x.data_ptr(), x.shape[0], n_total, x.shape[1], int(normalized_input),
                                              fhat.data_ptr(), self.ws[1], self.ws[2], s))
         self.launches += 1
@@ -78,7 +78,7 @@ class CudaBackend:
         loss = torch.empty((), dtype=torch.float32, device=f_all.device)
         stats = torch.empty(n_rows, 4, dtype=torch.float32, device=f_all.device)
         nl = ctypes.c_int(0)
-        s = torch.cuda.current_stream(f_all.device).cuda_stream
+        s = _lib.raw_stream(f_all.device)
         _lib.check(lib.oadg_supcon_forward_gathered(f_all.data_ptr(), labels_all.data_ptr(), pair_all.data_ptr(),
                                                     f_all.shape[0], row0, n_rows, f_all.shape[1], float(temperature),
                                                     float(loss_weight), int(min_samples), loss.data_ptr(),
@@ -90,7 +90,7 @@ class CudaBackend:
         lib = _lib.load()
         gx = torch.empty_like(x)
         nl = ctypes.c_int(0)
-        s = torch.cuda.current_stream(x.device).cuda_stream
+        s = _lib.raw_stream(x.device)
         _lib.check(lib.oadg_supcon_backward_gathered(x.data_ptr(), labels_all.data_ptr(), pair_all.data_ptr(),
                                                      stats_all.data_ptr(), f_all.shape[0], row0, x.shape[0], x.shape[1],
                                                      float(temperature), int(normalized_input), grad.data_ptr(),
@@ -183,7 +183,7 @@ def gathered_contrastive_loss(cont_feats, labels, temperature=0.07, loss_weight=
     labels = labels.view(-1)
     n = cont_feats.shape[0]
     if labels.shape[0] != n:
-        labels = torch.cat([labels, labels[-1:].repeat(n - labels.shape[0])])
+        labels = torch.cat([labels, labels[-1:].expand(n - labels.shape[0])])
     if pair_local is None:
         pair_local = reference_pair_map(n)
     backend = backend or CudaBackend()

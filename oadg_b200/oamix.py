@@ -167,6 +167,7 @@ class OAMix:
         self._native_cfg = None
         self._host_state = dict(dev={}, pin={})
         self._streams = {}
+        self.pipe_profile = None
         self.last_launches = 0
 
     def __repr__(self):
@@ -549,7 +550,8 @@ class OAMix:
             if self._ws_cache is not None:
                 torch.cuda.synchronize(self._ws_cache.device)
             self._ws_cache = None
-            self._ws_cache = torch.empty(int(nbytes * 1.5) + 4096, dtype=torch.uint8, device=device)
+            # plans differ in size from batch to batch: double, so that the drain above stops after a few batches
+            self._ws_cache = torch.empty(int(nbytes * 2) + 4096, dtype=torch.uint8, device=device)
         return self._ws_cache
 
     def execute(self, jobs, imgs, outs=None, stream=None, profile=None):
@@ -572,7 +574,7 @@ class OAMix:
             outs = [torch.empty_like(imgs[j[2]]) for j in jobs]
         src = (ctypes.c_void_p * len(imgs))(*[int(t.data_ptr()) for t in imgs])
         dst = (ctypes.c_void_p * len(outs))(*[int(t.data_ptr()) for t in outs])
-        s = torch.cuda.current_stream(dev) if stream is None else stream
+        s_raw = _lib.raw_stream(dev) if stream is None else stream.cuda_stream
         base = (ws.data_ptr() + 255) // 256 * 256
         room = ws.numel() - (base - ws.data_ptr())
         if profile is not None:
@@ -581,7 +583,7 @@ class OAMix:
             kstats = np.zeros(48, np.uint64)
             _lib.check(lib.oadg_oamix_execute_profiled(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
                                                        ctypes.byref(ms_chain), ctypes.byref(ms_mix), ctypes.byref(n_items),
-                                                       ctypes.byref(n_tiles), kstats.ctypes.data, s.cuda_stream))
+                                                       ctypes.byref(n_tiles), kstats.ctypes.data, s_raw))
             profile['chain_ms'] = profile.get('chain_ms', 0.0) + float(ms_chain.value)
             profile['mix_ms'] = profile.get('mix_ms', 0.0) + float(ms_mix.value)
             profile['chain_n'] = profile.get('chain_n', 0) + 1
@@ -598,7 +600,7 @@ class OAMix:
             return outs
         n = ctypes.c_int(0)
         _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
-                                          ctypes.byref(n), s.cuda_stream))
+                                          ctypes.byref(n), s_raw))
         self.last_launches += n.value
         return outs
 
@@ -650,14 +652,29 @@ class OAMix:
         dev.copy_(src, non_blocking=True)
         return dev, img
 
-    def _to_host(self, outs):
-        """CUDA views -> numpy arrays backed by freshly allocated page-locked memory (one sync for all of them)."""
+    def _pinned_out(self, shape):
+        """(page-locked uint8 tensor, numpy array over it) for one generated view.  Pinning memory costs
+        milliseconds, so the buffers are recycled: when the caller drops the array (and every view of it), a
+        finalizer puts the tensor back on the free list."""
+        import weakref
         torch = _lib.require_cuda()
-        host = [torch.empty(o.shape, dtype=torch.uint8, pin_memory=True) for o in outs]
-        for h_, o in zip(host, outs):
+        free = self._host_state.setdefault('out_free', {}).setdefault(tuple(shape), [])
+        try:
+            t = free.pop()
+        except IndexError:
+            t = torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=True)
+        a = t.numpy()
+        weakref.finalize(a, free.append, t)
+        return t, a
+
+    def _to_host(self, outs):
+        """CUDA views -> numpy arrays backed by page-locked memory (one sync for all of them)."""
+        torch = _lib.require_cuda()
+        host = [self._pinned_out(o.shape) for o in outs]
+        for (h_, _), o in zip(host, outs):
             h_.copy_(o, non_blocking=True)
         torch.cuda.current_stream(outs[0].device).synchronize()
-        return [h_.numpy() for h_ in host]
+        return [a for _, a in host]
 
     def oamix(self, img, gt_bboxes):
         """One view of one host image (reference oa_mix.py:207-243): H2D, kernels, D2H."""
@@ -697,25 +714,75 @@ class OAMix:
             r['custom_field'] += ['multilevel_boxes']
         return results_list
 
-    def iter_batches(self, batches):
+    def iter_batches(self, batches, threaded=True):
         """``call_batch`` for a loader loop, pipelined: yields ``call_batch(b)`` for every ``b`` of ``batches`` (lists
         of sample dicts), in order and with the same values, while the NEXT batch's kernel chain and the one after
         that's upload + saliency scores are already in flight, so host<->device copies, the score read-back and the
-        host sampling overlap the kernels instead of adding to them.
+        host sampling overlap the kernels instead of adding to them.  The pipeline has its own CUDA streams (like a
+        loader worker): what the caller enqueues on its stream between batches neither waits for nor delays it.
+        With ``threaded`` (default) the pipeline's host side runs in a worker thread, so its plan sampling and
+        scheduling (native code, GIL released) overlap the caller's own host work.
 
-        Differences from calling ``call_batch`` in a loop: ``batches`` is read two items ahead, and the np.random
-        draws of batch k + 1 are taken before batch k is yielded (the global stream is consumed in the same order, so
-        results match as long as the consumer draws nothing from np.random in between).  A batch whose plan cannot be
-        sampled raises when it is its turn to be yielded.  Configurations other than num_views=2, keep_orig=True are
-        served by ``call_batch`` without pipelining."""
+        Differences from calling ``call_batch`` in a loop: ``batches`` is read a few items ahead (the caller must
+        leave a batch's input arrays alone until it is yielded), and the np.random draws of later batches are taken
+        before earlier ones are yielded: the global stream is consumed in the same order, so results match as long
+        as the consumer draws nothing from np.random (and does not use this transform) while iterating.  A batch
+        whose plan cannot be sampled raises when it is its turn to be yielded.  Configurations other than
+        num_views=2, keep_orig=True are served by ``call_batch`` without pipelining."""
         if not (self.num_views == 2 and self.keep_orig):
             for b in batches:
                 yield self.call_batch(b)
             return
-        import collections
         torch = _lib.require_cuda()
         dev = torch.device('cuda', torch.cuda.current_device())
-        main = torch.cuda.current_stream(dev)
+        pipe = self._streams.get(('pipe', str(dev)))
+        if pipe is None:
+            pipe = self._streams[('pipe', str(dev))] = torch.cuda.Stream(dev)
+        if not threaded:
+            yield from self._pipeline(batches, dev, pipe)
+            return
+        import queue
+        import threading
+        q, stop = queue.Queue(maxsize=1), threading.Event()
+
+        def put(item):
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.05)
+                    return True
+                except queue.Full:
+                    pass
+            return False
+
+        def work():
+            try:
+                torch.cuda.set_device(dev)
+                for res in self._pipeline(batches, dev, pipe):
+                    if not put(('ok', res)):
+                        return
+                put(('end', None))
+            except BaseException as e:   # delivered to the consumer in order
+                put(('err', e))
+
+        th = threading.Thread(target=work, name='oamix-pipeline', daemon=True)
+        th.start()
+        try:
+            while True:
+                kind, val = q.get()
+                if kind == 'ok':
+                    yield val
+                elif kind == 'err':
+                    raise val
+                else:
+                    return
+        finally:
+            stop.set()
+            th.join(timeout=10)
+
+    def _pipeline(self, batches, dev, main):
+        """iter_batches' generator: `main` is the stream of the kernel chains."""
+        import collections
+        torch = _lib.require_cuda()
         side = self._side_stream(dev)
         cout = self._streams.get(('out', str(dev)))
         if cout is None:
@@ -723,6 +790,15 @@ class OAMix:
         it = iter(batches)
         staged, launched = collections.deque(), collections.deque()
         count = [0]
+        prof = self.pipe_profile          # optional dict: host seconds per phase (scripts/e2e_profile.py)
+        import time
+
+        def tick(name, t0):
+            if prof is not None:
+                dt = time.perf_counter() - t0
+                prof[name] = prof.get(name, 0.0) + dt
+                prof[name + '.max'] = max(prof.get(name + '.max', 0.0), dt)
+            return time.perf_counter()
 
         def stage_in():
             try:
@@ -731,40 +807,48 @@ class OAMix:
                 return
             idx = count[0]
             count[0] += 1
-            gts = [np.asarray(r['gt_bboxes'], dtype=np.float32).reshape(-1, 4) for r in results_list]
-            with torch.cuda.stream(side):   # upload, then the saliency kernel behind it on the same stream
-                ins = [self._to_device(r['img'], (idx % 3, i)) for i, r in enumerate(results_list)]
-                ready = torch.cuda.Event()
-                ready.record(side)
-            job = dict(results=results_list, gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins],
-                       ready=ready, idx=idx, error=None)
-            try:
+            t0 = time.perf_counter()
+            job = dict(results=results_list, idx=idx, error=None)
+            try:   # a failure surfaces when the batch is yielded, after the batches before it
+                gts = [np.asarray(r['gt_bboxes'], dtype=np.float32).reshape(-1, 4) for r in results_list]
+                with torch.cuda.stream(side):   # upload, then the saliency kernel behind it on the same stream
+                    ins = [self._to_device(r['img'], (idx % 3, i)) for i, r in enumerate(results_list)]
+                    ready = torch.cuda.Event()
+                    ready.record(side)
+                job.update(gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins], ready=ready)
+                t0 = tick('upload_enqueue', t0)
                 job['sal'] = self._saliency_launch(job['dimgs'], gts, None, True, slot=4 + idx % 3)
-            except Exception as e:   # surfaces when the batch is yielded
+                tick('saliency_enqueue', t0)
+            except Exception as e:
                 job['error'] = e
             staged.append(job)
 
         def launch(job):
             if job['error'] is None:
                 try:
+                    t0 = time.perf_counter()
                     scores = self._saliency_collect(job['sal'])
+                    t0 = tick('scores_wait', t0)
                     plan = job['plan'] = self.sample_plan(job['hw'], job['gts'], scores)
+                    t0 = tick('sample_plan', t0)
                     key = ('outs', job['idx'] % 2, tuple(tuple(d.shape) for d in job['dimgs']))
                     douts = self._host_state['dev'].get(key)
                     if douts is None:
                         douts = self._host_state['dev'][key] = [torch.empty_like(d) for d in job['dimgs']]
                     main.wait_event(job['ready'])
                     self.execute(plan.blob, job['dimgs'], outs=douts, stream=main)
+                    t0 = tick('execute_enqueue', t0)
                     done = torch.cuda.Event()
                     done.record(main)
-                    host = [torch.empty(o.shape, dtype=torch.uint8, pin_memory=True) for o in douts]
+                    host = [self._pinned_out(o.shape) for o in douts]
                     with torch.cuda.stream(cout):
                         cout.wait_event(done)
-                        for h_, o in zip(host, douts):
+                        for (h_, _), o in zip(host, douts):
                             h_.copy_(o, non_blocking=True)
                         job['out_ready'] = torch.cuda.Event()
                         job['out_ready'].record(cout)
                     job['host'] = host
+                    tick('download_enqueue', t0)
                 except Exception as e:
                     job['error'] = e
             launched.append(job)
@@ -780,8 +864,13 @@ class OAMix:
             job = launched.popleft()           # batch k
             if job['error'] is not None:
                 raise job['error']
+            t0 = time.perf_counter()
             job['out_ready'].synchronize()
-            yield self._fill_results(job['results'], [h_.numpy() for h_ in job['host']], job['plan'])
+            t0 = tick('views_wait', t0)
+            res = self._fill_results(job['results'], [a for _, a in job['host']], job['plan'])
+            t0 = tick('fill_results', t0)
+            yield res
+            tick('consumer', t0)
 
     def __call__(self, results, *args, **kwargs):
         """oa_mix.py:187-204."""

@@ -247,7 +247,8 @@ def test_prefetched_saliency_gives_the_same_views(cuda):
             assert torch.equal(x, y)
 
 
-def test_iter_batches_equals_call_batch(cuda):
+@pytest.mark.parametrize('threaded', [False, True])
+def test_iter_batches_equals_call_batch(cuda, threaded):
     """The pipelined loader loop (upload / saliency two batches ahead, kernel chain one ahead) yields exactly what
     call_batch returns for each batch in turn and leaves np.random in the same state; 7 batches exercise every
     staging slot twice, mixed frame sizes the per-shape buffers."""
@@ -264,7 +265,7 @@ def test_iter_batches_equals_call_batch(cuda):
     st_want = np.random.get_state()
     np.random.seed(91)
     got = []
-    for res in t.iter_batches(iter(make())):
+    for res in t.iter_batches(iter(make()), threaded=threaded):
         got.append([{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()} for r in res])
     st_got = np.random.get_state()
     assert len(got) == len(want)
@@ -275,9 +276,19 @@ def test_iter_batches_equals_call_batch(cuda):
             for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
                 assert np.array_equal(a[k], b[k]), k
     # an empty loader and a single batch
-    assert list(t.iter_batches([])) == []
+    assert list(t.iter_batches([], threaded=threaded)) == []
     np.random.seed(3)
     one = t.call_batch(make()[0])
     np.random.seed(3)
-    (again,) = list(t.iter_batches([make()[0]]))
+    (again,) = list(t.iter_batches([make()[0]], threaded=threaded))
     assert np.array_equal(one[0]['img2'], again[0]['img2']) and np.array_equal(one[1]['img2'], again[1]['img2'])
+    # a batch that cannot be processed raises when it is its turn, after the batches before it were delivered; the
+    # consumer may also stop early
+    bad = [dict(img=np.zeros((16, 16, 3), np.uint8))]          # no gt_bboxes key
+    it = t.iter_batches([make()[0], bad, make()[1]], threaded=threaded)
+    assert len(next(it)) == 2
+    with pytest.raises(KeyError):
+        next(it)
+    it = t.iter_batches(iter(make()), threaded=threaded)
+    next(it)
+    it.close()
