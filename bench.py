@@ -10,8 +10,10 @@ configs/OA-DG/cityscapes/faster_rcnn_r50_fpn_1x_cityscapes_oadg.py on synthetic 
   OA-Loss : ContrastiveLossPlus forward + backward on [2088, 256] two-view RoI embeddings
 images/sec = source images consumed per second (2 per step per GPU), whole job.
 
-value  : inputs resident in HBM, CUDA-event timed (includes the saliency D2H sync, host plan
-         sampling and the plan upload -- they are part of the path).
+value  : inputs resident in HBM, CUDA-event timed: OAMix.iter_batches over CUDA frames (device views out; includes
+         the saliency read-back, host plan sampling and the plan upload -- they are part of the path) with the loss
+         forward + backward of each step enqueued as its views arrive.  The loader loop keeps batch k + 1's chain
+         in flight while step k's loss runs, and consecutive chains are half-width launches sharing the SMs.
 e2e    : the registered plugins called with HOST buffers (pinned) in a loader loop: OAMix.iter_batches over the
          steps' sample dicts (numpy frames in, numpy views out; the pipelined form of OAMix.call_batch, same values)
          and ContrastiveLossPlus on a host tensor with loss.item() every step: H2D of frames / embeddings and D2H of
@@ -75,7 +77,9 @@ def workload_config(n_gpus):
             'imgs_per_gpu': BS, 'frame': [H, W, 3], 'gt_per_img': N_GT, 'rois': [N_ROI, C_ROI],
             'sharding': ('by image, %d rank(s); OA-Mix: no collective; OA-Loss: one all-gather of RoI embeddings'
                          % n_gpus) if n_gpus > 1 else 'single rank',
-            'l2': 'inputs larger than L2: %d distinct source frames (%.0f MB) cycled' % (POOL, POOL * H * W * 3 / 1e6)}
+            'l2': 'inputs larger than L2: %d distinct source frames (%.0f MB) cycled' % (POOL, POOL * H * W * 3 / 1e6),
+            'pipeline': 'OAMix.iter_batches: saliency two batches ahead, kernel chain one batch ahead of the step '
+                        'that consumes it; consecutive chains run as 2-CTA/SM launches on two streams'}
 
 
 # ------------------------------------------------------------------------------------------
@@ -311,6 +315,21 @@ def product_arm(args):
         loss.backward()
         return n_mix, loss
 
+    def dev_batches(n):
+        for i in range(n):
+            j = (i * BS) % POOL
+            yield [dict(img=dev_frames[(j + b) % POOL], gt_bboxes=gts[(j + b) % POOL]) for b in range(BS)]
+
+    def run_steps(n):
+        # the step loop with frames resident in HBM: the registered transform's loader loop (device views out), then
+        # the loss forward + backward of the step
+        loss = None
+        for _ in mix.iter_batches(dev_batches(n)):
+            x_dev.grad = None
+            loss = run_loss(x_dev)
+            loss.backward()
+        return loss
+
     def host_batches(n):
         for i in range(n):
             j = (i * BS) % POOL
@@ -343,8 +362,7 @@ def product_arm(args):
     log('inputs ready')
     # ---- warm-up
     np.random.seed(7 + rank)
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    run_steps(max(args.warmup, 3))
     barrier()
 
     log('warm-up done')
@@ -359,11 +377,10 @@ def product_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
-        n, _ = step(i)
-        launches += n
+    run_steps(args.steps)
     e1.record(stream)
     barrier()
+    launches += mix.pipe_launches
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     launches += loss_fn.stats['launches'] + (gbe.launches if gather else 0)

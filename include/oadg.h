@@ -194,6 +194,16 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
                        void* workspace_dev, size_t workspace_bytes,
                        int* launches_out, void* stream);
 
+/* Same as oadg_oamix_execute with the persistent chain kernel limited to ctas_per_sm resident CTAs per SM
+ * (0 = as many as fit, i.e. oadg_oamix_execute).  Two such launches on different streams, each with its own
+ * workspace, share the SMs: the tiles of one batch fill the dependency stalls of the other (the reference has no
+ * counterpart; its batches are independent DataLoader items, oa_mix.py:187-204). */
+int oadg_oamix_execute_shared(const void* plan_host, size_t plan_bytes,
+                              const uint8_t* const* src_dev, int n_img,
+                              uint8_t* const* dst_dev,
+                              void* workspace_dev, size_t workspace_bytes,
+                              int ctas_per_sm, int* launches_out, void* stream);
+
 /* Same as oadg_oamix_execute, with CUDA events on `stream` around the two launches (the chain kernel and the mix
  * kernel); the call synchronises the stream before returning (measurement only).  n_items_out / n_tiles_out: size
  * of the chain kernel's work queue.  kind_stats (optional, 48 x uint64): CTA-busy nanoseconds [16], tiles [16] and

@@ -20,6 +20,8 @@ SIGNATURES = {
     'oadg_saliency_scores': (_c.c_int, [_vp, _vp, _vp, _c.c_int, _vp, _vp]),
     'oadg_oamix_workspace_bytes': (_c.c_int, [_vp, _sz, _c.POINTER(_sz)]),
     'oadg_oamix_execute': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_oamix_execute_shared': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.c_int, _c.POINTER(_c.c_int),
+                                             _vp]),
     'oadg_oamix_execute_profiled': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_f32),
                                                _c.POINTER(_f32), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _vp, _vp]),
     'oadg_oamix_last_trace': (_c.c_int, [_vp, _c.c_int]),

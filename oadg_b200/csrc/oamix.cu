@@ -1237,22 +1237,34 @@ struct CudaBackend {
   std::vector<Item> items_host;
   std::vector<int32_t> deps_host;
 
+  int want_ctas = 0;   // oadg_oamix_execute_shared: resident CTAs per SM this launch may take (0 = all that fit)
   int grid() {
-    // per device, queried once per process (one process drives one GPU; the table covers the multi-device case)
-    static int grid_of_device[64] = {0};
+    // per device, queried once per process (one process drives one GPU; the tables cover the multi-device case)
+    static int sm_of_device[64] = {0}, ctas_of_device[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-    if (dev >= 0 && dev < 64 && grid_of_device[dev] > 0) return grid_of_device[dev];
-    if (n_sm == 0 && cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (ctas_per_sm == 0) {
+    const bool cacheable = dev >= 0 && dev < 64;
+    if (cacheable && ctas_of_device[dev] > 0) {
+      n_sm = sm_of_device[dev];
+      ctas_per_sm = ctas_of_device[dev];
+    } else {
+      if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
       int nb = 0;
       if (cudaFuncSetAttribute(oamix_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oamix_chain_kernel, kCT, kDynSmem) != cudaSuccess) return -1;
       ctas_per_sm = nb < 1 ? 0 : (nb > kCtaPerSm ? kCtaPerSm : nb);
+      if (const char* e = getenv("OADG_CTAS_PER_SM")) {   // experiments
+        const int want = atoi(e);
+        if (want >= 1 && want < ctas_per_sm) ctas_per_sm = want;
+      }
       if (ctas_per_sm == 0) return -1;
+      if (cacheable) {
+        sm_of_device[dev] = n_sm;
+        ctas_of_device[dev] = ctas_per_sm;
+      }
     }
-    if (dev >= 0 && dev < 64) grid_of_device[dev] = n_sm * ctas_per_sm;
-    return n_sm * ctas_per_sm;
+    const int c = (want_ctas >= 1 && want_ctas < ctas_per_sm) ? want_ctas : ctas_per_sm;
+    return n_sm * c;
   }
   // Plan + launch tables go up through a small ring of page-locked buffers (per calling thread): a copy from
   // pageable memory may make the host wait for the stream's earlier kernels, which would serialise the loader
@@ -1403,6 +1415,17 @@ extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_by
     if (ev) cudaEventDestroy(ev);
   if (rc) return rc;
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int oadg_oamix_execute_shared(const void* plan_host, size_t plan_bytes, const uint8_t* const* src_dev,
+                                         int n_img, uint8_t* const* dst_dev, void* workspace_dev,
+                                         size_t workspace_bytes, int ctas_per_sm, int* launches_out, void* stream) {
+  CudaBackend be;
+  be.stream = (cudaStream_t)stream;
+  be.want_ctas = ctas_per_sm;
+  int rc = execute_plan(be, plan_host, plan_bytes, src_dev, n_img, dst_dev, workspace_dev, workspace_bytes);
+  if (launches_out) *launches_out = be.launches;
+  return rc;
 }
 
 extern "C" int oadg_oamix_execute(const void* plan_host, size_t plan_bytes, const uint8_t* const* src_dev,

@@ -14,6 +14,7 @@ The one device->host dependency is the per-box saliency score, which gates the
 object-aware target list (oa_mix.py:249,295) and therefore later RNG draws.
 """
 import math
+import os
 import warnings
 
 import numpy as np
@@ -167,7 +168,15 @@ class OAMix:
         self._native_cfg = None
         self._host_state = dict(dev={}, pin={})
         self._streams = {}
+        self._ws_lanes = {}
         self.pipe_profile = None
+        self.pipe_launches = 0
+        # iter_batches: run consecutive batches as half-width launches on two streams, so that one batch's tiles
+        # fill the other's dependency stalls (measured: 736 -> 635 us per batch for chain + mix).  None = automatic:
+        # on for CUDA frames, off for host frames -- two resident chain launches leave no SM with room for another
+        # kernel's large shared-memory blocks, which starves a consumer that waits for its own kernels every step
+        # (bench e2e with loss.item() per step: 1915 images/s off, 1560 on; device frames: 2405 off, 2820 on).
+        self.overlap_batches = {'0': False, '1': True}.get(os.environ.get('OADG_OVERLAP', ''), None)
         self.last_launches = 0
 
     def __repr__(self):
@@ -541,8 +550,16 @@ class OAMix:
         slot = 1 + self._sal_slot
         self._sal_prefetch[self._saliency_key(imgs, gt_list)] = self._saliency_launch(imgs, gt_list, None, True, slot=slot)
 
-    def _workspace(self, nbytes, device):
+    def _workspace(self, nbytes, device, slot=0):
         torch = _lib.require_cuda()
+        if slot:   # the second lane of the overlapped pipeline owns its own scratch
+            ws = self._ws_lanes.get(slot)
+            if ws is None or ws.numel() < nbytes or ws.device != device:
+                if ws is not None:
+                    torch.cuda.synchronize(device)
+                self._ws_lanes[slot] = None
+                ws = self._ws_lanes[slot] = torch.empty(int(nbytes * 2) + 4096, dtype=torch.uint8, device=device)
+            return ws
         if self._ws_cache is None or self._ws_cache.numel() < nbytes or self._ws_cache.device != device:
             # The old workspace may still be in use by kernels in flight; once released, the caching allocator may hand
             # its block to a buffer that is used on ANOTHER stream (the saliency stream) right away.  Growing is rare:
@@ -554,7 +571,7 @@ class OAMix:
             self._ws_cache = torch.empty(int(nbytes * 2) + 4096, dtype=torch.uint8, device=device)
         return self._ws_cache
 
-    def execute(self, jobs, imgs, outs=None, stream=None, profile=None):
+    def execute(self, jobs, imgs, outs=None, stream=None, profile=None, ctas_per_sm=0, ws_slot=0):
         """Run the packed plans.  jobs: a packed plan blob (uint8 array, one view per image) or a list of
         (view_plan, gt, img_index); imgs: list of CUDA u8 HWC tensors; returns one output tensor per view.
         ``profile`` (a dict) switches to the event-timed entry point and receives per-kernel ms / counts."""
@@ -569,7 +586,7 @@ class OAMix:
             blob = self._pack(jobs)
         need = ctypes.c_size_t(0)
         _lib.check(lib.oadg_oamix_workspace_bytes(blob.ctypes.data, blob.nbytes, ctypes.byref(need)))
-        ws = self._workspace(need.value, dev)
+        ws = self._workspace(need.value, dev, ws_slot)
         if outs is None:
             outs = [torch.empty_like(imgs[j[2]]) for j in jobs]
         src = (ctypes.c_void_p * len(imgs))(*[int(t.data_ptr()) for t in imgs])
@@ -599,8 +616,12 @@ class OAMix:
             self.last_launches += 2
             return outs
         n = ctypes.c_int(0)
-        _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
-                                          ctypes.byref(n), s_raw))
+        if ctas_per_sm:
+            _lib.check(lib.oadg_oamix_execute_shared(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
+                                                     int(ctas_per_sm), ctypes.byref(n), s_raw))
+        else:
+            _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
+                                              ctypes.byref(n), s_raw))
         self.last_launches += n.value
         return outs
 
@@ -720,14 +741,20 @@ class OAMix:
         that's upload + saliency scores are already in flight, so host<->device copies, the score read-back and the
         host sampling overlap the kernels instead of adding to them.  The pipeline has its own CUDA streams (like a
         loader worker): what the caller enqueues on its stream between batches neither waits for nor delays it.
-        With ``threaded`` (default) the pipeline's host side runs in a worker thread, so its plan sampling and
-        scheduling (native code, GIL released) overlap the caller's own host work.
+        Consecutive batches of CUDA frames run as half-width launches on two streams, each filling the other's
+        dependency stalls (``overlap_batches``: None = CUDA frames only, True / False to force).  With ``threaded`` (default) the pipeline's host side runs in a worker thread,
+        so its plan sampling and scheduling (native code, GIL released) overlap the caller's own host work.
+
+        Samples whose ``img`` is a CUDA uint8 tensor (complete when the batch is read from ``batches``) stay on the
+        device: no upload, ``img2`` is a CUDA tensor ordered on the consumer's current stream; the consumer must
+        enqueue its work on a batch's views before it asks for the next batch (that work is fenced before the
+        buffers are reused, four batches later).
 
         Differences from calling ``call_batch`` in a loop: ``batches`` is read a few items ahead (the caller must
         leave a batch's input arrays alone until it is yielded), and the np.random draws of later batches are taken
         before earlier ones are yielded: the global stream is consumed in the same order, so results match as long
         as the consumer draws nothing from np.random (and does not use this transform) while iterating.  A batch
-        whose plan cannot be sampled raises when it is its turn to be yielded.  Configurations other than
+        that cannot be processed raises when it is its turn to be yielded.  Configurations other than
         num_views=2, keep_orig=True are served by ``call_batch`` without pipelining."""
         if not (self.num_views == 2 and self.keep_orig):
             for b in batches:
@@ -735,11 +762,29 @@ class OAMix:
             return
         torch = _lib.require_cuda()
         dev = torch.device('cuda', torch.cuda.current_device())
-        pipe = self._streams.get(('pipe', str(dev)))
-        if pipe is None:
-            pipe = self._streams[('pipe', str(dev))] = torch.cuda.Stream(dev)
+        released = {}     # batch index -> event on the consumer's stream: its work on that batch's device views
+        self.pipe_launches = 0
+
+        def hand_over(item):
+            # consumer thread: device views become valid on its current stream; when it comes back for the next
+            # batch, whatever it enqueued on them is fenced by an event the pipeline waits for before reuse
+            res, job = item
+            if job.get('device'):
+                torch.cuda.current_stream(dev).wait_event(job['done'])
+            return res, job
+
+        def release(job):
+            if job.get('device'):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                released[job['idx']] = ev
+                released.pop(job['idx'] - 8, None)
+
         if not threaded:
-            yield from self._pipeline(batches, dev, pipe)
+            for item in self._pipeline(batches, dev, released):
+                res, job = hand_over(item)
+                yield res
+                release(job)
             return
         import queue
         import threading
@@ -757,8 +802,8 @@ class OAMix:
         def work():
             try:
                 torch.cuda.set_device(dev)
-                for res in self._pipeline(batches, dev, pipe):
-                    if not put(('ok', res)):
+                for item in self._pipeline(batches, dev, released):
+                    if not put(('ok', item)):
                         return
                 put(('end', None))
             except BaseException as e:   # delivered to the consumer in order
@@ -770,7 +815,9 @@ class OAMix:
             while True:
                 kind, val = q.get()
                 if kind == 'ok':
-                    yield val
+                    res, job = hand_over(val)
+                    yield res
+                    release(job)
                 elif kind == 'err':
                     raise val
                 else:
@@ -779,19 +826,25 @@ class OAMix:
             stop.set()
             th.join(timeout=10)
 
-    def _pipeline(self, batches, dev, main):
-        """iter_batches' generator: `main` is the stream of the kernel chains."""
-        import collections
+    def _stream(self, name, dev):
         torch = _lib.require_cuda()
-        side = self._side_stream(dev)
-        cout = self._streams.get(('out', str(dev)))
-        if cout is None:
-            cout = self._streams[('out', str(dev))] = torch.cuda.Stream(dev)
+        st = self._streams.get((name, str(dev)))
+        if st is None:
+            st = self._streams[(name, str(dev))] = torch.cuda.Stream(dev)
+        return st
+
+    def _pipeline(self, batches, dev, released):
+        """iter_batches' generator: yields (results, job).  Batch k is yielded after batch k + 1's kernel chain was
+        launched and batch k + 2's upload + saliency kernel were enqueued."""
+        import collections
+        import time
+        torch = _lib.require_cuda()
+        side, cout = self._side_stream(dev), self._stream('out', dev)
+        lanes = [self._stream('pipe', dev), self._stream('pipe2', dev)]
         it = iter(batches)
         staged, launched = collections.deque(), collections.deque()
         count = [0]
         prof = self.pipe_profile          # optional dict: host seconds per phase (scripts/e2e_profile.py)
-        import time
 
         def tick(name, t0):
             if prof is not None:
@@ -808,16 +861,27 @@ class OAMix:
             idx = count[0]
             count[0] += 1
             t0 = time.perf_counter()
-            job = dict(results=results_list, idx=idx, error=None)
+            job = dict(results=results_list, idx=idx, error=None, device=False)
             try:   # a failure surfaces when the batch is yielded, after the batches before it
                 gts = [np.asarray(r['gt_bboxes'], dtype=np.float32).reshape(-1, 4) for r in results_list]
-                with torch.cuda.stream(side):   # upload, then the saliency kernel behind it on the same stream
-                    ins = [self._to_device(r['img'], (idx % 3, i)) for i, r in enumerate(results_list)]
-                    ready = torch.cuda.Event()
-                    ready.record(side)
-                job.update(gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins], ready=ready)
+                first = results_list[0]['img'] if results_list else None
+                if torch.is_tensor(first) and first.is_cuda:
+                    dimgs = [r['img'] for r in results_list]
+                    for t in dimgs:
+                        if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3 and
+                                t.is_contiguous()):
+                            raise TypeError('images must be contiguous CUDA uint8 HWC tensors')
+                    job.update(gts=gts, dimgs=dimgs, hw=[(int(t.shape[0]), int(t.shape[1])) for t in dimgs],
+                               ready=None, device=True)
+                else:
+                    with torch.cuda.stream(side):   # upload, then the saliency kernel behind it on the same stream
+                        ins = [self._to_device(r['img'], (idx % 3, i)) for i, r in enumerate(results_list)]
+                        ready = torch.cuda.Event()
+                        ready.record(side)
+                    job.update(gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins], ready=ready)
                 t0 = tick('upload_enqueue', t0)
                 job['sal'] = self._saliency_launch(job['dimgs'], gts, None, True, slot=4 + idx % 3)
+                self.pipe_launches += 1 if job['sal']['st'] is not None else 0
                 tick('saliency_enqueue', t0)
             except Exception as e:
                 job['error'] = e
@@ -827,27 +891,40 @@ class OAMix:
             if job['error'] is None:
                 try:
                     t0 = time.perf_counter()
+                    idx = job['idx']
                     scores = self._saliency_collect(job['sal'])
                     t0 = tick('scores_wait', t0)
                     plan = job['plan'] = self.sample_plan(job['hw'], job['gts'], scores)
                     t0 = tick('sample_plan', t0)
-                    key = ('outs', job['idx'] % 2, tuple(tuple(d.shape) for d in job['dimgs']))
+                    n_sets = 4 if job['device'] else 2   # device views: see iter_batches' hand-over protocol
+                    key = ('outs', idx % n_sets, n_sets, tuple(tuple(d.shape) for d in job['dimgs']))
                     douts = self._host_state['dev'].get(key)
                     if douts is None:
                         douts = self._host_state['dev'][key] = [torch.empty_like(d) for d in job['dimgs']]
-                    main.wait_event(job['ready'])
-                    self.execute(plan.blob, job['dimgs'], outs=douts, stream=main)
+                    overlap = job['device'] if self.overlap_batches is None else self.overlap_batches
+                    lane, ctas = (idx % 2, 2) if overlap else (0, 0)
+                    st = lanes[lane]
+                    if job['ready'] is not None:
+                        st.wait_event(job['ready'])
+                    if job['device'] and (idx - n_sets) in released:   # the consumer's work on this set's last views
+                        st.wait_event(released[idx - n_sets])
+                    before = self.last_launches
+                    self.execute(plan.blob, job['dimgs'], outs=douts, stream=st, ctas_per_sm=ctas, ws_slot=lane)
+                    self.pipe_launches += self.last_launches - before
                     t0 = tick('execute_enqueue', t0)
-                    done = torch.cuda.Event()
-                    done.record(main)
-                    host = [self._pinned_out(o.shape) for o in douts]
-                    with torch.cuda.stream(cout):
-                        cout.wait_event(done)
-                        for (h_, _), o in zip(host, douts):
-                            h_.copy_(o, non_blocking=True)
-                        job['out_ready'] = torch.cuda.Event()
-                        job['out_ready'].record(cout)
-                    job['host'] = host
+                    job['done'] = torch.cuda.Event()
+                    job['done'].record(st)
+                    if job['device']:
+                        job['views'] = douts
+                    else:
+                        host = [self._pinned_out(o.shape) for o in douts]
+                        with torch.cuda.stream(cout):
+                            cout.wait_event(job['done'])
+                            for (h_, _), o in zip(host, douts):
+                                h_.copy_(o, non_blocking=True)
+                            job['out_ready'] = torch.cuda.Event()
+                            job['out_ready'].record(cout)
+                        job['host'] = host
                     tick('download_enqueue', t0)
                 except Exception as e:
                     job['error'] = e
@@ -865,11 +942,15 @@ class OAMix:
             if job['error'] is not None:
                 raise job['error']
             t0 = time.perf_counter()
-            job['out_ready'].synchronize()
+            if job['device']:
+                views = job['views']
+            else:
+                job['out_ready'].synchronize()
+                views = [a for _, a in job['host']]
             t0 = tick('views_wait', t0)
-            res = self._fill_results(job['results'], [a for _, a in job['host']], job['plan'])
+            res = self._fill_results(job['results'], views, job['plan'])
             t0 = tick('fill_results', t0)
-            yield res
+            yield res, job
             tick('consumer', t0)
 
     def __call__(self, results, *args, **kwargs):

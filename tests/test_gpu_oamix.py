@@ -263,18 +263,21 @@ def test_iter_batches_equals_call_batch(cuda, threaded):
     np.random.seed(91)
     want = [t.call_batch(b) for b in make()]
     st_want = np.random.get_state()
-    np.random.seed(91)
-    got = []
-    for res in t.iter_batches(iter(make()), threaded=threaded):
-        got.append([{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()} for r in res])
-    st_got = np.random.get_state()
-    assert len(got) == len(want)
-    assert st_want[2] == st_got[2] and np.array_equal(st_want[1], st_got[1])
-    for wb, gb in zip(want, got):
-        for a, b in zip(wb, gb):
-            assert a['custom_field'] == b['custom_field'] and a['img_fields'] == b['img_fields']
-            for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
-                assert np.array_equal(a[k], b[k]), k
+    for overlap in (None, True):        # None: host frames go one full-width launch after the other
+        t.overlap_batches = overlap
+        np.random.seed(91)
+        got = []
+        for res in t.iter_batches(iter(make()), threaded=threaded):
+            got.append([{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()} for r in res])
+        st_got = np.random.get_state()
+        assert len(got) == len(want)
+        assert st_want[2] == st_got[2] and np.array_equal(st_want[1], st_got[1])
+        for wb, gb in zip(want, got):
+            for a, b in zip(wb, gb):
+                assert a['custom_field'] == b['custom_field'] and a['img_fields'] == b['img_fields']
+                for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
+                    assert np.array_equal(a[k], b[k]), k
+    t.overlap_batches = None
     # an empty loader and a single batch
     assert list(t.iter_batches([], threaded=threaded)) == []
     np.random.seed(3)
@@ -292,3 +295,42 @@ def test_iter_batches_equals_call_batch(cuda, threaded):
     it = t.iter_batches(iter(make()), threaded=threaded)
     next(it)
     it.close()
+
+
+@pytest.mark.parametrize('threaded', [False, True])
+def test_iter_batches_device_frames(cuda, threaded):
+    """CUDA frames in, CUDA views out (no upload / download): same pixels as oamix_batch on the same seeds, also when
+    the consumer keeps the GPU busy with work on each batch's views before asking for the next one (the fence the
+    pipeline waits for before it reuses a view buffer), and with batch overlap switched off."""
+    import torch
+    from oadg_b200 import OAMix
+    t = OAMix(**dict(OAMIX_CFG, version='augmix'))
+    frames = [synth.make_image(300 + k, 200, 333, 4) for k in range(18)]
+    dev = [torch.from_numpy(f).to(cuda) for f, _ in frames]
+    gts = [g for _, g in frames]
+    np.random.seed(13)
+    want = [[o.clone() for o in t.oamix_batch(dev[2 * k:2 * k + 2], gts[2 * k:2 * k + 2])[0]] for k in range(9)]
+
+    def batches():
+        for k in range(9):
+            yield [dict(img=dev[2 * k + j], gt_bboxes=gts[2 * k + j]) for j in range(2)]
+    for overlap in (True, False):
+        t.overlap_batches = overlap
+        np.random.seed(13)
+        sums, got = [], []
+        for res in t.iter_batches(batches(), threaded=threaded):
+            views = [r['img2'] for r in res]
+            assert all(v.is_cuda for v in views)
+            acc = views[0].to(torch.float32)
+            for _ in range(20):                      # keeps the consumer's stream busy on this batch's views
+                acc = acc * 0.5 + views[1].to(torch.float32)
+            sums.append(acc.sum())
+            got.append([v.clone() for v in views])
+        assert t.pipe_launches == 27
+        for k, (a, b) in enumerate(zip(want, got)):
+            for x, y in zip(a, b):
+                assert torch.equal(x, y), (overlap, k)
+            acc = a[0].to(torch.float32)
+            for _ in range(20):
+                acc = acc * 0.5 + a[1].to(torch.float32)
+            assert torch.equal(acc.sum(), sums[k]), (overlap, k)
