@@ -171,12 +171,14 @@ class OAMix:
         self._ws_lanes = {}
         self.pipe_profile = None
         self.pipe_launches = 0
-        # iter_batches: run consecutive batches as half-width launches on two streams, so that one batch's tiles
-        # fill the other's dependency stalls (measured: 736 -> 635 us per batch for chain + mix).  None = automatic:
-        # on for CUDA frames, off for host frames -- two resident chain launches leave no SM with room for another
-        # kernel's large shared-memory blocks, which starves a consumer that waits for its own kernels every step
-        # (bench e2e with loss.item() per step: 1915 images/s off, 1560 on; device frames: 2405 off, 2820 on).
-        self.overlap_batches = {'0': False, '1': True}.get(os.environ.get('OADG_OVERLAP', ''), None)
+        # iter_batches can run consecutive batches as half-width launches on two streams, so that one batch's tiles
+        # fill the other's dependency stalls (OA-Mix alone: 736 -> 661 us per batch).  Opt-in (True, or
+        # OADG_OVERLAP=1): two resident chain launches never drain together and leave no SM with room for another
+        # kernel's large shared-memory blocks, so a consumer that runs such kernels between batches (the OA-Loss
+        # tcgen05 kernels need 193 KB) either starves or, through the view fence, stalls the chains -- the bench
+        # step then flips between 0.71 and 1.29 ms; NCCL kernels of a multi-rank job starve the same way.  With one
+        # full-width launch after the other there is a drain point per batch and everything interleaves.
+        self.overlap_batches = os.environ.get('OADG_OVERLAP', '0') == '1'
         self.last_launches = 0
 
     def __repr__(self):
@@ -526,7 +528,9 @@ class OAMix:
         torch = _lib.require_cuda()
         side = self._streams.get(('side', str(dev)))
         if side is None:
-            side = self._streams[('side', str(dev))] = torch.cuda.Stream(dev)
+            # high priority: the persistent chain kernels hold every SM slot until they finish, and the small
+            # saliency kernel (whose scores the NEXT plan waits for) must get the first slot that frees up
+            side = self._streams[('side', str(dev))] = torch.cuda.Stream(dev, priority=-1)
         return side
 
     def _saliency_collect(self, handle):
@@ -673,20 +677,27 @@ class OAMix:
         dev.copy_(src, non_blocking=True)
         return dev, img
 
-    def _pinned_out(self, shape):
-        """(page-locked uint8 tensor, numpy array over it) for one generated view.  Pinning memory costs
-        milliseconds, so the buffers are recycled: when the caller drops the array (and every view of it), a
-        finalizer puts the tensor back on the free list."""
+    def _pinned_out(self, shape, reserve=0):
+        """(page-locked uint8 tensor, numpy array over it) for one generated view.  Pinning memory costs tens of
+        milliseconds per view, so the buffers are recycled: when the caller drops the array (and every view of it), a
+        finalizer puts the buffer back on the free list.  Buffers are flat and pooled by size class (1 MiB steps), so
+        frames of different shapes share them; ``reserve`` buffers of the class are pinned at first use (the loader
+        loop asks for as many as it can have in flight, so that it never pins in steady state), up to 2 GiB in all."""
         import weakref
         torch = _lib.require_cuda()
-        free = self._host_state.setdefault('out_free', {}).setdefault(tuple(shape), [])
-        try:
-            t = free.pop()
-        except IndexError:
-            t = torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=True)
-        a = t.numpy()
+        n = int(np.prod(shape))
+        cls = max(1, -(-n // (1 << 20))) << 20
+        pool = self._host_state.setdefault('out_pool', dict(free={}, made={}, bytes=0))
+        free = pool['free'].setdefault(cls, [])
+        while not free or (pool['made'].get(cls, 0) < reserve and pool['bytes'] + cls <= (2 << 30)):
+            free.append(torch.empty(cls, dtype=torch.uint8, pin_memory=True))
+            pool['made'][cls] = pool['made'].get(cls, 0) + 1
+            pool['bytes'] += cls
+        t = free.pop()
+        view = t[:n].view(tuple(shape))
+        a = view.numpy()
         weakref.finalize(a, free.append, t)
-        return t, a
+        return view, a
 
     def _to_host(self, outs):
         """CUDA views -> numpy arrays backed by page-locked memory (one sync for all of them)."""
@@ -741,8 +752,8 @@ class OAMix:
         that's upload + saliency scores are already in flight, so host<->device copies, the score read-back and the
         host sampling overlap the kernels instead of adding to them.  The pipeline has its own CUDA streams (like a
         loader worker): what the caller enqueues on its stream between batches neither waits for nor delays it.
-        Consecutive batches of CUDA frames run as half-width launches on two streams, each filling the other's
-        dependency stalls (``overlap_batches``: None = CUDA frames only, True / False to force).  With ``threaded`` (default) the pipeline's host side runs in a worker thread,
+        With ``overlap_batches`` (opt-in, see __init__) consecutive batches run as half-width launches on two
+        streams, each filling the other's dependency stalls.  With ``threaded`` (default) the pipeline's host side runs in a worker thread,
         so its plan sampling and scheduling (native code, GIL released) overlap the caller's own host work.
 
         Samples whose ``img`` is a CUDA uint8 tensor (complete when the batch is read from ``batches``) stay on the
@@ -901,7 +912,7 @@ class OAMix:
                     douts = self._host_state['dev'].get(key)
                     if douts is None:
                         douts = self._host_state['dev'][key] = [torch.empty_like(d) for d in job['dimgs']]
-                    overlap = job['device'] if self.overlap_batches is None else self.overlap_batches
+                    overlap = bool(self.overlap_batches)
                     lane, ctas = (idx % 2, 2) if overlap else (0, 0)
                     st = lanes[lane]
                     if job['ready'] is not None:
@@ -917,7 +928,7 @@ class OAMix:
                     if job['device']:
                         job['views'] = douts
                     else:
-                        host = [self._pinned_out(o.shape) for o in douts]
+                        host = [self._pinned_out(o.shape, reserve=6 * len(douts)) for o in douts]
                         with torch.cuda.stream(cout):
                             cout.wait_event(job['done'])
                             for (h_, _), o in zip(host, douts):

@@ -263,7 +263,7 @@ def test_iter_batches_equals_call_batch(cuda, threaded):
     np.random.seed(91)
     want = [t.call_batch(b) for b in make()]
     st_want = np.random.get_state()
-    for overlap in (None, True):        # None: host frames go one full-width launch after the other
+    for overlap in (False, True):       # False (default): one full-width launch after the other
         t.overlap_batches = overlap
         np.random.seed(91)
         got = []
@@ -277,7 +277,7 @@ def test_iter_batches_equals_call_batch(cuda, threaded):
                 assert a['custom_field'] == b['custom_field'] and a['img_fields'] == b['img_fields']
                 for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
                     assert np.array_equal(a[k], b[k]), k
-    t.overlap_batches = None
+    t.overlap_batches = False
     # an empty loader and a single batch
     assert list(t.iter_batches([], threaded=threaded)) == []
     np.random.seed(3)
