@@ -131,6 +131,10 @@ int  oadg_abi_version(void);
 /* sizes of the six plan structs in the order header, view, gt, op, bbo, target */
 void oadg_struct_sizes(int32_t out[6]);
 const char* oadg_error_string(int code);
+/* cudaMemcpyAsync between a host buffer (page-locked for a truly asynchronous copy) and a device buffer on `stream`;
+ * to_device != 0: host -> device.  Host-side plumbing of the plugin (frame upload / view download), no reference
+ * counterpart. */
+int oadg_memcpy_async(void* dst, const void* src, size_t bytes, int to_device, void* stream);
 
 /* ---- OA-Mix ----------------------------------------------------------------- */
 

@@ -19,6 +19,7 @@ SIGNATURES = {
     'oadg_error_string': (_c.c_char_p, [_c.c_int]),
     'oadg_saliency_scores': (_c.c_int, [_vp, _vp, _vp, _c.c_int, _vp, _vp]),
     'oadg_oamix_workspace_bytes': (_c.c_int, [_vp, _sz, _c.POINTER(_sz)]),
+    'oadg_memcpy_async': (_c.c_int, [_vp, _vp, _sz, _c.c_int, _vp]),
     'oadg_oamix_execute': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
     'oadg_oamix_execute_shared': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.c_int, _c.POINTER(_c.c_int),
                                              _vp]),

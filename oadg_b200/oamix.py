@@ -513,13 +513,11 @@ class OAMix:
             hb[o_hw:o_box].view(np.int32)[:] = [v for t in imgs for v in (int(t.shape[0]), int(t.shape[1]))]
             hb[o_box:nbytes].view(np.int32)[:] = [v for r in rows for v in r]
             s = st['stream'] if inputs_ready else cur
-            with torch.cuda.stream(s):
-                st['devbuf'][:nbytes].copy_(st['host'][:nbytes], non_blocking=True)
-                base = st['devbuf'].data_ptr()
-                _lib.check(lib.oadg_saliency_scores(base, base + o_hw, base + o_box, n, st['scores'].data_ptr(),
-                                                    s.cuda_stream))
-                st['scores_host'][:n].copy_(st['scores'][:n], non_blocking=True)
-                st['event'].record(s)
+            base, raw = st['devbuf'].data_ptr(), s.cuda_stream
+            _lib.check(lib.oadg_memcpy_async(base, st['host'].data_ptr(), nbytes, 1, raw))
+            _lib.check(lib.oadg_saliency_scores(base, base + o_hw, base + o_box, n, st['scores'].data_ptr(), raw))
+            _lib.check(lib.oadg_memcpy_async(st['scores_host'].data_ptr(), st['scores'].data_ptr(), 8 * n, 0, raw))
+            st['event'].record(s)
             self.last_launches += 1
         return dict(out=out, slots=slots, st=st, n=len(rows))
 
@@ -657,9 +655,10 @@ class OAMix:
         return outs, oamix_boxes, plan.ml_boxes
 
     # ------------------------------------------------------------------ host buffers
-    def _to_device(self, img, slot):
-        """Host uint8 HWC array -> CUDA tensor on the current stream.  Page-locked arrays (e.g. a loader's pinned
-        buffers) are copied asynchronously in place; pageable ones go through a persistent pinned staging buffer."""
+    def _to_device(self, img, slot, stream=None):
+        """Host uint8 HWC array -> CUDA tensor on the current stream (or ``stream``).  Page-locked arrays (e.g. a
+        loader's pinned buffers) are copied asynchronously in place; pageable ones go through a persistent pinned
+        staging buffer."""
         torch = _lib.require_cuda()
         img = np.ascontiguousarray(np.asarray(img, dtype=np.uint8))
         src = torch.from_numpy(img)
@@ -674,7 +673,10 @@ class OAMix:
                 pin = st['pin'][key] = torch.empty(img.shape, dtype=torch.uint8).pin_memory()
             pin.copy_(src)
             src = pin
-        dev.copy_(src, non_blocking=True)
+        if stream is None:
+            dev.copy_(src, non_blocking=True)
+        else:
+            _lib.check(_lib.load().oadg_memcpy_async(dev.data_ptr(), src.data_ptr(), src.numel(), 1, stream.cuda_stream))
         return dev, img
 
     def _pinned_out(self, shape, reserve=0):
@@ -850,6 +852,7 @@ class OAMix:
         import collections
         import time
         torch = _lib.require_cuda()
+        lib = _lib.load()
         side, cout = self._side_stream(dev), self._stream('out', dev)
         lanes = [self._stream('pipe', dev), self._stream('pipe2', dev)]
         it = iter(batches)
@@ -885,10 +888,10 @@ class OAMix:
                     job.update(gts=gts, dimgs=dimgs, hw=[(int(t.shape[0]), int(t.shape[1])) for t in dimgs],
                                ready=None, device=True)
                 else:
-                    with torch.cuda.stream(side):   # upload, then the saliency kernel behind it on the same stream
-                        ins = [self._to_device(r['img'], (idx % 3, i)) for i, r in enumerate(results_list)]
-                        ready = torch.cuda.Event()
-                        ready.record(side)
+                    # upload, then the saliency kernel behind it on the same stream
+                    ins = [self._to_device(r['img'], (idx % 3, i), side) for i, r in enumerate(results_list)]
+                    ready = torch.cuda.Event()
+                    ready.record(side)
                     job.update(gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins], ready=ready)
                 t0 = tick('upload_enqueue', t0)
                 job['sal'] = self._saliency_launch(job['dimgs'], gts, None, True, slot=4 + idx % 3)
@@ -929,12 +932,12 @@ class OAMix:
                         job['views'] = douts
                     else:
                         host = [self._pinned_out(o.shape, reserve=6 * len(douts)) for o in douts]
-                        with torch.cuda.stream(cout):
-                            cout.wait_event(job['done'])
-                            for (h_, _), o in zip(host, douts):
-                                h_.copy_(o, non_blocking=True)
-                            job['out_ready'] = torch.cuda.Event()
-                            job['out_ready'].record(cout)
+                        cout.wait_event(job['done'])
+                        for (h_, _), o in zip(host, douts):
+                            _lib.check(lib.oadg_memcpy_async(h_.data_ptr(), o.data_ptr(), o.numel(), 0,
+                                                             cout.cuda_stream))
+                        job['out_ready'] = torch.cuda.Event()
+                        job['out_ready'].record(cout)
                         job['host'] = host
                     tick('download_enqueue', t0)
                 except Exception as e:
