@@ -211,3 +211,34 @@ def test_pair_map_and_row_check():
         assert np.array_equal(reference_pair_map(n), supcon_np.pair_map(n))
     with pytest.raises(RuntimeError):
         reference_pair_map(1024)
+
+
+def test_view_buffer_pool_recycles_on_drop_and_shares_size_classes(monkeypatch):
+    """OAMix._pinned_out (host logic of the loader loop; page-locking itself needs a GPU box, so torch.empty is
+    relieved of pin_memory here): `reserve` buffers of a size class are made at first use, a buffer comes back only
+    when the array AND every view of it are gone, and shapes of the same 1 MiB class share buffers."""
+    import torch
+    import oadg_b200.oamix as m
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, 'empty', lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != 'pin_memory'}))
+    monkeypatch.setattr(m._lib, 'require_cuda', lambda: torch)
+    t = m.OAMix(version='augmix')
+    view, a = t._pinned_out((10, 20, 3), reserve=4)
+    pool = t._host_state['out_pool']
+    cls = 1 << 20
+    assert pool['made'] == {cls: 4} and len(pool['free'][cls]) == 3 and a.shape == (10, 20, 3) and a.dtype == np.uint8
+    assert view.data_ptr() == a.ctypes.data
+    a[:] = 7
+    part = a[2:4]
+    del a, view
+    assert len(pool['free'][cls]) == 3          # a view of the array still holds the buffer
+    del part
+    assert len(pool['free'][cls]) == 4
+    _, b = t._pinned_out((100, 200, 3))         # another shape, same class: no new buffer
+    assert pool['made'] == {cls: 4} and b.shape == (100, 200, 3)
+    held = [t._pinned_out((10, 20, 3)) for _ in range(5)]   # more than reserved: grows on demand
+    assert pool['made'][cls] == 6 and len(pool['free'][cls]) == 0
+    del held, b
+    assert len(pool['free'][cls]) == 6
+    _, c = t._pinned_out((1024, 2048, 3))
+    assert pool["made"][6 << 20] == 1 and c.nbytes == 1024 * 2048 * 3
