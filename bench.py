@@ -249,7 +249,7 @@ def reference_arm(args):
                              'wall_s': t_all},
             'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -501,9 +501,12 @@ def product_arm(args):
             'config': workload_config(world), 'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'roofline': roofline, 'oaloss': oaloss, 'cpu_baseline': cpu}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = sys.stdout
 
 
 def main():
@@ -517,6 +520,12 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-gather', action='store_true', help='N>1: keep the reference\'s per-rank local loss')
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library writes to fd 1 meanwhile (e.g. NCCL's version banner
+    # under NCCL_DEBUG) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         reference_arm(args)
     else:
