@@ -2,20 +2,17 @@
 //
 // Z = F F^T / T for the doubly-normalised RoI embeddings F [N, 256] fp32 (reference
 // contrastive_loss.py:157 `torch.matmul(logits_anchor, logits_contrast.T) / temper`), fused with
-// the per-row masked-InfoNCE statistics so that no N x N tensor reaches HBM.
+// the per-row masked-InfoNCE statistics; the only N x N tensor written is the logits Z the backward reads back
+// (17 MB at N = 2088, L2-resident between the two kernels).
 //
 // Precision: the loss must agree with the fp32 reference to 1e-5 relative while logits are
 // divided by T = 0.06 (x16.7 error gain), so the contraction is 3xTF32:
 //   F = Fh + Fl  (Fh = rna-tf32(F), Fl = rna-tf32(F - Fh));  Z ~= Fh Fh^T + Fh Fl^T + Fl Fh^T
 // with fp32 accumulation in TMEM (dropped term Fl Fl^T <= 2^-22).
 //
-// One CTA per 128 x 128 tile of Z (UMMA M=128, N=128, K=8 per instruction):
-//   thread 0   TMA producer: per K-chunk of 32 floats (one 128-byte swizzled row) four
-//              cp.async.bulk.tensor loads (A-hi, A-lo, B-hi, B-lo; 64 KB per stage, 3 stages)
-//   thread 32  MMA issuer: 4 K-steps x 3 tcgen05.mma.kind::tf32 per chunk, tcgen05.commit
-//              releases the stage, a last commit signals the epilogue
-//   4 warps    epilogue: tcgen05.ld 32 lanes x 32 columns at a time; each thread owns one row
-//              of the tile and keeps an online (max, sum-exp, positive-sum) over its 128 columns
+// Tiles of Z are 128 x 128 (UMMA M=128, N=128, K=8 per instruction); the forward kernel is persistent and
+// warp-specialised (TMA producer warp, MMA warp with two TMEM accumulators, four epilogue warps), see the comment
+// above sim_fwd_tc_kernel; the backward (sim_bwd_tc_kernel) builds its A operand from the stored logits.
 #include <cuda.h>
 #include <stdlib.h>
 
