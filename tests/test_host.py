@@ -242,3 +242,48 @@ def test_view_buffer_pool_recycles_on_drop_and_shares_size_classes(monkeypatch):
     assert len(pool['free'][cls]) == 6
     _, c = t._pinned_out((1024, 2048, 3))
     assert pool["made"][6 << 20] == 1 and c.nbytes == 1024 * 2048 * 3
+
+
+def test_native_sampler_randomized_sweep(libpath):
+    """40 random (frame size up to 1100x2100, 0..11 boxes, scores with rejected boxes, op set, mixture shape)
+    batches of two images: the native sampler's plan blob and final np.random state equal the Python statement of the
+    draw order byte for byte, and both raise together when no box fits."""
+    from oadg_b200.oamix import OAMix
+    rng = np.random.RandomState(9)
+    for k in range(40):
+        version = 'augmix.all' if k % 2 else 'augmix'
+        h, w = int(rng.randint(16, 1100)), int(rng.randint(16, 2100))
+        n_gt, seed = int(rng.randint(0, 12)), int(rng.randint(0, 1 << 30))
+        extra = {} if k % 3 else dict(mixture_width=int(rng.randint(1, 5)), mixture_depth=int(rng.choice([-1, 1, 2, 3])))
+        t = OAMix(version=version, **extra)
+        gts = []
+        for _ in range(2):
+            g = np.zeros((n_gt, 4), np.float32)
+            for i in range(n_gt):
+                x1, y1 = rng.uniform(0, w - 8), rng.uniform(0, h - 8)
+                g[i] = [x1, y1, min(w, x1 + rng.uniform(4, w / 2)), min(h, y1 + rng.uniform(4, h / 2))]
+            gts.append(g)
+        scores = [[np.float64(rng.uniform(0, 1)) if rng.rand() > 0.2 else -1 for _ in range(n_gt)] for _ in range(2)]
+        np.random.seed(seed)
+        err_py = blob_py = None
+        try:
+            jobs = []
+            for i, g in enumerate(gts):
+                vp = t._sample_head(h, w, g)
+                t._sample_tail(vp, g, scores[i])
+                jobs.append((vp, g, i))
+            blob_py = t._pack(jobs)
+        except ValueError as e:
+            err_py = e
+        st_py = np.random.get_state()
+        np.random.seed(seed)
+        err_c = plan = None
+        try:
+            plan = t.sample_plan([(h, w)] * 2, gts, scores)
+        except ValueError as e:
+            err_c = e
+        st_c = np.random.get_state()
+        assert (err_py is None) == (err_c is None), (k, err_py, err_c)
+        if err_py is None:
+            assert np.array_equal(blob_py, plan.blob), k
+            assert st_py[2] == st_c[2] and np.array_equal(st_py[1], st_c[1]), k
