@@ -26,6 +26,7 @@ SIGNATURES = {
     'oadg_oamix_execute_profiled': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_f32),
                                                _c.POINTER(_f32), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _vp, _vp]),
     'oadg_oamix_last_trace': (_c.c_int, [_vp, _c.c_int]),
+    'oadg_oamix_poll_fault': (_c.c_int, [_c.c_int]),
     'oadg_oamix_sample_plan': (_c.c_int, [_vp, _vp, _c.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _c.POINTER(_sz),
                                           _vp, _vp, _vp, _vp, _vp]),
     'oadg_supcon_workspace_bytes': (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_sz)]),

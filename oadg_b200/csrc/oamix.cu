@@ -5,29 +5,29 @@
 //   profiles    per gt box two float32 vectors ux[W], uy[H]; blurred mask(y,x) = uy[y]*ux[x]
 //               (the reference materialises a 25 MB float HxWx3 mask per box, oa_mix.py:75-93)
 //   hist / lut  per lane input 3x256 u32 histogram (+ luma sum), per LUT op 3x256 u8 table
-//   plan        the host-sampled plan blob (oadg.h records) + work tables, one H2D copy
+//   plan        the host-sampled plan blob (oadg.h records) + work tables + tensor maps + ready ring, one H2D copy
 //
-// Two launches per batch:
+// Two launches per call (a call may carry the views of SEVERAL loader batches: they are independent, and the more
+// lanes the queue holds the fewer CTAs ever wait for a dependency):
 //   oamix_chain_kernel   ONE persistent launch (four independent 256-thread CTAs per SM) that drains the host-built
 //                        work queue (oamix_exec.h): mask profiles, union masks, histograms, LUTs, the bboxes-only
-//                        chains level by level and every depth step of every (view, branch) lane.  The queue is a
-//                        list of work items cut into tiles, ordered so that dependencies come first; CTAs claim
-//                        tiles with one atomic counter and an item starts as soon as the items it depends on are
-//                        complete (per-item completion counters, no grid-wide barrier), so nothing returns to the
-//                        host between the ~10-40 dependent stages.
+//                        chains level by level and every depth step of every (view, branch) lane.  Items are cut
+//                        into tiles; an item is appended to the READY RING when the last tile of its last
+//                        dependency is published, CTAs take tiles from the ring in order (no grid-wide barrier).
+//                        The affine gathers (bboxes-only blends, bg-only steps) stage the source rectangle of every
+//                        64 x 16 sub-tile with TMA (cp.async.bulk.tensor.2d, zero fill = BORDER_CONSTANT) into a
+//                        two-stage mbarrier ring, so the staging of sub-tile k+1 overlaps the taps of sub-tile k.
 //   mix_kernel           branch mixing + object-aware mixing of all views (oa_mix.py:236,281-309)
 #include <stdlib.h>
 #include <string.h>
 
 #include "oadg_common.cuh"
+#include "oadg_tma.cuh"
 #include "oamix_exec.h"
 #include "oamix_tile.h"
 
 namespace oadg {
 namespace {
-
-// i / 255 in float64 (the reference divides a uint8 array by the python int 255, bbox_augmentation.py:267)
-__device__ const double g_div255[256] = {0.0 / 255.0, 1.0 / 255.0, 2.0 / 255.0, 3.0 / 255.0, 4.0 / 255.0, 5.0 / 255.0, 6.0 / 255.0, 7.0 / 255.0, 8.0 / 255.0, 9.0 / 255.0, 10.0 / 255.0, 11.0 / 255.0, 12.0 / 255.0, 13.0 / 255.0, 14.0 / 255.0, 15.0 / 255.0, 16.0 / 255.0, 17.0 / 255.0, 18.0 / 255.0, 19.0 / 255.0, 20.0 / 255.0, 21.0 / 255.0, 22.0 / 255.0, 23.0 / 255.0, 24.0 / 255.0, 25.0 / 255.0, 26.0 / 255.0, 27.0 / 255.0, 28.0 / 255.0, 29.0 / 255.0, 30.0 / 255.0, 31.0 / 255.0, 32.0 / 255.0, 33.0 / 255.0, 34.0 / 255.0, 35.0 / 255.0, 36.0 / 255.0, 37.0 / 255.0, 38.0 / 255.0, 39.0 / 255.0, 40.0 / 255.0, 41.0 / 255.0, 42.0 / 255.0, 43.0 / 255.0, 44.0 / 255.0, 45.0 / 255.0, 46.0 / 255.0, 47.0 / 255.0, 48.0 / 255.0, 49.0 / 255.0, 50.0 / 255.0, 51.0 / 255.0, 52.0 / 255.0, 53.0 / 255.0, 54.0 / 255.0, 55.0 / 255.0, 56.0 / 255.0, 57.0 / 255.0, 58.0 / 255.0, 59.0 / 255.0, 60.0 / 255.0, 61.0 / 255.0, 62.0 / 255.0, 63.0 / 255.0, 64.0 / 255.0, 65.0 / 255.0, 66.0 / 255.0, 67.0 / 255.0, 68.0 / 255.0, 69.0 / 255.0, 70.0 / 255.0, 71.0 / 255.0, 72.0 / 255.0, 73.0 / 255.0, 74.0 / 255.0, 75.0 / 255.0, 76.0 / 255.0, 77.0 / 255.0, 78.0 / 255.0, 79.0 / 255.0, 80.0 / 255.0, 81.0 / 255.0, 82.0 / 255.0, 83.0 / 255.0, 84.0 / 255.0, 85.0 / 255.0, 86.0 / 255.0, 87.0 / 255.0, 88.0 / 255.0, 89.0 / 255.0, 90.0 / 255.0, 91.0 / 255.0, 92.0 / 255.0, 93.0 / 255.0, 94.0 / 255.0, 95.0 / 255.0, 96.0 / 255.0, 97.0 / 255.0, 98.0 / 255.0, 99.0 / 255.0, 100.0 / 255.0, 101.0 / 255.0, 102.0 / 255.0, 103.0 / 255.0, 104.0 / 255.0, 105.0 / 255.0, 106.0 / 255.0, 107.0 / 255.0, 108.0 / 255.0, 109.0 / 255.0, 110.0 / 255.0, 111.0 / 255.0, 112.0 / 255.0, 113.0 / 255.0, 114.0 / 255.0, 115.0 / 255.0, 116.0 / 255.0, 117.0 / 255.0, 118.0 / 255.0, 119.0 / 255.0, 120.0 / 255.0, 121.0 / 255.0, 122.0 / 255.0, 123.0 / 255.0, 124.0 / 255.0, 125.0 / 255.0, 126.0 / 255.0, 127.0 / 255.0, 128.0 / 255.0, 129.0 / 255.0, 130.0 / 255.0, 131.0 / 255.0, 132.0 / 255.0, 133.0 / 255.0, 134.0 / 255.0, 135.0 / 255.0, 136.0 / 255.0, 137.0 / 255.0, 138.0 / 255.0, 139.0 / 255.0, 140.0 / 255.0, 141.0 / 255.0, 142.0 / 255.0, 143.0 / 255.0, 144.0 / 255.0, 145.0 / 255.0, 146.0 / 255.0, 147.0 / 255.0, 148.0 / 255.0, 149.0 / 255.0, 150.0 / 255.0, 151.0 / 255.0, 152.0 / 255.0, 153.0 / 255.0, 154.0 / 255.0, 155.0 / 255.0, 156.0 / 255.0, 157.0 / 255.0, 158.0 / 255.0, 159.0 / 255.0, 160.0 / 255.0, 161.0 / 255.0, 162.0 / 255.0, 163.0 / 255.0, 164.0 / 255.0, 165.0 / 255.0, 166.0 / 255.0, 167.0 / 255.0, 168.0 / 255.0, 169.0 / 255.0, 170.0 / 255.0, 171.0 / 255.0, 172.0 / 255.0, 173.0 / 255.0, 174.0 / 255.0, 175.0 / 255.0, 176.0 / 255.0, 177.0 / 255.0, 178.0 / 255.0, 179.0 / 255.0, 180.0 / 255.0, 181.0 / 255.0, 182.0 / 255.0, 183.0 / 255.0, 184.0 / 255.0, 185.0 / 255.0, 186.0 / 255.0, 187.0 / 255.0, 188.0 / 255.0, 189.0 / 255.0, 190.0 / 255.0, 191.0 / 255.0, 192.0 / 255.0, 193.0 / 255.0, 194.0 / 255.0, 195.0 / 255.0, 196.0 / 255.0, 197.0 / 255.0, 198.0 / 255.0, 199.0 / 255.0, 200.0 / 255.0, 201.0 / 255.0, 202.0 / 255.0, 203.0 / 255.0, 204.0 / 255.0, 205.0 / 255.0, 206.0 / 255.0, 207.0 / 255.0, 208.0 / 255.0, 209.0 / 255.0, 210.0 / 255.0, 211.0 / 255.0, 212.0 / 255.0, 213.0 / 255.0, 214.0 / 255.0, 215.0 / 255.0, 216.0 / 255.0, 217.0 / 255.0, 218.0 / 255.0, 219.0 / 255.0, 220.0 / 255.0, 221.0 / 255.0, 222.0 / 255.0, 223.0 / 255.0, 224.0 / 255.0, 225.0 / 255.0, 226.0 / 255.0, 227.0 / 255.0, 228.0 / 255.0, 229.0 / 255.0, 230.0 / 255.0, 231.0 / 255.0, 232.0 / 255.0, 233.0 / 255.0, 234.0 / 255.0, 235.0 / 255.0, 236.0 / 255.0, 237.0 / 255.0, 238.0 / 255.0, 239.0 / 255.0, 240.0 / 255.0, 241.0 / 255.0, 242.0 / 255.0, 243.0 / 255.0, 244.0 / 255.0, 245.0 / 255.0, 246.0 / 255.0, 247.0 / 255.0, 248.0 / 255.0, 249.0 / 255.0, 250.0 / 255.0, 251.0 / 255.0, 252.0 / 255.0, 253.0 / 255.0, 254.0 / 255.0, 255.0 / 255.0};
 
 // The phase handlers are separate device functions: compiled into one monolithic kernel body, ptxas (12.9) produced
 // wrong code for the mixed-tile path (caught by tests/test_gpu_oamix.py::test_single_op_plans_match_host_arithmetic).
@@ -37,9 +37,26 @@ __device__ const double g_div255[256] = {0.0 / 255.0, 1.0 / 255.0, 2.0 / 255.0, 
 #define OADG_HANDLER __noinline__
 #endif
 
-constexpr int kMaxQueueItems = 4096;   // work items per launch (a CTA keeps a bitmap of the exhausted ones)
 constexpr int kCT = 256;     // threads per CTA of the chain kernel
 constexpr int kCtaPerSm = 4; // independent CTAs per SM (64 registers per thread): tiles of different kinds overlap on an SM
+
+// ---- dynamic shared memory of a CTA ------------------------------------------------------------------------
+// [0, 2 * kStageBytes)   two gather stages: 3 TMA boxes of 16 rows x 256 B (frame) + 3 boxes of 16 rows x 96 B (mask)
+//                        (aliased by the profile tiles' prefix sums, the histogram tiles' privatised bins and the
+//                        hand-staged rows of frames without a tensor map)
+// [kColOff, ...)         per tile column: cv2's adelta / bdelta terms of the affine map (int2)
+// [kUxOff, ...)          per tile column: the x-profile of the blended box (float)
+constexpr int kSubW = 64, kSubH = 16;
+constexpr int kMaxSrcRows = 3 * kGatherBoxRows;                    // 48 source rows per sub-tile
+constexpr int kMaxSrcPx = (kGatherImgBoxBytes - 15) / 3;           // 80 source pixels per row (TMA boxes start at 16-byte columns)
+constexpr int kStageImgBytes = kMaxSrcRows * kGatherImgBoxBytes;   // 12288
+constexpr int kStageMaskBytes = kMaxSrcRows * kGatherMaskBoxBytes; // 4608
+constexpr int kStageBytes = kStageImgBytes + kStageMaskBytes;      // 16896 (a multiple of 128)
+constexpr int kMaxTileW = 512;
+constexpr int kColOff = 2 * kStageBytes;
+constexpr int kUxOff = kColOff + kMaxTileW * 8;
+constexpr int kDynSmem = kUxOff + kMaxTileW * 4;                   // 39936 B
+constexpr int kHandStage = 2 * kStageBytes;                        // bytes the hand-staged fallback may use
 
 struct RegOp {      // op parameters of one region, staged in shared memory for per-pixel tiles
   int32_t kind, p0, p1;
@@ -47,41 +64,34 @@ struct RegOp {      // op parameters of one region, staged in shared memory for 
   double minv[6];
 };
 
-struct BboStage {    // one bbo job staged for the CTA (bbo_r_segment / bbo_c_segment)
+struct BboStage {    // one bbo job staged for the CTA (bbo_r_tile / bbo_c_segment)
   double minv[6];
   int32_t rect[4];
   int32_t W, H, gt, n_excl;
   const uint8_t* X;
   uint8_t* Y;
+  int32_t x_map, pad;
   int32_t excl[16][4];   // supports of the next level's boxes (catch-up exclusion)
 };
 
 struct ChainSmem {
   int next_tile;       // the CTA's next claimed tile ...
   int next_item;       // ... and the item it belongs to (-1: the queue is drained)
-  unsigned epoch_seen; // value of the ready-epoch when this CTA last scanned the queue
-  unsigned exhausted[kMaxQueueItems / 32];   // items this CTA knows to have no unclaimed tile left
-  int rowoff[2][96];   // staged gathers: byte offset of every staged source row (frame rows, mask rows)
+  int rowoff[2][96];   // hand-staged gathers: byte offset of every staged source row (frame rows, mask rows)
   int cand[16];        // mask tiles: the gt boxes whose support meets the tile
   int step_class;      // measurement aid: class of the last step tile (7 stream, 8 staged bg, 9 mixed / per pixel)
-  int prof_ready;      // u.prof holds the profile slices of the staged blend job
-  int bs_key;          // which bbo job `bs` (and, for blends, the profile slices in u.prof) currently holds; -1 = none
+  int bs_key;          // which bbo job `bs` currently holds; -1 = none
+  int sub_cls[kMaxTileW / kSubW];   // step tiles: class of every sub-tile (see step_tile)
+  int gather_rect[2][4];            // per gather stage: source x0, y0, rows (-1: not staged, 0: outside the frame), -
+  __align__(8) uint64_t full[2];    // mbarriers of the two gather stages
   ChainArgs args;      // the kernel arguments, copied once: the (non-inlined) handlers read them from shared memory
   BboStage bs;
-  union {
-    unsigned hist[2][768];   // histogram tiles: 2 privatised copies (4 warps share one)
-    float prof[3072];        // bbo jobs: the support's slices of the two mask profiles
-    struct {
-      double K[1537];        // profile tiles: exclusive prefix sums of the gaussian kernel
-      float p[1024];         //                low-res blurred profile
-    } g;
-  } u;
   __align__(16) uint8_t lut[OADG_MAX_REGIONS * 768];
   RegOp rop[OADG_MAX_REGIONS];
   Lane lane;
   double red[32];
   double ksum;
-  uint8_t tab[3][256];
+  double div255[256];  // i / 255 in float64 (the reference divides a uint8 array by the python int 255, bbox_augmentation.py:267)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -92,17 +102,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 // ---- the work queue ---------------------------------------------------------------------------------------
 // Every item has a counter of claimed tiles and a counter of outstanding dependency tiles (`pending`, initialised by
-// the host).  A CTA drains the item it is working on (one atomic per tile, issued before the tile is processed); when
-// that item runs out it scans the queue from the front for the first item that is READY (pending == 0) and still has
-// unclaimed tiles, skipping items whose inputs are not complete -- so a CTA only idles when nothing at all is ready.
-// A finished tile is published with bar.sync + fence by one thread, which then decrements `pending` of the item's
-// successors; a claimer reads `pending` with an acquire load, fences, and the CTA bar.syncs before touching the data
-// (the pattern of a cooperative-groups grid sync, per item instead of per grid).  All CTAs are co-resident
-// (cooperative launch), and a waiting CTA holds no tile, so the scheme cannot deadlock.
-__device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// the host).  The thread that publishes the last outstanding dependency tile of an item appends the item to the READY
+// RING (entries = ntiles << 32 | item, in order of readiness; the host pre-fills the items that start ready, in
+// priority order).  A CTA walks the ring from its private cursor: entries whose tiles are all claimed are skipped for
+// good, the first entry with an unclaimed tile yields a tile (one atomic), an unpublished entry means nothing else is
+// ready yet.  Publishing a tile is bar.sync + fence + one atomic per successor; a claimer reads the ring entry with an
+// acquire load and fences, and the CTA bar.syncs before touching the data.  All CTAs are co-resident (cooperative
+// launch) and a waiting CTA holds no tile, so the scheme cannot deadlock; a CTA that waits longer than 2 s raises the
+// sticky fault flag (the host turns it into OADG_E_PLAN) instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
@@ -110,39 +124,40 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   return v;
 }
 
-// thread 0 only: find the next (item, tile); returns false when every item is exhausted
-__device__ bool scan_for_work(const ChainArgs& A, unsigned* exhausted, int& scan_from, int& item, int& tile) {
+// thread 0 only: find the next (item, tile); returns false when every item is exhausted (or the wait timed out)
+__device__ bool claim_work(const ChainArgs& A, int& cursor, int& item, int& tile) {
   unsigned long long spin_t0 = 0;
+  const unsigned long long* ring = A.ring + kRingHeader;
   for (;;) {
-    bool any_left = false;
-    while (scan_from < A.n_items && (exhausted[scan_from >> 5] >> (scan_from & 31) & 1u)) ++scan_from;
-    for (int k = scan_from; k < A.n_items; ++k) {
-      if (exhausted[k >> 5] >> (k & 31) & 1u) continue;
-      const unsigned nt = (unsigned)A.items[k].ntiles;
-      const unsigned cl = ld_relaxed_u32(A.claimed + k);   // the two loads are independent: one L2 round trip
-      const int pend = ld_acquire_s32(A.pending + k);
-      if (cl >= nt) {
-        exhausted[k >> 5] |= 1u << (k & 31);
-        continue;
+    int pos = cursor;
+    bool blocked = false;
+    while (pos < A.n_items) {
+      const unsigned long long e = ld_acquire_u64(ring + pos);
+      if (e == kRingEmpty) {
+        blocked = true;
+        break;
       }
-      any_left = true;
-      if (pend > 0) continue;   // inputs not complete yet: look further down the queue
-      const unsigned t = atomicAdd(A.claimed + k, 1u);
-      if (t < nt) {
-        item = k;
-        tile = (int)t;
-        __threadfence();
-        return true;
+      const int it = (int)(unsigned)e;
+      const unsigned nt = (unsigned)(e >> 32);
+      if (ld_relaxed_u32(A.claimed + it) < nt) {
+        const unsigned t = atomicAdd(A.claimed + it, 1u);
+        if (t < nt) {
+          cursor = pos;
+          item = it;
+          tile = (int)t;
+          __threadfence();
+          return true;
+        }
       }
-      exhausted[k >> 5] |= 1u << (k & 31);
+      ++pos;
     }
-    if (!any_left) return false;
-    __nanosleep(256);   // nothing is ready: back off before polling the counters again
-    // safety valve: a CTA that finds nothing ready for 2 s gives up (flag in stats slot 15) instead of hanging the GPU
+    cursor = pos;   // everything before pos is exhausted for good
+    if (!blocked) return false;
+    __nanosleep(200);   // nothing is ready: back off before polling the ring again
     const unsigned long long now = globaltimer_ns();
     if (spin_t0 == 0) spin_t0 = now;
     else if (now - spin_t0 > 2000000000ull) {
-      atomicAdd(A.kind_ns + 15, 1ull);
+      atomicAdd(A.fault, 1u);
       return false;
     }
   }
@@ -151,7 +166,15 @@ __device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) 
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    for (int k = 0; k < I.succ_count; ++k) atomicSub(A.pending + A.succ[I.succ_first + k], 1);
+    tma::fence_proxy_async();   // the tile's stores (generic proxy) precede TMA reads (async proxy) of later items
+    for (int k = 0; k < I.succ_count; ++k) {
+      const int s = A.succ[I.succ_first + k];
+      if (atomicSub(A.pending + s, 1) == 1) {   // the last outstanding dependency tile: the successor is ready
+        __threadfence();
+        const unsigned long long slot = atomicAdd(A.ring, 1ull);
+        st_release_u64(A.ring + kRingHeader + slot, ((unsigned long long)(unsigned)A.items[s].ntiles << 32) | (unsigned)s);
+      }
+    }
   }
 }
 
@@ -159,7 +182,7 @@ __device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) 
 // blurred-mask profile of one (gt box, axis) (oa_mix.py:78-91): indicator on the 1/sr canvas -> GaussianBlur
 // (separable, BORDER_REFLECT_101, float32 kernel from getGaussianKernel) -> bilinear cv2.resize to full resolution.
 // ------------------------------------------------------------------------------------
-__device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, int obj) {
+__device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int obj) {
   const DevPlan& P = A.P;
   const int sr = 4;
   const int g = obj >> 1, axis = obj & 1;
@@ -170,12 +193,11 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, int 
   const int lo = G.lo[axis], hi = G.lo[axis + 2];
   const int ks = axis == 0 ? G.kx : G.ky;
   const double sigma = axis == 0 ? G.sigma_x : G.sigma_y;
-  float* p = S.u.g.p;
-  double* K = S.u.g.K;
+  double* K = reinterpret_cast<double*>(dyn);                  // [1537] exclusive prefix sums of the gaussian kernel
+  float* p = reinterpret_cast<float*>(dyn + 1538 * 8);         // [1024] low-res blurred profile
   float* out = (axis == 0 ? A.prof_x + (size_t)g * P.max_w : A.prof_y + (size_t)g * P.max_h);
   const int tid = threadIdx.x;
   __syncthreads();  // the shared buffers may still be in use by the previous tile
-  if (tid == 0) S.bs_key = -1;   // u.g overwrites the staged profile slices
   if (n_lo <= 0) {
     for (int d = tid; d < n_hi; d += kCT) out[d] = 0.f;
     return;
@@ -262,7 +284,6 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, int 
     out[d] = fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));
   }
 }
-
 // union of the blurred gt masks of a view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260) as float32 and as
 // uint8(mask*255): written once per batch, read by every bg-only op.  Tile = 256 x 8 px, one column x 8 rows per
 // thread; the boxes whose support meets the tile are listed once per tile, and a thread keeps the x-profile value of
@@ -322,14 +343,13 @@ __device__ OADG_HANDLER void mask_tile(const ChainArgs& A, ChainSmem& S, int vie
     A.masku[o] = (uint8_t)mask_to_u8(m);
   }
 }
-
 // per-channel histogram + luma sum of a lane's input frame (PIL Image.histogram()); tile = 32768 px (linear)
-__device__ OADG_HANDLER void hist_tile(const Lane& L, ChainSmem& S, int local, unsigned long long& lsum) {
+__device__ OADG_HANDLER void hist_tile(const Lane& L, unsigned* hist, int local, unsigned long long& lsum) {
   const int tid = threadIdx.x;
   const size_t npx = (size_t)L.H * L.W;
   const size_t p0 = (size_t)local * kHistTilePx;
   const size_t p1 = p0 + kHistTilePx < npx ? p0 + kHistTilePx : npx;
-  unsigned* my = S.u.hist[(tid >> 5) & 1];
+  unsigned* my = hist + ((tid >> 5) & 1) * 768;
   if ((((uintptr_t)L.in) & 15) == 0) {
     // 16 px = 48 B = 3 x uint4 per iteration: the channel of byte k is k % 3 at a compile-time phase
     const size_t c1 = p1 / kChunkPx;
@@ -364,19 +384,18 @@ __device__ OADG_HANDLER void hist_tile(const Lane& L, ChainSmem& S, int local, u
     }
   }
 }
-__device__ OADG_HANDLER void hist_begin(ChainSmem& S) {
+__device__ OADG_HANDLER void hist_begin(unsigned* hist) {
   __syncthreads();
-  if (threadIdx.x == 0) S.bs_key = -1;   // u.hist overwrites the staged profile slices
-  for (int i = threadIdx.x; i < 2 * 768; i += kCT) (&S.u.hist[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < 2 * 768; i += kCT) hist[i] = 0;
   __syncthreads();
 }
-__device__ OADG_HANDLER void hist_flush(const ChainArgs& A, ChainSmem& S, int slot, unsigned long long& lsum) {
+__device__ OADG_HANDLER void hist_flush(const ChainArgs& A, const unsigned* hist, int slot, unsigned long long& lsum) {
   __syncthreads();
   unsigned* dst = A.hist + (size_t)slot * 768;
   for (int i = threadIdx.x; i < 768; i += kCT) {
     unsigned s = 0;
 #pragma unroll
-    for (int w = 0; w < 2; ++w) s += S.u.hist[w][i];
+    for (int w = 0; w < 2; ++w) s += hist[w * 768 + i];
     if (s) atomicAdd(dst + i, s);
   }
   lsum = warp_sum(lsum);
@@ -384,7 +403,6 @@ __device__ OADG_HANDLER void hist_flush(const ChainArgs& A, ChainSmem& S, int sl
   lsum = 0;
   __syncthreads();
 }
-
 // one LUT op: PIL.ImageOps autocontrast / equalize from the finished histogram, or a closed-form table
 __device__ OADG_HANDLER void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
   const LutJob J = A.lutjobs[job];
@@ -482,15 +500,12 @@ __device__ OADG_HANDLER void copy_segment(const Chain& C, size_t nbytes, bool bo
     }
   }
 }
-
 // ---- staged affine gathers ---------------------------------------------------------------------------------
 // Both geometric op families (bboxes-only blends and bg-only ops) resample a frame through cv::warpAffine's
 // fixed-point bilinear map.  A CTA works on sub-tiles of 64 x 16 output pixels: the source rectangle the sub-tile
 // reads (exact: the map is monotone in x and in y, so its extremes sit at the sub-tile corners) is copied into
 // shared memory with 16-byte vector loads of whole row spans, then every thread resamples 4 consecutive pixels
 // from shared memory and writes 12 bytes.  Out-of-frame taps read 0 (BORDER_CONSTANT).
-constexpr int kSubW = 64, kSubH = 16;
-constexpr int kDynSmem = 30 * 1024;
 
 struct StageView {
   const uint8_t* sm;   // staged rows: row r holds the 16-byte aligned global span that covers source row by0 + r
@@ -631,7 +646,6 @@ __device__ __forceinline__ void load12(const uint8_t* p, bool vec, int n, uint32
   }
 }
 __device__ __forceinline__ int byte_of(const uint32_t w[3], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 255u); }
-
 // ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
 __device__ OADG_HANDLER void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
   __syncthreads();
@@ -640,7 +654,6 @@ __device__ OADG_HANDLER void bbo_stage(const ChainArgs& A, ChainSmem& S, const I
   __syncthreads();
   if (threadIdx.x == 0) {
     S.bs_key = key;
-    S.prof_ready = 0;
     const BboJob J = A.bjobs[I.obj];
     const Chain C = A.chains[J.chain];
     const oadg_view_t& V = A.P.views[C.view];
@@ -654,15 +667,17 @@ __device__ OADG_HANDLER void bbo_stage(const ChainArgs& A, ChainSmem& S, const I
     const int level = catch_up ? J.level + 1 : J.level;   // a catch-up runs in the NEXT level's phase
     bs.X = chain_src(C, level);
     bs.Y = chain_dst(C, level);
+    bs.x_map = chain_src_map(C, level);
+    bs.pad = 0;
     bs.n_excl = catch_up ? J.next_count : 0;
     for (int k = 0; k < bs.n_excl && k < 16; ++k)
       for (int e = 0; e < 4; ++e) bs.excl[k][e] = A.bjobs[J.next_first + k].rect[e];
   }
   __syncthreads();
 }
-// blend of one box: tiles [l0, l1) of 128 x 16 px; Y = uint8(X*(1-m) + warp(X)*m) inside the support
-__device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
-  bbo_stage(A, S, I, false);
+// blend of one box, frames WITHOUT a tensor map (row pitch not a multiple of 16 bytes): the source rows of every
+// sub-tile are staged by hand (16-byte vector loads) between two block barriers
+__device__ OADG_HANDLER void bbo_r_tile_hand(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int l0, int l1) {
   const BboStage& bs = S.bs;
   const int t = threadIdx.x;
   if (A.debug & 8) {   // reference path: the shared per-pixel body
@@ -678,14 +693,6 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
     return;
   }
   const int W = bs.W, H = bs.H;
-  const int w = bs.rect[2] - bs.rect[0], h = bs.rect[3] - bs.rect[1];
-  const bool prof_smem = w + h <= 3072;
-  if (prof_smem && !S.prof_ready) {
-    for (int i = t; i < w; i += kCT) S.u.prof[i] = A.prof_x[(size_t)bs.gt * A.P.max_w + bs.rect[0] + i];
-    for (int i = t; i < h; i += kCT) S.u.prof[w + i] = A.prof_y[(size_t)bs.gt * A.P.max_h + bs.rect[1] + i];
-    __syncthreads();
-    if (t == 0) S.prof_ready = 1;
-  }
   const bool vec = ((W * 3) & 3) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 3) == 0;
   const int ax0 = bs.rect[0] & ~3, tx = I.tx;
   constexpr int kSubPerTile = kBboTileW / kSubW;   // 64 x 16 sub-tiles per tile, each with its own staged source
@@ -699,7 +706,7 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
     int sr[4];
     const bool any_src = warp_src_rect(bs.minv, x0, ty0, x1, y1, W, H, sr);
     const StageView sv = make_view(dyn, bs.X, W, H, 3, sr);
-    const bool staged = any_src && (size_t)(sr[3] - sr[1]) * sv.pitch <= (size_t)kDynSmem && !(A.debug & 2);
+    const bool staged = any_src && (size_t)(sr[3] - sr[1]) * sv.pitch <= (size_t)kHandStage && !(A.debug & 2);
     // this thread's 4 pixels of the running image are requested before the staging barriers
     const int y = ty0 + (t >> 4), xg = tx0 + (t & 15) * 4;
     const bool active = !(y >= y1 || xg >= x1 || xg + 4 <= x0);
@@ -721,14 +728,14 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
     }
     __syncthreads();
     if (!active) continue;
-    const float uy = prof_smem ? S.u.prof[w + y - bs.rect[1]] : A.prof_y[(size_t)bs.gt * A.P.max_h + y];
+    const float uy = A.prof_y[(size_t)bs.gt * A.P.max_h + y];
     const WarpRowTerm rt = warp_row_term(bs.minv, y);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int x = xg + i;
       int v[3] = {byte_of(in_w, 3 * i), byte_of(in_w, 3 * i + 1), byte_of(in_w, 3 * i + 2)};
       if (x >= x0 && x < x1) {
-        const float ux = prof_smem ? S.u.prof[x - bs.rect[0]] : A.prof_x[(size_t)bs.gt * A.P.max_w + x];
+        const float ux = A.prof_x[(size_t)bs.gt * A.P.max_w + x];
         const float m = fmul(uy, ux);
         // m <= 2^-25: fl(1 - m) == 1 and fl(1 - 1) == 0, so img*1 + aug*0 == img exactly
         if (m > 2.98023223876953125e-8f) {
@@ -758,6 +765,165 @@ __device__ OADG_HANDLER void bbo_r_segment(const ChainArgs& A, ChainSmem& S, uin
           for (int c = 0; c < 3; ++c) bs.Y[o + 3 * i + c] = (uint8_t)byte_of(out_w, 3 * i + c);
     }
   }
+}
+
+// ---- TMA-staged affine gathers ------------------------------------------------------------------------------
+// The source rectangle of a sub-tile (64 x 16 output pixels) is at most 85 px x 48 rows for every map the reference
+// can draw (rotations up to 30 degrees, shears up to 0.3, translations): thread 0 computes it from the four corners
+// (cv2's fixed-point map is monotone in x and in y) and issues up to three 16-row TMA boxes per plane into one of two
+// stages; parts of a box outside the frame arrive as zeros (BORDER_CONSTANT 0), so the taps need no bounds tests.
+// TMA needs 16-byte aligned box columns: the box starts at the byte column of the rectangle rounded down.
+// S.gather_rect[stage] = {first staged byte column of the frame, source y0, rows, first staged column of the mask}:
+// rows > 0 staged; 0 the rectangle misses the frame (every tap is 0); < 0 the rectangle exceeds the stage (the
+// sub-tile then gathers from global memory).
+__device__ __forceinline__ void gather_issue(ChainSmem& S, uint8_t* dyn, unsigned stage, const void* img_map,
+                                             const void* mask_map, const double* minv, int x0, int y0, int x1, int y1,
+                                             int W, int H) {
+  int sxa = 1 << 30, sxb = -(1 << 30), sya = 1 << 30, syb = -(1 << 30);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int sx, sy, fx, fy;
+    warp_coord(minv, (k & 1) ? x1 - 1 : x0, (k & 2) ? y1 - 1 : y0, sx, sy, fx, fy);
+    sxa = imin(sxa, sx); sxb = imax(sxb, sx);
+    sya = imin(sya, sy); syb = imax(syb, sy);
+  }
+  const int rows = syb + 2 - sya, wpx = sxb + 2 - sxa;
+  const bool ok = rows <= kMaxSrcRows && wpx <= kMaxSrcPx && sxa > -32768 && sxb < 32767 && sya > -32768 && syb < 32767;
+  const bool inside = sxa < W && sxa + wpx > 0 && sya < H && sya + rows > 0;
+  int* r = S.gather_rect[stage];
+  const int xb = (3 * sxa) & ~15, xm = sxa & ~15;
+  r[0] = xb;
+  r[1] = sya;
+  r[2] = !ok ? -1 : (inside ? rows : 0);
+  r[3] = xm;
+  uint64_t* bar = &S.full[stage];
+  if (ok && inside) {
+    const int nb = (rows + kGatherBoxRows - 1) / kGatherBoxRows;
+    uint8_t* img = dyn + stage * kStageBytes;
+    uint8_t* msk = img + kStageImgBytes;
+    tma::mbar_expect_tx(bar, (uint32_t)nb * (uint32_t)(kGatherBoxRows * (kGatherImgBoxBytes + (mask_map ? kGatherMaskBoxBytes : 0))));
+    for (int b = 0; b < nb; ++b) {
+      tma::load_2d(img + b * (kGatherBoxRows * kGatherImgBoxBytes), img_map, bar, xb, sya + b * kGatherBoxRows);
+      if (mask_map)
+        tma::load_2d(msk + b * (kGatherBoxRows * kGatherMaskBoxBytes), mask_map, bar, xm, sya + b * kGatherBoxRows);
+    }
+  } else {
+    tma::mbar_arrive(bar);
+  }
+}
+// taps of one pixel from a staged frame rectangle: 12 byte loads, no bounds tests
+__device__ __forceinline__ void tma_fetch3(const uint8_t* st, int xb, int ry0, int sx, int sy, int fx, int fy, int out[3]) {
+  const uint8_t* p = st + (sy - ry0) * kGatherImgBoxBytes + (sx * 3 - xb);
+  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    out[c] = ((int)p[c] * w00 + (int)p[3 + c] * w01 + (int)p[kGatherImgBoxBytes + c] * w10 +
+              (int)p[kGatherImgBoxBytes + 3 + c] * w11 + (1 << 14)) >> 15;
+}
+__device__ __forceinline__ int tma_fetch1(const uint8_t* st, int xm, int ry0, int sx, int sy, int fx, int fy) {
+  const uint8_t* p = st + (sy - ry0) * kGatherMaskBoxBytes + (sx - xm);
+  return bilerp_fix(p[0], p[1], p[kGatherMaskBoxBytes], p[kGatherMaskBoxBytes + 1], fx, fy);
+}
+__device__ __forceinline__ void col_coord(WarpRowTerm r, int2 cd, int& sx, int& sy, int& fx, int& fy) {
+  const int X = (r.X0 + cd.x) >> 5, Y = (r.Y0 + cd.y) >> 5;
+  sx = X >> 5;
+  sy = Y >> 5;
+  fx = X & 31;
+  fy = Y & 31;
+}
+
+// blend of one box, one tile of 256 x 16 px: Y = uint8(X*(1-m) + warp(X)*m) inside the support
+// (bbox_augmentation.py:57-71).  Returns the advanced gather-stage counter.
+__device__ OADG_HANDLER unsigned bbo_r_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Item& I, int local,
+                                            unsigned n_stage) {
+  bbo_stage(A, S, I, false);
+  const BboStage& bs = S.bs;
+  if (bs.x_map < 0 || (A.debug & (2 | 8 | 32))) {
+    bbo_r_tile_hand(A, S, dyn, I, local, local + 1);
+    return n_stage;
+  }
+  const int t = threadIdx.x, W = bs.W, H = bs.H;
+  const int tile_x0 = (bs.rect[0] & ~3) + (local % I.tx) * kBboTileW, ty0 = bs.rect[1] + (local / I.tx) * kBboTileH;
+  const int tile_x1 = imin(tile_x0 + kBboTileW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
+  const int nsub = (tile_x1 - tile_x0 + kSubW - 1) / kSubW;
+  int2* col = reinterpret_cast<int2*>(dyn + kColOff);
+  float* uxs = reinterpret_cast<float*>(dyn + kUxOff);
+  for (int c = t; c < tile_x1 - tile_x0; c += kCT) {   // per column: cv2's adelta / bdelta and the box's x-profile
+    const int x = tile_x0 + c;
+    col[c] = make_int2(cv_round(dmul(dmul(bs.minv[0], (double)x), 1024.0)), cv_round(dmul(dmul(bs.minv[3], (double)x), 1024.0)));
+    uxs[c] = x >= bs.rect[0] ? A.prof_x[(size_t)bs.gt * A.P.max_w + x] : 0.f;
+  }
+  const void* map = static_cast<const char*>(A.maps) + (size_t)bs.x_map * kTensorMapBytes;
+  if (t == 0) {
+    tma::fence_tensormap_acquire(map);
+    tma::fence_proxy_async();
+    gather_issue(S, dyn, n_stage & 1u, map, nullptr, bs.minv, imax(tile_x0, bs.rect[0]), ty0, imin(tile_x0 + kSubW, tile_x1),
+                 y1, W, H);
+  }
+  const int y = ty0 + (t >> 4);
+  const bool row_ok = y < y1;
+  const float uy = row_ok ? A.prof_y[(size_t)bs.gt * A.P.max_h + y] : 0.f;
+  const WarpRowTerm rt = warp_row_term(bs.minv, y);
+  __syncthreads();   // the column tables are in place
+  for (int s = 0; s < nsub; ++s, ++n_stage) {
+    const int sx0 = tile_x0 + s * kSubW;
+    const int x0 = imax(sx0, bs.rect[0]), x1 = imin(sx0 + kSubW, tile_x1);
+    if (t == 0 && s + 1 < nsub)
+      gather_issue(S, dyn, (n_stage + 1) & 1u, map, nullptr, bs.minv, sx0 + kSubW, ty0, imin(sx0 + 2 * kSubW, tile_x1), y1, W, H);
+    // this thread's 4 pixels of the running image are requested before it waits for the staged rows
+    const int xg = sx0 + (t & 15) * 4;
+    const bool active = row_ok && xg < x1 && xg + 4 > x0;
+    const bool full = xg >= x0 && xg + 4 <= x1;
+    const size_t o = ((size_t)y * W + xg) * 3;
+    uint32_t in_w[3] = {0u, 0u, 0u}, out_w[3] = {0u, 0u, 0u};
+    if (active) {
+      if (full) load12(bs.X + o, true, 4, in_w);
+      else
+        for (int i = 0; i < 4; ++i)
+          if (xg + i >= x0 && xg + i < x1)
+            for (int c = 0; c < 3; ++c) in_w[(3 * i + c) >> 2] |= (uint32_t)bs.X[o + 3 * i + c] << (((3 * i + c) & 3) * 8);
+    }
+    tma::mbar_wait(&S.full[n_stage & 1u], (n_stage >> 1) & 1u);
+    if (active) {
+      const int* gr = S.gather_rect[n_stage & 1u];
+      const int rx0 = gr[0], ry0 = gr[1], rows = gr[2];
+      const uint8_t* st = dyn + (n_stage & 1u) * kStageBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = xg + i;
+        int v[3] = {byte_of(in_w, 3 * i), byte_of(in_w, 3 * i + 1), byte_of(in_w, 3 * i + 2)};
+        if (x >= x0 && x < x1) {
+          const float m = fmul(uy, uxs[x - tile_x0]);
+          // m <= 2^-25: fl(1 - m) == 1 and fl(1 - 1) == 0, so img*1 + aug*0 == img exactly
+          if (m > 2.98023223876953125e-8f) {
+            int sx, sy, fx, fy, a[3];
+            col_coord(rt, col[x - tile_x0], sx, sy, fx, fy);
+            if (rows > 0) tma_fetch3(st, rx0, ry0, sx, sy, fx, fy, a);
+            else if (rows == 0) a[0] = a[1] = a[2] = 0;
+            else {
+              WarpTap tp;
+              tp.sx = imin(imax(sx, -32768), 32767); tp.sy = imin(imax(sy, -32768), 32767); tp.fx = fx; tp.fy = fy;
+              warp_fetch3(LdRW(), bs.X, H, W, tp, a);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = bbo_blend(m, v[c], a[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)v[c] << (((3 * i + c) & 3) * 8);
+      }
+      if (full) {
+        uint32_t* q = reinterpret_cast<uint32_t*>(bs.Y + o);
+        q[0] = out_w[0]; q[1] = out_w[1]; q[2] = out_w[2];
+      } else {
+        for (int i = 0; i < 4; ++i)
+          if (xg + i >= x0 && xg + i < x1)
+            for (int c = 0; c < 3; ++c) bs.Y[o + 3 * i + c] = (uint8_t)byte_of(out_w, 3 * i + c);
+      }
+    }
+    __syncthreads();   // the stage (and its rectangle record) may be refilled
+  }
+  return n_stage;
 }
 // catch-up copy of a level l-1 support into the frame level l writes, minus the supports level l rewrites
 __device__ OADG_HANDLER void bbo_c_segment(const ChainArgs& A, ChainSmem& S, const Item& I, int l0, int l1) {
@@ -808,7 +974,6 @@ __device__ OADG_HANDLER void bbo_c_segment(const ChainArgs& A, ChainSmem& S, con
     }
   }
 }
-
 // one pixel of a bg-only op with hoisted coordinate terms (same arithmetic as bg_pixel / eval_op)
 __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, const RegOp& R, int ax, int bx,
                                               const double* div255, int x, int y) {
@@ -832,7 +997,7 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
                             (y1 && x1) ? ldb(r1 + 1) : 0, t.fx, t.fy);
   const size_t o = ((size_t)y * L.W + x) * 3;
   if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
-    const double am = __ldg(div255 + wm);  // wm / 255 in float64, tabulated (exactly the reference's quotient)
+    const double am = div255[wm];  // wm / 255 in float64, tabulated (exactly the reference's quotient)
     const double keep = (double)M > am ? (double)M : am;
     const double rest = dsub(1.0, keep);
 #pragma unroll
@@ -844,7 +1009,6 @@ __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, c
   q[1] = (uint8_t)px[1];
   q[2] = (uint8_t)px[2];
 }
-
 // bg-only op (bbox_augmentation.py:240-272) on a sub-tile of 64 x 16 px that one region covers: the frame and the
 // uint8 union mask are both warped from staged shared-memory rows; 4 pixels per thread.
 __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, const Lane& L, const RegOp& R,
@@ -855,7 +1019,7 @@ __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, ChainSmem& S, uint8_
   const bool any_src = warp_src_rect(R.minv, x0, y0, x1, y1, W, H, sr);
   const int pitch_i = any_src ? stage_pitch(sr[0], sr[2], 3) : 0, pitch_m = any_src ? stage_pitch(sr[0], sr[2], 1) : 0;
   const int rows = any_src ? sr[3] - sr[1] : 0;
-  const bool staged = any_src && (size_t)rows * (pitch_i + pitch_m) <= (size_t)kDynSmem;
+  const bool staged = any_src && (size_t)rows * (pitch_i + pitch_m) <= (size_t)kHandStage;
   const uint8_t* mu = P.masku + (size_t)L.view * P.mask_stride;
   const StageView si = make_view(dyn, L.in, W, H, 3, sr);
   const StageView sm = make_view(dyn + (size_t)rows * pitch_i, mu, W, H, 1, sr);
@@ -917,7 +1081,7 @@ __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, ChainSmem& S, uint8_
       }
       const float M = Mv[i];
       if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
-        const double am = __ldg(div255 + wm);  // wm / 255 in float64, tabulated (exactly the reference's quotient)
+        const double am = div255[wm];  // wm / 255 in float64, tabulated (exactly the reference's quotient)
         const double keep = (double)M > am ? (double)M : am;
         const double rest = dsub(1.0, keep);
 #pragma unroll
@@ -937,7 +1101,6 @@ __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, ChainSmem& S, uint8_
         for (int c = 0; c < 3; ++c) L.out[o + 3 * i + c] = (uint8_t)byte_of(out_w, 3 * i + c);
   }
 }
-
 // one pixel of a non-bg op from the staged lane record, region op and LUTs (same arithmetic as eval_op, oamix_body.h)
 __device__ __forceinline__ void pixel_op_fast(const ChainArgs& A, const Lane& L, const RegOp& R, const uint8_t* luts,
                                               int r, int x, int y) {
@@ -982,92 +1145,188 @@ __device__ __forceinline__ void pixel_op_fast(const ChainArgs& A, const Lane& L,
 }
 
 // ------------------------------------------------------------------------------------
-// one 256 x 16 tile of one depth step of one lane (oa_mix.py:226-234).  Runs of 16 pixels that one table-lookup /
-// bbo-copy region covers move as three 16-byte vectors per thread (LUTs in shared memory); everything else (bg-only
-// gathers, invert / colour / sharpness, runs cut by a multi-level box edge) is evaluated per pixel with consecutive
-// lanes on consecutive pixels (run_is_stream, oamix_tile.h, decides which pass owns a run).
+// one tile (512 or 256 x 16 px) of one depth step of one lane (oa_mix.py:226-234), handled per 64 x 16 sub-tile:
+//   STREAM  one table-lookup / bbo-copy region covers the sub-tile: 16-pixel runs move as three 16-byte vectors per
+//           thread through the LUTs in shared memory;
+//   BG      one bg-only region covers it (bbox_augmentation.py:240-272): frame and uint8 union mask are resampled
+//           from TMA-staged rows (gather_issue), 4 pixels per thread, float64 blend;
+//   PIXEL   everything else (a multi-level box edge crosses it, or invert / colour / sharpness): per pixel.
+// Returns the advanced gather-stage counter.
 // ------------------------------------------------------------------------------------
-__device__ OADG_HANDLER void step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int local, int tx, int tw,
-                                       const double* div255) {
+enum { kSubStream = 0, kSubBg = 1, kSubPixel = 2 };
+
+__device__ OADG_HANDLER unsigned step_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int local, int tx, int tw,
+                                           unsigned n_stage) {
   const Lane& L = S.lane;
   const int W = L.W, H = L.H, t = threadIdx.x;
   const int x0 = (local % tx) * tw, y0 = (local / tx) * kStepTileH;
   const int x1 = min(x0 + tw, W), y1 = min(y0 + kStepTileH, H);
-  const int region = tile_region(L, x0, y0, x1, y1);
-  const bool tile_stream = region >= 0 && kind_streams(L.kind[region]);
-  const bool tile_pixel = region >= 0 && !tile_stream;
-  if (t == 0) S.step_class = tile_stream ? 7 : ((tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) ? 8 : 9);
-  const bool staged_bg = !(A.debug & 1);
-  if (!tile_stream && staged_bg) {
-    // bg-only regions of the tile: staged gathers, sub-tile by sub-tile (a mixed tile filters by region per pixel)
+  const int nsub = (x1 - x0 + kSubW - 1) / kSubW;
+  __syncthreads();   // the previous tile is done with the sub-tile classes and the column table
+  if (t < nsub) {
+    const int sx0 = x0 + t * kSubW, sx1 = min(sx0 + kSubW, x1);
+    const int region = tile_region(L, sx0, y0, sx1, y1);
+    int cls = kSubPixel;
+    if (region >= 0) {
+      const int kind = S.rop[region].kind;
+      if (kind_streams(kind)) cls = kSubStream | region << 4;
+      else if (kind == OADG_OP_BG_AFFINE && !(A.debug & 1)) cls = kSubBg | region << 4;
+    }
+    S.sub_cls[t] = cls;
+  }
+  __syncthreads();
+  bool any_bg = false, any_pixel = false;
+  for (int s = 0; s < nsub; ++s) {
+    any_bg |= (S.sub_cls[s] & 15) == kSubBg;
+    any_pixel |= (S.sub_cls[s] & 15) == kSubPixel;
+  }
+  if (t == 0) S.step_class = any_pixel ? 9 : (any_bg ? 8 : 7);
+  const bool use_tma = L.in_map >= 0 && L.mask_map >= 0 && !(A.debug & 32);
+  if (any_bg) {
+    const uint8_t* mu = A.P.masku + (size_t)L.view * A.P.mask_stride;
+    const float* mf = A.P.maskf + (size_t)L.view * A.P.mask_stride;
     for (int r = 0; r <= L.n_ml; ++r) {
       if (S.rop[r].kind != OADG_OP_BG_AFFINE) continue;
-      if (tile_pixel && r != region) continue;
-      for (int sy0 = y0; sy0 < y1; sy0 += kSubH)
-        for (int sx0 = x0; sx0 < x1; sx0 += kSubW) {
-          const int sx1 = min(sx0 + kSubW, x1), sy1 = min(sy0 + kSubH, y1);
-          if (!tile_pixel) {  // skip sub-tiles that hold no pixel of region r
-            const int sub = tile_region(L, sx0, sy0, sx1, sy1);
-            if (sub >= 0 && sub != r) continue;
-            if (r < L.n_ml && !rect_hit(L.box[r], sx0, sy0, sx1, sy1)) continue;
-          }
-          bg_subtile(A, S, dyn, L, S.rop[r], tile_pixel ? -1 : r, sx0, sy0, sx1, sy1, div255);
-        }
-    }
-    if (tile_pixel && S.rop[region].kind == OADG_OP_BG_AFFINE) return;
-  }
-  if (!tile_pixel) {
-    for (int x = x0 + (t & 15) * kChunkPx; x < x1; x += 16 * kChunkPx)
-    for (int y = y0 + (t >> 4); y < y1; y += 16) {
-      const int n = min(kChunkPx, W - x);
-      int reg;
-      if (run_is_stream(L, x, y, n, reg)) {
-        const bool vec = ((W * 3) & 15) == 0 &&
-                         ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)A.scratch) | A.frame_bytes) & 15) == 0;
-        if (reg >= 0 && kind_streams(L.kind[reg]) && vec && n == kChunkPx) {
-          Chunk c;
-          chunk_load(stream_src(L, reg, A.scratch, A.frame_bytes) + ((size_t)y * W + x) * 3, n, vec, c);
-          stream_chunk(L, reg, S.lut + reg * 768, A.scratch, A.frame_bytes, c, x, y, n, vec);
-        } else {
-          for (int i = 0; i < n; ++i) {
-            const int rr = region_of_pixel(L, x + i, y);
-            pixel_op_fast(A, L, S.rop[rr], S.lut, rr, x + i, y);
-          }
-        }
+      const int want = kSubBg | r << 4;
+      int first = -1;
+      for (int s = nsub - 1; s >= 0; --s)
+        if (S.sub_cls[s] == want) first = s;
+      if (first < 0) continue;
+      const RegOp& R = S.rop[r];
+      if (!use_tma) {   // frames without a tensor map: hand-staged rows
+        for (int s = first; s < nsub; ++s)
+          if (S.sub_cls[s] == want)
+            bg_subtile(A, S, dyn, L, R, -1, x0 + s * kSubW, y0, min(x0 + (s + 1) * kSubW, x1), y1, S.div255);
+        continue;
       }
-    }
-  }
-  if (!tile_stream && !L.all_streaming) {
-    for (int x = x0 + (t & 255); x < x1; x += 256) {  // this thread's columns
-    const int xc = x & ~(kChunkPx - 1), nc = min(kChunkPx, W - xc);  // the 16-pixel run this column belongs to
-    int ax[OADG_MAX_REGIONS], bx[OADG_MAX_REGIONS];
+      int2* col = reinterpret_cast<int2*>(dyn + kColOff);
+      for (int c = t; c < x1 - x0; c += kCT)
+        col[c] = make_int2(cv_round(dmul(dmul(R.minv[0], (double)(x0 + c)), 1024.0)),
+                           cv_round(dmul(dmul(R.minv[3], (double)(x0 + c)), 1024.0)));
+      const void* imap = static_cast<const char*>(A.maps) + (size_t)L.in_map * kTensorMapBytes;
+      const void* mmap = static_cast<const char*>(A.maps) + (size_t)L.mask_map * kTensorMapBytes;
+      if (t == 0) {
+        tma::fence_tensormap_acquire(imap);
+        tma::fence_tensormap_acquire(mmap);
+        tma::fence_proxy_async();
+        gather_issue(S, dyn, n_stage & 1u, imap, mmap, R.minv, x0 + first * kSubW, y0, min(x0 + (first + 1) * kSubW, x1), y1, W, H);
+      }
+      const int y = y0 + (t >> 4);
+      const bool row_ok = y < y1;
+      const WarpRowTerm rt = warp_row_term(R.minv, y);
+      __syncthreads();   // the column table is in place
+      for (int s = first; s >= 0;) {
+        int nxt = -1;
+        for (int k = nsub - 1; k > s; --k)
+          if (S.sub_cls[k] == want) nxt = k;
+        const int sx0 = x0 + s * kSubW, sx1 = min(sx0 + kSubW, x1);
+        if (t == 0 && nxt >= 0)
+          gather_issue(S, dyn, (n_stage + 1) & 1u, imap, mmap, R.minv, x0 + nxt * kSubW, y0, min(x0 + (nxt + 1) * kSubW, x1), y1, W, H);
+        // this thread's 4 pixels: the frame bytes and the float mask are requested before it waits for the staged rows
+        const int xg = sx0 + (t & 15) * 4;
+        const bool active = row_ok && xg < sx1;
+        const int n = active ? imin(4, sx1 - xg) : 0;
+        const size_t o = ((size_t)y * W + xg) * 3;
+        uint32_t in_w[3] = {0u, 0u, 0u}, out_w[3] = {0u, 0u, 0u};
+        float Mv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (active) {
+          load12(L.in + o, n == 4, n, in_w);
+          const float* mp = mf + (size_t)y * W + xg;
+          if (n == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(mp);
+            Mv[0] = q.x; Mv[1] = q.y; Mv[2] = q.z; Mv[3] = q.w;
+          } else {
+            for (int i = 0; i < n; ++i) Mv[i] = mp[i];
+          }
+        }
+        tma::mbar_wait(&S.full[n_stage & 1u], (n_stage >> 1) & 1u);
+        if (active) {
+          const int* gr = S.gather_rect[n_stage & 1u];
+          const int rx0 = gr[0], ry0 = gr[1], rows = gr[2], xm = gr[3];
+          const uint8_t* st = dyn + (n_stage & 1u) * kStageBytes;
 #pragma unroll
-    for (int r = 0; r < OADG_MAX_REGIONS; ++r) {
-      ax[r] = bx[r] = 0;
-      if (r <= L.n_ml && S.rop[r].kind == OADG_OP_BG_AFFINE) {
-        ax[r] = cv_round(dmul(dmul(S.rop[r].minv[0], (double)x), 1024.0));
-        bx[r] = cv_round(dmul(dmul(S.rop[r].minv[3], (double)x), 1024.0));
+          for (int i = 0; i < 4; ++i) {
+            int px[3] = {0, 0, 0};
+            if (i < n) {
+              int sx, sy, fx, fy, wm = 0;
+              col_coord(rt, col[xg + i - x0], sx, sy, fx, fy);
+              if (rows > 0) {
+                tma_fetch3(st, rx0, ry0, sx, sy, fx, fy, px);
+                wm = tma_fetch1(st + kStageImgBytes, xm, ry0, sx, sy, fx, fy);
+              } else if (rows < 0) {
+                WarpTap tp;
+                tp.sx = imin(imax(sx, -32768), 32767); tp.sy = imin(imax(sy, -32768), 32767); tp.fx = fx; tp.fy = fy;
+                warp_fetch3(LdRO(), L.in, H, W, tp, px);
+                const bool bx0 = (unsigned)tp.sx < (unsigned)W, bx1 = fx != 0 && (unsigned)(tp.sx + 1) < (unsigned)W;
+                const bool by0 = (unsigned)tp.sy < (unsigned)H, by1 = fy != 0 && (unsigned)(tp.sy + 1) < (unsigned)H;
+                const uint8_t* r0 = mu + (size_t)tp.sy * W + tp.sx;
+                const uint8_t* r1 = r0 + W;
+                wm = bilerp_fix((by0 && bx0) ? ldb(r0) : 0, (by0 && bx1) ? ldb(r0 + 1) : 0, (by1 && bx0) ? ldb(r1) : 0,
+                                (by1 && bx1) ? ldb(r1 + 1) : 0, fx, fy);
+              }
+              const float M = Mv[i];
+              if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
+                const double am = S.div255[wm];  // wm / 255 in float64, tabulated (exactly the reference's quotient)
+                const double keep = (double)M > am ? (double)M : am;
+                const double rest = dsub(1.0, keep);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                  px[c] = (int)dadd(dmul(keep, (double)byte_of(in_w, 3 * i + c)), dmul(rest, (double)px[c]));
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)px[c] << (((3 * i + c) & 3) * 8);
+          }
+          if (n == 4) {
+            uint32_t* q = reinterpret_cast<uint32_t*>(L.out + o);
+            q[0] = out_w[0]; q[1] = out_w[1]; q[2] = out_w[2];
+          } else {
+            for (int k = 0; k < 3 * n; ++k) L.out[o + k] = (uint8_t)byte_of(out_w, k);
+          }
+        }
+        __syncthreads();   // the stage (and its rectangle record) may be refilled
+        ++n_stage;
+        s = nxt;
       }
-    }
-    const int yb = y0, ye = y1;
-#pragma unroll 1
-    for (int y = yb; y < ye; ++y) {
-      int run_region;
-      if (run_is_stream(L, xc, y, nc, run_region)) continue;  // the vector pass owns this run
-      const int r = region_of_pixel(L, x, y);
-      if (S.rop[r].kind == OADG_OP_BG_AFFINE) {
-        if (staged_bg) continue;  // done above from staged rows
-        const int axr = r == 0 ? ax[0] : (r == 1 ? ax[1] : ax[2]);
-        const int bxr = r == 0 ? bx[0] : (r == 1 ? bx[1] : bx[2]);
-        bg_pixel_fast(A.P, L, S.rop[r], axr, bxr, div255, x, y);
-      } else {
-        pixel_op_fast(A, L, S.rop[r], S.lut, r, x, y);
-      }
-    }
     }
   }
+  // table-lookup / bbo-copy sub-tiles: 16-pixel runs as vectors
+  const bool vec = ((W * 3) & 15) == 0 &&
+                   ((((uintptr_t)L.in) | ((uintptr_t)L.out) | ((uintptr_t)A.scratch) | A.frame_bytes) & 15) == 0;
+  for (int x = x0 + (t & 15) * kChunkPx; x < x1; x += 16 * kChunkPx) {
+    const int cls = S.sub_cls[(x - x0) / kSubW];
+    if ((cls & 15) != kSubStream) continue;
+    const int reg = cls >> 4;
+    const int n = min(kChunkPx, x1 - x);
+    for (int y = y0 + (t >> 4); y < y1; y += 16) {
+      if (vec && n == kChunkPx) {
+        Chunk c;
+        chunk_load(stream_src(L, reg, A.scratch, A.frame_bytes) + ((size_t)y * W + x) * 3, n, vec, c);
+        stream_chunk(L, reg, S.lut + reg * 768, A.scratch, A.frame_bytes, c, x, y, n, vec);
+      } else {
+        for (int i = 0; i < n; ++i) pixel_op_fast(A, L, S.rop[reg], S.lut, reg, x + i, y);
+      }
+    }
+  }
+  // everything else per pixel, consecutive lanes on consecutive pixels
+  if (any_pixel) {
+    for (int s = 0; s < nsub; ++s) {
+      if ((S.sub_cls[s] & 15) != kSubPixel) continue;
+      const int sx0 = x0 + s * kSubW;
+      for (int q = t; q < kSubW * kStepTileH; q += kCT) {
+        const int x = sx0 + (q & (kSubW - 1)), y = y0 + q / kSubW;
+        if (x >= x1 || y >= y1) continue;
+        const int r = region_of_pixel(L, x, y);
+        if (S.rop[r].kind == OADG_OP_BG_AFFINE)
+          bg_pixel_fast(A.P, L, S.rop[r], cv_round(dmul(dmul(S.rop[r].minv[0], (double)x), 1024.0)),
+                        cv_round(dmul(dmul(S.rop[r].minv[3], (double)x), 1024.0)), S.div255, x, y);
+        else
+          pixel_op_fast(A, L, S.rop[r], S.lut, r, x, y);
+      }
+    }
+  }
+  return n_stage;
 }
-
 // stage a lane record, its LUTs and its region ops in shared memory (once per lane a CTA works on)
 __device__ OADG_HANDLER void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
   const int t = threadIdx.x;
@@ -1094,27 +1353,31 @@ __device__ OADG_HANDLER void stage_lane(const ChainArgs& A, ChainSmem& S, int la
   __syncthreads();
 }
 
+// kStats: per-kind CTA time accounting with %globaltimer and global atomics (oadg_oamix_execute_profiled only; the
+// production instantiation carries none of it)
+template <bool kStats>
 __global__ void __launch_bounds__(kCT, kCtaPerSm)
-oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
+oamix_chain_kernel(const ChainArgs Aparam) {
   __shared__ ChainSmem S;
-  extern __shared__ __align__(16) uint8_t dyn[];   // kDynSmem bytes: staged source rows of the affine gathers
+  extern __shared__ __align__(128) uint8_t dyn[];   // kDynSmem bytes, see the layout above
   if (threadIdx.x == 0) {
     S.args = Aparam;
     S.bs_key = -1;
-    S.prof_ready = 0;
+    tma::mbar_init(&S.full[0], 1);
+    tma::mbar_init(&S.full[1], 1);
+    tma::mbar_fence_init();
   }
+  S.div255[threadIdx.x] = (double)threadIdx.x / 255.0;   // kCT == 256
   __syncthreads();
   const ChainArgs& A = S.args;
-  int staged_lane = -1, scan_from = 0, streak = 0;
-  const int kStickyTiles = A.debug >> 8;
-  if (threadIdx.x < kMaxQueueItems / 32) S.exhausted[threadIdx.x] = 0u;
-  __syncthreads();
+  int staged_lane = -1, cursor = 0;
+  unsigned n_stage = 0;   // gather stages used so far by this CTA (stage = n & 1, mbarrier parity = (n >> 1) & 1)
   if (threadIdx.x == 0) {
     int item = -1, tile = -1;
-    const unsigned long long w0 = globaltimer_ns();
-    S.epoch_seen = ld_relaxed_u32(A.epoch);
-    if (!scan_for_work(A, S.exhausted, scan_from, item, tile)) item = -1;
-    if (!(A.debug & 4)) atomicAdd(A.kind_ns + 10, globaltimer_ns() - w0);
+    unsigned long long w0 = 0;
+    if (kStats) w0 = globaltimer_ns();
+    if (!claim_work(A, cursor, item, tile)) item = -1;
+    if (kStats) atomicAdd(A.kind_ns + 10, globaltimer_ns() - w0);
     S.next_item = item;
     S.next_tile = tile;
   }
@@ -1123,59 +1386,46 @@ oamix_chain_kernel(const ChainArgs Aparam, const double* div255) {
   while (it >= 0) {
     __syncthreads();  // every thread has read S.next_item / S.next_tile
     const Item I = A.items[it];
-    unsigned claim = 0;
-    bool prefetched = false;
-    if (threadIdx.x == 0) {
-      // A CTA never claims ahead: a tile claimed while the previous one is still being processed sits idle at the
-      // end of an item, and the items of the critical path then finish one tile time later (measured over 24 bench
-      // batches: claim-ahead 17.2-18.2 ms, re-scan after every tile 15.0 ms).  OADG_DEBUG bits 8..: n > 1 = claim ahead
-      // for n - 1 consecutive tiles, then re-scan.
-      prefetched = kStickyTiles > 1 && (++streak % kStickyTiles) != 0;
-      if (prefetched) claim = atomicAdd(A.claimed + it, 1u);
-    }
-    const int l0 = I.perm_first >= 0 ? A.perm[I.perm_first + tile] : tile, l1 = l0 + 1;
-    const unsigned long long seg_t0 = globaltimer_ns();
+    const int local = I.perm_first >= 0 ? A.perm[I.perm_first + tile] : tile;
+    unsigned long long seg_t0 = 0;
+    if (kStats) seg_t0 = globaltimer_ns();
     switch (I.kind) {
-      case OADG_IT_PROFILE: profile_tile(A, S, I.obj); break;
-      case OADG_IT_MASK:
-        for (int k = l0; k < l1; ++k) mask_tile(A, S, I.obj, k, I.tx);
-        break;
+      case OADG_IT_PROFILE: profile_tile(A, S, dyn, I.obj); break;
+      case OADG_IT_MASK: mask_tile(A, S, I.obj, local, I.tx); break;
       case OADG_IT_HIST: {
         const Lane& L = A.lanes[I.obj];
         unsigned long long lsum = 0;
-        hist_begin(S);
-        for (int k = l0; k < l1; ++k) hist_tile(L, S, k, lsum);
-        hist_flush(A, S, L.hist_slot, lsum);
+        unsigned* hist = reinterpret_cast<unsigned*>(dyn);
+        hist_begin(hist);
+        hist_tile(L, hist, local, lsum);
+        hist_flush(A, hist, L.hist_slot, lsum);
         break;
       }
       case OADG_IT_LUT: lut_tile(A, S, I.obj); break;
       case OADG_IT_COPY: {
         const Chain& C = A.chains[I.obj];
         const oadg_view_t& V = A.P.views[C.view];
-        copy_segment(C, (size_t)V.H * V.W * 3, I.aux != 0, l0, l1);
+        copy_segment(C, (size_t)V.H * V.W * 3, I.aux != 0, local, local + 1);
         break;
       }
-      case OADG_IT_BBO_R: bbo_r_segment(A, S, dyn, I, l0, l1); break;
-      case OADG_IT_BBO_C: bbo_c_segment(A, S, I, l0, l1); break;
+      case OADG_IT_BBO_R: n_stage = bbo_r_tile(A, S, dyn, I, local, n_stage); break;
+      case OADG_IT_BBO_C: bbo_c_segment(A, S, I, local, local + 1); break;
       case OADG_IT_STEP:
         if (staged_lane != I.obj) {
           stage_lane(A, S, I.obj);
           staged_lane = I.obj;
         }
-        for (int k = l0; k < l1; ++k) step_tile(A, S, dyn, k, I.tx, I.aux, div255);
+        n_stage = step_tile(A, S, dyn, local, I.tx, I.aux, n_stage);
         break;
       default: break;
     }
     publish_tile(A, I);
     if (threadIdx.x == 0) {
-      const unsigned long long t1 = globaltimer_ns();
-      int item = it, nt = (int)claim;
-      if (!prefetched || claim >= (unsigned)I.ntiles) {   // look for the first ready item with tiles left
-        if (prefetched) S.exhausted[it >> 5] |= 1u << (it & 31);
-        S.epoch_seen = ld_relaxed_u32(A.epoch);
-        if (!scan_for_work(A, S.exhausted, scan_from, item, nt)) item = -1;
-      }
-      if (!(A.debug & 4)) {
+      unsigned long long t1 = 0;
+      if (kStats) t1 = globaltimer_ns();
+      int item = it, nt = -1;
+      if (!claim_work(A, cursor, item, nt)) item = -1;
+      if (kStats) {
         const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
         const unsigned long long dt = t1 - seg_t0;
         atomicAdd(A.kind_ns + kk, dt);
@@ -1217,12 +1467,49 @@ mix_kernel(DevPlan P, const MixJob* jobs) {
 #pragma unroll 1
   for (int y = y0 + (t >> 4); y < y1; y += 16) mix_chunk(P, J, T, x, y, n, vec);
 }
-
 #define BE_TRY(expr)                       \
   do {                                     \
     cudaError_t _e = (expr);               \
     if (_e != cudaSuccess) return (int)_e; \
   } while (0)
+
+// Plan + launch tables go up through a small ring of page-locked buffers (per calling thread): a copy from pageable
+// memory may make the host wait for the stream's earlier kernels, which would serialise the loader loop with the
+// GPU.  A slot also receives the launch's fault flag (a CTA gave up waiting for work: the dependency tables were
+// inconsistent); it is reused once everything that touches it has finished (event), and a raised flag is reported
+// by the next call that looks at the slot (or by oadg_oamix_poll_fault).
+struct PinSlot {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  unsigned* fault = nullptr;
+  int dev = -1;
+  bool busy = false;
+};
+constexpr int kPinSlots = 4;
+thread_local PinSlot g_pin[kPinSlots];
+thread_local int g_pin_next = 0;
+
+// collect the fault flags of finished launches (wait = true: of all launches of this thread); OADG_E_PLAN if any
+int poll_faults(bool wait) {
+  int rc = 0;
+  for (PinSlot& sl : g_pin) {
+    if (!sl.busy || !sl.ev) continue;
+    if (wait) {
+      BE_TRY(cudaEventSynchronize(sl.ev));
+    } else {
+      const cudaError_t q = cudaEventQuery(sl.ev);
+      if (q == cudaErrorNotReady) continue;
+      if (q != cudaSuccess) return (int)q;
+    }
+    sl.busy = false;
+    if (sl.fault && *sl.fault) {
+      *sl.fault = 0;
+      rc = OADG_E_PLAN;
+    }
+  }
+  return rc;
+}
 
 struct CudaBackend {
   cudaStream_t stream;
@@ -1234,8 +1521,10 @@ struct CudaBackend {
   int n_items = 0, n_tiles = 0;
   const unsigned long long* kind_ns_dev = nullptr;
   const unsigned long long* item_ts_dev = nullptr;
+  const unsigned* fault_dev = nullptr;
   std::vector<Item> items_host;
   std::vector<int32_t> deps_host;
+  PinSlot* slot = nullptr;
 
   int want_ctas = 0;   // oadg_oamix_execute_shared: resident CTAs per SM this launch may take (0 = all that fit)
   int grid() {
@@ -1249,9 +1538,12 @@ struct CudaBackend {
       ctas_per_sm = ctas_of_device[dev];
     } else {
       if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-      int nb = 0;
-      if (cudaFuncSetAttribute(oamix_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oamix_chain_kernel, kCT, kDynSmem) != cudaSuccess) return -1;
+      int nb = 0, nb2 = 0;
+      if (cudaFuncSetAttribute(oamix_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
+      if (cudaFuncSetAttribute(oamix_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oamix_chain_kernel<false>, kCT, kDynSmem) != cudaSuccess) return -1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, oamix_chain_kernel<true>, kCT, kDynSmem) != cudaSuccess) return -1;
+      nb = nb2 < nb ? nb2 : nb;
       ctas_per_sm = nb < 1 ? 0 : (nb > kCtaPerSm ? kCtaPerSm : nb);
       if (const char* e = getenv("OADG_CTAS_PER_SM")) {   // experiments
         const int want = atoi(e);
@@ -1266,28 +1558,35 @@ struct CudaBackend {
     const int c = (want_ctas >= 1 && want_ctas < ctas_per_sm) ? want_ctas : ctas_per_sm;
     return n_sm * c;
   }
-  // Plan + launch tables go up through a small ring of page-locked buffers (per calling thread): a copy from
-  // pageable memory may make the host wait for the stream's earlier kernels, which would serialise the loader
-  // loop with the GPU.  A slot is reused once the copy that read it has finished (event).
-  struct PinSlot {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaEvent_t ev = nullptr;
-    int dev = -1;
-  };
+  int make_map(void* dst, const void* base, size_t inner_bytes, int rows, int box_inner) {
+    if (getenv("OADG_NO_TMA")) return -1;
+    return tma::encode_u8_2d(dst, base, inner_bytes, (uint64_t)rows, inner_bytes, (uint32_t)box_inner, kGatherBoxRows);
+  }
   int upload(void* dst, const void* src, size_t bytes) {
-    static thread_local PinSlot ring[4];
-    static thread_local int next = 0;
-    PinSlot& sl = ring[next];
-    next = (next + 1) & 3;
+    int rc = poll_faults(false);
+    if (rc) return rc;
+    PinSlot& sl = g_pin[g_pin_next];
+    g_pin_next = (g_pin_next + 1) % kPinSlots;
     int dev = 0;
     BE_TRY(cudaGetDevice(&dev));
     if (sl.ev && sl.dev != dev) {
       cudaEventDestroy(sl.ev);
       sl.ev = nullptr;
+      sl.busy = false;
     }
-    if (sl.ev) BE_TRY(cudaEventSynchronize(sl.ev));
-    else BE_TRY(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    if (sl.ev && sl.busy) {
+      BE_TRY(cudaEventSynchronize(sl.ev));
+      sl.busy = false;
+      if (sl.fault && *sl.fault) {
+        *sl.fault = 0;
+        return OADG_E_PLAN;
+      }
+    }
+    if (!sl.ev) BE_TRY(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    if (!sl.fault) {
+      BE_TRY(cudaHostAlloc((void**)&sl.fault, 64, cudaHostAllocPortable));
+      *sl.fault = 0;
+    }
     sl.dev = dev;
     if (sl.cap < bytes) {
       if (sl.p) cudaFreeHost(sl.p);
@@ -1299,6 +1598,8 @@ struct CudaBackend {
     memcpy(sl.p, src, bytes);
     BE_TRY(cudaMemcpyAsync(dst, sl.p, bytes, cudaMemcpyHostToDevice, stream));
     BE_TRY(cudaEventRecord(sl.ev, stream));
+    sl.busy = true;
+    slot = &sl;
     return 0;
   }
   int zero(void* dst, size_t bytes) {
@@ -1306,8 +1607,7 @@ struct CudaBackend {
     return 0;
   }
   int chain(const ChainArgs& A, const ChainArgs& Hh, const PlanView&) {
-    const double* div255 = nullptr;
-    BE_TRY(cudaGetSymbolAddress((void**)&div255, g_div255));
+    fault_dev = A.fault;
     if (profile) {
       for (auto& e : ev) BE_TRY(cudaEventCreate(&e));
       BE_TRY(cudaEventRecord(ev[0], stream));
@@ -1323,11 +1623,15 @@ struct CudaBackend {
     if (A.n_tiles > 0) {
       ChainArgs args = A;
       if (const char* dbg = getenv("OADG_DEBUG")) args.debug = atoi(dbg);
-      void* params[2] = {(void*)&args, (void*)&div255};
-      // cooperative launch: all CTAs are guaranteed co-resident, which the in-kernel grid barrier relies on
-      BE_TRY(cudaLaunchCooperativeKernel((const void*)oamix_chain_kernel, dim3(A.grid), dim3(kCT), params, kDynSmem,
-                                         stream));
+      void* params[1] = {(void*)&args};
+      // cooperative launch: all CTAs are guaranteed co-resident, which the in-kernel dependency waits rely on
+      const void* fn = profile ? (const void*)oamix_chain_kernel<true> : (const void*)oamix_chain_kernel<false>;
+      BE_TRY(cudaLaunchCooperativeKernel(fn, dim3(A.grid), dim3(kCT), params, kDynSmem, stream));
       ++launches;
+      if (slot) {   // the launch's fault flag travels to the upload slot; the slot's event now covers it
+        BE_TRY(cudaMemcpyAsync(slot->fault, A.fault, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        BE_TRY(cudaEventRecord(slot->ev, stream));
+      }
     }
     if (profile) BE_TRY(cudaEventRecord(ev[1], stream));
     return 0;
@@ -1357,6 +1661,8 @@ extern "C" int oadg_oamix_workspace_bytes(const void* plan_host, size_t plan_byt
   *out_bytes = L.total;
   return 0;
 }
+
+extern "C" int oadg_oamix_poll_fault(int wait) { return poll_faults(wait != 0); }
 
 // measurement aid: the work queue of the last profiled execution on this workspace (kind, obj, tiles, first claim and
 // last publish in ns relative to the earliest claim, dependencies) -- filled by oadg_oamix_execute_profiled
@@ -1391,7 +1697,9 @@ extern "C" int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_by
     unsigned long long ks[48] = {0};
     if (be.kind_ns_dev) e = cudaMemcpy(ks, be.kind_ns_dev, sizeof(ks), cudaMemcpyDeviceToHost);
     if (kind_stats) memcpy(kind_stats, ks, sizeof(ks));
-    if (ks[15] != 0) rc = OADG_E_PLAN;   // a CTA gave up waiting: the dependency tables were inconsistent
+    unsigned fault = 0;
+    if (be.fault_dev) e = cudaMemcpy(&fault, be.fault_dev, sizeof(fault), cudaMemcpyDeviceToHost);
+    if (fault != 0) rc = OADG_E_PLAN;   // a CTA gave up waiting: the dependency tables were inconsistent
     if (getenv("OADG_TRACE") && be.item_ts_dev && be.n_items > 0) {
       std::vector<unsigned long long> ts((size_t)be.n_items * 2);
       cudaMemcpy(ts.data(), be.item_ts_dev, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);

@@ -40,6 +40,7 @@ struct Lane {            // one (view, branch) chain alive at the current depth
   int32_t lut[OADG_MAX_REGIONS];     // LUT slot of region r or -1
   int32_t scratch[OADG_MAX_REGIONS]; // bbo result frame slot of region r or -1
   int32_t all_streaming;             // every region runs a table-lookup / bbo-copy op: no pixel kernel needed
+  int32_t in_map, mask_map;          // tensor-map slots (TMA staging) of `in` and of the view's uint8 union mask, -1: none
 };
 
 struct Chain {           // one bboxes-only op being evaluated (bbox_augmentation.py:74-88)
@@ -47,6 +48,8 @@ struct Chain {           // one bboxes-only op being evaluated (bbox_augmentatio
   const uint8_t* in;     // the lane input the chain starts from (read-only source of level 1)
   uint8_t* S;            // ping-pong frames of the running image: level l reads X_l and writes Y_l with
   uint8_t* T;            //   Y_l = (l odd ? T : S),  X_l = (l == 1 ? in : (l odd ? S : T))
+  int32_t map_in, map_S, map_T;   // tensor-map slots of the three frames (-1: none, the blend stages its rows by hand)
+  int32_t pad;
 };
 
 struct BboJob {          // one needed box of one chain
@@ -58,6 +61,7 @@ struct BboJob {          // one needed box of one chain
 };
 OADG_HD const uint8_t* chain_src(const Chain& C, int level) { return level == 1 ? C.in : ((level & 1) ? C.S : C.T); }
 OADG_HD uint8_t* chain_dst(const Chain& C, int level) { return (level & 1) ? C.T : C.S; }
+OADG_HD int chain_src_map(const Chain& C, int level) { return level == 1 ? C.map_in : ((level & 1) ? C.map_S : C.map_T); }
 
 // ---- work items of the chain kernel ------------------------------------------------------------------------
 // The host turns a plan into a queue of work ITEMS cut into TILES (one CTA iteration each), ordered so that every item

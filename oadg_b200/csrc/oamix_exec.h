@@ -13,6 +13,13 @@
 namespace oadg {
 
 constexpr int kMagic = 0x4F414447;
+constexpr int kTensorMapBytes = 128;   // sizeof(CUtensorMap), 64-byte aligned in device memory
+// The ready ring (see oamix.cu): entry k = (ntiles << 32 | item) of the k-th item that became ready, ~0 while
+// unpublished; the first kRingHeader words are the header: [0] = number of published entries (the append cursor).
+constexpr int kRingHeader = 2;
+constexpr unsigned long long kRingEmpty = ~0ull;
+// geometry of a staged gather source (one sub-tile of 64 x 16 output pixels, oamix.cu): TMA boxes of 16 rows
+constexpr int kGatherBoxRows = 16, kGatherImgBoxBytes = 256, kGatherMaskBoxBytes = 96;
 
 inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -98,7 +105,7 @@ struct Layout {
   size_t zero_bytes;
   int any_bg;
   size_t tables_bytes;
-  int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_deps, max_perm, n_bbo;
+  int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_deps, max_perm, n_bbo, max_maps;
   size_t total;
 };
 
@@ -138,6 +145,11 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   L.max_items = 2 * h.n_gt + h.n_views + 2 * lanes_total + n_lut + n_chains + 2 * h.n_bbo + 8;
   L.max_deps = 8 * L.max_items + n_chains * 4 * max_chain * max_chain + 64;
   L.max_perm = lanes_total * (((h.max_w + kStepTileWPx - 1) / kStepTileWPx) * ((h.max_h + kStepTileH - 1) / kStepTileH)) + 16;
+  {  // tensor maps: source + union mask per view, two ping-pong frames per branch, two frames per chain
+    int wsum = 0;
+    for (int v = 0; v < h.n_views; ++v) wsum += pv.views[v].width;
+    L.max_maps = 2 * h.n_views + 2 * wsum + 2 * n_chains + 1;
+  }
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -152,7 +164,9 @@ inline void make_layout(const PlanView& pv, Layout& L) {
                    2 * align_up_sz((size_t)L.max_deps * sizeof(int32_t), 16) +
                    align_up_sz((size_t)L.max_items * sizeof(int32_t), 16) +
                    align_up_sz((size_t)L.max_perm * sizeof(int32_t), 16) +
-                   align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 256;
+                   align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) +
+                   align_up_sz((size_t)L.max_maps * kTensorMapBytes, 128) + 128 +
+                   align_up_sz((size_t)(L.max_items + kRingHeader) * sizeof(unsigned long long), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
   L.off_tables = align_up_sz((size_t)h.total_bytes, 16);
   L.off_plan = take(L.off_tables + L.tables_bytes);
@@ -303,6 +317,9 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   const uint8_t* scratch;
   size_t frame_bytes;
   unsigned long long* kind_ns;   // [16] CTA-busy ns per item kind, [16] tiles per kind, [16] longest tile (measurement aid)
+  const void* maps;              // tensor maps (kTensorMapBytes each) of the frames the affine gathers stage with TMA
+  unsigned long long* ring;      // ready ring: header + one entry per item (uploaded with the tables)
+  unsigned* fault;               // sticky: != 0 when a CTA gave up waiting for work (inconsistent dependency tables)
 };
 
 // Backend concept (all return 0 or an error code):
@@ -310,6 +327,7 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
 //   upload(dst, src_host, bytes)   zero(dst, bytes)
 //   chain(args, host_tables...)    the work-queue interpreter (one persistent launch on the device)
 //   mix(P, jobs, n)
+//   make_map(dst, base, inner_bytes, rows, box_inner)   encode a tensor map into dst (host staging), != 0: unavailable
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
                  uint8_t* const* dst, void* workspace, size_t workspace_bytes) {
@@ -370,6 +388,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const size_t t_pending = carve((size_t)L.max_items * sizeof(int32_t));
   const size_t t_perm = carve((size_t)L.max_perm * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
+  to = align_up_sz(to, 128);   // L.off_plan is 256-byte aligned: the maps are 128-byte aligned on the device too
+  const size_t t_maps = carve((size_t)L.max_maps * kTensorMapBytes);
+  const size_t t_ring = carve((size_t)(L.max_items + kRingHeader) * sizeof(unsigned long long));
   auto* lanes = reinterpret_cast<Lane*>(stage.data() + t_lanes);
   auto* lutjobs = reinterpret_cast<LutJob*>(stage.data() + t_lut);
   auto* chains = reinterpret_cast<Chain*>(stage.data() + t_chain);
@@ -380,6 +401,25 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   auto* pending = reinterpret_cast<int32_t*>(stage.data() + t_pending);
   auto* perm = reinterpret_cast<int32_t*>(stage.data() + t_perm);
   auto* mixjobs = reinterpret_cast<MixJob*>(stage.data() + t_mix);
+  auto* ring = reinterpret_cast<unsigned long long*>(stage.data() + t_ring);
+  // tensor maps by (frame, bytes per pixel): encoded once per distinct frame of this plan
+  struct MapKey {
+    const void* base;
+    int slot;
+  };
+  std::vector<MapKey> map_keys;
+  int n_maps = 0;
+  auto map_for = [&](const void* base, int W_px, int H_px, int bpp) -> int {
+    for (const MapKey& k : map_keys)
+      if (k.base == base) return k.slot;
+    int slot = -1;
+    if (n_maps < L.max_maps &&
+        be.make_map(stage.data() + t_maps + (size_t)n_maps * kTensorMapBytes, base, (size_t)W_px * bpp, H_px,
+                    bpp == 3 ? kGatherImgBoxBytes : kGatherMaskBoxBytes) == 0)
+      slot = n_maps++;
+    map_keys.push_back(MapKey{base, slot});
+    return slot;
+  };
 
   // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
   // `phase` (the length of the longest dependency chain below an item) only orders the work queue; what an item
@@ -445,6 +485,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
         ln.W = V.W;
         ln.n_ml = V.n_ml;
         ln.all_streaming = 1;
+        ln.in_map = ln.mask_map = -1;
         for (int q = 0; q < 2; ++q)
           for (int e = 0; e < 4; ++e) ln.box[q][e] = q < V.n_ml ? V.ml_box[q][e] : 0;
         for (int r = 0; r < OADG_MAX_REGIONS; ++r) ln.kind[r] = ln.lut[r] = ln.scratch[r] = -1;
@@ -497,6 +538,10 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
               c.in = ln.in;
               c.S = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(2 * c_id) * L.frame_bytes);
               c.T = reinterpret_cast<uint8_t*>(ws + L.off_scratch + (size_t)(2 * c_id + 1) * L.frame_bytes);
+              c.map_in = map_for(c.in, V.W, V.H, 3);
+              c.map_S = map_for(c.S, V.W, V.H, 3);
+              c.map_T = map_for(c.T, V.W, V.H, 3);
+              c.pad = 0;
               const int NL = cs.n_levels;
               op.scratch = 2 * c_id + (NL & 1);  // the step reads Y of the last level: T when NL is odd, else S
               // T (and S when a second level exists) start as copies of the lane input
@@ -550,6 +595,8 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
           } else if (op.kind == OADG_OP_BG_AFFINE) {
             step_at = mask_done > step_at ? mask_done : step_at;
             step_deps.push_back(mask_item[v]);
+            ln.in_map = map_for(ln.in, V.W, V.H, 3);
+            ln.mask_map = map_for(ws + L.off_masku + (size_t)v * h.max_h * h.max_w, V.W, V.H, 1);
           }
         }
         for (int r = 0; r <= V.n_ml; ++r) {
@@ -693,6 +740,15 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       }
   }
 
+  {  // ready ring: the items without dependencies, in queue (priority) order; the rest is appended on the device
+    unsigned long long n_ready = 0;
+    for (int k = 0; k < n_items + kRingHeader; ++k) ring[k] = kRingEmpty;
+    for (int k = 0; k < n_items; ++k)
+      if (pending[k] == 0) ring[kRingHeader + n_ready++] = ((unsigned long long)(unsigned)items[k].ntiles << 32) | (unsigned)k;
+    ring[0] = n_ready;
+    ring[1] = 0;
+  }
+
   for (int v = 0; v < h.n_views; ++v) {
     const oadg_view_t& V = pv.views[v];
     MixJob& J = mixjobs[v];
@@ -749,6 +805,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.frame_bytes = L.frame_bytes;
   A.debug = 0;
   A.kind_ns = reinterpret_cast<unsigned long long*>(ws + L.off_zero + 64);
+  A.fault = reinterpret_cast<unsigned*>(ws + L.off_zero + 16);
+  A.maps = dplan + t_maps;
+  A.ring = reinterpret_cast<unsigned long long*>(const_cast<char*>(dplan) + t_ring);
   // host views of the same tables (the host arithmetic check interprets them directly)
   ChainArgs Hh = A;
   Hh.lanes = lanes;
@@ -760,6 +819,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   Hh.succ = succ;
   Hh.perm = perm;
   Hh.pending = pending;
+  Hh.ring = ring;
   if ((rc = be.chain(A, Hh, pv))) return rc;
   return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);
 }

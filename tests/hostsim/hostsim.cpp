@@ -25,6 +25,7 @@ struct HostBackend {
   int grid() { return n_cta; }
   int upload(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
   int zero(void* dst, size_t bytes) { memset(dst, 0, bytes); return 0; }
+  int make_map(void*, const void*, size_t, int, int) { return -1; }   // no TMA on the host: the per-pixel bodies gather directly
 
   static void profile_item(const ChainArgs& A, int obj) {
     const DevPlan& P = A.P;
