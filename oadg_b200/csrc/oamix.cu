@@ -101,15 +101,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // ---- the work queue ---------------------------------------------------------------------------------------
-// Every item has a counter of claimed tiles and a counter of outstanding dependency tiles (`pending`, initialised by
-// the host).  The thread that publishes the last outstanding dependency tile of an item appends the item to the READY
-// RING (entries = ntiles << 32 | item, in order of readiness; the host pre-fills the items that start ready, in
-// priority order).  A CTA walks the ring from its private cursor: entries whose tiles are all claimed are skipped for
-// good, the first entry with an unclaimed tile yields a tile (one atomic), an unpublished entry means nothing else is
-// ready yet.  Publishing a tile is bar.sync + fence + one atomic per successor; a claimer reads the ring entry with an
-// acquire load and fences, and the CTA bar.syncs before touching the data.  All CTAs are co-resident (cooperative
-// launch) and a waiting CTA holds no tile, so the scheme cannot deadlock; a CTA that waits longer than 2 s raises the
-// sticky fault flag (the host turns it into OADG_E_PLAN) instead of hanging the GPU.
+// Every item has a counter of outstanding dependency tiles (`pending`, initialised by the host).  The CTA that
+// publishes the last outstanding dependency tile of an item makes the item READY: it reserves a range of TICKETS for
+// the item's tiles (one atomic on the publish cursor) and writes them (warp 0, one ticket per lane and round).  A CTA
+// that wants work takes the next ticket number (one atomic on the claim cursor) and reads tickets[T] with an acquire
+// load, waiting if that ticket is not published yet: tiles are handed out in the order in which their items became
+// ready, with two memory round trips per claim and no per-item hot spot.  Publishing a tile is bar.sync + fence by
+// thread 0, then one atomic per successor; the CTA bar.syncs before it touches a claimed tile's data.  All CTAs are
+// co-resident (cooperative launch) and a waiting CTA holds no unfinished tile, so the scheme cannot deadlock; a CTA
+// that waits longer than 2 s raises the sticky fault flag (the host turns it into OADG_E_PLAN) instead of hanging
+// the GPU.
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -118,62 +119,62 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
-// thread 0 only: find the next (item, tile); returns false when every item is exhausted (or the wait timed out)
-__device__ bool claim_work(const ChainArgs& A, int& cursor, int& item, int& tile) {
+// thread 0 only: the next (item, tile); returns false when every tile is handed out (or the wait timed out)
+__device__ bool claim_work(const ChainArgs& A, int& item, int& tile, bool stats) {
+  unsigned long long t_enter = 0;
+  if (stats) t_enter = globaltimer_ns();
+  const unsigned long long T = atomicAdd(A.ring + 1, 1ull);
+  if (T >= (unsigned long long)A.n_tiles) return false;
+  unsigned long long e = ld_acquire_u64(A.tickets + T);   // acquire: the item's inputs are complete
   unsigned long long spin_t0 = 0;
-  const unsigned long long* ring = A.ring + kRingHeader;
-  for (;;) {
-    int pos = cursor;
-    bool blocked = false;
-    while (pos < A.n_items) {
-      const unsigned long long e = ld_acquire_u64(ring + pos);
-      if (e == kRingEmpty) {
-        blocked = true;
-        break;
-      }
-      const int it = (int)(unsigned)e;
-      const unsigned nt = (unsigned)(e >> 32);
-      if (ld_relaxed_u32(A.claimed + it) < nt) {
-        const unsigned t = atomicAdd(A.claimed + it, 1u);
-        if (t < nt) {
-          cursor = pos;
-          item = it;
-          tile = (int)t;
-          __threadfence();
-          return true;
-        }
-      }
-      ++pos;
-    }
-    cursor = pos;   // everything before pos is exhausted for good
-    if (!blocked) return false;
-    __nanosleep(200);   // nothing is ready: back off before polling the ring again
+  while (e == 0ull) {
+    __nanosleep(100);   // the ticket is not published yet: back off before polling again
+    if (stats) atomicAdd(A.kind_ns + 16 + 10, 1ull);   // measurement aid: polls that found the ticket unpublished
     const unsigned long long now = globaltimer_ns();
     if (spin_t0 == 0) spin_t0 = now;
     else if (now - spin_t0 > 2000000000ull) {
       atomicAdd(A.fault, 1u);
       return false;
     }
+    e = ld_acquire_u64(A.tickets + T);
   }
+  item = (int)(unsigned)(e >> 32) - 1;
+  tile = (int)(unsigned)e;
+  if (stats) {   // measurement aid: slot 11 = claims whose ticket was there, slot 12 = the others
+    const int k = spin_t0 ? 12 : 11;
+    atomicAdd(A.kind_ns + k, globaltimer_ns() - t_enter);
+    atomicAdd(A.kind_ns + 16 + k, 1ull);
+  }
+  return true;
 }
+// all threads: the tile's results become visible, successors whose last dependency tile this was get their tickets
 __device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    tma::fence_proxy_async();   // the tile's stores (generic proxy) precede TMA reads (async proxy) of later items
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+      fence_acq_rel_gpu();        // release: the tile's stores (all threads, ordered by the barrier) before the counters
+      tma::fence_proxy_async();   // ... and before TMA reads (async proxy) of later items
+    }
     for (int k = 0; k < I.succ_count; ++k) {
-      const int s = A.succ[I.succ_first + k];
-      if (atomicSub(A.pending + s, 1) == 1) {   // the last outstanding dependency tile: the successor is ready
-        __threadfence();
-        const unsigned long long slot = atomicAdd(A.ring, 1ull);
-        st_release_u64(A.ring + kRingHeader + slot, ((unsigned long long)(unsigned)A.items[s].ntiles << 32) | (unsigned)s);
+      int s = 0, nt = 0;
+      unsigned long long first = 0;
+      if (lane == 0) {
+        s = A.succ[I.succ_first + k];
+        if (atomicSub(A.pending + s, 1) == 1) {   // the last outstanding dependency tile: the successor is ready
+          nt = A.items[s].ntiles;
+          fence_acq_rel_gpu();
+          first = atomicAdd(A.ring, (unsigned long long)nt);
+        }
       }
+      nt = __shfl_sync(0xffffffffu, nt, 0);
+      if (nt <= 0) continue;
+      s = __shfl_sync(0xffffffffu, s, 0);
+      first = __shfl_sync(0xffffffffu, first, 0);
+      for (int t = lane; t < nt; t += 32)
+        st_release_u64(A.tickets + first + t, ((unsigned long long)(unsigned)(s + 1) << 32) | (unsigned)t);
     }
   }
 }
@@ -1370,13 +1371,22 @@ oamix_chain_kernel(const ChainArgs Aparam) {
   S.div255[threadIdx.x] = (double)threadIdx.x / 255.0;   // kCT == 256
   __syncthreads();
   const ChainArgs& A = S.args;
-  int staged_lane = -1, cursor = 0;
+  // tickets of the items that start ready (host-assigned ranges, priority order)
+  for (int k = blockIdx.x; k < (int)A.ring[2]; k += gridDim.x) {
+    const unsigned long long e = A.ring[kRingHeader + k];
+    const int it0 = (int)(unsigned)e;
+    const unsigned long long first = e >> 32;
+    const int nt = A.items[it0].ntiles;
+    for (int t = threadIdx.x; t < nt; t += kCT)
+      st_release_u64(A.tickets + first + t, ((unsigned long long)(unsigned)(it0 + 1) << 32) | (unsigned)t);
+  }
+  int staged_lane = -1;
   unsigned n_stage = 0;   // gather stages used so far by this CTA (stage = n & 1, mbarrier parity = (n >> 1) & 1)
   if (threadIdx.x == 0) {
     int item = -1, tile = -1;
     unsigned long long w0 = 0;
     if (kStats) w0 = globaltimer_ns();
-    if (!claim_work(A, cursor, item, tile)) item = -1;
+    if (!claim_work(A, item, tile, kStats)) item = -1;
     if (kStats) atomicAdd(A.kind_ns + 10, globaltimer_ns() - w0);
     S.next_item = item;
     S.next_tile = tile;
@@ -1424,7 +1434,7 @@ oamix_chain_kernel(const ChainArgs Aparam) {
       unsigned long long t1 = 0;
       if (kStats) t1 = globaltimer_ns();
       int item = it, nt = -1;
-      if (!claim_work(A, cursor, item, nt)) item = -1;
+      if (!claim_work(A, item, nt, kStats)) item = -1;
       if (kStats) {
         const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
         const unsigned long long dt = t1 - seg_t0;

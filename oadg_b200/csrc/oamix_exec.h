@@ -14,10 +14,13 @@ namespace oadg {
 
 constexpr int kMagic = 0x4F414447;
 constexpr int kTensorMapBytes = 128;   // sizeof(CUtensorMap), 64-byte aligned in device memory
-// The ready ring (see oamix.cu): entry k = (ntiles << 32 | item) of the k-th item that became ready, ~0 while
-// unpublished; the first kRingHeader words are the header: [0] = number of published entries (the append cursor).
-constexpr int kRingHeader = 2;
-constexpr unsigned long long kRingEmpty = ~0ull;
+// The tile tickets (see oamix.cu).  Every tile of the launch gets a TICKET, in the order in which its item became
+// ready; tickets[T] = (item + 1) << 32 | tile once ticket T is published, 0 before (the table is zeroed with the other
+// counters).  A CTA claims a tile with ONE atomic on the claim cursor and reads its ticket.  The uploaded `ring` holds
+// the header {[0] tickets published so far (the publish cursor), [1] the claim cursor, [2] number of initial items}
+// and then, for every item that starts ready (in queue = priority order), first_ticket << 32 | item: the kernel's
+// CTAs write those tickets themselves when they start.
+constexpr int kRingHeader = 4;
 // geometry of a staged gather source (one sub-tile of 64 x 16 output pixels, oamix.cu): TMA boxes of 16 rows
 constexpr int kGatherBoxRows = 16, kGatherImgBoxBytes = 256, kGatherMaskBoxBytes = 96;
 
@@ -106,6 +109,7 @@ struct Layout {
   int any_bg;
   size_t tables_bytes;
   int n_lanes_total, n_chains, n_lut, n_hist, max_depth, max_items, max_deps, max_perm, n_bbo, max_maps;
+  size_t max_tiles, off_tickets;
   size_t total;
 };
 
@@ -150,6 +154,31 @@ inline void make_layout(const PlanView& pv, Layout& L) {
     for (int v = 0; v < h.n_views; ++v) wsum += pv.views[v].width;
     L.max_maps = 2 * h.n_views + 2 * wsum + 2 * n_chains + 1;
   }
+  {  // upper bound of the launch's tiles (dead boxes / chains are only pruned at execute time)
+    auto cdiv = [](long long a, long long b) { return (size_t)((a + b - 1) / b); };
+    size_t tiles = 64;
+    for (int v = 0; v < h.n_views; ++v) {
+      const oadg_view_t& V = pv.views[v];
+      tiles += 2 * (size_t)V.n_gt + cdiv(V.W, kMaskTileW) * cdiv(V.H, kMaskTileH);
+      for (int b = 0; b < V.width; ++b)
+        for (int d = 0; d < V.depth[b]; ++d) {
+          tiles += cdiv(V.W, kStepTileWPx) * cdiv(V.H, kStepTileH) + cdiv((long long)V.W * V.H, kHistTilePx);
+          for (int r = 0; r <= V.n_ml; ++r) {
+            const oadg_op_t& op = pv.ops[op_index(V, b, d, r)];
+            tiles += 1;
+            if (op.kind != OADG_OP_BBO_AFFINE || op.bbo_count <= 0) continue;
+            tiles += cdiv((long long)V.W * V.H * 3, kCopyTileBytes);
+            for (int j = 0; j < op.bbo_count; ++j) {
+              const int32_t* sp = pv.gts[pv.bbo[op.bbo_first + j].gt].supp;
+              const int w = sp[2] - (sp[0] & ~3), hg = sp[3] - sp[1];
+              if (w <= 0 || hg <= 0) continue;
+              tiles += cdiv(w, kBboTileW) * cdiv(hg, kBboTileH) + cdiv(w, kBboCatchW) * cdiv(hg, kBboTileH);
+            }
+          }
+        }
+    }
+    L.max_tiles = tiles;
+  }
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -183,6 +212,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
   // claimed per item, then (measurement aid) per item 2^63 - first claim time and last publish time (globaltimer ns)
   L.off_hist = take((size_t)(n_hist > 0 ? n_hist : 1) * 768 * sizeof(unsigned));
   L.off_luma = take((size_t)(n_hist > 0 ? n_hist : 1) * sizeof(unsigned long long));
+  L.off_tickets = take(L.max_tiles * sizeof(unsigned long long));
   L.zero_bytes = o - L.off_zero;
   L.off_lut = take((size_t)(n_lut > 0 ? n_lut : 1) * 768);
   L.any_bg = any_bg;
@@ -318,7 +348,8 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
   size_t frame_bytes;
   unsigned long long* kind_ns;   // [16] CTA-busy ns per item kind, [16] tiles per kind, [16] longest tile (measurement aid)
   const void* maps;              // tensor maps (kTensorMapBytes each) of the frames the affine gathers stage with TMA
-  unsigned long long* ring;      // ready ring: header + one entry per item (uploaded with the tables)
+  unsigned long long* ring;      // ticket header + the initially ready items (uploaded with the tables)
+  unsigned long long* tickets;   // [n_tiles] tile tickets (zeroed before the launch)
   unsigned* fault;               // sticky: != 0 when a CTA gave up waiting for work (inconsistent dependency tables)
 };
 
@@ -740,13 +771,18 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       }
   }
 
-  {  // ready ring: the items without dependencies, in queue (priority) order; the rest is appended on the device
-    unsigned long long n_ready = 0;
-    for (int k = 0; k < n_items + kRingHeader; ++k) ring[k] = kRingEmpty;
+  if ((size_t)n_tiles > L.max_tiles) return OADG_E_LIMIT;
+  {  // tickets of the items without dependencies, in queue (priority) order; the rest is published on the device
+    unsigned long long n_init = 0, first = 0;
     for (int k = 0; k < n_items; ++k)
-      if (pending[k] == 0) ring[kRingHeader + n_ready++] = ((unsigned long long)(unsigned)items[k].ntiles << 32) | (unsigned)k;
-    ring[0] = n_ready;
+      if (pending[k] == 0) {
+        ring[kRingHeader + n_init++] = (first << 32) | (unsigned)k;
+        first += (unsigned)items[k].ntiles;
+      }
+    ring[0] = first;
     ring[1] = 0;
+    ring[2] = n_init;
+    ring[3] = 0;
   }
 
   for (int v = 0; v < h.n_views; ++v) {
@@ -808,6 +844,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   A.fault = reinterpret_cast<unsigned*>(ws + L.off_zero + 16);
   A.maps = dplan + t_maps;
   A.ring = reinterpret_cast<unsigned long long*>(const_cast<char*>(dplan) + t_ring);
+  A.tickets = reinterpret_cast<unsigned long long*>(ws + L.off_tickets);
   // host views of the same tables (the host arithmetic check interprets them directly)
   ChainArgs Hh = A;
   Hh.lanes = lanes;

@@ -609,7 +609,7 @@ class OAMix:
             profile['mix_n'] = profile.get('mix_n', 0) + 1
             profile['items'] = profile.get('items', 0) + int(n_items.value)
             profile['tiles'] = profile.get('tiles', 0) + int(n_tiles.value)
-            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed', 'dependency_wait')
+            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed', 'dependency_wait', 'claim_fast', 'claim_blocked')
             ks = profile.setdefault('kind_busy_us_and_tiles', {k: [0.0, 0, 0.0] for k in names})
             for i, k in enumerate(names):
                 ks[k][0] += float(kstats[i]) / 1e3

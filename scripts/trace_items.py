@@ -21,7 +21,8 @@ class Trace(ctypes.Structure):
 
 
 dev = torch.device('cuda:0')
-frames = [bench.make_image(s) for s in range(8)]
+G = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+frames = [bench.make_image(s) for s in range(max(8, G))]
 imgs = [torch.from_numpy(f).to(dev) for f, _ in frames]
 gts = [g for _, g in frames]
 mix = OAMix(**bench.OAMIX_CFG)
@@ -29,7 +30,7 @@ np.random.seed(1000)
 for i in range(3):
     mix.oamix_batch(imgs[0:2], gts[0:2])
 prof = {}
-mix.oamix_batch(imgs[0:2], gts[0:2], profile=prof)
+mix.oamix_batch(imgs[0:G], gts[0:G], profile=prof)
 lib = _lib.load()
 lib.oadg_oamix_last_trace.restype = ctypes.c_int
 n = lib.oadg_oamix_last_trace(None, 0)
@@ -50,3 +51,22 @@ print('critical path (item, kind, obj, tiles, first claim us, last publish us, r
 for row in reversed(path):
     print('  %4d %-12s obj %3d tiles %5d  start %7.1f  end %7.1f  (deps done %7.1f, ran %6.1f, waited %5.1f)' %
           (row + (row[5] - row[4], row[4] - row[6])))
+
+# occupancy of the queue over time: items in flight and tiles of items that are ready (dependencies done) but not finished
+import collections
+bins = collections.OrderedDict()
+step = max(end / 40.0, 1.0)
+ready = []
+for i in range(n):
+    t = buf[i]
+    deps = [d for d in t.deps[:min(t.dep_count, 8)] if d >= 0]
+    ready.append(max([buf[d].t1 for d in deps]) if deps else 0.0)
+print('time us : items in flight / tiles of ready-or-running items / items ready but not started')
+for b in range(int(end / step) + 1):
+    lo, hi = b * step, (b + 1) * step
+    mid = 0.5 * (lo + hi)
+    run = [i for i in range(n) if buf[i].t0 <= mid < buf[i].t1]
+    avail = [i for i in range(n) if ready[i] <= mid < buf[i].t1]
+    idle = [i for i in range(n) if ready[i] <= mid < buf[i].t0]
+    print('  %7.1f : %4d / %6d / %4d   kinds in flight: %s' % (mid, len(run), sum(buf[i].ntiles for i in avail), len(idle),
+          ' '.join('%s=%d' % (KINDS[k], sum(1 for i in run if buf[i].kind == k)) for k in range(8) if any(buf[i].kind == k for i in run))))
