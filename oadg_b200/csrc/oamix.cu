@@ -37,8 +37,17 @@ namespace {
 #define OADG_HANDLER __noinline__
 #endif
 
-constexpr int kCT = 256;     // threads per CTA of the chain kernel
-constexpr int kCtaPerSm = 4; // independent CTAs per SM (64 registers per thread): tiles of different kinds overlap on an SM
+constexpr int kCT = 256;     // WORKER threads per CTA of the chain kernel (warps 0-7): they run the tile handlers
+constexpr int kSchedThreads = 32;            // warp 8: the tile scheduler (claims the next tile, publishes the last one)
+constexpr int kCtaThreads = kCT + kSchedThreads;
+#ifndef OADG_CTAS_PER_SM_MAX
+#define OADG_CTAS_PER_SM_MAX 3
+#endif
+constexpr int kCtaPerSm = OADG_CTAS_PER_SM_MAX;   // independent CTAs per SM: tiles of different kinds overlap on an SM
+// named barriers: 1 = the workers' block barrier; 2,3 = "slot k holds the next tile" (scheduler arrives, workers sync)
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_all(int id) { asm volatile("bar.sync %0, 288;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive_all(int id) { asm volatile("bar.arrive %0, 288;" ::"r"(id) : "memory"); }
 
 // ---- dynamic shared memory of a CTA ------------------------------------------------------------------------
 // [0, 2 * kStageBytes)   two gather stages: 3 TMA boxes of 16 rows x 256 B (frame) + 3 boxes of 16 rows x 96 B (mask)
@@ -74,9 +83,14 @@ struct BboStage {    // one bbo job staged for the CTA (bbo_r_tile / bbo_c_segme
   int32_t excl[16][4];   // supports of the next level's boxes (catch-up exclusion)
 };
 
+struct TileSlot {      // the scheduler warp hands the workers one tile per slot
+  int item;            // -1: the queue is drained
+  int tile;            // tile index within the item (after the item's permutation)
+  Item I;
+};
 struct ChainSmem {
-  int next_tile;       // the CTA's next claimed tile ...
-  int next_item;       // ... and the item it belongs to (-1: the queue is drained)
+  TileSlot slot[2];
+  unsigned done_seq;   // tiles the workers have finished (written by worker thread 0, read by the scheduler)
   int rowoff[2][96];   // hand-staged gathers: byte offset of every staged source row (frame rows, mask rows)
   int cand[16];        // mask tiles: the gt boxes whose support meets the tile
   int step_class;      // measurement aid: class of the last step tile (7 stream, 8 staged bg, 9 mixed / per pixel)
@@ -121,60 +135,42 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
-// thread 0 only: the next (item, tile); returns false when every tile is handed out (or the wait timed out)
-__device__ bool claim_work(const ChainArgs& A, int& item, int& tile, bool stats) {
-  unsigned long long t_enter = 0;
-  if (stats) t_enter = globaltimer_ns();
-  const unsigned long long T = atomicAdd(A.ring + 1, 1ull);
-  if (T >= (unsigned long long)A.n_tiles) return false;
-  unsigned long long e = ld_acquire_u64(A.tickets + T);   // acquire: the item's inputs are complete
-  unsigned long long spin_t0 = 0;
-  while (e == 0ull) {
-    __nanosleep(100);   // the ticket is not published yet: back off before polling again
-    if (stats) atomicAdd(A.kind_ns + 16 + 10, 1ull);   // measurement aid: polls that found the ticket unpublished
-    const unsigned long long now = globaltimer_ns();
-    if (spin_t0 == 0) spin_t0 = now;
-    else if (now - spin_t0 > 2000000000ull) {
-      atomicAdd(A.fault, 1u);
-      return false;
-    }
-    e = ld_acquire_u64(A.tickets + T);
-  }
-  item = (int)(unsigned)(e >> 32) - 1;
-  tile = (int)(unsigned)e;
-  if (stats) {   // measurement aid: slot 11 = claims whose ticket was there, slot 12 = the others
-    const int k = spin_t0 ? 12 : 11;
-    atomicAdd(A.kind_ns + k, globaltimer_ns() - t_enter);
-    atomicAdd(A.kind_ns + 16 + k, 1ull);
-  }
-  return true;
+__device__ __forceinline__ unsigned ld_acquire_cta_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
 }
-// all threads: the tile's results become visible, successors whose last dependency tile this was get their tickets
+__device__ __forceinline__ void st_release_cta_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// scheduler warp (all 32 lanes), after the workers reported the tile finished (done_seq): the tile's results become
+// visible device-wide, and every successor whose last outstanding dependency tile this was gets its tickets.  One
+// lane per successor: the successor list, the dependency counters and the ticket reservations each cost ONE round
+// trip for the whole list.
 __device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) {
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    if (lane == 0) {
-      fence_acq_rel_gpu();        // release: the tile's stores (all threads, ordered by the barrier) before the counters
-      tma::fence_proxy_async();   // ... and before TMA reads (async proxy) of later items
-    }
-    for (int k = 0; k < I.succ_count; ++k) {
-      int s = 0, nt = 0;
-      unsigned long long first = 0;
-      if (lane == 0) {
-        s = A.succ[I.succ_first + k];
-        if (atomicSub(A.pending + s, 1) == 1) {   // the last outstanding dependency tile: the successor is ready
-          nt = A.items[s].ntiles;
-          fence_acq_rel_gpu();
-          first = atomicAdd(A.ring, (unsigned long long)nt);
-        }
+  const int lane = threadIdx.x & 31;
+  fence_acq_rel_gpu();        // release: the tile's stores (ordered before this warp by the barrier) before the counters
+  tma::fence_proxy_async();   // ... and before TMA reads (async proxy) of later items
+  for (int base = 0; base < I.succ_count; base += 32) {
+    int s = -1, nt = 0;
+    unsigned long long first = 0;
+    if (base + lane < I.succ_count) {
+      s = A.succ[I.succ_first + base + lane];
+      if (atomicSub(A.pending + s, 1) == 1) {   // the last outstanding dependency tile: the successor is ready
+        nt = A.items[s].ntiles;
+        fence_acq_rel_gpu();                    // acquire the other dependencies' results before handing out the item
+        first = atomicAdd(A.ring, (unsigned long long)nt);
       }
-      nt = __shfl_sync(0xffffffffu, nt, 0);
-      if (nt <= 0) continue;
-      s = __shfl_sync(0xffffffffu, s, 0);
-      first = __shfl_sync(0xffffffffu, first, 0);
-      for (int t = lane; t < nt; t += 32)
-        st_release_u64(A.tickets + first + t, ((unsigned long long)(unsigned)(s + 1) << 32) | (unsigned)t);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, nt > 0);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const int sj = __shfl_sync(0xffffffffu, s, j), ntj = __shfl_sync(0xffffffffu, nt, j);
+      const unsigned long long fj = __shfl_sync(0xffffffffu, first, j);
+      for (int t = lane; t < ntj; t += 32)
+        st_release_u64(A.tickets + fj + t, ((unsigned long long)(unsigned)(sj + 1) << 32) | (unsigned)t);
     }
   }
 }
@@ -198,7 +194,7 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
   float* p = reinterpret_cast<float*>(dyn + 1538 * 8);         // [1024] low-res blurred profile
   float* out = (axis == 0 ? A.prof_x + (size_t)g * P.max_w : A.prof_y + (size_t)g * P.max_h);
   const int tid = threadIdx.x;
-  __syncthreads();  // the shared buffers may still be in use by the previous tile
+  worker_sync();  // the shared buffers may still be in use by the previous tile
   if (n_lo <= 0) {
     for (int d = tid; d < n_hi; d += kCT) out[d] = 0.f;
     return;
@@ -213,28 +209,28 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
     }
     part = warp_sum(part);
     if ((tid & 31) == 0) S.red[tid >> 5] = part;
-    __syncthreads();
+    worker_sync();
     if (tid == 0) {
       double t = 0;
       for (int w = 0; w < kCT / 32; ++w) t += S.red[w];
       S.ksum = 1.0 / t;
     }
-    __syncthreads();
+    worker_sync();
     const double ksum = S.ksum;
     // K[j] = sum of the float32 taps 0..j-1 in float64 (the blur of an indicator is a difference of prefix sums)
     for (int i = tid; i <= ks; i += kCT) {
       double x = (i - 1) - (ks - 1) * 0.5;
       K[i] = i == 0 ? 0.0 : (double)(float)(exp(s2 * x * x) * ksum);
     }
-    __syncthreads();
+    worker_sync();
     for (int off = 1; off <= ks; off <<= 1) {  // Hillis-Steele inclusive scan over K[0..ks]
       double v[8];
       int n = 0;
       for (int i = tid; i <= ks; i += kCT, ++n) v[n] = i >= off ? K[i] + K[i - off] : K[i];
-      __syncthreads();
+      worker_sync();
       n = 0;
       for (int i = tid; i <= ks; i += kCT, ++n) K[i] = v[n];
-      __syncthreads();
+      worker_sync();
     }
     const int r = ks / 2;
     auto range = [&](int a, int b) {  // sum of taps j in [a, b) clipped to [0, ks)
@@ -272,7 +268,7 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
   } else {
     for (int x = tid; x < n_lo; x += kCT) p[x] = (x >= lo && x < hi) ? 1.f : 0.f;
   }
-  __syncthreads();
+  worker_sync();
   // cv2.resize(f32, INTER_LINEAR): fx = (float)((dx+0.5)*scale - 0.5)
   const double scale = (double)n_lo / (double)n_hi;
   for (int d = tid; d < n_hi; d += kCT) {
@@ -285,16 +281,18 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
     out[d] = fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));
   }
 }
+__device__ __forceinline__ int f32_trunc_u8(float f);
+
 // union of the blurred gt masks of a view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260) as float32 and as
 // uint8(mask*255): written once per batch, read by every bg-only op.  Tile = 256 x 8 px, one column x 8 rows per
 // thread; the boxes whose support meets the tile are listed once per tile, and a thread keeps the x-profile value of
 // each listed box for its column in registers.
-__device__ OADG_HANDLER void mask_tile(const ChainArgs& A, ChainSmem& S, int view, int local, int tx) {
+__device__ OADG_HANDLER void mask_tile(const ChainArgs& A, ChainSmem& S, uint8_t* dyn, int view, int local, int tx) {
   const DevPlan& P = A.P;
   const oadg_view_t& V = P.views[view];
   const int x0 = (local % tx) * kMaskTileW, y0 = (local / tx) * kMaskTileH;
   const int x1 = min(x0 + kMaskTileW, V.W), y1 = min(y0 + kMaskTileH, V.H);
-  __syncthreads();
+  worker_sync();
   if (threadIdx.x < 32) {  // lane k tests box k (+32, ...): one round trip instead of a serial walk
     if (threadIdx.x == 0) S.bs_key = -1;   // bs.excl is reused below
     int n = 0;
@@ -317,11 +315,45 @@ __device__ OADG_HANDLER void mask_tile(const ChainArgs& A, ChainSmem& S, int vie
     }
     if (threadIdx.x == 0) S.bs.n_excl = n;
   }
-  __syncthreads();
+  worker_sync();
   const int n = S.bs.n_excl;
+  const size_t base = (size_t)view * P.mask_stride;
+  if (n <= 16 && (V.W & 3) == 0 && (P.mask_stride & 3) == 0 && x1 - x0 == kMaskTileW) {
+    // full-width tile of a frame whose rows are 16-byte periodic: the listed boxes' profile slices go to shared
+    // memory (zeros outside a box's support: the product is then +0 and never wins the max), every thread owns 4
+    // consecutive columns of 8 rows and stores one float4 + one uint32 per row
+    const int t = threadIdx.x, g = t & 63, r0 = t >> 6;
+    float* spx = reinterpret_cast<float*>(dyn);          // [n][256]
+    float* spy = spx + n * kMaskTileW;                    // [n][32]
+    for (int i = t; i < n * kMaskTileW; i += kCT) {
+      const int c = i >> 8, x = x0 + (i & 255);
+      spx[i] = (x >= S.bs.excl[c][0] && x < S.bs.excl[c][2]) ? A.prof_x[(size_t)S.cand[c] * P.max_w + x] : 0.f;
+    }
+    for (int i = t; i < n * kMaskTileH; i += kCT) {
+      const int c = i / kMaskTileH, y = y0 + i % kMaskTileH;
+      spy[i] = (y < y1 && y >= S.bs.excl[c][1] && y < S.bs.excl[c][3]) ? A.prof_y[(size_t)S.cand[c] * P.max_h + y] : 0.f;
+    }
+    worker_sync();
+    for (int r = r0; r < y1 - y0; r += 4) {
+      float m[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < n; ++c) {
+        const float uy = spy[c * kMaskTileH + r];
+        const float4 ux = *reinterpret_cast<const float4*>(spx + c * kMaskTileW + 4 * g);
+        const float v0 = fmul(uy, ux.x), v1 = fmul(uy, ux.y), v2 = fmul(uy, ux.z), v3 = fmul(uy, ux.w);
+        m[0] = v0 > m[0] ? v0 : m[0]; m[1] = v1 > m[1] ? v1 : m[1];
+        m[2] = v2 > m[2] ? v2 : m[2]; m[3] = v3 > m[3] ? v3 : m[3];
+      }
+      const size_t o = base + (size_t)(y0 + r) * V.W + x0 + 4 * g;
+      *reinterpret_cast<float4*>(A.maskf + o) = make_float4(m[0], m[1], m[2], m[3]);
+      // uint8(mask * 255): truncation of a non-negative float32 (mask_to_u8, oamix_math.h) without the F2I instruction
+      *reinterpret_cast<uint32_t*>(A.masku + o) =
+          (uint32_t)f32_trunc_u8(fmul(m[0], 255.0f)) | (uint32_t)f32_trunc_u8(fmul(m[1], 255.0f)) << 8 |
+          (uint32_t)f32_trunc_u8(fmul(m[2], 255.0f)) << 16 | (uint32_t)f32_trunc_u8(fmul(m[3], 255.0f)) << 24;
+    }
+    return;
+  }
   const int x = x0 + (threadIdx.x & 255);
   if (x >= x1) return;
-  const size_t base = (size_t)view * P.mask_stride;
   if (n > 8) {  // many overlapping boxes: the plain per-pixel walk
     for (int y = y0; y < y1; ++y) mask_pixel(P, view, x, y, A.maskf, A.masku);
     return;
@@ -386,12 +418,12 @@ __device__ OADG_HANDLER void hist_tile(const Lane& L, unsigned* hist, int local,
   }
 }
 __device__ OADG_HANDLER void hist_begin(unsigned* hist) {
-  __syncthreads();
+  worker_sync();
   for (int i = threadIdx.x; i < 2 * 768; i += kCT) hist[i] = 0;
-  __syncthreads();
+  worker_sync();
 }
 __device__ OADG_HANDLER void hist_flush(const ChainArgs& A, const unsigned* hist, int slot, unsigned long long& lsum) {
-  __syncthreads();
+  worker_sync();
   unsigned* dst = A.hist + (size_t)slot * 768;
   for (int i = threadIdx.x; i < 768; i += kCT) {
     unsigned s = 0;
@@ -402,7 +434,7 @@ __device__ OADG_HANDLER void hist_flush(const ChainArgs& A, const unsigned* hist
   lsum = warp_sum(lsum);
   if ((threadIdx.x & 31) == 0 && lsum) atomicAdd(A.luma + slot, lsum);
   lsum = 0;
-  __syncthreads();
+  worker_sync();
 }
 // one LUT op: PIL.ImageOps autocontrast / equalize from the finished histogram, or a closed-form table
 __device__ OADG_HANDLER void lut_tile(const ChainArgs& A, ChainSmem& S, int job) {
@@ -410,7 +442,7 @@ __device__ OADG_HANDLER void lut_tile(const ChainArgs& A, ChainSmem& S, int job)
   const oadg_op_t& op = A.P.ops[J.op];
   uint8_t* out = A.luts + (size_t)op.lut * 768;
   const int tid = threadIdx.x;
-  __syncthreads();
+  worker_sync();
   if (op.kind == OADG_OP_AUTOCONTRAST || op.kind == OADG_OP_EQUALIZE) {
     // one thread per bin, channel after channel (same integer / float64 arithmetic as lut_autocontrast_ch /
     // lut_equalize_ch in oamix_math.h, with the scans done by ballots and a block prefix sum)
@@ -426,10 +458,10 @@ __device__ OADG_HANDLER void lut_tile(const ChainArgs& A, ChainSmem& S, int job)
         const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
-      __syncthreads();
+      worker_sync();
       if (lane == 31) wsum[warp] = incl;
       if (lane == 0) msk[warp] = bal;
-      __syncthreads();
+      worker_sync();
       int lo = 256, hi = -1, nnz = 0;
       unsigned total = 0, before = 0;
 #pragma unroll
@@ -649,10 +681,10 @@ __device__ __forceinline__ void load12(const uint8_t* p, bool vec, int n, uint32
 __device__ __forceinline__ int byte_of(const uint32_t w[3], int k) { return (int)((w[k >> 2] >> ((k & 3) * 8)) & 255u); }
 // ---- bboxes-only chains (bbox_augmentation.py:31-88), one box of one level ----------------------------------
 __device__ OADG_HANDLER void bbo_stage(const ChainArgs& A, ChainSmem& S, const Item& I, bool catch_up) {
-  __syncthreads();
+  worker_sync();
   const int key = I.obj * 2 + (catch_up ? 1 : 0);
   if (S.bs_key == key) return;   // the job is still staged from this CTA's previous tile (uniform: S.bs_key is shared)
-  __syncthreads();
+  worker_sync();
   if (threadIdx.x == 0) {
     S.bs_key = key;
     const BboJob J = A.bjobs[I.obj];
@@ -674,7 +706,7 @@ __device__ OADG_HANDLER void bbo_stage(const ChainArgs& A, ChainSmem& S, const I
     for (int k = 0; k < bs.n_excl && k < 16; ++k)
       for (int e = 0; e < 4; ++e) bs.excl[k][e] = A.bjobs[J.next_first + k].rect[e];
   }
-  __syncthreads();
+  worker_sync();
 }
 // blend of one box, frames WITHOUT a tensor map (row pitch not a multiple of 16 bytes): the source rows of every
 // sub-tile are staged by hand (16-byte vector loads) between two block barriers
@@ -721,13 +753,13 @@ __device__ OADG_HANDLER void bbo_r_tile_hand(const ChainArgs& A, ChainSmem& S, u
           if (xg + i >= x0 && xg + i < x1)
             for (int c = 0; c < 3; ++c) in_w[(3 * i + c) >> 2] |= (uint32_t)bs.X[o + 3 * i + c] << (((3 * i + c) & 3) * 8);
     }
-    __syncthreads();  // the previous tile's gathers are done (and the profile slices are in place)
+    worker_sync();  // the previous tile's gathers are done (and the profile slices are in place)
     const bool fast = staged && sr[3] - sr[1] <= 96;
     if (staged) {
       stage_rows(dyn, sv.pitch, bs.X, W, H, 3, sr[0], sr[1], sr[3] - sr[1]);
       fill_rowoff(S.rowoff[0], sv, sr[3] - sr[1]);
     }
-    __syncthreads();
+    worker_sync();
     if (!active) continue;
     const float uy = A.prof_y[(size_t)bs.gt * A.P.max_h + y];
     const WarpRowTerm rt = warp_row_term(bs.minv, y);
@@ -812,18 +844,60 @@ __device__ __forceinline__ void gather_issue(ChainSmem& S, uint8_t* dyn, unsigne
     tma::mbar_arrive(bar);
   }
 }
-// taps of one pixel from a staged frame rectangle: 12 byte loads, no bounds tests
+// Which taps carry weight is a property of the map: with m00 == 1, m01 == 0 and an integral m02 every X is a multiple
+// of 32 (fx == 0: translations, y-shears), likewise fy == 0 for m10 == 0, m11 == 1 and an integral m12 (translations,
+// x-shears); the weights (32-fx)(32-fy)*32 ... then reduce to the one- / two-tap forms below (same integers).
+//   mode bit 0: fx == 0 everywhere, bit 1: fy == 0 everywhere
+__device__ __forceinline__ int gather_mode(const double* m) {
+  const bool fx0 = m[0] == 1.0 && m[1] == 0.0 && m[2] == floor(m[2]);
+  const bool fy0 = m[3] == 0.0 && m[4] == 1.0 && m[5] == floor(m[5]);
+  return (fx0 ? 1 : 0) | (fy0 ? 2 : 0);
+}
+// taps of one pixel from a staged frame rectangle: byte loads, no bounds tests
+template <int kMode>
 __device__ __forceinline__ void tma_fetch3(const uint8_t* st, int xb, int ry0, int sx, int sy, int fx, int fy, int out[3]) {
   const uint8_t* p = st + (sy - ry0) * kGatherImgBoxBytes + (sx * 3 - xb);
-  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  if (kMode == 3) {
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-    out[c] = ((int)p[c] * w00 + (int)p[3 + c] * w01 + (int)p[kGatherImgBoxBytes + c] * w10 +
-              (int)p[kGatherImgBoxBytes + 3 + c] * w11 + (1 << 14)) >> 15;
+    for (int c = 0; c < 3; ++c) out[c] = p[c];
+  } else if (kMode == 1) {   // fx == 0: vertical pair
+    const int w0 = 32 - fy;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = ((int)p[c] * w0 + (int)p[kGatherImgBoxBytes + c] * fy + 16) >> 5;
+  } else if (kMode == 2) {   // fy == 0: horizontal pair
+    const int w0 = 32 - fx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = ((int)p[c] * w0 + (int)p[3 + c] * fx + 16) >> 5;
+  } else {
+    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      out[c] = ((int)p[c] * w00 + (int)p[3 + c] * w01 + (int)p[kGatherImgBoxBytes + c] * w10 +
+                (int)p[kGatherImgBoxBytes + 3 + c] * w11 + (1 << 14)) >> 15;
+  }
 }
+template <int kMode>
 __device__ __forceinline__ int tma_fetch1(const uint8_t* st, int xm, int ry0, int sx, int sy, int fx, int fy) {
   const uint8_t* p = st + (sy - ry0) * kGatherMaskBoxBytes + (sx - xm);
+  if (kMode == 3) return p[0];
+  if (kMode == 1) return ((int)p[0] * (32 - fy) + (int)p[kGatherMaskBoxBytes] * fy + 16) >> 5;
+  if (kMode == 2) return ((int)p[0] * (32 - fx) + (int)p[1] * fx + 16) >> 5;
   return bilerp_fix(p[0], p[1], p[kGatherMaskBoxBytes], p[kGatherMaskBoxBytes + 1], fx, fy);
+}
+// Conversion-free forms of the blends (the I2F / F2I / I2D / D2I instructions run on the quarter-rate pipe):
+// for an integer 0 <= v < 2^23, float(v) == as_float(0x4B000000 | v) - 2^23 exactly, and for a float 0 <= f < 2^23,
+// int(f) (truncation) == low bits of (f + 2^23) rounded toward -inf; likewise with 2^52 in float64.
+__device__ __forceinline__ float u8_to_f32(int v) { return __fsub_rn(__int_as_float(0x4B000000 | v), 8388608.0f); }
+__device__ __forceinline__ int f32_trunc_u8(float f) { return __float_as_int(__fadd_rd(f, 8388608.0f)) & 0x7FFFFF; }
+__device__ __forceinline__ double u8_to_f64(int v) { return __dsub_rn(__hiloint2double(0x43300000, v), 4503599627370496.0); }
+__device__ __forceinline__ int f64_trunc_u8(double d) { return __double2loint(__dadd_rd(d, 4503599627370496.0)); }
+// bbox_augmentation.py:63-71 (bbo_blend, oamix_math.h) with the box's two float32 factors hoisted
+__device__ __forceinline__ int bbo_blend_fast(float mask, float rest, int img, int aug) {
+  return f32_trunc_u8(fadd(fmul(u8_to_f32(img), mask), fmul(u8_to_f32(aug), rest)));
+}
+// bbox_augmentation.py:264-272 (bg_blend, oamix_math.h)
+__device__ __forceinline__ int bg_blend_fast(double keep, double rest, int img, int aug) {
+  return f64_trunc_u8(dadd(dmul(keep, u8_to_f64(img)), dmul(rest, u8_to_f64(aug))));
 }
 __device__ __forceinline__ void col_coord(WarpRowTerm r, int2 cd, int& sx, int& sy, int& fx, int& fy) {
   const int X = (r.X0 + cd.x) >> 5, Y = (r.Y0 + cd.y) >> 5;
@@ -831,6 +905,38 @@ __device__ __forceinline__ void col_coord(WarpRowTerm r, int2 cd, int& sx, int& 
   sy = Y >> 5;
   fx = X & 31;
   fy = Y & 31;
+}
+
+// the 4 pixels of one thread of a blend sub-tile whose source rectangle is staged (rows > 0)
+struct BboPx {
+  const uint8_t* st;   // staged frame rows
+  int xb, ry0;         // first staged byte column, first staged row
+  const int2* col;     // this thread's 4 column terms
+  const float* uxs;    // ... and x-profile values
+  WarpRowTerm rt;
+  float uy;
+  int lo, hi;          // pixels lo <= i < hi of the group lie inside the sub-tile
+};
+template <int kMode>
+__device__ __forceinline__ void bbo_pixels4(const BboPx& P, const uint32_t in_w[3], uint32_t out_w[3]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int v[3] = {byte_of(in_w, 3 * i), byte_of(in_w, 3 * i + 1), byte_of(in_w, 3 * i + 2)};
+    if (i >= P.lo && i < P.hi) {
+      const float m = fmul(P.uy, P.uxs[i]);
+      // m <= 2^-25: fl(1 - m) == 1 and fl(1 - 1) == 0, so img*1 + aug*0 == img exactly
+      if (m > 2.98023223876953125e-8f) {
+        int sx, sy, fx, fy, a[3];
+        col_coord(P.rt, P.col[i], sx, sy, fx, fy);
+        tma_fetch3<kMode>(P.st, P.xb, P.ry0, sx, sy, fx, fy, a);
+        const float mask = fsub(1.0f, m), rest = fsub(1.0f, mask);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = bbo_blend_fast(mask, rest, v[c], a[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)v[c] << (((3 * i + c) & 3) * 8);
+  }
 }
 
 // blend of one box, one tile of 256 x 16 px: Y = uint8(X*(1-m) + warp(X)*m) inside the support
@@ -865,7 +971,8 @@ __device__ OADG_HANDLER unsigned bbo_r_tile(const ChainArgs& A, ChainSmem& S, ui
   const bool row_ok = y < y1;
   const float uy = row_ok ? A.prof_y[(size_t)bs.gt * A.P.max_h + y] : 0.f;
   const WarpRowTerm rt = warp_row_term(bs.minv, y);
-  __syncthreads();   // the column tables are in place
+  const int mode = gather_mode(bs.minv);
+  worker_sync();   // the column tables are in place
   for (int s = 0; s < nsub; ++s, ++n_stage) {
     const int sx0 = tile_x0 + s * kSubW;
     const int x0 = imax(sx0, bs.rect[0]), x1 = imin(sx0 + kSubW, tile_x1);
@@ -887,31 +994,41 @@ __device__ OADG_HANDLER unsigned bbo_r_tile(const ChainArgs& A, ChainSmem& S, ui
     tma::mbar_wait(&S.full[n_stage & 1u], (n_stage >> 1) & 1u);
     if (active) {
       const int* gr = S.gather_rect[n_stage & 1u];
-      const int rx0 = gr[0], ry0 = gr[1], rows = gr[2];
-      const uint8_t* st = dyn + (n_stage & 1u) * kStageBytes;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int x = xg + i;
-        int v[3] = {byte_of(in_w, 3 * i), byte_of(in_w, 3 * i + 1), byte_of(in_w, 3 * i + 2)};
-        if (x >= x0 && x < x1) {
-          const float m = fmul(uy, uxs[x - tile_x0]);
-          // m <= 2^-25: fl(1 - m) == 1 and fl(1 - 1) == 0, so img*1 + aug*0 == img exactly
-          if (m > 2.98023223876953125e-8f) {
-            int sx, sy, fx, fy, a[3];
-            col_coord(rt, col[x - tile_x0], sx, sy, fx, fy);
-            if (rows > 0) tma_fetch3(st, rx0, ry0, sx, sy, fx, fy, a);
-            else if (rows == 0) a[0] = a[1] = a[2] = 0;
-            else {
-              WarpTap tp;
-              tp.sx = imin(imax(sx, -32768), 32767); tp.sy = imin(imax(sy, -32768), 32767); tp.fx = fx; tp.fy = fy;
-              warp_fetch3(LdRW(), bs.X, H, W, tp, a);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = bbo_blend(m, v[c], a[c]);
-          }
+      const int rows = gr[2];
+      BboPx P4;
+      P4.st = dyn + (n_stage & 1u) * kStageBytes;
+      P4.xb = gr[0]; P4.ry0 = gr[1];
+      P4.col = col + (xg - tile_x0); P4.uxs = uxs + (xg - tile_x0);
+      P4.rt = rt; P4.uy = uy; P4.lo = x0 - xg; P4.hi = x1 - xg;
+      if (rows > 0) {
+        switch (mode) {
+          case 0: bbo_pixels4<0>(P4, in_w, out_w); break;
+          case 1: bbo_pixels4<1>(P4, in_w, out_w); break;
+          case 2: bbo_pixels4<2>(P4, in_w, out_w); break;
+          default: bbo_pixels4<3>(P4, in_w, out_w); break;
         }
+      } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)v[c] << (((3 * i + c) & 3) * 8);
+        for (int i = 0; i < 4; ++i) {
+          const int x = xg + i;
+          int v[3] = {byte_of(in_w, 3 * i), byte_of(in_w, 3 * i + 1), byte_of(in_w, 3 * i + 2)};
+          if (x >= x0 && x < x1) {
+            const float m = fmul(uy, uxs[x - tile_x0]);
+            if (m > 2.98023223876953125e-8f) {
+              int sx, sy, fx, fy, a[3] = {0, 0, 0};
+              col_coord(rt, col[x - tile_x0], sx, sy, fx, fy);
+              if (rows < 0) {
+                WarpTap tp;
+                tp.sx = imin(imax(sx, -32768), 32767); tp.sy = imin(imax(sy, -32768), 32767); tp.fx = fx; tp.fy = fy;
+                warp_fetch3(LdRW(), bs.X, H, W, tp, a);
+              }
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[c] = bbo_blend(m, v[c], a[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)v[c] << (((3 * i + c) & 3) * 8);
+        }
       }
       if (full) {
         uint32_t* q = reinterpret_cast<uint32_t*>(bs.Y + o);
@@ -922,7 +1039,7 @@ __device__ OADG_HANDLER unsigned bbo_r_tile(const ChainArgs& A, ChainSmem& S, ui
             for (int c = 0; c < 3; ++c) bs.Y[o + 3 * i + c] = (uint8_t)byte_of(out_w, 3 * i + c);
       }
     }
-    __syncthreads();   // the stage (and its rectangle record) may be refilled
+    worker_sync();   // the stage (and its rectangle record) may be refilled
   }
   return n_stage;
 }
@@ -945,36 +1062,62 @@ __device__ OADG_HANDLER void bbo_c_segment(const ChainArgs& A, ChainSmem& S, con
     }
     return;
   }
+  const bool vec16 = ((W * 3) & 15) == 0 && ((((uintptr_t)bs.X) | ((uintptr_t)bs.Y)) & 15) == 0;
   for (int k = l0; k < l1; ++k) {
     const int tx0 = ax0 + (k % tx) * kBboCatchW, ty0 = bs.rect[1] + (k / tx) * kBboTileH;
     const int x0 = imax(tx0, bs.rect[0]), x1 = imin(tx0 + kBboCatchW, bs.rect[2]), y1 = imin(ty0 + kBboTileH, bs.rect[3]);
-    for (int y = ty0 + (t >> 4); y < y1; y += 16)
-#pragma unroll
-    for (int gq = 0; gq < kBboCatchW / 64; ++gq) {
-      const int xg = tx0 + gq * 64 + (t & 15) * 4;
-      if (xg >= x1 || xg + 4 <= x0) continue;
-      const size_t o = ((size_t)y * W + xg) * 3;
-      // does a next-level support touch this 4-px group?
-      bool touch = bs.n_excl > 16, all_in = false;
-      if (bs.n_excl <= 16)
-        for (int e = 0; e < bs.n_excl; ++e) {
-          const bool yy = y >= bs.excl[e][1] && y < bs.excl[e][3];
-          touch |= yy && xg < bs.excl[e][2] && xg + 4 > bs.excl[e][0];
-          all_in |= yy && xg >= bs.excl[e][0] && xg + 4 <= bs.excl[e][2];
-        }
-      if (all_in) continue;
-      if (!touch && vec && xg >= x0 && xg + 4 <= x1) {
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.X + o);
-        const uint32_t a0 = q[0], a1 = q[1], a2 = q[2];
-        uint32_t* d = reinterpret_cast<uint32_t*>(bs.Y + o);
+    if (x1 <= x0 || y1 <= ty0) continue;
+    // the next level's supports that meet this tile (uniform); one that covers it leaves nothing to copy
+    unsigned hit = 0;
+    bool covered = false;
+    const bool many = bs.n_excl > 16;
+    for (int e = 0; e < bs.n_excl && !many; ++e) {
+      const int32_t* r = bs.excl[e];
+      if (r[0] < x1 && r[2] > x0 && r[1] < y1 && r[3] > ty0) {
+        hit |= 1u << e;
+        covered |= r[0] <= x0 && r[2] >= x1 && r[1] <= ty0 && r[3] >= y1;
+      }
+    }
+    if (covered) continue;
+    // 16-pixel chunks on the frame's 16-pixel grid (48 bytes = three aligned 16-byte vectors), one (chunk, row) per
+    // thread.  skip = the pixels of the chunk that are not this tile's to copy (outside the support's columns, or
+    // inside a next-level support: that level's blend writes them in this very phase, they must not be touched).
+    const int c0 = x0 >> 4, nc = ((x1 - 1) >> 4) - c0 + 1, nrow = y1 - ty0;
+    if (many || !vec16) {
+      const int wpx = x1 - x0;
+      for (int q = t; q < wpx * nrow; q += kCT) bbo_c_pixel(jobs, J, W, bs.X, bs.Y, x0 + q % wpx, ty0 + q / wpx);
+      continue;
+    }
+    for (int idx = t; idx < nc * nrow; idx += kCT) {
+      const int y = ty0 + idx / nc, xc = (c0 + idx % nc) * 16;
+      unsigned skip = 0;
+      if (xc < x0) skip |= (1u << (x0 - xc)) - 1u;
+      if (xc + 16 > x1) skip |= 0xFFFFu & ~((1u << (x1 - xc)) - 1u);
+      for (unsigned h = hit; h; h &= h - 1) {
+        const int32_t* r = bs.excl[__ffs(h) - 1];
+        if (y < r[1] || y >= r[3]) continue;
+        const int a = imax(r[0] - xc, 0), b = imin(r[2] - xc, 16);
+        if (b > a) skip |= ((1u << b) - 1u) & ~((1u << a) - 1u);
+      }
+      if (skip == 0xFFFFu) continue;
+      const size_t o = ((size_t)y * W + xc) * 3;
+      if (skip == 0u) {
+        const uint4* q = reinterpret_cast<const uint4*>(bs.X + o);
+        const uint4 a0 = q[0], a1 = q[1], a2 = q[2];
+        uint4* d = reinterpret_cast<uint4*>(bs.Y + o);
         d[0] = a0; d[1] = a1; d[2] = a2;
         continue;
       }
-      for (int i = 0; i < 4; ++i)
-        if (xg + i >= x0 && xg + i < x1) bbo_c_pixel(jobs, J, W, bs.X, bs.Y, xg + i, y);
+      for (int i = 0; i < 16; ++i)
+        if (!(skip >> i & 1u)) {
+          bs.Y[o + 3 * i] = bs.X[o + 3 * i];
+          bs.Y[o + 3 * i + 1] = bs.X[o + 3 * i + 1];
+          bs.Y[o + 3 * i + 2] = bs.X[o + 3 * i + 2];
+        }
     }
   }
 }
+
 // one pixel of a bg-only op with hoisted coordinate terms (same arithmetic as bg_pixel / eval_op)
 __device__ __forceinline__ void bg_pixel_fast(const DevPlan& P, const Lane& L, const RegOp& R, int ax, int bx,
                                               const double* div255, int x, int y) {
@@ -1042,7 +1185,7 @@ __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, ChainSmem& S, uint8_
       for (int i = 0; i < n; ++i) Mv[i] = mf[i];
     }
   }
-  __syncthreads();  // the previous sub-tile's gathers are done
+  worker_sync();  // the previous sub-tile's gathers are done
   const bool fast = staged && rows <= 96;
   if (staged) {
     stage_rows(dyn, pitch_i, L.in, W, H, 3, sr[0], sr[1], rows);
@@ -1050,7 +1193,7 @@ __device__ OADG_HANDLER void bg_subtile(const ChainArgs& A, ChainSmem& S, uint8_
     fill_rowoff(S.rowoff[0], si, rows);
     fill_rowoff(S.rowoff[1], sm, rows);
   }
-  __syncthreads();
+  worker_sync();
   if (!active) return;
   const WarpRowTerm rt = warp_row_term(R.minv, y);
   unsigned keep_mask = 0;
@@ -1145,6 +1288,39 @@ __device__ __forceinline__ void pixel_op_fast(const ChainArgs& A, const Lane& L,
   q[0] = (uint8_t)out[0]; q[1] = (uint8_t)out[1]; q[2] = (uint8_t)out[2];
 }
 
+// the 4 pixels of one thread of a bg-only sub-tile whose source rectangle is staged (rows > 0)
+struct BgPx {
+  const uint8_t* st;     // staged frame rows, followed by the staged mask rows
+  int xb, ry0, xm;
+  const int2* col;
+  WarpRowTerm rt;
+  int n;                 // pixels of the group inside the frame
+  const double* div255;  // shared memory
+};
+template <int kMode>
+__device__ __forceinline__ void bg_pixels4(const BgPx& P, const uint32_t in_w[3], const float Mv[4], uint32_t out_w[3]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int px[3] = {0, 0, 0};
+    if (i < P.n) {
+      int sx, sy, fx, fy;
+      col_coord(P.rt, P.col[i], sx, sy, fx, fy);
+      tma_fetch3<kMode>(P.st, P.xb, P.ry0, sx, sy, fx, fy, px);
+      const int wm = tma_fetch1<kMode>(P.st + kStageImgBytes, P.xm, P.ry0, sx, sy, fx, fy);
+      const float M = Mv[i];
+      if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
+        const double am = P.div255[wm];  // wm / 255 in float64, tabulated (exactly the reference's quotient)
+        const double keep = (double)M > am ? (double)M : am;
+        const double rest = dsub(1.0, keep);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) px[c] = bg_blend_fast(keep, rest, byte_of(in_w, 3 * i + c), px[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)px[c] << (((3 * i + c) & 3) * 8);
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // one tile (512 or 256 x 16 px) of one depth step of one lane (oa_mix.py:226-234), handled per 64 x 16 sub-tile:
 //   STREAM  one table-lookup / bbo-copy region covers the sub-tile: 16-pixel runs move as three 16-byte vectors per
@@ -1163,7 +1339,7 @@ __device__ OADG_HANDLER unsigned step_tile(const ChainArgs& A, ChainSmem& S, uin
   const int x0 = (local % tx) * tw, y0 = (local / tx) * kStepTileH;
   const int x1 = min(x0 + tw, W), y1 = min(y0 + kStepTileH, H);
   const int nsub = (x1 - x0 + kSubW - 1) / kSubW;
-  __syncthreads();   // the previous tile is done with the sub-tile classes and the column table
+  worker_sync();   // the previous tile is done with the sub-tile classes and the column table
   if (t < nsub) {
     const int sx0 = x0 + t * kSubW, sx1 = min(sx0 + kSubW, x1);
     const int region = tile_region(L, sx0, y0, sx1, y1);
@@ -1175,7 +1351,7 @@ __device__ OADG_HANDLER unsigned step_tile(const ChainArgs& A, ChainSmem& S, uin
     }
     S.sub_cls[t] = cls;
   }
-  __syncthreads();
+  worker_sync();
   bool any_bg = false, any_pixel = false;
   for (int s = 0; s < nsub; ++s) {
     any_bg |= (S.sub_cls[s] & 15) == kSubBg;
@@ -1215,7 +1391,8 @@ __device__ OADG_HANDLER unsigned step_tile(const ChainArgs& A, ChainSmem& S, uin
       const int y = y0 + (t >> 4);
       const bool row_ok = y < y1;
       const WarpRowTerm rt = warp_row_term(R.minv, y);
-      __syncthreads();   // the column table is in place
+      const int mode = gather_mode(R.minv);
+      worker_sync();   // the column table is in place
       for (int s = first; s >= 0;) {
         int nxt = -1;
         for (int k = nsub - 1; k > s; --k)
@@ -1243,40 +1420,50 @@ __device__ OADG_HANDLER unsigned step_tile(const ChainArgs& A, ChainSmem& S, uin
         tma::mbar_wait(&S.full[n_stage & 1u], (n_stage >> 1) & 1u);
         if (active) {
           const int* gr = S.gather_rect[n_stage & 1u];
-          const int rx0 = gr[0], ry0 = gr[1], rows = gr[2], xm = gr[3];
-          const uint8_t* st = dyn + (n_stage & 1u) * kStageBytes;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int px[3] = {0, 0, 0};
-            if (i < n) {
-              int sx, sy, fx, fy, wm = 0;
-              col_coord(rt, col[xg + i - x0], sx, sy, fx, fy);
-              if (rows > 0) {
-                tma_fetch3(st, rx0, ry0, sx, sy, fx, fy, px);
-                wm = tma_fetch1(st + kStageImgBytes, xm, ry0, sx, sy, fx, fy);
-              } else if (rows < 0) {
-                WarpTap tp;
-                tp.sx = imin(imax(sx, -32768), 32767); tp.sy = imin(imax(sy, -32768), 32767); tp.fx = fx; tp.fy = fy;
-                warp_fetch3(LdRO(), L.in, H, W, tp, px);
-                const bool bx0 = (unsigned)tp.sx < (unsigned)W, bx1 = fx != 0 && (unsigned)(tp.sx + 1) < (unsigned)W;
-                const bool by0 = (unsigned)tp.sy < (unsigned)H, by1 = fy != 0 && (unsigned)(tp.sy + 1) < (unsigned)H;
-                const uint8_t* r0 = mu + (size_t)tp.sy * W + tp.sx;
-                const uint8_t* r1 = r0 + W;
-                wm = bilerp_fix((by0 && bx0) ? ldb(r0) : 0, (by0 && bx1) ? ldb(r0 + 1) : 0, (by1 && bx0) ? ldb(r1) : 0,
-                                (by1 && bx1) ? ldb(r1 + 1) : 0, fx, fy);
-              }
-              const float M = Mv[i];
-              if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
-                const double am = S.div255[wm];  // wm / 255 in float64, tabulated (exactly the reference's quotient)
-                const double keep = (double)M > am ? (double)M : am;
-                const double rest = dsub(1.0, keep);
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                  px[c] = (int)dadd(dmul(keep, (double)byte_of(in_w, 3 * i + c)), dmul(rest, (double)px[c]));
-              }
+          const int rows = gr[2];
+          if (rows > 0) {
+            BgPx P4;
+            P4.st = dyn + (n_stage & 1u) * kStageBytes;
+            P4.xb = gr[0]; P4.ry0 = gr[1]; P4.xm = gr[3];
+            P4.col = col + (xg - x0);
+            P4.rt = rt; P4.n = n; P4.div255 = S.div255;
+            switch (mode) {
+              case 0: bg_pixels4<0>(P4, in_w, Mv, out_w); break;
+              case 1: bg_pixels4<1>(P4, in_w, Mv, out_w); break;
+              case 2: bg_pixels4<2>(P4, in_w, Mv, out_w); break;
+              default: bg_pixels4<3>(P4, in_w, Mv, out_w); break;
             }
+          } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)px[c] << (((3 * i + c) & 3) * 8);
+            for (int i = 0; i < 4; ++i) {
+              int px[3] = {0, 0, 0};
+              if (i < n) {
+                int sx, sy, fx, fy, wm = 0;
+                col_coord(rt, col[xg + i - x0], sx, sy, fx, fy);
+                if (rows < 0) {
+                  WarpTap tp;
+                  tp.sx = imin(imax(sx, -32768), 32767); tp.sy = imin(imax(sy, -32768), 32767); tp.fx = fx; tp.fy = fy;
+                  warp_fetch3(LdRO(), L.in, H, W, tp, px);
+                  const bool bx0 = (unsigned)tp.sx < (unsigned)W, bx1 = fx != 0 && (unsigned)(tp.sx + 1) < (unsigned)W;
+                  const bool by0 = (unsigned)tp.sy < (unsigned)H, by1 = fy != 0 && (unsigned)(tp.sy + 1) < (unsigned)H;
+                  const uint8_t* r0 = mu + (size_t)tp.sy * W + tp.sx;
+                  const uint8_t* r1 = r0 + W;
+                  wm = bilerp_fix((by0 && bx0) ? ldb(r0) : 0, (by0 && bx1) ? ldb(r0 + 1) : 0, (by1 && bx0) ? ldb(r1) : 0,
+                                  (by1 && bx1) ? ldb(r1 + 1) : 0, fx, fy);
+                }
+                const float M = Mv[i];
+                if (M != 0.f || wm != 0) {  // keep == 0 => 0*img + 1*aug == aug exactly
+                  const double am = S.div255[wm];
+                  const double keep = (double)M > am ? (double)M : am;
+                  const double rest = dsub(1.0, keep);
+#pragma unroll
+                  for (int c = 0; c < 3; ++c)
+                    px[c] = (int)dadd(dmul(keep, (double)byte_of(in_w, 3 * i + c)), dmul(rest, (double)px[c]));
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < 3; ++c) out_w[(3 * i + c) >> 2] |= (uint32_t)px[c] << (((3 * i + c) & 3) * 8);
+            }
           }
           if (n == 4) {
             uint32_t* q = reinterpret_cast<uint32_t*>(L.out + o);
@@ -1285,7 +1472,7 @@ __device__ OADG_HANDLER unsigned step_tile(const ChainArgs& A, ChainSmem& S, uin
             for (int k = 0; k < 3 * n; ++k) L.out[o + k] = (uint8_t)byte_of(out_w, k);
           }
         }
-        __syncthreads();   // the stage (and its rectangle record) may be refilled
+        worker_sync();   // the stage (and its rectangle record) may be refilled
         ++n_stage;
         s = nxt;
       }
@@ -1331,10 +1518,10 @@ __device__ OADG_HANDLER unsigned step_tile(const ChainArgs& A, ChainSmem& S, uin
 // stage a lane record, its LUTs and its region ops in shared memory (once per lane a CTA works on)
 __device__ OADG_HANDLER void stage_lane(const ChainArgs& A, ChainSmem& S, int lane) {
   const int t = threadIdx.x;
-  __syncthreads();
+  worker_sync();
   if (t < (int)(sizeof(Lane) / 4))
     reinterpret_cast<uint32_t*>(&S.lane)[t] = reinterpret_cast<const uint32_t*>(A.lanes + lane)[t];
-  __syncthreads();
+  worker_sync();
   const Lane& L = S.lane;
 #pragma unroll
   for (int r = 0; r < OADG_MAX_REGIONS; ++r) {
@@ -1351,24 +1538,30 @@ __device__ OADG_HANDLER void stage_lane(const ChainArgs& A, ChainSmem& S, int la
 #pragma unroll
     for (int i = 0; i < 6; ++i) S.rop[t].minv[i] = op.minv[i];
   }
-  __syncthreads();
+  worker_sync();
 }
 
 // kStats: per-kind CTA time accounting with %globaltimer and global atomics (oadg_oamix_execute_profiled only; the
 // production instantiation carries none of it)
+//
+// Warps 0-7 (256 threads) are the WORKERS: they run the tile handlers.  Warp 8 is the SCHEDULER: while the workers
+// process tile n it claims tile n + 1 (ticket + item record into the other slot) and publishes tile n - 1 (release
+// fence, dependency counters, tickets of the successors), so none of the queue's memory round trips sits between two
+// tiles of the workers.  Hand-over is two named barriers per slot.
 template <bool kStats>
-__global__ void __launch_bounds__(kCT, kCtaPerSm)
+__global__ void __launch_bounds__(kCtaThreads, kCtaPerSm)
 oamix_chain_kernel(const ChainArgs Aparam) {
   __shared__ ChainSmem S;
   extern __shared__ __align__(128) uint8_t dyn[];   // kDynSmem bytes, see the layout above
   if (threadIdx.x == 0) {
     S.args = Aparam;
     S.bs_key = -1;
+    S.done_seq = 0u;
     tma::mbar_init(&S.full[0], 1);
     tma::mbar_init(&S.full[1], 1);
     tma::mbar_fence_init();
   }
-  S.div255[threadIdx.x] = (double)threadIdx.x / 255.0;   // kCT == 256
+  if (threadIdx.x < 256) S.div255[threadIdx.x] = (double)threadIdx.x / 255.0;
   __syncthreads();
   const ChainArgs& A = S.args;
   // tickets of the items that start ready (host-assigned ranges, priority order)
@@ -1377,31 +1570,105 @@ oamix_chain_kernel(const ChainArgs Aparam) {
     const int it0 = (int)(unsigned)e;
     const unsigned long long first = e >> 32;
     const int nt = A.items[it0].ntiles;
-    for (int t = threadIdx.x; t < nt; t += kCT)
+    for (int t = threadIdx.x; t < nt; t += kCtaThreads)
       st_release_u64(A.tickets + first + t, ((unsigned long long)(unsigned)(it0 + 1) << 32) | (unsigned)t);
   }
+  if (threadIdx.x >= kCT) {
+    // ---------------------------------------------------------------- scheduler warp
+    // Iteration n hands tile n to the workers.  A finished tile is published as soon as the scheduler sees it --
+    // in particular while it waits for an unpublished ticket: the work it waits for may depend on that very tile.
+    const int lane = threadIdx.x & 31;
+    unsigned published = 0;
+    auto publish_ready = [&]() {   // warp-uniform: publish the tiles the workers have finished; returns how many
+      unsigned done = 0;
+      if (lane == 0) done = ld_acquire_cta_u32(&S.done_seq);
+      done = __shfl_sync(0xffffffffu, done, 0);
+      unsigned cnt = 0;
+      while (published < done) {
+        publish_tile(A, S.slot[published & 1u].I);
+        ++published;
+        ++cnt;
+      }
+      return cnt;
+    };
+    for (unsigned n = 0;; ++n) {
+      const int k = (int)(n & 1u);
+      while (n >= 2 && published < n - 1) {   // slot k still holds tile n - 2: the workers are finishing it
+        if (!publish_ready()) __nanosleep(32);
+      }
+      int item = -1, tile = -1;
+      unsigned long long T = 0, t_enter = 0;
+      if (kStats && lane == 0) t_enter = globaltimer_ns();
+      if (lane == 0) T = atomicAdd(A.ring + 1, 1ull);
+      T = __shfl_sync(0xffffffffu, T, 0);
+      if (T < (unsigned long long)A.n_tiles) {
+        unsigned long long spin_t0 = 0;
+        for (;;) {
+          unsigned long long e = 0;
+          if (lane == 0) e = ld_acquire_u64(A.tickets + T);   // acquire: the item's inputs are complete
+          e = __shfl_sync(0xffffffffu, e, 0);
+          if (e != 0ull) {
+            item = (int)(unsigned)(e >> 32) - 1;
+            tile = (int)(unsigned)e;
+            break;
+          }
+          if (publish_ready()) continue;
+          __nanosleep(64);   // the ticket is not published yet
+          bool give_up = false;
+          if (lane == 0) {
+            if (kStats) atomicAdd(A.kind_ns + 16 + 10, 1ull);   // measurement aid: polls that found the ticket unpublished
+            const unsigned long long now = globaltimer_ns();
+            if (spin_t0 == 0) spin_t0 = now;
+            else if (now - spin_t0 > 2000000000ull) {   // safety valve: sticky fault flag instead of a hung GPU
+              atomicAdd(A.fault, 1u);
+              give_up = true;
+            }
+          }
+          if (__shfl_sync(0xffffffffu, (int)give_up, 0)) break;
+        }
+        if (kStats && lane == 0 && item >= 0) {   // slot 11 = claims whose ticket was there, slot 12 = the others
+          const int kk = spin_t0 ? 12 : 11;
+          atomicAdd(A.kind_ns + kk, globaltimer_ns() - t_enter);
+          atomicAdd(A.kind_ns + 16 + kk, 1ull);
+        }
+      }
+      if (item >= 0) {
+        constexpr int kItemWords = (int)(sizeof(Item) / 4);
+        uint32_t w = 0;
+        if (lane < kItemWords) w = reinterpret_cast<const uint32_t*>(A.items + item)[lane];
+        if (lane < kItemWords) reinterpret_cast<uint32_t*>(&S.slot[k].I)[lane] = w;
+        const int perm_first = __shfl_sync(0xffffffffu, (int)w, (int)(offsetof(Item, perm_first) / 4));
+        if (lane == 0) S.slot[k].tile = perm_first >= 0 ? A.perm[perm_first + tile] : tile;
+      }
+      if (lane == 0) S.slot[k].item = item;
+      __syncwarp();
+      bar_arrive_all(2 + k);          // the workers may start tile n
+      if (item < 0) {                 // drained: publish what the workers still hold, then leave
+        while (published < n)
+          if (!publish_ready()) __nanosleep(32);
+        break;
+      }
+      publish_ready();
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ workers
   int staged_lane = -1;
   unsigned n_stage = 0;   // gather stages used so far by this CTA (stage = n & 1, mbarrier parity = (n >> 1) & 1)
-  if (threadIdx.x == 0) {
-    int item = -1, tile = -1;
-    unsigned long long w0 = 0;
-    if (kStats) w0 = globaltimer_ns();
-    if (!claim_work(A, item, tile, kStats)) item = -1;
-    if (kStats) atomicAdd(A.kind_ns + 10, globaltimer_ns() - w0);
-    S.next_item = item;
-    S.next_tile = tile;
-  }
-  __syncthreads();
-  int it = S.next_item, tile = S.next_tile;
-  while (it >= 0) {
-    __syncthreads();  // every thread has read S.next_item / S.next_tile
-    const Item I = A.items[it];
-    const int local = I.perm_first >= 0 ? A.perm[I.perm_first + tile] : tile;
+  unsigned long long idle_t0 = 0;
+  if (kStats) idle_t0 = globaltimer_ns();
+  for (unsigned n = 0;; ++n) {
+    const int k = (int)(n & 1u);
+    bar_sync_all(2 + k);
+    const int it = S.slot[k].item;
+    if (it < 0) break;
+    const Item I = S.slot[k].I;
+    const int local = S.slot[k].tile;
     unsigned long long seg_t0 = 0;
     if (kStats) seg_t0 = globaltimer_ns();
     switch (I.kind) {
       case OADG_IT_PROFILE: profile_tile(A, S, dyn, I.obj); break;
-      case OADG_IT_MASK: mask_tile(A, S, I.obj, local, I.tx); break;
+      case OADG_IT_MASK: mask_tile(A, S, dyn, I.obj, local, I.tx); break;
       case OADG_IT_HIST: {
         const Lane& L = A.lanes[I.obj];
         unsigned long long lsum = 0;
@@ -1429,28 +1696,20 @@ oamix_chain_kernel(const ChainArgs Aparam) {
         break;
       default: break;
     }
-    publish_tile(A, I);
-    if (threadIdx.x == 0) {
-      unsigned long long t1 = 0;
-      if (kStats) t1 = globaltimer_ns();
-      int item = it, nt = -1;
-      if (!claim_work(A, item, nt, kStats)) item = -1;
-      if (kStats) {
-        const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
-        const unsigned long long dt = t1 - seg_t0;
-        atomicAdd(A.kind_ns + kk, dt);
-        atomicAdd(A.kind_ns + 16 + kk, 1ull);
-        atomicMax(A.kind_ns + 32 + kk, dt);
-        atomicAdd(A.kind_ns + 10, globaltimer_ns() - t1);   // slot 10: looking / waiting for ready work
-        atomicMax(A.item_ts + 2 * it, (1ull << 63) - seg_t0);
-        atomicMax(A.item_ts + 2 * it + 1, t1);
-      }
-      S.next_item = item;
-      S.next_tile = nt;
+    if (kStats && threadIdx.x == 0) {
+      const unsigned long long t1 = globaltimer_ns();
+      const int kk = I.kind == OADG_IT_STEP ? S.step_class : I.kind;   // 7 stream, 8 bg staged, 9 mixed / per pixel
+      const unsigned long long dt = t1 - seg_t0;
+      atomicAdd(A.kind_ns + kk, dt);
+      atomicAdd(A.kind_ns + 16 + kk, 1ull);
+      atomicMax(A.kind_ns + 32 + kk, dt);
+      atomicAdd(A.kind_ns + 10, seg_t0 - idle_t0);   // slot 10: the workers waited for the scheduler's next tile
+      atomicMax(A.item_ts + 2 * it, (1ull << 63) - seg_t0);
+      atomicMax(A.item_ts + 2 * it + 1, t1);
+      idle_t0 = t1;
     }
-    __syncthreads();
-    it = S.next_item;
-    tile = S.next_tile;
+    worker_sync();   // every worker's stores of the tile are issued ...
+    if (threadIdx.x == 0) st_release_cta_u32(&S.done_seq, n + 1u);   // ... finished: the scheduler publishes the tile
   }
 }
 
@@ -1551,8 +1810,8 @@ struct CudaBackend {
       int nb = 0, nb2 = 0;
       if (cudaFuncSetAttribute(oamix_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
       if (cudaFuncSetAttribute(oamix_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem) != cudaSuccess) return -1;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oamix_chain_kernel<false>, kCT, kDynSmem) != cudaSuccess) return -1;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, oamix_chain_kernel<true>, kCT, kDynSmem) != cudaSuccess) return -1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, oamix_chain_kernel<false>, kCtaThreads, kDynSmem) != cudaSuccess) return -1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, oamix_chain_kernel<true>, kCtaThreads, kDynSmem) != cudaSuccess) return -1;
       nb = nb2 < nb ? nb2 : nb;
       ctas_per_sm = nb < 1 ? 0 : (nb > kCtaPerSm ? kCtaPerSm : nb);
       if (const char* e = getenv("OADG_CTAS_PER_SM")) {   // experiments
@@ -1636,7 +1895,7 @@ struct CudaBackend {
       void* params[1] = {(void*)&args};
       // cooperative launch: all CTAs are guaranteed co-resident, which the in-kernel dependency waits rely on
       const void* fn = profile ? (const void*)oamix_chain_kernel<true> : (const void*)oamix_chain_kernel<false>;
-      BE_TRY(cudaLaunchCooperativeKernel(fn, dim3(A.grid), dim3(kCT), params, kDynSmem, stream));
+      BE_TRY(cudaLaunchCooperativeKernel(fn, dim3(A.grid), dim3(kCtaThreads), params, kDynSmem, stream));
       ++launches;
       if (slot) {   // the launch's fault flag travels to the upload slot; the slot's event now covers it
         BE_TRY(cudaMemcpyAsync(slot->fault, A.fault, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
