@@ -130,6 +130,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1595,6 +1600,20 @@ oamix_chain_kernel(const ChainArgs Aparam) {
       const int k = (int)(n & 1u);
       while (n >= 2 && published < n - 1) {   // slot k still holds tile n - 2: the workers are finishing it
         if (!publish_ready()) __nanosleep(32);
+      }
+      // Claiming AHEAD (while the workers are still on tile n - 1) hides the claim's round trips, but a ticket held
+      // by a busy CTA is a tile nobody runs: when published tickets are scarce (fewer than two per CTA unclaimed),
+      // the claim waits until the workers are done -- idle CTAs then find the tile at once.
+      if (n >= 1) {
+        for (;;) {
+          int go = 1;
+          if (lane == 0) {
+            const long long avail = (long long)ld_relaxed_u64(A.ring) - (long long)ld_relaxed_u64(A.ring + 1);
+            go = avail > 2ll * A.grid || ld_acquire_cta_u32(&S.done_seq) >= n;
+          }
+          if (__shfl_sync(0xffffffffu, go, 0)) break;
+          if (!publish_ready()) __nanosleep(100);
+        }
       }
       int item = -1, tile = -1;
       unsigned long long T = 0, t_enter = 0;

@@ -199,8 +199,46 @@ struct HostBackend {
   // The host twin therefore runs the items in an ADVERSARIAL order that honours nothing but the dependency table:
   // it always picks the LAST item of the queue whose dependencies are done (n_cta > 1), or the FIRST one like the
   // device does (n_cta == 1).  A missing dependency shows up as a wrong image in the tests.
+  std::vector<int32_t> dump;   // {n_items, then per item: kind, obj, ntiles, aux, streaming, dep_count, deps...}
+  bool want_dump = false;
   int chain(const ChainArgs& Adev, const ChainArgs& A, const PlanView&) {
     (void)Adev;
+    if (want_dump) {
+      dump.clear();
+      dump.push_back(A.n_items);
+      for (int k = 0; k < A.n_items; ++k) {
+        const Item& I = A.items[k];
+        dump.push_back(I.kind); dump.push_back(I.obj); dump.push_back(I.ntiles); dump.push_back(I.aux);
+        dump.push_back(I.kind == OADG_IT_STEP ? A.lanes[I.obj].all_streaming : 0);
+        int cls_n[4] = {0, 0, 0, 0};   // step items: tiles per class (0 stream, 1 per pixel, 2 bg-only, 3 box edge + bg-only)
+        if (I.kind == OADG_IT_STEP) {
+          const Lane& ln = A.lanes[I.obj];
+          const int tw = I.aux, th = kStepTileH;
+          for (int ti = 0; ti < I.ntiles; ++ti) {
+            const int x0 = (ti % I.tx) * tw, y0 = (ti / I.tx) * th;
+            const int x1 = x0 + tw < ln.W ? x0 + tw : ln.W, y1 = y0 + th < ln.H ? y0 + th : ln.H;
+            int region = ln.n_ml, c = 0;
+            bool edge = false, any_bg = false;
+            for (int bb = 0; bb < ln.n_ml; ++bb) {
+              const int32_t* B = ln.box[bb];
+              if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;
+              if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = bb;
+              else edge = true;
+            }
+            for (int r = 0; r <= ln.n_ml; ++r) any_bg |= ln.kind[r] == OADG_OP_BG_AFFINE;
+            if (edge) c = any_bg ? 3 : 1;
+            else if (ln.kind[region] == OADG_OP_BG_AFFINE) c = 2;
+            else c = (is_lut_kind(ln.kind[region]) || ln.kind[region] == OADG_OP_BBO_AFFINE) ? 0 : 1;
+            ++cls_n[c];
+          }
+        }
+        for (int c = 0; c < 4; ++c) dump.push_back(cls_n[c]);
+        dump.push_back(I.dep_count);
+        for (int d = 0; d < I.dep_count; ++d) dump.push_back(A.deps[I.dep_first + d]);
+      }
+      ++launches;
+      return 0;   // tables only: nothing is executed
+    }
     n_phases = 0;
     n_items += A.n_items;
     std::vector<char> finished(A.n_items, 0);
@@ -239,6 +277,7 @@ struct HostBackend {
     return 0;
   }
   int mix(const DevPlan& P, const MixJob* jobs, int n) {
+    if (want_dump) return 0;
     for (int k = 0; k < n; ++k) {
       const oadg_view_t& V = P.views[jobs[k].view];
       for (int y0 = 0; y0 < V.H; y0 += kTileH)
@@ -299,4 +338,22 @@ extern "C" int hostsim_oamix_execute_ex(const void* plan, size_t bytes, const ui
   }
   free(ws);
   return rc;
+}
+
+// measurement aid: the work queue (items, tiles, dependencies) the scheduler builds for a plan, without executing it
+extern "C" int hostsim_oamix_dump(const void* plan, size_t bytes, const uint8_t* const* src, int n_img,
+                                  uint8_t* const* dst, int32_t* out, int cap) {
+  size_t need = 0;
+  int rc = hostsim_workspace_bytes(plan, bytes, &need);
+  if (rc) return rc;
+  void* ws = aligned_alloc(256, (need + 255) / 256 * 256 + 256);
+  if (!ws) return -100;
+  HostBackend be;
+  be.want_dump = true;
+  rc = execute_plan(be, plan, bytes, src, n_img, dst, ws, need);
+  free(ws);
+  if (rc) return rc;
+  const int n = (int)be.dump.size();
+  if (out && n <= cap) memcpy(out, be.dump.data(), (size_t)n * sizeof(int32_t));
+  return n;
 }
