@@ -78,16 +78,16 @@ def workload_config(n_gpus):
             'sharding': ('by image, %d rank(s); OA-Mix: no collective; OA-Loss: one all-gather of RoI embeddings'
                          % n_gpus) if n_gpus > 1 else 'single rank',
             'l2': 'inputs larger than L2: %d distinct source frames (%.0f MB) cycled' % (POOL, POOL * H * W * 3 / 1e6),
-            'pipeline': 'OAMix.iter_batches: saliency two batches ahead, kernel chain one batch ahead of the step '
-                        'that consumes it'}
+            'pipeline': 'OAMix.iter_batches: steps travel in groups (1, 2, then 4 steps per plan and chain launch); '
+                        'saliency two groups ahead, kernel chain one group ahead of the step that consumes it'}
 
 
 # ------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region: an in-process NVML poller (every 5 ms, so that even a
-    sub-second region gets tens of samples), or `nvidia-smi -lms 50` when NVML is not importable."""
+    """SM clock + throttle reasons DURING the timed region: an in-process NVML poller (every 1 ms, so that even a
+    10 ms region gets several samples), or `nvidia-smi -lms 50` when NVML is not importable."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -109,7 +109,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:   # noqa: BLE001  (a failed poll is just a missing sample)
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def start(self):
         try:
@@ -142,7 +142,7 @@ class ClockSampler:
             self.stop_flag = True
             self.thread.join(timeout=2)
             return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.max_mhz,
-                    'samples': len(self.sm), 'reasons': sorted(self.reasons), 'source': 'nvml, 5 ms poll'}
+                    'samples': len(self.sm), 'reasons': sorted(self.reasons), 'source': 'nvml, 1 ms poll'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -296,24 +296,7 @@ def product_arm(args):
             return gathered_contrastive_loss(xin, labels_dev, temperature=LOSS_CFG['temperature'],
                                              loss_weight=LOSS_CFG['loss_weight'], backend=gbe)
         return loss_fn(xin, labels_dev)
-    out_bufs = [torch.empty_like(dev_frames[0]) for _ in range(BS)]
     stream = torch.cuda.current_stream(dev)
-
-    def step(i, profile=None, with_loss=True):
-        j = (i * BS) % POOL
-        imgs = [dev_frames[(j + b) % POOL] for b in range(BS)]
-        g = [gts[(j + b) % POOL] for b in range(BS)]
-        if profile is None:   # like a loader that knows the next batch: its saliency scores are requested now, ahead of
-            jn = ((i + 1) * BS) % POOL   # this step's kernels, and are finished when step i + 1 asks for them
-            mix.prefetch_saliency([dev_frames[(jn + b) % POOL] for b in range(BS)], [gts[(jn + b) % POOL] for b in range(BS)])
-        mix.oamix_batch(imgs, g, profile=profile, outs=out_bufs, inputs_ready=True)  # frames resident since setup
-        n_mix = mix.last_launches
-        if not with_loss:
-            return n_mix, None
-        x_dev.grad = None
-        loss = run_loss(x_dev)
-        loss.backward()
-        return n_mix, loss
 
     def dev_batches(n):
         for i in range(n):
@@ -417,8 +400,10 @@ def product_arm(args):
     # ---- roofline of the dominant kernel: event-instrumented replay of the same seeded plans (rank 0)
     prof = {}
     np.random.seed(1000 + rank)
-    for i in range(args.steps):
-        step(i, profile=prof, with_loss=False)   # rank 0 only: no collective may be issued here
+    gb = max(1, int(mix.group_batches))
+    for i0 in range(0, args.steps, gb):   # the loader loop's launches: the views of `gb` consecutive steps per plan
+        idx = [((i * BS) % POOL + b) % POOL for i in range(i0, min(i0 + gb, args.steps)) for b in range(BS)]
+        mix.oamix_batch([dev_frames[j] for j in idx], [gts[j] for j in idx], profile=prof, inputs_ready=True)
     torch.cuda.synchronize()
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
@@ -460,9 +445,7 @@ def product_arm(args):
     torch.cuda.synchronize()
     loop_ms = e0.elapsed_time(e1)
     roofline['as_run_in_timed_region'] = {
-        'mode': 'OAMix.iter_batches; batch overlap ' + (
-            'on: 2-CTA/SM chain launches, two in flight on two streams' if mix.overlap_batches else
-            'off: one full-width chain launch after the other'),
+        'mode': 'OAMix.iter_batches; the views of up to %d consecutive steps per plan / chain launch' % gb,
         'oamix_ms_per_batch': loop_ms / args.steps,
         'achieved': prof.get('step_bytes', 0) / (loop_ms / 1e3) / 1e9, 'unit': 'GB/s',
         'frac': prof.get('step_bytes', 0) / (loop_ms / 1e3) / 1e9 / peak,

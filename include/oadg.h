@@ -223,9 +223,9 @@ int oadg_oamix_execute_profiled(const void* plan_host, size_t plan_bytes,
 
 /* A chain-kernel CTA that finds no ready work for 2 s (inconsistent dependency tables, a stalled device) leaves
  * the kernel and raises a sticky device flag instead of hanging the GPU; the flag of every launch is copied to
- * page-locked memory behind the launch.  This call reports it for the launches of the CALLING THREAD:
+ * page-locked memory behind the launch.  This call reports it for the launches of this process so far:
  * wait != 0 waits for all of them, wait == 0 looks at the finished ones.  Returns OADG_E_PLAN when a launch left
- * views incomplete (the same code the next oadg_oamix_execute* call of this thread would return), else 0. */
+ * views incomplete (the same code the next oadg_oamix_execute* call would return), else 0. */
 int oadg_oamix_poll_fault(int wait);
 
 /* Measurement aid (set OADG_TRACE=1): per work item of the last profiled execution {kind, obj, tiles, dependency

@@ -21,6 +21,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "oadg_common.cuh"
 #include "oadg_tma.cuh"
 #include "oamix_exec.h"
@@ -1599,7 +1602,7 @@ oamix_chain_kernel(const ChainArgs Aparam) {
     for (unsigned n = 0;; ++n) {
       const int k = (int)(n & 1u);
       while (n >= 2 && published < n - 1) {   // slot k still holds tile n - 2: the workers are finishing it
-        if (!publish_ready()) __nanosleep(32);
+        if (!publish_ready()) __nanosleep(400);
       }
       // Claiming AHEAD (while the workers are still on tile n - 1) hides the claim's round trips, but a ticket held
       // by a busy CTA is a tile nobody runs: when published tickets are scarce (fewer than two per CTA unclaimed),
@@ -1612,7 +1615,7 @@ oamix_chain_kernel(const ChainArgs Aparam) {
             go = avail > 2ll * A.grid || ld_acquire_cta_u32(&S.done_seq) >= n;
           }
           if (__shfl_sync(0xffffffffu, go, 0)) break;
-          if (!publish_ready()) __nanosleep(100);
+          if (!publish_ready()) __nanosleep(300);
         }
       }
       int item = -1, tile = -1;
@@ -1632,7 +1635,7 @@ oamix_chain_kernel(const ChainArgs Aparam) {
             break;
           }
           if (publish_ready()) continue;
-          __nanosleep(64);   // the ticket is not published yet
+          __nanosleep(200);   // the ticket is not published yet
           bool give_up = false;
           if (lane == 0) {
             if (kStats) atomicAdd(A.kind_ns + 16 + 10, 1ull);   // measurement aid: polls that found the ticket unpublished
@@ -1664,7 +1667,7 @@ oamix_chain_kernel(const ChainArgs Aparam) {
       bar_arrive_all(2 + k);          // the workers may start tile n
       if (item < 0) {                 // drained: publish what the workers still hold, then leave
         while (published < n)
-          if (!publish_ready()) __nanosleep(32);
+          if (!publish_ready()) __nanosleep(200);
         break;
       }
       publish_ready();
@@ -1761,12 +1764,15 @@ mix_kernel(DevPlan P, const MixJob* jobs) {
     if (_e != cudaSuccess) return (int)_e; \
   } while (0)
 
-// Plan + launch tables go up through a small ring of page-locked buffers (per calling thread): a copy from pageable
-// memory may make the host wait for the stream's earlier kernels, which would serialise the loader loop with the
-// GPU.  A slot also receives the launch's fault flag (a CTA gave up waiting for work: the dependency tables were
-// inconsistent); it is reused once everything that touches it has finished (event), and a raised flag is reported
-// by the next call that looks at the slot (or by oadg_oamix_poll_fault).
+// Plan + launch tables go up through a small process-wide ring of page-locked buffers: a copy from pageable memory
+// may make the host wait for the stream's earlier kernels, which would serialise the loader loop with the GPU, and
+// pinning memory costs milliseconds, so the buffers outlive the calling thread (a loader starts a new worker thread
+// per epoch).  A slot also receives the launch's fault flag (a CTA gave up waiting for work: the dependency tables
+// were inconsistent); it is reused once everything that touches it has finished (event), and a raised flag is
+// reported by the next call that looks at the slot (or by oadg_oamix_poll_fault).  A slot is owned (mutex) by the
+// call that fills it until its launch is enqueued.
 struct PinSlot {
+  std::mutex mu;
   void* p = nullptr;
   size_t cap = 0;
   cudaEvent_t ev = nullptr;
@@ -1774,14 +1780,19 @@ struct PinSlot {
   int dev = -1;
   bool busy = false;
 };
-constexpr int kPinSlots = 4;
-thread_local PinSlot g_pin[kPinSlots];
-thread_local int g_pin_next = 0;
+constexpr int kPinSlots = 8;
+PinSlot g_pin[kPinSlots];
+std::atomic<unsigned> g_pin_next{0};
 
-// collect the fault flags of finished launches (wait = true: of all launches of this thread); OADG_E_PLAN if any
+// collect the fault flags of finished launches (wait = true: of all launches so far); OADG_E_PLAN if any
 int poll_faults(bool wait) {
   int rc = 0;
   for (PinSlot& sl : g_pin) {
+    std::unique_lock<std::mutex> lk(sl.mu, std::try_to_lock);
+    if (!lk.owns_lock()) {
+      if (!wait) continue;
+      lk.lock();
+    }
     if (!sl.busy || !sl.ev) continue;
     if (wait) {
       BE_TRY(cudaEventSynchronize(sl.ev));
@@ -1846,18 +1857,61 @@ struct CudaBackend {
     const int c = (want_ctas >= 1 && want_ctas < ctas_per_sm) ? want_ctas : ctas_per_sm;
     return n_sm * c;
   }
+  // cuTensorMapEncodeTiled costs microseconds and the same frames (workspace, a loader's frame pool) come back launch
+  // after launch: encoded maps are kept per calling thread, keyed by everything that goes into them
+  struct MapKey {
+    const void* base;
+    size_t inner;
+    int rows, box;
+    bool operator==(const MapKey& o) const { return base == o.base && inner == o.inner && rows == o.rows && box == o.box; }
+  };
+  struct MapEntry {
+    MapKey key;
+    bool valid = false;
+    alignas(64) unsigned char map[kTensorMapBytes];
+  };
   int make_map(void* dst, const void* base, size_t inner_bytes, int rows, int box_inner) {
-    if (getenv("OADG_NO_TMA")) return -1;
-    return tma::encode_u8_2d(dst, base, inner_bytes, (uint64_t)rows, inner_bytes, (uint32_t)box_inner, kGatherBoxRows);
+    static const bool off = getenv("OADG_NO_TMA") != nullptr;
+    if (off) return -1;
+    constexpr int kSlots = 1024;
+    static thread_local std::vector<MapEntry> cache(kSlots);
+    const MapKey key{base, inner_bytes, rows, box_inner};
+    const size_t h = ((reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull + inner_bytes * 31 + (size_t)rows * 7 + box_inner) % kSlots;
+    MapEntry& e = cache[h];
+    if (!(e.valid && e.key == key)) {
+      if (tma::encode_u8_2d(e.map, base, inner_bytes, (uint64_t)rows, inner_bytes, (uint32_t)box_inner, kGatherBoxRows) != 0) {
+        e.valid = false;
+        return -1;
+      }
+      e.key = key;
+      e.valid = true;
+    }
+    memcpy(dst, e.map, kTensorMapBytes);
+    return 0;
+  }
+  ~CudaBackend() {
+    if (slot) slot->mu.unlock();
   }
   int upload(void* dst, const void* src, size_t bytes) {
     int rc = poll_faults(false);
     if (rc) return rc;
-    PinSlot& sl = g_pin[g_pin_next];
-    g_pin_next = (g_pin_next + 1) % kPinSlots;
+    {  // first call of the process: pin every slot now (milliseconds each), not one by one under a running loader
+      static std::once_flag once;
+      std::call_once(once, [] {
+        for (PinSlot& s0 : g_pin) {
+          std::lock_guard<std::mutex> lk(s0.mu);
+          if (!s0.p && cudaHostAlloc(&s0.p, (size_t)2 << 20, cudaHostAllocPortable) == cudaSuccess) s0.cap = (size_t)2 << 20;
+          if (!s0.fault && cudaHostAlloc((void**)&s0.fault, 64, cudaHostAllocPortable) == cudaSuccess) *s0.fault = 0;
+        }
+      });
+    }
+    PinSlot& sl = g_pin[g_pin_next.fetch_add(1u) % kPinSlots];
+    sl.mu.lock();
+    slot = &sl;   // released by the destructor, after the launch that uses the slot is enqueued
     int dev = 0;
     BE_TRY(cudaGetDevice(&dev));
     if (sl.ev && sl.dev != dev) {
+      if (sl.busy) cudaEventSynchronize(sl.ev);
       cudaEventDestroy(sl.ev);
       sl.ev = nullptr;
       sl.busy = false;
@@ -1880,14 +1934,14 @@ struct CudaBackend {
       if (sl.p) cudaFreeHost(sl.p);
       sl.p = nullptr;
       sl.cap = 0;
-      BE_TRY(cudaHostAlloc(&sl.p, 2 * bytes, cudaHostAllocPortable));
-      sl.cap = 2 * bytes;
+      const size_t cap = 2 * bytes > ((size_t)2 << 20) ? 2 * bytes : ((size_t)2 << 20);   // pinning costs milliseconds: be generous
+      BE_TRY(cudaHostAlloc(&sl.p, cap, cudaHostAllocPortable));
+      sl.cap = cap;
     }
     memcpy(sl.p, src, bytes);
     BE_TRY(cudaMemcpyAsync(dst, sl.p, bytes, cudaMemcpyHostToDevice, stream));
     BE_TRY(cudaEventRecord(sl.ev, stream));
     sl.busy = true;
-    slot = &sl;
     return 0;
   }
   int zero(void* dst, size_t bytes) {

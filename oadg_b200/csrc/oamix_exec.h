@@ -10,6 +10,14 @@
 
 #include "oamix_body.h"
 
+#ifdef OADG_SCHED_TIMING
+#include <chrono>
+#include <stdio.h>
+#define OADG_T(name) do { auto _n = std::chrono::steady_clock::now(); fprintf(stderr, "[sched] %-12s %7.1f us\n", name, std::chrono::duration<double, std::micro>(_n - _t0).count()); _t0 = _n; } while (0)
+#else
+#define OADG_T(name) do { } while (0)
+#endif
+
 namespace oadg {
 
 constexpr int kMagic = 0x4F414447;
@@ -362,6 +370,9 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
                  uint8_t* const* dst, void* workspace, size_t workspace_bytes) {
+#ifdef OADG_SCHED_TIMING
+  auto _t0 = std::chrono::steady_clock::now();
+#endif
   PlanView pv;
   int rc = parse_plan(plan_host, plan_bytes, pv);
   if (rc) return rc;
@@ -386,6 +397,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const int G = be.grid();
   if (G < 1) return OADG_E_LIMIT;
 
+  OADG_T("parse+layout");
   // host staging buffer: plan (with lut / scratch slots filled in) followed by the launch tables
   std::vector<char> stage(L.off_tables + L.tables_bytes, 0);
   memcpy(stage.data(), plan_host, plan_bytes);
@@ -452,6 +464,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     return slot;
   };
 
+  OADG_T("stage alloc");
   // ---- items with their earliest phase (dependencies are always scheduled before their consumers) ----------
   // `phase` (the length of the longest dependency chain below an item) only orders the work queue; what an item
   // actually waits for is its `deps` list (indices into `todo`).
@@ -643,6 +656,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       }
     }
   }
+  OADG_T("todo build");
   if ((int)todo.size() > L.max_items || (int)todo.size() > 4096) return OADG_E_LIMIT;   // 4096: the kernel's item bitmap
 
   // ---- the work queue: items ordered by PRIORITY = the length of the longest dependency chain that still hangs on
@@ -690,7 +704,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     });
     for (int k = 0; k < n_items; ++k) pos[order[k]] = k;
   }
+  OADG_T("priority sort");
   int n_tiles = 0, n_deps = 0, n_perm = 0;
+  std::vector<uint8_t> tile_cls;
   for (int k = 0; k < n_items; ++k) {
     const Todo& t = todo[order[k]];
     Item& it = items[k];
@@ -721,25 +737,34 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       // long tiles first: the item is complete when its LAST tile is, so the tail should be made of short ones
       const Lane& ln = lanes[t.obj];
       it.perm_first = n_perm;
-      for (int cls = 3; cls >= 0; --cls)
-        for (int ti = 0; ti < it.ntiles; ++ti) {
-          const int x0 = (ti % it.tx) * tw, y0 = (ti / it.tx) * th;
-          const int x1 = x0 + tw < ln.W ? x0 + tw : ln.W, y1 = y0 + th < ln.H ? y0 + th : ln.H;
-          int region = ln.n_ml, c = 0;
-          bool edge = false;
-          for (int bb = 0; bb < ln.n_ml; ++bb) {
-            const int32_t* B = ln.box[bb];
-            if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;
-            if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = bb;
-            else edge = true;
-          }
-          bool any_bg = false;
-          for (int r = 0; r <= ln.n_ml; ++r) any_bg |= ln.kind[r] == OADG_OP_BG_AFFINE;
-          if (edge) c = any_bg ? 3 : 1;
-          else if (ln.kind[region] == OADG_OP_BG_AFFINE) c = 2;
-          else c = (is_lut_kind(ln.kind[region]) || ln.kind[region] == OADG_OP_BBO_AFFINE) ? 0 : 1;
-          if (c == cls) perm[n_perm++] = ti;
+      bool any_bg = false;
+      for (int r = 0; r <= ln.n_ml; ++r) any_bg |= ln.kind[r] == OADG_OP_BG_AFFINE;
+      tile_cls.resize((size_t)it.ntiles);
+      int cls_count[4] = {0, 0, 0, 0};
+      for (int ti = 0; ti < it.ntiles; ++ti) {   // class of every tile: 3 box edge + bg-only, 2 bg-only, 1 per pixel, 0 stream
+        const int x0 = (ti % it.tx) * tw, y0 = (ti / it.tx) * th;
+        const int x1 = x0 + tw < ln.W ? x0 + tw : ln.W, y1 = y0 + th < ln.H ? y0 + th : ln.H;
+        int region = ln.n_ml, c = 0;
+        bool edge = false;
+        for (int bb = 0; bb < ln.n_ml; ++bb) {
+          const int32_t* B = ln.box[bb];
+          if (!(B[0] < x1 && B[2] > x0 && B[1] < y1 && B[3] > y0)) continue;
+          if (B[0] <= x0 && B[2] >= x1 && B[1] <= y0 && B[3] >= y1) region = bb;
+          else edge = true;
         }
+        if (edge) c = any_bg ? 3 : 1;
+        else if (ln.kind[region] == OADG_OP_BG_AFFINE) c = 2;
+        else c = (is_lut_kind(ln.kind[region]) || ln.kind[region] == OADG_OP_BBO_AFFINE) ? 0 : 1;
+        tile_cls[ti] = (uint8_t)c;
+        ++cls_count[c];
+      }
+      int at[4];   // counting sort, classes in descending order, tiles of a class in ascending order
+      at[3] = n_perm;
+      at[2] = at[3] + cls_count[3];
+      at[1] = at[2] + cls_count[2];
+      at[0] = at[1] + cls_count[1];
+      for (int ti = 0; ti < it.ntiles; ++ti) perm[at[tile_cls[ti]]++] = ti;
+      n_perm += it.ntiles;
     }
     it.dep_first = n_deps;
     it.dep_count = 0;
@@ -749,6 +774,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
       ++it.dep_count;
     }
   }
+  OADG_T("items+perm");
   {  // successor lists (the reverse of deps) and the number of dependency tiles every item starts with
     std::vector<int> cnt(n_items + 1, 0);
     for (int k = 0; k < n_items; ++k) {
@@ -794,6 +820,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     for (int b = 0; b < V.width; ++b) J.branch[b] = final_frame[(size_t)v * OADG_MAX_WIDTH + b];
   }
 
+  OADG_T("succ+ring+mix");
   // upload plan + tables in one copy; clear the barrier counter and the histograms in one memset
   rc = be.upload(ws + L.off_plan, stage.data(), stage.size());
   if (rc) return rc;
@@ -857,6 +884,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   Hh.perm = perm;
   Hh.pending = pending;
   Hh.ring = ring;
+  OADG_T("upload+zero");
   if ((rc = be.chain(A, Hh, pv))) return rc;
   return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);
 }

@@ -96,6 +96,15 @@ class _NativePlan:
     __slots__ = ('blob', 'ml_boxes', 'oa_boxes', 'depth_sums', 'hw')
 
 
+class _PlanSlice:
+    """The result-dict boxes of images [lo, hi) of a (grouped) native plan."""
+    __slots__ = ('ml_boxes', 'oa_boxes')
+
+    def __init__(self, plan, lo, hi):
+        self.ml_boxes = plan.ml_boxes[lo:hi]
+        self.oa_boxes = plan.oa_boxes[lo:hi]
+
+
 _RNG = None
 
 
@@ -162,23 +171,19 @@ class OAMix:
         if spatial_ratio != 4:
             raise NotImplementedError('libOADG is built for spatial_ratio=4 (all reference configs)')
         self._ws_cache = None
+        self._ws_min_views = 0
         self._sal_state = None
         self._sal_prefetch = {}
         self._sal_slot = 0
         self._native_cfg = None
         self._host_state = dict(dev={}, pin={})
         self._streams = {}
-        self._ws_lanes = {}
         self.pipe_profile = None
         self.pipe_launches = 0
-        # iter_batches can run consecutive batches as half-width launches on two streams, so that one batch's tiles
-        # fill the other's dependency stalls (OA-Mix alone: 736 -> 661 us per batch).  Opt-in (True, or
-        # OADG_OVERLAP=1): two resident chain launches never drain together and leave no SM with room for another
-        # kernel's large shared-memory blocks, so a consumer that runs such kernels between batches (the OA-Loss
-        # tcgen05 kernels need 193 KB) either starves or, through the view fence, stalls the chains -- the bench
-        # step then flips between 0.71 and 1.29 ms; NCCL kernels of a multi-rank job starve the same way.  With one
-        # full-width launch after the other there is a drain point per batch and everything interleaves.
-        self.overlap_batches = os.environ.get('OADG_OVERLAP', '0') == '1'
+        # iter_batches puts the views of this many consecutive batches into one plan / one chain launch (their work
+        # items are independent: a queue with more lanes starves less often; OA-Mix alone on 1024x2048 frames:
+        # 265 / 204 / 182 us per view with 1 / 2 / 4 batches of two frames per launch)
+        self.group_batches = int(os.environ.get('OADG_GROUP_BATCHES', '4'))
         self.last_launches = 0
 
     def __repr__(self):
@@ -552,16 +557,11 @@ class OAMix:
         slot = 1 + self._sal_slot
         self._sal_prefetch[self._saliency_key(imgs, gt_list)] = self._saliency_launch(imgs, gt_list, None, True, slot=slot)
 
-    def _workspace(self, nbytes, device, slot=0):
+    def _workspace(self, nbytes, device, n_views=0, max_hw=(0, 0)):
+        """Scratch for oadg_oamix_execute.  What a plan needs varies with its bboxes-only chains (two frames each);
+        growing the buffer drains the device, so the first allocation already covers the largest plan this
+        configuration can draw for as many views of this size (every op a chain), up to 8 GiB."""
         torch = _lib.require_cuda()
-        if slot:   # the second lane of the overlapped pipeline owns its own scratch
-            ws = self._ws_lanes.get(slot)
-            if ws is None or ws.numel() < nbytes or ws.device != device:
-                if ws is not None:
-                    torch.cuda.synchronize(device)
-                self._ws_lanes[slot] = None
-                ws = self._ws_lanes[slot] = torch.empty(int(nbytes * 2) + 4096, dtype=torch.uint8, device=device)
-            return ws
         if self._ws_cache is None or self._ws_cache.numel() < nbytes or self._ws_cache.device != device:
             # The old workspace may still be in use by kernels in flight; once released, the caching allocator may hand
             # its block to a buffer that is used on ANOTHER stream (the saliency stream) right away.  Growing is rare:
@@ -569,11 +569,15 @@ class OAMix:
             if self._ws_cache is not None:
                 torch.cuda.synchronize(self._ws_cache.device)
             self._ws_cache = None
-            # plans differ in size from batch to batch: double, so that the drain above stops after a few batches
-            self._ws_cache = torch.empty(int(nbytes * 2) + 4096, dtype=torch.uint8, device=device)
+            depth = self.mixture_depth if self.mixture_depth > 0 else 3
+            frame = (int(max_hw[0]) * int(max_hw[1]) * 3 + 255) // 256 * 256
+            worst = n_views * (frame * (2 * self.mixture_width + 2 * self.mixture_width * depth * P.MAX_REGIONS) +
+                               int(max_hw[0]) * int(max_hw[1]) * 5) + (8 << 20)
+            want = max(int(nbytes * 1.25), min(worst, 8 << 30))
+            self._ws_cache = torch.empty(want + 4096, dtype=torch.uint8, device=device)
         return self._ws_cache
 
-    def execute(self, jobs, imgs, outs=None, stream=None, profile=None, ctas_per_sm=0, ws_slot=0):
+    def execute(self, jobs, imgs, outs=None, stream=None, profile=None):
         """Run the packed plans.  jobs: a packed plan blob (uint8 array, one view per image) or a list of
         (view_plan, gt, img_index); imgs: list of CUDA u8 HWC tensors; returns one output tensor per view.
         ``profile`` (a dict) switches to the event-timed entry point and receives per-kernel ms / counts."""
@@ -588,7 +592,8 @@ class OAMix:
             blob = self._pack(jobs)
         need = ctypes.c_size_t(0)
         _lib.check(lib.oadg_oamix_workspace_bytes(blob.ctypes.data, blob.nbytes, ctypes.byref(need)))
-        ws = self._workspace(need.value, dev, ws_slot)
+        ws = self._workspace(need.value, dev, max(len(jobs), self._ws_min_views),
+                             (max(int(t.shape[0]) for t in imgs), max(int(t.shape[1]) for t in imgs)))
         if outs is None:
             outs = [torch.empty_like(imgs[j[2]]) for j in jobs]
         src = (ctypes.c_void_p * len(imgs))(*[int(t.data_ptr()) for t in imgs])
@@ -618,12 +623,8 @@ class OAMix:
             self.last_launches += 2
             return outs
         n = ctypes.c_int(0)
-        if ctas_per_sm:
-            _lib.check(lib.oadg_oamix_execute_shared(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
-                                                     int(ctas_per_sm), ctypes.byref(n), s_raw))
-        else:
-            _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
-                                              ctypes.byref(n), s_raw))
+        _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
+                                          ctypes.byref(n), s_raw))
         self.last_launches += n.value
         return outs
 
@@ -667,6 +668,10 @@ class OAMix:
         dev = st['dev'].get(key)
         if dev is None:
             dev = st['dev'][key] = torch.empty(img.shape, dtype=torch.uint8, device='cuda')
+            if isinstance(slot, tuple) and len(slot) == 3:   # (slot, image, slots): a loader's ring, allocated at once
+                for k in range(slot[2]):
+                    st['dev'].setdefault(((k, slot[1], slot[2]), tuple(img.shape)),
+                                         torch.empty(img.shape, dtype=torch.uint8, device='cuda'))
         if not src.is_pinned():
             pin = st['pin'].get(key)
             if pin is None:
@@ -754,14 +759,14 @@ class OAMix:
         that's upload + saliency scores are already in flight, so host<->device copies, the score read-back and the
         host sampling overlap the kernels instead of adding to them.  The pipeline has its own CUDA streams (like a
         loader worker): what the caller enqueues on its stream between batches neither waits for nor delays it.
-        With ``overlap_batches`` (opt-in, see __init__) consecutive batches run as half-width launches on two
-        streams, each filling the other's dependency stalls.  With ``threaded`` (default) the pipeline's host side runs in a worker thread,
+        The views of up to ``group_batches`` consecutive batches share one plan and one chain launch (see
+        ``_pipeline``).  With ``threaded`` (default) the pipeline's host side runs in a worker thread,
         so its plan sampling and scheduling (native code, GIL released) overlap the caller's own host work.
 
         Samples whose ``img`` is a CUDA uint8 tensor (complete when the batch is read from ``batches``) stay on the
         device: no upload, ``img2`` is a CUDA tensor ordered on the consumer's current stream; the consumer must
         enqueue its work on a batch's views before it asks for the next batch (that work is fenced before the
-        buffers are reused, four batches later).
+        buffers are reused, 3 * group_batches + 4 batches later).
 
         Differences from calling ``call_batch`` in a loop: ``batches`` is read a few items ahead (the caller must
         leave a batch's input arrays alone until it is yielded), and the np.random draws of later batches are taken
@@ -791,7 +796,7 @@ class OAMix:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
                 released[job['idx']] = ev
-                released.pop(job['idx'] - 8, None)
+                released.pop(job['idx'] - 128, None)
 
         if not threaded:
             for item in self._pipeline(batches, dev, released):
@@ -847,18 +852,28 @@ class OAMix:
         return st
 
     def _pipeline(self, batches, dev, released):
-        """iter_batches' generator: yields (results, job).  Batch k is yielded after batch k + 1's kernel chain was
-        launched and batch k + 2's upload + saliency kernel were enqueued."""
+        """iter_batches' generator: yields (results, job) per batch, in order.
+
+        Batches travel in GROUPS: the views of up to ``group_batches`` consecutive batches are sampled into ONE plan
+        and executed by ONE chain launch (they are independent, oa_mix.py:187-204, and the more lanes the launch's
+        work queue holds the fewer CTAs ever wait for a dependency).  The first groups of a loop are smaller (1, 2,
+        then ``group_batches``) so that the first batch is not held back.  While the consumer works through group
+        k, group k + 1's launch is in flight and group k + 2's upload + saliency kernel are enqueued.  np.random is
+        consumed image by image in batch order, exactly as by per-batch calls."""
         import collections
         import time
         torch = _lib.require_cuda()
         lib = _lib.load()
         side, cout = self._side_stream(dev), self._stream('out', dev)
-        lanes = [self._stream('pipe', dev), self._stream('pipe2', dev)]
+        pipe = self._stream('pipe', dev)
         it = iter(batches)
         staged, launched = collections.deque(), collections.deque()
-        count = [0]
+        count = [0, 0]                    # batches read, groups staged
+        exhausted = [False]
         prof = self.pipe_profile          # optional dict: host seconds per phase (scripts/e2e_profile.py)
+        gmax = max(1, int(self.group_batches))
+        n_sets = 3 * gmax + 4             # view buffer sets: more than the batches launched ahead + being consumed
+        n_in = 5 * gmax + 4               # frame staging slots (host frames): more than the batches staged + in flight
 
         def tick(name, t0):
             if prof is not None:
@@ -867,92 +882,161 @@ class OAMix:
                 prof[name + '.max'] = max(prof.get(name + '.max', 0.0), dt)
             return time.perf_counter()
 
-        def stage_in():
-            try:
-                results_list = next(it)
-            except StopIteration:
+        def stage_group():
+            """Read the next group's batches, upload their frames and enqueue ONE saliency kernel for all of them."""
+            if exhausted[0]:
                 return
-            idx = count[0]
-            count[0] += 1
-            t0 = time.perf_counter()
-            job = dict(results=results_list, idx=idx, error=None, device=False)
-            try:   # a failure surfaces when the batch is yielded, after the batches before it
-                gts = [np.asarray(r['gt_bboxes'], dtype=np.float32).reshape(-1, 4) for r in results_list]
-                first = results_list[0]['img'] if results_list else None
-                if torch.is_tensor(first) and first.is_cuda:
-                    dimgs = [r['img'] for r in results_list]
-                    for t in dimgs:
-                        if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3 and
-                                t.is_contiguous()):
-                            raise TypeError('images must be contiguous CUDA uint8 HWC tensors')
-                    job.update(gts=gts, dimgs=dimgs, hw=[(int(t.shape[0]), int(t.shape[1])) for t in dimgs],
-                               ready=None, device=True)
-                else:
-                    # upload, then the saliency kernel behind it on the same stream
-                    ins = [self._to_device(r['img'], (idx % 3, i), side) for i, r in enumerate(results_list)]
-                    ready = torch.cuda.Event()
-                    ready.record(side)
-                    job.update(gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins], ready=ready)
-                t0 = tick('upload_enqueue', t0)
-                job['sal'] = self._saliency_launch(job['dimgs'], gts, None, True, slot=4 + idx % 3)
-                self.pipe_launches += 1 if job['sal']['st'] is not None else 0
-                tick('saliency_enqueue', t0)
-            except Exception as e:
-                job['error'] = e
-            staged.append(job)
-
-        def launch(job):
-            if job['error'] is None:
+            want = min(gmax, 1 << count[1])       # 1, 2, 4, ... batches per group
+            jobs = []
+            while len(jobs) < want:
                 try:
-                    t0 = time.perf_counter()
-                    idx = job['idx']
-                    scores = self._saliency_collect(job['sal'])
-                    t0 = tick('scores_wait', t0)
-                    plan = job['plan'] = self.sample_plan(job['hw'], job['gts'], scores)
-                    t0 = tick('sample_plan', t0)
-                    n_sets = 4 if job['device'] else 2   # device views: see iter_batches' hand-over protocol
-                    key = ('outs', idx % n_sets, n_sets, tuple(tuple(d.shape) for d in job['dimgs']))
-                    douts = self._host_state['dev'].get(key)
-                    if douts is None:
-                        douts = self._host_state['dev'][key] = [torch.empty_like(d) for d in job['dimgs']]
-                    overlap = bool(self.overlap_batches)
-                    lane, ctas = (idx % 2, 2) if overlap else (0, 0)
-                    st = lanes[lane]
-                    if job['ready'] is not None:
-                        st.wait_event(job['ready'])
-                    if job['device'] and (idx - n_sets) in released:   # the consumer's work on this set's last views
-                        st.wait_event(released[idx - n_sets])
-                    before = self.last_launches
-                    self.execute(plan.blob, job['dimgs'], outs=douts, stream=st, ctas_per_sm=ctas, ws_slot=lane)
-                    self.pipe_launches += self.last_launches - before
-                    t0 = tick('execute_enqueue', t0)
-                    job['done'] = torch.cuda.Event()
-                    job['done'].record(st)
-                    if job['device']:
-                        job['views'] = douts
+                    results_list = next(it)
+                except StopIteration:
+                    exhausted[0] = True
+                    break
+                idx = count[0]
+                count[0] += 1
+                t0 = time.perf_counter()
+                job = dict(results=results_list, idx=idx, error=None, device=False)
+                try:   # a failure surfaces when the batch is yielded, after the batches before it
+                    gts = [np.asarray(r['gt_bboxes'], dtype=np.float32).reshape(-1, 4) for r in results_list]
+                    first = results_list[0]['img'] if results_list else None
+                    if torch.is_tensor(first) and first.is_cuda:
+                        dimgs = [r['img'] for r in results_list]
+                        for t in dimgs:
+                            if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3 and
+                                    t.is_contiguous()):
+                                raise TypeError('images must be contiguous CUDA uint8 HWC tensors')
+                        job.update(gts=gts, dimgs=dimgs, hw=[(int(t.shape[0]), int(t.shape[1])) for t in dimgs],
+                                   device=True)
                     else:
-                        host = [self._pinned_out(o.shape, reserve=6 * len(douts)) for o in douts]
-                        cout.wait_event(job['done'])
-                        for (h_, _), o in zip(host, douts):
-                            _lib.check(lib.oadg_memcpy_async(h_.data_ptr(), o.data_ptr(), o.numel(), 0,
-                                                             cout.cuda_stream))
-                        job['out_ready'] = torch.cuda.Event()
-                        job['out_ready'].record(cout)
-                        job['host'] = host
-                    tick('download_enqueue', t0)
+                        ins = [self._to_device(r['img'], (idx % n_in, i, n_in), side) for i, r in enumerate(results_list)]
+                        job.update(gts=gts, dimgs=[d for d, _ in ins], hw=[h.shape[:2] for _, h in ins])
+                    tick('upload_enqueue', t0)
                 except Exception as e:
                     job['error'] = e
-            launched.append(job)
+                jobs.append(job)
+                if job['error'] is not None:
+                    break                          # the group ends at a failed batch
+            if not jobs:
+                return
+            grp = dict(jobs=jobs, idx=count[1], ready=None, sal=None)
+            count[1] += 1
+            good = [j for j in jobs if j['error'] is None]
+            if good:
+                t0 = time.perf_counter()
+                try:
+                    if not all(j['device'] for j in good):
+                        grp['ready'] = torch.cuda.Event()
+                        grp['ready'].record(side)
+                    imgs = [d for j in good for d in j['dimgs']]
+                    gts = [g for j in good for g in j['gts']]
+                    grp['sal'] = self._saliency_launch(imgs, gts, None, True, slot=4 + grp['idx'] % 3)
+                    self.pipe_launches += 1 if grp['sal']['st'] is not None else 0
+                except Exception as e:
+                    for j in good:
+                        j['error'] = e
+                tick('saliency_enqueue', t0)
+            staged.append(grp)
 
-        stage_in()
-        stage_in()
+        def launch_batches(jobs, scores):
+            """Sample ONE plan for `jobs` (consecutive batches) and enqueue its execution + the downloads."""
+            t0 = time.perf_counter()
+            hw = [x for j in jobs for x in j['hw']]
+            gts = [g for j in jobs for g in j['gts']]
+            imgs = [d for j in jobs for d in j['dimgs']]
+            plan = self.sample_plan(hw, gts, scores)
+            t0 = tick('sample_plan', t0)
+            douts, k = [], 0
+            for j in jobs:
+                shapes = tuple(tuple(d.shape) for d in j['dimgs'])
+                key = ('outs', j['idx'] % n_sets, n_sets, shapes)
+                o = self._host_state['dev'].get(key)
+                if o is None:   # all view sets of this batch shape at once: allocation belongs to the warm-up
+                    for k2 in range(n_sets):
+                        self._host_state['dev'].setdefault(('outs', k2, n_sets, shapes),
+                                                           [torch.empty_like(d) for d in j['dimgs']])
+                    o = self._host_state['dev'][key]
+                douts.extend(o)
+                # this batch's slice of the group's plan
+                n = len(j['dimgs'])
+                j['plan'] = _PlanSlice(plan, k, k + n)
+                j['douts'] = o
+                k += n
+                if j['device'] and (j['idx'] - n_sets) in released:   # the consumer's work on this set's last views
+                    pipe.wait_event(released[j['idx'] - n_sets])
+            before = self.last_launches
+            self._ws_min_views = max(self._ws_min_views, gmax * max(len(j['dimgs']) for j in jobs))
+            self.execute(plan.blob, imgs, outs=douts, stream=pipe)
+            self.pipe_launches += self.last_launches - before
+            t0 = tick('execute_enqueue', t0)
+            done = torch.cuda.Event()
+            done.record(pipe)
+            for j in jobs:
+                j['done'] = done
+                if j['device']:
+                    j['views'] = j['douts']
+            host_jobs = [j for j in jobs if not j['device']]
+            if host_jobs:
+                cout.wait_event(done)
+                for j in host_jobs:
+                    host = [self._pinned_out(o.shape, reserve=(2 * gmax + 2) * len(j['douts'])) for o in j['douts']]
+                    for (h_, _), o in zip(host, j['douts']):
+                        _lib.check(lib.oadg_memcpy_async(h_.data_ptr(), o.data_ptr(), o.numel(), 0, cout.cuda_stream))
+                    j['out_ready'] = torch.cuda.Event()
+                    j['out_ready'].record(cout)
+                    j['host'] = host
+            tick('download_enqueue', t0)
+
+        def launch_group(grp):
+            good = [j for j in grp['jobs'] if j['error'] is None]
+            if good:
+                try:
+                    t0 = time.perf_counter()
+                    scores = self._saliency_collect(grp['sal'])
+                    tick('scores_wait', t0)
+                    if grp['ready'] is not None:
+                        pipe.wait_event(grp['ready'])
+                    state = np.random.get_state() if len(good) > 1 else None
+                    try:
+                        launch_batches(good, scores)
+                    except Exception:
+                        if state is None:
+                            raise
+                        # a batch of the group cannot be sampled: redo the group batch by batch from the saved
+                        # random state, so that the draws (and the batch that raises) match per-batch calls
+                        np.random.set_state(state)
+                        k = 0
+                        for j in good:
+                            n = len(j['dimgs'])
+                            try:
+                                launch_batches([j], scores[k:k + n])
+                            except Exception as e:
+                                j['error'] = e
+                                for j2 in good[good.index(j) + 1:]:
+                                    j2['error'] = e
+                                break
+                            k += n
+                except Exception as e:
+                    for j in good:
+                        if j['error'] is None and 'done' not in j:
+                            j['error'] = e
+            for j in grp['jobs']:
+                launched.append(j)
+
+        stage_group()
+        stage_group()
         if staged:
-            launch(staged.popleft())
-        while launched:
-            stage_in()                         # batch k + 2: upload + saliency
-            if staged:
-                launch(staged.popleft())       # batch k + 1: sampling + kernel chain + download
-            job = launched.popleft()           # batch k
+            launch_group(staged.popleft())
+        stage_group()
+        while launched or staged:
+            # keep the GPU fed: up to a full group's batches launched beyond the batch being handed over, and one
+            # more group staged (uploads + saliency) behind them
+            if staged and len(launched) <= gmax:
+                launch_group(staged.popleft())     # group k + 1: sampling + kernel chain + downloads
+                stage_group()                      # group k + 2: uploads + saliency
+                continue
+            job = launched.popleft()               # the next batch of group k
             if job['error'] is not None:
                 raise job['error']
             t0 = time.perf_counter()
@@ -961,6 +1045,7 @@ class OAMix:
             else:
                 job['out_ready'].synchronize()
                 views = [a for _, a in job['host']]
+            _lib.check(lib.oadg_oamix_poll_fault(0))   # a launch that left views incomplete raises here
             t0 = tick('views_wait', t0)
             res = self._fill_results(job['results'], views, job['plan'])
             t0 = tick('fill_results', t0)

@@ -249,9 +249,9 @@ def test_prefetched_saliency_gives_the_same_views(cuda):
 
 @pytest.mark.parametrize('threaded', [False, True])
 def test_iter_batches_equals_call_batch(cuda, threaded):
-    """The pipelined loader loop (upload / saliency two batches ahead, kernel chain one ahead) yields exactly what
-    call_batch returns for each batch in turn and leaves np.random in the same state; 7 batches exercise every
-    staging slot twice, mixed frame sizes the per-shape buffers."""
+    """The pipelined loader loop (groups of batches: upload / saliency two groups ahead, kernel chain one ahead) yields
+    exactly what call_batch returns for each batch in turn and leaves np.random in the same state; mixed frame
+    sizes exercise the per-shape buffers and plans that hold views of different sizes."""
     from oadg_b200 import OAMix
     t = OAMix(**dict(OAMIX_CFG, version='augmix'))
     sizes = [(200, 333), (200, 333), (160, 288), (200, 333), (160, 288), (160, 288), (200, 333)]
@@ -263,8 +263,8 @@ def test_iter_batches_equals_call_batch(cuda, threaded):
     np.random.seed(91)
     want = [t.call_batch(b) for b in make()]
     st_want = np.random.get_state()
-    for overlap in (False, True):       # False (default): one full-width launch after the other
-        t.overlap_batches = overlap
+    for group in (4, 1, 3):       # batches per plan / chain launch (4 is the default)
+        t.group_batches = group
         np.random.seed(91)
         got = []
         for res in t.iter_batches(iter(make()), threaded=threaded):
@@ -277,7 +277,7 @@ def test_iter_batches_equals_call_batch(cuda, threaded):
                 assert a['custom_field'] == b['custom_field'] and a['img_fields'] == b['img_fields']
                 for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
                     assert np.array_equal(a[k], b[k]), k
-    t.overlap_batches = False
+    t.group_batches = 4
     # an empty loader and a single batch
     assert list(t.iter_batches([], threaded=threaded)) == []
     np.random.seed(3)
@@ -301,7 +301,7 @@ def test_iter_batches_equals_call_batch(cuda, threaded):
 def test_iter_batches_device_frames(cuda, threaded):
     """CUDA frames in, CUDA views out (no upload / download): same pixels as oamix_batch on the same seeds, also when
     the consumer keeps the GPU busy with work on each batch's views before asking for the next one (the fence the
-    pipeline waits for before it reuses a view buffer), and with batch overlap switched off."""
+    pipeline waits for before it reuses a view buffer), with grouped and with per-batch launches."""
     import torch
     from oadg_b200 import OAMix
     t = OAMix(**dict(OAMIX_CFG, version='augmix'))
@@ -314,8 +314,8 @@ def test_iter_batches_device_frames(cuda, threaded):
     def batches():
         for k in range(9):
             yield [dict(img=dev[2 * k + j], gt_bboxes=gts[2 * k + j]) for j in range(2)]
-    for overlap in (True, False):
-        t.overlap_batches = overlap
+    for group in (4, 1):
+        t.group_batches = group
         np.random.seed(13)
         sums, got = [], []
         for res in t.iter_batches(batches(), threaded=threaded):
@@ -326,11 +326,11 @@ def test_iter_batches_device_frames(cuda, threaded):
                 acc = acc * 0.5 + views[1].to(torch.float32)
             sums.append(acc.sum())
             got.append([v.clone() for v in views])
-        assert t.pipe_launches == 27
+        assert t.pipe_launches == (27 if group == 1 else 12)   # saliency + chain + mix per group of batches (1, 2, 4, 2)
         for k, (a, b) in enumerate(zip(want, got)):
             for x, y in zip(a, b):
-                assert torch.equal(x, y), (overlap, k)
+                assert torch.equal(x, y), (group, k)
             acc = a[0].to(torch.float32)
             for _ in range(20):
                 acc = acc * 0.5 + a[1].to(torch.float32)
-            assert torch.equal(acc.sum(), sums[k]), (overlap, k)
+            assert torch.equal(acc.sum(), sums[k]), (group, k)
