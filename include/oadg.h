@@ -36,7 +36,7 @@ extern "C" {
 #define OADG_ABI_VERSION 1
 
 #define OADG_E_ARG      (-1)   /* null pointer / bad size                         */
-#define OADG_E_PLAN     (-2)   /* malformed plan blob                             */
+#define OADG_E_PLAN     (-2)   /* malformed plan blob; or a chain launch gave up waiting for work (views incomplete) */
 #define OADG_E_LIMIT    (-3)   /* exceeds a compiled limit (OADG_MAX_*)           */
 #define OADG_E_NOBOX    (-5)   /* OA-Mix sampler: no multi-level box could be placed
                                   (the reference raises ValueError from np.stack([]), oa_mix.py:217) */

@@ -17,7 +17,7 @@ extern "C" const char* oadg_error_string(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   switch (code) {
     case OADG_E_ARG: return "OADG_E_ARG: null pointer, bad size or misaligned buffer";
-    case OADG_E_PLAN: return "OADG_E_PLAN: malformed plan blob";
+    case OADG_E_PLAN: return "OADG_E_PLAN: malformed plan blob, or a launch whose work queue starved (incomplete views)";
     case OADG_E_LIMIT: return "OADG_E_LIMIT: exceeds a compiled limit";
     case OADG_E_NOBOX: return "OADG_E_NOBOX: no random box could be placed";
     case OADG_E_ROWS: return "OADG_E_ROWS: fewer rows than the two-view layout needs";

@@ -160,6 +160,7 @@ __device__ __forceinline__ void publish_tile(const ChainArgs& A, const Item& I) 
   const int lane = threadIdx.x & 31;
   fence_acq_rel_gpu();        // release: the tile's stores (ordered before this warp by the barrier) before the counters
   tma::fence_proxy_async();   // ... and before TMA reads (async proxy) of later items
+  if (A.debug & 64) return;   // fault injection (tests): no successor is ever released, the queue starves
   for (int base = 0; base < I.succ_count; base += 32) {
     int s = -1, nt = 0;
     unsigned long long first = 0;
@@ -1586,6 +1587,7 @@ oamix_chain_kernel(const ChainArgs Aparam) {
     // Iteration n hands tile n to the workers.  A finished tile is published as soon as the scheduler sees it --
     // in particular while it waits for an unpublished ticket: the work it waits for may depend on that very tile.
     const int lane = threadIdx.x & 31;
+    const int ahead_q = (A.debug >> 8) ? (A.debug >> 8) : 8;   // claim ahead when more than ahead_q / 4 tickets per CTA are unclaimed
     unsigned published = 0;
     auto publish_ready = [&]() {   // warp-uniform: publish the tiles the workers have finished; returns how many
       unsigned done = 0;
@@ -1612,7 +1614,7 @@ oamix_chain_kernel(const ChainArgs Aparam) {
           int go = 1;
           if (lane == 0) {
             const long long avail = (long long)ld_relaxed_u64(A.ring) - (long long)ld_relaxed_u64(A.ring + 1);
-            go = avail > 2ll * A.grid || ld_acquire_cta_u32(&S.done_seq) >= n;
+            go = avail > ((long long)A.grid * ahead_q) / 4 || ld_acquire_cta_u32(&S.done_seq) >= n;
           }
           if (__shfl_sync(0xffffffffu, go, 0)) break;
           if (!publish_ready()) __nanosleep(300);
@@ -1732,6 +1734,11 @@ oamix_chain_kernel(const ChainArgs Aparam) {
     }
     worker_sync();   // every worker's stores of the tile are issued ...
     if (threadIdx.x == 0) st_release_cta_u32(&S.done_seq, n + 1u);   // ... finished: the scheduler publishes the tile
+    if (kStats && threadIdx.x == 0) {   // slot 13: thread 0 waited for the CTA's slower warps at the end of the tile
+      const unsigned long long t2 = globaltimer_ns();
+      atomicAdd(A.kind_ns + 13, t2 - idle_t0);
+      atomicAdd(A.kind_ns + 16 + 13, 1ull);
+    }
   }
 }
 

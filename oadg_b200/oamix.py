@@ -614,7 +614,7 @@ class OAMix:
             profile['mix_n'] = profile.get('mix_n', 0) + 1
             profile['items'] = profile.get('items', 0) + int(n_items.value)
             profile['tiles'] = profile.get('tiles', 0) + int(n_tiles.value)
-            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed', 'dependency_wait', 'claim_fast', 'claim_blocked')
+            names = ITEM_KINDS[:7] + ('step_stream', 'step_bg_staged', 'step_mixed', 'dependency_wait', 'claim_fast', 'claim_blocked', 'tile_end_sync')
             ks = profile.setdefault('kind_busy_us_and_tiles', {k: [0.0, 0, 0.0] for k in names})
             for i, k in enumerate(names):
                 ks[k][0] += float(kstats[i]) / 1e3
@@ -713,6 +713,7 @@ class OAMix:
         for (h_, _), o in zip(host, outs):
             h_.copy_(o, non_blocking=True)
         torch.cuda.current_stream(outs[0].device).synchronize()
+        _lib.check(_lib.load().oadg_oamix_poll_fault(1))   # a launch that left its views incomplete raises here
         return [a for _, a in host]
 
     def oamix(self, img, gt_bboxes):

@@ -6,7 +6,7 @@ the pre-truncation floats; saliency score |d| <= 5e-3 with identical `score <= 1
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, OAMIX_CFG, sampler_cfg
+from conftest import GOLDEN, OAMIX_CFG, ROOT as ROOT_DIR, sampler_cfg
 from oracle import oamix_np, saliency_np, synth
 
 pytestmark = pytest.mark.gpu
@@ -334,3 +334,33 @@ def test_iter_batches_device_frames(cuda, threaded):
             for _ in range(20):
                 acc = acc * 0.5 + a[1].to(torch.float32)
             assert torch.equal(acc.sum(), sums[k]), (group, k)
+
+
+def test_starved_queue_raises_instead_of_returning_half_written_views(cuda):
+    """A chain launch whose dependency tables never release work (injected: OADG_DEBUG=64 drops every successor
+    release) must not hang the GPU and must not hand back views silently: its CTAs give up after 2 s, raise the
+    sticky fault flag, and the plugin raises (OADG_E_PLAN) when the views are handed over / at the next call."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, %r)
+        sys.path.insert(0, %r + '/tests')
+        import numpy as np, torch
+        from oracle import synth
+        from oadg_b200 import OAMix, _lib
+        img, gt = synth.make_image(3, 200, 320, 4)
+        t = OAMix()
+        np.random.seed(5)
+        try:
+            out = t.oamix(img, gt)          # H2D, kernels, D2H + fault poll
+        except _lib.OADGError as e:
+            print('RAISED', e)
+            sys.exit(0)
+        print('RETURNED')
+    ''') % (ROOT_DIR, ROOT_DIR)
+    import os
+    env = dict(os.environ, OADG_DEBUG='64')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120, env=env)
+    assert 'RAISED' in out.stdout and 'OADG_E_PLAN' in out.stdout, (out.stdout[-500:], out.stderr[-500:])
