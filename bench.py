@@ -466,6 +466,38 @@ def product_arm(args):
     loss_ms = e0.elapsed_time(e1) / 20
     oaloss = {'fwd_bwd_ms': loss_ms, 'algorithmic_gflop': 6.0 * N_ROI * N_ROI * C_ROI / 1e9,
               'tflops': 6.0 * N_ROI * N_ROI * C_ROI / (loss_ms / 1e3) / 1e12}
+    # the reference's own GPU path for the loss: its eager ATen op sequence (oracle/supcon_torch.py, the checker --
+    # timed beside the product, never part of it), f32, TF32 off, same inputs, same box, CUDA events; parity first
+    from oracle import supcon_torch
+    tf32_was = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    xt = x_dev.detach().clone().requires_grad_(True)
+
+    def torch_step():
+        xt.grad = None
+        l_ = supcon_torch.contrastive_loss_plus_torch(xt, labels_dev, LOSS_CFG['loss_weight'], LOSS_CFG['temperature'])
+        l_.backward()
+        return l_
+    x_dev.grad = None
+    ours = loss_fn(x_dev, labels_dev)
+    ours.backward()
+    ref_l = torch_step()
+    rel_l = abs(float(ours) - float(ref_l)) / abs(float(ref_l))
+    rel_g = float((x_dev.grad - xt.grad).norm() / xt.grad.norm())
+    assert rel_l <= 1e-4 and rel_g <= 1e-4, ('OA-Loss differs from the stock-torch path', rel_l, rel_g)
+    for _ in range(3):
+        torch_step()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(20):
+        torch_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_was
+    oaloss.update(torch_reference_ms=e0.elapsed_time(e1) / 20, torch_reference='oracle/supcon_torch.py: the '
+                  'reference\'s eager ATen op sequence (contrastive_loss.py:147-232), f32, allow_tf32=False, CUDA '
+                  'events, same inputs', vs_torch_reference=e0.elapsed_time(e1) / 20 / loss_ms,
+                  parity_vs_torch={'loss_rel': rel_l, 'grad_rel': rel_g})
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample on the host cores
     log('loss timing done')

@@ -281,6 +281,29 @@ int oadg_supcon_backward_gathered(const float* feats_local_dev, const int64_t* l
                                   int normalized_input, const float* grad_loss_dev, float* grad_feats_dev,
                                   void* workspace_dev, size_t workspace_bytes, int* launches_out, void* stream);
 
+/* The same sequence with PACKED buffers, so that no pack / slice / copy kernels sit around the two collectives:
+ *   gather_pack      normalises the rank's rows straight into its send buffer: n_rows rows of oadg_supcon_pack_width(c)
+ *                    floats = [fhat | the row's int64 label as two 32-bit words | padding]; labels_dev may hold fewer
+ *                    than n_rows labels, the rest take the last one (contrastive_loss_plus.py:44-47)
+ *   -> all_gather(send) -> forward_packed reads the gathered buffer in place and writes the rank's TAIL buffer:
+ *                    n_rows rows of 4 floats (row statistics) + one row {loss part, -, -, -}
+ *   -> all_gather(tail) -> finish_packed: total loss (rank order, same bits on every rank) and the statistics of all
+ *                    rows, kept in the workspace
+ *   -> backward_packed (labels and statistics come from the workspace). */
+int oadg_supcon_pack_width(int c);
+int oadg_supcon_gather_pack(const float* feats_dev, const int64_t* labels_dev, int n_labels, int n_rows, int n_total,
+                            int c, int normalized_input, float* send_dev, void* workspace_dev, size_t workspace_bytes,
+                            void* stream);
+int oadg_supcon_forward_packed(const float* recv_dev, const int32_t* pair_all_dev, int n_total, int row0, int n_rows,
+                               int c, float temperature, float loss_weight, int min_samples, float* tail_dev,
+                               void* workspace_dev, size_t workspace_bytes, int* launches_out, void* stream);
+int oadg_supcon_finish_packed(const float* tail_all_dev, int world, int n_rows, int c, float* loss_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream);
+int oadg_supcon_backward_packed(const float* feats_local_dev, const int32_t* pair_all_dev, int n_total, int row0,
+                                int n_rows, int c, float temperature, int normalized_input, const float* grad_loss_dev,
+                                float* grad_feats_dev, void* workspace_dev, size_t workspace_bytes, int* launches_out,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,13 @@ SIGNATURES = {
                                                 _c.c_int, _vp, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
     'oadg_supcon_backward_gathered': (_c.c_int, [_vp, _vp, _vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _f32,
                                                  _c.c_int, _vp, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_supcon_pack_width': (_c.c_int, [_c.c_int]),
+    'oadg_supcon_gather_pack': (_c.c_int, [_vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _sz, _vp]),
+    'oadg_supcon_forward_packed': (_c.c_int, [_vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _f32, _f32, _c.c_int,
+                                              _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_supcon_finish_packed': (_c.c_int, [_vp, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _sz, _vp]),
+    'oadg_supcon_backward_packed': (_c.c_int, [_vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _f32, _c.c_int, _vp,
+                                               _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
 }
 
 _lib = None

@@ -36,6 +36,20 @@ def _digest():
     return h.hexdigest()
 
 
+def build_test_variant(path, extra_flags):
+    """A second library built from the same sources with extra -D flags (test infrastructure: the FFMA cross-check
+    of the OA-Loss, tests/test_gpu_oaloss.py); rebuilt when older than the product library."""
+    build()
+    if os.path.exists(path) and os.path.getmtime(path) >= os.path.getmtime(LIB):
+        return path
+    cmd = [NVCC] + [f for f in FLAGS if f not in ('-Xptxas', '-v')] + list(extra_flags) + _sources() + ['-o', path]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed building %s' % path)
+    return path
+
+
 def build(force=False, verbose=False):
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:

@@ -102,11 +102,18 @@ def supcontrast(logits_clean, labels=None, num_views=2, lambda_weight=0.1, tempe
     if not logits_clean.is_cuda:
         raise _lib.OADGError('supcontrast: features must live on a CUDA device (no CPU fallback)')
     n = logits_clean.shape[0]
-    labels = labels.reshape(-1)
-    if labels.dtype != torch.int64 or labels.device != logits_clean.device:
-        labels = labels.to(device=logits_clean.device, dtype=torch.int64)
+    # the kernels read raw pointers: labels and pair must be dense, on the features' device, of the declared dtype
+    labels = labels.reshape(-1).to(device=logits_clean.device, dtype=torch.int64).contiguous()
+    if labels.shape[0] != n:
+        raise ValueError('supcontrast: %d labels for %d rows' % (labels.shape[0], n))
     if pair is None:
         pair = _pair_tensor(n, logits_clean.device)
+    else:
+        if not torch.is_tensor(pair):
+            pair = torch.as_tensor(np.asarray(pair))
+        if pair.dim() != 1 or pair.shape[0] != n or pair.is_floating_point():
+            raise ValueError('supcontrast: pair must be an integer vector of %d entries' % n)
+        pair = pair.to(device=logits_clean.device, dtype=torch.int32).contiguous()
     feats = logits_clean if logits_clean.dtype == torch.float32 else logits_clean.float()
     return _SupConFn.apply(feats, labels, pair, temper, loss_weight, min_samples, normalized_input,
                            stats if stats is not None else {})

@@ -417,14 +417,73 @@ normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dpar
 
 using namespace oadg;
 
-// 1 = tcgen05 similarity (default), 0 = CUDA-core FFMA path (OADG_LOSS_TC=0)
-static int loss_tc_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("OADG_LOSS_TC");
-    v = (e && e[0] == '0') ? 0 : 1;
+// ---- cross-rank path, packed buffers: a rank's contribution to the all-gather is ONE buffer of n_rows rows of
+// kPackW floats = [fhat (c) | the row's int64 label as two float-sized words | 0 | 0]; the gathered buffer is read in
+// place (row stride kPackW), so no pack / slice / contiguous kernels sit around the collectives.
+constexpr int kPackPad = 4;   // keeps rows 16-byte aligned
+__global__ void __launch_bounds__(256)
+normalize_pack_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, int n_labels, int n, int c,
+                      int normalized_input, float* __restrict__ send, float* __restrict__ inv1, float* __restrict__ inv2) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + (size_t)row * c;
+  float s = 0.f;
+  for (int k = lane; k < c; k += 32) {
+    float v = xr[k];
+    s += v * v;
   }
-  return v;
+  s = warp_sum(s);
+  float i1 = normalized_input ? 1.f / fmaxf(sqrtf(s), 1e-12f) : 1.f;
+  float s2 = 0.f;
+  for (int k = lane; k < c; k += 32) {
+    float v = xr[k] * i1;
+    s2 += v * v;
+  }
+  s2 = warp_sum(s2);
+  float i2 = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+  float* out = send + (size_t)row * (c + kPackPad);
+  for (int k = lane; k < c; k += 32) out[k] = (xr[k] * i1) * i2;
+  if (lane == 0) {
+    inv1[row] = i1;
+    inv2[row] = i2;
+    // rows beyond the label list (random proposals) take the last label (contrastive_loss_plus.py:44-47)
+    const long long y = labels[row < n_labels ? row : n_labels - 1];
+    out[c] = __uint_as_float((unsigned)((unsigned long long)y & 0xffffffffull));
+    out[c + 1] = __uint_as_float((unsigned)((unsigned long long)y >> 32));
+    out[c + 2] = 0.f;
+    out[c + 3] = 0.f;
+  }
+}
+__global__ void __launch_bounds__(256)
+unpack_labels_kernel(const float* __restrict__ recv, int n_total, int c, int64_t* __restrict__ labels_all) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_total) return;
+  const float* r = recv + (size_t)i * (c + kPackPad) + c;
+  labels_all[i] = (int64_t)((unsigned long long)__float_as_uint(r[0]) | ((unsigned long long)__float_as_uint(r[1]) << 32));
+}
+// gathered tails [world][n_rows + 1][4] (row statistics, then {the rank's loss part, 0, 0, 0}) -> contiguous statistics
+// of all rows + the total loss (summed in rank order: every rank gets the same bits)
+__global__ void __launch_bounds__(256)
+finish_packed_kernel(const float4* __restrict__ tail_all, int world, int n_rows, float4* __restrict__ stats_all,
+                     float* __restrict__ loss_out) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j < world * n_rows) stats_all[j] = tail_all[(size_t)(j / n_rows) * (n_rows + 1) + j % n_rows];
+  if (j == 0) {
+    float t = 0.f;
+    for (int r = 0; r < world; ++r) t += tail_all[(size_t)r * (n_rows + 1) + n_rows].x;
+    *loss_out = t;
+  }
+}
+
+// The product computes the similarity on the tensor cores (tcgen05, oaloss_tc.cu).  The CUDA-core FFMA kernels above
+// are kept as a TEST BUILD only (-DOADG_LOSS_FFMA, tests/test_gpu_oaloss.py builds it as a second library): an
+// independent implementation of the same closed form to cross-check the tcgen05 path; there is no runtime switch.
+static constexpr int loss_tc_enabled() {
+#ifdef OADG_LOSS_FFMA
+  return 0;
+#else
+  return 1;
+#endif
 }
 
 extern "C" int oadg_supcon_workspace_bytes(int n, int c, size_t* out_bytes) {
@@ -590,6 +649,94 @@ extern "C" int oadg_supcon_backward_gathered(const float* feats_local_dev, const
   int launches = 0;
   int rc = launch_sim_bwd_tc(w, reinterpret_cast<const RowStats*>(stats_all_dev), labels_all_dev, pair_all_dev, n_total,
                              row0, n_rows, 1.f / temperature, stream, &launches);
+  if (rc) return rc;
+  normalize_bwd_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(feats_local_dev, w.dpart, kBwdSplits, w.inv1, w.inv2, w.meta,
+                                                            grad_loss_dev, n_rows, c, normalized_input, grad_feats_dev);
+  OADG_LAUNCH_CHECK();
+  ++launches;
+  if (launches_out) *launches_out = launches;
+  return 0;
+}
+
+// ---- cross-rank variant with packed buffers (see normalize_pack_kernel) ----------------------------------------------
+extern "C" int oadg_supcon_pack_width(int c) { return c + kPackPad; }
+
+extern "C" int oadg_supcon_gather_pack(const float* feats_dev, const int64_t* labels_dev, int n_labels, int n_rows,
+                                       int n_total, int c, int normalized_input, float* send_dev, void* workspace_dev,
+                                       size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_rows <= 0 || n_total < n_rows || n_labels < 1 || n_labels > n_rows || !feats_dev || !labels_dev || !send_dev ||
+      !workspace_dev)
+    return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if (((uintptr_t)workspace_dev & 255) || ((uintptr_t)send_dev & 15)) return OADG_E_ARG;
+  LossWs w = carve_loss_ws(workspace_dev, n_total, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  normalize_pack_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(feats_dev, labels_dev, n_labels, n_rows, c,
+                                                              normalized_input, send_dev, w.inv1, w.inv2);
+  OADG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int oadg_supcon_forward_packed(const float* recv_dev, const int32_t* pair_all_dev, int n_total, int row0,
+                                          int n_rows, int c, float temperature, float loss_weight, int min_samples,
+                                          float* tail_dev, void* workspace_dev, size_t workspace_bytes,
+                                          int* launches_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!recv_dev || !pair_all_dev || !tail_dev || !workspace_dev) return OADG_E_ARG;
+  if (n_rows <= 0 || row0 < 0 || row0 + n_rows > n_total) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if (!(temperature > 0.f) || ((uintptr_t)recv_dev & 15) || ((uintptr_t)tail_dev & 15) || ((uintptr_t)workspace_dev & 255))
+    return OADG_E_ARG;
+  if (!loss_tc_enabled()) return OADG_E_LIMIT;  // the cross-rank path exists for the tcgen05 kernels only
+  LossWs w = carve_loss_ws(workspace_dev, n_total, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  int launches = 0;
+  w.fhat = const_cast<float*>(recv_dev);
+  w.fhat_ld = c + kPackPad;
+  unpack_labels_kernel<<<(n_total + 255) / 256, 256, 0, stream>>>(recv_dev, n_total, c, w.labels_all);
+  OADG_LAUNCH_CHECK();
+  label_prep_kernel<<<1, 1024, 0, stream>>>(w.labels_all, pair_all_dev, n_total, min_samples, w.meta, w.npos);
+  OADG_LAUNCH_CHECK();
+  int rc = launch_sim_fwd_tc(w, w.labels_all, pair_all_dev, n_total, row0, n_rows, 1.f / temperature, stream, &launches);
+  if (rc) return rc;
+  if ((n_rows + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
+  row_reduce_kernel<<<(n_rows + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
+      w.partial, w.npos, w.meta, n_rows, row0, n_total, (n_total + 127) / 128, loss_weight,
+      reinterpret_cast<RowStats*>(tail_dev), w.red, tail_dev + (size_t)n_rows * 4, w.z, w.ld, w.labels_all, pair_all_dev);
+  OADG_LAUNCH_CHECK();
+  launches += 3;
+  if (launches_out) *launches_out = launches;
+  return 0;
+}
+
+extern "C" int oadg_supcon_finish_packed(const float* tail_all_dev, int world, int n_rows, int c, float* loss_dev,
+                                         void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!tail_all_dev || !loss_dev || !workspace_dev || world < 1 || n_rows <= 0) return OADG_E_ARG;
+  if (((uintptr_t)tail_all_dev & 15) || ((uintptr_t)workspace_dev & 255)) return OADG_E_ARG;
+  LossWs w = carve_loss_ws(workspace_dev, world * n_rows, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  finish_packed_kernel<<<(world * n_rows + 255) / 256, 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(tail_all_dev), world, n_rows, reinterpret_cast<float4*>(w.stats_all), loss_dev);
+  OADG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int oadg_supcon_backward_packed(const float* feats_local_dev, const int32_t* pair_all_dev, int n_total,
+                                           int row0, int n_rows, int c, float temperature, int normalized_input,
+                                           const float* grad_loss_dev, float* grad_feats_dev, void* workspace_dev,
+                                           size_t workspace_bytes, int* launches_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!feats_local_dev || !pair_all_dev || !grad_loss_dev || !grad_feats_dev || !workspace_dev) return OADG_E_ARG;
+  if (n_rows <= 0 || row0 < 0 || row0 + n_rows > n_total) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if (!loss_tc_enabled()) return OADG_E_LIMIT;
+  LossWs w = carve_loss_ws(workspace_dev, n_total, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  int launches = 0;
+  int rc = launch_sim_bwd_tc(w, w.stats_all, w.labels_all, pair_all_dev, n_total, row0, n_rows, 1.f / temperature, stream,
+                             &launches);
   if (rc) return rc;
   normalize_bwd_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(feats_local_dev, w.dpart, kBwdSplits, w.inv1, w.inv2, w.meta,
                                                             grad_loss_dev, n_rows, c, normalized_input, grad_feats_dev);

@@ -29,6 +29,9 @@ struct LossWs {
   float* ft_lo;
   float* z;          // [n, ld] logits kept by the tcgen05 forward for its backward (L2-resident, 17 MB at n=2088)
   float* dpart;      // [kBwdSplits][n, c] partial gradients of the tcgen05 backward
+  int64_t* labels_all;   // [n] labels of the gathered rows (cross-rank path: unpacked from the gathered buffer)
+  RowStats* stats_all;   // [n] row statistics of every rank (cross-rank path)
+  int fhat_ld;       // row stride of fhat in floats (c, or the packed width of a gathered buffer)
   int ld;            // n rounded up to 32
   size_t bytes;
 };
@@ -51,6 +54,7 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
   size_t o_th = take((size_t)c * ld * 4), o_tl = take((size_t)c * ld * 4);
   size_t o_z = take((size_t)n * ld * 4), o_dp = take((size_t)kBwdSplits * n * c * 4);
   size_t o_red = take(1024 * sizeof(double));
+  size_t o_la = take((size_t)n * sizeof(int64_t)), o_sa = take((size_t)n * sizeof(RowStats));
   w.fhat = reinterpret_cast<float*>(p + o_f);
   w.inv1 = reinterpret_cast<float*>(p + o_i1);
   w.inv2 = reinterpret_cast<float*>(p + o_i2);
@@ -66,6 +70,9 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
   w.z = reinterpret_cast<float*>(p + o_z);
   w.dpart = reinterpret_cast<float*>(p + o_dp);
   w.red = reinterpret_cast<double*>(p + o_red);
+  w.labels_all = reinterpret_cast<int64_t*>(p + o_la);
+  w.stats_all = reinterpret_cast<RowStats*>(p + o_sa);
+  w.fhat_ld = c;
   w.ld = ld;
   w.bytes = o;
   return w;

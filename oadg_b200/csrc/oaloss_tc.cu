@@ -96,7 +96,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // split the normalised embeddings into the two TF32 operands, row-major [n, 256] for the forward and
 // transposed [256, ld] for the backward GEMM (32 x 32 tiles through shared memory)
 __global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ f, int n, int ld, float* __restrict__ hi, float* __restrict__ lo,
+split_tf32_kernel(const float* __restrict__ f, int f_ld, int n, int ld, float* __restrict__ hi, float* __restrict__ lo,
                   float* __restrict__ thi, float* __restrict__ tlo) {
   __shared__ float sh[32][33], sl[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -106,7 +106,7 @@ split_tf32_kernel(const float* __restrict__ f, int n, int ld, float* __restrict_
     const int r = r0 + ty + k * 8;
     float h = 0.f, l = 0.f;
     if (r < n) {
-      const float v = f[(size_t)r * 256 + c0 + tx];
+      const float v = f[(size_t)r * f_ld + c0 + tx];
       uint32_t hb, lb;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
       const float rem = __fsub_rn(v, __uint_as_float(hb));
@@ -584,7 +584,7 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
 int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, int row0, int n_rows,
                       float inv_t, cudaStream_t stream, int* launches) {
   using namespace tc;
-  split_tf32_kernel<<<dim3((w.ld + 31) / 32, 8), 256, 0, stream>>>(w.fhat, n, w.ld, w.f_hi, w.f_lo, w.ft_hi, w.ft_lo);
+  split_tf32_kernel<<<dim3((w.ld + 31) / 32, 8), 256, 0, stream>>>(w.fhat, w.fhat_ld, n, w.ld, w.f_hi, w.f_lo, w.ft_hi, w.ft_lo);
   OADG_LAUNCH_CHECK();
   CUtensorMap mh, ml;
   int rc = make_map(&mh, w.f_hi, n, 256, 256, kM);

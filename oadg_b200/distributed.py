@@ -45,8 +45,56 @@ def _all_gather_cat(t, group):
     return torch.cat(parts, dim=0)
 
 
-class CudaBackend:
-    """Local compute through libOADG (tcgen05 kernels)."""
+PACK_PAD = 4   # floats appended to a packed row: the int64 label as two 32-bit words + padding (oadg_supcon_pack_width)
+
+
+class UnpackedBackend:
+    """The packed protocol `_GatheredSupCon` speaks, expressed through a backend's plain `normalize / forward /
+    backward` (the numpy stand-in of the CPU tests derives from this; the CUDA backend overrides all four with
+    direct library calls and no tensor glue)."""
+
+    def pack(self, x, labels, n_total, normalized_input):
+        fhat = self.normalize(x, n_total, normalized_input)
+        n, c = fhat.shape
+        lab = labels.contiguous().view(-1).to(torch.int64)
+        if lab.shape[0] != n:
+            lab = torch.cat([lab, lab[-1:].expand(n - lab.shape[0])])
+        send = torch.zeros(n, c + PACK_PAD, dtype=fhat.dtype, device=fhat.device)
+        send[:, :c] = fhat
+        w32 = lab.view(n, 1).view(torch.int32).view(n, 2)            # the raw bits travel, never their values
+        if fhat.dtype == torch.float32:
+            send[:, c:c + 2] = w32.view(torch.float32)
+        else:                                                        # float64 stand-in: one 64-bit column
+            send[:, c] = lab.view(torch.float64)
+        return send
+
+    def forward_packed(self, recv, pair_all, row0, n_rows, temperature, loss_weight, min_samples):
+        c = recv.shape[1] - PACK_PAD
+        f_all = recv[:, :c].contiguous()
+        if recv.dtype == torch.float32:
+            labels_all = recv[:, c:c + 2].contiguous().view(torch.int32).view(-1, 2).view(torch.int64).view(-1)
+        else:
+            labels_all = recv[:, c].contiguous().view(torch.int64)
+        self._saved = (f_all, labels_all)
+        loss_part, stats = self.forward(f_all, labels_all, pair_all, row0, n_rows, temperature, loss_weight, min_samples)
+        tail = torch.zeros(n_rows + 1, stats.shape[1], dtype=stats.dtype, device=stats.device)
+        tail[:n_rows] = stats
+        tail[n_rows, 0] = loss_part
+        return tail
+
+    def finish(self, tail_all, world, n_rows):
+        t = tail_all.view(world, n_rows + 1, tail_all.shape[1])
+        self._stats_all = t[:, :n_rows].reshape(world * n_rows, tail_all.shape[1]).contiguous()
+        return t[:, n_rows, 0].sum()
+
+    def backward_packed(self, x, pair_all, row0, temperature, normalized_input, grad):
+        f_all, labels_all = self._saved
+        return self.backward(x, f_all, labels_all, pair_all, self._stats_all, row0, temperature, normalized_input, grad)
+
+
+class CudaBackend(UnpackedBackend):
+    """Local compute through libOADG (tcgen05 kernels).  The packed protocol is four library calls on buffers the
+    collectives read / write directly: no pack, slice or copy kernels between them."""
 
     def __init__(self):
         self.launches = 0
@@ -62,6 +110,55 @@ class CudaBackend:
         ws = self._ws_buf
         return ws, (ws.data_ptr() + 255) // 256 * 256, need.value
 
+    # ---- packed protocol
+    def pack(self, x, labels, n_total, normalized_input):
+        _lib.require_cuda()
+        lib = _lib.load()
+        n, c = x.shape
+        self.ws = self._ws(n_total, c, x.device)
+        labels = labels.reshape(-1)
+        if labels.dtype != torch.int64 or labels.device != x.device or not labels.is_contiguous():
+            labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
+        send = torch.empty(n, lib.oadg_supcon_pack_width(c), dtype=torch.float32, device=x.device)
+        _lib.check(lib.oadg_supcon_gather_pack(x.data_ptr(), labels.data_ptr(), labels.shape[0], n, n_total, c,
+                                               int(normalized_input), send.data_ptr(), self.ws[1], self.ws[2],
+                                               _lib.raw_stream(x.device)))
+        self.launches += 1
+        self._c = c
+        return send
+
+    def forward_packed(self, recv, pair_all, row0, n_rows, temperature, loss_weight, min_samples):
+        lib = _lib.load()
+        tail = torch.empty(n_rows + 1, 4, dtype=torch.float32, device=recv.device)
+        nl = ctypes.c_int(0)
+        _lib.check(lib.oadg_supcon_forward_packed(recv.data_ptr(), pair_all.data_ptr(), recv.shape[0], row0, n_rows,
+                                                  self._c, float(temperature), float(loss_weight), int(min_samples),
+                                                  tail.data_ptr(), self.ws[1], self.ws[2], ctypes.byref(nl),
+                                                  _lib.raw_stream(recv.device)))
+        self.launches += nl.value
+        self._n_total = recv.shape[0]
+        return tail
+
+    def finish(self, tail_all, world, n_rows):
+        lib = _lib.load()
+        loss = torch.empty((), dtype=torch.float32, device=tail_all.device)
+        _lib.check(lib.oadg_supcon_finish_packed(tail_all.data_ptr(), world, n_rows, self._c, loss.data_ptr(),
+                                                 self.ws[1], self.ws[2], _lib.raw_stream(tail_all.device)))
+        self.launches += 1
+        return loss
+
+    def backward_packed(self, x, pair_all, row0, temperature, normalized_input, grad):
+        lib = _lib.load()
+        gx = torch.empty_like(x)
+        nl = ctypes.c_int(0)
+        _lib.check(lib.oadg_supcon_backward_packed(x.data_ptr(), pair_all.data_ptr(), self._n_total, row0, x.shape[0],
+                                                   x.shape[1], float(temperature), int(normalized_input),
+                                                   grad.data_ptr(), gx.data_ptr(), self.ws[1], self.ws[2],
+                                                   ctypes.byref(nl), _lib.raw_stream(x.device)))
+        self.launches += nl.value
+        return gx
+
+    # ---- plain entry points (one rank playing several, tests)
     def normalize(self, x, n_total, normalized_input):
         _lib.require_cuda()
         lib = _lib.load()
@@ -131,44 +228,31 @@ def _all_gather_rows(t, group):
 
 
 class _GatheredSupCon(torch.autograd.Function):
-    """Two collectives in the forward (embeddings + labels in one buffer; row statistics + the rank's loss part in
-    another), none in the backward."""
+    """Two collectives in the forward -- the packed [embeddings | labels] rows, then the packed [row statistics ;
+    loss part] tail -- none in the backward; between them only the backend's calls."""
 
     @staticmethod
     def forward(ctx, x, labels, pair_local, cfg, backend, group):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        n, c = x.shape
+        n = x.shape[0]
         temperature, loss_weight, min_samples, normalized_input = cfg
         x = x.contiguous()
-        fhat = backend.normalize(x, world * n, normalized_input)
-        # one gather for [fhat | labels]: the int64 labels travel as two float32-sized columns of raw bits
-        lab = labels.contiguous().view(-1).to(torch.int64).view(n, 1).view(fhat.dtype)   # 2 columns of f32, 1 of f64
-        packed = torch.empty(n, c + lab.shape[1], dtype=fhat.dtype, device=x.device)
-        packed[:, :c] = fhat
-        packed[:, c:] = lab
-        g_all = _all_gather_rows(packed, group)
-        f_all = g_all[:, :c].contiguous()
-        labels_all = g_all[:, c:].contiguous().view(torch.int64).view(-1)
+        send = backend.pack(x, labels, world * n, normalized_input)
+        recv = _all_gather_rows(send, group)
         pair_all = _pair_all_on(x.device, pair_local, world)
-        loss_part, stats = backend.forward(f_all, labels_all, pair_all, rank * n, n, temperature, loss_weight,
-                                           min_samples)
-        # one gather for [row statistics ; loss part]: the loss is the sum of the W parts
-        tail = torch.zeros(n + 1, stats.shape[1], dtype=stats.dtype, device=x.device)
-        tail[:n] = stats
-        tail[n, 0] = loss_part
-        t_all = _all_gather_rows(tail, group).view(world, n + 1, stats.shape[1])
-        stats_all = t_all[:, :n].reshape(world * n, stats.shape[1]).contiguous()
-        loss = t_all[:, n, 0].sum()
-        ctx.save_for_backward(x, f_all, labels_all, pair_all, stats_all)
+        tail = backend.forward_packed(recv, pair_all, rank * n, n, temperature, loss_weight, min_samples)
+        tail_all = _all_gather_rows(tail, group)
+        loss = backend.finish(tail_all, world, n)
+        ctx.save_for_backward(x, recv, pair_all, tail_all)   # recv / tail_all stay alive: the backend reads them again
         ctx.meta = (rank * n, temperature, normalized_input, world, backend)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, f_all, labels_all, pair_all, stats_all = ctx.saved_tensors
+        x, _recv, pair_all, _tail_all = ctx.saved_tensors
         row0, temperature, normalized_input, world, backend = ctx.meta
         g = (grad_out.to(torch.float32) * float(world)).contiguous()   # undo DDP's 1/W gradient averaging
-        gx = backend.backward(x, f_all, labels_all, pair_all, stats_all, row0, temperature, normalized_input, g)
+        gx = backend.backward_packed(x, pair_all, row0, temperature, normalized_input, g)
         return gx, None, None, None, None, None
 
 
@@ -177,13 +261,15 @@ def gathered_contrastive_loss(cont_feats, labels, temperature=0.07, loss_weight=
     """``ContrastiveLossPlus`` semantics with the contrast set all-gathered over ``group``.
 
     cont_feats [N, 256] (N equal on every rank), labels [M, 1] or [M] with M <= N (padded with the last label like
-    contrastive_loss_plus.py:44-47).  With one rank (or no process group) it equals the local loss."""
+    contrastive_loss_plus.py:44-47).  In a world of one rank it equals the local loss; without an initialised process
+    group it raises."""
     if not (dist.is_available() and dist.is_initialized()):
-        raise RuntimeError('gathered_contrastive_loss needs an initialised torch.distributed process group')
-    labels = labels.view(-1)
+        raise RuntimeError('gathered_contrastive_loss needs an initialised torch.distributed process group '
+                           '(a world of one rank is fine: the result then equals the local loss)')
+    labels = labels.reshape(-1)
     n = cont_feats.shape[0]
-    if labels.shape[0] != n:
-        labels = torch.cat([labels, labels[-1:].expand(n - labels.shape[0])])
+    if labels.shape[0] > n or labels.shape[0] < 1:
+        raise ValueError('labels: between 1 and %d entries expected, got %d' % (n, labels.shape[0]))
     if pair_local is None:
         pair_local = reference_pair_map(n)
     backend = backend or CudaBackend()

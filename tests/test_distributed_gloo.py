@@ -22,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-class NumpyBackend:
+class NumpyBackend(__import__('oadg_b200.distributed', fromlist=['UnpackedBackend']).UnpackedBackend):
     """CPU stand-in with the same decomposition as the kernels: local anchors x gathered contrasts, per-row
     statistics (lse, coef, n_pos, u), backward from the statistics of ALL rows."""
 

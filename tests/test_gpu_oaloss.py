@@ -88,10 +88,14 @@ def test_property_invariances(cuda):
 
 
 def test_cuda_core_path_agrees_with_tensor_core_path(cuda):
-    """OADG_LOSS_TC=0 selects the FFMA similarity kernels; both must meet the same tolerance."""
+    """A test build of the library (-DOADG_LOSS_FFMA: CUDA-core similarity kernels, an independent implementation of
+    the same closed form; the product has no such switch) must meet the same tolerance as the tcgen05 path."""
     import os
     import subprocess
     import sys
+    from oadg_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ffma = build.build_test_variant(os.path.join(root, 'tests', 'hostsim', 'libOADG_ffma.so'), ['-DOADG_LOSS_FFMA'])
     code = r'''
 import numpy as np, torch
 from oracle import supcon_np, synth
@@ -104,9 +108,8 @@ assert abs(loss.item() - ref) <= 1e-5 * abs(ref), (loss.item(), ref)
 assert np.linalg.norm(xd.grad.cpu().numpy() - gref) <= 1e-5 * np.linalg.norm(gref)
 print("FFMA-OK", loss.item())
 '''
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, '-c', code], cwd=root, capture_output=True, text=True,
-                         env=dict(os.environ, PYTHONPATH=root, OADG_LOSS_TC='0'))
+                         env=dict(os.environ, PYTHONPATH=root, OADG_LIB=ffma))
     assert 'FFMA-OK' in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
 
 

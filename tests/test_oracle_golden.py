@@ -57,6 +57,26 @@ def test_supcon_oracle_matches_reference_golden(n):
     assert abs(np.linalg.norm(grad) - float(SUPCON['n%d/f64/grad_norm' % n])) <= 1e-10 * np.linalg.norm(grad)
 
 
+@pytest.mark.parametrize('n', [2048, 2088])
+def test_supcon_torch_restatement_matches_reference_golden(n):
+    """oracle/supcon_torch.py (the stock-torch op sequence bench.py times on the GPU as the reference's own path) in
+    f64 on the CPU: loss and gradient rows against the fixtures the reference itself produced."""
+    import torch
+    from oracle import supcon_torch
+    x, labels = synth.make_roi_set(n)
+    xr = x.double().requires_grad_(True)
+    loss = supcon_torch.contrastive_loss_plus_torch(xr, labels, loss_weight=0.01, temperature=0.06)
+    loss.backward()
+    ref64 = float(SUPCON['n%d/f64/loss' % n])
+    assert abs(float(loss) - ref64) <= 1e-12 * abs(ref64)
+    g = xr.grad.numpy()
+    rows = np.concatenate([g[0:8], g[1024:1032], g[n - 8:n]])
+    g64 = SUPCON['n%d/f64/grad_rows' % n]
+    assert np.linalg.norm(rows - g64) <= 1e-10 * np.linalg.norm(g64)
+    few, lab = synth.make_roi_set(2048, n_fg=5)
+    assert float(supcon_torch.contrastive_loss_plus_torch(few, lab, 0.01, 0.06)) == 0.0
+
+
 def test_supcon_oracle_quirks():
     x, labels = synth.make_roi_set(2048, n_fg=5)
     assert supcon_np.supcon_loss(x.numpy(), labels.numpy(), 0.06, 10, 0.01) == float(SUPCON['fewfg/loss']) == 0.0
