@@ -198,6 +198,27 @@ int oadg_oamix_execute(const void* plan_host, size_t plan_bytes,
                        void* workspace_dev, size_t workspace_bytes,
                        int* launches_out, void* stream);
 
+/* Opt-in epilogue of the mix kernel: besides the uint8 views, write what the rest of the training pipeline makes of
+ * them -- Normalize (mmdet/datasets/pipelines/transforms.py:672-704 -> mmcv.imnormalize: BGR->RGB swap, float32
+ * (x - mean) * (1/std) in cv2's arithmetic), Pad to a multiple of size_divisor with zeros (transforms.py:573-640) and
+ * the HWC -> CHW transpose of DefaultFormatBundle (formating.py:217-234) -- as float32 [3, Hp, Wp] tensors, for the
+ * generated views and (optionally) for the untouched source frames (the first view under keep_orig).  The values
+ * are exact: a 3 x 256 table of the normalised value of every uint8 level is built on the host in float64 / float32
+ * exactly as cv2.subtract / cv2.multiply round. */
+typedef struct oadg_fused_out {
+  float mean[3], std[3];        /* per OUTPUT channel (after the optional swap), as the Normalize config gives them */
+  int32_t to_rgb;               /* != 0: channel k of the output is channel 2-k of the frame                        */
+  int32_t size_divisor;         /* >= 1: Hp = ceil(H / d) * d, Wp likewise                                          */
+  float* const* view_f32_dev;   /* HOST table of n_views DEVICE pointers, each [3, Hp, Wp] float32                  */
+  float* const* src_f32_dev;    /* HOST table of n_img DEVICE pointers or NULL (entries may be NULL)                */
+} oadg_fused_out_t;
+
+int oadg_oamix_execute_fused(const void* plan_host, size_t plan_bytes,
+                             const uint8_t* const* src_dev, int n_img,
+                             uint8_t* const* dst_dev, const oadg_fused_out_t* fused,
+                             void* workspace_dev, size_t workspace_bytes,
+                             int* launches_out, void* stream);
+
 /* Same as oadg_oamix_execute with the persistent chain kernel limited to ctas_per_sm resident CTAs per SM
  * (0 = as many as fit, i.e. oadg_oamix_execute).  Two such launches on different streams, each with its own
  * workspace, share the SMs: the tiles of one batch fill the dependency stalls of the other (the reference has no

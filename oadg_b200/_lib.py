@@ -21,6 +21,7 @@ SIGNATURES = {
     'oadg_oamix_workspace_bytes': (_c.c_int, [_vp, _sz, _c.POINTER(_sz)]),
     'oadg_memcpy_async': (_c.c_int, [_vp, _vp, _sz, _c.c_int, _vp]),
     'oadg_oamix_execute': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_oamix_execute_fused': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
     'oadg_oamix_execute_shared': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.c_int, _c.POINTER(_c.c_int),
                                              _vp]),
     'oadg_oamix_execute_profiled': (_c.c_int, [_vp, _sz, _vp, _c.c_int, _vp, _vp, _sz, _c.POINTER(_f32),

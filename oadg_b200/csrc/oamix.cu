@@ -290,8 +290,6 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
     out[d] = fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));
   }
 }
-__device__ __forceinline__ int f32_trunc_u8(float f);
-
 // union of the blurred gt masks of a view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260) as float32 and as
 // uint8(mask*255): written once per batch, read by every bg-only op.  Tile = 256 x 8 px, one column x 8 rows per
 // thread; the boxes whose support meets the tile are listed once per tile, and a thread keeps the x-profile value of
@@ -893,13 +891,7 @@ __device__ __forceinline__ int tma_fetch1(const uint8_t* st, int xm, int ry0, in
   if (kMode == 2) return ((int)p[0] * (32 - fx) + (int)p[1] * fx + 16) >> 5;
   return bilerp_fix(p[0], p[1], p[kGatherMaskBoxBytes], p[kGatherMaskBoxBytes + 1], fx, fy);
 }
-// Conversion-free forms of the blends (the I2F / F2I / I2D / D2I instructions run on the quarter-rate pipe):
-// for an integer 0 <= v < 2^23, float(v) == as_float(0x4B000000 | v) - 2^23 exactly, and for a float 0 <= f < 2^23,
-// int(f) (truncation) == low bits of (f + 2^23) rounded toward -inf; likewise with 2^52 in float64.
-__device__ __forceinline__ float u8_to_f32(int v) { return __fsub_rn(__int_as_float(0x4B000000 | v), 8388608.0f); }
-__device__ __forceinline__ int f32_trunc_u8(float f) { return __float_as_int(__fadd_rd(f, 8388608.0f)) & 0x7FFFFF; }
-__device__ __forceinline__ double u8_to_f64(int v) { return __dsub_rn(__hiloint2double(0x43300000, v), 4503599627370496.0); }
-__device__ __forceinline__ int f64_trunc_u8(double d) { return __double2loint(__dadd_rd(d, 4503599627370496.0)); }
+// Conversion-free forms of the blends (u8_to_f32 / f32_trunc_u8 / u8_to_f64 / f64_trunc_u8, oamix_math.h):
 // bbox_augmentation.py:63-71 (bbo_blend, oamix_math.h) with the box's two float32 factors hoisted
 __device__ __forceinline__ int bbo_blend_fast(float mask, float rest, int img, int aug) {
   return f32_trunc_u8(fadd(fmul(u8_to_f32(img), mask), fmul(u8_to_f32(aug), rest)));
@@ -1742,28 +1734,153 @@ oamix_chain_kernel(const ChainArgs Aparam) {
   }
 }
 
-// branch mixing + object-aware mixing (oa_mix.py:236,281-309); grid = (.., .., views)
+// branch mixing + object-aware mixing (oa_mix.py:236,281-309); grid = (tiles x, tiles y, views).
+// A thread owns groups of 4 pixels (12 bytes = three 32-bit words of each of the up to five frames it reads); the
+// object-aware targets that can be non-zero in the tile are listed once per tile (classify_mix_tile), most tiles
+// have none.  Same per-pixel arithmetic as mix_chunk / mix_pixel (oamix_tile.h, oamix_body.h), which serve frames
+// whose rows are not 4-byte periodic and the host arithmetic check.  kFused: the opt-in Normalize + Pad + CHW
+// float32 epilogue (oadg_fused_out_t).
 constexpr int kTileThreads = 256;
-// (2 CTAs per SM measured best: 3 -> +13 %, 4 -> +5 % kernel time)
-__global__ void __launch_bounds__(kTileThreads, 2)
+template <bool kFused>
+__global__ void __launch_bounds__(kTileThreads, 4)
 mix_kernel(DevPlan P, const MixJob* jobs) {
   __shared__ MixTile T;
+  __shared__ float s_lut[kFused ? 768 : 1];
+  __shared__ float s_keep[256];   // float((1 - m) * v): the float64 term of mix_finish for a pixel outside every target
   const MixJob J = jobs[blockIdx.z];
   const oadg_view_t& V = P.views[J.view];
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   if (x0 >= V.W || y0 >= V.H) return;
   const int x1 = min(x0 + kTileW, V.W), y1 = min(y0 + kTileH, V.H);
-  if (threadIdx.x == 0) classify_mix_tile(P, J, x0, y0, x1, y1, T);
-  __syncthreads();
-  uintptr_t al = ((uintptr_t)J.src) | ((uintptr_t)J.out);
-  for (int b = 0; b < V.width; ++b) al |= (uintptr_t)J.branch[b];
-  const bool vec = ((V.W * 3) & 15) == 0 && (al & 15) == 0;
   const int t = threadIdx.x;
-  const int x = x0 + (t & 15) * kChunkPx;
-  if (x >= x1) return;
-  const int n = min(kChunkPx, x1 - x);
+  if (t == 0) classify_mix_tile(P, J, x0, y0, x1, y1, T);
+  if (kFused)
+    for (int i = t; i < 768; i += kTileThreads) s_lut[i] = P.norm_lut[i];
+  s_keep[t] = (float)dmul(dsub(1.0, V.m), (double)t);   // kTileThreads == 256
+  __syncthreads();
+  const int width = V.width;
+  uintptr_t al = ((uintptr_t)J.src) | ((uintptr_t)J.out);
+  for (int b = 0; b < width; ++b) al |= (uintptr_t)J.branch[b];
+  const bool fast = ((V.W * 3) & 3) == 0 && (al & 3) == 0 && !T.overflow && width <= 4;
+  if (!fast) {   // odd row pitch / many targets / wide mixtures: the per-pixel body
+    for (int q = t; q < kTileW * kTileH; q += kTileThreads) {
+      const int x = x0 + (q & (kTileW - 1)), y = y0 + q / kTileW;
+      if (x < x1 && y < y1) mix_pixel(P, J, x, y);
+    }
+    return;
+  }
+  const float w0 = V.ws[0], w1 = V.ws[1], w2 = V.ws[2], w3 = V.ws[3];
+  const double m = V.m;
+  const float mf = (float)m;
+  const int ntgt = T.n;
+  const int gw = (x1 - x0 + 3) >> 2;                 // 4-pixel groups per tile row
+  const size_t plane = kFused ? (size_t)J.Hp * J.Wp : 0;
 #pragma unroll 1
-  for (int y = y0 + (t >> 4); y < y1; y += 16) mix_chunk(P, J, T, x, y, n, vec);
+  for (int q = t; q < gw * (y1 - y0); q += kTileThreads) {
+    const int y = y0 + q / gw, x = x0 + (q % gw) * 4;
+    const int n = min(4, x1 - x);
+    const size_t o = ((size_t)y * V.W + x) * 3;
+    uint32_t sw[3], bw[4][3], ow[3] = {0u, 0u, 0u};
+    if (n == 4) {
+      const uint32_t* ps = reinterpret_cast<const uint32_t*>(J.src + o);
+      sw[0] = ps[0]; sw[1] = ps[1]; sw[2] = ps[2];
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < width) {
+          const uint32_t* pb = reinterpret_cast<const uint32_t*>(J.branch[b] + o);
+          bw[b][0] = pb[0]; bw[b][1] = pb[1]; bw[b][2] = pb[2];
+        }
+    } else {   // ragged right edge
+      sw[0] = sw[1] = sw[2] = 0u;
+      for (int k = 0; k < 3 * n; ++k) sw[k >> 2] |= (uint32_t)J.src[o + k] << ((k & 3) * 8);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < width) {
+          bw[b][0] = bw[b][1] = bw[b][2] = 0u;
+          for (int k = 0; k < 3 * n; ++k) bw[b][k >> 2] |= (uint32_t)J.branch[b][o + k] << ((k & 3) * 8);
+        }
+    }
+    if (ntgt == 0) {
+      // no object-aware target reaches this tile: orig = aug = 0 and mask_sum = 0, so (mix_finish)
+      //   out = clip(float((1 - m) * img) + float(m) * acc), with the float64 product tabulated per uint8 level
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int wi = k >> 2, sel = 0x7650 + (k & 3);   // byte k of a frame word into an exact float: 2^23 + v
+        float a = fadd(0.f, fmul(w0, fsub(__int_as_float(__byte_perm(bw[0][wi], 0x4B000000u, sel)), 8388608.0f)));
+        if (width > 1) a = fadd(a, fmul(w1, fsub(__int_as_float(__byte_perm(bw[1][wi], 0x4B000000u, sel)), 8388608.0f)));
+        if (width > 2) a = fadd(a, fmul(w2, fsub(__int_as_float(__byte_perm(bw[2][wi], 0x4B000000u, sel)), 8388608.0f)));
+        if (width > 3) a = fadd(a, fmul(w3, fsub(__int_as_float(__byte_perm(bw[3][wi], 0x4B000000u, sel)), 8388608.0f)));
+        float out = fadd(s_keep[__byte_perm(sw[wi], 0u, 0x4440 + (k & 3))], fmul(mf, a));
+        if (!(out > 0.0f)) out = 0.0f;
+        if (out > 255.0f) out = 255.0f;
+        ow[wi] |= (uint32_t)f32_trunc_u8(out) << ((k & 3) * 8);
+      }
+    } else
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float acc[3];
+      int img[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int k = 3 * i + c;
+        float a = fadd(0.f, fmul(w0, u8_to_f32(byte_of(bw[0], k))));
+        if (width > 1) a = fadd(a, fmul(w1, u8_to_f32(byte_of(bw[1], k))));
+        if (width > 2) a = fadd(a, fmul(w2, u8_to_f32(byte_of(bw[2], k))));
+        if (width > 3) a = fadd(a, fmul(w3, u8_to_f32(byte_of(bw[3], k))));
+        acc[c] = a;
+        img[c] = byte_of(sw, k);
+      }
+      float orig[3] = {0.f, 0.f, 0.f}, aug[3] = {0.f, 0.f, 0.f};
+      MixMask ms = {0.f, 0.f};
+      if (ntgt > 0 && i < n) {
+        for (int tg = 0; tg < ntgt; ++tg) {
+          const oadg_target_t& G = P.tgts[T.idx[tg]];
+          float mask;
+          if (G.kind == 0) mask = fg_mask(P, G.gt, x + i, y);
+          else mask = (x + i >= G.box[0] && x + i < G.box[2] && y >= G.box[1] && y < G.box[3]) ? 1.f : 0.f;
+          if (mask == 0.f) continue;   // exact: weight 0 adds +0 and leaves sum == max
+          const float w = mix_target_weight(ms, mask);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) mix_accumulate(orig[c], aug[c], G.m_oa, img[c], acc[c], w);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int k = 3 * i + c;
+        ow[k >> 2] |= (uint32_t)mix_finish(orig[c], aug[c], m, img[c], acc[c], ms.sum) << ((k & 3) * 8);
+      }
+    }
+    if (n == 4) {
+      uint32_t* po = reinterpret_cast<uint32_t*>(J.out + o);
+      po[0] = ow[0]; po[1] = ow[1]; po[2] = ow[2];
+    } else {
+      for (int k = 0; k < 3 * n; ++k) J.out[o + k] = (uint8_t)byte_of(ow, k);
+    }
+    if (kFused) {
+      const size_t at = (size_t)y * J.Wp + x;
+      const bool v4 = n == 4 && ((J.Wp | x) & 3) == 0 && (plane & 3) == 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int c = P.norm_rgb ? 2 - k : k;
+        const float* lut = s_lut + k * 256;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          float* dst = which == 0 ? J.f32_out : J.f32_src;
+          if (!dst) continue;
+          const uint32_t* px = which == 0 ? ow : sw;
+          float* row = dst + k * plane + at;
+          if (v4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<float4*>(row) = make_float4(lut[byte_of(px, c)], lut[byte_of(px, 3 + c)],
+                                                          lut[byte_of(px, 6 + c)], lut[byte_of(px, 9 + c)]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < n) row[i] = lut[byte_of(px, 3 * i + c)];
+          }
+        }
+      }
+    }
+  }
 }
 #define BE_TRY(expr)                       \
   do {                                     \
@@ -1823,6 +1940,7 @@ struct CudaBackend {
   int n_sm = 0, ctas_per_sm = 0;
   // optional CUDA-event timing of the two launches (oadg_oamix_execute_profiled)
   bool profile = false;
+  bool fused = false;   // the mix writes the Normalize + Pad + CHW epilogue (oadg_oamix_execute_fused)
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   int n_items = 0, n_tiles = 0;
   const unsigned long long* kind_ns_dev = nullptr;
@@ -1955,6 +2073,10 @@ struct CudaBackend {
     BE_TRY(cudaMemsetAsync(dst, 0, bytes, stream));
     return 0;
   }
+  int zero2d(void* dst, size_t pitch, size_t width, size_t rows) {
+    BE_TRY(cudaMemset2DAsync(dst, pitch, 0, width, rows, stream));
+    return 0;
+  }
   int chain(const ChainArgs& A, const ChainArgs& Hh, const PlanView&) {
     fault_dev = A.fault;
     if (profile) {
@@ -1987,7 +2109,8 @@ struct CudaBackend {
   }
   int mix(const DevPlan& P, const MixJob* jobs, int n) {
     dim3 grid((P.max_w + kTileW - 1) / kTileW, (P.max_h + kTileH - 1) / kTileH, n);
-    mix_kernel<<<grid, kTileThreads, 0, stream>>>(P, jobs);
+    if (fused) mix_kernel<true><<<grid, kTileThreads, 0, stream>>>(P, jobs);
+    else mix_kernel<false><<<grid, kTileThreads, 0, stream>>>(P, jobs);
     BE_TRY(cudaGetLastError());
     ++launches;
     if (profile) BE_TRY(cudaEventRecord(ev[2], stream));
@@ -2081,6 +2204,18 @@ extern "C" int oadg_oamix_execute_shared(const void* plan_host, size_t plan_byte
   be.stream = (cudaStream_t)stream;
   be.want_ctas = ctas_per_sm;
   int rc = execute_plan(be, plan_host, plan_bytes, src_dev, n_img, dst_dev, workspace_dev, workspace_bytes);
+  if (launches_out) *launches_out = be.launches;
+  return rc;
+}
+
+extern "C" int oadg_oamix_execute_fused(const void* plan_host, size_t plan_bytes, const uint8_t* const* src_dev,
+                                        int n_img, uint8_t* const* dst_dev, const oadg_fused_out_t* fused,
+                                        void* workspace_dev, size_t workspace_bytes, int* launches_out, void* stream) {
+  if (!fused) return OADG_E_ARG;
+  CudaBackend be;
+  be.stream = (cudaStream_t)stream;
+  be.fused = true;
+  int rc = execute_plan(be, plan_host, plan_bytes, src_dev, n_img, dst_dev, workspace_dev, workspace_bytes, fused);
   if (launches_out) *launches_out = be.launches;
   return rc;
 }

@@ -25,6 +25,10 @@ struct DevPlan {
   const float* maskf;    // [view][max_h*max_w] float32 value
   const uint8_t* masku;  // [view][max_h*max_w] uint8(mask*255), the image bg-only ops warp (bbox_augmentation.py:264)
   size_t mask_stride;    // max_h*max_w
+  // fused Normalize + Pad + CHW epilogue of the mix (oadg_fused_out_t): normalised float32 value of every uint8 level,
+  // [3 output planes][256]; plane k reads frame channel (norm_rgb ? 2 - k : k)
+  const float* norm_lut;
+  int32_t norm_rgb, pad0;
 };
 
 struct Lane {            // one (view, branch) chain alive at the current depth
@@ -130,6 +134,9 @@ struct MixJob {
   const uint8_t* src;
   const uint8_t* branch[OADG_MAX_WIDTH];
   uint8_t* out;
+  float* f32_out;        // fused epilogue: [3, Hp, Wp] of the generated view, or null
+  float* f32_src;        // ... and of the source frame, or null
+  int32_t Wp, Hp;
 };
 
 struct LutJob {
@@ -332,7 +339,16 @@ OADG_HD void mix_pixel(const DevPlan& P, const MixJob& J, int x, int y) {
     for (int c = 0; c < 3; ++c) mix_accumulate(orig[c], aug[c], T.m_oa, img[c], acc[c], w);
   }
   uint8_t* q = J.out + o;
-  for (int c = 0; c < 3; ++c) q[c] = (uint8_t)mix_finish(orig[c], aug[c], V.m, img[c], acc[c], ms.sum);
+  int res[3];
+  for (int c = 0; c < 3; ++c) q[c] = (uint8_t)(res[c] = mix_finish(orig[c], aug[c], V.m, img[c], acc[c], ms.sum));
+  if (J.f32_out || J.f32_src) {   // fused Normalize + Pad + CHW epilogue
+    const size_t plane = (size_t)J.Hp * J.Wp, at = (size_t)y * J.Wp + x;
+    for (int k = 0; k < 3; ++k) {
+      const int c = P.norm_rgb ? 2 - k : k;
+      if (J.f32_out) J.f32_out[k * plane + at] = P.norm_lut[k * 256 + res[c]];
+      if (J.f32_src) J.f32_src[k * plane + at] = P.norm_lut[k * 256 + img[c]];
+    }
+  }
 }
 
 }  // namespace oadg

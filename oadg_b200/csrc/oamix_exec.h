@@ -201,7 +201,7 @@ inline void make_layout(const PlanView& pv, Layout& L) {
                    2 * align_up_sz((size_t)L.max_deps * sizeof(int32_t), 16) +
                    align_up_sz((size_t)L.max_items * sizeof(int32_t), 16) +
                    align_up_sz((size_t)L.max_perm * sizeof(int32_t), 16) +
-                   align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) +
+                   align_up_sz((size_t)h.n_views * sizeof(MixJob), 16) + 3 * 256 * sizeof(float) +
                    align_up_sz((size_t)L.max_maps * kTensorMapBytes, 128) + 128 +
                    align_up_sz((size_t)(L.max_items + kRingHeader) * sizeof(unsigned long long), 16) + 256;
   // plan blob and launch tables are contiguous so that one H2D copy uploads both
@@ -365,11 +365,11 @@ struct ChainArgs {       // everything the chain kernel needs (device pointers)
 //   grid()                         CTAs the chain kernel will run (one per SM)
 //   upload(dst, src_host, bytes)   zero(dst, bytes)
 //   chain(args, host_tables...)    the work-queue interpreter (one persistent launch on the device)
-//   mix(P, jobs, n)
+//   mix(P, jobs, n)                zero2d(dst, pitch_bytes, width_bytes, rows)
 //   make_map(dst, base, inner_bytes, rows, box_inner)   encode a tensor map into dst (host staging), != 0: unavailable
 template <class Backend>
 int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const uint8_t* const* src, int n_img,
-                 uint8_t* const* dst, void* workspace, size_t workspace_bytes) {
+                 uint8_t* const* dst, void* workspace, size_t workspace_bytes, const oadg_fused_out_t* fused = nullptr) {
 #ifdef OADG_SCHED_TIMING
   auto _t0 = std::chrono::steady_clock::now();
 #endif
@@ -431,6 +431,7 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   const size_t t_pending = carve((size_t)L.max_items * sizeof(int32_t));
   const size_t t_perm = carve((size_t)L.max_perm * sizeof(int32_t));
   const size_t t_mix = carve((size_t)h.n_views * sizeof(MixJob));
+  const size_t t_norm = carve(3 * 256 * sizeof(float));
   to = align_up_sz(to, 128);   // L.off_plan is 256-byte aligned: the maps are 128-byte aligned on the device too
   const size_t t_maps = carve((size_t)L.max_maps * kTensorMapBytes);
   const size_t t_ring = carve((size_t)(L.max_items + kRingHeader) * sizeof(unsigned long long));
@@ -818,6 +819,31 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
     J.src = src[V.img];
     J.out = dst[v];
     for (int b = 0; b < V.width; ++b) J.branch[b] = final_frame[(size_t)v * OADG_MAX_WIDTH + b];
+    J.f32_out = J.f32_src = nullptr;
+    J.Wp = J.Hp = 0;
+    if (fused) {
+      const int d = fused->size_divisor;
+      J.Wp = (V.W + d - 1) / d * d;
+      J.Hp = (V.H + d - 1) / d * d;
+      J.f32_out = fused->view_f32_dev[v];
+      J.f32_src = fused->src_f32_dev ? fused->src_f32_dev[V.img] : nullptr;
+    }
+  }
+  if (fused) {
+    // normalised value of every uint8 level per output plane, rounded exactly like mmcv.imnormalize's
+    // cv2.subtract(float32 img, float64 mean) then cv2.multiply(float32 img, float64 1/std): float64 arithmetic,
+    // float32 result, twice
+    if (fused->size_divisor < 1 || !fused->view_f32_dev) return OADG_E_ARG;
+    for (int v = 0; v < h.n_views; ++v)
+      if (!fused->view_f32_dev[v]) return OADG_E_ARG;
+    float* lut = reinterpret_cast<float*>(stage.data() + t_norm);
+    for (int k = 0; k < 3; ++k) {
+      const double mean = (double)fused->mean[k], stdinv = 1.0 / (double)fused->std[k];
+      for (int i = 0; i < 256; ++i) {
+        const float d1 = (float)((double)(float)i - mean);
+        lut[k * 256 + i] = (float)((double)d1 * stdinv);
+      }
+    }
   }
 
   OADG_T("succ+ring+mix");
@@ -842,6 +868,9 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   P.maskf = reinterpret_cast<const float*>(ws + L.off_maskf);
   P.masku = reinterpret_cast<const uint8_t*>(ws + L.off_masku);
   P.mask_stride = (size_t)h.max_h * h.max_w;
+  P.norm_lut = reinterpret_cast<const float*>(dplan + t_norm);
+  P.norm_rgb = fused ? (fused->to_rgb != 0) : 0;
+  P.pad0 = 0;
   A.lanes = reinterpret_cast<const Lane*>(dplan + t_lanes);
   A.lutjobs = reinterpret_cast<const LutJob*>(dplan + t_lut);
   A.chains = reinterpret_cast<const Chain*>(dplan + t_chain);
@@ -886,7 +915,23 @@ int execute_plan(Backend& be, const void* plan_host, size_t plan_bytes, const ui
   Hh.ring = ring;
   OADG_T("upload+zero");
   if ((rc = be.chain(A, Hh, pv))) return rc;
-  return be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views);
+  if ((rc = be.mix(P, reinterpret_cast<const MixJob*>(dplan + t_mix), h.n_views))) return rc;
+  if (fused) {   // Pad (transforms.py:573-640): zeros right of column W and below row H, in every plane
+    for (int v = 0; v < h.n_views; ++v) {
+      const oadg_view_t& V = pv.views[v];
+      const MixJob& J = mixjobs[v];
+      float* bufs[2] = {J.f32_out, J.f32_src};
+      for (float* b : bufs) {
+        if (!b) continue;
+        for (int k = 0; k < 3; ++k) {
+          float* plane = b + (size_t)k * J.Hp * J.Wp;
+          if (J.Wp > V.W && (rc = be.zero2d(plane + V.W, (size_t)J.Wp * 4, (size_t)(J.Wp - V.W) * 4, (size_t)V.H))) return rc;
+          if (J.Hp > V.H && (rc = be.zero(plane + (size_t)V.H * J.Wp, (size_t)(J.Hp - V.H) * J.Wp * 4))) return rc;
+        }
+      }
+    }
+  }
+  return 0;
 }
 
 }  // namespace oadg

@@ -163,6 +163,34 @@ OADG_HD void classify_mix_tile(const DevPlan& P, const MixJob& J, int x0, int y0
   }
 }
 
+// fused Normalize + Pad + CHW epilogue (oadg_fused_out_t): the n pixels of a chunk as float32 into the 3 planes
+OADG_HD void emit_f32_chunk(const DevPlan& P, const MixJob& J, const Chunk& px, float* dst, int x, int y, int n) {
+  const size_t plane = (size_t)J.Hp * J.Wp, at = (size_t)y * J.Wp + x;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int k = 0; k < 3; ++k) {
+    const int c = P.norm_rgb ? 2 - k : k;
+    const float* lut = P.norm_lut + k * 256;
+    float* row = dst + k * plane + at;
+#ifdef __CUDA_ARCH__
+    if (n == kChunkPx && ((J.Wp | x) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (plane & 3) == 0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        reinterpret_cast<float4*>(row)[g] =
+            make_float4(lut[chunk_get(px, (4 * g) * 3 + c)], lut[chunk_get(px, (4 * g + 1) * 3 + c)],
+                        lut[chunk_get(px, (4 * g + 2) * 3 + c)], lut[chunk_get(px, (4 * g + 3) * 3 + c)]);
+      continue;
+    }
+#pragma unroll
+    for (int i = 0; i < kChunkPx; ++i)   // unrolled: the chunk must stay in registers (no dynamic byte index)
+      if (i < n) row[i] = lut[chunk_get(px, i * 3 + c)];
+#else
+    for (int i = 0; i < n; ++i) row[i] = lut[chunk_get(px, i * 3 + c)];
+#endif
+  }
+}
+
 // 16 pixels of branch mixing + object-aware mixing, 4 pixels (12 bytes = 3 words) at a time
 OADG_HD void mix_chunk(const DevPlan& P, const MixJob& J, const MixTile& T, int x, int y, int n, bool vec) {
   const oadg_view_t& V = P.views[J.view];
@@ -194,10 +222,10 @@ OADG_HD void mix_chunk(const DevPlan& P, const MixJob& J, const MixTile& T, int 
 #endif
     for (int k = 0; k < 12; ++k) {
       const int kk = g * 12 + k;
-      float a = fadd(0.f, fmul(w0, (float)chunk_get(br[0], kk)));
-      if (width > 1) a = fadd(a, fmul(w1, (float)chunk_get(br[1], kk)));
-      if (width > 2) a = fadd(a, fmul(w2, (float)chunk_get(br[2], kk)));
-      if (width > 3) a = fadd(a, fmul(w3, (float)chunk_get(br[3], kk)));
+      float a = fadd(0.f, fmul(w0, u8_to_f32(chunk_get(br[0], kk))));
+      if (width > 1) a = fadd(a, fmul(w1, u8_to_f32(chunk_get(br[1], kk))));
+      if (width > 2) a = fadd(a, fmul(w2, u8_to_f32(chunk_get(br[2], kk))));
+      if (width > 3) a = fadd(a, fmul(w3, u8_to_f32(chunk_get(br[3], kk))));
       acc[k] = a;
     }
     uint32_t ow[3] = {0u, 0u, 0u};
@@ -230,6 +258,8 @@ OADG_HD void mix_chunk(const DevPlan& P, const MixJob& J, const MixTile& T, int 
     out.w[g * 3 + 2] = ow[2];
   }
   chunk_store(J.out + o, n, vec, out);
+  if (J.f32_out) emit_f32_chunk(P, J, out, J.f32_out, x, y, n);
+  if (J.f32_src) emit_f32_chunk(P, J, src, J.f32_src, x, y, n);
 }
 
 }  // namespace oadg

@@ -133,6 +133,12 @@ class _SamplerCfg(__import__('ctypes').Structure):
                 ('sigma_ratio', _c.c_double)]
 
 
+class _FusedOut(__import__('ctypes').Structure):     # oadg_fused_out_t (include/oadg.h)
+    _c = __import__('ctypes')
+    _fields_ = [('mean', _c.c_float * 3), ('std', _c.c_float * 3), ('to_rgb', _c.c_int32), ('size_divisor', _c.c_int32),
+                ('view_f32', _c.c_void_p), ('src_f32', _c.c_void_p)]
+
+
 class _ViewPlan:
     __slots__ = ('h', 'w', 'ws', 'ml_boxes', 'depths', 'ops', 'scores', 'oa_low', 'oa_boxes', 'm', 'm_oa')
 
@@ -146,8 +152,16 @@ class OAMix:
                  random_box_scale=(0.01, 0.1), random_box_ratio=(3, 1 / 3),
                  oa_random_box_scale=(0.005, 0.1), oa_random_box_ratio=(3, 1 / 3), num_bboxes=(3, 5),
                  spatial_ratio=4, sigma_ratio=0.3,
+                 fused_output=None,
                  **kwargs):
+        """Reference keys (oa_mix.py:34-41) plus one opt-in extension: ``fused_output=dict(mean=..., std=...,
+        to_rgb=True, size_divisor=32)`` (the config's ``img_norm_cfg`` + ``Pad``) makes the device paths also return
+        what Normalize -> Pad -> DefaultFormatBundle produce from the frames: float32 [3, Hp, Wp] CUDA tensors
+        ``img_norm`` / ``img2_norm`` (transforms.py:672-704,573-640, formating.py:217-234), written by the mix
+        kernel itself."""
         self.aug_list = get_aug_list(version)
+        self.fused_output = dict(fused_output) if fused_output else None
+        self.last_fused = None
         self.version = version
         self.num_views = num_views
         self.keep_orig = keep_orig
@@ -577,7 +591,7 @@ class OAMix:
             self._ws_cache = torch.empty(want + 4096, dtype=torch.uint8, device=device)
         return self._ws_cache
 
-    def execute(self, jobs, imgs, outs=None, stream=None, profile=None):
+    def execute(self, jobs, imgs, outs=None, stream=None, profile=None, fused=None):
         """Run the packed plans.  jobs: a packed plan blob (uint8 array, one view per image) or a list of
         (view_plan, gt, img_index); imgs: list of CUDA u8 HWC tensors; returns one output tensor per view.
         ``profile`` (a dict) switches to the event-timed entry point and receives per-kernel ms / counts."""
@@ -623,6 +637,23 @@ class OAMix:
             self.last_launches += 2
             return outs
         n = ctypes.c_int(0)
+        if fused is not None:   # (view_f32 tensors, src_f32 tensors or None): the mix kernel's Normalize + Pad + CHW epilogue
+            views32, srcs32 = fused
+            cfg = self.fused_output
+            fo = _FusedOut()
+            fo.mean = (ctypes.c_float * 3)(*[float(v) for v in cfg['mean']])
+            fo.std = (ctypes.c_float * 3)(*[float(v) for v in cfg['std']])
+            fo.to_rgb = int(bool(cfg.get('to_rgb', True)))
+            fo.size_divisor = int(cfg.get('size_divisor', 1) or 1)
+            vt = (ctypes.c_void_p * len(views32))(*[int(t.data_ptr()) for t in views32])
+            st_ = (ctypes.c_void_p * len(imgs))(*[int(t.data_ptr()) if t is not None else None for t in srcs32]) \
+                if srcs32 is not None else None
+            fo.view_f32 = ctypes.cast(vt, ctypes.c_void_p)
+            fo.src_f32 = ctypes.cast(st_, ctypes.c_void_p) if st_ is not None else None
+            _lib.check(lib.oadg_oamix_execute_fused(blob.ctypes.data, blob.nbytes, src, len(imgs), dst,
+                                                    ctypes.addressof(fo), base, room, ctypes.byref(n), s_raw))
+            self.last_launches += n.value
+            return outs
         _lib.check(lib.oadg_oamix_execute(blob.ctypes.data, blob.nbytes, src, len(imgs), dst, base, room,
                                           ctypes.byref(n), s_raw))
         self.last_launches += n.value
@@ -646,7 +677,11 @@ class OAMix:
         else:
             scores = self.saliency_scores(imgs, gt_list, stream, inputs_ready=inputs_ready)
         plan = self.sample_plan([(int(t.shape[0]), int(t.shape[1])) for t in imgs], gt_list, scores)
-        outs = self.execute(plan.blob, imgs, outs=outs, stream=stream, profile=profile)
+        fused = None
+        if self.fused_output is not None and profile is None:
+            fused = self.fused_buffers(imgs)
+            self.last_fused = fused
+        outs = self.execute(plan.blob, imgs, outs=outs, stream=stream, profile=profile, fused=fused)
         if profile is not None:  # algorithmic bytes: 1 read + 1 write of a frame per lane step (+ the mix, per view)
             for (h, w), dsum in zip(plan.hw, plan.depth_sums):
                 profile['step_bytes'] = profile.get('step_bytes', 0) + 2 * 3 * int(h) * int(w) * int(dsum)
@@ -654,6 +689,17 @@ class OAMix:
                     3 * int(h) * int(w) * (2 * int(dsum) + self.mixture_width + 2)
         oamix_boxes = [np.stack(list(b), axis=0) for b in plan.oa_boxes]   # ValueError when none could be placed
         return outs, oamix_boxes, plan.ml_boxes
+
+    def fused_buffers(self, imgs):
+        """(view_f32, src_f32): float32 [3, Hp, Wp] CUDA tensors for the fused Normalize + Pad + CHW output of every
+        generated view and of every source frame."""
+        torch = _lib.require_cuda()
+        d = int(self.fused_output.get('size_divisor', 1) or 1)
+
+        def buf(t):
+            h, w = int(t.shape[0]), int(t.shape[1])
+            return torch.empty(3, -(-h // d) * d, -(-w // d) * d, dtype=torch.float32, device=t.device)
+        return [buf(t) for t in imgs], [buf(t) for t in imgs]
 
     # ------------------------------------------------------------------ host buffers
     def _to_device(self, img, slot, stream=None):

@@ -395,3 +395,27 @@ def saliency_score_emul(crop):
     with np.errstate(all='ignore'):
         v = np.where(np.isnan(out), 0, out * _F32(255)).astype(np.uint8)
     return float(v.astype(np.int64).sum() / (w * h))
+
+
+# ---- Normalize -> Pad -> DefaultFormatBundle on one frame (the fused epilogue's oracle) ---------------------------
+def imnormalize_pad_chw(img_u8, mean, std, to_rgb=True, size_divisor=32):
+    """What the training pipeline makes of a uint8 HWC frame after OAMix:
+    ``Normalize`` (mmdet/datasets/pipelines/transforms.py:672-704) calls ``mmcv.imnormalize`` -- mmcv is third party
+    and absent from this image (PARITY UNPINNED against its binary); its published source (mmcv 1.x
+    ``mmcv/image/photometric.py::imnormalize_``) is restated here with the cv2 calls it makes: float32 copy,
+    ``cv2.cvtColor(BGR2RGB)`` in place, ``cv2.subtract(img, float64 mean)``, ``cv2.multiply(img, 1 / float64 std)``;
+    ``Pad(size_divisor)`` (transforms.py:573-640 -> ``mmcv.impad_to_multiple``, zeros right / below) and the HWC ->
+    CHW transpose of ``DefaultFormatBundle`` (formating.py:217-234).  Returns float32 [3, Hp, Wp]."""
+    import cv2
+    img = np.ascontiguousarray(img_u8).astype(np.float32)
+    mean64 = np.float64(np.asarray(mean, np.float32).reshape(1, -1))
+    stdinv = 1 / np.float64(np.asarray(std, np.float32).reshape(1, -1))
+    if to_rgb:
+        cv2.cvtColor(img, cv2.COLOR_BGR2RGB, img)
+    cv2.subtract(img, mean64, img)
+    cv2.multiply(img, stdinv, img)
+    h, w = img.shape[:2]
+    hp, wp = -(-h // size_divisor) * size_divisor, -(-w // size_divisor) * size_divisor
+    out = np.zeros((hp, wp, 3), np.float32)
+    out[:h, :w] = img
+    return np.ascontiguousarray(out.transpose(2, 0, 1))

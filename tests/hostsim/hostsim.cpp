@@ -25,6 +25,10 @@ struct HostBackend {
   int grid() { return n_cta; }
   int upload(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
   int zero(void* dst, size_t bytes) { memset(dst, 0, bytes); return 0; }
+  int zero2d(void* dst, size_t pitch, size_t width, size_t rows) {
+    for (size_t r = 0; r < rows; ++r) memset(static_cast<char*>(dst) + r * pitch, 0, width);
+    return 0;
+  }
   int make_map(void*, const void*, size_t, int, int) { return -1; }   // no TMA on the host: the per-pixel bodies gather directly
 
   static void profile_item(const ChainArgs& A, int obj) {
@@ -316,6 +320,20 @@ extern "C" int hostsim_oamix_execute(const void* plan, size_t bytes, const uint8
   HostBackend be;
   rc = execute_plan(be, plan, bytes, src, n_img, dst, ws, need);
   if (launches_out) *launches_out = be.launches;
+  free(ws);
+  return rc;
+}
+
+// with the fused Normalize + Pad + CHW epilogue (host twin of oadg_oamix_execute_fused)
+extern "C" int hostsim_oamix_execute_fused(const void* plan, size_t bytes, const uint8_t* const* src, int n_img,
+                                           uint8_t* const* dst, const oadg_fused_out_t* fused) {
+  size_t need = 0;
+  int rc = hostsim_workspace_bytes(plan, bytes, &need);
+  if (rc) return rc;
+  void* ws = aligned_alloc(256, (need + 255) / 256 * 256 + 256);
+  if (!ws) return -100;
+  HostBackend be;
+  rc = execute_plan(be, plan, bytes, src, n_img, dst, ws, need, fused);
   free(ws);
   return rc;
 }

@@ -364,3 +364,26 @@ def test_starved_queue_raises_instead_of_returning_half_written_views(cuda):
     env = dict(os.environ, OADG_DEBUG='64')
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120, env=env)
     assert 'RAISED' in out.stdout and 'OADG_E_PLAN' in out.stdout, (out.stdout[-500:], out.stderr[-500:])
+
+
+@pytest.mark.parametrize('hw', [(96, 160), (200, 333), (1024, 2048)])
+def test_fused_normalize_pad_chw_output_is_exact(cuda, hw):
+    """fused_output: the mix kernel also writes Normalize + Pad + HWC->CHW float32 tensors for the generated view and
+    the source frame; bit-exact against the oracle's restatement (mmcv.imnormalize with the installed cv2) applied
+    to the uint8 view of the same call."""
+    from oadg_b200 import OAMix
+    from oracle import prims_np
+    norm = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True, size_divisor=32)
+    h, w = hw
+    img, gt = synth.make_image(2, h, w, 5)
+    t = OAMix(**dict(OAMIX_CFG, version='augmix', fused_output=norm))
+    np.random.seed(77)
+    outs, _, _ = t.oamix_batch(_views(cuda, [img]), [gt])
+    views32, srcs32 = t.last_fused
+    plain = OAMix(**dict(OAMIX_CFG, version='augmix'))
+    np.random.seed(77)
+    outs2, _, _ = plain.oamix_batch(_views(cuda, [img]), [gt])
+    u8 = outs[0].cpu().numpy()
+    assert np.array_equal(u8, outs2[0].cpu().numpy())          # the uint8 view is unchanged by the epilogue
+    assert np.array_equal(views32[0].cpu().numpy(), prims_np.imnormalize_pad_chw(u8, norm['mean'], norm['std'], True, 32))
+    assert np.array_equal(srcs32[0].cpu().numpy(), prims_np.imnormalize_pad_chw(img, norm['mean'], norm['std'], True, 32))

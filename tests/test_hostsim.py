@@ -192,3 +192,48 @@ def test_randomized_sweep_against_oracle_in_two_execution_orders(hostsim, case):
     assert np.array_equal(outs[0], outs[1])
     d = np.abs(outs[0].astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d != 0).mean() <= 1e-3, (int(d.max()), float((d != 0).mean()))
+
+
+class _FusedOut(ctypes.Structure):   # oadg_fused_out_t
+    _fields_ = [('mean', ctypes.c_float * 3), ('std', ctypes.c_float * 3), ('to_rgb', ctypes.c_int32),
+                ('size_divisor', ctypes.c_int32), ('view_f32', ctypes.c_void_p), ('src_f32', ctypes.c_void_p)]
+
+
+NORM = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375])
+
+
+@pytest.mark.parametrize('hw,to_rgb,div', [((96, 160), True, 32), ((101, 203), True, 32), ((64, 64), False, 1)])
+def test_fused_normalize_pad_chw_epilogue_is_exact(hostsim, hw, to_rgb, div):
+    """The mix's opt-in epilogue (Normalize + Pad + HWC->CHW float32, oadg_fused_out_t) against the oracle's restatement
+    of mmcv.imnormalize / impad_to_multiple / DefaultFormatBundle with the installed cv2: bit-exact floats, for the
+    generated view (computed from the uint8 view the same call returns) and for the untouched source frame."""
+    from oadg_b200.oamix import OAMix
+    from oracle import prims_np
+    h, w = hw
+    cfg = sampler_cfg(dict(OAMIX_CFG, version='augmix'))
+    img, gt = synth.make_image(5, h, w, 3)
+    np.random.seed(31)
+    _, plan = oamix_np.oamix_view(img, gt, **cfg)
+    np.random.seed(31)
+    t = OAMix(**cfg)
+    vp = t._sample_head(h, w, gt)
+    t._sample_tail(vp, gt, plan['scores'])
+    blob = t._pack([(vp, gt, 0)])
+    out = np.zeros_like(img)
+    hp, wp = -(-h // div) * div, -(-w // div) * div
+    v32 = np.full((3, hp, wp), np.nan, np.float32)
+    s32 = np.full((3, hp, wp), np.nan, np.float32)
+    fo = _FusedOut()
+    fo.mean = (ctypes.c_float * 3)(*NORM['mean'])
+    fo.std = (ctypes.c_float * 3)(*NORM['std'])
+    fo.to_rgb, fo.size_divisor = int(to_rgb), div
+    vt = (ctypes.c_void_p * 1)(v32.ctypes.data)
+    st = (ctypes.c_void_p * 1)(s32.ctypes.data)
+    fo.view_f32, fo.src_f32 = ctypes.cast(vt, ctypes.c_void_p), ctypes.cast(st, ctypes.c_void_p)
+    src = (ctypes.c_void_p * 1)(img.ctypes.data)
+    dst = (ctypes.c_void_p * 1)(out.ctypes.data)
+    rc = hostsim.hostsim_oamix_execute_fused(ctypes.c_void_p(blob.ctypes.data), ctypes.c_size_t(blob.nbytes), src, 1, dst,
+                                             ctypes.byref(fo))
+    assert rc == 0, rc
+    assert np.array_equal(v32, prims_np.imnormalize_pad_chw(out, NORM['mean'], NORM['std'], to_rgb, div))
+    assert np.array_equal(s32, prims_np.imnormalize_pad_chw(img, NORM['mean'], NORM['std'], to_rgb, div))
