@@ -325,6 +325,16 @@ int oadg_supcon_backward_packed(const float* feats_local_dev, const int32_t* pai
                                 float* grad_feats_dev, void* workspace_dev, size_t workspace_bytes, int* launches_out,
                                 void* stream);
 
+/* ---- OA-Loss, consistency half ------------------------------------------------------------------------------
+ * Jensen-Shannon divergence between the two views' class distributions (cross_entropy_loss_plus.py:264-319
+ * jsdv1_3_2aug): pred_dev [2 n, c] float32 = view 1 rows then view 2 rows, c <= 32 (c == 1: the RPN's single logit,
+ * classes (sigmoid, 1 - sigmoid); else softmax).  Writes loss_dev[0] = sum of the row divergences / n and
+ * grad_dev [2 n, c] = d loss / d pred (so the backward is a scale).  scratch_dev: oadg_jsd2_scratch_bytes() bytes,
+ * zeroed once by the caller. */
+int oadg_jsd2_scratch_bytes(void);
+int oadg_jsd2_forward(const float* pred_dev, int n, int c, float* loss_dev, float* grad_dev, void* scratch_dev,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

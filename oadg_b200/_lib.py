@@ -47,6 +47,8 @@ SIGNATURES = {
     'oadg_supcon_finish_packed': (_c.c_int, [_vp, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _sz, _vp]),
     'oadg_supcon_backward_packed': (_c.c_int, [_vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _f32, _c.c_int, _vp,
                                                _vp, _vp, _sz, _c.POINTER(_c.c_int), _vp]),
+    'oadg_jsd2_scratch_bytes': (_c.c_int, []),
+    'oadg_jsd2_forward': (_c.c_int, [_vp, _c.c_int, _c.c_int, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -40,6 +40,17 @@ def reference_pair_map(n, ori_size=ORI_SIZE):
     return pair
 
 
+def yolo_pair_map(n):
+    """The two-view layout of ``supcontrast_yolo`` (contrastive_loss.py:234-299): ``ori_size = n // 2`` rows per view,
+    row i <-> row i + n // 2; a trailing odd row has no other view (its ``rp_size`` is 0)."""
+    half = n // 2
+    pair = np.full(n, -1, np.int32)
+    i = np.arange(half)
+    pair[i] = i + half
+    pair[i + half] = i
+    return pair
+
+
 _PAIR_CACHE = {}
 
 
@@ -117,6 +128,18 @@ def supcontrast(logits_clean, labels=None, num_views=2, lambda_weight=0.1, tempe
     feats = logits_clean if logits_clean.dtype == torch.float32 else logits_clean.float()
     return _SupConFn.apply(feats, labels, pair, temper, loss_weight, min_samples, normalized_input,
                            stats if stats is not None else {})
+
+
+def supcontrast_yolo(logits_clean, labels=None, num_views=2, lambda_weight=0.1, temper=0.07, min_samples=10):
+    """Reference ``supcontrast_yolo`` (contrastive_loss.py:234-299; called by dense_heads/yolo_head_cont.py:463 on the
+    sampled grid cells of both views): the same masked InfoNCE with the view boundary at N // 2.  Same kernels, other
+    pair map."""
+    n = logits_clean.shape[0]
+    key = ('yolo', n, str(logits_clean.device))
+    if key not in _PAIR_CACHE:
+        _PAIR_CACHE[key] = torch.from_numpy(yolo_pair_map(n)).to(logits_clean.device)
+    return supcontrast(logits_clean, labels, num_views=num_views, lambda_weight=lambda_weight, temper=temper,
+                       min_samples=min_samples, pair=_PAIR_CACHE[key])
 
 
 @LOSSES.register_module()

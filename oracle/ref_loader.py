@@ -115,6 +115,14 @@ def load_reference():
     clossp = _load('mmdet.models.losses.oadg.contrastive_loss_plus',
                    'mmdet/models/losses/oadg/contrastive_loss_plus.py')
 
+    # the consistency losses: losses/utils.py + oadg/{cross_entropy,smooth_l1}_loss_plus.py
+    mmcv.jit = lambda *a, **k: (lambda f: f)
+    _load('mmdet.models.losses.utils', 'mmdet/models/losses/utils.py')
+    cel = _load('mmdet.models.losses.oadg.cross_entropy_loss_plus', 'mmdet/models/losses/oadg/cross_entropy_loss_plus.py')
+    sl1 = _load('mmdet.models.losses.oadg.smooth_l1_loss_plus', 'mmdet/models/losses/oadg/smooth_l1_loss_plus.py')
+    _CACHE.update(dict(CrossEntropyLossPlus=cel.CrossEntropyLossPlus, jsdv1_3_2aug=cel.jsdv1_3_2aug,
+                       SmoothL1LossPlus=sl1.SmoothL1LossPlus, L1LossPlus=sl1.L1LossPlus,
+                       supcontrast_yolo=closs.supcontrast_yolo))
     _CACHE.update(dict(
         OAMix=oa_mix.OAMix, oa_mix=oa_mix, augmix=augmix, bbox_augmentation=bbox_aug,
         supcontrast=closs.supcontrast, supcontrast_mask=closs.supcontrast_mask,
