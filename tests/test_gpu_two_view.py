@@ -37,9 +37,10 @@ def test_jsd_kernel_matches_torch_form(n, c, scale):
 
 def test_jsd_kernel_matches_reference_golden_and_is_deterministic():
     from oadg_b200 import consistency_losses as CL
-    import tests.test_two_view as T
+    import conftest as T
+    from oadg_b200.registry import build_loss
     for kind in ('roi', 'rpn'):
-        pred, label, weight, avg = T._inputs(kind)
+        pred, label, weight, avg = T.f2_inputs(kind)
         x = pred.float().cuda().requires_grad_(True)
         j = CL.jsdv1_3_2aug(x, label.cuda(), None)
         j.backward()
@@ -48,7 +49,7 @@ def test_jsd_kernel_matches_reference_golden_and_is_deterministic():
         again = CL.jsd_two_views(x.detach())
         assert again.item() == j.item()
         # the whole module, as the head calls it
-        mod = T.build_loss(dict(T.CE_CFG[kind])).cuda()
+        mod = build_loss(dict(T.CE_CFG[kind])).cuda()
         y = pred.float().cuda().requires_grad_(True)
         loss = mod(y, label.cuda(), weight.float().cuda(), avg_factor=avg)
         loss.backward()

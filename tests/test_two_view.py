@@ -16,33 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = np.load(os.path.join(HERE, 'golden', 'consistency.npz'))
 
 
-def _inputs(kind):
-    """Same seeded tensors as scripts/make_golden_f2.py::inputs."""
-    g = torch.Generator().manual_seed({'roi': 11, 'rpn': 12, 'reg': 13}[kind])
-    if kind == 'roi':
-        n = 256
-        pred = torch.randn(n, 9, generator=g, dtype=torch.float64) * 3
-        half = torch.randint(0, 9, (n // 2,), generator=g)
-        return pred, torch.cat([half, half]), torch.ones(n, dtype=torch.float64), float(n)
-    if kind == 'rpn':
-        n = 4096
-        pred = torch.randn(n, 1, generator=g, dtype=torch.float64) * 4
-        half = torch.randint(0, 2, (n // 2,), generator=g)
-        w = (torch.rand(n // 2, generator=g) < 0.25).double()
-        return pred, torch.cat([half, half]), torch.cat([w, w]), 512.0
-    n = 512
-    pred = torch.randn(n, 4, generator=g, dtype=torch.float64)
-    tgt = torch.randn(n // 2, 4, generator=g, dtype=torch.float64)
-    w = (torch.rand(n // 2, 4, generator=g) < 0.8).double()
-    return pred, torch.cat([tgt, tgt]), torch.cat([w, w]), float(n)
-
-
-CE_CFG = {
-    'roi': dict(type='CrossEntropyLossPlus', use_sigmoid=False, loss_weight=1.0, num_views=2,
-                additional_loss='jsdv1_3_2aug', lambda_weight=10, wandb_name='roi_cls', log_pos_ratio=True),
-    'rpn': dict(type='CrossEntropyLossPlus', use_sigmoid=True, loss_weight=1.0, num_views=2,
-                additional_loss='jsdv1_3_2aug', lambda_weight=0.1, wandb_name='rpn_cls'),
-}
+from conftest import CE_CFG, f2_inputs as _inputs  # noqa: E402
 
 
 # ------------------------------------------------------------------------------------------------- f2: losses
