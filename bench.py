@@ -75,7 +75,8 @@ def workload_config(n_gpus):
     return {'workload': 'oamix(2x1024x2048x3 u8, 8 gt/img, version=augmix) + '
                         'contrastive_loss_plus fwd+bwd([2088,256] f32, T=0.06) per GPU step',
             'imgs_per_gpu': BS, 'frame': [H, W, 3], 'gt_per_img': N_GT, 'rois': [N_ROI, C_ROI],
-            'sharding': ('by image, %d rank(s); OA-Mix: no collective; OA-Loss: one all-gather of RoI embeddings'
+            'sharding': ('by image, %d rank(s); OA-Mix: no collective; OA-Loss: the RoI embeddings of all ranks are '
+                         'gathered before the contrastive loss (anchors local, contrasts global)'
                          % n_gpus) if n_gpus > 1 else 'single rank',
             'l2': 'inputs larger than L2: %d distinct source frames (%.0f MB) cycled' % (POOL, POOL * H * W * 3 / 1e6),
             'pipeline': 'OAMix.iter_batches: steps travel in groups (1, 2, then 4 steps per plan and chain launch); '
@@ -290,11 +291,12 @@ def product_arm(args):
     if gather:
         from oadg_b200.distributed import gathered_contrastive_loss, CudaBackend
         gbe = CudaBackend()
+        exchange = args.exchange
 
     def run_loss(xin):
         if gather:   # one all-gather of the RoI embeddings over NVLink before the contrastive loss
             return gathered_contrastive_loss(xin, labels_dev, temperature=LOSS_CFG['temperature'],
-                                             loss_weight=LOSS_CFG['loss_weight'], backend=gbe)
+                                             loss_weight=LOSS_CFG['loss_weight'], backend=gbe, exchange=exchange)
         return loss_fn(xin, labels_dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -392,8 +394,38 @@ def product_arm(args):
     d2h = BS * frame_bytes + 4
 
     log('e2e done')
+    # ---- N > 1, outside every timed region: all ranks report the same loss bits, and rank 0 checks them against the
+    # oracle's closed form on the concatenated batch (oracle/supcon_np.py, float64)
+    parity = None
+    if gather:
+        x_dev.grad = None
+        lg = run_loss(x_dev)
+        lg.backward()
+        mine = torch.stack([lg.detach().double(), x_dev.grad.double().norm()])
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        xs = [torch.empty_like(x_dev) for _ in range(world)]
+        dist.all_gather(xs, x_dev.detach())
+        ys = [torch.empty_like(labels_dev) for _ in range(world)]
+        dist.all_gather(ys, labels_dev)
+        if rank == 0:
+            from oadg_b200 import reference_pair_map
+            from oadg_b200.distributed import gathered_pair_map
+            from oracle import supcon_np
+            vals = [float(e[0]) for e in every]
+            assert all(v == vals[0] for v in vals), 'ranks disagree on the gathered loss: %r' % (vals,)
+            y_all = np.concatenate([supcon_np.pad_labels(y.cpu().numpy(), N_ROI) for y in ys])
+            x_all = np.concatenate([t.cpu().numpy() for t in xs])
+            ref = supcon_np.supcon_loss(x_all, y_all, LOSS_CFG['temperature'], 10, LOSS_CFG['loss_weight'],
+                                        pair=gathered_pair_map(reference_pair_map(N_ROI), world))
+            rel = abs(vals[0] - ref) / abs(ref)
+            assert rel <= 1e-5, 'gathered loss %.9g vs oracle %.9g' % (vals[0], ref)
+            parity = {'ranks_equal_bits': True, 'loss_rel_vs_oracle_on_concatenated_batch': rel,
+                      'oracle': 'oracle/supcon_np.py float64, %d rows' % (world * N_ROI)}
+            log('gathered-loss parity: rel %.2e vs the oracle on %d rows' % (rel, world * N_ROI))
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -516,8 +548,19 @@ def product_arm(args):
             'config': workload_config(world), 'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'roofline': roofline, 'oaloss': oaloss, 'cpu_baseline': cpu}
+    if gather:
+        px = getattr(gbe, '_px', None)
+        line['config']['exchange'] = (
+            'peer: the pack kernel stores the rows into every rank\'s gather buffer over NVLink and raises a flag, the '
+            'row statistics are scattered the same way; no collective kernel in the step' if exchange == 'peer' and px
+            else 'nccl: two all_gather_into_tensor per step')
+        line['comm'] = {'collectives_per_step': 0 if exchange == 'peer' and px else 2,
+                        'nvlink_bytes_out_per_rank_per_step': px.nvlink_bytes_per_step if exchange == 'peer' and px else
+                        (world - 1) * (N_ROI * (C_ROI + 4) * 4 + (N_ROI + 1) * 16)}
+        line['parity'] = parity
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -534,6 +577,8 @@ def main():
     ap.add_argument('--cores', type=int, default=0, help='worker processes of the CPU arm (0 = min(cpu_count, 64))')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-gather', action='store_true', help='N>1: keep the reference\'s per-rank local loss')
+    ap.add_argument('--exchange', default=os.environ.get('OADG_EXCHANGE', 'peer'), choices=['peer', 'nccl'],
+                    help='N>1: how the RoI rows travel (peer stores over NVLink without a collective | NCCL all-gathers)')
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything a library writes to fd 1 meanwhile (e.g. NCCL's version banner
     # under NCCL_DEBUG) goes to stderr

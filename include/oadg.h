@@ -328,12 +328,47 @@ int oadg_supcon_backward_packed(const float* feats_local_dev, const int32_t* pai
 /* ---- OA-Loss, consistency half ------------------------------------------------------------------------------
  * Jensen-Shannon divergence between the two views' class distributions (cross_entropy_loss_plus.py:264-319
  * jsdv1_3_2aug): pred_dev [2 n, c] float32 = view 1 rows then view 2 rows, c <= 32 (c == 1: the RPN's single logit,
- * classes (sigmoid, 1 - sigmoid); else softmax).  Writes loss_dev[0] = sum of the row divergences / n and
+ * classes (sigmoid, 1 - sigmoid); else softmax).  Writes loss_dev[0] = the sum of the row divergences (the
+ * reference's `/ len(p_aug1)` divides by the leading 1 of a [1, n, C] reshape) and
  * grad_dev [2 n, c] = d loss / d pred (so the backward is a scale).  scratch_dev: oadg_jsd2_scratch_bytes() bytes,
  * zeroed once by the caller. */
 int oadg_jsd2_scratch_bytes(void);
 int oadg_jsd2_forward(const float* pred_dev, int n, int c, float* loss_dev, float* grad_dev, void* scratch_dev,
                       void* stream);
+
+/* ---- OA-Loss across ranks without a collective library on the critical path (new capability) ----------
+ * Every rank owns one exportable device buffer (oadg_peer_alloc), maps the other ranks' buffers through CUDA IPC
+ * (oadg_peer_export / _import, handles exchanged once by the host) and from then on the kernels of a step store their
+ * results straight into every rank's buffer over NVLink and raise a per-source flag word there; the consumer waits on
+ * its own flags (oadg_peer_wait).  No kernel of another library has to be resident on either side.
+ *   oadg_supcon_gather_pack_peers = oadg_supcon_gather_pack whose packed rows land in EVERY rank's gather buffer
+ *                                   (peers->base[r] + rows_offset, row index rank * n_rows), followed by
+ *                                   flag word (peers->base[r] + flag_offset)[rank] = seq
+ *   oadg_peer_scatter              copies `bytes` (multiple of 16) from this rank's own buffer at `offset` to the same
+ *                                   offset of every other rank, then raises flag word [rank] at flag_offset
+ *   oadg_peer_wait                 returns (in stream order) once flags_dev[r] has reached seq for every r < world
+ *                                   (cyclic comparison); after timeout_ms it writes 1 to *fault_host (page-locked, mapped)
+ *                                   and gives up, so a dead peer surfaces as an error instead of a hang.
+ * counter_offset names a zero-initialised 32-bit word of the caller's own buffer (last-block-done ticket). */
+#define OADG_PEER_MAX 16
+typedef struct {
+  void* base[OADG_PEER_MAX]; /* base[rank] is this rank's own buffer */
+  int32_t world, rank;
+} oadg_peers_t;
+int oadg_peer_alloc(size_t bytes, void** ptr_out);
+int oadg_peer_free(void* ptr);
+int oadg_peer_export(void* ptr, unsigned char handle_out[64]);
+int oadg_peer_import(const unsigned char handle[64], void** ptr_out);
+int oadg_peer_release(void* ptr);
+int oadg_peer_fault_alloc(uint32_t** fault_host_out);
+int oadg_supcon_gather_pack_peers(const float* feats_dev, const int64_t* labels_dev, int n_labels, int n_rows,
+                                  int n_total, int c, int normalized_input, const oadg_peers_t* peers,
+                                  size_t rows_offset, size_t flag_offset, size_t counter_offset, uint32_t seq,
+                                  void* workspace_dev, size_t workspace_bytes, void* stream);
+int oadg_peer_scatter(const oadg_peers_t* peers, size_t offset, size_t bytes, size_t flag_offset,
+                      size_t counter_offset, uint32_t seq, void* stream);
+int oadg_peer_wait(const uint32_t* flags_dev, int world, uint32_t seq, uint32_t timeout_ms, uint32_t* fault_host,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libOADG.so')
 STAMP = os.path.join(HERE, '.libOADG.stamp')
-SOURCES = ['api.cu', 'saliency.cu', 'oamix.cu', 'oamix_sampler.cpp', 'oaloss.cu', 'oaloss_tc.cu', 'jsd.cu']
+SOURCES = ['api.cu', 'saliency.cu', 'oamix.cu', 'oamix_sampler.cpp', 'oaloss.cu', 'oaloss_tc.cu', 'jsd.cu', 'peer.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-shared', '-fmad=false', '-Xptxas', '-v',

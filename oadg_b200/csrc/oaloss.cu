@@ -16,6 +16,7 @@
 
 #include "oadg_common.cuh"
 #include "oaloss.h"
+#include "oadg_peer.cuh"
 
 namespace oadg {
 namespace {
@@ -454,6 +455,46 @@ normalize_pack_kernel(const float* __restrict__ x, const int64_t* __restrict__ l
     out[c + 3] = 0.f;
   }
 }
+// The same rows, stored straight into EVERY rank's gather buffer over NVLink (row index rank * n + row of the buffer at
+// rows_offset), then this rank's flag word raised everywhere: the all-gather without a collective kernel.
+__global__ void __launch_bounds__(256)
+normalize_pack_peers_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, int n_labels, int n, int c,
+                            int normalized_input, const oadg_peers_t P, size_t rows_offset, size_t flag_offset,
+                            size_t counter_offset, unsigned seq, float* __restrict__ inv1, float* __restrict__ inv2) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row < n) {
+    const float* xr = x + (size_t)row * c;
+    float s = 0.f;
+    for (int k = lane; k < c; k += 32) {
+      float v = xr[k];
+      s += v * v;
+    }
+    s = warp_sum(s);
+    float i1 = normalized_input ? 1.f / fmaxf(sqrtf(s), 1e-12f) : 1.f;
+    float s2 = 0.f;
+    for (int k = lane; k < c; k += 32) {
+      float v = xr[k] * i1;
+      s2 += v * v;
+    }
+    s2 = warp_sum(s2);
+    float i2 = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+    const size_t at = ((size_t)P.rank * n + row) * (c + kPackPad);
+    for (int k = lane; k < c; k += 32) {
+      const float v = (xr[k] * i1) * i2;
+      for (int r = 0; r < P.world; ++r) (reinterpret_cast<float*>(static_cast<char*>(P.base[r]) + rows_offset) + at)[k] = v;
+    }
+    if (lane == 0) {
+      inv1[row] = i1;
+      inv2[row] = i2;
+      const long long y = labels[row < n_labels ? row : n_labels - 1];
+      const float4 t = make_float4(__uint_as_float((unsigned)((unsigned long long)y & 0xffffffffull)),
+                                   __uint_as_float((unsigned)((unsigned long long)y >> 32)), 0.f, 0.f);
+      for (int r = 0; r < P.world; ++r)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(static_cast<char*>(P.base[r]) + rows_offset) + at + c) = t;
+    }
+  }
+  peer_signal(P, flag_offset, counter_offset, seq);
+}
 __global__ void __launch_bounds__(256)
 unpack_labels_kernel(const float* __restrict__ recv, int n_total, int c, int64_t* __restrict__ labels_all) {
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -674,6 +715,29 @@ extern "C" int oadg_supcon_gather_pack(const float* feats_dev, const int64_t* la
   if (workspace_bytes < w.bytes) return OADG_E_ARG;
   normalize_pack_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(feats_dev, labels_dev, n_labels, n_rows, c,
                                                               normalized_input, send_dev, w.inv1, w.inv2);
+  OADG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int oadg_supcon_gather_pack_peers(const float* feats_dev, const int64_t* labels_dev, int n_labels, int n_rows,
+                                             int n_total, int c, int normalized_input, const oadg_peers_t* peers,
+                                             size_t rows_offset, size_t flag_offset, size_t counter_offset, uint32_t seq,
+                                             void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_rows <= 0 || n_labels < 1 || n_labels > n_rows || !feats_dev || !labels_dev || !peers || !workspace_dev)
+    return OADG_E_ARG;
+  if (peers->world < 1 || peers->world > OADG_PEER_MAX || peers->rank < 0 || peers->rank >= peers->world ||
+      n_total != peers->world * n_rows)
+    return OADG_E_ARG;
+  for (int r = 0; r < peers->world; ++r)
+    if (!peers->base[r]) return OADG_E_ARG;
+  if (c != kC) return OADG_E_LIMIT;
+  if (((uintptr_t)workspace_dev & 255) || (rows_offset & 15) || (flag_offset & 3) || (counter_offset & 3)) return OADG_E_ARG;
+  LossWs w = carve_loss_ws(workspace_dev, n_total, c);
+  if (workspace_bytes < w.bytes) return OADG_E_ARG;
+  normalize_pack_peers_kernel<<<(n_rows + 7) / 8, 256, 0, stream>>>(feats_dev, labels_dev, n_labels, n_rows, c,
+                                                                    normalized_input, *peers, rows_offset, flag_offset,
+                                                                    counter_offset, seq, w.inv1, w.inv2);
   OADG_LAUNCH_CHECK();
   return 0;
 }

@@ -3,11 +3,12 @@
 New capability: the reference computes ``loss_cont`` per rank on its own 2048(+rp) rows.  Here every
 rank's rows are anchors against the embeddings of ALL ranks:
 
-    fhat_r  = normalize(normalize(x_r))                      local kernel
-    F_all   = all_gather(fhat_r), y_all = all_gather(y_r)    one collective over NVLink (2 MB per rank at N=2048)
-    loss_r, stats_r = forward(F_all; anchors = rows of r)    tcgen05 similarity, rectangular [N, W*N]
-    loss    = all_reduce_sum(loss_r)                         = mean over all W*N anchors
-    stats   = all_gather(stats_r)                            16 bytes per row
+    rows_r  = [normalize(normalize(x_r)) | y_r]              local kernel, packed rows of 260 floats
+    ROWS    = gather(rows_r)                                 exchange 1 over NVLink (2.2 MB per rank at N=2088)
+    tail_r  = forward(ROWS; anchors = rows of r)             tcgen05 similarity, rectangular [N, W*N]: row statistics
+                                                             (16 bytes per row) + the rank's loss part
+    TAIL    = gather(tail_r)                                 exchange 2 (33 KB per rank)
+    loss    = sum of the loss parts in rank order            = mean over all W*N anchors, same bits on every rank
     dx_r    = W * dL/dx_r,  dL/dfhat_r = (G + G^T)[rows of r, :] F_all / T
 
 Positives: foreground rows of the same class on ANY rank; background rows only with their own other view (same
@@ -15,10 +16,15 @@ rank).  With the per-row statistics of every rank at hand, (G + G^T) restricted 
 reduce-scatter of column gradients is needed.  The factor W compensates DDP's gradient averaging: every rank
 reports the same global-mean loss, and sum_r J_r^T (W dL/dx_r) / W is the true gradient.
 
-The collectives go through ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests, where the local compute is
-replaced by a numpy stand-in to exercise exactly this plumbing).
+The two exchanges run either as ``all_gather_into_tensor`` collectives (``exchange='nccl'``; gloo in the CPU tests,
+where the local compute is replaced by a numpy stand-in to exercise exactly this plumbing) or -- the default on GPUs
+-- with no collective at all (``exchange='peer'``, class PeerExchange): the pack kernel stores its rows straight into
+every rank's gather buffer over NVLink and raises a flag there, the forward's tail is scattered the same way, and each
+rank's stream waits on its own flags.  A collective kernel needs a free SM on BOTH ranks at the same moment, which the
+persistent OA-Mix kernel grants only between its launches; a one-sided store needs nothing on the receiving side.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -127,9 +133,10 @@ class CudaBackend(UnpackedBackend):
         self._c = c
         return send
 
-    def forward_packed(self, recv, pair_all, row0, n_rows, temperature, loss_weight, min_samples):
+    def forward_packed(self, recv, pair_all, row0, n_rows, temperature, loss_weight, min_samples, tail=None):
         lib = _lib.load()
-        tail = torch.empty(n_rows + 1, 4, dtype=torch.float32, device=recv.device)
+        if tail is None:
+            tail = torch.empty(n_rows + 1, 4, dtype=torch.float32, device=recv.device)
         nl = ctypes.c_int(0)
         _lib.check(lib.oadg_supcon_forward_packed(recv.data_ptr(), pair_all.data_ptr(), recv.shape[0], row0, n_rows,
                                                   self._c, float(temperature), float(loss_weight), int(min_samples),
@@ -157,6 +164,37 @@ class CudaBackend(UnpackedBackend):
                                                    ctypes.byref(nl), _lib.raw_stream(x.device)))
         self.launches += nl.value
         return gx
+
+    # ---- the same protocol with the exchanges done by the kernels themselves (PeerExchange)
+    def peer_exchange(self, group, device, n, c):
+        key = (id(group), str(device), n, c)
+        if getattr(self, '_px_key', None) != key:
+            self._px = PeerExchange(group, device, n, _lib.load().oadg_supcon_pack_width(c))
+            self._px_key = key
+        return self._px
+
+    def forward_peers(self, x, labels, pair_all, px, temperature, loss_weight, min_samples, normalized_input):
+        lib = _lib.load()
+        n, c = x.shape
+        n_total = px.world * n
+        self.ws = self._ws(n_total, c, x.device)
+        labels = labels.reshape(-1)
+        if labels.dtype != torch.int64 or labels.device != x.device or not labels.is_contiguous():
+            labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
+        seq, half = px.begin_step()
+        s = _lib.raw_stream(x.device)
+        _lib.check(lib.oadg_supcon_gather_pack_peers(x.data_ptr(), labels.data_ptr(), labels.shape[0], n, n_total, c,
+                                                     int(normalized_input), ctypes.byref(px.peers), px.off_rows[half],
+                                                     px.off_flag_rows, px.off_counter, seq, self.ws[1], self.ws[2], s))
+        px.wait(px.off_flag_rows, seq, s)
+        self.launches += 2
+        self._c = c
+        self.forward_packed(px.rows(half), pair_all, px.rank * n, n, temperature, loss_weight, min_samples,
+                            tail=px.tail_own(half))
+        px.scatter_tail(half, seq, s)
+        px.wait(px.off_flag_tail, seq, s)
+        self.launches += 2
+        return self.finish(px.tail_all(half), px.world, n)
 
     # ---- plain entry points (one rank playing several, tests)
     def normalize(self, x, n_total, normalized_input):
@@ -196,6 +234,108 @@ class CudaBackend(UnpackedBackend):
         return gx
 
 
+PEER_MAX = 16   # OADG_PEER_MAX
+
+
+class _Peers(ctypes.Structure):
+    """oadg_peers_t (include/oadg.h)."""
+    _fields_ = [('base', ctypes.c_void_p * PEER_MAX), ('world', ctypes.c_int32), ('rank', ctypes.c_int32)]
+
+
+class _Raw:
+    """A region of the exchange buffer, with the two attributes the backend's library calls read off a tensor."""
+
+    def __init__(self, ptr, shape, device):
+        self._ptr, self.shape, self.device = ptr, tuple(shape), device
+
+    def data_ptr(self):
+        return self._ptr
+
+
+class PeerExchange:
+    """The step's two exchanges as stores into peer memory (include/oadg.h, `oadg_peer_*`): each rank owns one
+    exportable buffer holding, twice (steps alternate between the halves), the gathered packed rows [W * n, width] and
+    the gathered tails [W, n + 1, 4], plus one flag word per (exchange, source rank) and a ticket word.  The buffers
+    are mapped across the ranks of the node once (CUDA IPC; the 64-byte handles travel through
+    ``all_gather_object``); from then on the pack kernel stores a rank's rows into every buffer and raises its flag,
+    the forward's tail is scattered the same way, and a rank's kernels wait on its own flags.  No collective kernel
+    runs in a step, so nothing of another library has to find a free SM next to the persistent OA-Mix kernel.
+
+    Why two halves are enough: a peer overwrites my rows half of step s at its step s + 2, after it has seen my tail of
+    step s + 1, which my stream produced after the forward of step s; my tail half of step s is overwritten by a
+    peer's forward of step s + 2, which waited for my rows of s + 2, packed after my `finish` of step s.  The backward
+    reads the workspace only."""
+
+    TIMEOUT_MS = 20000
+
+    def __init__(self, group, device, n_rows, width):
+        lib = _lib.load()
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > PEER_MAX:
+            raise ValueError('PeerExchange: at most %d ranks (one NVLink domain)' % PEER_MAX)
+        self.n, self.width = n_rows, width
+        a256 = lambda v: (v + 255) // 256 * 256
+        self.rows_bytes = a256(self.world * n_rows * width * 4)
+        self.tail_bytes = a256(self.world * (n_rows + 1) * 16)
+        self.off_rows = (0, self.rows_bytes)
+        self.off_tail = (2 * self.rows_bytes, 2 * self.rows_bytes + self.tail_bytes)
+        self.off_flag_rows = 2 * self.rows_bytes + 2 * self.tail_bytes
+        self.off_flag_tail = self.off_flag_rows + 256
+        self.off_counter = self.off_flag_tail + 256
+        self.bytes = self.off_counter + 256
+        own = ctypes.c_void_p()
+        _lib.check(lib.oadg_peer_alloc(self.bytes, ctypes.byref(own)))
+        self.own = own.value
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.oadg_peer_export(self.own, handle))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (bytes(handle), self.bytes, n_rows, width), group=group)
+        self.peers = _Peers()
+        self.peers.world, self.peers.rank = self.world, self.rank
+        for r, (h, nbytes, n_r, w_r) in enumerate(gathered):
+            if (nbytes, n_r, w_r) != (self.bytes, n_rows, width):
+                raise ValueError('PeerExchange: rank %d has %d rows of %d floats, this rank %d x %d (the gathered loss '
+                                 'needs the same number of rows on every rank)' % (r, n_r, w_r, n_rows, width))
+            if r == self.rank:
+                self.peers.base[r] = self.own
+            else:
+                p = ctypes.c_void_p()
+                _lib.check(lib.oadg_peer_import((ctypes.c_ubyte * 64).from_buffer_copy(h), ctypes.byref(p)))
+                self.peers.base[r] = p.value
+        fault = ctypes.POINTER(ctypes.c_uint32)()
+        _lib.check(lib.oadg_peer_fault_alloc(ctypes.byref(fault)))
+        self.fault = fault
+        self.seq = 0
+        self.nvlink_bytes_per_step = (self.world - 1) * (n_rows * width * 4 + (n_rows + 1) * 16)
+        dist.barrier(group=group)            # every buffer is mapped everywhere before the first store
+
+    def begin_step(self):
+        if self.fault[0]:
+            raise _lib.OADGError('gathered OA-Loss: a peer rank did not deliver its rows / statistics within %d s'
+                                 % (self.TIMEOUT_MS // 1000))
+        self.seq += 1
+        return self.seq, self.seq & 1
+
+    def rows(self, half):
+        return _Raw(self.own + self.off_rows[half], (self.world * self.n, self.width), self.device)
+
+    def tail_own(self, half):
+        return _Raw(self.own + self.off_tail[half] + self.rank * (self.n + 1) * 16, (self.n + 1, 4), self.device)
+
+    def tail_all(self, half):
+        return _Raw(self.own + self.off_tail[half], (self.world, self.n + 1, 4), self.device)
+
+    def wait(self, flag_offset, seq, stream):
+        _lib.check(_lib.load().oadg_peer_wait(self.own + flag_offset, self.world, seq, self.TIMEOUT_MS, self.fault,
+                                              stream))
+
+    def scatter_tail(self, half, seq, stream):
+        off = self.off_tail[half] + self.rank * (self.n + 1) * 16
+        _lib.check(_lib.load().oadg_peer_scatter(ctypes.byref(self.peers), off, (self.n + 1) * 16, self.off_flag_tail,
+                                                 self.off_counter, seq, stream))
+
+
 _PAIR_CACHE = {}
 
 
@@ -228,41 +368,66 @@ def _all_gather_rows(t, group):
 
 
 class _GatheredSupCon(torch.autograd.Function):
-    """Two collectives in the forward -- the packed [embeddings | labels] rows, then the packed [row statistics ;
-    loss part] tail -- none in the backward; between them only the backend's calls."""
+    """Two exchanges in the forward -- the packed [embeddings | labels] rows, then the packed [row statistics ;
+    loss part] tail -- none in the backward; between them only the backend's calls.  ``exchange='nccl'``: two
+    ``all_gather_into_tensor`` collectives; ``'peer'``: the kernels store into the peers' buffers (PeerExchange)."""
 
     @staticmethod
-    def forward(ctx, x, labels, pair_local, cfg, backend, group):
+    def forward(ctx, x, labels, pair_local, cfg, backend, group, exchange):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         n = x.shape[0]
         temperature, loss_weight, min_samples, normalized_input = cfg
         x = x.contiguous()
-        send = backend.pack(x, labels, world * n, normalized_input)
-        recv = _all_gather_rows(send, group)
         pair_all = _pair_all_on(x.device, pair_local, world)
-        tail = backend.forward_packed(recv, pair_all, rank * n, n, temperature, loss_weight, min_samples)
-        tail_all = _all_gather_rows(tail, group)
-        loss = backend.finish(tail_all, world, n)
-        ctx.save_for_backward(x, recv, pair_all, tail_all)   # recv / tail_all stay alive: the backend reads them again
-        ctx.meta = (rank * n, temperature, normalized_input, world, backend)
+        if exchange == 'peer':
+            px = backend.peer_exchange(group, x.device, n, x.shape[1])
+            loss = backend.forward_peers(x, labels, pair_all, px, temperature, loss_weight, min_samples,
+                                         normalized_input)
+            ctx.save_for_backward(x, pair_all)
+        else:
+            send = backend.pack(x, labels, world * n, normalized_input)
+            recv = _all_gather_rows(send, group)
+            tail = backend.forward_packed(recv, pair_all, rank * n, n, temperature, loss_weight, min_samples)
+            tail_all = _all_gather_rows(tail, group)
+            loss = backend.finish(tail_all, world, n)
+            ctx.save_for_backward(x, pair_all, recv, tail_all)   # stay alive: the backend reads them again
+        # the backward reads the backend's workspace, which the next forward overwrites
+        backend.fwd_seq = getattr(backend, 'fwd_seq', 0) + 1
+        ctx.meta = (rank * n, temperature, normalized_input, world, backend, backend.fwd_seq)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, _recv, pair_all, _tail_all = ctx.saved_tensors
-        row0, temperature, normalized_input, world, backend = ctx.meta
+        x, pair_all = ctx.saved_tensors[:2]
+        row0, temperature, normalized_input, world, backend, seq = ctx.meta
+        if seq != backend.fwd_seq:
+            raise RuntimeError('gathered_contrastive_loss: backward of step %d after the forward of step %d -- the '
+                               'loss keeps one step of statistics; call backward before the next forward (or use '
+                               'one backend per loss that is alive at the same time)' % (seq, backend.fwd_seq))
         g = (grad_out.to(torch.float32) * float(world)).contiguous()   # undo DDP's 1/W gradient averaging
         gx = backend.backward_packed(x, pair_all, row0, temperature, normalized_input, g)
-        return gx, None, None, None, None, None
+        return gx, None, None, None, None, None, None
+
+
+_DEFAULT_BACKEND = None
+
+
+def _default_backend():
+    """One CUDA backend per process: it owns the workspace and the mapped peer buffers."""
+    global _DEFAULT_BACKEND
+    if _DEFAULT_BACKEND is None:
+        _DEFAULT_BACKEND = CudaBackend()
+    return _DEFAULT_BACKEND
 
 
 def gathered_contrastive_loss(cont_feats, labels, temperature=0.07, loss_weight=1.0, min_samples=10,
-                              normalized_input=True, pair_local=None, backend=None, group=None):
+                              normalized_input=True, pair_local=None, backend=None, group=None, exchange=None):
     """``ContrastiveLossPlus`` semantics with the contrast set all-gathered over ``group``.
 
     cont_feats [N, 256] (N equal on every rank), labels [M, 1] or [M] with M <= N (padded with the last label like
     contrastive_loss_plus.py:44-47).  In a world of one rank it equals the local loss; without an initialised process
-    group it raises."""
+    group it raises.  ``exchange``: 'peer' (default on CUDA, env OADG_EXCHANGE) or 'nccl'; both give the same bits.
+    The loss keeps ONE step of statistics per backend: call ``backward`` before the next forward."""
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError('gathered_contrastive_loss needs an initialised torch.distributed process group '
                            '(a world of one rank is fine: the result then equals the local loss)')
@@ -272,6 +437,12 @@ def gathered_contrastive_loss(cont_feats, labels, temperature=0.07, loss_weight=
         raise ValueError('labels: between 1 and %d entries expected, got %d' % (n, labels.shape[0]))
     if pair_local is None:
         pair_local = reference_pair_map(n)
-    backend = backend or CudaBackend()
+    backend = backend or _default_backend()
+    if exchange is None:
+        exchange = os.environ.get('OADG_EXCHANGE', 'peer' if hasattr(backend, 'forward_peers') else 'nccl')
+    if exchange not in ('peer', 'nccl'):
+        raise ValueError("exchange: 'peer' (stores into the peers' buffers over NVLink) or 'nccl' (two all-gathers)")
+    if exchange == 'peer' and (not hasattr(backend, 'forward_peers') or dist.get_world_size(group) == 1):
+        exchange = 'nccl'                  # a world of one rank has nobody to store to; stand-in backends have no kernels
     return _GatheredSupCon.apply(cont_feats, labels, pair_local,
-                                 (temperature, loss_weight, min_samples, normalized_input), backend, group)
+                                 (temperature, loss_weight, min_samples, normalized_input), backend, group, exchange)

@@ -135,25 +135,47 @@ def test_gathered_entry_points_match_oracle_single_rank(cuda, tmp_path):
         dist.destroy_process_group()
 
 
-def _two_rank_worker(rank, world, port, q):
+def _two_rank_worker(rank, world, port, q, exchange):
     import os
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
-    from oadg_b200.distributed import gathered_contrastive_loss
-    x, labels = synth.make_roi_set(2048, seed=40 + rank)
-    xd = x.cuda().requires_grad_(True)
-    loss = gathered_contrastive_loss(xd, labels.cuda(), temperature=0.06, loss_weight=0.01)
-    loss.backward()
-    q.put((rank, x.numpy(), labels.numpy().reshape(-1), loss.item(), xd.grad.cpu().numpy()))
+    from oadg_b200.distributed import CudaBackend, gathered_contrastive_loss
+    be = CudaBackend()
+    out = []
+    for step in range(3):            # three steps: both halves of the exchange buffer and the first reuse of one
+        x, labels = synth.make_roi_set(2048, seed=40 + rank + 10 * step)
+        xd = x.cuda().requires_grad_(True)
+        loss = gathered_contrastive_loss(xd, labels.cuda(), temperature=0.06, loss_weight=0.01, backend=be,
+                                         exchange=exchange)
+        loss.backward()
+        out.append((x.numpy(), labels.numpy().reshape(-1), loss.item(), xd.grad.cpu().numpy()))
+    # the other exchange gives the same bits (same kernels on the same gathered rows)
+    other = CudaBackend()
+    x2 = torch.from_numpy(out[-1][0]).cuda().requires_grad_(True)
+    loss2 = gathered_contrastive_loss(x2, torch.from_numpy(out[-1][1]).cuda(), temperature=0.06, loss_weight=0.01,
+                                      backend=other, exchange='nccl' if exchange == 'peer' else 'peer')
+    loss2.backward()
+    same = loss2.item() == out[-1][2] and bool((x2.grad.cpu().numpy() == out[-1][3]).all())
+    # a backward that comes after the next forward must refuse (the statistics of its step are gone)
+    stale = gathered_contrastive_loss(x2, torch.from_numpy(out[-1][1]).cuda(), backend=be, exchange=exchange)
+    gathered_contrastive_loss(x2, torch.from_numpy(out[-1][1]).cuda(), backend=be, exchange=exchange)
+    try:
+        stale.backward()
+        refused = False
+    except RuntimeError:
+        refused = True
+    q.put((rank, out, same, refused, be.launches))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_gathered_loss_two_gpus_nccl(cuda):
-    """2 ranks over NCCL: all-gathered contrast set vs the single-process oracle on the concatenated batch."""
+@pytest.mark.parametrize('exchange', ['peer', 'nccl'])
+def test_gathered_loss_two_gpus_nccl(cuda, exchange):
+    """2 ranks: all-gathered contrast set vs the single-process oracle on the concatenated batch, with the rows
+    exchanged by peer stores over NVLink (no collective) and by NCCL all-gathers."""
     import socket
     import torch
     import torch.multiprocessing as mp
@@ -166,18 +188,23 @@ def test_gathered_loss_two_gpus_nccl(cuda):
         port = s.getsockname()[1]
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
     [p.start() for p in procs]
     res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
     [p.join(60) for p in procs]
-    x_all = np.concatenate([r[1] for r in res])
-    y_all = np.concatenate([r[2] for r in res])
     pair_all = gathered_pair_map(reference_pair_map(2048), 2)
-    ref, gref = supcon_np.supcon_loss(x_all, y_all, 0.06, 10, 0.01, want_grad=True, pair=pair_all)
-    for rank, _, _, loss, grad in res:
-        assert abs(loss - ref) <= RTOL * abs(ref)
-        want = 2 * gref[rank * 2048:(rank + 1) * 2048]
-        assert np.linalg.norm(grad - want) <= RTOL * np.linalg.norm(want)
+    for step in range(3):
+        x_all = np.concatenate([r[1][step][0] for r in res])
+        y_all = np.concatenate([r[1][step][1] for r in res])
+        ref, gref = supcon_np.supcon_loss(x_all, y_all, 0.06, 10, 0.01, want_grad=True, pair=pair_all)
+        for rank, out, same, refused, launches in res:
+            _, _, loss, grad = out[step]
+            assert abs(loss - ref) <= RTOL * abs(ref), (step, rank)
+            want = 2 * gref[rank * 2048:(rank + 1) * 2048]
+            assert np.linalg.norm(grad - want) <= RTOL * np.linalg.norm(want), (step, rank)
+    assert res[0][1][2][2] == res[1][1][2][2]            # every rank reports the same bits
+    assert all(r[2] for r in res), 'peer and nccl exchanges disagree'
+    assert all(r[3] for r in res), 'a stale backward was not refused'
 
 
 @pytest.mark.parametrize('world', [4, 8])
