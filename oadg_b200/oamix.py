@@ -198,6 +198,9 @@ class OAMix:
         # items are independent: a queue with more lanes starves less often; OA-Mix alone on 1024x2048 frames:
         # 265 / 204 / 182 us per view with 1 / 2 / 4 batches of two frames per launch)
         self.group_batches = int(os.environ.get('OADG_GROUP_BATCHES', '4'))
+        # iter_batches: a group's chain launch waits for what the consumer has enqueued (on its own stream) for the
+        # batches it was already handed, see _pipeline.launch_batches
+        self.consumer_fence = os.environ.get('OADG_CONSUMER_FENCE', '1') != '0'
         self.last_launches = 0
 
     def __repr__(self):
@@ -839,11 +842,13 @@ class OAMix:
             return res, job
 
         def release(job):
-            if job.get('device'):
+            if job.get('device') or self.consumer_fence:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
-                released[job['idx']] = ev
-                released.pop(job['idx'] - 128, None)
+                if job.get('device'):
+                    released[job['idx']] = ev
+                    released.pop(job['idx'] - 128, None)
+                released['latest'] = ev
 
         if not threaded:
             for item in self._pipeline(batches, dev, released):
@@ -1012,6 +1017,11 @@ class OAMix:
                 k += n
                 if j['device'] and (j['idx'] - n_sets) in released:   # the consumer's work on this set's last views
                     pipe.wait_event(released[j['idx'] - n_sets])
+            if self.consumer_fence and released.get('latest') is not None:
+                # the persistent chain kernel takes every SM for its whole run: let what the consumer has enqueued on
+                # the batches it already holds (its loss kernels, and in a multi-rank job the exchange they wait on)
+                # go first, so that the step alternates [chain of group k + 2] [consumer's work on group k]
+                pipe.wait_event(released['latest'])
             before = self.last_launches
             self._ws_min_views = max(self._ws_min_views, gmax * max(len(j['dimgs']) for j in jobs))
             self.execute(plan.blob, imgs, outs=douts, stream=pipe)
