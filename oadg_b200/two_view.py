@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .consistency_losses import CrossEntropyLossPlus, SmoothL1LossPlus
 from .contrastive_loss import ContrastiveLossPlus
 
 
@@ -162,7 +163,7 @@ class Shared2FCContrastiveHead(nn.Module):
     two shared FCs (1024) -> ``fc_cls`` (num_classes + 1), ``fc_reg`` (4 * num_classes), ``fc_cont``."""
 
     def __init__(self, in_channels=256, roi_feat_size=7, fc_out_channels=1024, num_classes=8, out_dim_cont=256,
-                 loss_cont=None, target_stds=(0.1, 0.1, 0.2, 0.2)):
+                 loss_cont=None, loss_cls=None, loss_bbox=None, target_stds=(0.1, 0.1, 0.2, 0.2)):
         super().__init__()
         self.num_classes = num_classes
         d = in_channels * roi_feat_size * roi_feat_size
@@ -176,6 +177,14 @@ class Shared2FCContrastiveHead(nn.Module):
         cfg.update({k: v for k, v in (loss_cont or {}).items() if k != 'type'})
         self.loss_cont = ContrastiveLossPlus(**cfg)
         self.loss_cont.num_classes = num_classes          # contrastive_head.py:58
+        # ..._oadg.py:33-38: first-view cross entropy + 10 x JSD between the views, first-view smooth L1
+        cfg = dict(use_sigmoid=False, loss_weight=1.0, num_views=2, additional_loss='jsdv1_3_2aug', lambda_weight=10,
+                   wandb_name='roi_cls')
+        cfg.update({k: v for k, v in (loss_cls or {}).items() if k != 'type'})
+        self.loss_cls = CrossEntropyLossPlus(**cfg)
+        cfg = dict(beta=1.0, loss_weight=1.0, num_views=2, additional_loss='None', lambda_weight=0.0, wandb_name='roi_bbox')
+        cfg.update({k: v for k, v in (loss_bbox or {}).items() if k != 'type'})
+        self.loss_bbox = SmoothL1LossPlus(**cfg)
         self.register_buffer('target_stds', torch.tensor(target_stds, dtype=torch.float32), persistent=False)
 
     def forward(self, x):
@@ -208,15 +217,16 @@ class Shared2FCContrastiveHead(nn.Module):
         return torch.cat(labels), torch.cat(weights), torch.cat(targets), torch.cat(tweights)
 
     def loss(self, cls_score, bbox_pred, cont_feats, labels, label_weights, bbox_targets, bbox_weights):
-        """contrastive_head.py:60-138: cross entropy + L1 on the positives + the gated contrastive term."""
+        """contrastive_head.py:60-138: CrossEntropyLossPlus over the sampled RoIs of all views, SmoothL1LossPlus on
+        the positives, and the gated contrastive term on the embeddings (which may carry extra random-proposal rows)."""
         losses = {}
-        avg = max(float((label_weights > 0).sum()), 1.0)
-        n_cls = cls_score.shape[0]                        # cont_feats may carry extra random-proposal rows
-        losses['loss_cls'] = (F.cross_entropy(cls_score, labels[:n_cls], reduction='none') * label_weights[:n_cls]).sum() / avg
+        avg = max(float((label_weights > 0).sum()), 1.0)           # :76 (a host sync in the reference as well)
+        losses['loss_cls'] = self.loss_cls(cls_score, labels, label_weights, avg_factor=avg)
         pos = (labels >= 0) & (labels < self.num_classes)
         if pos.any():
             pred = bbox_pred.view(bbox_pred.shape[0], -1, 4)[pos, labels[pos]]
-            losses['loss_bbox'] = (torch.abs(pred - bbox_targets[pos]) * bbox_weights[pos]).sum() / bbox_targets.shape[0]
+            losses['loss_bbox'] = self.loss_bbox(pred, bbox_targets[pos], bbox_weights[pos],
+                                                 avg_factor=bbox_targets.shape[0])
         else:
             losses['loss_bbox'] = bbox_pred[pos].sum()
         lab = labels.contiguous().view(-1, 1)

@@ -111,6 +111,30 @@ def test_reference_configs_load_unchanged_and_build_our_plugins():
     assert cfg.data.samples_per_gpu == 2 and cfg.custom_imports['imports'] == ['mmdet.datasets.pipelines.oa_mix']
 
 
+@pytest.mark.skipif(not os.path.isdir(REF + '/configs/OA-DG'), reason='its _base_ files only exist in the dev container')
+def test_composed_dwd_oadg_config_builds_every_plugin_of_the_step():
+    """BASELINE config 5 (configs/OA-DG/dwd/faster_rcnn_r101_dc5_1x_dwd_oadg.py, composed here: the reference has no
+    DWD OA-DG config): R101-DC5 baseline + the OA-DG losses with 7 classes + the two-view pipeline."""
+    from oadg_b200 import (Config, PIPELINES, build_from_cfg, build_loss, OAMix, ContrastiveLossPlus,
+                           CrossEntropyLossPlus, SmoothL1LossPlus, L1LossPlus)
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs/OA-DG/dwd/faster_rcnn_r101_dc5_1x_dwd_oadg.py'),
+                          base_remap={'/ws/external/': REF + '/'})
+    assert cfg.model.backbone.depth == 101 and cfg.model.roi_head.type == 'ContrastiveRoIHead'
+    head = cfg.model.roi_head.bbox_head
+    assert head.type == 'Shared2FCContrastiveHead' and head.num_classes == 7
+    built = [build_loss(head.loss_cls), build_loss(head.loss_bbox), build_loss(head.loss_cont),
+             build_loss(cfg.model.rpn_head.loss_cls), build_loss(cfg.model.rpn_head.loss_bbox)]
+    assert [type(b) for b in built] == [CrossEntropyLossPlus, SmoothL1LossPlus, ContrastiveLossPlus,
+                                        CrossEntropyLossPlus, L1LossPlus]
+    assert built[0].lambda_weight == 10 and built[3].lambda_weight == 0.1 and built[3].use_sigmoid
+    assert built[2].temperature == 0.06 and built[2].loss_weight == 0.01
+    assert cfg.model.train_cfg.random_proposal_cfg['bbox_from'] == 'oagrb'
+    t = build_from_cfg(cfg.oamix_config, PIPELINES)
+    assert isinstance(t, OAMix) and t.num_views == 2 and t.keep_orig
+    assert [s['type'] for s in cfg.train_pipeline][4:7] == ['OAMix', 'Normalize', 'Pad']
+    assert cfg.data.samples_per_gpu == 2 and cfg.optimizer.lr == 0.001          # inherited from the DWD baseline
+
+
 @pytest.mark.parametrize('case', [('augmix', 96, 160, 3, 0, 100, {}), ('augmix.all', 120, 200, 4, 1, 201, {}),
                                   ('augmix', 64, 64, 0, 2, 302, dict(mixture_width=1)),
                                   ('augmix.all', 80, 90, 2, 3, 7, dict(mixture_width=2, mixture_depth=2))])
