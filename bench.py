@@ -537,7 +537,7 @@ def product_arm(args):
     log('loss timing done')
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = min(os.cpu_count() or 1, 16)
+        cores = args.cores if args.cores > 0 else min(os.cpu_count() or 1, 64)   # the same rule as --impl reference
         n_img, t_mix, t_loss = run_cpu_baseline(1, cores)
         cpu = {'value': cpu_images_per_sec(n_img, t_mix, t_loss), 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                'sample': '%d frames (1 per worker process, cv2 1 thread each) through oracle/oamix_np.py + 1 OA-Loss '

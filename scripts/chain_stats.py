@@ -47,7 +47,7 @@ for i in range(n_launch):
     for k, (us, n, mx) in prof['kind_busy_us_and_tiles'].items():
         tot += us
         print('   kind %-16s busy %9.1f CTA-us over %6d tiles = %7.2f us/tile, longest %7.1f us' % (k, us, n, us / max(n, 1), mx))
-    print('   total %.1f CTA-us = %.1f us on 592 CTAs' % (tot, tot / 592))
+    print('   total %.1f CTA-us = %.1f us on 444 CTAs (3 per SM)' % (tot, tot / 444))
 print('%d launches x %d views: chain %.1f us/view, mix %.1f us/view; chain %.0f GB/s of lane-step bytes, '
       'chain+mix %.0f GB/s of whole-view bytes (profiled build: timers on)' % (
           n_launch, group, tot_chain / (n_launch * group), tot_mix / (n_launch * group),
