@@ -51,6 +51,7 @@ def yolo_pair_map(n):
     return pair
 
 
+MIN_TEMPERATURE = 0.025
 _PAIR_CACHE = {}
 
 
@@ -112,6 +113,10 @@ def supcontrast(logits_clean, labels=None, num_views=2, lambda_weight=0.1, tempe
     _lib.require_cuda()
     if not logits_clean.is_cuda:
         raise _lib.OADGError('supcontrast: features must live on a CUDA device (no CPU fallback)')
+    if not temper >= MIN_TEMPERATURE:
+        raise ValueError('supcontrast: temperature %r is below %g, the bound of the fixed-shift exponent of the '
+                         'tcgen05 forward (oaloss.cu kMinTemperatureTc); the reference configs use 0.06 / 0.07'
+                         % (temper, MIN_TEMPERATURE))
     n = logits_clean.shape[0]
     # the kernels read raw pointers: labels and pair must be dense, on the features' device, of the declared dtype
     labels = labels.reshape(-1).to(device=logits_clean.device, dtype=torch.int64).contiguous()

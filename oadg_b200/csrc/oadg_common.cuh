@@ -22,6 +22,14 @@ namespace oadg {
 
 constexpr int kNumSMs = 148;  // B200
 
+// index of the calling thread's current device, for per-device caches of function attributes / SM counts
+// (cudaFuncSetAttribute applies to the current device only)
+inline int device_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 63;
+}
+
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __device__ __forceinline__ float warp_sum(float v) {

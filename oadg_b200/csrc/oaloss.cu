@@ -519,6 +519,10 @@ finish_packed_kernel(const float4* __restrict__ tail_all, int world, int n_rows,
 // The product computes the similarity on the tensor cores (tcgen05, oaloss_tc.cu).  The CUDA-core FFMA kernels above
 // are kept as a TEST BUILD only (-DOADG_LOSS_FFMA, tests/test_gpu_oaloss.py builds it as a second library): an
 // independent implementation of the same closed form to cross-check the tcgen05 path; there is no runtime switch.
+// The tcgen05 forward shifts every logit by the diagonal 1 / T instead of a running row maximum (rows are unit vectors)
+// and evaluates exp with ex2.approx.ftz: below this temperature a row whose other similarities are all low could have
+// every term flushed to zero (2 / T * log2(e) > 126).  The reference's configs use 0.06 / 0.07.
+static constexpr float kMinTemperatureTc = 0.025f;
 static constexpr int loss_tc_enabled() {
 #ifdef OADG_LOSS_FFMA
   return 0;
@@ -548,6 +552,7 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
   if (!feats_dev || !labels_dev || !pair_dev || !workspace_dev) return OADG_E_ARG;
   if (c != kC) return OADG_E_LIMIT;
   if (!(temperature > 0.f)) return OADG_E_ARG;
+  if (loss_tc_enabled() && temperature < kMinTemperatureTc) return OADG_E_LIMIT;
   if (((uintptr_t)feats_dev & 15) || ((uintptr_t)workspace_dev & 255)) return OADG_E_ARG;
   LossWs w = carve_loss_ws(workspace_dev, n, c);
   if (workspace_bytes < w.bytes) return OADG_E_ARG;
@@ -608,10 +613,11 @@ extern "C" int oadg_supcon_backward(const float* feats_dev, const int64_t* label
     if (splits > col_tiles) splits = col_tiles;
     if (splits < 1) splits = 1;
     const size_t smem = (size_t)2 * kTK * (kTM + 4) * 4 + (size_t)kTM * (kTN + 1) * 4;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr_of[64] = {false};
+    const int slot = device_slot();
+    if (!attr_of[slot]) {
       OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
+      attr_of[slot] = true;
     }
     sim_bwd_kernel<<<dim3(splits, row_tiles), kBwdThreads, smem, stream>>>(w.fhat, labels_dev, pair_dev, w.meta,
                                                                            w.stats, n, c, 1.f / temperature, col_tiles,
@@ -655,6 +661,7 @@ extern "C" int oadg_supcon_forward_gathered(const float* fhat_all_dev, const int
   if (c != kC) return OADG_E_LIMIT;
   if (!(temperature > 0.f) || ((uintptr_t)fhat_all_dev & 15) || ((uintptr_t)workspace_dev & 255)) return OADG_E_ARG;
   if (!loss_tc_enabled()) return OADG_E_LIMIT;  // the cross-rank path exists for the tcgen05 kernels only
+  if (temperature < kMinTemperatureTc) return OADG_E_LIMIT;
   LossWs w = carve_loss_ws(workspace_dev, n_total, c);
   if (workspace_bytes < w.bytes) return OADG_E_ARG;
   int launches = 0;
@@ -753,6 +760,7 @@ extern "C" int oadg_supcon_forward_packed(const float* recv_dev, const int32_t* 
   if (!(temperature > 0.f) || ((uintptr_t)recv_dev & 15) || ((uintptr_t)tail_dev & 15) || ((uintptr_t)workspace_dev & 255))
     return OADG_E_ARG;
   if (!loss_tc_enabled()) return OADG_E_LIMIT;  // the cross-rank path exists for the tcgen05 kernels only
+  if (temperature < kMinTemperatureTc) return OADG_E_LIMIT;
   LossWs w = carve_loss_ws(workspace_dev, n_total, c);
   if (workspace_bytes < w.bytes) return OADG_E_ARG;
   int launches = 0;

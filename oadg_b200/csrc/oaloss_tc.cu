@@ -591,18 +591,18 @@ int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pai
   if (rc) return rc;
   rc = make_map(&ml, w.f_lo, n, 256, 256, kM);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr_of[64] = {false};   // per device: the attribute belongs to the device's context
+  static int sm_of[64] = {0};
+  const int slot = device_slot();
+  if (!attr_of[slot]) {
     OADG_CUDA_TRY(cudaFuncSetAttribute(sim_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
-    attr = true;
-  }
-  static int n_sm = 0;
-  if (!n_sm) {
     int dev = 0;
     OADG_CUDA_TRY(cudaGetDevice(&dev));
-    OADG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    OADG_CUDA_TRY(cudaDeviceGetAttribute(&sm_of[slot], cudaDevAttrMultiProcessorCount, dev));
+    attr_of[slot] = true;
   }
+  const int n_sm = sm_of[slot];
   const int col_tiles = (n + kN - 1) / kN, n_tiles = col_tiles * ((n_rows + kM - 1) / kM);
   sim_fwd_tc_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, kFwdThreads, kSmemBytes, stream>>>(
       mh, ml, labels, w.meta, n, row0, n_rows, inv_t, col_tiles, n_tiles, w.partial, w.z, w.ld);

@@ -272,11 +272,12 @@ extern "C" int oadg_saliency_scores(const uint8_t* const* imgs_dev, const int32_
   if (n_boxes == 0) return 0;
   if (!imgs_dev || !hw_dev || !boxes_dev || !scores_dev) return OADG_E_ARG;
   const size_t smem = 3 * oadg::kN * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_of[64] = {false};   // per device
+  const int slot = oadg::device_slot();
+  if (!attr_of[slot]) {
     OADG_CUDA_TRY(cudaFuncSetAttribute(oadg::saliency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    attr_set = true;
+    attr_of[slot] = true;
   }
   oadg::saliency_kernel<<<n_boxes, oadg::kThreads, smem, (cudaStream_t)stream>>>(imgs_dev, hw_dev, boxes_dev,
                                                                                    scores_dev);

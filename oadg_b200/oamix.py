@@ -562,17 +562,28 @@ class OAMix:
                 out[i][k] = np.float64(v)
         return out
 
-    def prefetch_saliency(self, imgs, gt_list):
+    def prefetch_saliency(self, imgs, gt_list, tag=None):
         """Enqueue the saliency scores of an UPCOMING batch (frames already resident on the device) so that its
         ``oamix_batch`` call finds them finished: the scores consume no random numbers and depend on nothing but
         the frames and boxes, so a loader that knows the next batch can hide the kernel and its read-back behind
-        the current step."""
+        the current step.  Returns a handle to pass as ``oamix_batch(..., saliency=handle)``.
+
+        Without a handle ``oamix_batch`` looks the request up by (frame pointers, shapes, boxes): a loader that
+        REWRITES a frame buffer in place between the prefetch and the call must pass the handle or a ``tag`` of its
+        own (e.g. the step number), otherwise the scores of the buffer's previous content would be used.  At most
+        three requests are outstanding; a fourth first completes and drops the oldest (its staging slot is reused)."""
         gt_list = [np.asarray(g, dtype=np.float32).reshape(-1, 4) for g in gt_list]
-        if len(self._sal_prefetch) >= 3:          # at most three batches in flight: drop the oldest request
-            self._sal_prefetch.pop(next(iter(self._sal_prefetch)))
-        self._sal_slot = (self._sal_slot + 1) % 3   # staging slot 0 serves un-prefetched calls, 1..3 the prefetches
-        slot = 1 + self._sal_slot
-        self._sal_prefetch[self._saliency_key(imgs, gt_list)] = self._saliency_launch(imgs, gt_list, None, True, slot=slot)
+        busy = {h['slot'] for h in self._sal_prefetch.values()}
+        free = [k for k in (1, 2, 3) if k not in busy]       # staging slot 0 serves un-prefetched calls
+        if not free:
+            oldest = self._sal_prefetch.pop(next(iter(self._sal_prefetch)))
+            self._saliency_collect(oldest)                     # its copies must be over before the slot is reused
+            free = [oldest['slot']]
+        handle = self._saliency_launch(imgs, gt_list, None, True, slot=free[0])
+        handle['slot'] = free[0]
+        key = (tag, self._saliency_key(imgs, gt_list))
+        self._sal_prefetch[key] = handle
+        return key
 
     def _workspace(self, nbytes, device, n_views=0, max_hw=(0, 0)):
         """Scratch for oadg_oamix_execute.  What a plan needs varies with its bboxes-only chains (two frames each);
@@ -662,7 +673,7 @@ class OAMix:
         self.last_launches += n.value
         return outs
 
-    def oamix_batch(self, imgs, gt_list, stream=None, profile=None, outs=None, inputs_ready=False):
+    def oamix_batch(self, imgs, gt_list, stream=None, profile=None, outs=None, inputs_ready=False, saliency=None):
         """Device fast path: one generated view per image (the ``num_views=2, keep_orig=True`` case).
 
         imgs: list of CUDA uint8 HWC tensors; gt_list: list of float32 [n,4] arrays.
@@ -673,7 +684,14 @@ class OAMix:
             if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3 and t.shape[2] == 3 and t.is_contiguous()):
                 raise TypeError('images must be contiguous CUDA uint8 HWC tensors')
         gt_list = [np.asarray(g, dtype=np.float32).reshape(-1, 4) for g in gt_list]
-        pre = self._sal_prefetch.pop(self._saliency_key(imgs, gt_list), None) if self._sal_prefetch else None
+        if saliency is not None:                      # the handle prefetch_saliency() returned
+            if saliency not in self._sal_prefetch:
+                raise KeyError('oamix_batch: unknown or already consumed saliency handle')
+            if saliency[1] != self._saliency_key(imgs, gt_list):
+                raise ValueError('oamix_batch: the saliency handle belongs to other frames / boxes')
+            pre = self._sal_prefetch.pop(saliency)
+        else:
+            pre = self._sal_prefetch.pop((None, self._saliency_key(imgs, gt_list)), None) if self._sal_prefetch else None
         if pre is not None:
             scores = self._saliency_collect(pre)      # requested earlier by prefetch_saliency()
             self.last_launches = 1

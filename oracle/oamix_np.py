@@ -4,7 +4,7 @@ ORACLE / TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 Follows reference ``mmdet/datasets/pipelines/oa_mix.py:32-313`` with the op
 library of ``augmix.py:32-212`` and ``bbox_augmentation.py:31-118,240-302``.
-Pinned: ``tests/test_oracle_pin.py`` checks this file bit-exactly against the
+Pinned: ``tests/test_oracle_golden.py`` checks this file bit-exactly against the
 unmodified reference (run under ``oracle.ref_loader``) and against the committed
 goldens in ``tests/golden/`` that were produced by the reference itself
 (``scripts/make_golden.py``).  The one un-pinned ingredient is

@@ -247,6 +247,47 @@ def test_prefetched_saliency_gives_the_same_views(cuda):
             assert torch.equal(x, y)
 
 
+def test_prefetch_handles_survive_rewritten_buffers_and_oversubscription(cuda):
+    """A frame buffer rewritten in place after the prefetch: the handle (or a tag) keeps the request apart from the
+    pointer-keyed lookup; five requests for three staging slots: the oldest is completed and dropped, the others
+    still deliver their own scores."""
+    from oadg_b200 import OAMix
+    import torch
+    t = OAMix(**dict(OAMIX_CFG, version='augmix'))
+    sets = []
+    for k in range(5):
+        imgs, gts = zip(*[synth.make_image(60 + 2 * k + j, 160, 288, 4) for j in range(2)])
+        sets.append((list(imgs), list(gts)))
+    bufs = _views(cuda, sets[0][0])                       # ONE pair of device buffers, rewritten for every batch
+    np.random.seed(9)
+    plain = []
+    for imgs, gts in sets:
+        for b, im in zip(bufs, imgs):
+            b.copy_(torch.from_numpy(im))
+        plain.append([o.clone() for o in t.oamix_batch(bufs, gts)[0]])
+    # handles: the request of batch k is made while the buffers hold batch k, consumed right after
+    np.random.seed(9)
+    for (imgs, gts), want in zip(sets, plain):
+        for b, im in zip(bufs, imgs):
+            b.copy_(torch.from_numpy(im))
+        h = t.prefetch_saliency(bufs, gts, tag=len(want))
+        got = t.oamix_batch(bufs, gts, saliency=h)[0]
+        assert all(torch.equal(x, y) for x, y in zip(got, want))
+    with pytest.raises(KeyError):
+        t.oamix_batch(bufs, sets[-1][1], saliency=h)      # consumed
+    # five outstanding requests on distinct buffers: the first one is dropped, the last three are served
+    devs = [_views(cuda, imgs) for imgs, _ in sets]
+    hs = [t.prefetch_saliency(d, g) for d, (_, g) in zip(devs, sets)]
+    assert len(t._sal_prefetch) == 3 and hs[0] not in t._sal_prefetch and hs[1] not in t._sal_prefetch
+    np.random.seed(9)
+    for k in range(5):
+        got = t.oamix_batch(devs[k], sets[k][1], saliency=hs[k] if k >= 2 else None)[0]
+        assert all(torch.equal(x, y) for x, y in zip(got, plain[k]))
+    with pytest.raises(ValueError):
+        h = t.prefetch_saliency(devs[0], sets[0][1])
+        t.oamix_batch(devs[1], sets[1][1], saliency=h)
+
+
 @pytest.mark.parametrize('threaded', [False, True])
 def test_iter_batches_equals_call_batch(cuda, threaded):
     """The pipelined loader loop (groups of batches: upload / saliency two groups ahead, kernel chain one ahead) yields

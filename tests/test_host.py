@@ -111,6 +111,53 @@ def test_reference_configs_load_unchanged_and_build_our_plugins():
     assert cfg.data.samples_per_gpu == 2 and cfg.custom_imports['imports'] == ['mmdet.datasets.pipelines.oa_mix']
 
 
+def test_mmdet_shim_steps_aside_for_a_real_mmdet(tmp_path):
+    """With another `mmdet` package further down sys.path, `import mmdet` must give THAT package even though the
+    repository root (with the shim) comes first."""
+    import subprocess
+    import sys
+    pkg = tmp_path / 'site' / 'mmdet'
+    pkg.mkdir(parents=True)
+    (pkg / '__init__.py').write_text("REAL = True\n__version__ = '2.20.0'\n")
+    (pkg / 'sub.py').write_text('X = 1\n')
+    code = ("import sys; sys.path[:0] = [%r]; sys.path.append(%r); import mmdet, mmdet.sub; "
+            "print(getattr(mmdet, 'REAL', False), mmdet.__version__, mmdet.sub.X)" % (ROOT, str(tmp_path / 'site')))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert out.stdout.split() == ['True', '2.20.0', '1'], out.stdout + out.stderr
+    # and without one, the shim serves the reference configs' dotted paths
+    code = "import sys; sys.path[:0] = [%r]; import mmdet, mmdet.datasets.pipelines.oa_mix as m; print(mmdet.__version__, m.OAMix.__name__)" % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=str(tmp_path))
+    assert out.stdout.split() == ['2.20.0+oadg_b200', 'OAMix'], out.stdout + out.stderr
+
+
+def test_register_into_a_foreign_mmdet_registry_replaces_the_stock_classes():
+    """oadg_b200.plugins against a stand-in for mmcv.utils.Registry (same register_module(name, force, module)
+    contract, reference mmdet/datasets/builder.py:28, mmdet/models/builder.py:13)."""
+    from oadg_b200 import plugins, OAMix, ContrastiveLossPlus, CrossEntropyLossPlus
+
+    class Stock:
+        pass
+
+    class MmcvLikeRegistry:
+        def __init__(self):
+            self.module_dict = {'OAMix': Stock, 'ContrastiveLossPlus': Stock, 'CrossEntropyLossPlus': Stock}
+
+        def register_module(self, name=None, force=False, module=None):
+            if name in self.module_dict and not force:
+                raise KeyError(name + ' is already registered')
+            self.module_dict[name] = module
+
+    pipes, losses = MmcvLikeRegistry(), MmcvLikeRegistry()
+    done = plugins.register_into_mmdet(pipes, losses)
+    assert sorted(done) == ['ContrastiveLossPlus', 'CrossEntropyLossPlus', 'L1LossPlus', 'OAMix', 'SmoothL1LossPlus']
+    assert pipes.module_dict['OAMix'] is OAMix and losses.module_dict['ContrastiveLossPlus'] is ContrastiveLossPlus
+    assert losses.module_dict['CrossEntropyLossPlus'] is CrossEntropyLossPlus
+    only = plugins.register_into_mmdet(MmcvLikeRegistry(), MmcvLikeRegistry(), which=['OAMix'])
+    assert only == ['OAMix']
+    # with this repository's mmdet shim on the path the registries are our own: nothing is re-registered
+    assert plugins.register_into_mmdet() == []
+
+
 @pytest.mark.skipif(not os.path.isdir(REF + '/configs/OA-DG'), reason='its _base_ files only exist in the dev container')
 def test_composed_dwd_oadg_config_builds_every_plugin_of_the_step():
     """BASELINE config 5 (configs/OA-DG/dwd/faster_rcnn_r101_dc5_1x_dwd_oadg.py, composed here: the reference has no
