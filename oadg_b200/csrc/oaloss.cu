@@ -223,7 +223,7 @@ sim_fwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels, 
       ps += __shfl_xor_sync(0xffffffffu, ps, o);
     }
     if (tx == 0 && row_ok) {
-      float* out = partial + ((size_t)blockIdx.x * n + i) * 3;
+      float* out = partial + ((size_t)i * gridDim.x + blockIdx.x) * 3;   // [row][column tile][3]
       out[0] = m;
       out[1] = s;
       out[2] = ps;
@@ -234,6 +234,11 @@ sim_fwd_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels, 
 // combine the column-tile partials, emit per-row stats and the scalar loss (single block,
 // fixed summation order => deterministic)
 constexpr int kRowReduceThreads = 256;
+// one warp per row, rows strided over at most 1024 blocks (`red` holds one partial sum per block)
+inline int row_reduce_blocks(int n) {
+  const int b = (n + kRowReduceThreads / 32 - 1) / (kRowReduceThreads / 32);
+  return b < 1 ? 1 : (b > 1024 ? 1024 : b);
+}
 __global__ void __launch_bounds__(kRowReduceThreads)
 row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ npos, int* __restrict__ meta,
                   int n, int row0, int n_total, int col_tiles, float loss_weight, RowStats* __restrict__ stats,
@@ -241,50 +246,68 @@ row_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ n
                   const int64_t* __restrict__ labels, const int32_t* __restrict__ pair) {
   // rows [row0, row0 + n) of an n_total-row problem (single GPU: row0 = 0, n = n_total); partial / stats are
   // indexed by the local row, npos by the global row; the loss is this range's share of the mean over n_total.
-  // One row per thread; the block sums go to `red` and the block that takes the last ticket adds them in block
-  // order (deterministic).
   __shared__ double sred[kRowReduceThreads / 32];
-  const int tid = threadIdx.x, i = blockIdx.x * kRowReduceThreads + tid;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarps = kRowReduceThreads / 32;
   if (!meta[2]) {
-    if (i < n) stats[i] = RowStats{0.f, 0.f, 0.f, 0.f};
-    if (i == 0) *loss = 0.f;
+    for (int i = blockIdx.x * kRowReduceThreads + tid; i < n; i += gridDim.x * kRowReduceThreads)
+      stats[i] = RowStats{0.f, 0.f, 0.f, 0.f};
+    if (blockIdx.x == 0 && tid == 0) *loss = 0.f;
     return;
   }
+  // one warp per row (lanes stride over the column-tile partials), rows strided over the grid; every sum has a
+  // fixed order: lanes, then warps, then blocks
   double local = 0.0;
-  if (i < n) {
+  for (int i = blockIdx.x * kWarps + warp; i < n; i += gridDim.x * kWarps) {
     float M = -INFINITY;
-    for (int t = 0; t < col_tiles; ++t) M = fmaxf(M, partial[((size_t)t * n + i) * 3]);
+    const float* prow = partial + (size_t)i * col_tiles * 3;   // [row][column tile][3]: contiguous per row
+    for (int t = lane; t < col_tiles; t += 32) M = fmaxf(M, prow[t * 3]);
+    M = warp_max(M);
     float S = 0.f, Ps = 0.f;
-    for (int t = 0; t < col_tiles; ++t) {
-      const float* p = partial + ((size_t)t * n + i) * 3;
+    for (int t = lane; t < col_tiles; t += 32) {
+      const float* p = prow + t * 3;
       S += p[1] * expf(p[0] - M);
       Ps += p[2];
     }
-    const float lse = M + logf(S);
-    const float np = npos[row0 + i];
-    // tcgen05 forward: a background row's only positive is its other view (contrastive_loss.py:216-221); the
-    // similarity kernel leaves it out and the stored logit is read here (np > 0 <=> the pair is a valid bg row)
-    if (z && np > 0.f && labels[row0 + i] == (int64_t)meta[0]) Ps = z[(size_t)i * ld + pair[row0 + i]];
-    RowStats st;
-    st.lse = lse;
-    st.npos = np;
-    st.coef = np > 0.f ? -(loss_weight / (float)n_total) / np : 0.f;
-    st.u = st.coef * np * expf(-lse);
-    stats[i] = st;
-    if (np > 0.f) local = (double)(Ps / np - lse);
+    S = warp_sum(S);
+    Ps = warp_sum(Ps);
+    if (lane == 0) {
+      const float lse = M + logf(S);
+      const float np = npos[row0 + i];
+      // tcgen05 forward: a background row's only positive is its other view (contrastive_loss.py:216-221); the
+      // similarity kernel leaves it out and the stored logit is read here (np > 0 <=> the pair is a valid bg row)
+      if (z && np > 0.f && labels[row0 + i] == (int64_t)meta[0]) Ps = z[(size_t)i * ld + pair[row0 + i]];
+      RowStats st;
+      st.lse = lse;
+      st.npos = np;
+      st.coef = np > 0.f ? -(loss_weight / (float)n_total) / np : 0.f;
+      st.u = st.coef * np * expf(-lse);
+      stats[i] = st;
+      if (np > 0.f) local += (double)(Ps / np - lse);
+    }
   }
-  local = warp_sum(local);
-  if ((tid & 31) == 0) sred[tid >> 5] = local;
+  __shared__ int last_s;
+  if (lane == 0) sred[warp] = local;
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;
-    for (int w = 0; w < kRowReduceThreads / 32; ++w) t += sred[w];
+    for (int w = 0; w < kWarps; ++w) t += sred[w];
     red[blockIdx.x] = t;
     __threadfence();
-    if (atomicAdd(&meta[4], 1) == (int)gridDim.x - 1) {   // the last block: every partial sum is visible
-      __threadfence();
+    last_s = atomicAdd(&meta[4], 1) == (int)gridDim.x - 1;   // the last block: every partial sum is visible
+  }
+  __syncthreads();
+  if (last_s) {   // block partials added in a fixed order by the whole block: thread, then lanes, then warps
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b2 = tid; b2 < gridDim.x; b2 += kRowReduceThreads) t += *((volatile double*)red + b2);
+    t = warp_sum(t);
+    __syncthreads();
+    if (lane == 0) sred[warp] = t;
+    __syncthreads();
+    if (tid == 0) {
       double tot = 0.0;
-      for (unsigned b2 = 0; b2 < gridDim.x; ++b2) tot += *((volatile double*)red + b2);
+      for (int w = 0; w < kWarps; ++w) tot += sred[w];
       *loss = (float)(-(double)loss_weight * tot / (double)n_total);
       meta[4] = 0;
     }
@@ -566,15 +589,14 @@ extern "C" int oadg_supcon_forward(const float* feats_dev, const int64_t* labels
   if (loss_tc_enabled()) {
     int rc = launch_sim_fwd_tc(w, labels_dev, pair_dev, n, 0, n, 1.f / temperature, stream, &launches);
     if (rc) return rc;
-    red_tiles = (n + 127) / 128;
+    red_tiles = 2 * ((n + 127) / 128);   // the tcgen05 forward writes one partial per 64-column half tile
   } else {
     sim_fwd_kernel<<<dim3(col_tiles, row_tiles), 256, 0, stream>>>(w.fhat, labels_dev, pair_dev, w.meta, n, c,
                                                                    1.f / temperature, w.partial);
     OADG_LAUNCH_CHECK();
     ++launches;
   }
-  if ((n + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
-  row_reduce_kernel<<<(n + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
+  row_reduce_kernel<<<row_reduce_blocks(n), kRowReduceThreads, 0, stream>>>(
       w.partial, w.npos, w.meta, n, 0, n, red_tiles, loss_weight, w.stats, w.red, loss_dev,
       loss_tc_enabled() ? w.z : nullptr, w.ld, labels_dev, pair_dev);
   OADG_LAUNCH_CHECK();
@@ -670,9 +692,8 @@ extern "C" int oadg_supcon_forward_gathered(const float* fhat_all_dev, const int
   OADG_LAUNCH_CHECK();
   int rc = launch_sim_fwd_tc(w, labels_all_dev, pair_all_dev, n_total, row0, n_rows, 1.f / temperature, stream, &launches);
   if (rc) return rc;
-  if ((n_rows + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
-  row_reduce_kernel<<<(n_rows + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
-      w.partial, w.npos, w.meta, n_rows, row0, n_total, (n_total + 127) / 128, loss_weight,
+  row_reduce_kernel<<<row_reduce_blocks(n_rows), kRowReduceThreads, 0, stream>>>(
+      w.partial, w.npos, w.meta, n_rows, row0, n_total, 2 * ((n_total + 127) / 128), loss_weight,
       reinterpret_cast<RowStats*>(stats_local_dev), w.red, loss_part_dev, w.z, w.ld, labels_all_dev, pair_all_dev);
   OADG_LAUNCH_CHECK();
   launches += 2;
@@ -772,9 +793,8 @@ extern "C" int oadg_supcon_forward_packed(const float* recv_dev, const int32_t* 
   OADG_LAUNCH_CHECK();
   int rc = launch_sim_fwd_tc(w, w.labels_all, pair_all_dev, n_total, row0, n_rows, 1.f / temperature, stream, &launches);
   if (rc) return rc;
-  if ((n_rows + kRowReduceThreads - 1) / kRowReduceThreads > 1024) return OADG_E_LIMIT;
-  row_reduce_kernel<<<(n_rows + kRowReduceThreads - 1) / kRowReduceThreads, kRowReduceThreads, 0, stream>>>(
-      w.partial, w.npos, w.meta, n_rows, row0, n_total, (n_total + 127) / 128, loss_weight,
+  row_reduce_kernel<<<row_reduce_blocks(n_rows), kRowReduceThreads, 0, stream>>>(
+      w.partial, w.npos, w.meta, n_rows, row0, n_total, 2 * ((n_total + 127) / 128), loss_weight,
       reinterpret_cast<RowStats*>(tail_dev), w.red, tail_dev + (size_t)n_rows * 4, w.z, w.ld, w.labels_all, pair_all_dev);
   OADG_LAUNCH_CHECK();
   launches += 3;

@@ -45,7 +45,8 @@ inline LossWs carve_loss_ws(void* base, int n, int c) {
     o = align_up(o + b, 256);
     return at;
   };
-  const int col_tiles = (n + 63) / 64;
+  // partial row statistics: one per 64-column tile (FFMA test build) or per half of a 128-column tile (tcgen05)
+  const int col_tiles = (n + 63) / 64 > 2 * ((n + 127) / 128) ? (n + 63) / 64 : 2 * ((n + 127) / 128);
   size_t o_f = take((size_t)n * c * 4), o_i1 = take((size_t)n * 4), o_i2 = take((size_t)n * 4);
   size_t o_st = take((size_t)n * sizeof(RowStats)), o_meta = take(64), o_np = take((size_t)n * 4);
   size_t o_pa = take((size_t)col_tiles * n * 3 * 4), o_df = take((size_t)n * c * 4);

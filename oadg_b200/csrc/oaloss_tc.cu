@@ -14,6 +14,7 @@
 // warp-specialised (TMA producer warp, MMA warp with two TMEM accumulators, four epilogue warps), see the comment
 // above sim_fwd_tc_kernel; the backward (sim_bwd_tc_kernel) builds its A operand from the stored logits.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "oadg_common.cuh"
@@ -93,11 +94,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// split the normalised embeddings into the two TF32 operands, row-major [n, 256] for the forward and
-// transposed [256, ld] for the backward GEMM (32 x 32 tiles through shared memory)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// split the normalised embeddings into the operands of the two similarity kernels:
+//   forward   row-major [n, 256] fp16 pair  h = fp16(f),  l = fp16((f - h) * 2^11)   (sim_fwd_f16_kernel)
+//   backward  transposed [256, ld] TF32 pair (B operand of the backward GEMM; 32 x 32 tiles through shared memory)
+constexpr float kLoScale = 2048.f;   // 2^11: keeps the fp16 remainder out of the subnormal range
 __global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ f, int f_ld, int n, int ld, float* __restrict__ hi, float* __restrict__ lo,
-                  float* __restrict__ thi, float* __restrict__ tlo) {
+split_operands_kernel(const float* __restrict__ f, int f_ld, int n, int ld, __half* __restrict__ h16,
+                      __half* __restrict__ l16, float* __restrict__ thi, float* __restrict__ tlo) {
   __shared__ float sh[32][33], sl[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -113,8 +129,9 @@ split_tf32_kernel(const float* __restrict__ f, int f_ld, int n, int ld, float* _
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
       h = __uint_as_float(hb);
       l = __uint_as_float(lb);
-      hi[(size_t)r * 256 + c0 + tx] = h;
-      lo[(size_t)r * 256 + c0 + tx] = l;
+      const __half vh = __float2half_rn(v);
+      h16[(size_t)r * 256 + c0 + tx] = vh;
+      l16[(size_t)r * 256 + c0 + tx] = __float2half_rn(__fmul_rn(__fsub_rn(v, __half2float(vh)), kLoScale));
     }
     sh[ty + k * 8][tx] = h;
     sl[ty + k * 8][tx] = l;
@@ -130,19 +147,46 @@ split_tf32_kernel(const float* __restrict__ f, int f_ld, int n, int ld, float* _
   }
 }
 
-// ---- forward: persistent, warp-specialised, two TMEM accumulators ------------------------------------
-//   warp 0     TMA producer (lane 0), runs up to kStages chunks ahead across tile boundaries
-//   warp 1     TMEM owner + MMA issuer (lane 0): tile t accumulates into TMEM columns (t & 1) * 128, so the
-//              contraction of tile t + 1 overlaps the epilogue of tile t
-//   warps 2-5  epilogue: warp w reads TMEM lane quadrant w % 4 (a hardware rule), one tile row per thread
+// ---- forward: persistent, warp-specialised, A-stationary, two TMEM accumulator pairs ----------------------------
+//   warp 0     TMA producer (lane 0): the CTA's 128-row A panel (fp16 h and l, all of K = 256: 128 KB) is loaded ONCE
+//              per run of tiles that share a row tile; the column tiles stream through a 3-stage ring of B chunks
+//              (64 channels of h and l, 32 KB), running ahead across tile boundaries
+//   warp 1     TMEM owner + MMA issuer (lane 0): tile t accumulates h.h^T into TMEM columns (t & 1) * 256 and the
+//              cross terms h.l^T + l.h^T into the 128 columns after them, so the contraction of tile t + 1 overlaps
+//              the epilogue of tile t
+//   warps 2-9  epilogue: warp w reads TMEM lane quadrant w % 4 (a hardware rule); the two warps of a quadrant take
+//              one half (64 columns) of the tile each, one tile row per thread; dot = main + cross * 2^-11.  Each half
+//              writes its own partial row statistics (the row reduce combines 64-column partials)
+// A CTA owns a CONTIGUOUS range of tiles in row-major order, so its A panel changes once or twice per launch.
+// Per tile the tensor pipe does 48 kind::f16 MMAs (M = N = 128, K = 16) and shared memory takes 128 KB of B: a
+// quarter of the operand bytes and half the MMA time of the 3xTF32 tiles this kernel replaces.
 // The row maximum of the reference (contrastive_loss.py:159 `logits_max`) is the diagonal z_ii = |f_i|^2 / T and
 // rows are unit vectors, so every tile shifts by the same constant 1/T: exp(z - 1/T) = 2^(c1 * (dot - 1)),
 // one FFMA + one ex2 per logit and no running maximum.  Tiles that touch the diagonal or the ragged last
 // column tile take the general (per-element predicated) epilogue; all others the fast one.
 // Positives of background rows (a single column, pair[i]) are picked up from the stored logits by the
 // row reduce; here background rows contribute no positive sum.
-constexpr int kFwdThreads = 192;
-constexpr int kFwdTmemCols = 256;
+constexpr int kFwdThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kFwdTmemCols = 512;
+constexpr int kKH = 64;                                  // fp16 channels per chunk: 128 B per row
+constexpr int kHChunks = 256 / kKH;                      // 4
+constexpr int kAPanelBytes = 2 * kHChunks * kOperandBytes;   // h and l of all chunks: 128 KB
+constexpr int kBStageF16 = 2 * kOperandBytes;            // h and l of one chunk: 32 KB
+constexpr int kFwdStages = 3;
+constexpr int kFwdSmemBytes = kAPanelBytes + kFwdStages * kBStageF16 + 1024;
+// kind::f16 (A, B fp16), fp32 accumulate, A and B K-major, M=128, N=128
+constexpr uint32_t kIdescH = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(a), "l"(b), "r"(kIdescH), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -152,13 +196,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 template <bool kGeneral>
 __device__ __forceinline__ void fwd_epilogue_tile(uint32_t tacc, int i, int j0, int n, float inv_t, float c1,
-                                                  long long yi, bool fg_row, const long long* ycol, float* zrow,
-                                                  int ld, float& s_out, float& pa_out) {
+                                                  int yi, bool fg_row, const int* ycol, float* zrow,
+                                                  int ld, int cbeg, float& s_out, float& pa_out) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, pa0 = 0.f, pa1 = 0.f;
 #pragma unroll 1
-  for (int c0 = 0; c0 < kN; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(tacc + (uint32_t)c0, r);
+  for (int c0 = cbeg; c0 < cbeg + kN / 2; c0 += 32) {
+    uint32_t r[32], x[32];
+    tmem_ld32_issue(tacc + (uint32_t)c0, r);
+    tmem_ld32_issue(tacc + (uint32_t)(kN + c0), x);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 32; ++q)   // dot = h.h + (h.l + l.h) / 2^11
+      r[q] = __float_as_uint(fmaf(__uint_as_float(x[q]), 1.f / kLoScale, __uint_as_float(r[q])));
     if (zrow && j0 + c0 < ld) {  // keep the logits for the backward (128 B per thread)
       float4* zp = reinterpret_cast<float4*>(zrow + c0);
 #pragma unroll
@@ -170,7 +219,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(uint32_t tacc, int i, int j0, 
     for (int q = 0; q < 32; q += 2) {
       const float a0 = __uint_as_float(r[q]), a1 = __uint_as_float(r[q + 1]);
       const float e0 = ex2_approx(fmaf(a0, c1, -c1)), e1 = ex2_approx(fmaf(a1, c1, -c1));
-      const longlong2 y2 = *reinterpret_cast<const longlong2*>(ycol + c0 + q);
+      const int2 y2 = *reinterpret_cast<const int2*>(ycol + c0 + q);
       bool v0 = true, v1 = true;
       if (kGeneral) {
         const int j = j0 + c0 + q;
@@ -193,32 +242,38 @@ __device__ __forceinline__ void fwd_epilogue_tile(uint32_t tacc, int i, int j0, 
 }
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
-sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                  const int64_t* __restrict__ labels, const int* __restrict__ meta, int n, int row0, int n_rows,
-                  float inv_t, int col_tiles, int n_tiles, float* __restrict__ partial, float* __restrict__ zout,
-                  int ld) {
+sim_fwd_f16_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_l,
+                   const int64_t* __restrict__ labels, const int* __restrict__ meta, int n, int row0, int n_rows,
+                   float inv_t, int col_tiles, int n_tiles, float* __restrict__ partial, float* __restrict__ zout,
+                   int ld) {
   if (!meta[2]) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
+  uint8_t* smem_b = smem + kAPanelBytes;
+  __shared__ __align__(8) uint64_t full_bar[kFwdStages], empty_bar[kFwdStages], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t afull_bar, afree_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) long long ycol[2][kN];
+  __shared__ __align__(16) int ycol[2][kN];   // class ids fit 32 bits
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int kChunks = 256 / kKC;
+  // this CTA's contiguous range of tiles (row-major: consecutive tiles share the row tile)
+  const int t_begin = (int)(((long long)blockIdx.x * n_tiles) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * n_tiles) / gridDim.x);
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kFwdStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp
+      mbar_init(&tempty_bar[a], kEpiThreads / 32);   // one arrival per epilogue warp
     }
+    mbar_init(&afull_bar, 1);
+    mbar_init(&afree_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_h) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_l) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -233,18 +288,27 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer
-      int g = 0;   // chunks issued so far: stage = g % kStages
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int i0 = row0 + (t / col_tiles) * kM, j0 = (t % col_tiles) * kN;
-        for (int kc = 0; kc < kChunks; ++kc, ++g) {
-          const int s = g % kStages;
-          if (g >= kStages) mbar_wait(&empty_bar[s], ((g / kStages) - 1) & 1);
-          uint8_t* st = smem + s * kStageBytes;
-          mbar_expect_tx(&full_bar[s], kStageBytes);
-          tma_load_2d(st, &tm_hi, &full_bar[s], kc * kKC, i0);
-          tma_load_2d(st + kOperandBytes, &tm_lo, &full_bar[s], kc * kKC, i0);
-          tma_load_2d(st + 2 * kOperandBytes, &tm_hi, &full_bar[s], kc * kKC, j0);
-          tma_load_2d(st + 3 * kOperandBytes, &tm_lo, &full_bar[s], kc * kKC, j0);
+      int g = 0, runs = 0, cur = -1;   // B chunks issued so far (stage = g % kFwdStages); A panels loaded so far
+      for (int t = t_begin; t < t_end; ++t) {
+        const int rt = t / col_tiles;
+        const int i0 = row0 + rt * kM, j0 = (t % col_tiles) * kN;
+        if (rt != cur) {
+          if (runs > 0) mbar_wait(&afree_bar, (runs - 1) & 1);   // the MMAs of the previous run have read the panel
+          mbar_expect_tx(&afull_bar, kAPanelBytes);
+          for (int kc = 0; kc < kHChunks; ++kc) {
+            tma_load_2d(smem + (2 * kc) * kOperandBytes, &tm_h, &afull_bar, kc * kKH, i0);
+            tma_load_2d(smem + (2 * kc + 1) * kOperandBytes, &tm_l, &afull_bar, kc * kKH, i0);
+          }
+          cur = rt;
+          ++runs;
+        }
+        for (int kc = 0; kc < kHChunks; ++kc, ++g) {
+          const int s = g % kFwdStages;
+          if (g >= kFwdStages) mbar_wait(&empty_bar[s], ((g / kFwdStages) - 1) & 1);
+          uint8_t* st = smem_b + s * kBStageF16;
+          mbar_expect_tx(&full_bar[s], kBStageF16);
+          tma_load_2d(st, &tm_h, &full_bar[s], kc * kKH, j0);
+          tma_load_2d(st + kOperandBytes, &tm_l, &full_bar[s], kc * kKH, j0);
         }
       }
     }
@@ -252,62 +316,72 @@ sim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ---- MMA issuer
-      int g = 0, it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      int g = 0, it = 0, runs = 0, cur = -1;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int rt = t / col_tiles;
+        if (rt != cur) {
+          mbar_wait(&afull_bar, runs & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          cur = rt;
+          ++runs;
+        }
         const int acc = it & 1;
-        if (it >= 2) {   // the epilogue must have drained this accumulator (tile it - 2)
+        if (it >= 2) {   // the epilogue must have drained this accumulator pair (tile it - 2)
           mbar_wait(&tempty_bar[acc], ((it >> 1) - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const uint32_t tacc = tmem_base + (uint32_t)(acc * kN);
-        for (int kc = 0; kc < kChunks; ++kc, ++g) {
-          const int s = g % kStages;
-          mbar_wait(&full_bar[s], (g / kStages) & 1);
+        const uint32_t tmain = tmem_base + (uint32_t)(acc * 2 * kN), tcross = tmain + (uint32_t)kN;
+        for (int kc = 0; kc < kHChunks; ++kc, ++g) {
+          const int s = g % kFwdStages;
+          mbar_wait(&full_bar[s], (g / kFwdStages) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t base = smem_u32(smem + s * kStageBytes);
-          const uint64_t ah = umma_desc(base), al = umma_desc(base + kOperandBytes);
-          const uint64_t bh = umma_desc(base + 2 * kOperandBytes), bl = umma_desc(base + 3 * kOperandBytes);
+          const uint32_t abase = smem_u32(smem + (2 * kc) * kOperandBytes), bbase = smem_u32(smem_b + s * kBStageF16);
+          const uint64_t ah = umma_desc(abase), al = umma_desc(abase + kOperandBytes);
+          const uint64_t bh = umma_desc(bbase), bl = umma_desc(bbase + kOperandBytes);
 #pragma unroll
-          for (int k = 0; k < kKC / 8; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 floats = 32 B along the swizzled row
-            umma_tf32(tacc, ah + adv, bh + adv, (kc | k) ? 1u : 0u);
-            umma_tf32(tacc, ah + adv, bl + adv, 1u);
-            umma_tf32(tacc, al + adv, bh + adv, 1u);
+          for (int k = 0; k < kKH / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 halves = 32 B along the swizzled row
+            umma_f16(tmain, ah + adv, bh + adv, (kc | k) ? 1u : 0u);
+            umma_f16(tcross, ah + adv, bl + adv, (kc | k) ? 1u : 0u);
+            umma_f16(tcross, al + adv, bh + adv, 1u);
           }
           umma_commit(&empty_bar[s]);  // frees the stage when these MMAs have read it
         }
         umma_commit(&tfull_bar[acc]);
+        if (t + 1 >= t_end || (t + 1) / col_tiles != rt) umma_commit(&afree_bar);   // last tile of this A panel
       }
     }
     __syncwarp();
   } else {
-    // ---- epilogue: thread (quadrant, lane) owns tile row quadrant * 32 + lane
-    const int quad = warp & 3, et = tid - 64;   // et: 0..127, loads one column label per tile
-    const long long bg = (long long)meta[0];
+    // ---- epilogue: thread (quadrant, lane, half) owns tile row quadrant * 32 + lane, columns half * 64 .. + 63
+    const int quad = warp & 3, half = (warp - 2) >> 2, et = tid - 64;   // et: 0..255; the first 128 load a column label
+    const int bg = meta[0];
     const float c1 = inv_t * 1.4426950408889634f;
     int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int t = t_begin; t < t_end; ++t, ++it) {
       const int acc = it & 1, bx = t % col_tiles;
       const int i0 = row0 + (t / col_tiles) * kM, j0 = bx * kN;
       const int i = i0 + quad * 32 + lane;
       const bool row_ok = i < row0 + n_rows;
-      const long long yi = row_ok ? labels[i] : 0;
-      ycol[acc][et] = (j0 + et) < n ? labels[j0 + et] : 0;
+      const int yi = row_ok ? (int)labels[i] : 0;
+      if (et < kN) ycol[acc][et] = (j0 + et) < n ? (int)labels[j0 + et] : 0;
       // ycol[acc] was last read for tile it - 2; every epilogue warp has passed the barrier of tile it - 1 since
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kN);
+      const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 2 * kN);
       float* zrow = row_ok ? zout + (size_t)(i - row0) * ld + j0 : nullptr;
       const bool general = (j0 + kN > n) || (i0 < j0 + kN && j0 < i0 + kM);
       float s, pa;
-      if (general) fwd_epilogue_tile<true>(tacc, i, j0, n, inv_t, c1, yi, row_ok && yi != bg, ycol[acc], zrow, ld, s, pa);
-      else fwd_epilogue_tile<false>(tacc, i, j0, n, inv_t, c1, yi, row_ok && yi != bg, ycol[acc], zrow, ld, s, pa);
+      if (general)
+        fwd_epilogue_tile<true>(tacc, i, j0, n, inv_t, c1, yi, row_ok && yi != bg, ycol[acc], zrow, ld, half * (kN / 2), s, pa);
+      else
+        fwd_epilogue_tile<false>(tacc, i, j0, n, inv_t, c1, yi, row_ok && yi != bg, ycol[acc], zrow, ld, half * (kN / 2), s, pa);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (row_ok) {
-        float* out = partial + ((size_t)bx * n_rows + (i - row0)) * 3;
+      if (row_ok) {   // partial statistics per 64-column half tile
+        float* out = partial + ((size_t)(i - row0) * (2 * col_tiles) + (2 * bx + half)) * 3;   // [row][half tile][3]
         out[0] = inv_t;          // the common shift
         out[1] = s;
         out[2] = pa * inv_t;
@@ -379,6 +453,45 @@ inline int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
   c.cols = cols;
   c.ld = ld_elems;
   c.box_rows = box_rows;
+  c.map = *map;
+  return 0;
+}
+
+// 2-D fp16 tensor [rows, 256], dense; box = 64 halves (128 B) x 128 rows; 128-byte swizzle; rows beyond the tensor read
+// as zero
+inline int make_map_f16(CUtensorMap* map, const __half* base, int rows) {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(0);
+    bound = true;
+  }
+  struct Cached {
+    const __half* base;
+    int rows;
+    CUtensorMap map;
+  };
+  static thread_local Cached cache[8];
+  static thread_local int n_cached = 0, victim = 0;
+  for (int k = 0; k < n_cached; ++k)
+    if (cache[k].base == base && cache[k].rows == rows) {
+      *map = cache[k].map;
+      return 0;
+    }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {256 * sizeof(__half)};
+  cuuint32_t box[2] = {kKH, kM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && getenv("OADG_DEBUG"))
+    fprintf(stderr, "[oadg] cuTensorMapEncodeTiled (fp16) failed: %d (base %p rows %d)\n", (int)r, (const void*)base, rows);
+  if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  Cached& c = cache[n_cached < 8 ? n_cached++ : (victim = (victim + 1) & 7)];
+  c.base = base;
+  c.rows = rows;
   c.map = *map;
   return 0;
 }
@@ -584,18 +697,21 @@ sim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
 int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pair, int n, int row0, int n_rows,
                       float inv_t, cudaStream_t stream, int* launches) {
   using namespace tc;
-  split_tf32_kernel<<<dim3((w.ld + 31) / 32, 8), 256, 0, stream>>>(w.fhat, w.fhat_ld, n, w.ld, w.f_hi, w.f_lo, w.ft_hi, w.ft_lo);
+  // the row-major operand buffers of the workspace hold the forward's fp16 pair (half of each is used)
+  __half* h16 = reinterpret_cast<__half*>(w.f_hi);
+  __half* l16 = reinterpret_cast<__half*>(w.f_lo);
+  split_operands_kernel<<<dim3((w.ld + 31) / 32, 8), 256, 0, stream>>>(w.fhat, w.fhat_ld, n, w.ld, h16, l16, w.ft_hi, w.ft_lo);
   OADG_LAUNCH_CHECK();
   CUtensorMap mh, ml;
-  int rc = make_map(&mh, w.f_hi, n, 256, 256, kM);
+  int rc = make_map_f16(&mh, h16, n);
   if (rc) return rc;
-  rc = make_map(&ml, w.f_lo, n, 256, 256, kM);
+  rc = make_map_f16(&ml, l16, n);
   if (rc) return rc;
   static bool attr_of[64] = {false};   // per device: the attribute belongs to the device's context
   static int sm_of[64] = {0};
   const int slot = device_slot();
   if (!attr_of[slot]) {
-    OADG_CUDA_TRY(cudaFuncSetAttribute(sim_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OADG_CUDA_TRY(cudaFuncSetAttribute(sim_fwd_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
     OADG_CUDA_TRY(cudaFuncSetAttribute(sim_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     int dev = 0;
     OADG_CUDA_TRY(cudaGetDevice(&dev));
@@ -604,7 +720,7 @@ int launch_sim_fwd_tc(const LossWs& w, const int64_t* labels, const int32_t* pai
   }
   const int n_sm = sm_of[slot];
   const int col_tiles = (n + kN - 1) / kN, n_tiles = col_tiles * ((n_rows + kM - 1) / kM);
-  sim_fwd_tc_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, kFwdThreads, kSmemBytes, stream>>>(
+  sim_fwd_f16_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, kFwdThreads, kFwdSmemBytes, stream>>>(
       mh, ml, labels, w.meta, n, row0, n_rows, inv_t, col_tiles, n_tiles, w.partial, w.z, w.ld);
   OADG_LAUNCH_CHECK();
   if (launches) *launches += 2;

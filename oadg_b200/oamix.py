@@ -204,6 +204,7 @@ class OAMix:
         # iter_batches: groups whose uploads + saliency are enqueued beyond the launched ones (1 measured 12 % slower:
         # the plan then waits for scores whose upload has only just been queued)
         self.stage_ahead = int(os.environ.get('OADG_STAGE_AHEAD', '2'))
+        self.first_group = max(1, int(os.environ.get('OADG_FIRST_GROUP', '1')))   # batches in a loop's first group
         self.last_launches = 0
 
     def __repr__(self):
@@ -959,7 +960,7 @@ class OAMix:
             """Read the next group's batches, upload their frames and enqueue ONE saliency kernel for all of them."""
             if exhausted[0]:
                 return
-            want = min(gmax, 1 << count[1])       # 1, 2, 4, ... batches per group
+            want = min(gmax, self.first_group << count[1])   # 1, 2, 4, ... batches per group
             jobs = []
             while len(jobs) < want:
                 try:

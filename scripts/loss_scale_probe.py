@@ -13,7 +13,9 @@ from oracle import synth  # noqa: E402
 dev = torch.device('cuda:0')
 n = 2088
 pair_local = reference_pair_map(n)
-for world in (1, 2, 4, 8):
+worlds = [int(a) for a in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 2, 4, 8]
+n_warm, n_iter = (1, 2) if len(sys.argv) > 2 else (5, 20)   # a second argument: short run for ncu
+for world in worlds:
     be = D.CudaBackend()
     sets = [synth.make_roi_set(n, seed=100 + r) for r in range(world)]
     xs = [s[0].to(dev) for s in sets]
@@ -45,10 +47,10 @@ for world in (1, 2, 4, 8):
             timed.append((ev[1].elapsed_time(ev[2]), e3.elapsed_time(ev[3]), ev[3].elapsed_time(ev[4])))
         return loss, gx
 
-    for _ in range(5):
+    for _ in range(n_warm):
         step()
     t = []
-    for _ in range(20):
+    for _ in range(n_iter):
         step(t)
     t = np.median(np.array(t), axis=0) * 1e3
     print('W=%d  rows %5d  forward_packed %7.1f us  finish %5.1f us  backward_packed %7.1f us  sum %7.1f us' %
