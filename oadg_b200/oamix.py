@@ -1059,7 +1059,7 @@ class OAMix:
             if host_jobs:
                 cout.wait_event(done)
                 for j in host_jobs:
-                    host = [self._pinned_out(o.shape, reserve=(2 * gmax + 2) * len(j['douts'])) for o in j['douts']]
+                    host = [self._pinned_out(o.shape, reserve=(3 * gmax + 6) * len(j['douts'])) for o in j['douts']]
                     for (h_, _), o in zip(host, j['douts']):
                         _lib.check(lib.oadg_memcpy_async(h_.data_ptr(), o.data_ptr(), o.numel(), 0, cout.cuda_stream))
                     j['out_ready'] = torch.cuda.Event()
