@@ -925,6 +925,27 @@ class OAMix:
             st = self._streams[(name, str(dev))] = torch.cuda.Stream(dev)
         return st
 
+    @staticmethod
+    def _group_sizes(total, gmax, first=1):
+        """Batches per group for a loop of known length: the ramp-up first, 2 * first, ... then full groups.  Batches
+        that would be left over for a short last group (a launch with few lanes runs at a lower rate) are folded into
+        the ramp-up groups instead."""
+        sizes, left, g = [], total, max(1, first)
+        while left > 0 and g < gmax:
+            sizes.append(min(g, left))
+            left -= sizes[-1]
+            g *= 2
+        n_ramp = len(sizes)
+        full, rem = divmod(left, gmax)
+        for k in range(n_ramp):            # fold the remainder into the ramp-up, first group first
+            add = min(rem, gmax - sizes[k])
+            sizes[k] += add
+            rem -= add
+        sizes += [gmax] * full
+        if rem:
+            sizes.append(rem)
+        return sizes
+
     def _pipeline(self, batches, dev, released):
         """iter_batches' generator: yields (results, job) per batch, in order.
 
@@ -946,6 +967,7 @@ class OAMix:
         exhausted = [False]
         prof = self.pipe_profile          # optional dict: host seconds per phase (scripts/e2e_profile.py)
         gmax = max(1, int(self.group_batches))
+        sizes = self._group_sizes(len(batches), gmax, self.first_group) if hasattr(batches, '__len__') else None
         n_sets = 3 * gmax + 4             # view buffer sets: more than the batches launched ahead + being consumed
         n_in = 5 * gmax + 4               # frame staging slots (host frames): more than the batches staged + in flight
 
@@ -960,7 +982,8 @@ class OAMix:
             """Read the next group's batches, upload their frames and enqueue ONE saliency kernel for all of them."""
             if exhausted[0]:
                 return
-            want = min(gmax, self.first_group << count[1])   # 1, 2, 4, ... batches per group
+            want = sizes[count[1]] if sizes is not None and count[1] < len(sizes) else \
+                min(gmax, self.first_group << count[1])   # 1, 2, 4, ... batches per group
             jobs = []
             while len(jobs) < want:
                 try:

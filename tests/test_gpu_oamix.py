@@ -375,6 +375,14 @@ def test_iter_batches_device_frames(cuda, threaded):
             for _ in range(20):
                 acc = acc * 0.5 + a[1].to(torch.float32)
             assert torch.equal(acc.sum(), sums[k]), (group, k)
+    # a loop of KNOWN length (a list, a DataLoader): the two batches that would be left for a short last group join
+    # the ramp-up (groups of 3, 2, 4 batches), same pixels
+    t.group_batches = 4
+    np.random.seed(13)
+    got = [[r['img2'].clone() for r in res] for res in t.iter_batches(list(batches()), threaded=threaded)]
+    assert t.pipe_launches == 9
+    for a, b in zip(want, got):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
 def test_starved_queue_raises_instead_of_returning_half_written_views(cuda):

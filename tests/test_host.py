@@ -111,6 +111,21 @@ def test_reference_configs_load_unchanged_and_build_our_plugins():
     assert cfg.data.samples_per_gpu == 2 and cfg.custom_imports['imports'] == ['mmdet.datasets.pipelines.oa_mix']
 
 
+def test_group_sizes_of_a_loop_of_known_length():
+    from oadg_b200.oamix import OAMix
+    for total in list(range(0, 40)) + [100, 101, 1000]:
+        for gmax in (1, 2, 3, 4, 8):
+            for first in (1, 2, 4):
+                sizes = OAMix._group_sizes(total, gmax, first)
+                assert sum(sizes) == total and all(1 <= g <= gmax for g in sizes), (total, gmax, first, sizes)
+                # at most one group below full size after the ramp-up, and only when the ramp-up is saturated
+                tail = sizes[3:]
+                assert sum(1 for g in tail if g < gmax) <= 1
+    assert OAMix._group_sizes(20, 4) == [2, 2, 4, 4, 4, 4]        # not 1, 2, 4, 4, 4, 4, 1
+    assert OAMix._group_sizes(19, 4) == [1, 2, 4, 4, 4, 4]
+    assert OAMix._group_sizes(3, 4) == [1, 2]
+
+
 def test_mmdet_shim_steps_aside_for_a_real_mmdet(tmp_path):
     """With another `mmdet` package further down sys.path, `import mmdet` must give THAT package even though the
     repository root (with the shim) comes first."""
