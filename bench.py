@@ -79,8 +79,7 @@ def workload_config(n_gpus):
                          'gathered before the contrastive loss (anchors local, contrasts global)'
                          % n_gpus) if n_gpus > 1 else 'single rank',
             'l2': 'inputs larger than L2: %d distinct source frames (%.0f MB) cycled' % (POOL, POOL * H * W * 3 / 1e6),
-            'pipeline': 'OAMix.iter_batches: steps travel in groups (a short ramp-up, then 4 steps per plan and chain '
-                        'launch; the loop length is known, so no short group is left for the end); '
+            'pipeline': 'OAMix.iter_batches: steps travel in groups (1, 2, then 4 steps per plan and chain launch); '
                         'saliency two groups ahead, kernel chain one group ahead of the step that consumes it'}
 
 
@@ -310,7 +309,7 @@ def product_arm(args):
         # the step loop with frames resident in HBM: the registered transform's loader loop (device views out), then
         # the loss forward + backward of the step
         loss = None
-        for _ in mix.iter_batches(list(dev_batches(n))):   # a loop of known length, like a DataLoader epoch
+        for _ in mix.iter_batches(dev_batches(n)):
             x_dev.grad = None
             loss = run_loss(x_dev)
             loss.backward()
@@ -325,7 +324,7 @@ def product_arm(args):
         # the loader loop a user writes: host numpy in, host numpy out, every step's loss read back
         marks = [time.perf_counter()]
         mix.pipe_profile = {}
-        for results in mix.iter_batches(list(host_batches(n))):
+        for results in mix.iter_batches(host_batches(n)):
             views = [res['img2'] for res in results]
             xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
             loss = run_loss(xd)
