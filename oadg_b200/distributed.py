@@ -268,6 +268,18 @@ class PeerExchange:
 
     TIMEOUT_MS = 20000
 
+    @staticmethod
+    def layout(world, n_rows, width):
+        """Byte offsets inside a rank's exchange buffer: two halves of gathered rows, two halves of gathered tails, one
+        flag word per (exchange, source rank), the ticket word of the last-block-done protocol; 256-byte sections."""
+        a256 = lambda v: (v + 255) // 256 * 256
+        rows_bytes = a256(world * n_rows * width * 4)
+        tail_bytes = a256(world * (n_rows + 1) * 16)
+        off_flag_rows = 2 * rows_bytes + 2 * tail_bytes
+        return dict(rows_bytes=rows_bytes, tail_bytes=tail_bytes, off_rows=(0, rows_bytes),
+                    off_tail=(2 * rows_bytes, 2 * rows_bytes + tail_bytes), off_flag_rows=off_flag_rows,
+                    off_flag_tail=off_flag_rows + 256, off_counter=off_flag_rows + 512, bytes=off_flag_rows + 768)
+
     def __init__(self, group, device, n_rows, width):
         lib = _lib.load()
         self.group, self.device = group, device
@@ -275,15 +287,8 @@ class PeerExchange:
         if self.world > PEER_MAX:
             raise ValueError('PeerExchange: at most %d ranks (one NVLink domain)' % PEER_MAX)
         self.n, self.width = n_rows, width
-        a256 = lambda v: (v + 255) // 256 * 256
-        self.rows_bytes = a256(self.world * n_rows * width * 4)
-        self.tail_bytes = a256(self.world * (n_rows + 1) * 16)
-        self.off_rows = (0, self.rows_bytes)
-        self.off_tail = (2 * self.rows_bytes, 2 * self.rows_bytes + self.tail_bytes)
-        self.off_flag_rows = 2 * self.rows_bytes + 2 * self.tail_bytes
-        self.off_flag_tail = self.off_flag_rows + 256
-        self.off_counter = self.off_flag_tail + 256
-        self.bytes = self.off_counter + 256
+        for k, v in self.layout(self.world, n_rows, width).items():
+            setattr(self, k, v)
         own = ctypes.c_void_p()
         _lib.check(lib.oadg_peer_alloc(self.bytes, ctypes.byref(own)))
         self.own = own.value

@@ -840,6 +840,12 @@ class OAMix:
         enqueue its work on a batch's views before it asks for the next batch (that work is fenced before the
         buffers are reused, 3 * group_batches + 4 batches later).
 
+        Host views are numpy arrays over page-locked buffers that go back to the transform's pool when the last
+        reference to them is dropped; the transform stores them in the sample dicts it was given (``img2``), so a
+        caller that keeps all its dicts (a materialised list of batches) keeps all the buffers, and the loop pins new
+        ones as it goes (milliseconds each).  An iterable with ``__len__`` lets the loop size its groups so that no
+        short group is left for the end.
+
         Differences from calling ``call_batch`` in a loop: ``batches`` is read a few items ahead (the caller must
         leave a batch's input arrays alone until it is yielded), and the np.random draws of later batches are taken
         before earlier ones are yielded: the global stream is consumed in the same order, so results match as long

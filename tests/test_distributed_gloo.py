@@ -166,3 +166,20 @@ def test_oamix_shards_by_image_without_a_collective():
         np.random.seed(500 + idx)
         plan = oamix_np.sample_plan(img, gt, version='augmix')
         assert ml == plan['ml_boxes'].tolist() and oa == [b.tolist() for b in plan['oa_boxes']] and m == plan['m']
+
+
+def test_peer_exchange_layout_sections_do_not_overlap():
+    """The byte layout of a rank's exchange buffer (PeerExchange.layout): every section inside the buffer, aligned,
+    disjoint, flags large enough for OADG_PEER_MAX sources."""
+    from oadg_b200.distributed import PeerExchange, PEER_MAX
+    for world in (2, 3, 8, PEER_MAX):
+        for n in (1, 2048, 2088):
+            lay = PeerExchange.layout(world, n, 260)
+            spans = [(lay['off_rows'][h], world * n * 260 * 4) for h in (0, 1)]
+            spans += [(lay['off_tail'][h], world * (n + 1) * 16) for h in (0, 1)]
+            spans += [(lay['off_flag_rows'], 4 * PEER_MAX), (lay['off_flag_tail'], 4 * PEER_MAX), (lay['off_counter'], 4)]
+            spans.sort()
+            for (a, la), (b, _) in zip(spans, spans[1:]):
+                assert a + la <= b, (world, n, spans)
+            assert spans[-1][0] + spans[-1][1] <= lay['bytes']
+            assert all(a % 16 == 0 for a, _ in spans)
