@@ -557,7 +557,7 @@ def product_arm(args):
             'row statistics are scattered the same way; no collective kernel in the step' if exchange == 'peer' and px
             else 'nccl: two all_gather_into_tensor per step')
         line['comm'] = {'collectives_per_step': 0 if exchange == 'peer' and px else 2,
-                        'nvlink_bytes_out_per_rank_per_step': px.nvlink_bytes_per_step if exchange == 'peer' and px else
+                        'nvlink_bytes_out_per_rank_per_step': px.nvlink_bytes(N_ROI) if exchange == 'peer' and px else
                         (world - 1) * (N_ROI * (C_ROI + 4) * 4 + (N_ROI + 1) * 16)}
         line['parity'] = parity
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)

@@ -349,6 +349,9 @@ int oadg_jsd2_forward(const float* pred_dev, int n, int c, float* loss_dev, floa
  *   oadg_peer_wait                 returns (in stream order) once flags_dev[r] has reached seq for every r < world
  *                                   (cyclic comparison); after timeout_ms it writes 1 to *fault_host (page-locked, mapped)
  *                                   and gives up, so a dead peer surfaces as an error instead of a hang.
+ * Next to its flag every sender leaves a tag (flag word [OADG_PEER_MAX + rank]; the pack kernel sends its row count,
+ * oadg_peer_scatter whatever the caller passes): a waiter whose own tag differs writes 2 to *fault_host -- ranks that
+ * disagree on the shape of the exchange must not read each other's rows at the wrong offsets.
  * counter_offset names a zero-initialised 32-bit word of the caller's own buffer (last-block-done ticket). */
 #define OADG_PEER_MAX 16
 typedef struct {
@@ -366,9 +369,9 @@ int oadg_supcon_gather_pack_peers(const float* feats_dev, const int64_t* labels_
                                   size_t rows_offset, size_t flag_offset, size_t counter_offset, uint32_t seq,
                                   void* workspace_dev, size_t workspace_bytes, void* stream);
 int oadg_peer_scatter(const oadg_peers_t* peers, size_t offset, size_t bytes, size_t flag_offset,
-                      size_t counter_offset, uint32_t seq, void* stream);
-int oadg_peer_wait(const uint32_t* flags_dev, int world, uint32_t seq, uint32_t timeout_ms, uint32_t* fault_host,
-                   void* stream);
+                      size_t counter_offset, uint32_t seq, uint32_t tag, void* stream);
+int oadg_peer_wait(const uint32_t* flags_dev, int world, uint32_t seq, uint32_t tag, uint32_t timeout_ms,
+                   uint32_t* fault_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,8 +55,8 @@ SIGNATURES = {
     'oadg_peer_fault_alloc': (_c.c_int, [_c.POINTER(_c.POINTER(_c.c_uint32))]),
     'oadg_supcon_gather_pack_peers': (_c.c_int, [_vp, _vp, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _vp, _sz, _sz,
                                                  _sz, _c.c_uint32, _vp, _sz, _vp]),
-    'oadg_peer_scatter': (_c.c_int, [_vp, _sz, _sz, _sz, _sz, _c.c_uint32, _vp]),
-    'oadg_peer_wait': (_c.c_int, [_vp, _c.c_int, _c.c_uint32, _c.c_uint32, _vp, _vp]),
+    'oadg_peer_scatter': (_c.c_int, [_vp, _sz, _sz, _sz, _sz, _c.c_uint32, _c.c_uint32, _vp]),
+    'oadg_peer_wait': (_c.c_int, [_vp, _c.c_int, _c.c_uint32, _c.c_uint32, _c.c_uint32, _vp, _vp]),
     'oadg_jsd2_scratch_bytes': (_c.c_int, []),
     'oadg_jsd2_forward': (_c.c_int, [_vp, _c.c_int, _c.c_int, _vp, _vp, _vp, _vp]),
 }

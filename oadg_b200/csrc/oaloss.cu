@@ -516,7 +516,7 @@ normalize_pack_peers_kernel(const float* __restrict__ x, const int64_t* __restri
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(static_cast<char*>(P.base[r]) + rows_offset) + at + c) = t;
     }
   }
-  peer_signal(P, flag_offset, counter_offset, seq);
+  peer_signal(P, flag_offset, counter_offset, seq, (unsigned)n);
 }
 __global__ void __launch_bounds__(256)
 unpack_labels_kernel(const float* __restrict__ recv, int n_total, int c, int64_t* __restrict__ labels_all) {

@@ -14,18 +14,19 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 peer_scatter_kernel(const oadg_peers_t P, size_t offset, size_t n_vec, size_t flag_offset, size_t counter_offset,
-                    unsigned seq) {
+                    unsigned seq, unsigned tag) {
   const uint4* src = reinterpret_cast<const uint4*>(static_cast<const char*>(P.base[P.rank]) + offset);
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * 256) {
     const uint4 v = src[i];
     for (int r = 0; r < P.world; ++r)
       if (r != P.rank) reinterpret_cast<uint4*>(static_cast<char*>(P.base[r]) + offset)[i] = v;
   }
-  peer_signal(P, flag_offset, counter_offset, seq);
+  peer_signal(P, flag_offset, counter_offset, seq, tag);
 }
 
 __global__ void __launch_bounds__(32)
-peer_wait_kernel(const unsigned* flags, int world, unsigned seq, unsigned long long timeout_ns, unsigned* fault_host) {
+peer_wait_kernel(const unsigned* flags, int world, unsigned seq, unsigned tag, unsigned long long timeout_ns,
+                 unsigned* fault_host) {
   const int r = threadIdx.x;
   if (r >= world) return;
   unsigned long long t0 = 0;
@@ -34,7 +35,14 @@ peer_wait_kernel(const unsigned* flags, int world, unsigned seq, unsigned long l
   for (;;) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-    if ((int)(v - seq) >= 0) return;
+    if ((int)(v - seq) >= 0) {
+      // the sender's view of the exchange must be ours (same row count on every rank), unless it is already a step ahead
+      if (v == seq && flags[OADG_PEER_MAX + r] != tag) {
+        *fault_host = 2u;
+        __threadfence_system();
+      }
+      return;
+    }
     __nanosleep(spins < 64 ? 20 : 200);
     if ((++spins & 1023u) == 0) {
       unsigned long long t1;
@@ -99,7 +107,7 @@ extern "C" int oadg_peer_fault_alloc(uint32_t** fault_host_out) {
 }
 
 extern "C" int oadg_peer_scatter(const oadg_peers_t* peers, size_t offset, size_t bytes, size_t flag_offset,
-                                 size_t counter_offset, uint32_t seq, void* stream) {
+                                 size_t counter_offset, uint32_t seq, uint32_t tag, void* stream) {
   if (!peers || peers->world < 1 || peers->world > OADG_PEER_MAX || peers->rank < 0 || peers->rank >= peers->world)
     return OADG_E_ARG;
   if ((bytes & 15) || (offset & 15) || (flag_offset & 3) || (counter_offset & 3) || !bytes) return OADG_E_ARG;
@@ -108,16 +116,17 @@ extern "C" int oadg_peer_scatter(const oadg_peers_t* peers, size_t offset, size_
   const size_t n_vec = bytes / 16;
   int blocks = (int)((n_vec + 255) / 256);
   if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
-  peer_scatter_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*peers, offset, n_vec, flag_offset, counter_offset, seq);
+  peer_scatter_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*peers, offset, n_vec, flag_offset, counter_offset, seq,
+                                                                tag);
   OADG_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int oadg_peer_wait(const uint32_t* flags_dev, int world, uint32_t seq, uint32_t timeout_ms,
+extern "C" int oadg_peer_wait(const uint32_t* flags_dev, int world, uint32_t seq, uint32_t tag, uint32_t timeout_ms,
                               uint32_t* fault_host, void* stream) {
   if (!flags_dev || !fault_host || world < 1 || world > OADG_PEER_MAX) return OADG_E_ARG;
-  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_dev, world, seq, (unsigned long long)timeout_ms * 1000000ull,
-                                                       fault_host);
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_dev, world, seq, tag,
+                                                       (unsigned long long)timeout_ms * 1000000ull, fault_host);
   OADG_LAUNCH_CHECK();
   return 0;
 }

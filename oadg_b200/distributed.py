@@ -167,10 +167,19 @@ class CudaBackend(UnpackedBackend):
 
     # ---- the same protocol with the exchanges done by the kernels themselves (PeerExchange)
     def peer_exchange(self, group, device, n, c):
-        key = (id(group), str(device), n, c)
-        if getattr(self, '_px_key', None) != key:
-            self._px = PeerExchange(group, device, n, _lib.load().oadg_supcon_pack_width(c))
+        """The mapped buffers for steps of up to a capacity of rows (RoI counts vary from step to step with the random
+        proposals); a new, larger exchange is set up -- collectively, every rank sees the same n -- only when a step
+        exceeds it."""
+        key = (id(group), str(device), c)
+        px = getattr(self, '_px', None)
+        if px is None or getattr(self, '_px_key', None) != key or n > px.n:
+            cap = max(4096, (n + 1023) // 1024 * 1024)
+            self._px = PeerExchange(group, device, cap, _lib.load().oadg_supcon_pack_width(c))
             self._px_key = key
+            if px is not None:               # every rank is past the new exchange's barrier: retire the old buffers
+                torch.cuda.synchronize(device)
+                dist.barrier(group=group)
+                px.close()
         return self._px
 
     def forward_peers(self, x, labels, pair_all, px, temperature, loss_weight, min_samples, normalized_input):
@@ -181,20 +190,20 @@ class CudaBackend(UnpackedBackend):
         labels = labels.reshape(-1)
         if labels.dtype != torch.int64 or labels.device != x.device or not labels.is_contiguous():
             labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
-        seq, half = px.begin_step()
+        seq, half = px.begin_step(n)
         s = _lib.raw_stream(x.device)
         _lib.check(lib.oadg_supcon_gather_pack_peers(x.data_ptr(), labels.data_ptr(), labels.shape[0], n, n_total, c,
                                                      int(normalized_input), ctypes.byref(px.peers), px.off_rows[half],
                                                      px.off_flag_rows, px.off_counter, seq, self.ws[1], self.ws[2], s))
-        px.wait(px.off_flag_rows, seq, s)
+        px.wait(px.off_flag_rows, seq, n, s)
         self.launches += 2
         self._c = c
-        self.forward_packed(px.rows(half), pair_all, px.rank * n, n, temperature, loss_weight, min_samples,
-                            tail=px.tail_own(half))
-        px.scatter_tail(half, seq, s)
-        px.wait(px.off_flag_tail, seq, s)
+        self.forward_packed(px.rows(half, n), pair_all, px.rank * n, n, temperature, loss_weight, min_samples,
+                            tail=px.tail_own(half, n))
+        px.scatter_tail(half, seq, n, s)
+        px.wait(px.off_flag_tail, seq, n, s)
         self.launches += 2
-        return self.finish(px.tail_all(half), px.world, n)
+        return self.finish(px.tail_all(half, n), px.world, n)
 
     # ---- plain entry points (one rank playing several, tests)
     def normalize(self, x, n_total, normalized_input):
@@ -281,6 +290,8 @@ class PeerExchange:
                     off_flag_tail=off_flag_rows + 256, off_counter=off_flag_rows + 512, bytes=off_flag_rows + 768)
 
     def __init__(self, group, device, n_rows, width):
+        """``n_rows``: the CAPACITY in rows per rank; a step may exchange any row count up to it (the same on every
+        rank: senders tag their flag with it and a waiter that expected another count raises)."""
         lib = _lib.load()
         self.group, self.device = group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
@@ -312,33 +323,54 @@ class PeerExchange:
         _lib.check(lib.oadg_peer_fault_alloc(ctypes.byref(fault)))
         self.fault = fault
         self.seq = 0
-        self.nvlink_bytes_per_step = (self.world - 1) * (n_rows * width * 4 + (n_rows + 1) * 16)
         dist.barrier(group=group)            # every buffer is mapped everywhere before the first store
 
-    def begin_step(self):
+    def begin_step(self, n):
+        if self.fault[0] == 2:
+            raise _lib.OADGError('gathered OA-Loss: the ranks disagree on the number of rows of a step (every rank '
+                                 'must pass the same N)')
         if self.fault[0]:
             raise _lib.OADGError('gathered OA-Loss: a peer rank did not deliver its rows / statistics within %d s'
                                  % (self.TIMEOUT_MS // 1000))
+        if n > self.n:
+            raise ValueError('PeerExchange: %d rows exceed the capacity of %d' % (n, self.n))
         self.seq += 1
         return self.seq, self.seq & 1
 
-    def rows(self, half):
-        return _Raw(self.own + self.off_rows[half], (self.world * self.n, self.width), self.device)
+    # a step's regions are packed for ITS row count n (<= capacity): rank r's rows start at row r * n
+    def rows(self, half, n):
+        return _Raw(self.own + self.off_rows[half], (self.world * n, self.width), self.device)
 
-    def tail_own(self, half):
-        return _Raw(self.own + self.off_tail[half] + self.rank * (self.n + 1) * 16, (self.n + 1, 4), self.device)
+    def tail_own(self, half, n):
+        return _Raw(self.own + self.off_tail[half] + self.rank * (n + 1) * 16, (n + 1, 4), self.device)
 
-    def tail_all(self, half):
-        return _Raw(self.own + self.off_tail[half], (self.world, self.n + 1, 4), self.device)
+    def tail_all(self, half, n):
+        return _Raw(self.own + self.off_tail[half], (self.world, n + 1, 4), self.device)
 
-    def wait(self, flag_offset, seq, stream):
-        _lib.check(_lib.load().oadg_peer_wait(self.own + flag_offset, self.world, seq, self.TIMEOUT_MS, self.fault,
+    def wait(self, flag_offset, seq, n, stream):
+        _lib.check(_lib.load().oadg_peer_wait(self.own + flag_offset, self.world, seq, n, self.TIMEOUT_MS, self.fault,
                                               stream))
 
-    def scatter_tail(self, half, seq, stream):
-        off = self.off_tail[half] + self.rank * (self.n + 1) * 16
-        _lib.check(_lib.load().oadg_peer_scatter(ctypes.byref(self.peers), off, (self.n + 1) * 16, self.off_flag_tail,
-                                                 self.off_counter, seq, stream))
+    def scatter_tail(self, half, seq, n, stream):
+        off = self.off_tail[half] + self.rank * (n + 1) * 16
+        _lib.check(_lib.load().oadg_peer_scatter(ctypes.byref(self.peers), off, (n + 1) * 16, self.off_flag_tail,
+                                                 self.off_counter, seq, n, stream))
+
+    def nvlink_bytes(self, n):
+        """Bytes this rank stores into its peers' buffers in a step of n rows."""
+        return (self.world - 1) * (n * self.width * 4 + (n + 1) * 16)
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (collective in effect: call it on every rank, after a
+        barrier, when no step is in flight)."""
+        lib = _lib.load()
+        for r in range(self.world):
+            if r != self.rank and self.peers.base[r]:
+                lib.oadg_peer_release(self.peers.base[r])
+                self.peers.base[r] = None
+        if self.own:
+            lib.oadg_peer_free(self.own)
+            self.own = None
 
 
 _PAIR_CACHE = {}

@@ -167,7 +167,31 @@ def _two_rank_worker(rank, world, port, q, exchange):
         refused = False
     except RuntimeError:
         refused = True
-    q.put((rank, out, same, refused, be.launches))
+    # RoI counts vary from step to step (random proposals): other row counts reuse the mapped buffers
+    varied = []
+    if exchange == 'peer':
+        for n_rows in (2088, 2052):
+            x, labels = synth.make_roi_set(n_rows, seed=70 + rank + n_rows)
+            xd = x.cuda().requires_grad_(True)
+            loss = gathered_contrastive_loss(xd, labels.cuda(), temperature=0.06, loss_weight=0.01, backend=be,
+                                             exchange=exchange)
+            loss.backward()
+            varied.append((n_rows, x.numpy(), labels.numpy().reshape(-1), loss.item(), xd.grad.cpu().numpy()))
+        assert be._px.n == 4096 and be._px.seq == 7
+    # ranks that disagree on the row count: the step's result is meaningless, and the NEXT call must raise
+    mismatch = None
+    if exchange == 'peer':
+        from oadg_b200._lib import OADGError
+        n_bad = 2048 + 2 * rank
+        x, labels = synth.make_roi_set(n_bad, seed=5)
+        gathered_contrastive_loss(x.cuda(), labels.cuda(), backend=be, exchange=exchange)
+        torch.cuda.synchronize()
+        try:
+            gathered_contrastive_loss(x.cuda(), labels.cuda(), backend=be, exchange=exchange)
+            mismatch = False
+        except OADGError as e:
+            mismatch = 'disagree' in str(e)
+    q.put((rank, out, same, refused, be.launches, varied, mismatch))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -197,7 +221,7 @@ def test_gathered_loss_two_gpus_nccl(cuda, exchange):
         x_all = np.concatenate([r[1][step][0] for r in res])
         y_all = np.concatenate([r[1][step][1] for r in res])
         ref, gref = supcon_np.supcon_loss(x_all, y_all, 0.06, 10, 0.01, want_grad=True, pair=pair_all)
-        for rank, out, same, refused, launches in res:
+        for rank, out, same, refused, launches, _, _ in res:
             _, _, loss, grad = out[step]
             assert abs(loss - ref) <= RTOL * abs(ref), (step, rank)
             want = 2 * gref[rank * 2048:(rank + 1) * 2048]
@@ -205,6 +229,18 @@ def test_gathered_loss_two_gpus_nccl(cuda, exchange):
     assert res[0][1][2][2] == res[1][1][2][2]            # every rank reports the same bits
     assert all(r[2] for r in res), 'peer and nccl exchanges disagree'
     assert all(r[3] for r in res), 'a stale backward was not refused'
+    if exchange == 'peer':
+        for k, n_rows in enumerate((2088, 2052)):
+            x_all = np.concatenate([r[5][k][1] for r in res])
+            y_all = np.concatenate([supcon_np.pad_labels(r[5][k][2], n_rows) for r in res])
+            ref, gref = supcon_np.supcon_loss(x_all, y_all, 0.06, 10, 0.01, want_grad=True,
+                                              pair=gathered_pair_map(reference_pair_map(n_rows), 2))
+            for rank, *_rest in res:
+                _, _, _, loss, grad = res[rank][5][k]
+                assert abs(loss - ref) <= RTOL * abs(ref), (n_rows, rank)
+                want = 2 * gref[rank * n_rows:(rank + 1) * n_rows]
+                assert np.linalg.norm(grad - want) <= RTOL * np.linalg.norm(want), (n_rows, rank)
+        assert all(r[6] is True for r in res), 'a row-count mismatch between the ranks went unnoticed'
 
 
 @pytest.mark.parametrize('world', [4, 8])
