@@ -533,6 +533,18 @@ def product_arm(args):
                   'events, same inputs', vs_torch_reference=e0.elapsed_time(e1) / 20 / loss_ms,
                   parity_vs_torch={'loss_rel': rel_l, 'grad_rel': rel_g})
 
+    # ---- the single-sample transform call a stock config makes (OAMix.__call__ on one host frame: H2D, kernels, D2H,
+    # one synchronisation per image), for reference next to the batched / pipelined paths
+    single_ms = None
+    if world == 1:
+        np.random.seed(3)
+        ts = []
+        for k in range(6):
+            f, g = frames[k % POOL]
+            t0 = time.perf_counter()
+            mix(dict(img=f, gt_bboxes=g))
+            ts.append((time.perf_counter() - t0) * 1e3)
+        single_ms = float(np.median(ts[1:]))
     # ---- CPU baseline (rank 0, N=1 only): bounded sample on the host cores
     log('loss timing done')
     cpu = None
@@ -549,7 +561,8 @@ def product_arm(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32', 'data': 'synthetic',
             'config': workload_config(world), 'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': launches, 'roofline': roofline, 'oaloss': oaloss, 'cpu_baseline': cpu}
+            'gpu_launches': launches, 'roofline': roofline, 'oaloss': oaloss, 'cpu_baseline': cpu,
+            'single_sample_call_ms': single_ms}
     if gather:
         px = getattr(gbe, '_px', None)
         line['config']['exchange'] = (

@@ -247,20 +247,39 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
       b = min(b, ks);
       return b > a ? K[b] - K[a] : 0.0;
     };
+    auto span = [&](int a, int b) {   // how many taps that is
+      a = max(a, 0);
+      b = min(b, ks);
+      return b > a ? b - a : 0;
+    };
+    // A window that lies entirely inside the box (only boxes that span the frame get there, through the reflected
+    // border) carries cv2's saturated value, whose last bit decides every truncation of the blend: the x profile
+    // carries 1.0 and the y profile the constant of cv_saturated_col / _row (oamix_math.h); kSatMark is replaced below.
+    constexpr float kSatMark = 2.0f;
+    if (tid == 0) S.red[0] = 0.0;
+    worker_sync();
+    bool any_sat = false;
     if (r <= n_lo - 1) {
       // BORDER_REFLECT_101 with at most one reflection per side: tap j reads q = x + j - r, -q or 2(n_lo-1) - q
       for (int x = tid; x < n_lo; x += kCT) {
         const int s = r - x;  // j = q + s
+        const int m2 = 2 * (n_lo - 1);
         double acc = range(lo + s, hi + s);                                    // q in [lo, hi)
         acc += range(-hi + 1 + s, min(-lo, -1) + 1 + s);                       // q in [-hi+1, min(-lo,-1)]
-        const int m2 = 2 * (n_lo - 1);
         acc += range(max(m2 - hi + 1, n_lo) + s, m2 - lo + 1 + s);             // q in [max(m2-hi+1,n_lo), m2-lo]
+        const int cov = span(lo + s, hi + s) + span(-hi + 1 + s, min(-lo, -1) + 1 + s) +
+                        span(max(m2 - hi + 1, n_lo) + s, m2 - lo + 1 + s);
         p[x] = (float)acc;
+        if (cov == ks) {
+          p[x] = axis == 0 ? 1.f : kSatMark;
+          any_sat = true;
+        }
       }
     } else {
       const int period = 2 * (n_lo - 1);
       for (int x = tid; x < n_lo; x += kCT) {
         double acc = 0.0;
+        int cov = 0;
         for (int j = 0; j < ks; ++j) {
           int q = x + j - r;
           if (n_lo == 1) q = 0;
@@ -269,9 +288,52 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
             q %= period;
             if (q >= n_lo) q = period - q;
           }
-          if (q >= lo && q < hi) acc += K[j + 1] - K[j];
+          if (q >= lo && q < hi) {
+            acc += K[j + 1] - K[j];
+            ++cov;
+          }
         }
         p[x] = (float)acc;
+        if (cov == ks) {
+          p[x] = axis == 0 ? 1.f : kSatMark;
+          any_sat = true;
+        }
+      }
+    }
+    if (axis == 1) {
+      if (any_sat) S.red[0] = 1.0;   // same value from every writer
+      worker_sync();
+      if (S.red[0] != 0.0) {         // rare: both kernels as float32 taps, then the two float sums in cv2's order
+        float* kyf = reinterpret_cast<float*>(dyn + 1538 * 8 + 4096);
+        float* kxf = kyf + 1540;
+        const int ksx = G.kx;
+        const double s2x = -0.5 / (G.sigma_x * G.sigma_x);
+        worker_sync();
+        double px = 0.0;
+        for (int i = tid; i < ksx; i += kCT) {
+          double x = i - (ksx - 1) * 0.5;
+          px += exp(s2x * x * x);
+        }
+        px = warp_sum(px);
+        if ((tid & 31) == 0) S.red[tid >> 5] = px;
+        worker_sync();
+        double tx = 0;
+        for (int w = 0; w < kCT / 32; ++w) tx += S.red[w];
+        const double ksumx = 1.0 / tx;
+        for (int i = tid; i < ksx; i += kCT) {
+          double x = i - (ksx - 1) * 0.5;
+          kxf[i] = (float)(exp(s2x * x * x) * ksumx);
+        }
+        for (int i = tid; i < ks; i += kCT) {
+          double x = i - (ks - 1) * 0.5;
+          kyf[i] = (float)(exp(s2 * x * x) * ksum);
+        }
+        worker_sync();
+        if (tid == 0) S.ksum = (double)cv_saturated_col(kyf, ks, cv_saturated_row(kxf, ksx));
+        worker_sync();
+        const float sat = (float)S.ksum;
+        for (int x = tid; x < n_lo; x += kCT)
+          if (p[x] == kSatMark) p[x] = sat;
       }
     }
   } else {
@@ -287,7 +349,7 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
     if (s < 0) { s = 0; t = 0.f; }
     if (s >= n_lo - 1) { s = n_lo - 1; t = 0.f; }
     int s1 = min(s + 1, n_lo - 1);
-    out[d] = fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));
+    out[d] = p[s] == p[s1] ? p[s] : fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));   // a constant run stays constant
   }
 }
 // union of the blurred gt masks of a view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260) as float32 and as

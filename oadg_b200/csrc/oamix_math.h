@@ -40,6 +40,31 @@ OADG_HD float fsub(float a, float b) {
   return a - b;
 #endif
 }
+// the one place where the reference's arithmetic IS fused: OpenCV's vectorised column filter (v_fma)
+OADG_HD float ffma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+// Value of cv2.GaussianBlur on a window that lies entirely inside the box (all taps read 1.0), as OpenCV computes it
+// in float32 (verified against cv2 4.13 for 400 sigmas, scripts in DESIGN.md section 7): the row filter adds the taps in
+// order, the symmetric column filter starts at the centre tap and adds k[c+j] * (v + v) outward with fused
+// multiply-adds.  The result is 1 - 2^-24, 1 or 1 + 2^-23 depending on the kernel, and where the mask saturates the
+// blend img*(1-m) + aug*m sits on an integer, so this last bit decides the truncation of EVERY pixel there.
+OADG_HD float cv_saturated_row(const float* k, int ks) {
+  float s = k[0];
+  for (int j = 1; j < ks; ++j) s = fadd(s, k[j]);
+  return s;
+}
+OADG_HD float cv_saturated_col(const float* k, int ks, float v) {
+  const int c = ks / 2;
+  float s = fmul(k[c], v);
+  const float v2 = fadd(v, v);
+  for (int j = 1; j <= c; ++j) s = ffma(k[c + j], v2, s);
+  return s;
+}
 OADG_HD double dmul(double a, double b) {
 #ifdef __CUDA_ARCH__
   return __dmul_rn(a, b);

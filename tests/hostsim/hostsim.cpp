@@ -47,21 +47,33 @@ struct HostBackend {
       return;
     }
     std::vector<float> p(n_lo), kern(ks > 0 ? ks : 1);
-    if (G.blur) {
-      const double s2 = -0.5 / (sigma * sigma);
+    auto taps = [](int n, double sg, std::vector<float>& k) {
+      k.assign(n > 0 ? n : 1, 0.f);
+      const double s2 = -0.5 / (sg * sg);
       double sum = 0;
-      for (int i = 0; i < ks; ++i) {
-        double x = i - (ks - 1) * 0.5;
+      for (int i = 0; i < n; ++i) {
+        double x = i - (n - 1) * 0.5;
         sum += exp(s2 * x * x);
       }
       const double ksum = 1.0 / sum;
-      for (int i = 0; i < ks; ++i) {
-        double x = i - (ks - 1) * 0.5;
-        kern[i] = (float)(exp(s2 * x * x) * ksum);
+      for (int i = 0; i < n; ++i) {
+        double x = i - (n - 1) * 0.5;
+        k[i] = (float)(exp(s2 * x * x) * ksum);
+      }
+    };
+    if (G.blur) {
+      taps(ks, sigma, kern);
+      // a window that lies entirely inside the box: the x profile carries 1.0 and the y profile cv2's saturated value
+      float sat = 1.f;
+      if (axis == 1) {
+        std::vector<float> kx;
+        taps(G.kx, G.sigma_x, kx);
+        sat = cv_saturated_col(kern.data(), ks, cv_saturated_row(kx.data(), G.kx));
       }
       const int r = ks / 2, period = 2 * (n_lo - 1);
       for (int x = 0; x < n_lo; ++x) {
         double acc = 0;
+        int hits = 0;
         for (int j = 0; j < ks; ++j) {
           int q = x + j - r;
           if (n_lo == 1) q = 0;
@@ -70,9 +82,12 @@ struct HostBackend {
             q %= period;
             if (q >= n_lo) q = period - q;
           }
-          if (q >= lo && q < hi) acc += (double)kern[j];
+          if (q >= lo && q < hi) {
+            acc += (double)kern[j];
+            ++hits;
+          }
         }
-        p[x] = (float)acc;
+        p[x] = hits == ks ? sat : (float)acc;
       }
     } else {
       for (int x = 0; x < n_lo; ++x) p[x] = (x >= lo && x < hi) ? 1.f : 0.f;
@@ -85,7 +100,7 @@ struct HostBackend {
       if (s < 0) { s = 0; t = 0.f; }
       if (s >= n_lo - 1) { s = n_lo - 1; t = 0.f; }
       int s1 = s + 1 < n_lo - 1 ? s + 1 : n_lo - 1;
-      out[d] = fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));
+      out[d] = p[s] == p[s1] ? p[s] : fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));   // a constant run stays constant
     }
   }
   static void lut_item(const ChainArgs& A, int job) {

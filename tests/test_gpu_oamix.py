@@ -36,7 +36,7 @@ def test_saliency_scores_match_oracle(cuda):
         ref = oamix_np.fg_scores(img, gt)
         assert len(ref) == len(sc)
         for a, b in zip(sc, ref):
-            assert abs(a - b) <= 5e-3, (a, b)
+            assert abs(a - b) <= 1e-3, (a, b)      # SURVEY 8d; measured: 2.4e-5 on the bench frames
             assert (a <= 10) == (b <= 10)
     assert got[3][1] == -1          # narrower than spatial_ratio (oa_mix.py:103-105)
     assert got[4][0] == 0.0         # flat crop: NaN map -> 0 like the reference's uint8 cast
@@ -148,9 +148,23 @@ def test_edge_cases(cuda):
         ref, plan = oamix_np.oamix_view(img, gt, **sampler_cfg(cfg))
         np.random.seed(seed)
         out = OAMix(**cfg).oamix_batch(_views(cuda, [img]), [gt])[0][0].cpu().numpy()
-        # a frame-sized box saturates its blurred mask at 1.0 +- 1 ulp, where `img*(1-m) + aug*m` sits exactly on
-        # an integer: the truncation then follows the last bit of cv2's float blur (still <= 1 LSB, <= 1e-4 rel)
-        _close(out, ref, frac=2e-2 if gt.shape[0] == 1 and gt[0, 2] >= w else 2e-3)
+        # (a frame-sized box saturates its blurred mask, where `img*(1-m) + aug*m` sits exactly on an integer at every
+        # pixel: the profile tile reproduces cv2's float32 constant there, see test_frame_sized_box_... below)
+        _close(out, ref, frac=1e-3)
+
+
+@pytest.mark.parametrize('rep', range(4))
+def test_frame_sized_box_saturated_mask_is_exact(cuda, rep):
+    """tests/test_hostsim.py::test_frame_sized_box_saturated_mask_is_exact on the GPU."""
+    from oadg_b200 import OAMix
+    h, w, gt = 128, 96, np.float32([[0, 0, 96, 128]])
+    img, _ = synth.make_image(3, h, w, 0)
+    cfg = dict(OAMIX_CFG, version='augmix.all')
+    np.random.seed(3 + 100 * rep)
+    ref, plan = oamix_np.oamix_view(img, gt, **sampler_cfg(cfg))
+    np.random.seed(3 + 100 * rep)
+    out = OAMix(**cfg).oamix_batch(_views(cuda, [img]), [gt])[0][0].cpu().numpy()
+    assert np.array_equal(out, ref)
 
 
 def test_single_op_plans_match_host_arithmetic_bit_for_bit(cuda):
@@ -383,6 +397,40 @@ def test_iter_batches_device_frames(cuda, threaded):
     assert t.pipe_launches == 9
     for a, b in zip(want, got):
         assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+class _FrameSet:
+    """A map-style dataset of sample dicts the way the reference's pipeline hands them to OAMix (decoded frame + gt)."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        img, gt = synth.make_image(500 + i, 160, 288, 4)
+        return dict(img=img, gt_bboxes=gt, idx=i)
+
+
+def test_iter_batches_under_a_torch_dataloader(cuda):
+    """A real torch DataLoader with worker processes (decode on the CPU workers, the transform in the process that owns
+    the CUDA context): `len(loader)` sizes the groups (7 batches -> 1 + 2 + 4), results equal call_batch."""
+    import torch
+    from torch.utils.data import DataLoader
+    from oadg_b200 import OAMix
+    t = OAMix(**dict(OAMIX_CFG, version='augmix'))
+    loader = DataLoader(_FrameSet(14), batch_size=2, shuffle=False, num_workers=2, collate_fn=lambda b: b)
+    np.random.seed(21)
+    want = [t.call_batch([dict(s) for s in batch]) for batch in loader]
+    np.random.seed(21)
+    got = list(t.iter_batches(loader))
+    assert t.pipe_launches == 9 and len(got) == 7
+    for a, b in zip(want, got):
+        for ra, rb in zip(a, b):
+            assert ra['idx'] == rb['idx']
+            for k in ('img', 'img2', 'gt_bboxes2', 'oamix_boxes', 'multilevel_boxes'):
+                assert np.array_equal(ra[k], rb[k]), k
 
 
 def test_starved_queue_raises_instead_of_returning_half_written_views(cuda):

@@ -53,6 +53,27 @@ def test_kernel_arithmetic_matches_oracle(hostsim, case):
     assert d.max() <= 1 and (d != 0).mean() <= 1e-3, (int(d.max()), float((d != 0).mean()))
 
 
+@pytest.mark.parametrize('rep', range(8))
+def test_frame_sized_box_saturated_mask_is_exact(hostsim, rep):
+    """A gt box that spans the frame: every blur window is fully covered through the reflected border, the mask
+    saturates at cv2's float32 constant (1 - 2^-24, 1 or 1 + 2^-23 depending on the kernel) and `img*(1-m) + aug*m`
+    sits on an integer at EVERY pixel, so the last bit of that constant decides every truncation.  With the constant
+    summed in OpenCV's order (cv_saturated_row / _col, oamix_math.h) the views are exact; with 1.0 in its place up to
+    43 % of the values were off by 1-3 LSB."""
+    from oadg_b200.oamix import OAMix
+    h, w, gt = 128, 96, np.float32([[0, 0, 96, 128]])
+    img, _ = synth.make_image(3, h, w, 0)
+    cfg = sampler_cfg(dict(OAMIX_CFG, version='augmix.all'))
+    np.random.seed(3 + 100 * rep)
+    ref, plan = oamix_np.oamix_view(img, gt, **cfg)
+    np.random.seed(3 + 100 * rep)
+    t = OAMix(**cfg)
+    vp = t._sample_head(h, w, gt)
+    t._sample_tail(vp, gt, plan['scores'])
+    out, = run(hostsim, t, [(vp, gt, 0)], [img])
+    assert np.array_equal(out, ref)
+
+
 def test_two_views_one_batch(hostsim):
     from oadg_b200.oamix import OAMix
     cfg = sampler_cfg(dict(OAMIX_CFG, version='augmix'))
