@@ -215,6 +215,46 @@ def test_randomized_sweep_against_oracle_in_two_execution_orders(hostsim, case):
     assert d.max() <= 1 and (d != 0).mean() <= 1e-3, (int(d.max()), float((d != 0).mean()))
 
 
+def _adversarial_boxes(n=48, seed=77):
+    rng = np.random.RandomState(seed)
+    cases = []
+    for k in range(n):
+        h, w = int(rng.randint(48, 280)), int(rng.randint(48, 400))
+        n_gt, s, draw = int(rng.randint(1, 7)), int(rng.randint(0, 1000)), int(rng.randint(0, 100000))
+        cases.append((k, h, w, n_gt, s, draw, int(rng.randint(n_gt))))
+    return cases
+
+
+@pytest.mark.parametrize('case', _adversarial_boxes())
+def test_adversarial_gt_boxes_against_oracle(hostsim, case):
+    """gt boxes the synthetic generator never draws: beyond the frame, narrower than spatial_ratio, sub-pixel, inverted,
+    strips along a border, spanning an axis, all but a one-pixel frame.  Boxes that touch two borders have zones where
+    the blurred mask is within ~1e-6 of 1 and a 1e-7 difference to cv2's float32 filter flips a truncation, and the
+    flips of successive depth steps can add up: the bound here (3 LSB; more than 1 LSB on <= 3e-4 and any difference on
+    <= 0.3 % of the values; measured worst: 3 LSB on 5e-5, 1 LSB on 2.6e-3) is looser than the 1 LSB / 0.1 % every
+    other test holds, and is stated as a known deviation in DESIGN.md section 7."""
+    from oadg_b200.oamix import OAMix
+    k, h, w, n_gt, s, seed, j = case
+    img, gt = synth.make_image(s, h, w, n_gt)
+    gt = gt.copy()
+    gt[j] = [[w * 0.5, h * 0.3, w + 30.7, h + 12.2], [10, 10, 13.9, 40], [30.2, 20.7, 30.9, 21.1],
+             [w * 0.6, h * 0.6, w * 0.3, h * 0.2], [0, 0, w, 4], [w - 5, 0, w, h], [1, 1, w - 1, h - 1],
+             [0, h * 0.25, w, h * 0.75]][k % 8]
+    cfg = sampler_cfg(dict(OAMIX_CFG, version='augmix.all' if k % 2 else 'augmix'))
+    np.random.seed(seed)
+    try:
+        ref, plan = oamix_np.oamix_view(img, gt, **cfg)
+    except ValueError:
+        pytest.skip('no random box fits this frame (the reference raises as well)')
+    np.random.seed(seed)
+    t = OAMix(**cfg)
+    vp = t._sample_head(h, w, gt)
+    t._sample_tail(vp, gt, plan['scores'])
+    out, = run(hostsim, t, [(vp, gt, 0)], [img])
+    d = np.abs(out.astype(int) - ref.astype(int))
+    assert d.max() <= 3 and (d != 0).mean() <= 3e-3 and (d > 1).mean() <= 3e-4, (int(d.max()), float((d != 0).mean()))
+
+
 class _FusedOut(ctypes.Structure):   # oadg_fused_out_t
     _fields_ = [('mean', ctypes.c_float * 3), ('std', ctypes.c_float * 3), ('to_rgb', ctypes.c_int32),
                 ('size_divisor', ctypes.c_int32), ('view_f32', ctypes.c_void_p), ('src_f32', ctypes.c_void_p)]
