@@ -352,8 +352,9 @@ def product_arm(args):
 
     log('warm-up done')
     # ---- timed region (device-resident inputs)
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks = ClockSampler(local) if rank == 0 else None   # rank 0 reports the line; one sampler, not one per rank
+    if clocks is not None:
+        clocks.start()
     np.random.seed(1000 + rank)
     loss_fn.stats['launches'] = 0
     if gather:
@@ -367,7 +368,7 @@ def product_arm(args):
     barrier()
     launches += mix.pipe_launches
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks is not None else None
     launches += loss_fn.stats['launches'] + (gbe.launches if gather else 0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
