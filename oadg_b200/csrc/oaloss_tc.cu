@@ -1,18 +1,18 @@
-// OA-Loss similarity on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), forward.
+// OA-Loss similarity on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
 //
 // Z = F F^T / T for the doubly-normalised RoI embeddings F [N, 256] fp32 (reference
 // contrastive_loss.py:157 `torch.matmul(logits_anchor, logits_contrast.T) / temper`), fused with
 // the per-row masked-InfoNCE statistics; the only N x N tensor written is the logits Z the backward reads back
 // (17 MB at N = 2088, L2-resident between the two kernels).
 //
-// Precision: the loss must agree with the fp32 reference to 1e-5 relative while logits are
-// divided by T = 0.06 (x16.7 error gain), so the contraction is 3xTF32:
-//   F = Fh + Fl  (Fh = rna-tf32(F), Fl = rna-tf32(F - Fh));  Z ~= Fh Fh^T + Fh Fl^T + Fl Fh^T
-// with fp32 accumulation in TMEM (dropped term Fl Fl^T <= 2^-22).
-//
-// Tiles of Z are 128 x 128 (UMMA M=128, N=128, K=8 per instruction); the forward kernel is persistent and
-// warp-specialised (TMA producer warp, MMA warp with two TMEM accumulators, four epilogue warps), see the comment
-// above sim_fwd_tc_kernel; the backward (sim_bwd_tc_kernel) builds its A operand from the stored logits.
+// Precision: the loss must agree with the fp32 reference to 1e-5 relative while logits are divided by T = 0.06
+// (x16.7 error gain), so every fp32 operand is split in two and three tensor-core products stand for one fp32 product
+// (the dropped low x low term is <= 2^-22):
+//   forward   2-term fp16 split  F = h + l / 2^11 (h = fp16(F), l = fp16((F - h) 2^11));  Z ~= h h^T + (h l^T + l h^T) / 2^11,
+//             main and cross terms in two TMEM accumulators (sim_fwd_f16_kernel: persistent, A-stationary)
+//   backward  3xTF32  F = Fh + Fl (rna-tf32);  dF = A F with A = G + G^T built from the stored logits (sim_bwd_tc_kernel)
+// Both accumulate in fp32 in TMEM; tiles are 128 rows tall (UMMA M = 128), warp-specialised (TMA producer warp, MMA
+// issuer warp, epilogue / transform warps); see the comments above the kernels.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
