@@ -468,6 +468,10 @@ def gathered_contrastive_loss(cont_feats, labels, temperature=0.07, loss_weight=
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError('gathered_contrastive_loss needs an initialised torch.distributed process group '
                            '(a world of one rank is fine: the result then equals the local loss)')
+    from .contrastive_loss import MIN_TEMPERATURE
+    if not temperature >= MIN_TEMPERATURE:
+        raise ValueError('gathered_contrastive_loss: temperature %r is below %g (the bound of the fixed-shift exponent '
+                         'of the tcgen05 forward)' % (temperature, MIN_TEMPERATURE))
     labels = labels.reshape(-1)
     n = cont_feats.shape[0]
     if labels.shape[0] > n or labels.shape[0] < 1:
