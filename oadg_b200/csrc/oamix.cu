@@ -349,7 +349,9 @@ __device__ OADG_HANDLER void profile_tile(const ChainArgs& A, ChainSmem& S, uint
     if (s < 0) { s = 0; t = 0.f; }
     if (s >= n_lo - 1) { s = n_lo - 1; t = 0.f; }
     int s1 = min(s + 1, n_lo - 1);
-    out[d] = p[s] == p[s1] ? p[s] : fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));   // a constant run stays constant
+    // OpenCV's float32 bilinear resize evaluates a + t * (b - a) with one fused multiply-add (checked bit for bit
+    // against cv2.resize on 1.1 M values, horizontal and vertical pass alike); a constant run stays constant
+    out[d] = ffma(t, fsub(p[s1], p[s]), p[s]);
   }
 }
 // union of the blurred gt masks of a view (np.max(mask_bboxes, axis=0), bbox_augmentation.py:260) as float32 and as

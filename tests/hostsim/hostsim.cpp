@@ -100,7 +100,7 @@ struct HostBackend {
       if (s < 0) { s = 0; t = 0.f; }
       if (s >= n_lo - 1) { s = n_lo - 1; t = 0.f; }
       int s1 = s + 1 < n_lo - 1 ? s + 1 : n_lo - 1;
-      out[d] = p[s] == p[s1] ? p[s] : fadd(fmul(p[s], fsub(1.f, t)), fmul(p[s1], t));   // a constant run stays constant
+      out[d] = ffma(t, fsub(p[s1], p[s]), p[s]);   // cv2.resize (float32, linear): a + t * (b - a), fused
     }
   }
   static void lut_item(const ChainArgs& A, int job) {
