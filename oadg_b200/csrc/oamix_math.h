@@ -49,11 +49,13 @@ OADG_HD float ffma(float a, float b, float c) {
 #endif
 }
 // Value of cv2.GaussianBlur on a window that lies entirely inside the box (all taps read 1.0), as OpenCV computes it
-// in float32 (verified against cv2 4.13 for 400 sigmas, scripts in DESIGN.md section 7): the row filter adds the taps in
-// order, the symmetric column filter starts at the centre tap and adds k[c+j] * (v + v) outward with fused
+// in float32 (checked against cv2 4.13 on 700 sigma pairs): the row filter adds the taps in order (kernels of 3 and
+// 5 taps take the symmetric form below instead), the symmetric column filter starts at the centre tap and adds k[c+j] * (v + v) outward with fused
 // multiply-adds.  The result is 1 - 2^-24, 1 or 1 + 2^-23 depending on the kernel, and where the mask saturates the
 // blend img*(1-m) + aug*m sits on an integer, so this last bit decides the truncation of EVERY pixel there.
+OADG_HD float cv_saturated_col(const float* k, int ks, float v);
 OADG_HD float cv_saturated_row(const float* k, int ks) {
+  if (ks <= 5) return cv_saturated_col(k, ks, 1.0f);   // OpenCV's small symmetric row filter: same order as its column filter
   float s = k[0];
   for (int j = 1; j < ks; ++j) s = fadd(s, k[j]);
   return s;

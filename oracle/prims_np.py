@@ -245,6 +245,59 @@ def _profile_1d(lo, hi, n_lo, n_hi, sigma, blur):
     return (p[s] * (np.float32(1) - t) + p[s1] * t).astype(np.float32)
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add on arrays: the product of two float32 is exact in float64."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def _reflect101(idx, n):
+    if n == 1:
+        return np.zeros_like(idx)
+    period = 2 * (n - 1)
+    idx = np.abs(idx) % period
+    return np.where(idx >= n, period - idx, idx)
+
+
+def _resize_linear_f32(a, n_hi, axis):
+    """One pass of cv2.resize(float32, INTER_LINEAR) along ``axis``: a + t * (b - a) with ONE fused multiply-add."""
+    a = np.moveaxis(a, axis, 0)
+    n_lo = a.shape[0]
+    d = np.arange(n_hi)
+    f = ((d + 0.5) * (n_lo / n_hi) - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    t = (f - s).astype(np.float32)
+    t = np.where(s < 0, np.float32(0), t)
+    s = np.where(s < 0, 0, s)
+    t = np.where(s >= n_lo - 1, np.float32(0), t)
+    s = np.where(s >= n_lo - 1, n_lo - 1, s)
+    s1 = np.minimum(s + 1, n_lo - 1)
+    tt = t.reshape((-1,) + (1,) * (a.ndim - 1))
+    out = _fma32(np.broadcast_to(tt, a[s].shape), (a[s1] - a[s]).astype(np.float32), a[s])
+    return np.moveaxis(out, 0, axis)
+
+
+def saturated_blur_value(sigma_x, sigma_y):
+    """cv2.GaussianBlur(ones, (0, 0), sigma_x, sigma_y) as OpenCV 4.13 computes it in float32 -- the value a blurred box
+    mask takes where its window is fully covered (1 - 2^-24, 1 or 1 + 2^-23): the row filter adds the taps in order
+    (kernels of 3 and 5 taps: the symmetric form), the symmetric column filter starts at the centre tap and adds
+    k[c + j] * (v + v) outward with fused multiply-adds.  BIT-EXACT against cv2 (tests/test_prims.py)."""
+    def col(k, v):
+        c = len(k) // 2
+        s = np.float32(k[c] * v)
+        v2 = np.float32(v + v)
+        for j in range(1, c + 1):
+            s = np.float32(np.float64(k[c + j]) * np.float64(v2) + np.float64(s))
+        return s
+    kx, ky = gaussian_kernel_f32(sigma_x), gaussian_kernel_f32(sigma_y)
+    if len(kx) <= 5:
+        rx = col(kx, np.float32(1))
+    else:
+        rx = np.float32(kx[0])
+        for v in kx[1:]:
+            rx = np.float32(rx + v)
+    return col(ky, rx)
+
+
 def mask_profiles(box, h, w, spatial_ratio=4, sigma_ratio=0.3):
     """(uy[h], ux[w]) with blurred_mask(box)[y,x,:] ~= uy[y]*ux[x]  (<=1e-6 abs)."""
     x1, y1, x2, y2 = [int(v) for v in np.array(np.asarray(box, np.float32) // spatial_ratio, dtype=np.int32)]

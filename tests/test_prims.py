@@ -82,3 +82,29 @@ def test_saliency_front_end_exact_and_score_spec():
             assert abs(S.saliency_score(crop) - P.saliency_score_emul(crop)) < 1e-3
     flat = np.full((20, 30, 3), 77, np.uint8)
     assert S.saliency_score(flat) == P.saliency_score_emul(flat) == 0.0
+
+
+def test_resize_linear_f32_restatement_is_bit_exact():
+    """cv2.resize(float32, INTER_LINEAR) = horizontal pass then vertical pass, each a + t * (b - a) with one fused
+    multiply-add (prims_np._resize_linear_f32): what the profile tile's up-sampling follows."""
+    rng = np.random.RandomState(2)
+    for _ in range(12):
+        n, m = int(rng.randint(5, 70)), int(rng.randint(5, 50))
+        a = rng.rand(m, n, 3).astype(np.float32)
+        if _ % 3 == 0:
+            a = (1.0 - a * 1e-5).astype(np.float32)              # near-saturated values
+        got = cv2.resize(a, (4 * n, 4 * m))
+        mine = P._resize_linear_f32(P._resize_linear_f32(a, 4 * n, axis=1), 4 * m, axis=0)
+        assert np.array_equal(got, mine)
+
+
+def test_saturated_blur_value_is_bit_exact():
+    """The value of a fully covered Gaussian window in OpenCV's float32 arithmetic (prims_np.saturated_blur_value), incl.
+    the 3- and 5-tap kernels that take another code path: what the kernels put where a blurred box mask saturates."""
+    rng = np.random.RandomState(3)
+    ones = np.ones((16, 16, 3), np.float32)
+    for i in range(160):
+        sx = float(rng.uniform(0.2, 0.75)) if i % 2 else float(rng.uniform(0.2, 40))
+        sy = float(rng.uniform(0.2, 0.75)) if i % 4 < 2 else float(rng.uniform(0.2, 40))
+        got = np.unique(cv2.GaussianBlur(ones, (0, 0), sigmaX=sx, sigmaY=sy))
+        assert len(got) == 1 and float(got[0]) == float(P.saturated_blur_value(sx, sy)), (sx, sy)
