@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .consistency_losses import CrossEntropyLossPlus, SmoothL1LossPlus
+from .consistency_losses import CrossEntropyLossPlus, L1LossPlus, SmoothL1LossPlus
 from .contrastive_loss import ContrastiveLossPlus
 
 
@@ -158,6 +158,60 @@ def random_proposals(img_shape, gt_bboxes, num_views, multilevel_boxes=None, oam
 
 
 # ---------------------------------------------------------------------------------------------------------------
+class TwoViewRPNLoss(nn.Module):
+    """The RPN losses of the OA-DG configs (..._oadg.py:19-26) in the layout of ``AnchorHead.loss`` /
+    ``loss_single`` (dense_heads/anchor_head.py:402-453,455-547): the objectness logits of every anchor of every image of
+    the integrated batch (view-major), ``CrossEntropyLossPlus(use_sigmoid=True)`` = binary cross entropy on the SAMPLED
+    anchors of the first view + ``lambda_weight`` (0.1) x the JSD between the two views' objectness over ALL anchors, and
+    ``L1LossPlus`` on the sampled positives of the first view; both averaged by the number of anchors sampled over all
+    images.  The reference evaluates the two losses level by level and adds the levels up; every term is a sum over
+    anchors divided by the same ``avg_factor``, so one call over all levels gives the same number."""
+
+    def __init__(self, loss_cls=None, loss_bbox=None):
+        super().__init__()
+        cfg = dict(use_sigmoid=True, loss_weight=1.0, num_views=2, additional_loss='jsdv1_3_2aug', lambda_weight=0.1,
+                   wandb_name='rpn_cls')
+        cfg.update({k: v for k, v in (loss_cls or {}).items() if k != 'type'})
+        self.loss_cls = CrossEntropyLossPlus(**cfg)
+        cfg = dict(loss_weight=1.0, num_views=2, additional_loss='None', lambda_weight=0.0, wandb_name='rpn_bbox')
+        cfg.update({k: v for k, v in (loss_bbox or {}).items() if k != 'type'})
+        self.loss_bbox = L1LossPlus(**cfg)
+
+    def forward(self, objectness, pred_deltas, anchor_labels, sampled, reg_targets):
+        """objectness [B * A, 1], pred_deltas [B * A, 4] (image-major, B = batch_size * num_views, view-major images);
+        anchor_labels [B * A] in torchvision's convention (1 foreground, 0 background, -1 neither); sampled [B * A] bool
+        (the anchors the sampler kept); reg_targets [B * A, 4]."""
+        n_sampled = max(float(sampled.sum()), 1.0)
+        # mmdet's RPN labels: class 0 = object, 1 (= num_classes) = background
+        labels = torch.where(anchor_labels > 0, torch.zeros_like(anchor_labels), torch.ones_like(anchor_labels))
+        weights = sampled.to(objectness.dtype)
+        loss_cls = self.loss_cls(objectness, labels, weights, avg_factor=n_sampled)
+        pos = (sampled & (anchor_labels > 0)).to(pred_deltas.dtype).view(-1, 1).expand(-1, 4)
+        loss_bbox = self.loss_bbox(pred_deltas, reg_targets, pos, avg_factor=n_sampled)
+        return dict(loss_rpn_cls=loss_cls, loss_rpn_bbox=loss_bbox)
+
+
+def rpn_forward_oadg(rpn, images, features, targets, rpn_loss):
+    """torchvision's ``RegionProposalNetwork.forward`` with the OA-DG losses in place of its own: same head, anchors,
+    target assignment (IoU 0.7 / 0.3), sampler (256 per image, half positive) and proposal filtering."""
+    from torchvision.models.detection.rpn import concat_box_prediction_layers
+    feats = list(features.values())
+    objectness, deltas = rpn.head(feats)
+    anchors = rpn.anchor_generator(images, feats)
+    num_images = len(anchors)
+    per_level = [o[0].numel() for o in objectness]
+    obj_flat, deltas_flat = concat_box_prediction_layers(objectness, deltas)
+    proposals = rpn.box_coder.decode(deltas_flat.detach(), anchors).view(num_images, -1, 4)
+    boxes, _ = rpn.filter_proposals(proposals, obj_flat.detach(), images.image_sizes, per_level)
+    labels, matched = rpn.assign_targets_to_anchors(anchors, targets)
+    reg_targets = rpn.box_coder.encode(matched, anchors)
+    pos_masks, neg_masks = rpn.fg_bg_sampler(labels)
+    sampled = torch.cat([(p | n).bool() for p, n in zip(pos_masks, neg_masks)])
+    losses = rpn_loss(obj_flat, deltas_flat, torch.cat(labels).long(), sampled, torch.cat(reg_targets))
+    return boxes, losses
+
+
+# ---------------------------------------------------------------------------------------------------------------
 class Shared2FCContrastiveHead(nn.Module):
     """contrastive_head.py:141-366 with the OA-DG config values (..._oadg.py:17-44): roi features [n, 256, 7, 7] ->
     two shared FCs (1024) -> ``fc_cls`` (num_classes + 1), ``fc_reg`` (4 * num_classes), ``fc_cont``."""
@@ -285,6 +339,7 @@ class TwoViewFasterRCNN(nn.Module):
         self.rpn = RegionProposalNetwork(anchors, RPNHead(self.backbone.out_channels, 3), 0.7, 0.3, 256, 0.5,
                                          dict(training=rpn_pre_nms, testing=1000), dict(training=rpn_post_nms, testing=1000), 0.7)
         self.roi_head = TwoViewRoIHead(num_classes=num_classes, loss_cont=loss_cont)
+        self.rpn_loss = TwoViewRPNLoss()
         self.random_proposal_cfg = random_proposal_cfg
 
     def forward_train(self, data, generator=None):
@@ -295,7 +350,7 @@ class TwoViewFasterRCNN(nn.Module):
         shapes = [tuple(img.shape[-2:])] * img.shape[0]
         feats = self.backbone(img)
         targets = [dict(boxes=b, labels=l) for b, l in zip(data['gt_bboxes'], data['gt_labels'])]
-        proposals, rpn_losses = self.rpn(ImageList(img, shapes), feats, targets)
+        proposals, rpn_losses = rpn_forward_oadg(self.rpn, ImageList(img, shapes), feats, targets, self.rpn_loss)
         rp = None
         if self.random_proposal_cfg is not None:
             rp = random_proposals(img.shape[-2:], data['gt_bboxes'], nv, data.get('multilevel_boxes'),

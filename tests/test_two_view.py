@@ -111,6 +111,24 @@ for seed in range(6):
         mine = getattr(CL, name)(**kw)(pred, tgt, w4, avg_factor=11.0)
         ref = R[name](**kw)(pred, tgt, w4, avg_factor=11.0)
         assert torch.allclose(mine, ref, rtol=1e-12, atol=0), (seed, name)
+from oadg_b200.two_view import TwoViewRPNLoss
+g = torch.Generator().manual_seed(7)
+n = 4 * 600                                              # 2 images x 2 views x 600 anchors
+obj = torch.randn(n, 1, generator=g, dtype=torch.float64) * 3
+dl = torch.randn(n, 4, generator=g, dtype=torch.float64)
+tv = torch.randint(-1, 2, (n,), generator=g)             # torchvision labels: 1 fg, 0 bg, -1 neither
+sampled = (torch.rand(n, generator=g) < 0.2) & (tv >= 0)
+tgt = torch.randn(n, 4, generator=g, dtype=torch.float64)
+mine = TwoViewRPNLoss()(obj, dl, tv, sampled, tgt)
+ns = float(sampled.sum())
+mm = torch.where(tv > 0, torch.zeros_like(tv), torch.ones_like(tv))
+ref_cls = R['CrossEntropyLossPlus'](use_sigmoid=True, loss_weight=1.0, num_views=2, additional_loss='jsdv1_3_2aug',
+                                    lambda_weight=0.1, wandb_name='rpn_cls')(obj, mm, sampled.double(), avg_factor=ns)
+posw = (sampled & (tv > 0)).double().view(-1, 1).expand(-1, 4)
+ref_box = R['L1LossPlus'](loss_weight=1.0, num_views=2, additional_loss='None', lambda_weight=0.0,
+                          wandb_name='rpn_bbox')(dl, tgt, posw, avg_factor=ns)
+assert torch.allclose(mine['loss_rpn_cls'], ref_cls, rtol=1e-12, atol=0)
+assert torch.allclose(mine['loss_rpn_bbox'], ref_box, rtol=1e-12, atol=0)
 print("LIVE-OK")
 '''
     root = os.path.dirname(HERE)
@@ -268,3 +286,48 @@ def test_two_view_roi_head_row_order_on_cpu():
     assert torch.equal(head.last_rois[:2 * per, 1:], head.last_rois[2 * per:, 1:])
     assert torch.equal(seen['labels'][:2 * per], seen['labels'][2 * per:])
     assert set(out) == {'loss_cls', 'loss_bbox', 'loss_cont'}
+
+
+def test_rpn_losses_take_the_first_view_and_the_jsd_of_all_anchors():
+    """TwoViewRPNLoss against the formula written out: BCE on the sampled anchors of view 1 and L1 on its sampled
+    positives, both over the number of anchors sampled in ALL views, plus 0.1 x the JSD (sigmoid, 1 - sigmoid) between
+    the views over every anchor, over the same count."""
+    g = torch.Generator().manual_seed(3)
+    n = 2 * 500
+    obj = torch.randn(n, 1, generator=g, dtype=torch.float64) * 2
+    dl, tgt = torch.randn(n, 4, generator=g, dtype=torch.float64), torch.randn(n, 4, generator=g, dtype=torch.float64)
+    tv = torch.randint(-1, 2, (n,), generator=g)
+    sampled = (torch.rand(n, generator=g) < 0.3) & (tv >= 0)
+    out = TV.TwoViewRPNLoss()(obj, dl, tv, sampled, tgt)
+    ns = float(sampled.sum())
+    h = n // 2
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(obj[:h, 0], (tv[:h] > 0).double(), reduction='none')
+    want_cls = (bce * sampled[:h]).sum() / ns + 0.1 * CL.jsd_two_views_torch(obj) / ns
+    pos = (sampled & (tv > 0))[:h]
+    want_box = (torch.abs(dl[:h] - tgt[:h]) * pos.view(-1, 1)).sum() / ns
+    # (the reference feeds float32 labels to binary_cross_entropy_with_logits, so its float64 result carries ~1e-8)
+    assert out['loss_rpn_cls'].item() == pytest.approx(want_cls.item(), rel=1e-7)
+    assert out['loss_rpn_bbox'].item() == pytest.approx(want_box.item(), rel=1e-12)
+
+
+def test_rpn_forward_oadg_on_a_small_torchvision_rpn():
+    """torchvision's head / anchors / assignment / sampler / proposal filter with the OA-DG losses on top: proposals
+    for every image of the integrated batch, finite losses, gradients reach the RPN head from view 1's sampled anchors
+    and (through the JSD term) from both views' logits."""
+    from torchvision.models.detection.anchor_utils import AnchorGenerator
+    from torchvision.models.detection.image_list import ImageList
+    from torchvision.models.detection.rpn import RegionProposalNetwork, RPNHead
+    torch.manual_seed(0)
+    anchors = AnchorGenerator(sizes=((32,), (64,)), aspect_ratios=((0.5, 1.0, 2.0),) * 2)
+    rpn = RegionProposalNetwork(anchors, RPNHead(16, 3), 0.7, 0.3, 64, 0.5, dict(training=200, testing=100),
+                                dict(training=50, testing=50), 0.7).train()
+    feats = {'0': torch.randn(4, 16, 16, 32), '1': torch.randn(4, 16, 8, 16)}
+    images = ImageList(torch.randn(4, 3, 128, 256), [(128, 256)] * 4)
+    gt = [torch.tensor([[10., 10., 100., 100.]]), torch.tensor([[30., 20., 200., 120.], [5., 60., 60., 120.]])] * 2
+    targets = [dict(boxes=b, labels=torch.ones(len(b), dtype=torch.long)) for b in gt]
+    boxes, losses = TV.rpn_forward_oadg(rpn, images, feats, targets, TV.TwoViewRPNLoss())
+    assert len(boxes) == 4 and all(b.shape[1] == 4 and 0 < b.shape[0] <= 50 for b in boxes)
+    total = losses['loss_rpn_cls'] + losses['loss_rpn_bbox']
+    assert torch.isfinite(total)
+    total.backward()
+    assert rpn.head.cls_logits.weight.grad.abs().sum() > 0 and rpn.head.bbox_pred.weight.grad.abs().sum() > 0
