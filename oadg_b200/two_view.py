@@ -14,6 +14,8 @@ restates the OA-DG-specific glue of the reference:
                                 ``fc_cont`` = Linear(1024, 256) + ReLU + Linear(256, 256); ``loss`` gates the contrastive
                                 term on the number of foreground RoIs (:125-129) but -- unlike the reference -- always emits
                                 ``loss_cont`` (a zero attached to the graph) so that DDP sees the same parameters every step
+* ``TwoViewRPNLoss`` / ``rpn_forward_oadg``  dense_heads/anchor_head.py:402-547 with the configs' RPN losses (first-view
+                                BCE + 0.1 x JSD over all anchors, first-view L1) on torchvision's RPN
 * ``TwoViewRoIHead`` / ``TwoViewFasterRCNN``  the step: RoI row order [v1 img0, v1 img1, v2 img0, v2 img1, rp ...], 512
                                 rows per image, positives first (core/bbox/samplers/sampling_result.py:53-55)
 """
