@@ -299,11 +299,12 @@ class TwoViewRoIHead(nn.Module):
     """ContrastiveRoIHead (roi_heads/contrastive_roi_head.py) on torchvision's MultiScaleRoIAlign."""
 
     def __init__(self, num_classes=8, featmap_names=('0', '1', '2', '3'), roi_size=7, num=512, pos_fraction=0.25,
-                 loss_cont=None):
+                 loss_cont=None, in_channels=256):
         super().__init__()
         from torchvision.ops import MultiScaleRoIAlign
         self.roi_align = MultiScaleRoIAlign(list(featmap_names), roi_size, 0)
-        self.bbox_head = Shared2FCContrastiveHead(num_classes=num_classes, roi_feat_size=roi_size, loss_cont=loss_cont)
+        self.bbox_head = Shared2FCContrastiveHead(in_channels=in_channels, num_classes=num_classes, roi_feat_size=roi_size,
+                                                  loss_cont=loss_cont)
         self.num, self.pos_fraction = num, pos_fraction
         self.last_rois = None
 
@@ -325,22 +326,48 @@ class TwoViewRoIHead(nn.Module):
         return self.bbox_head.loss(cls_score, bbox_pred, cont_feats, *targets)
 
 
+class _DC5Backbone(nn.Module):
+    """ResNet with a dilated last stage and no neck: one stride-16 map of 2048 channels (the reference's
+    ``configs/_base_/models/faster_rcnn_r50_caffe_dc5.py``: strides (1, 2, 2, 1), dilations (1, 1, 1, 2), out_indices (3,))."""
+
+    def __init__(self, name):
+        super().__init__()
+        import torchvision
+        net = getattr(torchvision.models, name)(weights=None, replace_stride_with_dilation=[False, False, True])
+        self.body = nn.Sequential(net.conv1, net.bn1, net.relu, net.maxpool, net.layer1, net.layer2, net.layer3, net.layer4)
+        self.out_channels = 2048
+
+    def forward(self, x):
+        from collections import OrderedDict
+        return OrderedDict([('0', self.body(x))])
+
+
 class TwoViewFasterRCNN(nn.Module):
-    """Faster R-CNN (torchvision backbone + FPN + RPN, stock torch) with the OA-DG two-view step around it
+    """Faster R-CNN (torchvision backbone + FPN or dilated-C5, RPN: stock torch) with the OA-DG two-view step around it
     (detectors/two_stage.py forward_train): integrate the views, RPN on all of them, RoIs sampled on view 1 and
-    replicated, random proposals, contrastive head."""
+    replicated, random proposals, contrastive head.  ``arch='fpn'``: BASELINE configs 3 / 4 (R50-FPN);
+    ``arch='dc5'``: config 5 (R101-DC5, ``configs/OA-DG/dwd/faster_rcnn_r101_dc5_1x_dwd_oadg.py``)."""
 
     def __init__(self, num_classes=8, backbone='resnet50', trainable_layers=5, rpn_pre_nms=2000, rpn_post_nms=1000,
-                 random_proposal_cfg=None, loss_cont=None):
+                 random_proposal_cfg=None, loss_cont=None, arch='fpn'):
         super().__init__()
         from torchvision.models.detection.anchor_utils import AnchorGenerator
-        from torchvision.models.detection.backbone_utils import resnet_fpn_backbone
         from torchvision.models.detection.rpn import RegionProposalNetwork, RPNHead
-        self.backbone = resnet_fpn_backbone(backbone_name=backbone, weights=None, trainable_layers=trainable_layers)
-        anchors = AnchorGenerator(sizes=((32,), (64,), (128,), (256,), (512,)), aspect_ratios=((0.5, 1.0, 2.0),) * 5)
-        self.rpn = RegionProposalNetwork(anchors, RPNHead(self.backbone.out_channels, 3), 0.7, 0.3, 256, 0.5,
+        if arch == 'fpn':
+            from torchvision.models.detection.backbone_utils import resnet_fpn_backbone
+            self.backbone = resnet_fpn_backbone(backbone_name=backbone, weights=None, trainable_layers=trainable_layers)
+            anchors = AnchorGenerator(sizes=((32,), (64,), (128,), (256,), (512,)), aspect_ratios=((0.5, 1.0, 2.0),) * 5)
+            names, per_loc = ('0', '1', '2', '3'), 3
+        elif arch == 'dc5':
+            self.backbone = _DC5Backbone(backbone)
+            anchors = AnchorGenerator(sizes=((32, 64, 128, 256, 512),), aspect_ratios=((0.5, 1.0, 2.0),))
+            names, per_loc = ('0',), 15
+        else:
+            raise ValueError("arch: 'fpn' or 'dc5'")
+        self.rpn = RegionProposalNetwork(anchors, RPNHead(self.backbone.out_channels, per_loc), 0.7, 0.3, 256, 0.5,
                                          dict(training=rpn_pre_nms, testing=1000), dict(training=rpn_post_nms, testing=1000), 0.7)
-        self.roi_head = TwoViewRoIHead(num_classes=num_classes, loss_cont=loss_cont)
+        self.roi_head = TwoViewRoIHead(num_classes=num_classes, featmap_names=names, loss_cont=loss_cont,
+                                       in_channels=self.backbone.out_channels)
         self.rpn_loss = TwoViewRPNLoss()
         self.random_proposal_cfg = random_proposal_cfg
 

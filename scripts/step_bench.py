@@ -1,7 +1,8 @@
 """BASELINE config 3: one OA-DG training step of a random-init Faster R-CNN R50-FPN (8 classes) on a synthetic
 1024x2048 batch of 2 frames, 1 x B200 (GPU box).
 
-    python scripts/step_bench.py [--steps 10] [--backbone resnet50]
+    python scripts/step_bench.py [--steps 10] [--backbone resnet50]                                   # config 3
+    python scripts/step_bench.py --arch dc5 --backbone resnet101 --classes 7 --hw 600 1067            # config 5
 
 The detector (backbone, FPN, RPN, RoIAlign) is stock torch / torchvision, as BASELINE.json's north_star prescribes; the
 OA-DG parts are this repo's: OA-Mix produces view 2 on the GPU and its mix kernel writes the Normalize + Pad + CHW
@@ -30,18 +31,20 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--backbone', default='resnet50')
     ap.add_argument('--classes', type=int, default=8)
+    ap.add_argument('--arch', default='fpn', choices=['fpn', 'dc5'])
+    ap.add_argument('--hw', type=int, nargs=2, default=[bench.H, bench.W], help='frame height and width')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     torch.manual_seed(0)
     norm = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True, size_divisor=32)
     mix = OAMix(fused_output=norm, **bench.OAMIX_CFG)
-    frames = [bench.make_image(s) for s in range(8)]
+    frames = [bench.make_image(s, args.hw[0], args.hw[1]) for s in range(8)]
     imgs = [torch.from_numpy(f).to(dev) for f, _ in frames]
     gts = [g for _, g in frames]
     rng = np.random.RandomState(0)
     labels = [torch.from_numpy(rng.randint(0, args.classes, len(g))).to(dev) for g in gts]
     gts_dev = [torch.from_numpy(g).to(dev) for g in gts]
-    model = TwoViewFasterRCNN(num_classes=args.classes, backbone=args.backbone,
+    model = TwoViewFasterRCNN(num_classes=args.classes, backbone=args.backbone, arch=args.arch,
                               random_proposal_cfg=dict(num_bboxes=10, scales=(0.01, 0.3), ratios=(0.3, 1 / 0.3),
                                                        iou_max=0.7, iou_min=0.0),
                               loss_cont=dict(loss_weight=0.01, num_views=2, temperature=0.06)).to(dev).train()
@@ -97,9 +100,9 @@ def main():
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / args.steps
     print(json.dumps({
-        'workload': 'OA-DG two-view training step, torchvision %s-FPN Faster R-CNN (random init, %d classes), 2 frames '
-                    '1024x2048 -> 4 images 3x1024x2048 f32 per step, 512 RoIs/img + random proposals, SGD' %
-                    (args.backbone, args.classes),
+        'workload': 'OA-DG two-view training step, torchvision %s-%s Faster R-CNN (random init, %d classes), 2 frames '
+                    '%dx%d -> 4 padded float32 images per step, 512 RoIs/img + random proposals, SGD' %
+                    (args.backbone, args.arch.upper(), args.classes, args.hw[0], args.hw[1]),
         'steps': args.steps, 'ms_per_step': ms, 'images_per_s': 2 * 1e3 / ms,
         'phase_ms_per_step': {k: v / args.steps for k, v in phases.items()},
         'oamix_share_of_step': phases['oamix'] / args.steps / ms,

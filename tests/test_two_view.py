@@ -331,3 +331,17 @@ def test_rpn_forward_oadg_on_a_small_torchvision_rpn():
     assert torch.isfinite(total)
     total.backward()
     assert rpn.head.cls_logits.weight.grad.abs().sum() > 0 and rpn.head.bbox_pred.weight.grad.abs().sum() > 0
+
+
+def test_dc5_architecture_of_config_5():
+    """R-DC5 (configs/_base_/models/faster_rcnn_r50_caffe_dc5.py): one stride-16 map of 2048 channels, 15 anchors per
+    location, a 2048-channel RoI head with the 7 DWD classes."""
+    torch.manual_seed(0)
+    m = TV.TwoViewFasterRCNN(num_classes=7, backbone='resnet50', arch='dc5')
+    feats = m.backbone(torch.randn(1, 3, 96, 160))
+    assert list(feats) == ['0'] and feats['0'].shape == (1, 2048, 6, 10)
+    assert m.rpn.head.cls_logits.out_channels == 15 and m.rpn.head.bbox_pred.out_channels == 60
+    head = m.roi_head.bbox_head
+    assert head.shared_fcs[0].in_features == 2048 * 7 * 7 and head.fc_cls.out_features == 8 and head.fc_reg.out_features == 28
+    with pytest.raises(ValueError):
+        TV.TwoViewFasterRCNN(arch='c4')
