@@ -159,6 +159,22 @@ def random_proposals(img_shape, gt_bboxes, num_views, multilevel_boxes=None, oam
     return out
 
 
+def _world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def fixed_count(boxes, k):
+    """Exactly k boxes: the first k, or the list padded by repeating its last box (an all-zero box when it is empty).
+    The gathered loss needs the same number of rows on every rank, and the number of random proposals that survive
+    the IoU filters varies."""
+    n = boxes.shape[0]
+    if n >= k:
+        return boxes[:k]
+    pad = boxes[-1:].expand(k - n, -1) if n else boxes.new_zeros((k, 4))[:k - n]
+    return torch.cat([boxes, pad], dim=0)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 class TwoViewRPNLoss(nn.Module):
     """The RPN losses of the OA-DG configs (..._oadg.py:19-26) in the layout of ``AnchorHead.loss`` /
@@ -219,9 +235,12 @@ class Shared2FCContrastiveHead(nn.Module):
     two shared FCs (1024) -> ``fc_cls`` (num_classes + 1), ``fc_reg`` (4 * num_classes), ``fc_cont``."""
 
     def __init__(self, in_channels=256, roi_feat_size=7, fc_out_channels=1024, num_classes=8, out_dim_cont=256,
-                 loss_cont=None, loss_cls=None, loss_bbox=None, target_stds=(0.1, 0.1, 0.2, 0.2)):
+                 loss_cont=None, loss_cls=None, loss_bbox=None, target_stds=(0.1, 0.1, 0.2, 0.2), gather=False):
         super().__init__()
         self.num_classes = num_classes
+        # gather=True (BASELINE config 4): under an initialised process group of several ranks the contrast set is the
+        # embeddings of ALL ranks (oadg_b200.distributed); every rank must then bring the same number of rows
+        self.gather = gather
         d = in_channels * roi_feat_size * roi_feat_size
         self.shared_fcs = nn.ModuleList([nn.Linear(d, fc_out_channels), nn.Linear(fc_out_channels, fc_out_channels)])
         self.fc_cls = nn.Linear(fc_out_channels, num_classes + 1)
@@ -286,6 +305,15 @@ class Shared2FCContrastiveHead(nn.Module):
         else:
             losses['loss_bbox'] = bbox_pred[pos].sum()
         lab = labels.contiguous().view(-1, 1)
+        if self.gather and cont_feats is not None and _world_size() > 1:
+            # the foreground gate is the kernel's, on the labels of all ranks: a per-rank gate could leave a rank out
+            # of the exchange the others wait for
+            from .distributed import gathered_contrastive_loss
+            lc = self.loss_cont
+            losses['loss_cont'] = gathered_contrastive_loss(cont_feats, lab, temperature=lc.temperature,
+                                                            loss_weight=lc.loss_weight, min_samples=lc.min_samples,
+                                                            normalized_input=lc.normalized_input)
+            return losses
         n_fg = int((lab != lab.max()).sum())              # the reference's host sync (:125-126)
         if cont_feats is not None and cont_feats.numel() > 0 and n_fg > self.loss_cont.min_samples:
             losses['loss_cont'] = self.loss_cont(cont_feats, lab)
@@ -299,12 +327,13 @@ class TwoViewRoIHead(nn.Module):
     """ContrastiveRoIHead (roi_heads/contrastive_roi_head.py) on torchvision's MultiScaleRoIAlign."""
 
     def __init__(self, num_classes=8, featmap_names=('0', '1', '2', '3'), roi_size=7, num=512, pos_fraction=0.25,
-                 loss_cont=None, in_channels=256):
+                 loss_cont=None, in_channels=256, gather=False, rp_per_image=None):
         super().__init__()
         from torchvision.ops import MultiScaleRoIAlign
         self.roi_align = MultiScaleRoIAlign(list(featmap_names), roi_size, 0)
         self.bbox_head = Shared2FCContrastiveHead(in_channels=in_channels, num_classes=num_classes, roi_feat_size=roi_size,
-                                                  loss_cont=loss_cont)
+                                                  loss_cont=loss_cont, gather=gather)
+        self.rp_per_image = rp_per_image if rp_per_image is not None else (10 if gather else None)
         self.num, self.pos_fraction = num, pos_fraction
         self.last_rois = None
 
@@ -320,6 +349,8 @@ class TwoViewRoIHead(nn.Module):
         self.last_rois = bbox2roi(boxes)
         cls_score, bbox_pred, cont_feats = self.bbox_head(self._extract(feats, boxes, image_shapes))
         if random_proposal_list is not None:              # contrastive_roi_head.py:146-149: embeddings only
+            if self.rp_per_image is not None:
+                random_proposal_list = [fixed_count(b, self.rp_per_image) for b in random_proposal_list]
             _, _, cont_rp = self.bbox_head(self._extract(feats, list(random_proposal_list), image_shapes))
             cont_feats = torch.cat([cont_feats, cont_rp], dim=0)
         targets = self.bbox_head.get_targets(sampling)
@@ -349,7 +380,7 @@ class TwoViewFasterRCNN(nn.Module):
     ``arch='dc5'``: config 5 (R101-DC5, ``configs/OA-DG/dwd/faster_rcnn_r101_dc5_1x_dwd_oadg.py``)."""
 
     def __init__(self, num_classes=8, backbone='resnet50', trainable_layers=5, rpn_pre_nms=2000, rpn_post_nms=1000,
-                 random_proposal_cfg=None, loss_cont=None, arch='fpn'):
+                 random_proposal_cfg=None, loss_cont=None, arch='fpn', gather=False):
         super().__init__()
         from torchvision.models.detection.anchor_utils import AnchorGenerator
         from torchvision.models.detection.rpn import RegionProposalNetwork, RPNHead
@@ -367,9 +398,13 @@ class TwoViewFasterRCNN(nn.Module):
         self.rpn = RegionProposalNetwork(anchors, RPNHead(self.backbone.out_channels, per_loc), 0.7, 0.3, 256, 0.5,
                                          dict(training=rpn_pre_nms, testing=1000), dict(training=rpn_post_nms, testing=1000), 0.7)
         self.roi_head = TwoViewRoIHead(num_classes=num_classes, featmap_names=names, loss_cont=loss_cont,
-                                       in_channels=self.backbone.out_channels)
+                                       in_channels=self.backbone.out_channels, gather=gather)
         self.rpn_loss = TwoViewRPNLoss()
         self.random_proposal_cfg = random_proposal_cfg
+
+    def forward(self, data, generator=None):
+        """``forward_train`` under the name DistributedDataParallel wraps."""
+        return self.forward_train(data, generator=generator)
 
     def forward_train(self, data, generator=None):
         from torchvision.models.detection.image_list import ImageList
