@@ -345,3 +345,16 @@ def test_dc5_architecture_of_config_5():
     assert head.shared_fcs[0].in_features == 2048 * 7 * 7 and head.fc_cls.out_features == 8 and head.fc_reg.out_features == 28
     with pytest.raises(ValueError):
         TV.TwoViewFasterRCNN(arch='c4')
+
+
+def test_fixed_count_pads_and_truncates_random_proposals():
+    """Under the gathered loss every rank must bring the same number of rows: each image's random proposals are cut or
+    padded (by repeating the last box) to a fixed count."""
+    b = torch.arange(12.).view(3, 4)
+    assert torch.equal(TV.fixed_count(b, 2), b[:2])
+    out = TV.fixed_count(b, 5)
+    assert out.shape == (5, 4) and torch.equal(out[:3], b) and torch.equal(out[3:], b[-1:].expand(2, -1))
+    assert TV.fixed_count(b[:0], 3).shape == (3, 4)
+    head = TV.TwoViewRoIHead(num_classes=8, featmap_names=('0',), gather=True)
+    assert head.rp_per_image == 10 and head.bbox_head.gather
+    assert TV.TwoViewRoIHead(num_classes=8, featmap_names=('0',)).rp_per_image is None
