@@ -145,6 +145,24 @@ def test_mmdet_shim_steps_aside_for_a_real_mmdet(tmp_path):
     assert out.stdout.split() == ['2.20.0+oadg_b200', 'OAMix'], out.stdout + out.stderr
 
 
+def test_standalone_plugin_config_builds_everywhere():
+    """configs/OA-DG/standalone/oadg_plugins.py has no `_base_`: the plugin surface is exercised on boxes that have
+    neither the reference tree nor mmcv (the reference's own configs are loaded by the dev-container tests above)."""
+    from oadg_b200 import (Config, PIPELINES, build_from_cfg, build_loss, OAMix, ContrastiveLossPlus,
+                           CrossEntropyLossPlus, SmoothL1LossPlus, L1LossPlus)
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs/OA-DG/standalone/oadg_plugins.py'))
+    t = build_from_cfg(cfg.oamix_config, PIPELINES)
+    assert isinstance(t, OAMix) and t.num_views == 2 and t.keep_orig and t.fused_output is None
+    f = build_from_cfg(cfg.oamix_fused_config, PIPELINES)
+    assert f.fused_output['size_divisor'] == 32 and f.fused_output['to_rgb'] is True
+    built = {k: build_loss(v) for k, v in cfg.losses.items()}
+    assert [type(built[k]) for k in ('rpn_cls', 'rpn_bbox', 'roi_cls', 'roi_bbox', 'cont')] == \
+        [CrossEntropyLossPlus, L1LossPlus, CrossEntropyLossPlus, SmoothL1LossPlus, ContrastiveLossPlus]
+    assert built['rpn_cls'].use_sigmoid and built['rpn_cls'].lambda_weight == 0.1 and built['roi_cls'].lambda_weight == 10
+    assert built['cont'].temperature == 0.06 and built['cont'].loss_weight == 0.01
+    assert cfg.train_pipeline[0]['type'] == 'OAMix' and cfg.random_proposal_cfg['num_bboxes'] == 10
+
+
 def test_register_into_a_foreign_mmdet_registry_replaces_the_stock_classes():
     """oadg_b200.plugins against a stand-in for mmcv.utils.Registry (same register_module(name, force, module)
     contract, reference mmdet/datasets/builder.py:28, mmdet/models/builder.py:13)."""
